@@ -1,0 +1,416 @@
+// Row engine: the one HBM-bound kernel behind Replay gather / append / update
+// and the Driver's stage-obs / mask-actions (include/embodied_b200.h).
+//
+// A launch moves `nrows` rows of up to EMB_MAX_KEYS keys.  Keys are split by
+// row size:
+//   big   (row_bytes >= 256, 16-byte aligned, plain copy or u8->f32 normalise):
+//         work unit = (row, key, 16 KiB slice) handled by one 256-thread CTA
+//         iteration, four 16-byte loads in flight per thread before any store;
+//   small (everything else: flags, rewards, stepid, consec, actions):
+//         work unit = 1024 consecutive (row, vector) elements of one key.
+// The grid is persistent (SMs x 8 CTAs) and strides over the unit list, so a
+// default dreamerv3 batch (16x65 rows x {image 12 KiB, deter 32 KiB, stoch 8 KiB}
+// + seven small keys) is ~4.2k big units + ~10 small units in ONE launch.
+//
+// Everything here is byte/integer exact; the only arithmetic is the typed
+// multiply of Driver._mask and float(u8)/255-0.5 (IEEE fp32 divide, no FMA).
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/embodied_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr uint32_t kBigSlice = 16384;        // bytes per big unit
+constexpr uint32_t kSmallElems = 1024;       // vector elements per small unit
+constexpr uint32_t kBigMin = 256;
+
+struct DevKey {
+  const uint8_t* src;
+  uint8_t* dst;
+  uint8_t* dst2;
+  const uint8_t* aux;
+  uint64_t src_stride, dst_stride, dst2_stride, aux_stride;
+  uint32_t row_bytes;
+  uint32_t op;
+  uint32_t dtype;
+  int32_t fill;
+  uint32_t unit_begin;   // big: first slice index within a row; small: first unit
+  uint32_t vec;          // small: bytes per vector element; big: 16
+  uint32_t vecs_per_row; // small: row_bytes / vec
+  uint32_t pad;
+};
+
+struct Table {
+  uint32_t nbig, nsmall;
+  uint32_t big_units_per_row;
+  uint32_t small_units;
+  DevKey k[EMB_MAX_KEYS];   // big keys first, then small keys
+};
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+__device__ __forceinline__ float norm_u8(uint32_t b) {
+  // dreamerv3/rssm.py:230  x.astype(f32) / 255 - 0.5, IEEE round-to-nearest.
+  return __fsub_rn(__fdiv_rn((float)b, 255.0f), 0.5f);
+}
+
+__device__ __forceinline__ void store_norm16(float* out, const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float4 f;
+    f.x = norm_u8(w[i] & 0xff);
+    f.y = norm_u8((w[i] >> 8) & 0xff);
+    f.z = norm_u8((w[i] >> 16) & 0xff);
+    f.w = norm_u8(w[i] >> 24);
+    reinterpret_cast<float4*>(out)[i] = f;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void mask_mul(uint8_t* d, const uint8_t* s, bool keep) {
+  // driver.py:84-87  value * mask.astype(value.dtype)
+  T v = *reinterpret_cast<const T*>(s);
+  T m = keep ? T(1) : T(0);
+  *reinterpret_cast<T*>(d) = v * m;
+}
+
+__device__ __forceinline__ void mask_elem(uint32_t dtype, uint8_t* d,
+                                          const uint8_t* s, bool keep) {
+  switch (dtype) {
+    case EMB_U8: case EMB_I8: mask_mul<uint8_t>(d, s, keep); break;
+    case EMB_BOOL: *d = (*s && keep) ? 1 : 0; break;
+    case EMB_I16: case EMB_U16: mask_mul<uint16_t>(d, s, keep); break;
+    case EMB_I32: case EMB_U32: mask_mul<uint32_t>(d, s, keep); break;
+    case EMB_I64: case EMB_U64: mask_mul<unsigned long long>(d, s, keep); break;
+    case EMB_F32: {
+      float v = *reinterpret_cast<const float*>(s);
+      *reinterpret_cast<float*>(d) = __fmul_rn(v, keep ? 1.0f : 0.0f);
+    } break;
+    case EMB_F64: {
+      double v = *reinterpret_cast<const double*>(s);
+      *reinterpret_cast<double*>(d) = __dmul_rn(v, keep ? 1.0 : 0.0);
+    } break;
+    case EMB_F16: {
+      __half v = *reinterpret_cast<const __half*>(s);
+      *reinterpret_cast<__half*>(d) = __hmul(v, __float2half(keep ? 1.f : 0.f));
+    } break;
+    case EMB_BF16: {
+      __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(s);
+      *reinterpret_cast<__nv_bfloat16*>(d) =
+          __hmul(v, __float2bfloat16(keep ? 1.f : 0.f));
+    } break;
+    default: break;
+  }
+}
+
+__device__ __forceinline__ uint32_t dtype_size(uint32_t dtype) {
+  switch (dtype) {
+    case EMB_U8: case EMB_I8: case EMB_BOOL: return 1;
+    case EMB_I16: case EMB_U16: case EMB_F16: case EMB_BF16: return 2;
+    case EMB_I32: case EMB_U32: case EMB_F32: return 4;
+    default: return 8;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+rows_kernel(const __grid_constant__ Table tab,
+            const int64_t* __restrict__ src_rows,
+            const int64_t* __restrict__ dst_rows,
+            int64_t nrows, int32_t window) {
+  const uint64_t big_units = (uint64_t)nrows * tab.big_units_per_row;
+  const uint64_t total = big_units + tab.small_units;
+  for (uint64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    if (unit < big_units) {
+      // ---------------- big path: one 16 KiB slice of one row of one key
+      const int64_t r = (int64_t)(unit / tab.big_units_per_row);
+      const uint32_t j = (uint32_t)(unit % tab.big_units_per_row);
+      uint32_t ki = 0;
+      while (ki + 1 < tab.nbig && tab.k[ki + 1].unit_begin <= j) ++ki;
+      const DevKey& key = tab.k[ki];
+      const int64_t sr = src_rows ? src_rows[r] : r;
+      const int64_t dr = dst_rows ? dst_rows[r] : r;
+      if (sr < 0 || dr < 0) continue;
+      const uint32_t off = (j - key.unit_begin) * kBigSlice;
+      const uint32_t nvec = (min(key.row_bytes - off, kBigSlice)) >> 4;
+      const uint4* s = reinterpret_cast<const uint4*>(
+          key.src + (uint64_t)sr * key.src_stride + off);
+      uint4* d = key.dst ? reinterpret_cast<uint4*>(
+          key.dst + (uint64_t)dr * key.dst_stride + off) : nullptr;
+      uint8_t* d2 = key.dst2 ? key.dst2 + (uint64_t)r * key.dst2_stride : nullptr;
+      const bool norm = key.op == EMB_OP_NORM_U8_F32;
+      // 4 independent 16-byte loads per thread before the stores (64 B/thread,
+      // 16 KiB per CTA iteration in flight).
+      uint4 v[4];
+      const uint32_t t = threadIdx.x;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = t + u * kThreads;
+        if (i < nvec) v[u] = ld_stream(s + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = t + u * kThreads;
+        if (i < nvec) {
+          if (d) st_stream(d + i, v[u]);
+          if (d2) {
+            if (norm) {
+              store_norm16(reinterpret_cast<float*>(d2) + (off + i * 16), v[u]);
+            } else {
+              st_stream(reinterpret_cast<uint4*>(d2 + off) + i, v[u]);
+            }
+          }
+        }
+      }
+    } else {
+      // ---------------- small path: 1024 (row, vector) elements of one key
+      const uint32_t su = (uint32_t)(unit - big_units);
+      uint32_t ki = tab.nbig;
+      const uint32_t kend = tab.nbig + tab.nsmall;
+      while (ki + 1 < kend && tab.k[ki + 1].unit_begin <= su) ++ki;
+      const DevKey& key = tab.k[ki];
+      const uint64_t base = (uint64_t)(su - key.unit_begin) * kSmallElems;
+      const uint64_t nelem = (uint64_t)nrows * key.vecs_per_row;
+#pragma unroll 1
+      for (uint32_t u = 0; u < kSmallElems / kThreads; ++u) {
+        const uint64_t e = base + threadIdx.x + u * kThreads;
+        if (e >= nelem) break;
+        const int64_t r = (int64_t)(e / key.vecs_per_row);
+        const uint32_t c = (uint32_t)(e % key.vecs_per_row) * key.vec;
+        const int64_t sr = src_rows ? src_rows[r] : r;
+        const int64_t dr = dst_rows ? dst_rows[r] : r;
+        if (sr < 0 || dr < 0) continue;
+        uint8_t* d = key.dst ? key.dst + (uint64_t)dr * key.dst_stride + c : nullptr;
+        uint8_t* d2 = key.dst2 ? key.dst2 + (uint64_t)r * key.dst2_stride + c : nullptr;
+        const uint8_t* s = key.src ? key.src + (uint64_t)sr * key.src_stride + c : nullptr;
+        uint8_t tmp[16];
+        switch (key.op) {
+          case EMB_OP_FILL32:
+            *reinterpret_cast<int32_t*>(tmp) = key.fill;
+            break;
+          case EMB_OP_MASK: {
+            const bool keep = key.aux[(uint64_t)r * key.aux_stride] == 0;
+            const uint32_t es = dtype_size(key.dtype);
+            for (uint32_t b = 0; b < key.vec; b += es)
+              mask_elem(key.dtype, tmp + b, s + b, keep);
+          } break;
+          case EMB_OP_NOT:
+            for (uint32_t b = 0; b < key.vec; ++b) tmp[b] = s[b] ? 0 : 1;
+            break;
+          default:
+            switch (key.vec) {
+              case 16: *reinterpret_cast<uint4*>(tmp) = *reinterpret_cast<const uint4*>(s); break;
+              case 8: *reinterpret_cast<uint2*>(tmp) = *reinterpret_cast<const uint2*>(s); break;
+              case 4: *reinterpret_cast<uint32_t*>(tmp) = *reinterpret_cast<const uint32_t*>(s); break;
+              case 2: *reinterpret_cast<uint16_t*>(tmp) = *reinterpret_cast<const uint16_t*>(s); break;
+              default: tmp[0] = *s; break;
+            }
+            if (c == 0 && window > 0) {
+              const int32_t tpos = (int32_t)(r % window);
+              if (key.op == EMB_OP_FIRST && tpos == 0) {
+                tmp[0] = 1;                                   // replay.py:285-286
+              } else if (key.op == EMB_OP_LAST && tpos + 1 < window) {
+                const int64_t nr = src_rows ? src_rows[r + 1] : r + 1;
+                if (nr >= 0 && key.aux[(uint64_t)nr * key.aux_stride])
+                  tmp[0] = 1;                                 // replay.py:288-291
+              }
+            }
+            break;
+        }
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          uint8_t* o = which ? d2 : d;
+          if (!o) continue;
+          switch (key.vec) {
+            case 16: *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(tmp); break;
+            case 8: *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(tmp); break;
+            case 4: *reinterpret_cast<uint32_t*>(o) = *reinterpret_cast<uint32_t*>(tmp); break;
+            case 2: *reinterpret_cast<uint16_t*>(o) = *reinterpret_cast<uint16_t*>(tmp); break;
+            default: *o = tmp[0]; break;
+          }
+        }
+      }
+    }
+  }
+}
+
+uint32_t pow2_divisor(uint64_t x, uint32_t cap) {
+  uint32_t v = 1;
+  while (v < cap && (x % (v * 2)) == 0) v *= 2;
+  return v;
+}
+
+int g_sm_count = 0;
+
+int launch(const emb_key_t* keys, int nkeys, const int64_t* src_rows,
+           const int64_t* dst_rows, int64_t nrows, int32_t window, void* stream,
+           uint32_t allowed_ops, const char* who) {
+  if (nkeys < 0 || nkeys > EMB_MAX_KEYS)
+    return emb::fail(-1, "%s: nkeys=%d outside [0,%d]", who, nkeys, EMB_MAX_KEYS);
+  if (nrows < 0) return emb::fail(-1, "%s: nrows=%lld < 0", who, (long long)nrows);
+  if (nrows == 0 || nkeys == 0) return 0;
+  if (!keys) return emb::fail(-1, "%s: keys is NULL", who);
+  Table tab;
+  memset(&tab, 0, sizeof(tab));
+  DevKey big[EMB_MAX_KEYS], small[EMB_MAX_KEYS];
+  uint32_t nbig = 0, nsmall = 0, big_units = 0;
+  uint64_t small_units = 0;
+  for (int i = 0; i < nkeys; ++i) {
+    const emb_key_t& k = keys[i];
+    if (!((allowed_ops >> k.op) & 1u))
+      return emb::fail(-2, "%s: key %d has op %u not valid for this entry point",
+                       who, i, k.op);
+    if (k.row_bytes == 0) continue;
+    if (!k.dst && !k.dst2)
+      return emb::fail(-2, "%s: key %d has no destination", who, i);
+    if (!k.src && k.op != EMB_OP_FILL32)
+      return emb::fail(-2, "%s: key %d has no source", who, i);
+    if ((k.op == EMB_OP_LAST || k.op == EMB_OP_MASK) && !k.aux)
+      return emb::fail(-2, "%s: key %d (op %u) needs aux", who, i, k.op);
+    if (k.op == EMB_OP_NORM_U8_F32 && !k.dst2)
+      return emb::fail(-2, "%s: key %d NORM needs dst2", who, i);
+    if (k.op == EMB_OP_FILL32 && k.row_bytes != 4)
+      return emb::fail(-2, "%s: key %d FILL32 needs row_bytes==4", who, i);
+    DevKey d;
+    memset(&d, 0, sizeof(d));
+    d.src = (const uint8_t*)k.src; d.dst = (uint8_t*)k.dst;
+    d.dst2 = (uint8_t*)k.dst2; d.aux = (const uint8_t*)k.aux;
+    d.src_stride = k.src_stride; d.dst_stride = k.dst_stride;
+    d.dst2_stride = k.dst2_stride; d.aux_stride = k.aux_stride;
+    d.row_bytes = k.row_bytes; d.op = k.op; d.dtype = k.dtype; d.fill = k.fill;
+    // alignment every pointer/stride of this key shares
+    uint64_t mix = k.row_bytes | 16;
+    if (k.src) mix |= (uint64_t)k.src | k.src_stride;
+    if (k.dst) mix |= (uint64_t)k.dst | k.dst_stride;
+    const bool norm = k.op == EMB_OP_NORM_U8_F32;
+    if (k.dst2) mix |= (uint64_t)k.dst2 | (norm ? 16 : k.dst2_stride);
+    uint32_t vec = pow2_divisor(mix, 16);
+    if (norm && (k.dst2_stride % 16 || ((uint64_t)k.dst2 % 16)))
+      return emb::fail(-2, "%s: key %d NORM dst2 must be 16-byte aligned", who, i);
+    const bool plain = k.op == EMB_OP_COPY || norm;
+    if (norm && vec != 16)
+      return emb::fail(-2, "%s: key %d NORM needs 16-byte aligned rows", who, i);
+    if (plain && vec == 16 && (k.row_bytes >= kBigMin || norm)) {
+      d.vec = 16;
+      d.unit_begin = big_units;
+      big_units += (k.row_bytes + kBigSlice - 1) / kBigSlice;
+      big[nbig++] = d;
+    } else {
+      if (k.op == EMB_OP_MASK) {
+        uint32_t es = 8;
+        switch (k.dtype) {
+          case EMB_U8: case EMB_I8: case EMB_BOOL: es = 1; break;
+          case EMB_I16: case EMB_U16: case EMB_F16: case EMB_BF16: es = 2; break;
+          case EMB_I32: case EMB_U32: case EMB_F32: es = 4; break;
+          default: es = 8; break;
+        }
+        if (k.row_bytes % es)
+          return emb::fail(-2, "%s: key %d row_bytes %% elem size", who, i);
+        if (vec < es) vec = es;   // element-aligned by construction of the dtype
+      }
+      if (k.op == EMB_OP_FILL32) vec = 4;
+      d.vec = vec;
+      d.vecs_per_row = k.row_bytes / vec;
+      d.unit_begin = (uint32_t)small_units;
+      small_units += ((uint64_t)nrows * d.vecs_per_row + kSmallElems - 1) / kSmallElems;
+      small[nsmall++] = d;
+    }
+  }
+  if (small_units > 0xffffffffull)
+    return emb::fail(-3, "%s: too many small units", who);
+  tab.nbig = nbig; tab.nsmall = nsmall;
+  tab.big_units_per_row = big_units; tab.small_units = (uint32_t)small_units;
+  for (uint32_t i = 0; i < nbig; ++i) tab.k[i] = big[i];
+  for (uint32_t i = 0; i < nsmall; ++i) tab.k[nbig + i] = small[i];
+  const uint64_t total = (uint64_t)nrows * big_units + small_units;
+  if (total == 0) return 0;
+  if (g_sm_count == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return emb::fail_cuda(who);
+    g_sm_count = sms;
+  }
+  // persistent grid: a multiple of the SM count (8 x 256 threads = full SM)
+  uint64_t grid = (uint64_t)g_sm_count * 8;
+  if (total < grid) grid = total;
+  rows_kernel<<<(unsigned)grid, kThreads, 0, (cudaStream_t)stream>>>(
+      tab, src_rows, dst_rows, nrows, window);
+  emb::count_launch();
+  if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
+  return 0;
+}
+
+constexpr uint32_t bit(uint32_t op) { return 1u << op; }
+
+}  // namespace
+
+extern "C" {
+
+int emb_rows_copy(const emb_key_t* keys, int nkeys, const int64_t* src_rows,
+                  const int64_t* dst_rows, int64_t nrows, int32_t window,
+                  void* stream) {
+  return launch(keys, nkeys, src_rows, dst_rows, nrows, window, stream,
+                0xffffffffu, "emb_rows_copy");
+}
+
+int emb_replay_gather(const emb_key_t* keys, int nkeys, const int64_t* src_rows,
+                      int64_t nrows, int32_t window, void* stream) {
+  if (!src_rows) return emb::fail(-1, "emb_replay_gather: src_rows is NULL");
+  if (window <= 0 || nrows % window)
+    return emb::fail(-1, "emb_replay_gather: nrows=%lld not a multiple of window=%d",
+                     (long long)nrows, window);
+  return launch(keys, nkeys, src_rows, nullptr, nrows, window, stream,
+                bit(EMB_OP_COPY) | bit(EMB_OP_FIRST) | bit(EMB_OP_LAST) |
+                bit(EMB_OP_FILL32), "emb_replay_gather");
+}
+
+int emb_replay_append_rows(const emb_key_t* keys, int nkeys,
+                           const int64_t* dst_rows, int64_t nrows, void* stream) {
+  if (!dst_rows) return emb::fail(-1, "emb_replay_append_rows: dst_rows is NULL");
+  return launch(keys, nkeys, nullptr, dst_rows, nrows, 0, stream,
+                bit(EMB_OP_COPY), "emb_replay_append_rows");
+}
+
+int emb_replay_scatter_update(const emb_key_t* keys, int nkeys,
+                              const int64_t* dst_rows, int64_t nrows, void* stream) {
+  if (!dst_rows) return emb::fail(-1, "emb_replay_scatter_update: dst_rows is NULL");
+  return launch(keys, nkeys, nullptr, dst_rows, nrows, 0, stream,
+                bit(EMB_OP_COPY), "emb_replay_scatter_update");
+}
+
+int emb_driver_stage_obs(const emb_key_t* keys, int nkeys, const int64_t* dst_rows,
+                         int64_t nrows, void* stream) {
+  return launch(keys, nkeys, nullptr, dst_rows, nrows, 0, stream,
+                bit(EMB_OP_COPY) | bit(EMB_OP_NORM_U8_F32),
+                "emb_driver_stage_obs");
+}
+
+int emb_driver_scatter_mask_actions(const emb_key_t* keys, int nkeys,
+                                    const int64_t* dst_rows, int64_t nrows,
+                                    void* stream) {
+  return launch(keys, nkeys, nullptr, dst_rows, nrows, 0, stream,
+                bit(EMB_OP_COPY) | bit(EMB_OP_MASK) | bit(EMB_OP_NOT),
+                "emb_driver_scatter_mask_actions");
+}
+
+}  // extern "C"

@@ -1,0 +1,89 @@
+"""Synthetic benchmark environments: obs of a
+given image shape drawn from ``default_rng(1000 + env_id)``, reward ~ N(0, 1),
+episode ends every `length` steps, one discrete action.  No simulator."""
+import numpy as np
+
+from .. import elements
+from ..core import base
+
+
+class SyntheticImage(base.Env):
+
+  def __init__(self, index=0, size=(64, 64, 3), classes=5, length=500,
+               pool=8):
+    self.shape = tuple(size)
+    self.classes = classes
+    self.length = length
+    rng = np.random.default_rng(1000 + index)
+    # A small pool of pre-drawn frames: the env itself must not dominate the
+    # Driver measurement (the reference's Dummy allocates one frame per step).
+    self.frames = rng.integers(0, 256, (pool, *self.shape), dtype=np.uint8)
+    self.rewards = rng.standard_normal(1024).astype(np.float32)
+    self.t = 0
+    self.done = False
+
+  @property
+  def obs_space(self):
+    S = elements.Space
+    return {
+        'image': S(np.uint8, self.shape),
+        'reward': S(np.float32),
+        'is_first': S(bool), 'is_last': S(bool), 'is_terminal': S(bool),
+    }
+
+  @property
+  def act_space(self):
+    S = elements.Space
+    return {'reset': S(bool), 'action': S(np.int32, (), 0, self.classes)}
+
+  def step(self, action):
+    if action['reset'] or self.done:
+      self.t, self.done = 0, False
+      first = True
+    else:
+      self.t += 1
+      first = False
+    self.done = self.t >= self.length
+    return dict(
+        image=self.frames[self.t % len(self.frames)],
+        reward=self.rewards[self.t % 1024],
+        is_first=first, is_last=self.done, is_terminal=self.done)
+
+
+class SyntheticProprio(base.Env):
+  """DMC-walker-shaped proprioceptive obs (config 4)."""
+
+  def __init__(self, index=0, length=500):
+    self.length = length
+    self.rng = np.random.default_rng(1000 + index)
+    self.t = 0
+    self.done = False
+
+  @property
+  def obs_space(self):
+    S = elements.Space
+    return {
+        'orientations': S(np.float32, (14,)), 'height': S(np.float32),
+        'velocity': S(np.float32, (9,)), 'reward': S(np.float32),
+        'is_first': S(bool), 'is_last': S(bool), 'is_terminal': S(bool),
+    }
+
+  @property
+  def act_space(self):
+    S = elements.Space
+    return {'reset': S(bool), 'action': S(np.float32, (6,), -1, 1)}
+
+  def step(self, action):
+    if action['reset'] or self.done:
+      self.t, self.done, first = 0, False, True
+    else:
+      self.t += 1
+      first = False
+    self.done = self.t >= self.length
+    r = self.rng
+    return dict(
+        orientations=r.standard_normal(14).astype(np.float32),
+        height=np.float32(r.standard_normal()),
+        velocity=r.standard_normal(9).astype(np.float32),
+        reward=np.float32(r.standard_normal()),
+        is_first=first, is_last=self.done, is_terminal=self.done)

@@ -1,0 +1,167 @@
+"""Single-process actor + learner loop.
+
+Same factories, arguments, pacing and metric names as the reference
+``embodied.run.train`` (embodied/run/train.py:10-118):
+``train(make_agent, make_replay, make_env, make_stream, make_logger, args)``
+with ``args`` holding ``steps, envs, debug, batch_size, batch_length,
+train_ratio, log_every, report_every, save_every, consec_report,
+report_batches, from_checkpoint, usage, logdir``.
+
+Loop: ``driver(policy, steps=10)``; each Driver step appends N transitions to
+the replay and runs ``when.Ratio(train_ratio / (B*T))`` train steps
+(train.py:25-26,69-80), each followed by ``replay.update(outs['replay'])``
+(train.py:77-78).  ``fps/policy`` and ``fps/train`` (train.py:110-111) are the
+two numbers BASELINE.json's metric asks for.
+
+Differences, all on the host side: the N per-transition callbacks of one
+Driver step are served batched (one replay append launch, vectorised episode
+statistics), so pacing is evaluated once per Driver step with the same
+cumulative counts.
+"""
+import collections
+import pickle
+
+import numpy as np
+
+from .. import elements
+from ..core import clock
+from ..core import driver as driverlib
+
+
+class _EpisodeStats:
+  """Vectorised logfn (train.py:31-54): score / length / reward_rate per env,
+  `log/` keys aggregated avg/max/sum."""
+
+  def __init__(self, logger, epstats):
+    self.logger, self.epstats = logger, epstats
+    self.score = self.length = self.changes = self.prev = None
+    self.logs = collections.defaultdict(dict)
+
+  def __call__(self, trans, n):
+    reward = np.asarray(trans['reward'], np.float64)
+    first = np.asarray(trans['is_first'], bool)
+    last = np.asarray(trans['is_last'], bool)
+    if self.score is None:
+      self.score = np.zeros(n)
+      self.length = np.zeros(n, np.int64)
+      self.changes = np.zeros(n, np.int64)
+      self.prev = np.zeros(n)
+    self.score[first] = 0
+    self.length[first] = 0
+    self.changes[first] = 0
+    moved = (np.abs(reward - self.prev) >= 0.01) & ~first
+    self.changes += moved
+    self.score += reward
+    self.length += 1
+    self.prev = reward
+    logkeys = [k for k in trans if k.startswith('log/')]
+    for i in np.nonzero(last)[0]:
+      self.logger.add(
+          {'score': self.score[i], 'length': self.length[i]}, prefix='episode')
+      result = {}
+      if self.length[i] > 1:
+        result['reward_rate'] = self.changes[i] / (self.length[i] - 1)
+      for k in logkeys:
+        result[k] = trans[k][i]
+      self.epstats.add(result)
+
+
+def train(make_agent, make_replay, make_env, make_stream, make_logger, args):
+
+  agent = make_agent()
+  replay = make_replay()
+  logger = make_logger()
+
+  logdir = elements.Path(args.logdir)
+  step = logger.step
+  usage = elements.Usage(**args.usage)
+  train_agg = elements.Agg()
+  epstats = elements.Agg()
+  policy_fps = elements.FPS()
+  train_fps = elements.FPS()
+
+  batch_steps = args.batch_size * args.batch_length
+  should_train = elements.when.Ratio(args.train_ratio / batch_steps)
+  should_log = clock.LocalClock(args.log_every)
+  should_report = clock.LocalClock(args.report_every)
+  should_save = clock.LocalClock(args.save_every)
+
+  fns = [(lambda i=i: make_env(i)) for i in range(args.envs)]
+  driver = driverlib.Driver(
+      fns, parallel=not args.debug, fetch_outs=False,
+      ops=getattr(args, 'driver_ops', None))
+  episode_stats = _EpisodeStats(logger, epstats)
+  driver.on_step(replay.add)
+
+  stream_train = iter(agent.stream(make_stream(replay, 'train')))
+  stream_report = iter(agent.stream(make_stream(replay, 'report')))
+  carry_train = [agent.init_train(args.batch_size)]
+  carry_report = agent.init_report(args.batch_size)
+
+  def after_step(trans, n):
+    step.increment(n)
+    policy_fps.step(n)
+    episode_stats(trans, n)
+    if len(replay) < args.batch_size * args.batch_length:
+      return
+    for _ in range(should_train(step)):
+      with elements.timer.section('stream_next'):
+        batch = next(stream_train)
+      carry_train[0], outs, mets = agent.train(carry_train[0], batch)
+      train_fps.step(batch_steps)
+      if 'replay' in outs:
+        replay.update(outs['replay'])
+      train_agg.add(mets, prefix='train')
+  driver.on_batch(after_step)
+
+  cp = elements.Checkpoint(logdir / 'checkpoint.pkl')
+  cp.step = step
+  cp.agent = agent
+  cp.replay = replay
+  if args.from_checkpoint:
+    data = pickle.loads(elements.Path(args.from_checkpoint).read(mode='rb'))
+    agent.load(data['agent'])
+  cp.load_or_save()
+
+  print('Start training loop')
+  policy = _with_mode(agent, 'train')
+  driver.reset(agent.init_policy)
+  while step < args.steps:
+
+    driver(policy, steps=10)
+
+    if should_report(step) and len(replay):
+      agg = elements.Agg()
+      for _ in range(args.get('consec_report', 1) * args.report_batches):
+        carry_report, mets = agent.report(carry_report, next(stream_report))
+        agg.add(mets)
+      logger.add(agg.result(), prefix='report')
+
+    if should_log(step):
+      logger.add(train_agg.result())
+      logger.add(epstats.result(), prefix='epstats')
+      logger.add(replay.stats(), prefix='replay')
+      logger.add(usage.stats(), prefix='usage')
+      logger.add({'fps/policy': policy_fps.result()})
+      logger.add({'fps/train': train_fps.result()})
+      logger.add({'timer': elements.timer.stats()['summary']})
+      logger.write()
+
+    if should_save(step):
+      cp.save()
+
+  driver.close()
+  logger.close()
+
+
+class _with_mode:
+  """policy(carry, obs) -> agent.policy(carry, obs, mode=...), keeping the
+  agent visible to the Driver (device_obs / ext_space lookups)."""
+
+  def __init__(self, agent, mode):
+    self.agent, self.mode = agent, mode
+    self.device_obs = bool(getattr(agent, 'device_obs', False))
+    self.ext_space = getattr(agent, 'ext_space', None)
+
+  def __call__(self, carry, obs, **kwargs):
+    return self.agent.policy(carry, obs, mode=self.mode, **kwargs)

@@ -1,0 +1,123 @@
+/* embodied_b200 -- C ABI of the B200-native actor-learner hot path.
+ *
+ * The reference (danijar/embodied) is 100% Python and has no FFI: its plugin
+ * boundary is the duck-typed Agent / Env / Stream protocols
+ * (embodied/core/base.py:1-73) plus Driver / Replay.  This header is the
+ * boundary we put UNDERNEATH those Python classes: each entry point names the
+ * reference function whose per-element work it replaces.  A maintainer of the
+ * reference would bind it with ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 on success, <0 on error; emb_last_error() gives a
+ *    thread-local message.
+ *  - no allocation / ownership crosses the ABI: every buffer is a caller-owned
+ *    DEVICE pointer (or pinned host pointer where stated) with explicit sizes.
+ *  - every launch takes a cudaStream_t (as void*) and is asynchronous.
+ *  - integer / byte paths are bit-exact with the reference's numpy code.
+ */
+#ifndef EMBODIED_B200_H_
+#define EMBODIED_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMB_ABI_VERSION 1
+#define EMB_MAX_KEYS 32
+
+/* per-key row operation */
+enum emb_op {
+  EMB_OP_COPY = 0,        /* dst[row] = src[row]                                            */
+  EMB_OP_FIRST = 1,       /* COPY, then byte 0 of the first row of every window := 1        */
+                          /*   Replay._annotate_batch  embodied/core/replay.py:283-286      */
+  EMB_OP_LAST = 2,        /* COPY | is_first(next row of the same window)                   */
+                          /*   Replay._annotate_batch  embodied/core/replay.py:287-291      */
+  EMB_OP_FILL32 = 3,      /* dst[row] = fill (one int32 per row): the 'consec' key          */
+                          /*   streams.Consec.__next__ embodied/core/streams.py:134         */
+  EMB_OP_MASK = 4,        /* dst[row] = src[row] * (elem)(!aux[row])  typed multiply        */
+                          /*   Driver._mask            embodied/core/driver.py:72-74,84-87  */
+  EMB_OP_NORM_U8_F32 = 5, /* COPY u8 rows, and dst2[row] = float(src)/255 - 0.5 (fp32)       */
+                          /*   Encoder.__call__        dreamerv3/rssm.py:230                */
+  EMB_OP_NOT = 6          /* dst[row] = !src[row] (bool rows)                               */
+};
+
+/* element type for EMB_OP_MASK */
+enum emb_dtype {
+  EMB_U8 = 0, EMB_BOOL = 1, EMB_I32 = 2, EMB_I64 = 3, EMB_F32 = 4, EMB_F64 = 5,
+  EMB_F16 = 6, EMB_BF16 = 7, EMB_I16 = 8, EMB_I8 = 9, EMB_U16 = 10,
+  EMB_U32 = 11, EMB_U64 = 12
+};
+
+/* One key (= one named field of a transition) of a row-copy launch.  Rows of a
+ * key are `row_bytes` long and `*_stride` bytes apart. */
+typedef struct emb_key {
+  const void* src;      /* device; row r of the source is src + srow(r)*src_stride  */
+  void* dst;            /* device; row r of the destination is dst + drow(r)*dst_stride */
+  void* dst2;           /* EMB_OP_NORM_U8_F32: float32 output, dense rows (else NULL) */
+  const void* aux;      /* EMB_OP_LAST: the is_first SOURCE table (stride aux_stride, indexed
+                           like src);  EMB_OP_MASK: bool is_last[nrows] (stride 1, indexed by r) */
+  uint64_t src_stride;
+  uint64_t dst_stride;
+  uint64_t dst2_stride; /* bytes between rows of dst2 */
+  uint64_t aux_stride;
+  uint32_t row_bytes;
+  uint32_t op;          /* enum emb_op */
+  uint32_t dtype;       /* enum emb_dtype (EMB_OP_MASK only) */
+  int32_t fill;         /* EMB_OP_FILL32 */
+} emb_key_t;
+
+const char* emb_last_error(void);
+int emb_abi_version(void);
+/* Number of kernels this library has launched in this process (gpu_launches). */
+uint64_t emb_launch_count(void);
+/* SM count of the current device (grid sizing), <0 on error. */
+int emb_device_sm_count(void);
+
+/* The row engine.  For r in [0, nrows):
+ *     srow(r) = src_rows ? src_rows[r] : r        drow(r) = dst_rows ? dst_rows[r] : r
+ *   rows with srow(r) < 0 or drow(r) < 0 are skipped (evicted chunk,
+ *   Replay.update embodied/core/replay.py:146-149).
+ * `window` = rows per sampled sequence (for EMB_OP_FIRST / EMB_OP_LAST); 0 if unused.
+ * src_rows / dst_rows are DEVICE int64 arrays (or NULL = identity). */
+int emb_rows_copy(const emb_key_t* keys, int nkeys,
+                  const int64_t* src_rows, const int64_t* dst_rows,
+                  int64_t nrows, int32_t window, void* stream);
+
+/* Named entry points = emb_rows_copy restricted to the ops each reference
+ * function performs (argument meaning identical). */
+
+/* Replay._assemble_batch + _annotate_batch + streams.Consec contiguous copy
+ * (embodied/core/replay.py:256-292, embodied/core/streams.py:131-138):
+ * gather B windows of `window` rows into dense (B, window, ...) outputs. */
+int emb_replay_gather(const emb_key_t* keys, int nkeys, const int64_t* src_rows,
+                      int64_t nrows, int32_t window, void* stream);
+
+/* Replay.add / Chunk.append for N workers at once
+ * (embodied/core/replay.py:77-99, embodied/core/chunk.py:41-50). */
+int emb_replay_append_rows(const emb_key_t* keys, int nkeys,
+                           const int64_t* dst_rows, int64_t nrows, void* stream);
+
+/* Replay.update / _setseq / Chunk.update
+ * (embodied/core/replay.py:130-149,216-235, embodied/core/chunk.py:54-58). */
+int emb_replay_scatter_update(const emb_key_t* keys, int nkeys,
+                              const int64_t* dst_rows, int64_t nrows, void* stream);
+
+/* Driver._step obs side: np.stack + cast/normalise for the policy, fused with
+ * the replay append of the observation keys
+ * (embodied/core/driver.py:65, dreamerv3/rssm.py:230). */
+int emb_driver_stage_obs(const emb_key_t* keys, int nkeys,
+                         const int64_t* dst_rows, int64_t nrows, void* stream);
+
+/* Driver._step action side: mask actions where is_last, emit reset, and scatter
+ * action / policy-output rows into the replay
+ * (embodied/core/driver.py:72-76,84-87). */
+int emb_driver_scatter_mask_actions(const emb_key_t* keys, int nkeys,
+                                    const int64_t* dst_rows, int64_t nrows,
+                                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* EMBODIED_B200_H_ */
