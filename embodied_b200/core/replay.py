@@ -443,8 +443,16 @@ class Replay:
           # reference: KeyError from the first chunk -> row skipped entirely;
           # a missing successor leaves the leading piece written (:224-235).
           rows[b] = self._rows_reachable(uuid, index, T)
+      flat = rows.reshape(-1)
+      # Overlapping windows name the same table row more than once.  The
+      # reference applies rows b = 0..B-1 in order, so the LAST writer wins;
+      # inside one launch that must be made explicit.
+      _, at = np.unique(flat[::-1], return_index=True)
+      keep = np.zeros(len(flat), bool)
+      keep[len(flat) - 1 - at] = True
+      flat = np.where(keep, flat, -1)
       self._flush()
-      self.store.scatter(rows.reshape(-1), data)
+      self.store.scatter(flat, data)
 
   def _rows_reachable(self, uuid, index, count):
     out = np.full(count, -1, np.int64)

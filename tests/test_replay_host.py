@@ -283,3 +283,22 @@ def test_threading(tmpdir, length=5, capacity=128, chunksize=32,
     [w.join() for w in workers]
   assert not errors, errors
   assert len(replay) == capacity
+
+
+def test_update_overlapping_windows_last_writer_wins():
+  replay = make(3, 50, chunksize=4)
+  for step in range(6):
+    replay.add({'step': np.int32(step), 'lat': np.zeros(1, np.float32)})
+  batch = replay.sample(8)          # 4 items, 8 draws: overlaps guaranteed
+  new = np.arange(8 * 3, dtype=np.float32).reshape(8, 3, 1) + 1
+  replay.update({'stepid': batch['stepid'], 'lat': new})
+  want = {}
+  for b in range(8):
+    for t in range(3):
+      want[int(batch['step'][b, t])] = new[b, t, 0]
+  got = replay.sample(8)
+  for b in range(8):
+    for t in range(3):
+      assert got['lat'][b, t, 0] == want[int(got['step'][b, t])]
+  kinds = [k for k, _ in replay.store.launches]
+  assert kinds.count('scatter') == 1
