@@ -18,6 +18,10 @@ from .. import _lib
 
 STEPID_BYTES = 20
 
+# bench.py sets this to a list to collect ('gather', start, end) CUDA event
+# pairs around the launches (the live per-launch timing of the roofline line).
+PROFILE = None
+
 
 def _np_to_torch_dtype(dtype):
   return {
@@ -331,9 +335,17 @@ class DeviceStore:
       klist.append(_lib.Key(
           dst=out['consec'].data_ptr(), dst_stride=4, row_bytes=4,
           op=_lib.OP_FILL32, fill=int(consec)))
+    prof = PROFILE
+    if prof is not None:
+      t0 = torch.cuda.Event(enable_timing=True)
+      t1 = torch.cuda.Event(enable_timing=True)
+      t0.record(stream)
     _lib.check(self.lib.emb_replay_gather(
         _lib.keys_array(klist), len(klist), rows_dev.data_ptr(),
         batch * window, window, stream.cuda_stream))
+    if prof is not None:
+      t1.record(stream)
+      prof.append(('gather', t0, t1))
     return out
 
   # ------------------------------------------------------------ write (update)

@@ -94,6 +94,20 @@ __device__ __forceinline__ void mask_mul(uint8_t* d, const uint8_t* s, bool keep
   *reinterpret_cast<T*>(d) = v * m;
 }
 
+template <typename U>
+__device__ __forceinline__ U float_bits_times_zero(U v, int ebits, int mbits) {
+  const U one = 1;
+  const U sign = one << (ebits + mbits);
+  const U emask = ((one << ebits) - 1) << mbits;
+  const U mmask = (one << mbits) - 1;
+  const U quiet = one << (mbits - 1);
+  if ((v & emask) == emask) {
+    if (v & mmask) return v | quiet;          // NaN in -> same NaN, quieted
+    return sign | emask | quiet;              // inf * 0 -> default NaN
+  }
+  return v & sign;                            // finite * (+0) -> +-0
+}
+
 __device__ __forceinline__ void mask_elem(uint32_t dtype, uint8_t* d,
                                           const uint8_t* s, bool keep) {
   switch (dtype) {
@@ -102,22 +116,29 @@ __device__ __forceinline__ void mask_elem(uint32_t dtype, uint8_t* d,
     case EMB_I16: case EMB_U16: mask_mul<uint16_t>(d, s, keep); break;
     case EMB_I32: case EMB_U32: mask_mul<uint32_t>(d, s, keep); break;
     case EMB_I64: case EMB_U64: mask_mul<unsigned long long>(d, s, keep); break;
+    // Floating point: value * mask.astype(dtype) with mask in {0, 1}.  Done on
+    // the bit pattern so that the result is what numpy on the reference's x86
+    // host produces, byte for byte: x*1 = x; finite*0 = +-0 (sign kept);
+    // inf*0 = the x86 default NaN (sign set, quiet); nan*0 = the input NaN quieted.
     case EMB_F32: {
-      float v = *reinterpret_cast<const float*>(s);
-      *reinterpret_cast<float*>(d) = __fmul_rn(v, keep ? 1.0f : 0.0f);
+      uint32_t v = *reinterpret_cast<const uint32_t*>(s);
+      *reinterpret_cast<uint32_t*>(d) =
+          keep ? v : float_bits_times_zero<uint32_t>(v, 8, 23);
     } break;
     case EMB_F64: {
-      double v = *reinterpret_cast<const double*>(s);
-      *reinterpret_cast<double*>(d) = __dmul_rn(v, keep ? 1.0 : 0.0);
+      unsigned long long v = *reinterpret_cast<const unsigned long long*>(s);
+      *reinterpret_cast<unsigned long long*>(d) =
+          keep ? v : float_bits_times_zero<unsigned long long>(v, 11, 52);
     } break;
     case EMB_F16: {
-      __half v = *reinterpret_cast<const __half*>(s);
-      *reinterpret_cast<__half*>(d) = __hmul(v, __float2half(keep ? 1.f : 0.f));
+      uint16_t v = *reinterpret_cast<const uint16_t*>(s);
+      *reinterpret_cast<uint16_t*>(d) =
+          keep ? v : float_bits_times_zero<uint16_t>(v, 5, 10);
     } break;
     case EMB_BF16: {
-      __nv_bfloat16 v = *reinterpret_cast<const __nv_bfloat16*>(s);
-      *reinterpret_cast<__nv_bfloat16*>(d) =
-          __hmul(v, __float2bfloat16(keep ? 1.f : 0.f));
+      uint16_t v = *reinterpret_cast<const uint16_t*>(s);
+      *reinterpret_cast<uint16_t*>(d) =
+          keep ? v : float_bits_times_zero<uint16_t>(v, 8, 7);
     } break;
     default: break;
   }
