@@ -119,6 +119,8 @@ class FeedAgent:
   def init_policy(self, n):
     return ()
 
+  init_train = init_policy
+
   def policy(self, carry, obs, mode='train'):
     i = self.t % 4
     self.t += 1
@@ -141,14 +143,22 @@ class Loop:
   """Config-2 wiring (dreamerv3/main.py:183-272): Replay(length=65, online,
   chunksize 1024) + Stateless -> Consec(length 64, consec 1, prefix 1)."""
 
-  def __init__(self, torch, rank, capacity):
+  def __init__(self, torch, rank, capacity, agent='dreamerv3', size='size200m',
+               dtype='bfloat16'):
     import embodied_b200 as embodied
     from embodied_b200 import _lib
     self.torch, self.lib, self.embodied = torch, _lib, embodied
     self.replay = embodied.Replay(
         L, capacity, chunksize=1024, online=True, seed=0,
         staging_rows=NENVS, workers=NENVS)
-    self.agent = FeedAgent(torch, NENVS, seed=rank)
+    if agent == 'feed':
+      self.agent = FeedAgent(torch, NENVS, seed=rank)
+    else:
+      from embodied_b200 import dreamerv3
+      env = make_env(0)
+      self.agent = dreamerv3.Agent(
+          env.obs_space, env.act_space,
+          dreamerv3.config.make(size, compute_dtype=dtype, seed=0))
     base = embodied.streams.Stateless(self.replay.sample, B, 'train')
     self.stream = iter(embodied.streams.Consec(
         base, length=T, consec=1, prefix=PREFIX, strict=True, contiguous=True))
@@ -158,7 +168,8 @@ class Loop:
     self.driver.on_step(self.replay.add)
     self.driver.on_batch(lambda trans, n: self.learn())
     self.driver.reset(self.agent.init_policy)
-    self.carry = None
+    self.carry = self.agent.init_train(B) if agent != 'feed' else None
+    self.pcarry = self.agent.init_policy(NENVS)
     self.learner_on = False
     self.result = None
 
@@ -167,14 +178,14 @@ class Loop:
       return
     for _ in range(TRAINS_PER_STEP):
       batch = next(self.stream)
-      self.carry, outs, _ = self.agent.train(self.carry, batch)
+      self.carry, outs, mets = self.agent.train(self.carry, batch)
       self.replay.update(outs['replay'])
-      self.result = batch['reward']
+      self.result = mets.get('loss', batch['reward'][0, 0])
 
   def step_e2e(self):
     """The user-facing call: host envs -> pinned staging -> H2D -> kernels."""
     self.driver(self.agent.policy, steps=NENVS)
-    return self.result.sum(1)[:1].cpu()      # D2H read of the step's result
+    return self.result.cpu()                  # D2H read of the step's result (loss)
 
   def make_resident(self):
     """Pre-stage the observations of a Driver step in HBM (for `value`)."""
@@ -190,7 +201,7 @@ class Loop:
   def step_resident(self):
     """Same work with the N observations already on the device: policy, append
     (one launch), then the learner steps."""
-    _, acts, outs = self.agent.policy((), self.res)
+    self.pcarry, acts, outs = self.agent.policy(self.pcarry, self.res)
     self.replay.add_batch({**self.res, **acts, **outs})
     self.learn()
 
@@ -211,7 +222,7 @@ def run_b200(args):
   peak, peak_src = peaks()
 
   capacity = int(args.capacity)
-  loop = Loop(torch, rank, capacity)
+  loop = Loop(torch, rank, capacity, args.agent, args.size, args.dtype)
   flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
   # prefill through the public API until windows exist
@@ -270,13 +281,14 @@ def run_b200(args):
       'learner_samples_per_sec': env_steps / t_dev * TRAIN_RATIO,
       'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': t_dev / args.steps * 1e3, 'higher_is_better': True,
-      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+      'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'u8' if args.agent == 'feed' else {'bfloat16': 'bf16', 'float32': 'f32'}[args.dtype],
+      'data': 'synthetic',
       'config': {
-          'workload': 'config 2 PLUMBING ONLY: Driver(256 envs, 64x64x3 u8) + Replay(L=65, '
-                      '53 299 B rows incl. f32 latents) append/sample(B=16)/update, '
-                      f'{TRAINS_PER_STEP} learner iterations per Driver step (train_ratio 32); '
-                      'NO model yet: latents come from a device pool',
-          'envs_per_gpu': NENVS, 'batch': [B, T], 'replay_capacity_items': capacity,
+          'workload': workload_name(args),
+          'envs_per_gpu': NENVS, 'batch': [B, T], 'train_ratio': TRAIN_RATIO,
+          'learner_steps_per_step': TRAINS_PER_STEP, 'replay_capacity_items': capacity,
+          'parallelism': f'dp{world}: envs, replay shard and batch per rank; NCCL grad all-reduce',
           'cache': 'L2 flushed (256 MiB write) before every timed step; replay tables > L2'},
       'e2e': {'value': env_steps / t_e2e, 'unit': 'env steps/s',
               'ms_per_step': t_e2e / args.steps * 1e3,
@@ -291,10 +303,18 @@ def run_b200(args):
   }
   if rank == 0:
     if world == 1 and not args.no_cpu:
-      line['cpu_baseline'] = cpu_baseline(seconds=args.cpu_seconds)
+      line['cpu_baseline'] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()
+
+
+def workload_name(args):
+  if args.agent == 'feed':
+    return ('config 2 PLUMBING ONLY: Driver(256 envs, 64x64x3 u8) + Replay(L=65, 53 299 B rows '
+            'incl. f32 latents) append/sample(B=16)/update; no model, latents from a device pool')
+  return (f'config 2: dreamerv3 {args.size} on synthetic 64x64x3 image env, 256 envs, '
+          'replay (B=16,T=64,L=65), one Driver step + 8 x (sample -> train -> update)')
 
 
 # ------------------------------------------------------ the reference (CPU) arm
@@ -334,7 +354,7 @@ class OracleLoop:
       self.replay.update({k: batch[k][:, PREFIX:] for k in ('stepid', 'dyn/deter', 'dyn/stoch')})
 
 
-def time_oracle(steps, warmup):
+def time_plumbing(steps, warmup):
   loop = OracleLoop()
   while len(loop.replay) < 4 * B * L:
     loop.step()
@@ -344,37 +364,107 @@ def time_oracle(steps, warmup):
   t0 = time.perf_counter()
   for _ in range(steps):
     loop.step()
-  return time.perf_counter() - t0
+  return (time.perf_counter() - t0) / steps
 
 
-def cpu_baseline(seconds=15.0):
-  t1 = time_oracle(1, 1)
-  steps = int(max(2, min(200, seconds / max(t1, 1e-3))))
-  t = time_oracle(steps, 0)
-  return {'value': NENVS * steps / t, 'unit': 'env steps/s', 'cores': 1, 'kind': 'port',
-          'sample': f'{steps} iterations of the same config-2 loop (256 envs + {TRAINS_PER_STEP} '
-                    'sample/update) with oracle/host_oracle.py, single thread as in '
-                    'run.train debug mode (dreamerv3/configs.yaml:70)',
-          'ms_per_step': t / steps * 1e3}
+class OracleLearner:
+  """The fp32 torch-CPU restatement of the reference's dreamerv3 step
+  (oracle/dreamer_oracle.py) at the benchmark's model size, all host threads."""
+
+  def __init__(self, size):
+    import torch
+    from oracle import dreamer_oracle as do
+    from embodied_b200.dreamerv3 import config as C
+    self.torch, self.do = torch, do
+    self.threads = os.cpu_count() or 1
+    torch.set_num_threads(self.threads)
+    self.cfg = do.default_config(**C.SIZES[size])
+    self.model = do.Dreamer(self.cfg, do.init_params(self.cfg, 0))
+
+  def batch(self, b):
+    torch, cfg = self.torch, self.cfg
+    g = torch.Generator().manual_seed(b)
+    return {
+        'image': torch.randint(0, 256, (b, L, *IMAGE), generator=g, dtype=torch.uint8),
+        'reward': torch.randn(b, L, generator=g),
+        'is_first': torch.zeros(b, L, dtype=torch.bool),
+        'is_last': torch.zeros(b, L, dtype=torch.bool),
+        'is_terminal': torch.zeros(b, L, dtype=torch.bool),
+        'action': torch.randint(0, CLASSES, (b, L), generator=g, dtype=torch.int32),
+        'dyn/deter': torch.zeros(b, L, cfg.deter),
+        'dyn/stoch': torch.zeros(b, L, cfg.stoch, cfg.classes),
+        'stepid': torch.zeros(b, L, 20, dtype=torch.uint8)}
+
+  def time_train(self, b):
+    data, noise = self.batch(b), self.do.make_noise(self.cfg, b, T, 0)
+    t0 = time.perf_counter()
+    self.model.train(data, noise)
+    return time.perf_counter() - t0
+
+  def time_policy(self, n):
+    torch, cfg = self.torch, self.cfg
+    carry = dict(deter=torch.zeros(n, cfg.deter), stoch=torch.zeros(n, cfg.stoch, cfg.classes),
+                 action=torch.zeros(n, dtype=torch.int32))
+    image = torch.randint(0, 256, (n, *IMAGE), dtype=torch.uint8)
+    noise = dict(stoch=torch.zeros(n, cfg.stoch, cfg.classes), action=torch.zeros(n, cfg.actions))
+    t0 = time.perf_counter()
+    self.model.policy(carry, image, torch.zeros(n, dtype=torch.bool), noise)
+    return time.perf_counter() - t0
+
+
+def cpu_iteration(args, learner=None):
+  """Seconds per benchmark step on the host, from a bounded sample: the
+  Driver+Replay iteration is timed whole; agent.policy is timed on 64 of the 256
+  envs (x4); agent.train on sub-batches B=1 and B=2 of the (16, 64) batch and
+  extrapolated linearly to B=16 (the per-step weight traffic does not scale
+  with B, so a plain x16 would overstate the CPU time)."""
+  t_plumb = time_plumbing(2, 1)
+  if args.agent == 'feed':
+    return t_plumb, {'plumbing_s': t_plumb}, 1
+  learner = learner or OracleLearner(args.size)
+  t_pol = 4 * learner.time_policy(64)
+  t1 = learner.time_train(1)
+  t2 = learner.time_train(2)
+  t16 = t1 + 15 * max(t2 - t1, 0.0)
+  parts = {'plumbing_s': t_plumb, 'policy_256_s': t_pol, 'train_B1_s': t1, 'train_B2_s': t2,
+           'train_B16_extrapolated_s': t16}
+  return t_plumb + t_pol + TRAINS_PER_STEP * t16, parts, learner.threads
+
+
+def cpu_baseline(args):
+  t, parts, threads = cpu_iteration(args)
+  return {'value': NENVS / t, 'unit': 'env steps/s', 'cores': threads, 'kind': 'port',
+          'sample': 'one benchmark step assembled from a bounded sample: oracle Driver+Replay '
+                    'iteration timed whole (1 thread, as in run.train debug mode); oracle '
+                    'dreamerv3 policy on 64/256 envs x4; oracle train step at B=1 and B=2 '
+                    f'(T=64) extrapolated linearly to B=16, x{TRAINS_PER_STEP} (fp32, '
+                    f'{threads} torch threads)', 'ms_per_step': t * 1e3, 'parts': parts}
 
 
 def run_reference(args):
   if int(os.environ.get('RANK', 0)) != 0:
     return
-  steps = max(1, min(args.steps, 50))
-  t = time_oracle(steps, min(args.warmup, 3))
-  v = NENVS * steps / t
+  steps = max(1, min(args.steps, 3))
+  warm = min(args.warmup, 1)
+  learner = None if args.agent == 'feed' else OracleLearner(args.size)
+  for _ in range(warm):
+    if learner is not None:
+      learner.time_policy(8)
+  times = [cpu_iteration(args, learner) for _ in range(steps)]
+  t = float(np.mean([x[0] for x in times]))
+  v = NENVS / t
+  threads = times[0][2]
   print(json.dumps({
       'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': v, 'unit': 'env steps/s',
       'learner_samples_per_sec': v * TRAIN_RATIO,
-      'n_gpus': args.gpus, 'steps': steps, 'warmup': min(args.warmup, 3),
-      'ms_per_step': t / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-      'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
-      'config': {'workload': 'config 2 PLUMBING ONLY (same as the b200 arm), numpy port of the '
-                             'reference Driver+Replay+Consec on the host', 'envs': NENVS,
-                 'batch': [B, T]},
-      'cpu_baseline': {'value': v, 'unit': 'env steps/s', 'cores': 1, 'kind': 'port',
-                       'sample': f'{steps} iterations'},
+      'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
+      'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': {'workload': workload_name(args) + ' -- CPU restatement of the reference '
+                             '(oracle/), see cpu_baseline.sample', 'envs': NENVS, 'batch': [B, T]},
+      'cpu_baseline': {'value': v, 'unit': 'env steps/s', 'cores': threads, 'kind': 'port',
+                       'sample': cpu_iteration.__doc__.strip().replace('\n  ', ' '),
+                       'parts': times[-1][1]},
       'e2e': {'value': v, 'unit': 'env steps/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0}}), flush=True)
 
@@ -382,11 +472,13 @@ def run_reference(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=30)
-  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--steps', type=int, default=10)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--agent', default='dreamerv3', choices=['dreamerv3', 'feed'])
+  ap.add_argument('--size', default='size200m')
+  ap.add_argument('--dtype', default='bfloat16', choices=['bfloat16', 'float32'])
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--capacity', type=float, default=2e5)
-  ap.add_argument('--cpu-seconds', type=float, default=15.0)
   ap.add_argument('--no-cpu', action='store_true')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3)

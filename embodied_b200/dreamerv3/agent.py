@@ -1,0 +1,211 @@
+"""DreamerV3 agent behind the embodied Agent protocol (embodied/core/base.py:1-31).
+
+Same constructor and methods as the reference's ``dreamerv3.Agent`` wrapped by
+``embodied.jax.Agent`` (dreamerv3/agent.py:24-154, embodied/jax/agent.py:220-337):
+``Agent(obs_space, act_space, config)``, ``init_policy/init_train/init_report``,
+``policy(carry, obs, mode) -> (carry, act, out)``, ``train(carry, data) ->
+(carry, outs, metrics)`` with ``outs['replay'] = {stepid, dyn/deter, dyn/stoch}``,
+``report``, ``stream``, ``save``, ``load``, ``ext_space``, ``policy_keys``.
+
+Differences, all about where bytes live: observations arrive as device tensors
+staged by ``emb_driver_stage_obs`` (``device_obs = True``; uint8 images also
+normalised to float32 there), actions / latents are returned as device tensors
+and appended to the replay by ``emb_driver_scatter_mask_actions`` without
+visiting the host, train batches are the dense device tensors of
+``emb_replay_gather`` and ``outs['replay']`` stays on the device for
+``emb_replay_scatter_update``.  With ``torch.distributed`` initialised, the flat
+gradient buffer is averaged with ONE NCCL all-reduce (embodied/jax/opt.py:52-54).
+"""
+import numpy as np
+import torch
+
+from .. import elements
+from ..core import base
+from . import config as configlib
+from . import model as modellib
+from . import optim
+from . import params as paramlib
+
+f32 = torch.float32
+
+
+class Agent(base.Agent):
+
+  device_obs = True
+
+  def __init__(self, obs_space, act_space, config=None, device=None, values=None):
+    if not torch.cuda.is_available():
+      raise RuntimeError(
+          'embodied_b200.dreamerv3.Agent runs on a CUDA device; none is visible '
+          'and there is no CPU fallback.')
+    self.obs_space = dict(obs_space)
+    self.act_space = {k: v for k, v in act_space.items() if k != 'reset'}
+    cfg = config if isinstance(config, configlib.Config) else configlib.make(**(config or {}))
+    imgkeys = [k for k, s in self.obs_space.items()
+               if s.dtype == np.uint8 and len(s.shape) == 3]
+    if imgkeys != ['image'] or list(self.act_space) != ['action'] or \
+        not self.act_space['action'].discrete:
+      raise NotImplementedError(
+          'this build covers the BASELINE configs: one uint8 `image` observation '
+          f'and one discrete `action` (got obs {list(self.obs_space)}, '
+          f'act {list(self.act_space)})')
+    cfg = configlib.Config(cfg)
+    cfg.update(image=tuple(self.obs_space['image'].shape),
+               actions=int(np.asarray(self.act_space['action'].classes).flatten()[0]))
+    self.cfg = cfg
+    self.device = torch.device(device if device is not None else
+                               f'cuda:{torch.cuda.current_device()}')
+    self.cd = {'bfloat16': torch.bfloat16, 'float32': f32}[cfg.compute_dtype]
+    if self.cd == f32:
+      # parity mode: strict IEEE fp32 GEMMs and convolutions
+      torch.backends.cuda.matmul.allow_tf32 = False
+      torch.backends.cudnn.allow_tf32 = False
+    self.store = paramlib.ParamStore(cfg, self.device, self.cd, cfg.seed, values)
+    self.model = modellib.Model(cfg, self.store)
+    self.opt = optim.Optimizer(cfg, self.store)
+    self.world = 1
+    self.rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+      self.world = torch.distributed.get_world_size()
+      self.rank = torch.distributed.get_rank()
+      self.model.reduce_percentiles = self._gathered_percentiles
+    self.gen = torch.Generator(device=self.device)
+    self.gen.manual_seed(cfg.seed * 1000003 + self.rank)     # transform.py:84-85 fold_in(rank)
+    self.updates = 0
+
+  # --------------------------------------------------------------- plugin props
+  @property
+  def policy_keys(self):
+    return '^(enc|dyn|dec|pol)/'
+
+  @property
+  def ext_space(self):                                       # dreamerv3/agent.py:88-99
+    S = elements.Space
+    cfg = self.cfg
+    return {'dyn/deter': S(np.float32, (cfg.deter,)),
+            'dyn/stoch': S(np.float32, (cfg.stoch, cfg.classes))}
+
+  def init_policy(self, batch_size):                         # agent.py:101-107
+    cfg, dev = self.cfg, self.device
+    return (torch.zeros((batch_size, cfg.deter), dtype=self.cd, device=dev),
+            torch.zeros((batch_size, cfg.stoch, cfg.classes), dtype=self.cd, device=dev),
+            torch.zeros((batch_size,), dtype=torch.int32, device=dev))
+
+  init_train = init_policy
+  init_report = init_policy
+
+  # --------------------------------------------------------------------- policy
+  @torch.no_grad()
+  def policy(self, carry, obs, mode='train', noise=None):    # agent.py:115-135
+    cfg, m = self.cfg, self.model
+    deter, stoch, prevact = carry
+    image = obs['image']
+    if not isinstance(image, torch.Tensor):
+      image = torch.as_tensor(np.asarray(image), device=self.device)
+    normalized = (getattr(obs, 'normalized', None) or {}).get('image')
+    reset = obs['is_first']
+    if not isinstance(reset, torch.Tensor):
+      reset = torch.as_tensor(np.asarray(reset), device=self.device)
+    n = len(reset)
+    if noise is None:
+      noise = dict(
+          stoch=modellib.gumbel_like((n, cfg.stoch, cfg.classes), self.device, self.gen),
+          action=modellib.gumbel_like((n, cfg.actions), self.device, self.gen))
+    tokens = m.encoder(image, normalized)
+    (deter, stoch), feat = m.observe(
+        (deter, stoch), tokens[:, None], prevact[:, None], reset[:, None],
+        noise['stoch'][:, None])
+    logits = m.head(m.feat2tensor(deter, stoch), 'pol', cfg.pol_layers, 'action/logits')
+    act = torch.argmax(logits + noise['action'], -1).to(torch.int32)
+    out = {'dyn/deter': deter.to(f32), 'dyn/stoch': stoch.to(f32)}   # _take_outs upcast, jax/agent.py:399-403
+    return (deter, stoch, act), {'action': act}, out
+
+  # ---------------------------------------------------------------------- train
+  def _apply_replay_context(self, carry, data):              # agent.py:312-340
+    K = self.cfg.replay_context
+    deter, stoch, prevact = carry
+    obs = {k: data[k] for k in ('image', 'reward', 'is_first', 'is_last', 'is_terminal')}
+    act = data['action']
+    if not K:
+      pa = torch.cat([prevact[:, None], act[:, :-1]], 1)
+      return (deter, stoch), obs, pa, data['stepid']
+    first = data['consec'][:, 0] == 0
+    rep_deter = data['dyn/deter'][:, K - 1].to(self.cd)
+    rep_stoch = data['dyn/stoch'][:, K - 1].to(self.cd)
+    normal_pa = torch.cat([prevact[:, None], act[:, :-1]], 1)[:, K:]
+    rep_pa = act[:, K - 1: -1]
+    deter = torch.where(first[:, None], rep_deter, deter)
+    stoch = torch.where(first[:, None, None], rep_stoch, stoch)
+    pa = torch.where(first[:, None], rep_pa, normal_pa)
+    obs = {k: v[:, K:] for k, v in obs.items()}
+    return (deter, stoch), obs, pa, data['stepid'][:, K:]
+
+  def make_noise(self, B, T):
+    cfg, dev, H = self.cfg, self.device, self.cfg.imag_length
+    return dict(
+        observe=modellib.gumbel_like((B, T, cfg.stoch, cfg.classes), dev, self.gen),
+        imag_stoch=modellib.gumbel_like((B * T, H, cfg.stoch, cfg.classes), dev, self.gen),
+        imag_act=modellib.gumbel_like((B * T, H + 1, cfg.actions), dev, self.gen))
+
+  def train(self, carry, data, noise=None):                  # agent.py:137-154, opt.py:31-81
+    carry, obs, prevact, stepid = self._apply_replay_context(carry, data)
+    B, T = obs['is_first'].shape
+    if noise is None:
+      noise = self.make_noise(B, T)
+    self.store.begin_step()
+    self.store.grad.zero_()
+    total, carry, outs, metrics = self.model.loss(carry, obs, prevact, noise, update=True)
+    total.backward()
+    if self.world > 1:
+      torch.distributed.all_reduce(self.store.grad, op=torch.distributed.ReduceOp.AVG)
+    metrics.update(self.opt.step())
+    self.opt.update_slow()
+    self.store.begin_step()
+    self.updates += 1
+    metrics['loss'] = total.detach()
+    feat = outs['feat']
+    replay = {'stepid': stepid, 'dyn/deter': feat['deter'].detach().to(f32),
+              'dyn/stoch': feat['stoch'].detach().to(f32)}
+    self.last_outs = outs
+    carry = (carry[0].detach(), carry[1].detach(), data['action'][:, -1])
+    return carry, {'replay': replay}, metrics
+
+  @torch.no_grad()
+  def report(self, carry, data, noise=None):                 # agent.py:247-310 (metrics part)
+    carry, obs, prevact, _ = self._apply_replay_context(carry, data)
+    B, T = obs['is_first'].shape
+    if noise is None:
+      noise = self.make_noise(B, T)
+    self.store.begin_step()
+    total, carry, outs, metrics = self.model.loss(carry, obs, prevact, noise, update=False)
+    self.store.begin_step()
+    metrics['loss'] = total
+    carry = (carry[0], carry[1], data['action'][:, -1])
+    return carry, metrics
+
+  def stream(self, st):
+    """Batches from Replay.sample are already dense device tensors; the
+    reference's device_put + NaN scan (jax/agent.py:326-337) has nothing to do."""
+    return st
+
+  def save(self):
+    data = self.store.state_dict()
+    data['retnorm/lo'] = self.model.ret_lo.cpu().numpy()
+    data['retnorm/hi'] = self.model.ret_hi.cpu().numpy()
+    data['updates'] = np.asarray(self.updates)
+    return data
+
+  def load(self, data, regex=None):
+    self.store.load_state_dict(data)
+    if 'retnorm/lo' in data:
+      self.model.ret_lo = torch.as_tensor(data['retnorm/lo'], device=self.device)
+      self.model.ret_hi = torch.as_tensor(data['retnorm/hi'], device=self.device)
+    self.updates = int(data.get('updates', 0))
+
+  def _gathered_percentiles(self, q, x):                     # utils.py:83-88
+    cfg = self.cfg
+    parts = [torch.empty_like(x) for _ in range(self.world)]
+    torch.distributed.all_gather(parts, x.contiguous())
+    allx = torch.cat(parts)
+    return torch.quantile(allx, torch.tensor(
+        [cfg.perclo / 100, cfg.perchi / 100], device=x.device, dtype=f32))

@@ -1,0 +1,396 @@
+"""DreamerV3 world model + actor-critic losses on the device.
+
+Math follows dreamerv3/rssm.py and dreamerv3/agent.py of the reference (cited
+per function); structure is chosen for the B200:
+
+* everything that does not depend on the recurrent state is hoisted out of the
+  T-step scan and done as one (B*T)-row GEMM: the action branch `dynin2`
+  (rssm.py:145-146) and the token half of `obs0` (rssm.py:83-85);
+* imagination (rssm.py:94-118) is forward-only -- `imgfeat` is stop-gradient'ed
+  (agent.py:195, ac_grads False) and actions are integer samples -- so it runs
+  under no_grad and keeps no activations;
+* parameters are views of one flat buffer (params.py), gradients accumulate in
+  place into one flat buffer that NCCL reduces with a single call;
+* sampling noise is an explicit input (Gumbel tensors), generated on the device
+  by default and injectable for parity tests.
+
+Compute dtype is bfloat16 (the reference default, embodied/jax/nets.py:12) or
+float32 (parity); norms, softmaxes and losses are always float32
+(nets.py:372, outs.py:209,276).
+"""
+import torch
+import torch.nn.functional as F
+
+f32 = torch.float32
+
+
+def silu(x):
+  return F.silu(x)
+
+
+def symexp(x):
+  return torch.sign(x) * torch.expm1(torch.abs(x))
+
+
+def gumbel_like(shape, device, generator=None):
+  u = torch.rand(shape, device=device, dtype=f32, generator=generator)
+  u.clamp_(1e-20, 1 - 1e-7)
+  return -torch.log(-torch.log(u))
+
+
+class Model:
+
+  def __init__(self, cfg, store):
+    self.cfg = cfg
+    self.store = store
+    self.cd = store.compute_dtype
+    self.device = store.device
+    n = cfg.bins
+    half = symexp(torch.linspace(-20, 0, (n - 1) // 2 + 1, dtype=f32))
+    self.bins = torch.cat([half, -half[:-1].flip(0)], 0).to(self.device)   # heads.py:132-144
+    self.ret_lo = torch.zeros((), dtype=f32, device=self.device)
+    self.ret_hi = torch.zeros((), dtype=f32, device=self.device)
+
+  # ---------------------------------------------------------------- primitives
+  def W(self, name):
+    return self.store.get(name)
+
+  def dense(self, x, name):                                  # nets.py:239-247
+    w, b = self.W(f'{name}/kernel'), self.W(f'{name}/bias')
+    return torch.addmm(b, x.reshape(-1, x.shape[-1]), w).reshape(*x.shape[:-1], -1)
+
+  def block(self, x, name):                                  # nets.py:267-278
+    w, b = self.W(f'{name}/kernel'), self.W(f'{name}/bias')
+    g = w.shape[0]
+    lead = x.shape[:-1]
+    x = x.reshape(-1, g, x.shape[-1] // g).transpose(0, 1)   # (g, M, in/g)
+    y = torch.bmm(x, w).transpose(0, 1)                      # (M, g, out/g)
+    return y.reshape(*lead, -1) + b
+
+  def norm(self, x, name, act=True):                         # nets.py:369-399 'rms', eps 1e-4
+    scale = self.store.w[f'{name}/scale']
+    xf = x.to(f32)
+    y = xf * (torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-4) * scale)
+    y = y.to(self.cd)
+    return silu(y) if act else y
+
+  def conv(self, x, name):                                   # nets.py:298-323; x is NHWC
+    w = self.W(f'{name}/kernel').permute(3, 2, 0, 1)         # HWIO -> OIHW
+    b = self.W(f'{name}/bias')
+    y = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=w.shape[-1] // 2)
+    return y.permute(0, 2, 3, 1)                             # NHWC view (channels_last memory)
+
+  def mlp(self, x, name, layers, params=None):               # nets.py:580-587
+    for i in range(layers):
+      x = self.dense(x, f'{name}/mlp/linear{i}')
+      x = self.norm(x, f'{name}/mlp/norm{i}')
+    return x
+
+  # -------------------------------------------------------------------- encoder
+  def encoder(self, image, normalized=None):                 # rssm.py:226-246 (image keys)
+    """image: uint8 (..., H, W, C) or `normalized` float32 x/255-0.5 already
+    produced by emb_driver_stage_obs."""
+    cfg = self.cfg
+    if normalized is None:
+      x = image.to(f32) / 255 - 0.5
+    else:
+      x = normalized
+    lead = x.shape[:-3]
+    x = x.reshape(-1, *x.shape[-3:]).to(self.cd)
+    for i in range(len(cfg.mults)):
+      x = self.conv(x, f'enc/cnn{i}')
+      x = F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+      x = self.norm(x, f'enc/cnn{i}norm')
+    return x.reshape(*lead, -1)
+
+  # ----------------------------------------------------------------------- rssm
+  def action_embed(self, action, reset):
+    """DictConcat one-hot (nets.py:467-500) with the reset mask of
+    rssm.py:76-79, then `action / max(1, |action|)` (rssm.py:137)."""
+    a = F.one_hot(action.long(), self.cfg.actions).to(self.cd)
+    return a * (~reset)[..., None].to(self.cd)
+
+  def core(self, deter, stoch_flat, x2):                     # rssm.py:135-159
+    """x2 = silu(rms(dynin2(action))) is precomputed by the caller."""
+    g = self.cfg.blocks
+    x0 = self.norm(self.dense(deter, 'dyn/dynin0'), 'dyn/dynin0norm')
+    x1 = self.norm(self.dense(stoch_flat, 'dyn/dynin1'), 'dyn/dynin1norm')
+    x = torch.cat([x0, x1, x2], -1)[:, None, :].expand(-1, g, -1)
+    x = torch.cat([deter.reshape(len(deter), g, -1), x], -1).reshape(len(deter), -1)
+    x = self.norm(self.block(x, 'dyn/dynhid0'), 'dyn/dynhid0norm')
+    x = self.block(x, 'dyn/dyngru')
+    reset, cand, update = [
+        y.reshape(len(x), -1) for y in x.reshape(len(x), g, -1).chunk(3, -1)]
+    reset = torch.sigmoid(reset)
+    cand = torch.tanh(reset * cand)
+    update = torch.sigmoid(update - 1)
+    return update * cand + (1 - update) * deter
+
+  def unimix(self, logit):                                   # outs.py:210-216
+    probs = torch.softmax(logit.to(f32), -1)
+    return (1 - self.cfg.unimix) * probs + self.cfg.unimix / probs.shape[-1]
+
+  def sample_stoch(self, logit, gumbel):                     # outs.py:252-270
+    probs = self.unimix(logit)
+    index = torch.argmax(torch.log(probs) + gumbel, -1)
+    value = F.one_hot(index, probs.shape[-1]).to(f32)
+    return (value + (probs - probs.detach())).to(self.cd)
+
+  def act_branch(self, action, reset):
+    a = self.action_embed(action, reset)
+    return self.norm(self.dense(a, 'dyn/dynin2'), 'dyn/dynin2norm')
+
+  def observe(self, carry, tokens, prevact, reset, gumbel):  # rssm.py:61-92
+    """carry: (deter (B,D), stoch (B,S,C)); tokens (B,T,E); prevact (B,T) int;
+    reset (B,T) bool; gumbel (B,T,S,C) f32.  Returns the new carry and
+    deter (B,T,D), stoch (B,T,S,C), logit (B,T,S,C)."""
+    cfg = self.cfg
+    B, T = reset.shape
+    D = cfg.deter
+    x2 = self.act_branch(prevact, reset)                     # (B,T,H) hoisted
+    wobs, bobs = self.W('dyn/obs0/kernel'), self.W('dyn/obs0/bias')
+    tok = torch.addmm(bobs, tokens.reshape(B * T, -1), wobs[D:]).reshape(B, T, -1)
+    deter, stoch = carry
+    deter, stoch = deter.to(self.cd), stoch.to(self.cd)
+    deters, stochs, logits = [], [], []
+    for t in range(T):
+      keep = (~reset[:, t]).to(self.cd)
+      deter = deter * keep[:, None]
+      stoch = stoch * keep[:, None, None]
+      deter = self.core(deter, stoch.reshape(B, -1), x2[:, t])
+      x = self.norm(deter @ wobs[:D] + tok[:, t], 'dyn/obs0norm')
+      logit = self.dense(x, 'dyn/obslogit').reshape(B, cfg.stoch, cfg.classes)
+      stoch = self.sample_stoch(logit, gumbel[:, t])
+      deters.append(deter); stochs.append(stoch); logits.append(logit)
+    feat = dict(deter=torch.stack(deters, 1), stoch=torch.stack(stochs, 1),
+                logit=torch.stack(logits, 1))
+    return (deter, stoch), feat
+
+  def prior(self, deter):                                    # rssm.py:161-171
+    x = deter
+    for i in range(self.cfg.imglayers):
+      x = self.norm(self.dense(x, f'dyn/prior{i}'), f'dyn/prior{i}norm')
+    x = self.dense(x, 'dyn/priorlogit')
+    return x.reshape(*x.shape[:-1], self.cfg.stoch, self.cfg.classes)
+
+  def kl_losses(self, post_logit, prior_logit):              # rssm.py:123-132, outs.py:236-240
+    """dyn = max(KL(sg(post) || prior), free), rep = max(KL(post || sg(prior)), free),
+    both on unimixed distributions, summed over the S latents."""
+    cfg = self.cfg
+    post = torch.log(self.unimix(post_logit))
+    prior = torch.log(self.unimix(prior_logit))
+
+    def kl(a, b):
+      la, lb = torch.log_softmax(a, -1), torch.log_softmax(b, -1)
+      return (torch.softmax(a, -1) * (la - lb)).sum(-1).sum(-1)
+
+    def ent(a):
+      la = torch.log_softmax(a, -1)
+      return -(torch.softmax(a, -1) * la).sum(-1).sum(-1)
+    dyn = torch.clamp(kl(post.detach(), prior), min=cfg.free_nats)
+    rep = torch.clamp(kl(post, prior.detach()), min=cfg.free_nats)
+    mets = dict(dyn_ent=ent(prior.detach()).mean(), rep_ent=ent(post.detach()).mean())
+    return dyn, rep, mets
+
+  # -------------------------------------------------------------------- decoder
+  def decoder(self, deter, stoch):                           # rssm.py:288-359 (image key)
+    cfg = self.cfg
+    lead = deter.shape[:-1]
+    depths = [cfg.depth * m for m in cfg.mults]
+    minres = cfg.image[0] // 2 ** len(cfg.mults)
+    g, c = cfg.bspace, depths[-1] // cfg.bspace
+    x0 = deter.reshape(-1, deter.shape[-1])
+    x1 = stoch.reshape(x0.shape[0], -1)
+    x0 = self.block(x0, 'dec/sp0')
+    x0 = x0.reshape(-1, g, minres, minres, c).permute(0, 2, 3, 1, 4).reshape(
+        -1, minres, minres, g * c)                           # '(g h w c) -> h w (g c)'
+    x1 = self.norm(self.dense(x1, 'dec/sp1'), 'dec/sp1norm')
+    x1 = self.dense(x1, 'dec/sp2').reshape(-1, minres, minres, depths[-1])
+    x = self.norm(x0 + x1, 'dec/spnorm')
+    for i in reversed(range(len(depths) - 1)):
+      x = self.upsample(x)
+      x = self.norm(self.conv(x, f'dec/conv{i}'), f'dec/conv{i}norm')
+    x = torch.sigmoid(self.conv(self.upsample(x), 'dec/imgout').to(f32))
+    return x.reshape(*lead, *x.shape[1:])
+
+  @staticmethod
+  def upsample(x):                                           # x.repeat(2,-2).repeat(2,-3)
+    y = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode='nearest')
+    return y.permute(0, 2, 3, 1)
+
+  # ---------------------------------------------------------------------- heads
+  def feat2tensor(self, deter, stoch):                       # agent.py:51-53
+    return torch.cat([deter.to(self.cd), stoch.reshape(*stoch.shape[:-2], -1).to(self.cd)], -1)
+
+  def head(self, x, name, layers, out):                      # heads.py:34-41
+    return self.dense(self.mlp(x, name, layers), f'{name}/head/{out}').to(f32)
+
+  def slow_value_logits(self, x):
+    """The slow critic (utils.py:94-127): val's architecture, slow parameters."""
+    slow = self.store.slow
+    with torch.no_grad():
+      for i in range(self.cfg.val_layers):
+        w = slow[f'slowval/mlp/linear{i}/kernel'].to(self.cd)
+        b = slow[f'slowval/mlp/linear{i}/bias'].to(self.cd)
+        x = torch.addmm(b, x.reshape(-1, x.shape[-1]), w).reshape(*x.shape[:-1], -1)
+        xf = x.to(f32)
+        x = silu((xf * (torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-4) *
+                        slow[f'slowval/mlp/norm{i}/scale'])).to(self.cd))
+      w = slow['slowval/head/logits/kernel'].to(self.cd)
+      b = slow['slowval/head/logits/bias'].to(self.cd)
+      return torch.addmm(b, x.reshape(-1, x.shape[-1]), w).reshape(
+          *x.shape[:-1], -1).to(f32)
+
+  def twohot_pred(self, logits):                             # outs.py:285-302 (symmetric sum)
+    probs = torch.softmax(logits, -1)
+    bins = self.bins
+    m = (logits.shape[-1] - 1) // 2
+    p1, p2, p3 = probs[..., :m], probs[..., m: m + 1], probs[..., m + 1:]
+    b1, b2, b3 = bins[:m], bins[m: m + 1], bins[m + 1:]
+    return (p2 * b2).sum(-1) + ((p1 * b1).flip(-1) + (p3 * b3)).sum(-1)
+
+  def twohot_loss(self, logits, target):                     # outs.py:311-330
+    bins, n = self.bins, len(self.bins)
+    target = target.detach().to(f32)
+    below = (bins <= target[..., None]).sum(-1) - 1
+    above = n - (bins > target[..., None]).sum(-1)
+    below = below.clamp(0, n - 1)
+    above = above.clamp(0, n - 1)
+    equal = below == above
+    one = torch.ones_like(target)
+    to_below = torch.where(equal, one, (bins[below] - target).abs())
+    to_above = torch.where(equal, one, (bins[above] - target).abs())
+    total = to_below + to_above
+    logp = logits - torch.logsumexp(logits, -1, keepdim=True)
+    lb = logp.gather(-1, below[..., None]).squeeze(-1)
+    la = logp.gather(-1, above[..., None]).squeeze(-1)
+    return -(lb * (to_above / total) + la * (to_below / total))
+
+  @staticmethod
+  def lambda_return(last, term, rew, val, boot, disc, lam):  # agent.py:482-490
+    live = (1 - term.to(f32))[:, 1:] * disc
+    cont = (1 - last.to(f32))[:, 1:] * lam
+    interm = rew[:, 1:] + (1 - cont) * live * boot[:, 1:]
+    rets = [boot[:, -1]]
+    for t in reversed(range(live.shape[1])):
+      rets.append(interm[:, t] + live[:, t] * cont[:, t] * rets[-1])
+    return torch.stack(list(reversed(rets))[:-1], 1)
+
+  def retnorm(self, ret, update):                            # utils.py:37-77 'perc', debias False
+    cfg = self.cfg
+    if update:
+      x = ret.detach().to(f32).flatten()
+      q = torch.quantile(x, torch.tensor(
+          [cfg.perclo / 100, cfg.perchi / 100], device=x.device, dtype=f32))
+      q = self.reduce_percentiles(q, x)
+      r = cfg.retnorm_rate
+      self.ret_lo = (1 - r) * self.ret_lo + r * q[0]
+      self.ret_hi = (1 - r) * self.ret_hi + r * q[1]
+    return self.ret_lo, torch.clamp(self.ret_hi - self.ret_lo, min=cfg.retnorm_limit)
+
+  def reduce_percentiles(self, q, x):
+    """Multi-rank hook: utils.py:83-88 all_gathers the returns before the
+    percentile.  Replaced by the Agent when world_size > 1."""
+    return q
+
+  # ----------------------------------------------------------------- imagination
+  @torch.no_grad()
+  def imagine(self, deter, stoch, noise_stoch, noise_act):   # rssm.py:94-118, agent.py:188-200
+    """From B*K start states roll H steps with the policy in the loop.  Returns
+    deter (BK,H+1,D), stoch (BK,H+1,S,C), action (BK,H+1)."""
+    cfg = self.cfg
+    H = cfg.imag_length
+    n = len(deter)
+    never = torch.zeros(n, dtype=torch.bool, device=deter.device)
+    deters, stochs, acts = [deter], [stoch], []
+    for h in range(H):
+      logits = self.head(self.feat2tensor(deter, stoch), 'pol', cfg.pol_layers, 'action/logits')
+      a = torch.argmax(logits + noise_act[:, h], -1)
+      x2 = self.act_branch(a, never)
+      deter = self.core(deter, stoch.reshape(n, -1), x2)
+      stoch = self.sample_stoch(self.prior(deter), noise_stoch[:, h])
+      acts.append(a); deters.append(deter); stochs.append(stoch)
+    logits = self.head(self.feat2tensor(deter, stoch), 'pol', cfg.pol_layers, 'action/logits')
+    acts.append(torch.argmax(logits + noise_act[:, H], -1))
+    return torch.stack(deters, 1), torch.stack(stochs, 1), torch.stack(acts, 1)
+
+  # ------------------------------------------------------------------------ loss
+  def loss(self, carry, obs, prevact, noise, update=True):   # agent.py:156-245
+    cfg = self.cfg
+    reset = obs['is_first']
+    B, T = reset.shape
+    losses, metrics = {}, {}
+    tokens = self.encoder(obs['image'])
+    carry, feat = self.observe(carry, tokens, prevact, reset, noise['observe'])
+    dyn, rep, mets = self.kl_losses(feat['logit'], self.prior(feat['deter']))
+    losses['dyn'], losses['rep'] = dyn, rep
+    metrics.update(mets)
+    recon = self.decoder(feat['deter'], feat['stoch'])
+    inp = self.feat2tensor(feat['deter'], feat['stoch'])
+    losses['rew'] = self.twohot_loss(
+        self.head(inp, 'rew', cfg.rew_layers, 'logits'), obs['reward'])
+    con = (~obs['is_terminal']).to(f32)
+    if cfg.contdisc:
+      con = con * (1 - 1 / cfg.horizon)
+    clogit = self.head(inp, 'con', cfg.con_layers, 'logit').squeeze(-1)
+    losses['con'] = -(con * F.logsigmoid(clogit) + (1 - con) * F.logsigmoid(-clogit))
+    target = obs['image'].to(f32) / 255
+    losses['image'] = (recon - target).square().sum((-3, -2, -1))
+
+    K, H = T, cfg.imag_length
+    imgdeter, imgstoch, imgact = self.imagine(
+        feat['deter'].detach().reshape(B * K, -1),
+        feat['stoch'].detach().reshape(B * K, cfg.stoch, cfg.classes),
+        noise['imag_stoch'], noise['imag_act'])
+    los, ret, mets = self.imag_loss(imgact, self.feat2tensor(imgdeter, imgstoch), update)
+    losses.update({k: v.mean(1).reshape(B, K) for k, v in los.items()})
+    metrics.update(mets)
+
+    # replay value loss (agent.py:219-235, repl_loss :449-479)
+    boot = ret[:, 0].reshape(B, K)
+    vlogits = self.head(inp, 'val', cfg.val_layers, 'logits')
+    val = self.twohot_pred(vlogits)
+    slow = self.twohot_pred(self.slow_value_logits(inp.detach()))
+    rret = self.lambda_return(
+        obs['is_last'], obs['is_terminal'], obs['reward'].to(f32), val, boot,
+        1 - 1 / cfg.horizon, cfg.lam)
+    padded = torch.cat([rret, 0 * rret[:, -1:]], 1)
+    weight = (~obs['is_last']).to(f32)
+    losses['repval'] = weight[:, :-1] * (
+        self.twohot_loss(vlogits, padded) +
+        cfg.slowreg * self.twohot_loss(vlogits, slow))[:, :-1]
+
+    assert set(losses) == set(cfg.scales), (sorted(losses), sorted(cfg.scales))
+    metrics.update({f'loss/{k}': v.detach().mean() for k, v in losses.items()})
+    total = sum(v.mean() * cfg.scales[k] for k, v in losses.items())
+    outs = dict(tokens=tokens, feat=feat, losses=losses, recon=recon,
+                imgdeter=imgdeter, imgstoch=imgstoch, imgact=imgact, ret=ret)
+    return total, carry, outs, metrics
+
+  def imag_loss(self, act, inp, update):                     # agent.py:382-446
+    cfg = self.cfg
+    with torch.no_grad():
+      rew = self.twohot_pred(self.head(inp, 'rew', cfg.rew_layers, 'logits'))
+      con = torch.sigmoid(self.head(inp, 'con', cfg.con_layers, 'logit').squeeze(-1))
+      slowval = self.twohot_pred(self.slow_value_logits(inp))
+    pol = self.head(inp, 'pol', cfg.pol_layers, 'action/logits')
+    vlogits = self.head(inp, 'val', cfg.val_layers, 'logits')
+    val = self.twohot_pred(vlogits).detach()
+    disc = 1 if cfg.contdisc else 1 - 1 / cfg.horizon
+    weight = torch.cumprod(disc * con, 1) / disc
+    ret = self.lambda_return(torch.zeros_like(con), 1 - con, rew, val, val, disc, cfg.lam)
+    roffset, rscale = self.retnorm(ret, update)
+    adv = (ret - val[:, :-1]) / rscale
+    logp_all = torch.log_softmax(pol, -1)
+    logpi = logp_all.gather(-1, act[..., None]).squeeze(-1)[:, :-1]
+    ent = -(torch.softmax(pol, -1) * logp_all).sum(-1)[:, :-1]
+    losses = {}
+    losses['policy'] = weight[:, :-1] * -(logpi * adv + cfg.actent * ent)
+    padded = torch.cat([ret, 0 * ret[:, -1:]], 1)
+    losses['value'] = weight[:, :-1] * (
+        self.twohot_loss(vlogits, padded) +
+        cfg.slowreg * self.twohot_loss(vlogits, slowval))[:, :-1]
+    ret_normed = (ret - roffset) / rscale
+    mets = dict(adv=adv.mean(), rew=rew.mean(), con=con.mean(), ret=ret_normed.mean(),
+                val=val.mean(), weight=weight.mean(), ent=ent.detach().mean())
+    return losses, ret, mets

@@ -1,0 +1,183 @@
+"""Parameter storage of the dreamerv3 learner, laid out for the B200.
+
+All optimised parameters live in ONE float32 device buffer (`master`), each
+tensor at a 64-byte aligned offset; gradients (`grad`), RMS (`nu`) and momentum
+(`mu`) state are three more buffers of the same layout.  That makes the
+gradient all-reduce one NCCL call on one pointer and the optimiser one fused
+launch over the flat buffer (embodied/jax/opt.py:31-81 applies the optax chain
+tensor by tensor).  The model casts a weight to the compute dtype where it is
+used, as the reference does (embodied/jax/nets.py:243,272,301); the cast's
+backward adds the bf16 gradient into the float32 `grad` view.
+
+Names and shapes follow the reference's ninjax paths ('dyn/dynin0/kernel',
+'enc/cnn0norm/scale', ...) so checkpoints are interchangeable key for key.
+Initialisation: trunc_normal(-2, 2) * 1.1368 / sqrt(fan_in) * outscale, zero
+biases, unit norm scales (embodied/jax/nets.py:144-197, 236-251).
+"""
+import math
+
+import numpy as np
+import torch
+
+ALIGN = 16   # elements (64 B in fp32)
+
+
+def shapes(cfg):
+  """name -> (shape, fan_in or None, outscale).  Order is the storage order."""
+  D, H, S, C, g = cfg.deter, cfg.hidden, cfg.stoch, cfg.classes, cfg.blocks
+  U, A, k = cfg.units, cfg.actions, cfg.kernel
+  depths = [cfg.depth * m for m in cfg.mults]
+  minres = cfg.image[0] // 2 ** len(cfg.mults)
+  sp = minres * minres * depths[-1]
+  out = {}
+
+  def dense(name, i, o, outscale=1.0):
+    out[f'{name}/kernel'] = ((i, o), i, outscale)
+    out[f'{name}/bias'] = ((o,), None, 0.0)
+
+  def block(name, i, o):
+    out[f'{name}/kernel'] = ((g, i // g, o // g), i, 1.0)
+    out[f'{name}/bias'] = ((o,), None, 0.0)
+
+  def conv(name, i, o):
+    out[f'{name}/kernel'] = ((k, k, i, o), k * k * i, 1.0)
+    out[f'{name}/bias'] = ((o,), None, 0.0)
+
+  def norm(name, n):
+    out[f'{name}/scale'] = ((n,), None, None)
+
+  # dyn first: the scan kernels want these contiguous
+  dense('dyn/dynin0', D, H); norm('dyn/dynin0norm', H)
+  dense('dyn/dynin1', S * C, H); norm('dyn/dynin1norm', H)
+  dense('dyn/dynin2', A, H); norm('dyn/dynin2norm', H)
+  block('dyn/dynhid0', D + g * 3 * H, D); norm('dyn/dynhid0norm', D)
+  block('dyn/dyngru', D, 3 * D)
+  dense('dyn/obs0', D + sp, H); norm('dyn/obs0norm', H)
+  dense('dyn/obslogit', H, S * C)
+  dense('dyn/prior0', D, H); norm('dyn/prior0norm', H)
+  dense('dyn/prior1', H, H); norm('dyn/prior1norm', H)
+  dense('dyn/priorlogit', H, S * C)
+  cin = cfg.image[2]
+  for i, d in enumerate(depths):
+    conv(f'enc/cnn{i}', cin, d); norm(f'enc/cnn{i}norm', d); cin = d
+  block('dec/sp0', D, sp)
+  dense('dec/sp1', S * C, 2 * U); norm('dec/sp1norm', 2 * U)
+  dense('dec/sp2', 2 * U, sp)
+  norm('dec/spnorm', depths[-1])
+  cin = depths[-1]
+  for i in reversed(range(len(depths) - 1)):
+    conv(f'dec/conv{i}', cin, depths[i]); norm(f'dec/conv{i}norm', depths[i])
+    cin = depths[i]
+  conv('dec/imgout', cin, cfg.image[2])
+  feat = D + S * C
+
+  def head(name, layers, outname, outdim, outscale):
+    i = feat
+    for l in range(layers):
+      dense(f'{name}/mlp/linear{l}', i, U); norm(f'{name}/mlp/norm{l}', U); i = U
+    dense(f'{name}/head/{outname}', U, outdim, outscale)
+
+  head('rew', cfg.rew_layers, 'logits', cfg.bins, 0.0)
+  head('con', cfg.con_layers, 'logit', 1, 1.0)
+  head('pol', cfg.pol_layers, 'action/logits', A, 0.01)
+  head('val', cfg.val_layers, 'logits', cfg.bins, 0.0)
+  return out
+
+
+class ParamStore:
+
+  def __init__(self, cfg, device, compute_dtype, seed=0, values=None):
+    self.device = torch.device(device)
+    self.compute_dtype = compute_dtype
+    self.specs = shapes(cfg)
+    self.offsets, total = {}, 0
+    for name, (shape, _, _) in self.specs.items():
+      self.offsets[name] = total
+      total += (int(np.prod(shape)) + ALIGN - 1) // ALIGN * ALIGN
+    self.total = total
+    self.count = sum(int(np.prod(s[0])) for s in self.specs.values())
+    f32 = torch.float32
+    self.master = torch.zeros(total, dtype=f32, device=self.device)
+    self.grad = torch.zeros(total, dtype=f32, device=self.device)
+    self.nu = torch.zeros(total, dtype=f32, device=self.device)
+    self.mu = torch.zeros(total, dtype=f32, device=self.device)
+    self.step = 0
+    # segment table for the per-tensor AGC norms of the fused optimiser
+    names = list(self.specs)
+    self.seg_begin = torch.tensor(
+        [self.offsets[n] for n in names], dtype=torch.int64, device=self.device)
+    self.seg_size = torch.tensor(
+        [int(np.prod(self.specs[n][0])) for n in names], dtype=torch.int64,
+        device=self.device)
+    self._init(seed, values)
+    # autograd leaves: float32 views of `master` whose .grad are views of
+    # `grad`, so backward accumulates straight into the flat gradient buffer.
+    self.w = {}
+    for name in names:
+      leaf = self._view(self.master, name).requires_grad_(True)
+      leaf.grad = self._view(self.grad, name)
+      self.w[name] = leaf
+    self._cast = {}
+    # slow value network (utils.py:94-127): a separate small buffer
+    self.slow = {n.replace('val/', 'slowval/', 1): self.view('master', n).clone()
+                 for n in names if n.startswith('val/')}
+
+  def _view(self, buf, name):
+    shape = self.specs[name][0]
+    off = self.offsets[name]
+    return buf[off: off + int(np.prod(shape))].view(shape)
+
+  def view(self, which, name):
+    return self._view(getattr(self, which), name)
+
+  def _init(self, seed, values):
+    gen = torch.Generator().manual_seed(seed)
+    for name, (shape, fan, outscale) in self.specs.items():
+      if values is not None:
+        x = torch.as_tensor(np.asarray(values[name]), dtype=torch.float32)
+        assert tuple(x.shape) == tuple(shape), (name, x.shape, shape)
+      elif name.endswith('/scale'):
+        x = torch.ones(shape)
+      elif fan is None:
+        x = torch.zeros(shape)
+      else:
+        x = torch.empty(shape)
+        torch.nn.init.trunc_normal_(x, 0.0, 1.0, -2.0, 2.0, generator=gen)
+        x = x * (1.1368 * math.sqrt(1 / fan) * outscale)
+      self.view('master', name).copy_(x)
+
+  def get(self, name):
+    """The parameter in the compute dtype (cast once per step; the cast is part
+    of the autograd graph, so bf16 gradients land in the f32 buffer as in
+    embodied/jax/nets.py:243)."""
+    if self.compute_dtype == torch.float32:
+      return self.w[name]
+    hit = self._cast.get(name)
+    if hit is None:
+      hit = self._cast[name] = self.w[name].to(self.compute_dtype)
+    return hit
+
+  def begin_step(self):
+    self._cast.clear()
+
+  def named_grads(self):
+    return {n: self.view('grad', n) for n in self.specs}
+
+  def state_dict(self):
+    out = {n: self.view('master', n).cpu().numpy() for n in self.specs}
+    out.update({n: v.cpu().numpy() for n, v in self.slow.items()})
+    out['opt/nu'] = self.nu.cpu().numpy()
+    out['opt/mu'] = self.mu.cpu().numpy()
+    out['opt/step'] = np.asarray(self.step)
+    return out
+
+  def load_state_dict(self, data):
+    for n in self.specs:
+      self.view('master', n).copy_(torch.as_tensor(data[n]))
+    for n in self.slow:
+      self.slow[n].copy_(torch.as_tensor(data[n]))
+    if 'opt/nu' in data:
+      self.nu.copy_(torch.as_tensor(data['opt/nu']))
+      self.mu.copy_(torch.as_tensor(data['opt/mu']))
+      self.step = int(data['opt/step'])
+    self._cast.clear()

@@ -1,0 +1,603 @@
+"""fp32 torch-CPU restatement of the reference's dreamerv3 math (TEST INFRASTRUCTURE).
+
+PARITY UNPINNED: the reference holds no test or golden tensor for dreamerv3
+ and JAX/ninjax/optax cannot be installed in this image, so
+this file cannot be checked against the running original.  It restates, line by
+line, the code cited below; sampling noise is INJECTED (Gumbel tensors) so that
+the product kernels and this file can be compared on identical draws
+(jax.random.categorical(key, l) == argmax(l + gumbel(key))).
+
+Restated here (reference file:line):
+  linear / block_linear / conv / rms      embodied/jax/nets.py:230-251, 254-281, 284-323, 361-399
+  onehot_dist (unimix, straight-through)  embodied/jax/outs.py:208-270
+  twohot (bins, symmetric pred, loss)     embodied/jax/heads.py:132-144, outs.py:273-330
+  binary                                   embodied/jax/outs.py:189-205
+  Encoder / Decoder                        dreamerv3/rssm.py:210-250, 288-359
+  RSSM core / observe / prior / loss       dreamerv3/rssm.py:61-92, 120-176
+  RSSM imagine                             dreamerv3/rssm.py:94-118
+  Agent.loss / policy / replay context     dreamerv3/agent.py:115-135, 156-245, 312-340
+  imag_loss / repl_loss / lambda_return    dreamerv3/agent.py:382-490
+  Normalize('perc')                        embodied/jax/utils.py:16-91
+  optimizer chain                          embodied/jax/opt.py:109-164, dreamerv3/agent.py:342-379
+  SlowModel.update                         embodied/jax/utils.py:113-119
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+f32 = torch.float32
+
+
+class Config(dict):
+  __getattr__ = dict.__getitem__
+
+
+def default_config(**over):
+  """dreamerv3/configs.yaml:81-117 (size200m) as a flat dict."""
+  cfg = Config(
+      deter=8192, hidden=1024, stoch=32, classes=64, blocks=8, unimix=0.01,
+      free_nats=1.0, imglayers=2, obslayers=1, dynlayers=1,
+      depth=64, mults=(2, 3, 4, 4), kernel=5, units=1024, bspace=8,
+      image=(64, 64, 3), actions=5, bins=255,
+      rew_layers=1, con_layers=1, pol_layers=3, val_layers=3,
+      imag_length=15, horizon=333, contdisc=True, lam=0.95, actent=3e-4,
+      slowreg=1.0, slowrate=0.02, replay_context=1,
+      retnorm_rate=0.01, retnorm_limit=1.0, perclo=5.0, perchi=95.0,
+      scales=dict(image=1.0, rew=1.0, con=1.0, dyn=1.0, rep=0.1,
+                  policy=1.0, value=1.0, repval=0.3),
+      lr=4e-5, agc=0.3, eps=1e-20, beta1=0.9, beta2=0.999, warmup=1000,
+      pmin=1e-3)
+  cfg.update(over)
+  return cfg
+
+
+# ------------------------------------------------------------------ primitives
+def silu(x):
+  return x * torch.sigmoid(x)
+
+
+def rms(x, scale, eps=1e-4):                                   # nets.py:374-383
+  mean2 = (x * x).mean(-1, keepdim=True)
+  return x * (torch.rsqrt(mean2 + eps) * scale)
+
+
+def linear(p, name, x):                                         # nets.py:239-247
+  return x @ p[f'{name}/kernel'] + p[f'{name}/bias']
+
+
+def block_linear(p, name, x, g):                                # nets.py:267-278
+  k = p[f'{name}/kernel']                                       # (g, in/g, out/g)
+  x = x.reshape(*x.shape[:-1], g, x.shape[-1] // g)
+  x = torch.einsum('...ki,kio->...ko', x, k)
+  return x.reshape(*x.shape[:-2], -1) + p[f'{name}/bias']
+
+
+def conv(p, name, x):                                           # nets.py:298-323 (NHWC, HWIO, SAME)
+  k = p[f'{name}/kernel'].permute(3, 2, 0, 1)
+  y = F.conv2d(x.permute(0, 3, 1, 2), k, padding=k.shape[-1] // 2)
+  return y.permute(0, 2, 3, 1) + p[f'{name}/bias']
+
+
+def layer(p, name, x):
+  """Linear -> rms -> silu with the '<name>norm' scale (rssm.py:141-146 pattern)."""
+  return silu(rms(linear(p, name, x), p[f'{name}norm/scale']))
+
+
+def mlp(p, name, x, layers):                                    # nets.py:580-587
+  for i in range(layers):
+    x = linear(p, f'{name}/linear{i}', x)
+    x = silu(rms(x, p[f'{name}/norm{i}/scale']))
+  return x
+
+
+def unimix_logits(logits, unimix):                              # outs.py:210-216
+  probs = torch.softmax(logits, -1)
+  probs = (1 - unimix) * probs + unimix / probs.shape[-1]
+  return torch.log(probs)
+
+
+def onehot_sample(logits, unimix, gumbel):                      # outs.py:252-270
+  lg = unimix_logits(logits, unimix)
+  index = torch.argmax(lg + gumbel, -1)
+  value = F.one_hot(index, lg.shape[-1]).to(f32)
+  probs = torch.softmax(lg, -1)
+  return value + (probs - probs.detach())
+
+
+def cat_kl(a, b):                                               # outs.py:236-240 (+ Agg sum :73-76)
+  la, lb = torch.log_softmax(a, -1), torch.log_softmax(b, -1)
+  return (torch.softmax(a, -1) * (la - lb)).sum(-1).sum(-1)
+
+
+def cat_entropy(a):                                             # outs.py:230-234
+  la = torch.log_softmax(a, -1)
+  return -(torch.softmax(a, -1) * la).sum(-1)
+
+
+def symexp(x):
+  return torch.sign(x) * torch.expm1(torch.abs(x))
+
+
+def twohot_bins(n=255):                                         # heads.py:132-144
+  assert n % 2 == 1
+  half = symexp(torch.linspace(-20, 0, (n - 1) // 2 + 1, dtype=f32))
+  return torch.cat([half, -half[:-1].flip(0)], 0)
+
+
+def twohot_pred(logits, bins):                                  # outs.py:285-302
+  probs = torch.softmax(logits, -1)
+  n = logits.shape[-1]
+  m = (n - 1) // 2
+  p1, p2, p3 = probs[..., :m], probs[..., m: m + 1], probs[..., m + 1:]
+  b1, b2, b3 = bins[:m], bins[m: m + 1], bins[m + 1:]
+  return (p2 * b2).sum(-1) + ((p1 * b1).flip(-1) + (p3 * b3)).sum(-1)
+
+
+def twohot_loss(logits, bins, target):                          # outs.py:311-330
+  target = target.detach()
+  n = len(bins)
+  below = (bins <= target[..., None]).to(torch.int32).sum(-1) - 1
+  above = n - (bins > target[..., None]).to(torch.int32).sum(-1)
+  below = below.clamp(0, n - 1).long()
+  above = above.clamp(0, n - 1).long()
+  equal = below == above
+  one = torch.ones_like(target)
+  to_below = torch.where(equal, one, (bins[below] - target).abs())
+  to_above = torch.where(equal, one, (bins[above] - target).abs())
+  total = to_below + to_above
+  wb, wa = to_above / total, to_below / total
+  tgt = F.one_hot(below, n) * wb[..., None] + F.one_hot(above, n) * wa[..., None]
+  logp = logits - torch.logsumexp(logits, -1, keepdim=True)
+  return -(tgt * logp).sum(-1)
+
+
+def binary_logp(logit, event):                                  # outs.py:197-201
+  return event * F.logsigmoid(logit) + (1 - event) * F.logsigmoid(-logit)
+
+
+def lambda_return(last, term, rew, val, boot, disc, lam):       # agent.py:482-490
+  rets = [boot[:, -1]]
+  live = (1 - term.to(f32))[:, 1:] * disc
+  cont = (1 - last.to(f32))[:, 1:] * lam
+  interm = rew[:, 1:] + (1 - cont) * live * boot[:, 1:]
+  for t in reversed(range(live.shape[1])):
+    rets.append(interm[:, t] + live[:, t] * cont[:, t] * rets[-1])
+  return torch.stack(list(reversed(rets))[:-1], 1)
+
+
+# --------------------------------------------------------------------- model
+class Dreamer:
+  """`p`: dict name -> float32 torch CPU tensor in the reference's parameter
+  naming (ninjax paths: 'dyn/dynin0/kernel', 'enc/cnn0norm/scale', ...)."""
+
+  def __init__(self, cfg, params, slow=None, state=None):
+    self.cfg = cfg
+    self.p = params
+    self.slow = slow if slow is not None else {
+        k.replace('val/', 'slowval/', 1): v.detach().clone()
+        for k, v in params.items() if k.startswith('val/')}
+    self.bins = twohot_bins(cfg.bins)
+    self.state = state if state is not None else dict(
+        ret_lo=torch.zeros((), dtype=f32), ret_hi=torch.zeros((), dtype=f32),
+        step=0, nu={k: torch.zeros_like(v) for k, v in params.items()},
+        mu={k: torch.zeros_like(v) for k, v in params.items()})
+
+  # -- encoder (rssm.py:210-250, image keys only: config 2 has no vector obs) --
+  def encoder(self, image_u8):
+    p, cfg = self.p, self.cfg
+    x = image_u8.to(f32) / 255 - 0.5
+    lead = x.shape[:-3]
+    x = x.reshape(-1, *x.shape[-3:])
+    for i in range(len(cfg.mults)):
+      x = conv(p, f'enc/cnn{i}', x)
+      n, h, w, c = x.shape
+      x = x.reshape(n, h // 2, 2, w // 2, 2, c).amax((2, 4))
+      x = silu(rms(x, p[f'enc/cnn{i}norm/scale']))
+    return x.reshape(*lead, -1)
+
+  # -- rssm ------------------------------------------------------------------
+  def action_embed(self, action, reset=None):
+    """DictConcat one-hot of the single discrete action (nets.py:467-500) with
+    the reset masking of rssm.py:76-79."""
+    a = action.long()
+    if reset is not None:
+      a = torch.where(reset, torch.zeros_like(a), a)
+    a = F.one_hot(a, self.cfg.actions).to(f32)
+    if reset is not None:
+      a = a * (~reset)[..., None]
+    return a
+
+  def core(self, deter, stoch, action):                         # rssm.py:135-159
+    p, cfg, g = self.p, self.cfg, self.cfg.blocks
+    stoch = stoch.reshape(stoch.shape[0], -1)
+    action = action / torch.clamp(action.abs(), min=1).detach()
+    x0 = layer(p, 'dyn/dynin0', deter)
+    x1 = layer(p, 'dyn/dynin1', stoch)
+    x2 = layer(p, 'dyn/dynin2', action)
+    x = torch.cat([x0, x1, x2], -1)[:, None, :].expand(-1, g, -1)
+    x = torch.cat([deter.reshape(len(deter), g, -1), x], -1).reshape(len(deter), -1)
+    x = block_linear(p, 'dyn/dynhid0', x, g)
+    x = silu(rms(x, p['dyn/dynhid0norm/scale']))
+    x = block_linear(p, 'dyn/dyngru', x, g)
+    gates = x.reshape(len(x), g, -1).chunk(3, -1)
+    reset, cand, update = [y.reshape(len(x), -1) for y in gates]
+    reset = torch.sigmoid(reset)
+    cand = torch.tanh(reset * cand)
+    update = torch.sigmoid(update - 1)
+    return update * cand + (1 - update) * deter
+
+  def prior(self, deter):                                       # rssm.py:161-171
+    x = deter
+    for i in range(self.cfg.imglayers):
+      x = layer(self.p, f'dyn/prior{i}', x)
+    x = linear(self.p, 'dyn/priorlogit', x)
+    return x.reshape(*x.shape[:-1], self.cfg.stoch, self.cfg.classes)
+
+  def observe_step(self, carry, tokens, action, reset, gumbel):  # rssm.py:75-92
+    cfg = self.cfg
+    keep = (~reset).to(f32)
+    deter = carry['deter'] * keep[:, None]
+    stoch = carry['stoch'] * keep[:, None, None]
+    act = self.action_embed(action, reset)
+    deter = self.core(deter, stoch, act)
+    x = torch.cat([deter, tokens], -1)
+    x = layer(self.p, 'dyn/obs0', x)
+    logit = linear(self.p, 'dyn/obslogit', x).reshape(len(x), cfg.stoch, cfg.classes)
+    stoch = onehot_sample(logit, cfg.unimix, gumbel)
+    return dict(deter=deter, stoch=stoch), dict(deter=deter, stoch=stoch, logit=logit)
+
+  def observe(self, carry, tokens, action, reset, gumbel):       # rssm.py:61-73
+    feats = []
+    for t in range(tokens.shape[1]):
+      carry, feat = self.observe_step(
+          carry, tokens[:, t], action[:, t], reset[:, t], gumbel[:, t])
+      feats.append(feat)
+    feat = {k: torch.stack([f[k] for f in feats], 1) for k in feats[0]}
+    return carry, feat
+
+  def rssm_loss(self, feat):                                    # rssm.py:120-133
+    cfg = self.cfg
+    prior = unimix_logits(self.prior(feat['deter']), cfg.unimix)
+    post = unimix_logits(feat['logit'], cfg.unimix)
+    dyn = cat_kl(post.detach(), prior)
+    rep = cat_kl(post, prior.detach())
+    dyn = torch.clamp(dyn, min=cfg.free_nats)
+    rep = torch.clamp(rep, min=cfg.free_nats)
+    mets = dict(dyn_ent=cat_entropy(prior).sum(-1).mean(),
+                rep_ent=cat_entropy(post).sum(-1).mean())
+    return dict(dyn=dyn, rep=rep), mets
+
+  def imagine_step(self, carry, action_onehot, gumbel):         # rssm.py:95-104
+    deter = self.core(carry['deter'], carry['stoch'], action_onehot)
+    logit = self.prior(deter)
+    stoch = onehot_sample(logit, self.cfg.unimix, gumbel)
+    return dict(deter=deter, stoch=stoch)
+
+  # -- decoder (rssm.py:288-359, image key only) -------------------------------
+  def decoder(self, deter, stoch):
+    p, cfg = self.p, self.cfg
+    lead = deter.shape[:-1]
+    x0 = deter.reshape(-1, deter.shape[-1])
+    x1 = stoch.reshape(x0.shape[0], -1)
+    minres = cfg.image[0] // 2 ** len(cfg.mults)
+    depths = [cfg.depth * m for m in cfg.mults]
+    g, c = cfg.bspace, depths[-1] // cfg.bspace
+    x0 = block_linear(p, 'dec/sp0', x0, g)
+    x0 = x0.reshape(-1, g, minres, minres, c).permute(0, 2, 3, 1, 4).reshape(
+        -1, minres, minres, g * c)                              # '(g h w c) -> h w (g c)'
+    x1 = layer(p, 'dec/sp1', x1)
+    x1 = linear(p, 'dec/sp2', x1).reshape(-1, minres, minres, depths[-1])
+    x = silu(rms(x0 + x1, p['dec/spnorm/scale']))
+    for i in reversed(range(len(depths) - 1)):
+      x = x.repeat_interleave(2, 2).repeat_interleave(2, 1)
+      x = conv(p, f'dec/conv{i}', x)
+      x = silu(rms(x, p[f'dec/conv{i}norm/scale']))
+    x = x.repeat_interleave(2, 2).repeat_interleave(2, 1)
+    x = torch.sigmoid(conv(p, 'dec/imgout', x))
+    return x.reshape(*lead, *x.shape[1:])
+
+  # -- heads (heads.py:16-41) ----------------------------------------------------
+  def feat2tensor(self, deter, stoch):                          # agent.py:51-53
+    return torch.cat([deter, stoch.reshape(*stoch.shape[:-2], -1)], -1)
+
+  def head(self, name, x, layers, out, p=None):
+    p = self.p if p is None else p
+    x = mlp(p, f'{name}/mlp', x, layers)
+    return linear(p, f'{name}/head/{out}', x)
+
+  def rew_logits(self, x):
+    return self.head('rew', x, self.cfg.rew_layers, 'logits')
+
+  def con_logit(self, x):
+    return self.head('con', x, self.cfg.con_layers, 'logit').squeeze(-1)
+
+  def pol_logits(self, x):
+    return self.head('pol', x, self.cfg.pol_layers, 'action/logits')
+
+  def val_logits(self, x):
+    return self.head('val', x, self.cfg.val_layers, 'logits')
+
+  def slowval_logits(self, x):
+    return self.head('slowval', x, self.cfg.val_layers, 'logits', self.slow)
+
+  # -- policy (agent.py:115-135) ---------------------------------------------------
+  def policy(self, carry, image_u8, is_first, noise):
+    """carry: dict(deter, stoch, action); noise: dict(stoch=(N,S,C), action=(N,A))."""
+    with torch.no_grad():
+      tokens = self.encoder(image_u8)
+      dyn, feat = self.observe_step(
+          carry, tokens, carry['action'], is_first, noise['stoch'])
+      logits = self.pol_logits(self.feat2tensor(feat['deter'], feat['stoch']))
+      act = torch.argmax(logits + noise['action'], -1).to(torch.int32)
+    carry = dict(deter=dyn['deter'], stoch=dyn['stoch'], action=act)
+    out = {'dyn/deter': dyn['deter'], 'dyn/stoch': dyn['stoch']}
+    return carry, {'action': act}, out
+
+  # -- replay context (agent.py:312-340), K = replay_context, consec == 0 rows ----
+  def apply_replay_context(self, data):
+    K = self.cfg.replay_context
+    carry = dict(deter=data['dyn/deter'][:, K - 1], stoch=data['dyn/stoch'][:, K - 1])
+    obs = {k: data[k][:, K:] for k in ('image', 'reward', 'is_first', 'is_last', 'is_terminal')}
+    prevact = data['action'][:, K - 1: -1]
+    return carry, obs, prevact, data['stepid'][:, K:]
+
+  # -- loss (agent.py:156-245) --------------------------------------------------------
+  def loss(self, carry, obs, prevact, noise, update=True):
+    """noise: dict(observe=(B,T,S,C), imag_stoch=(B*T,H,S,C), imag_act=(B*T,H+1,A))."""
+    cfg = self.cfg
+    reset = obs['is_first']
+    B, T = reset.shape
+    losses, metrics = {}, {}
+    tokens = self.encoder(obs['image'])
+    carry, feat = self.observe(carry, tokens, prevact, reset, noise['observe'])
+    los, mets = self.rssm_loss(feat)
+    losses.update(los)
+    metrics.update(mets)
+    recon = self.decoder(feat['deter'], feat['stoch'])
+    inp = self.feat2tensor(feat['deter'], feat['stoch'])
+    losses['rew'] = twohot_loss(self.rew_logits(inp), self.bins, obs['reward'])
+    con = (~obs['is_terminal']).to(f32)
+    if cfg.contdisc:
+      con = con * (1 - 1 / cfg.horizon)
+    losses['con'] = -binary_logp(self.con_logit(inp), con)
+    target = obs['image'].to(f32) / 255
+    losses['image'] = ((recon - target) ** 2).sum((-3, -2, -1))
+
+    # imagination: forward only (imgfeat is stop-gradient'ed, ac_grads False)
+    K, H = T, cfg.imag_length
+    with torch.no_grad():
+      c = dict(deter=feat['deter'].reshape(B * K, -1),
+               stoch=feat['stoch'].reshape(B * K, cfg.stoch, cfg.classes))
+      deters, stochs, acts = [c['deter']], [c['stoch']], []
+      for h in range(H):
+        logits = self.pol_logits(self.feat2tensor(c['deter'], c['stoch']))
+        a = torch.argmax(logits + noise['imag_act'][:, h], -1)
+        c = self.imagine_step(c, F.one_hot(a, cfg.actions).to(f32), noise['imag_stoch'][:, h])
+        acts.append(a)
+        deters.append(c['deter'])
+        stochs.append(c['stoch'])
+      logits = self.pol_logits(self.feat2tensor(c['deter'], c['stoch']))
+      acts.append(torch.argmax(logits + noise['imag_act'][:, H], -1))
+      imgdeter, imgstoch = torch.stack(deters, 1), torch.stack(stochs, 1)
+      imgact = torch.stack(acts, 1)
+    inp = self.feat2tensor(imgdeter, imgstoch)
+    los, ret, mets = self.imag_loss(imgact, inp, update)
+    losses.update({k: v.mean(1).reshape(B, K) for k, v in los.items()})
+    metrics.update(mets)
+
+    # replay value loss (agent.py:219-235, repl_loss :449-479)
+    boot = ret[:, 0].reshape(B, K)
+    inp = self.feat2tensor(feat['deter'], feat['stoch'])
+    vlogits = self.val_logits(inp)
+    val = twohot_pred(vlogits, self.bins)
+    slow = twohot_pred(self.slowval_logits(inp), self.bins)
+    disc = 1 - 1 / cfg.horizon
+    weight = (~obs['is_last']).to(f32)
+    rret = lambda_return(obs['is_last'], obs['is_terminal'], obs['reward'], val, boot, disc, cfg.lam)
+    padded = torch.cat([rret, 0 * rret[:, -1:]], 1)
+    losses['repval'] = weight[:, :-1] * (
+        twohot_loss(vlogits, self.bins, padded) +
+        cfg.slowreg * twohot_loss(vlogits, self.bins, slow))[:, :-1]
+
+    assert set(losses) == set(cfg.scales), (sorted(losses), sorted(cfg.scales))
+    metrics.update({f'loss/{k}': v.mean() for k, v in losses.items()})
+    total = sum(v.mean() * cfg.scales[k] for k, v in losses.items())
+    entries = {'dyn/deter': feat['deter'], 'dyn/stoch': feat['stoch']}
+    outs = dict(tokens=tokens, feat=feat, losses=losses, recon=recon,
+                imgdeter=imgdeter, imgstoch=imgstoch, imgact=imgact, ret=ret)
+    return total, carry, entries, outs, metrics
+
+  def imag_loss(self, act, inp, update):                        # agent.py:382-446
+    cfg = self.cfg
+    rew = twohot_pred(self.rew_logits(inp), self.bins)
+    con = torch.exp(binary_logp(self.con_logit(inp), torch.ones(())))
+    pol = self.pol_logits(inp)
+    vlogits = self.val_logits(inp)
+    val = twohot_pred(vlogits, self.bins)
+    slowval = twohot_pred(self.slowval_logits(inp), self.bins)
+    tarval = val                                                # slowtar False
+    disc = 1 if cfg.contdisc else 1 - 1 / cfg.horizon
+    weight = torch.cumprod(disc * con, 1) / disc
+    last = torch.zeros_like(con)
+    term = 1 - con
+    ret = lambda_return(last, term, rew, tarval, tarval, disc, cfg.lam)
+    roffset, rscale = self.retnorm(ret, update)
+    adv = (ret - tarval[:, :-1]) / rscale
+    logp_all = torch.log_softmax(pol, -1)
+    logpi = logp_all.gather(-1, act[..., None].long()).squeeze(-1)[:, :-1]
+    ent = -(torch.softmax(pol, -1) * logp_all).sum(-1)[:, :-1]
+    losses = {}
+    losses['policy'] = weight[:, :-1].detach() * -(
+        logpi * adv.detach() + cfg.actent * ent)
+    padded = torch.cat([ret, 0 * ret[:, -1:]], 1).detach()
+    losses['value'] = weight[:, :-1].detach() * (
+        twohot_loss(vlogits, self.bins, padded) +
+        cfg.slowreg * twohot_loss(vlogits, self.bins, slowval.detach()))[:, :-1]
+    ret_normed = (ret - roffset) / rscale
+    mets = dict(adv=adv.mean(), rew=rew.mean(), con=con.mean(), ret=ret_normed.mean(),
+                val=val.mean(), weight=weight.mean(), ent=ent.mean())
+    return losses, ret.detach(), mets
+
+  def retnorm(self, x, update):                                 # utils.py:37-77 ('perc', debias False)
+    cfg, st = self.cfg, self.state
+    if update:
+      x = x.detach().to(f32).flatten()
+      lo = torch.quantile(x, cfg.perclo / 100)
+      hi = torch.quantile(x, cfg.perchi / 100)
+      st['ret_lo'] = (1 - cfg.retnorm_rate) * st['ret_lo'] + cfg.retnorm_rate * lo
+      st['ret_hi'] = (1 - cfg.retnorm_rate) * st['ret_hi'] + cfg.retnorm_rate * hi
+    lo, hi = st['ret_lo'], st['ret_hi']
+    return lo, torch.clamp(hi - lo, min=cfg.retnorm_limit)
+
+  # -- one train step (agent.py:137-154, opt.py:31-81) -----------------------------------
+  def train(self, data, noise):
+    carry, obs, prevact, stepid = self.apply_replay_context(data)
+    names = list(self.p)
+    leaves = [self.p[k].detach().requires_grad_(True) for k in names]
+    saved = self.p
+    self.p = dict(zip(names, leaves))
+    total, carry, entries, outs, metrics = self.loss(carry, obs, prevact, noise, update=True)
+    grads = torch.autograd.grad(total, leaves, allow_unused=True)
+    self.p = saved
+    grads = {k: (torch.zeros_like(self.p[k]) if g is None else g)
+             for k, g in zip(names, grads)}
+    self.apply_updates(grads)
+    self.update_slow()
+    metrics['loss'] = total.detach()
+    replay = {'stepid': stepid, **{k: v.detach() for k, v in entries.items()}}
+    return {k: v.detach() for k, v in carry.items()}, {'replay': replay}, metrics, grads, outs
+
+  def learning_rate(self, count):                               # agent.py:368-378 (const + warmup)
+    cfg = self.cfg
+    if cfg.warmup and count < cfg.warmup:
+      return cfg.lr * count / cfg.warmup
+    return cfg.lr
+
+  def apply_updates(self, grads):                               # opt.py:109-164
+    cfg, st = self.cfg, self.state
+    count = st['step']
+    step = count + 1
+    lr = self.learning_rate(count)
+    for k, g in grads.items():
+      w = self.p[k]
+      unorm, pnorm = torch.linalg.norm(g.flatten()), torch.linalg.norm(w.flatten())
+      upper = cfg.agc * torch.clamp(pnorm, min=cfg.pmin)
+      u = g * (1 / torch.clamp(unorm / upper, min=1.0))
+      st['nu'][k] = cfg.beta2 * st['nu'][k] + (1 - cfg.beta2) * (u * u)
+      nu_hat = st['nu'][k] / (1 - cfg.beta2 ** step)
+      u = u / (torch.sqrt(nu_hat) + cfg.eps)
+      st['mu'][k] = (1 - cfg.beta1) * u + cfg.beta1 * st['mu'][k]
+      mu_hat = st['mu'][k] / (1 - cfg.beta1 ** step)
+      self.p[k] = w - lr * mu_hat
+    st['step'] = step
+
+  def update_slow(self):                                        # utils.py:113-119 (every 1)
+    r = self.cfg.slowrate
+    for k in self.slow:
+      src = self.p[k.replace('slowval/', 'val/', 1)]
+      self.slow[k] = r * src + (1 - r) * self.slow[k]
+
+
+# ----------------------------------------------------------------- param shapes
+def param_shapes(cfg):
+  """Every optimised parameter and its shape, in the reference's naming; also the
+  fan-in and outscale its initialiser uses (nets.py:144-197)."""
+  D, H, S, C, g = cfg.deter, cfg.hidden, cfg.stoch, cfg.classes, cfg.blocks
+  U, A = cfg.units, cfg.actions
+  depths = [cfg.depth * m for m in cfg.mults]
+  minres = cfg.image[0] // 2 ** len(cfg.mults)
+  tokens = minres * minres * depths[-1]
+  out = {}
+
+  def lin(name, i, o, outscale=1.0):
+    out[f'{name}/kernel'] = ((i, o), i, outscale)
+    out[f'{name}/bias'] = ((o,), None, 0.0)
+
+  def blk(name, i, o):
+    out[f'{name}/kernel'] = ((g, i // g, o // g), i, 1.0)
+    out[f'{name}/bias'] = ((o,), None, 0.0)
+
+  def cnv(name, i, o, outscale=1.0):
+    k = cfg.kernel
+    out[f'{name}/kernel'] = ((k, k, i, o), k * k * i, outscale)
+    out[f'{name}/bias'] = ((o,), None, 0.0)
+
+  def nrm(name, n):
+    out[f'{name}/scale'] = ((n,), None, None)
+
+  cin = cfg.image[2]
+  for i, d in enumerate(depths):
+    cnv(f'enc/cnn{i}', cin, d); nrm(f'enc/cnn{i}norm', d); cin = d
+  lin('dyn/dynin0', D, H); nrm('dyn/dynin0norm', H)
+  lin('dyn/dynin1', S * C, H); nrm('dyn/dynin1norm', H)
+  lin('dyn/dynin2', A, H); nrm('dyn/dynin2norm', H)
+  blk('dyn/dynhid0', D + g * 3 * H, D); nrm('dyn/dynhid0norm', D)
+  blk('dyn/dyngru', D, 3 * D)
+  lin('dyn/obs0', D + tokens, H); nrm('dyn/obs0norm', H)
+  lin('dyn/obslogit', H, S * C)
+  lin('dyn/prior0', D, H); nrm('dyn/prior0norm', H)
+  lin('dyn/prior1', H, H); nrm('dyn/prior1norm', H)
+  lin('dyn/priorlogit', H, S * C)
+  blk('dec/sp0', D, minres * minres * depths[-1])
+  lin('dec/sp1', S * C, 2 * U); nrm('dec/sp1norm', 2 * U)
+  lin('dec/sp2', 2 * U, minres * minres * depths[-1])
+  nrm('dec/spnorm', depths[-1])
+  cin = depths[-1]
+  for i in reversed(range(len(depths) - 1)):
+    cnv(f'dec/conv{i}', cin, depths[i]); nrm(f'dec/conv{i}norm', depths[i]); cin = depths[i]
+  cnv('dec/imgout', cin, cfg.image[2])
+  F_ = D + S * C
+
+  def headmlp(name, layers):
+    i = F_
+    for l in range(layers):
+      lin(f'{name}/mlp/linear{l}', i, U); nrm(f'{name}/mlp/norm{l}', U); i = U
+
+  headmlp('rew', cfg.rew_layers); lin('rew/head/logits', U, cfg.bins, 0.0)
+  headmlp('con', cfg.con_layers); lin('con/head/logit', U, 1, 1.0)
+  headmlp('pol', cfg.pol_layers); lin('pol/head/action/logits', U, A, 0.01)
+  headmlp('val', cfg.val_layers); lin('val/head/logits', U, cfg.bins, 0.0)
+  return out
+
+
+def init_params(cfg, seed=0, outscale_override=None):
+  """trunc_normal(-2,2) * 1.1368 / sqrt(fan_in) * outscale; biases 0; scales 1
+  (nets.py:166-170).  `outscale_override` lets tests make the zero-initialised
+  heads non-trivial."""
+  gen = torch.Generator().manual_seed(seed)
+  params = {}
+  for name, (shape, fan, outscale) in param_shapes(cfg).items():
+    if name.endswith('/scale'):
+      params[name] = torch.ones(shape, dtype=f32)
+    elif fan is None:
+      params[name] = torch.zeros(shape, dtype=f32)
+    else:
+      if outscale_override is not None and outscale != 1.0:
+        outscale = outscale_override
+      x = torch.empty(shape, dtype=f32)
+      torch.nn.init.trunc_normal_(x, 0.0, 1.0, -2.0, 2.0, generator=gen)
+      params[name] = x * (1.1368 * math.sqrt(1 / fan) * outscale)
+  return params
+
+
+def make_noise(cfg, B, T, seed=0):
+  gen = torch.Generator().manual_seed(seed)
+
+  def gumbel(*shape):
+    u = torch.rand(shape, generator=gen, dtype=f32).clamp_(1e-20, 1 - 1e-7)
+    return -torch.log(-torch.log(u))
+  S, C, A, H = cfg.stoch, cfg.classes, cfg.actions, cfg.imag_length
+  return dict(observe=gumbel(B, T, S, C), imag_stoch=gumbel(B * T, H, S, C),
+              imag_act=gumbel(B * T, H + 1, A))
+
+
+def tiny_config(**over):
+  """size1m-like (dreamerv3/configs.yaml:120-123) for tests that finish in seconds."""
+  cfg = default_config(deter=512, hidden=64, classes=4, stoch=8, depth=4, units=64,
+                       imag_length=5, bins=255)
+  cfg.update(over)
+  return cfg
