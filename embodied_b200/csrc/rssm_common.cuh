@@ -1,0 +1,208 @@
+// Shared machinery of the fused RSSM scan kernels (rssm_fwd.cu, rssm_bwd.cu):
+// a persistent cooperative grid (one CTA per SM) walks the T steps of
+// dreamerv3's RSSM.observe (dreamerv3/rssm.py:61-92,135-159); every step is a
+// chain of small-M (16 batch rows) dense layers separated by grid barriers.
+// Each layer is HBM-bound weight streaming: the layer's output columns are
+// split into n8 tiles over the CTAs, every weight is read exactly once per step
+// by exactly one CTA, in the tensor-core B-fragment order it is consumed in.
+//
+// Two engines, one code path:
+//   ENG_BF16  weights packed bf16 in mma.m16n8k16 B-fragment order, activations
+//             built as A fragments (shared memory or, for the deter state, a
+//             global fragment buffer), mma.sync with fp32 accumulation;
+//   ENG_F32   weights fp32 [tile][K][8], plain FFMA -- the parity engine
+//             (1e-5 vs the fp32 oracle), not a performance path.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rssm {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kRows = 16;          // padded batch rows (one m16 tile)
+constexpr int kMaxTiles = 24;      // n8 tiles accumulated per pass
+constexpr int ENG_F32 = 0;
+constexpr int ENG_BF16 = 1;
+
+__device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// ---------------------------------------------------------------- grid barrier
+// Monotonic counter; every CTA arrives once per barrier.  All cross-CTA data is
+// read with ld.global.cg (L2), never through the non-coherent L1.
+struct GridBarrier {
+  unsigned* counter;
+  unsigned epoch;
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      epoch += gridDim.x;
+      __threadfence();
+      atomicAdd(counter, 1u);
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      } while ((int)(v - epoch) < 0);
+      __threadfence();
+    }
+    __syncthreads();
+  }
+};
+
+// -------------------------------------------------------------- fragment maths
+// mma.m16n8k16 A fragment: element (row r, k) of a 16 x 16 tile lives in
+// lane (r%8)*4 + (k%8)/2, register (r/8) + 2*(k/8), half k%2.
+__device__ __forceinline__ uint32_t afrag_index(int r, int k) {
+  const int ks = k >> 4, kk = k & 15;
+  const int lane = ((r & 7) << 2) + ((kk & 7) >> 1);
+  const int reg = (r >> 3) + ((kk >> 3) << 1);
+  return ((((uint32_t)ks * 32 + lane) * 4 + reg) << 1) + (kk & 1);   // in bf16 elements
+}
+
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint4& a, const uint2& b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
+      "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y));
+}
+
+__device__ __forceinline__ uint2 ldg_nc_u2(const uint2* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldcg_u4(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// Sum of squares of each of the 16 rows of y[16][n] (global, fp32) -> rstd[16]
+// = rsqrt(mean + eps).  Warp w handles rows w and w + 8.
+__device__ __forceinline__ void row_rstd(const float* y, int n, float eps, float* rstd) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < kRows; r += kWarps) {
+    float s = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float v = ldcg(y + (size_t)r * n + i);
+      s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) rstd[r] = rsqrtf(s / (float)n + eps);
+  }
+}
+
+// ------------------------------------------------------------------ tile GEMM
+// out[16][ntiles*8] (shared, fp32) = A[16][K] @ W[K][tiles tile0 .. tile0+ntiles)
+//
+// ENG_BF16: `afrag` points at A fragments ([K/16][32] uint4; shared memory, or
+//   global when A_GLOBAL), `w` at the layer's packed weights
+//   [K/16][tiles_total][32] uint2.  Warp w takes k16 steps w, w+8, ...
+// ENG_F32: `aval(r, k)` yields A on the fly, `w` is [tiles_total][K][8] fp32.
+//   Lane l owns row l/2 and columns (l%2)*4..+3; warp w takes k = w, w+8, ...
+template <int ENG, bool A_GLOBAL, typename AVal>
+__device__ __forceinline__ void tile_gemm(
+    const void* __restrict__ w, int tiles_total, int tile0, int ntiles, int K,
+    const uint4* afrag, AVal aval, float* out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ncols = ntiles * 8;
+  for (int i = threadIdx.x; i < kRows * ncols; i += kThreads) out[i] = 0.f;
+  __syncthreads();
+  float acc[kMaxTiles][4];
+#pragma unroll
+  for (int j = 0; j < kMaxTiles; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  if (ENG == ENG_BF16) {
+    const uint2* wp = reinterpret_cast<const uint2*>(w);
+    const int ksteps = K >> 4;
+    for (int ks = warp; ks < ksteps; ks += kWarps) {
+      uint4 a;
+      if (A_GLOBAL) a = ldcg_u4(afrag + (size_t)ks * 32 + lane);
+      else a = afrag[(size_t)ks * 32 + lane];
+      const uint2* row = wp + ((size_t)ks * tiles_total + tile0) * 32 + lane;
+#pragma unroll
+      for (int j0 = 0; j0 < kMaxTiles; j0 += 8) {      // 8 independent 8-byte loads in flight
+        uint2 b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j0 + j < ntiles) b[j] = ldg_nc_u2(row + (size_t)(j0 + j) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (j0 + j < ntiles) mma_bf16(acc[j0 + j], a, b[j]);
+      }
+    }
+    const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+    for (int j = 0; j < kMaxTiles; ++j) {
+      if (j < ntiles) {
+        float* o = out + j * 8 + 2 * q;
+        atomicAdd(o + g * ncols, acc[j][0]);
+        atomicAdd(o + g * ncols + 1, acc[j][1]);
+        atomicAdd(o + (g + 8) * ncols, acc[j][2]);
+        atomicAdd(o + (g + 8) * ncols + 1, acc[j][3]);
+      }
+    }
+  } else {
+    const float* wp = reinterpret_cast<const float*>(w);
+    const int r = lane >> 1, h = lane & 1;
+    for (int k = warp; k < K; k += kWarps) {
+      const float x = aval(r, k);
+#pragma unroll
+      for (int j = 0; j < kMaxTiles; ++j) {
+        if (j < ntiles) {
+          const float4 wv = ldg_nc_f4(reinterpret_cast<const float4*>(
+              wp + ((size_t)(tile0 + j) * K + k) * 8 + h * 4));
+          acc[j][0] = fmaf(x, wv.x, acc[j][0]);
+          acc[j][1] = fmaf(x, wv.y, acc[j][1]);
+          acc[j][2] = fmaf(x, wv.z, acc[j][2]);
+          acc[j][3] = fmaf(x, wv.w, acc[j][3]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxTiles; ++j) {
+      if (j < ntiles) {
+        float* o = out + r * ncols + j * 8 + h * 4;
+        atomicAdd(o, acc[j][0]); atomicAdd(o + 1, acc[j][1]);
+        atomicAdd(o + 2, acc[j][2]); atomicAdd(o + 3, acc[j][3]);
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Build A fragments in shared memory from aval(r, k), k in [0, K).
+template <typename AVal>
+__device__ __forceinline__ void build_afrag(__nv_bfloat16* afrag, int K, AVal aval) {
+  for (int i = threadIdx.x; i < kRows * (K >> 1); i += kThreads) {
+    const int r = i / (K >> 1), k = (i - r * (K >> 1)) << 1;
+    const __nv_bfloat162 v = __floats2bfloat162_rn(aval(r, k), aval(r, k + 1));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k)) = v;
+  }
+  __syncthreads();
+}
+
+struct NoVal {
+  __device__ __forceinline__ float operator()(int, int) const { return 0.f; }
+};
+
+// CTA c's share [begin, end) of `total` work units.
+__device__ __forceinline__ void cta_range(int total, int& begin, int& end) {
+  const int per = (total + gridDim.x - 1) / gridDim.x;
+  begin = min(total, (int)blockIdx.x * per);
+  end = min(total, begin + per);
+}
+
+}  // namespace rssm

@@ -49,6 +49,7 @@ class Optimizer:
     st.mu.mul_(cfg.beta1).add_(u, alpha=1 - cfg.beta1)
     st.master.add_(st.mu, alpha=-lr / (1 - cfg.beta1 ** t))
     st.step = t
+    st.version += 1
     return {'opt/grad_norm': torch.linalg.vector_norm(gn), 'opt/updates': t,
             'opt/lr': lr}
 

@@ -102,6 +102,7 @@ class ParamStore:
     self.nu = torch.zeros(total, dtype=f32, device=self.device)
     self.mu = torch.zeros(total, dtype=f32, device=self.device)
     self.step = 0
+    self.version = 0      # bumped whenever `master` changes (packed copies key on it)
     # segment table for the per-tensor AGC norms of the fused optimiser
     names = list(self.specs)
     self.seg_begin = torch.tensor(
@@ -181,3 +182,4 @@ class ParamStore:
       self.mu.copy_(torch.as_tensor(data['opt/mu']))
       self.step = int(data['opt/step'])
     self._cast.clear()
+    self.version += 1

@@ -117,6 +117,51 @@ int emb_driver_scatter_mask_actions(const emb_key_t* keys, int nkeys,
                                     const int64_t* dst_rows, int64_t nrows,
                                     void* stream);
 
+
+/* ------------------------------------------------------------------ learner:
+ * the fused RSSM scan (dreamerv3/rssm.py:61-92 `_observe`, :135-159 `_core`).
+ * One persistent cooperative kernel walks the T steps; see
+ * embodied_b200/csrc/rssm_fwd.cu for the phase schedule.  All activations are
+ * TIME-MAJOR with the batch padded to 16 rows: [T][16][...]; rows >= B are
+ * computed and ignored.  engine 1 = bf16 tensor-core weights (packed by
+ * emb_rssm_pack), engine 0 = fp32 FFMA (parity). */
+typedef struct emb_rssm_fwd_args {
+  int32_t B, T, D, H, S, C, G;   /* batch rows (<=16), steps, deter, hidden, stoch, classes, blocks */
+  int32_t engine;                /* 0 fp32, 1 bf16 */
+  float unimix, eps;             /* 0.01, 1e-4 (embodied/jax/outs.py:210-216, nets.py:364) */
+  /* packed weights, engine layout (bf16: [K/16][N/8][32 lanes][2 u32] mma B fragments;
+   * fp32: [N/8][K][8]) */
+  const void* w_ph1;     /* [D][2H]: obs0/kernel[:D] | dynin0/kernel            rssm.py:83-85,141 */
+  const void* w_logit;   /* [H][S*C]: obslogit/kernel                           rssm.py:168-171 */
+  const void* w_hid;     /* [G][D/G+3H][D/G]: dynhid0/kernel                    rssm.py:149 */
+  const void* w_gru;     /* [G][D/G][3D/G], columns reordered (j/8, gate, j%8)  rssm.py:152-154 */
+  const void* w_in1;     /* dynin1/kernel row-major [S*C][H], bf16 or fp32      rssm.py:143 */
+  const float *b0, *b1, *b_hid, *b_gru, *b_logit;   /* biases (flat, reference layout) */
+  const float *s0, *s1, *s_hid, *s_obs;             /* rms-norm scales */
+  /* inputs */
+  const float* deter0;   /* [16][D]   carry */
+  const float* x2;       /* [T][16][H]   silu(rms(dynin2(action)))  (hoisted)  */
+  const float* pre_tok;  /* [T][16][H]   tokens @ obs0[D:] + bias   (hoisted)  */
+  const float* keep;     /* [T+1][16]    1 - reset; keep[T] = 1                */
+  const float* gumbel;   /* [T][16][S*C] injected sampling noise               */
+  /* outputs */
+  float* deter;          /* [T][16][D] */
+  float* logit;          /* [T][16][S*C] */
+  int32_t* index;        /* [T][16][S]   sampled class of every latent */
+  /* saved for the backward pass; y0[0], y1[0] are INPUTS (step 0, hoisted) */
+  float* y0;             /* [T+1][16][H] pre-norm dynin0 */
+  float* y1;             /* [T+1][16][H] pre-norm dynin1 */
+  float* yhid;           /* [T][16][D]   pre-norm dynhid0 */
+  float* gates;          /* [T][3][16][D] reset, cand, update after their nonlinearity */
+  float* yobs;           /* [T][16][H]   pre-norm obs0 */
+  float* sumsq;          /* [T][16]      row sums of yhid^2; ZEROED by the caller */
+  /* scratch */
+  void* deterA;          /* bf16 engine: [2][16*D] bf16, A-fragment order */
+  uint32_t* barrier;     /* one ZEROED u32 */
+} emb_rssm_fwd_args;
+
+int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
