@@ -29,6 +29,8 @@ constexpr int ENG_BF16 = 1;
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// bf16 engine: the result is rounded to bf16 (8 mantissa bits) right away
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 // ---------------------------------------------------------------- grid barrier
@@ -95,9 +97,11 @@ __device__ __forceinline__ void row_rstd(const float* y, int n, float eps, float
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int r = warp; r < kRows; r += kWarps) {
     float s = 0.f;
-    for (int i = lane; i < n; i += 32) {
-      const float v = ldcg(y + (size_t)r * n + i);
-      s = fmaf(v, v, s);
+#pragma unroll 4
+    for (int i = lane * 4; i < n; i += 128) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(y + (size_t)r * n + i));
+      s = fmaf(v.x, v.x, s); s = fmaf(v.y, v.y, s);
+      s = fmaf(v.z, v.z, s); s = fmaf(v.w, v.w, s);
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -106,64 +110,109 @@ __device__ __forceinline__ void row_rstd(const float* y, int n, float eps, float
 }
 
 // ------------------------------------------------------------------ tile GEMM
-// out[16][ntiles*8] (shared, fp32) = A[16][K] @ W[K][tiles tile0 .. tile0+ntiles)
+// out[16][nt*8] (shared, fp32) = A[16][K] @ W[:, tiles j0 .. j0+nt of this CTA)
 //
-// ENG_BF16: `afrag` points at A fragments ([K/16][32] uint4; shared memory, or
-//   global when A_GLOBAL), `w` at the layer's packed weights
-//   [K/16][tiles_total][32] uint2.  Warp w takes k16 steps w, w+8, ...
-// ENG_F32: `aval(r, k)` yields A on the fly, `w` is [tiles_total][K][8] fp32.
-//   Lane l owns row l/2 and columns (l%2)*4..+3; warp w takes k = w, w+8, ...
+// ENG_BF16: `wblk` is THIS CTA's contiguous weight block [K/16][per][32] uint2
+//   (mma B fragments of its `per` n8 tiles, k16-step major); `afrag` the A
+//   fragments ([K/16][32] uint4; shared memory, or global when A_GLOBAL).
+//   A warp takes KB consecutive k16 steps at a time and keeps KB x TB 8-byte
+//   weight loads in flight (16 per lane) before the dependent MMAs.
+// ENG_F32: `aval(r, k)` yields A on the fly, `wf32` is the whole layer
+//   [tiles][K][8] fp32 and `tile_global0` this call's first tile.  Lane l owns
+//   row l/2 and columns (l%2)*4..+3; warp w takes k = w, w+8, ...
+template <int KB, int NT, bool A_GLOBAL>
+__device__ __forceinline__ void gemm_bf16(
+    const uint2* __restrict__ wblk, int per, int j0, int ksteps,
+    const uint4* afrag, float* red) {
+  // No guards inside the loops: NT is the exact tile count, the k16 steps are
+  // consumed in whole rounds of kWarps * KB, the remainder one step at a time.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int ncols = NT * 8;
+  float acc[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const uint2* wl = wblk + (size_t)j0 * 32 + lane;
+  const int done = (ksteps / (kWarps * KB)) * (kWarps * KB);
+  for (int ks0 = warp * KB; ks0 < done; ks0 += kWarps * KB) {
+    uint4 a[KB];
+    uint2 b[KB][NT];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+      if (A_GLOBAL) a[kb] = ldcg_u4(afrag + (size_t)(ks0 + kb) * 32 + lane);
+      else a[kb] = afrag[(size_t)(ks0 + kb) * 32 + lane];
+    }
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+      for (int j = 0; j < NT; ++j)
+        b[kb][j] = ldg_nc_u2(wl + ((size_t)(ks0 + kb) * per + j) * 32);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+      for (int j = 0; j < NT; ++j) mma_bf16(acc[j], a[kb], b[kb][j]);
+  }
+  for (int ks = done + warp; ks < ksteps; ks += kWarps) {
+    uint4 a;
+    uint2 b[NT];
+    if (A_GLOBAL) a = ldcg_u4(afrag + (size_t)ks * 32 + lane);
+    else a = afrag[(size_t)ks * 32 + lane];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) b[j] = ldg_nc_u2(wl + ((size_t)ks * per + j) * 32);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma_bf16(acc[j], a, b[j]);
+  }
+  // every warp parks its partial sums in its own slab; tile_gemm adds the slabs
+  float* slab = red + (size_t)warp * kRows * ncols;
+  const int g = lane >> 2, q = lane & 3;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    float* o = slab + j * 8 + 2 * q;
+    *reinterpret_cast<float2*>(o + g * ncols) = make_float2(acc[j][0], acc[j][1]);
+    *reinterpret_cast<float2*>(o + (g + 8) * ncols) = make_float2(acc[j][2], acc[j][3]);
+  }
+}
+
 template <int ENG, bool A_GLOBAL, typename AVal>
 __device__ __forceinline__ void tile_gemm(
-    const void* __restrict__ w, int tiles_total, int tile0, int ntiles, int K,
-    const uint4* afrag, AVal aval, float* out) {
+    const uint2* __restrict__ wblk, int per, int j0,
+    const float* __restrict__ wf32, int tile_global0,
+    int nt, int K, const uint4* afrag, AVal aval, float* out, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ncols = ntiles * 8;
-  for (int i = threadIdx.x; i < kRows * ncols; i += kThreads) out[i] = 0.f;
-  __syncthreads();
-  float acc[kMaxTiles][4];
-#pragma unroll
-  for (int j = 0; j < kMaxTiles; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const int ncols = nt * 8;
   if (ENG == ENG_BF16) {
-    const uint2* wp = reinterpret_cast<const uint2*>(w);
     const int ksteps = K >> 4;
-    for (int ks = warp; ks < ksteps; ks += kWarps) {
-      uint4 a;
-      if (A_GLOBAL) a = ldcg_u4(afrag + (size_t)ks * 32 + lane);
-      else a = afrag[(size_t)ks * 32 + lane];
-      const uint2* row = wp + ((size_t)ks * tiles_total + tile0) * 32 + lane;
-#pragma unroll
-      for (int j0 = 0; j0 < kMaxTiles; j0 += 8) {      // 8 independent 8-byte loads in flight
-        uint2 b[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j0 + j < ntiles) b[j] = ldg_nc_u2(row + (size_t)(j0 + j) * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (j0 + j < ntiles) mma_bf16(acc[j0 + j], a, b[j]);
-      }
+    switch (nt) {
+#define EMB_CASE(NT, KB) \
+      case NT: gemm_bf16<KB, NT, A_GLOBAL>(wblk, per, j0, ksteps, afrag, red); break;
+      EMB_CASE(1, 8) EMB_CASE(2, 8) EMB_CASE(3, 4) EMB_CASE(4, 4) EMB_CASE(5, 2) EMB_CASE(6, 2)
+      EMB_CASE(7, 2) EMB_CASE(8, 2) EMB_CASE(9, 1) EMB_CASE(10, 1) EMB_CASE(11, 1) EMB_CASE(12, 1)
+      EMB_CASE(13, 1) EMB_CASE(14, 1) EMB_CASE(15, 1) EMB_CASE(16, 1) EMB_CASE(17, 1) EMB_CASE(18, 1)
+      EMB_CASE(19, 1) EMB_CASE(20, 1) EMB_CASE(21, 1) EMB_CASE(22, 1) EMB_CASE(23, 1) EMB_CASE(24, 1)
+#undef EMB_CASE
+      default: break;
     }
-    const int g = lane >> 2, q = lane & 3;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRows * ncols; i += kThreads) {
+      float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxTiles; ++j) {
-      if (j < ntiles) {
-        float* o = out + j * 8 + 2 * q;
-        atomicAdd(o + g * ncols, acc[j][0]);
-        atomicAdd(o + g * ncols + 1, acc[j][1]);
-        atomicAdd(o + (g + 8) * ncols, acc[j][2]);
-        atomicAdd(o + (g + 8) * ncols + 1, acc[j][3]);
-      }
+      for (int w = 0; w < kWarps; ++w) s += red[(size_t)w * kRows * ncols + i];
+      out[i] = s;
     }
   } else {
-    const float* wp = reinterpret_cast<const float*>(w);
+    for (int i = threadIdx.x; i < kRows * ncols; i += kThreads) out[i] = 0.f;
+    __syncthreads();
+    const float* wp = wf32;
     const int r = lane >> 1, h = lane & 1;
+    float acc[kMaxTiles][4];
+#pragma unroll
+    for (int j = 0; j < kMaxTiles; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
     for (int k = warp; k < K; k += kWarps) {
       const float x = aval(r, k);
 #pragma unroll
       for (int j = 0; j < kMaxTiles; ++j) {
-        if (j < ntiles) {
+        if (j < nt) {
           const float4 wv = ldg_nc_f4(reinterpret_cast<const float4*>(
-              wp + ((size_t)(tile0 + j) * K + k) * 8 + h * 4));
+              wp + ((size_t)(tile_global0 + j) * K + k) * 8 + h * 4));
           acc[j][0] = fmaf(x, wv.x, acc[j][0]);
           acc[j][1] = fmaf(x, wv.y, acc[j][1]);
           acc[j][2] = fmaf(x, wv.z, acc[j][2]);
@@ -173,7 +222,7 @@ __device__ __forceinline__ void tile_gemm(
     }
 #pragma unroll
     for (int j = 0; j < kMaxTiles; ++j) {
-      if (j < ntiles) {
+      if (j < nt) {
         float* o = out + r * ncols + j * 8 + h * 4;
         atomicAdd(o, acc[j][0]); atomicAdd(o + 1, acc[j][1]);
         atomicAdd(o + 2, acc[j][2]); atomicAdd(o + 3, acc[j][3]);
@@ -181,6 +230,30 @@ __device__ __forceinline__ void tile_gemm(
     }
   }
   __syncthreads();
+}
+
+// Copy `n16` A fragments (uint4) from global (L2) to shared memory.
+__device__ __forceinline__ void copy_frags(uint4* dst, const uint4* src, int n16) {
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n16; i += kThreads) dst[i] = ldcg_u4(src + i);
+}
+
+// A-fragment builders (bf16 engine).  `src` is fp32 [16][n] in global memory
+// written by other CTAs (read through L2); f(r, k, v) transforms element (r, k).
+// Four consecutive k per thread: one 16-byte load, two 4-byte fragment stores.
+template <typename F>
+__device__ __forceinline__ void build_part(__nv_bfloat16* afrag, int koff, const float* src,
+                                           int n, int ld, F f) {
+  const int n4 = n >> 2;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < kRows * n4; i += kThreads) {
+    const int r = i / n4, k = (i - r * n4) << 2;
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * ld + k));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k)) =
+        __floats2bfloat162_rn(f(r, k, v.x), f(r, k + 1, v.y));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k + 2)) =
+        __floats2bfloat162_rn(f(r, k + 2, v.z), f(r, k + 3, v.w));
+  }
 }
 
 // Build A fragments in shared memory from aval(r, k), k in [0, K).

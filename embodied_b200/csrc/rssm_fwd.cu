@@ -31,42 +31,111 @@ struct Dims {
 
 template <int ENG>
 __global__ void __launch_bounds__(kThreads, 1)
-rssm_fwd_kernel(const emb_rssm_fwd_args a) {
+rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Dims d = {a.B, a.T, a.D, a.H, a.S, a.C, a.G, a.D / a.G, a.S * a.C, a.unimix, a.eps};
   const int Kh = d.Dg + 3 * d.H;                 // dynhid0 input width per group
+  constexpr bool BF = ENG == ENG_BF16;
   // shared memory carve-up
   float* out = reinterpret_cast<float*>(smem_raw);                   // [16][kMaxTiles*8]
   float* rstd_a = out + kRows * kMaxTiles * 8;                       // [16]
   float* rstd_b = rstd_a + kRows;                                    // [16]
-  int* sidx = reinterpret_cast<int*>(rstd_b + kRows);                // [16][S]
-  __nv_bfloat16* afrag = reinterpret_cast<__nv_bfloat16*>(sidx + kRows * d.S + 16);
-  afrag = reinterpret_cast<__nv_bfloat16*>(((uintptr_t)afrag + 15) & ~(uintptr_t)15);
-  const uint4* afrag4 = reinterpret_cast<const uint4*>(afrag);
+  __nv_bfloat16* afrag = reinterpret_cast<__nv_bfloat16*>(rstd_b + kRows);
+  uint4* afrag4 = reinterpret_cast<uint4*>(afrag);
+  // per-warp partial sums live right behind the phase's A fragments (K * 32 B)
+  auto red_after = [&](int K) -> float* {
+    return reinterpret_cast<float*>(afrag + (BF ? (size_t)kRows * K : 0));
+  };
+  auto act = [](float x) -> float { return BF ? silu_fast(x) : silu_f(x); };
 
   GridBarrier bar{a.barrier, 0};
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
   const size_t RH = (size_t)kRows * d.H, RD = (size_t)kRows * d.D, RSC = (size_t)kRows * d.SC;
 
+  // static work split (must match scan.py pack(): per = ceil(tiles / ncta))
+  const int tiles_hid = d.D / 8, per_hid = (tiles_hid + ncta - 1) / ncta;
+  const int units_gru = d.D / 8, per_gru = (units_gru + ncta - 1) / ncta;
+  const int tiles_ph1 = 2 * d.H / 8, per_ph1 = (tiles_ph1 + ncta - 1) / ncta;
+  const int tiles_log = d.SC / 8, per_log = (tiles_log + ncta - 1) / ncta;
+  const uint2* blk_hid = reinterpret_cast<const uint2*>(a.w_hid) + (size_t)cta * (Kh / 16) * per_hid * 32;
+  const uint2* blk_gru = reinterpret_cast<const uint2*>(a.w_gru) + (size_t)cta * (d.Dg / 16) * per_gru * 3 * 32;
+  const uint2* blk_ph1 = reinterpret_cast<const uint2*>(a.w_ph1) + (size_t)cta * (d.D / 16) * per_ph1 * 32;
+  const uint2* blk_log = reinterpret_cast<const uint2*>(a.w_logit) + (size_t)cta * (d.H / 16) * per_log * 32;
+  const float* wf_hid = reinterpret_cast<const float*>(a.w_hid);
+  const float* wf_gru = reinterpret_cast<const float*>(a.w_gru);
+  const float* wf_ph1 = reinterpret_cast<const float*>(a.w_ph1);
+  const float* wf_log = reinterpret_cast<const float*>(a.w_logit);
+  __nv_bfloat16* deterA = reinterpret_cast<__nv_bfloat16*>(a.deterA);
+  __nv_bfloat16* x0A = deterA + 2 * RD;                       // [16*H] x0 fragments
+  // x0 = silu(rms(y0)) is built ONCE per step, row r by CTA ncta-1-r, instead
+  // of by every CTA in its P4 prologue.
+  auto build_x0 = [&](const float* y0v) {
+    const int r = ncta - 1 - cta;
+    if (!BF || r < 0 || r >= kRows) return;
+    float s = 0.f;
+    for (int i = tid * 4; i < d.H; i += kThreads * 4) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(y0v + (size_t)r * d.H + i));
+      s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((tid & 31) == 0) out[tid >> 5] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < kWarps; ++w) tot += out[w];
+    const float rstd = rsqrtf(tot / (float)d.H + d.eps);
+    for (int k = tid * 2; k < d.H; k += kThreads * 2) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(y0v + (size_t)r * d.H + k));
+      *reinterpret_cast<__nv_bfloat162*>(x0A + afrag_index(r, k)) = __floats2bfloat162_rn(
+          silu_fast(v.x * (rstd * a.s0[k])), silu_fast(v.y * (rstd * a.s0[k + 1])));
+    }
+    __syncthreads();
+  };
+
+  if (BF) {
+    // deter0 -> A fragments (slot 1 = "(t-1) & 1" of step 0)
+    for (size_t i = (size_t)cta * kThreads + tid; i < RD; i += (size_t)ncta * kThreads) {
+      const int r = (int)(i / d.D), k = (int)(i - (size_t)r * d.D);
+      deterA[RD + afrag_index(r, k)] = __float2bfloat16_rn(a.deter0[i]);
+    }
+    build_x0(a.y0);
+    bar.sync();
+  }
+
+#define MARK(i)                                                              \
+  if (a.timing && cta == 0 && tid == 0) {                                    \
+    unsigned long long now_;                                                 \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                  \
+    a.timing[(size_t)t * 16 + (i)] = now_;                                   \
+  }
   for (int t = 0; t < d.T; ++t) {
+    MARK(0)
     const float* keep = a.keep + (size_t)t * kRows;
     const float* keep_next = a.keep + (size_t)(t + 1) * kRows;
     const float* deter_prev = t == 0 ? a.deter0 : a.deter + (size_t)(t - 1) * RD;
     const float* y0 = a.y0 + (size_t)t * RH;
     const float* y1 = a.y1 + (size_t)t * RH;
-    const float* x2 = a.x2 + (size_t)t * RH;
+    const float* x2 = reinterpret_cast<const float*>(a.x2) + (size_t)t * RH;   // fp32 engine view
     float* yhid = a.yhid + (size_t)t * RD;
+    const bool last = t + 1 == d.T;
 
     // ------------------------------------------------------------------ P4
     {
-      int u0, u1;
-      cta_range(d.D / 8, u0, u1);
+      const int u0 = min(tiles_hid, cta * per_hid), u1 = min(tiles_hid, u0 + per_hid);
       const int tpg = d.Dg / 8;                   // tiles per group
       if (u0 < u1) {
-        row_rstd(y0, d.H, d.eps, rstd_a);
+        if (!BF) row_rstd(y0, d.H, d.eps, rstd_a);
         row_rstd(y1, d.H, d.eps, rstd_b);
         __syncthreads();
+        if (BF) {   // the group-independent part of A: x0 (prebuilt), x1, x2 (prebuilt by the host)
+          copy_frags(afrag4 + (d.Dg / 16) * 32, reinterpret_cast<const uint4*>(x0A), (d.H / 16) * 32);
+          build_part(afrag, d.Dg + d.H, y1, d.H, d.H, [&](int r, int k, float v) {
+            return silu_fast(v * (rstd_b[r] * a.s1[k])); });
+          copy_frags(afrag4 + ((d.Dg + 2 * d.H) / 16) * 32,
+                     reinterpret_cast<const uint4*>(a.x2) + (size_t)t * (d.H / 16) * 32, (d.H / 16) * 32);
+        }
       }
+      MARK(1)
       for (int tile = u0; tile < u1;) {
         const int g = tile / tpg;
         const int seg_end = min(u1, (g + 1) * tpg);
@@ -79,12 +148,21 @@ rssm_fwd_kernel(const emb_rssm_fwd_args a) {
           k -= d.H;
           return ldcg(x2 + (size_t)r * d.H + k);
         };
-        if (ENG == ENG_BF16) build_afrag(afrag, Kh, aval);
-        const char* wg = reinterpret_cast<const char*>(a.w_hid) +
-            (size_t)g * Kh * d.Dg * (ENG == ENG_BF16 ? 2 : 4);
+        if (BF) {   // deter slice of group g: copy fragments, zero the reset rows
+          const uint4* src = reinterpret_cast<const uint4*>(deterA + (size_t)((t + 1) & 1) * RD) +
+              (size_t)(g * d.Dg / 16) * 32;
+          for (int i = tid; i < (d.Dg / 16) * 32; i += kThreads) {
+            uint4 v = ldcg_u4(src + i);
+            const int r = (i & 31) >> 2;
+            if (ldcg(keep + r) == 0.f) { v.x = 0; v.z = 0; }
+            if (ldcg(keep + r + 8) == 0.f) { v.y = 0; v.w = 0; }
+            afrag4[i] = v;
+          }
+          __syncthreads();
+        }
         for (int base = tile; base < seg_end; base += kMaxTiles) {
           const int nt = min(kMaxTiles, seg_end - base);
-          tile_gemm<ENG, false>(wg, tpg, base - g * tpg, nt, Kh, afrag4, aval, out);
+          tile_gemm<ENG, false>(blk_hid, per_hid, base - u0, wf_hid, base, nt, Kh, afrag4, aval, out, red_after(Kh));
           const int ncols = nt * 8;
           // epilogue: + bias -> yhid ; row sums of squares -> sumsq[t]
           for (int i = tid; i < kRows * ncols; i += kThreads) {
@@ -105,13 +183,14 @@ rssm_fwd_kernel(const emb_rssm_fwd_args a) {
         tile = seg_end;
       }
     }
+    MARK(2)
     bar.sync();
+    MARK(3)
 
     // ------------------------------------------------------------------ P5
     float* deter = a.deter + (size_t)t * RD;
     {
-      int u0, u1;
-      cta_range(d.D / 8, u0, u1);                 // units of 8 deter columns (3 tiles each)
+      const int u0 = min(units_gru, cta * per_gru), u1 = min(units_gru, u0 + per_gru);
       const int upg = d.Dg / 8;
       if (u0 < u1) {
         if (tid < kRows)
@@ -125,13 +204,16 @@ rssm_fwd_kernel(const emb_rssm_fwd_args a) {
           const int col = g * d.Dg + k;
           return silu_f(ldcg(yhid + (size_t)r * d.D + col) * (rstd_a[r] * a.s_hid[col]));
         };
-        if (ENG == ENG_BF16) build_afrag(afrag, d.Dg, aval);
-        const char* wg = reinterpret_cast<const char*>(a.w_gru) +
-            (size_t)g * d.Dg * 3 * d.Dg * (ENG == ENG_BF16 ? 2 : 4);
+        if (BF) {
+          build_part(afrag, 0, yhid + g * d.Dg, d.Dg, d.D, [&](int r, int k, float v) {
+            return silu_fast(v * (rstd_a[r] * a.s_hid[g * d.Dg + k])); });
+          __syncthreads();
+        }
         constexpr int kMaxUnits = kMaxTiles / 3;
         for (int base = unit; base < seg_end; base += kMaxUnits) {
           const int nu = min(kMaxUnits, seg_end - base);
-          tile_gemm<ENG, false>(wg, 3 * upg, (base - g * upg) * 3, nu * 3, d.Dg, afrag4, aval, out);
+          tile_gemm<ENG, false>(blk_gru, per_gru * 3, (base - u0) * 3, wf_gru, base * 3, nu * 3,
+                                d.Dg, afrag4, aval, out, red_after(d.Dg));
           const int ncols = nu * 24;
           // epilogue: GRU gates (rssm.py:152-158)
           for (int i = tid; i < kRows * nu * 8; i += kThreads) {
@@ -142,37 +224,35 @@ rssm_fwd_kernel(const emb_rssm_fwd_args a) {
             const float* o = out + r * ncols + u * 24 + nn;
             const float* bg = a.b_gru + (size_t)g * 3 * d.Dg + jj;
             const float rs = sigmoid_f(o[0] + bg[0]);
-            const float cand = tanhf(rs * (o[8] + bg[d.Dg]));
+            const float cpre = o[8] + bg[d.Dg];
+            const float cand = tanhf(rs * cpre);
             const float up = sigmoid_f(o[16] + bg[2 * d.Dg] - 1.0f);
             const float old = ldcg(keep + r) * ldcg(deter_prev + (size_t)r * d.D + col);
             const float nw = up * cand + (1.0f - up) * old;
             deter[(size_t)r * d.D + col] = nw;
-            float* gs = a.gates + (size_t)t * 3 * RD + (size_t)r * d.D + col;
-            gs[0] = rs; gs[RD] = cand; gs[2 * RD] = up;
-            if (ENG == ENG_BF16) {
-              __nv_bfloat16* da = reinterpret_cast<__nv_bfloat16*>(a.deterA) + (size_t)(t & 1) * RD;
-              da[afrag_index(r, col)] = __float2bfloat16_rn(nw);
-            }
+            float* gs = a.gates + (size_t)t * 4 * RD + (size_t)r * d.D + col;
+            gs[0] = rs; gs[RD] = cand; gs[2 * RD] = up; gs[3 * RD] = cpre;
+            if (BF) deterA[(size_t)(t & 1) * RD + afrag_index(r, col)] = __float2bfloat16_rn(nw);
           }
           __syncthreads();
         }
         unit = seg_end;
       }
     }
+    MARK(4)
     bar.sync();
+    MARK(5)
 
     // ------------------------------------------------------------------ P1
     float* yobs = a.yobs + (size_t)t * RH;
     {
-      const bool last = t + 1 == d.T;
-      int u0, u1;
-      cta_range((last ? d.H : 2 * d.H) / 8, u0, u1);
+      const int total = (last ? d.H : 2 * d.H) / 8;
+      const int u0 = min(total, cta * per_ph1), u1 = min(total, u0 + per_ph1);
       auto aval = [&](int r, int k) -> float { return ldcg(deter + (size_t)r * d.D + k); };
-      const uint4* dA = reinterpret_cast<const uint4*>(
-          reinterpret_cast<const __nv_bfloat16*>(a.deterA) + (size_t)(t & 1) * RD);
+      const uint4* dA = reinterpret_cast<const uint4*>(deterA + (size_t)(t & 1) * RD);
       for (int base = u0; base < u1; base += kMaxTiles) {
         const int nt = min(kMaxTiles, u1 - base);
-        tile_gemm<ENG, true>(a.w_ph1, 2 * d.H / 8, base, nt, d.D, dA, aval, out);
+        tile_gemm<ENG, true>(blk_ph1, per_ph1, base - u0, wf_ph1, base, nt, d.D, dA, aval, out, red_after(0));
         const int ncols = nt * 8;
         for (int i = tid; i < kRows * ncols; i += kThreads) {
           const int r = i / ncols, c = i - r * ncols;
@@ -180,30 +260,36 @@ rssm_fwd_kernel(const emb_rssm_fwd_args a) {
           if (col < d.H) {
             yobs[(size_t)r * d.H + col] = out[i] + ldcg(a.pre_tok + (size_t)t * RH + (size_t)r * d.H + col);
           } else {
-            a.y0[(size_t)(t + 1) * RH + (size_t)r * d.H + col - d.H] =
-                ldcg(keep_next + r) * out[i] + a.b0[col - d.H];
+            const size_t at = (size_t)(t + 1) * RH + (size_t)r * d.H + col - d.H;
+            a.y0[at] = ldcg(keep_next + r) * out[i] + a.b0[col - d.H];
+            a.y1[at] = a.b1[col - d.H];          // P3 adds the sampled dynin1 rows on top
           }
         }
         __syncthreads();
       }
     }
+    MARK(6)
     bar.sync();
+    MARK(7)
 
     // ------------------------------------------------------------------ P2
     float* logit = a.logit + (size_t)t * RSC;
     {
-      int u0, u1;
-      cta_range(d.SC / 8, u0, u1);
+      const int u0 = min(tiles_log, cta * per_log), u1 = min(tiles_log, u0 + per_log);
       if (u0 < u1) {
         row_rstd(yobs, d.H, d.eps, rstd_a);
         __syncthreads();
         auto aval = [&](int r, int k) -> float {
           return silu_f(ldcg(yobs + (size_t)r * d.H + k) * (rstd_a[r] * a.s_obs[k]));
         };
-        if (ENG == ENG_BF16) build_afrag(afrag, d.H, aval);
+        if (BF) {
+          build_part(afrag, 0, yobs, d.H, d.H, [&](int r, int k, float v) {
+            return silu_fast(v * (rstd_a[r] * a.s_obs[k])); });
+          __syncthreads();
+        }
         for (int base = u0; base < u1; base += kMaxTiles) {
           const int nt = min(kMaxTiles, u1 - base);
-          tile_gemm<ENG, false>(a.w_logit, d.SC / 8, base, nt, d.H, afrag4, aval, out);
+          tile_gemm<ENG, false>(blk_log, per_log, base - u0, wf_log, base, nt, d.H, afrag4, aval, out, red_after(d.H));
           const int ncols = nt * 8;
           for (int i = tid; i < kRows * ncols; i += kThreads) {
             const int r = i / ncols, c = i - r * ncols;
@@ -214,79 +300,97 @@ rssm_fwd_kernel(const emb_rssm_fwd_args a) {
         }
       }
     }
+    if (!last) build_x0(a.y0 + (size_t)(t + 1) * RH);
+    MARK(8)
     bar.sync();
+    MARK(9)
 
     // ------------------------------------------------------------------ P3
+    // Sampling is split over the grid: one warp per (row, latent).  The winner's
+    // dynin1 row is added straight into y1[t+1] (the one-hot matmul of
+    // rssm.py:143 is a row gather).
     {
-      const bool last = t + 1 == d.T;
-      int u0, u1;
-      cta_range(d.H / 8, u0, u1);
-      const bool writer = blockIdx.x == gridDim.x - 1;     // usually idle in the gather
-      if ((u0 < u1 && !last) || writer) {
-        // sample every (row, latent): warp-cooperative over the C classes
-        const int warp = tid >> 5, lane = tid & 31;
-        const float* gum = a.gumbel + (size_t)t * RSC;
-        for (int grp = warp; grp < kRows * d.S; grp += kWarps) {
-          const float* l = logit + (size_t)grp * d.C;
-          const float* gn = gum + (size_t)grp * d.C;
-          float m = -INFINITY;
-          for (int c = lane; c < d.C; c += 32) m = fmaxf(m, ldcg(l + c));
+      const int warp = tid >> 5, lane = tid & 31;
+      const int groups = d.B * d.S;
+      const float* gum = a.gumbel + (size_t)t * RSC;
+      for (int grp = cta * kWarps + warp; grp < groups; grp += ncta * kWarps) {
+        const int r = grp / d.S, sv = grp - r * d.S;
+        const float* l = logit + (size_t)r * d.SC + (size_t)sv * d.C;
+        const float* gn = gum + (size_t)r * d.SC + (size_t)sv * d.C;
+        // classes c = lane, lane+32, ... (C <= 128): all loads first, then the maths
+        float lv[4], gv[4];
 #pragma unroll
-          for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-          float z = 0.f;
-          for (int c = lane; c < d.C; c += 32) z += expf(ldcg(l + c) - m);
+        for (int i = 0; i < 4; ++i) {
+          const int c = lane + 32 * i;
+          lv[i] = c < d.C ? ldcg(l + c) : -INFINITY;
+          gv[i] = c < d.C ? ldcg(gn + c) : 0.f;
+        }
+        float m = fmaxf(fmaxf(lv[0], lv[1]), fmaxf(lv[2], lv[3]));
 #pragma unroll
-          for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-          float best = -INFINITY;
-          int arg = 0x7fffffff;
-          for (int c = lane; c < d.C; c += 32) {
-            const float p = expf(ldcg(l + c) - m) / z;
-            const float pm = (1.0f - d.unimix) * p + d.unimix / (float)d.C;
-            const float v = logf(pm) + ldcg(gn + c);
+        for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float e[4], z = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { e[i] = lane + 32 * i < d.C ? expf(lv[i] - m) : 0.f; z += e[i]; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        float best = -INFINITY;
+        int arg = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = lane + 32 * i;
+          if (c < d.C) {
+            const float pm = (1.0f - d.unimix) * (e[i] / z) + d.unimix / (float)d.C;
+            const float v = logf(pm) + gv[i];
             if (v > best) { best = v; arg = c; }
           }
-#pragma unroll
-          for (int o = 16; o; o >>= 1) {
-            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-            if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
-          }
-          if (lane == 0) sidx[grp] = arg;
         }
-        __syncthreads();
-        if (writer)
-          for (int i = tid; i < kRows * d.S; i += kThreads)
-            a.index[(size_t)t * kRows * d.S + i] = sidx[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+          if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (lane == 0) a.index[(size_t)t * kRows * d.S + grp] = arg;
         if (!last) {
-          // y1' = keep' * sum_s dynin1[s*C + idx[r][s]][cols] + b1
-          const int ncols = (u1 - u0) * 8;
-          for (int i = tid; i < kRows * ncols; i += kThreads) {
-            const int r = i / ncols, c = i - r * ncols;
-            const int col = u0 * 8 + c;
-            float s = 0.f;
-            for (int sv = 0; sv < d.S; ++sv) {
-              const size_t row = (size_t)sv * d.C + sidx[r * d.S + sv];
-              if (ENG == ENG_BF16)
-                s += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.w_in1)[row * d.H + col]);
-              else
-                s += reinterpret_cast<const float*>(a.w_in1)[row * d.H + col];
+          const float kn = ldcg(keep_next + r);
+          if (kn != 0.f) {
+            const size_t row = (size_t)sv * d.C + arg;
+            float* dst = a.y1 + (size_t)(t + 1) * RH + (size_t)r * d.H;
+#pragma unroll 8
+            for (int c = lane; c < d.H; c += 32) {
+              const float w = BF
+                  ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.w_in1)[row * d.H + c])
+                  : reinterpret_cast<const float*>(a.w_in1)[row * d.H + c];
+              atomicAdd(dst + c, kn * w);
             }
-            a.y1[(size_t)(t + 1) * RH + (size_t)r * d.H + col] = ldcg(keep_next + r) * s + a.b1[col];
           }
         }
       }
     }
+    MARK(10)
     bar.sync();
+    MARK(11)
   }
+#undef MARK
 }
 
 size_t fwd_smem_bytes(const emb_rssm_fwd_args& a) {
-  const int Kh = a.D / a.G + 3 * a.H;
-  int kmax = Kh > a.H ? Kh : a.H;
-  if (a.D / a.G > kmax) kmax = a.D / a.G;
-  size_t n = sizeof(float) * (kRows * kMaxTiles * 8 + 2 * kRows) + sizeof(int) * (kRows * a.S + 16) + 16;
-  if (a.engine == rssm::ENG_BF16) n += (size_t)kRows * kmax * 2;
-  return n;
+  size_t n = sizeof(float) * (kRows * kMaxTiles * 8 + 2 * kRows);
+  if (a.engine != rssm::ENG_BF16) return n;
+  auto cdiv = [](int x, int y) { return (x + y - 1) / y; };
+  auto tiles = [&](int total, int unit) {
+    int per = cdiv(total / unit, a.ncta) * unit;
+    return per < kMaxTiles ? per : (kMaxTiles / unit) * unit;
+  };
+  auto need = [&](int K, int nt) {
+    return (size_t)kRows * K * 2 + (size_t)kWarps * kRows * nt * 8 * sizeof(float);
+  };
+  const int Dg = a.D / a.G, Kh = Dg + 3 * a.H;
+  size_t m = need(Kh, tiles(a.D / 8, 1));
+  size_t v = need(Dg, tiles(3 * a.D / 8, 3)); if (v > m) m = v;
+  v = need(0, tiles(2 * a.H / 8, 1)); if (v > m) m = v;
+  v = need(a.H, tiles(a.S * a.C / 8, 1)); if (v > m) m = v;
+  return n + m;
 }
 
 int g_sms = 0;
@@ -299,6 +403,7 @@ extern "C" int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream)
   const emb_rssm_fwd_args& a = *args;
   if (a.B < 1 || a.B > kRows) return emb::fail(-1, "%s: B=%d outside [1,16]", who, a.B);
   if (a.T < 1) return emb::fail(-1, "%s: T=%d < 1", who, a.T);
+  if (a.C > 128) return emb::fail(-1, "%s: classes=%d > 128", who, a.C);
   if (a.G < 1 || a.D % a.G || (a.D / a.G) % 16 || a.H % 16 || (a.S * a.C) % 16 || a.D % 16)
     return emb::fail(-1, "%s: D/G, H and S*C must be multiples of 16 (D=%d G=%d H=%d S=%d C=%d)",
                      who, a.D, a.G, a.H, a.S, a.C);
@@ -310,14 +415,18 @@ extern "C" int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream)
         cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       return emb::fail_cuda(who);
   }
+  if (a.ncta < 1 || a.ncta > g_sms)
+    return emb::fail(-1, "%s: ncta=%d outside [1, %d SMs] (cooperative grid)", who, a.ncta, g_sms);
   const size_t smem = fwd_smem_bytes(a);
+  if (smem > 227 * 1024)
+    return emb::fail(-1, "%s: needs %zu bytes of shared memory (> 227 KiB)", who, smem);
   const void* fn = a.engine == rssm::ENG_BF16 ? (const void*)rssm_fwd_kernel<rssm::ENG_BF16>
                                               : (const void*)rssm_fwd_kernel<rssm::ENG_F32>;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return emb::fail_cuda(who);
   emb_rssm_fwd_args copy = a;
   void* params[] = {&copy};
-  if (cudaLaunchCooperativeKernel(fn, dim3(g_sms), dim3(kThreads), params, smem,
+  if (cudaLaunchCooperativeKernel(fn, dim3(a.ncta), dim3(kThreads), params, smem,
                                   (cudaStream_t)stream) != cudaSuccess)
     return emb::fail_cuda(who);
   emb::count_launch();

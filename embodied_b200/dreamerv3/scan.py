@@ -23,14 +23,14 @@ _vp, _i32, _fl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
 
 class FwdArgs(ctypes.Structure):
   _fields_ = (
-      [(n, _i32) for n in ('B', 'T', 'D', 'H', 'S', 'C', 'G', 'engine')] +
+      [(n, _i32) for n in ('B', 'T', 'D', 'H', 'S', 'C', 'G', 'engine', 'ncta', 'pad_')] +
       [('unimix', _fl), ('eps', _fl)] +
       [(n, _vp) for n in (
           'w_ph1', 'w_logit', 'w_hid', 'w_gru', 'w_in1',
           'b0', 'b1', 'b_hid', 'b_gru', 'b_logit', 's0', 's1', 's_hid', 's_obs',
           'deter0', 'x2', 'pre_tok', 'keep', 'gumbel',
           'deter', 'logit', 'index',
-          'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'deterA', 'barrier')])
+          'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'deterA', 'barrier', 'timing')])
 
 
 def _bind(lib):
@@ -41,34 +41,47 @@ def _bind(lib):
   lib._rssm_bound = True
 
 
-def pack_matrix(w, engine):
-  """w: (..., K, N) fp32 -> the engine's streaming layout (see rssm_common.cuh)."""
-  *lead, K, N = w.shape
+def pack_matrix(w, engine, ncta, unit=1):
+  """w: (K, N) fp32 -> the engine's streaming layout (rssm_common.cuh).
+
+  bf16: the N/8 column tiles are dealt to `ncta` CTAs in runs of `per` =
+  ceil(tiles / unit / ncta) * unit (the kernel uses the same formula); every
+  CTA's tiles are stored as one contiguous block [K/16][per][32 lanes][4 bf16]
+  in mma.m16n8k16 B-fragment order: element (k, n) of a 16 x 8 tile sits in
+  lane (n%8)*4 + (k%8)/2, register k/8, half k%2.
+  fp32: [N/8][K][8]."""
+  K, N = w.shape
   assert K % 16 == 0 and N % 8 == 0, (K, N)
-  if engine == ENG_BF16:
-    n = len(lead)
-    x = w.reshape(*lead, K // 16, 2, 4, 2, N // 8, 8)      # kstep, reg, kq, half, tile, nn
-    x = x.permute(*range(n), n, n + 4, n + 5, n + 2, n + 1, n + 3)
-    return x.to(torch.bfloat16).contiguous()
-  x = w.reshape(*lead, K, N // 8, 8).transpose(-3, -2)
-  return x.contiguous()
+  if engine != ENG_BF16:
+    return w.reshape(K, N // 8, 8).transpose(0, 1).contiguous()
+  tiles = N // 8
+  per = -(-(tiles // unit) // ncta) * unit
+  padded = torch.zeros((K, ncta * per * 8), dtype=torch.bfloat16, device=w.device)
+  padded[:, :N] = w
+  x = padded.reshape(K // 16, 2, 4, 2, ncta, per, 8)      # kstep, reg, kq, half, cta, tile, nn
+  return x.permute(4, 0, 5, 6, 2, 1, 3).contiguous()      # cta, kstep, tile, nn, kq, reg, half
 
 
 @torch.no_grad()
-def pack(store, cfg, engine):
-  """The packed copies of the in-scan weights (dreamerv3/rssm.py:135-159, 81-86)."""
+def pack(store, cfg, engine, ncta):
+  """The packed copies of the in-scan weights (dreamerv3/rssm.py:135-159, 81-86).
+  The block-diagonal layers become one (K, N) matrix whose column decides the
+  group: dynhid0 -> (D/G+3H, D); dyngru -> (D/G, 3D) with columns ordered
+  (group, j/8, gate, j%8) so the three gates of a deter column are adjacent tiles."""
   D, G = cfg.deter, cfg.blocks
   Dg = D // G
   m = lambda n: store.view('master', n)
   wobs = m('dyn/obs0/kernel')
+  hid = m('dyn/dynhid0/kernel')                             # (G, Kh, Dg)
+  hid = hid.permute(1, 0, 2).reshape(hid.shape[1], D)
   gru = m('dyn/dyngru/kernel')                              # (G, Dg, 3*Dg), columns (gate, j)
-  gru = gru.reshape(G, Dg, 3, Dg // 8, 8).permute(0, 1, 3, 2, 4).reshape(G, Dg, 3 * Dg)
+  gru = gru.reshape(G, Dg, 3, Dg // 8, 8).permute(1, 0, 3, 2, 4).reshape(Dg, 3 * D)
   cd = torch.bfloat16 if engine == ENG_BF16 else f32
   return dict(
-      w_ph1=pack_matrix(torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1), engine),
-      w_logit=pack_matrix(m('dyn/obslogit/kernel'), engine),
-      w_hid=pack_matrix(m('dyn/dynhid0/kernel'), engine),
-      w_gru=pack_matrix(gru, engine),
+      w_ph1=pack_matrix(torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1), engine, ncta),
+      w_logit=pack_matrix(m('dyn/obslogit/kernel'), engine, ncta),
+      w_hid=pack_matrix(hid, engine, ncta),
+      w_gru=pack_matrix(gru, engine, ncta, unit=3),
       w_in1=m('dyn/dynin1/kernel').to(cd).contiguous())
 
 
@@ -78,6 +91,15 @@ def time_major(x, B):
   out = torch.zeros((T, ROWS, *x.shape[2:]), dtype=f32, device=x.device)
   out[:, :B] = x.transpose(0, 1)
   return out
+
+
+def a_fragments(x):
+  """fp32 (T, 16, K) -> bf16 mma.m16n8k16 A fragments (T, K/16, 32 lanes, 4 regs, 2):
+  element (r, k) in lane (r%8)*4 + (k%8)/2, register r/8 + 2*((k%16)/8), half k%2."""
+  T, R, K = x.shape
+  v = x.reshape(T, 2, 8, K // 16, 2, 4, 2)            # rhi, rlo, ks, khi, kq, half
+  v = v.permute(0, 3, 2, 5, 4, 1, 6)                  # ks, rlo, kq, khi, rhi, half
+  return v.to(torch.bfloat16).contiguous()
 
 
 def rows16(x, B):
@@ -95,12 +117,21 @@ class Scan:
     _bind(self.lib)
     self.packed = None
     self.packed_step = -1
+    self.timing = False
+    self.ncta = int(self.lib.emb_device_sm_count())
+    if self.ncta <= 0:
+      _lib.check(self.ncta)
 
   def weights(self):
     if self.packed is None or self.packed_step != self.store.version:
-      self.packed = pack(self.store, self.cfg, self.engine)
+      self.packed = pack(self.store, self.cfg, self.engine, self.ncta)
       self.packed_step = self.store.version
     return self.packed
+
+  def relaunch(self, args):
+    """Launch again on the same buffers (micro-benchmarks)."""
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(self.lib.emb_rssm_observe_fwd(ctypes.byref(args), stream))
 
   @torch.no_grad()
   def forward(self, deter0, y0, y1, x2, pre_tok, keep, gumbel):
@@ -120,12 +151,14 @@ class Scan:
         pre_tok=time_major(pre_tok, B), keep=keep_tm,
         gumbel=time_major(gumbel.reshape(B, T, S * C), B),
         deter=z(T, ROWS, D), logit=z(T, ROWS, S * C),
-        index=torch.empty((T, ROWS, S), dtype=torch.int32, device=dev),
+        index=torch.zeros((T, ROWS, S), dtype=torch.int32, device=dev),
         y0=z(T + 1, ROWS, H), y1=z(T + 1, ROWS, H), yhid=z(T, ROWS, D),
-        gates=z(T, 3, ROWS, D), yobs=z(T, ROWS, H),
+        gates=z(T, 4, ROWS, D), yobs=z(T, ROWS, H),
         sumsq=torch.zeros((T, ROWS), dtype=f32, device=dev),
-        deterA=torch.empty((2, ROWS * D), dtype=torch.bfloat16, device=dev),
+        deterA=torch.empty(2 * ROWS * D + ROWS * H, dtype=torch.bfloat16, device=dev),
         barrier=torch.zeros(4, dtype=torch.int32, device=dev))
+    if self.engine == ENG_BF16:
+      sv['x2'] = a_fragments(sv['x2'])
     sv['y0'][0] = rows16(y0.to(f32), B)
     sv['y1'][0] = rows16(y1.to(f32), B)
     vec = dict(
@@ -133,13 +166,16 @@ class Scan:
         b_gru=m('dyn/dyngru/bias'), b_logit=m('dyn/obslogit/bias'),
         s0=m('dyn/dynin0norm/scale'), s1=m('dyn/dynin1norm/scale'),
         s_hid=m('dyn/dynhid0norm/scale'), s_obs=m('dyn/obs0norm/scale'))
-    args = FwdArgs(B=B, T=T, D=D, H=H, S=S, C=C, G=G, engine=self.engine,
+    args = FwdArgs(B=B, T=T, D=D, H=H, S=S, C=C, G=G, engine=self.engine, ncta=self.ncta,
                    unimix=cfg.unimix, eps=1e-4)
+    if self.timing:
+      sv['timing'] = torch.zeros((T, 16), dtype=torch.int64, device=dev)
     for k, v in {**w, **vec, **sv}.items():
       assert v.is_contiguous(), k
       setattr(args, k, v.data_ptr())
     stream = torch.cuda.current_stream(dev).cuda_stream
     _lib.check(self.lib.emb_rssm_observe_fwd(ctypes.byref(args), stream))
+    self.last_args = args
     out = dict(
         deter=sv['deter'][:, :B].transpose(0, 1),
         logit=sv['logit'][:, :B].transpose(0, 1).reshape(B, T, S, C),

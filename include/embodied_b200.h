@@ -128,9 +128,13 @@ int emb_driver_scatter_mask_actions(const emb_key_t* keys, int nkeys,
 typedef struct emb_rssm_fwd_args {
   int32_t B, T, D, H, S, C, G;   /* batch rows (<=16), steps, deter, hidden, stoch, classes, blocks */
   int32_t engine;                /* 0 fp32, 1 bf16 */
+  int32_t ncta;                  /* grid size the weights were packed for (<= SM count) */
+  int32_t pad_;
   float unimix, eps;             /* 0.01, 1e-4 (embodied/jax/outs.py:210-216, nets.py:364) */
-  /* packed weights, engine layout (bf16: [K/16][N/8][32 lanes][2 u32] mma B fragments;
-   * fp32: [N/8][K][8]) */
+  /* packed weights.  bf16: per CTA a contiguous block [K/16][per][32 lanes][2 u32] of mma B
+   * fragments, per = ceil((N/8) / ncta) n8 tiles, CTA c owning tiles [c*per, (c+1)*per);
+   * fp32: whole layer [N/8][K][8].  Block-diagonal layers are stored as one [K][N] matrix
+   * whose column tile decides the group. */
   const void* w_ph1;     /* [D][2H]: obs0/kernel[:D] | dynin0/kernel            rssm.py:83-85,141 */
   const void* w_logit;   /* [H][S*C]: obslogit/kernel                           rssm.py:168-171 */
   const void* w_hid;     /* [G][D/G+3H][D/G]: dynhid0/kernel                    rssm.py:149 */
@@ -140,7 +144,8 @@ typedef struct emb_rssm_fwd_args {
   const float *s0, *s1, *s_hid, *s_obs;             /* rms-norm scales */
   /* inputs */
   const float* deter0;   /* [16][D]   carry */
-  const float* x2;       /* [T][16][H]   silu(rms(dynin2(action)))  (hoisted)  */
+  const void* x2;        /* silu(rms(dynin2(action))) (hoisted): fp32 [T][16][H]; bf16 engine:
+                          * per step [H/16][32 lanes][8 bf16] mma A fragments               */
   const float* pre_tok;  /* [T][16][H]   tokens @ obs0[D:] + bias   (hoisted)  */
   const float* keep;     /* [T+1][16]    1 - reset; keep[T] = 1                */
   const float* gumbel;   /* [T][16][S*C] injected sampling noise               */
@@ -148,16 +153,18 @@ typedef struct emb_rssm_fwd_args {
   float* deter;          /* [T][16][D] */
   float* logit;          /* [T][16][S*C] */
   int32_t* index;        /* [T][16][S]   sampled class of every latent */
-  /* saved for the backward pass; y0[0], y1[0] are INPUTS (step 0, hoisted) */
+  /* saved for the backward pass; y0[0], y1[0] are INPUTS (step 0, hoisted).
+   * Only rows < B of `index` are written. */
   float* y0;             /* [T+1][16][H] pre-norm dynin0 */
   float* y1;             /* [T+1][16][H] pre-norm dynin1 */
   float* yhid;           /* [T][16][D]   pre-norm dynhid0 */
-  float* gates;          /* [T][3][16][D] reset, cand, update after their nonlinearity */
+  float* gates;          /* [T][4][16][D] reset, cand, update after their nonlinearity; cand before tanh/reset */
   float* yobs;           /* [T][16][H]   pre-norm obs0 */
   float* sumsq;          /* [T][16]      row sums of yhid^2; ZEROED by the caller */
   /* scratch */
-  void* deterA;          /* bf16 engine: [2][16*D] bf16, A-fragment order */
+  void* deterA;          /* bf16 engine scratch: (2*16*D + 16*H) bf16, A-fragment order */
   uint32_t* barrier;     /* one ZEROED u32 */
+  uint64_t* timing;      /* optional [T][16] globaltimer marks of CTA 0 (NULL = off) */
 } emb_rssm_fwd_args;
 
 int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream);

@@ -1,0 +1,67 @@
+"""Times the fused RSSM scan kernels at BASELINE config-2 size (size200m, B=16,
+T=64) with CUDA events; prints achieved weight-streaming GB/s vs the measured
+HBM peak.  Algorithmic bytes per launch = T x (in-scan weight bytes)."""
+import json
+import pathlib
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+from embodied_b200.dreamerv3 import config as C, params as P, scan as S  # noqa: E402
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+try:
+  PEAK = json.load(open(ROOT / 'MEASURED_PEAKS.json'))['hbm_gbs']
+except Exception:
+  PEAK = 6650.0
+
+
+def main():
+  size = sys.argv[1] if len(sys.argv) > 1 else 'size200m'
+  engine = S.ENG_BF16 if (len(sys.argv) <= 2 or sys.argv[2] == 'bf16') else S.ENG_F32
+  B, T = 16, 64
+  cfg = C.make(size)
+  store = P.ParamStore(cfg, 'cuda', torch.float32, 0)
+  sc = S.Scan(cfg, store, engine)
+  D, H, Sx, Cx, G = cfg.deter, cfg.hidden, cfg.stoch, cfg.classes, cfg.blocks
+  g = torch.Generator(device='cuda').manual_seed(0)
+  r = lambda *s: torch.randn(s, generator=g, device='cuda')
+  args = (r(B, D) * 0.3, r(B, H), r(B, H), r(B, T, H), r(B, T, H),
+          torch.ones(B, T, device='cuda'), r(B, T, Sx, Cx))
+  nw = D * 2 * H + H * Sx * Cx + D * (D // G + 3 * H) + D * 3 * (D // G)
+  wbytes = nw * (2 if engine == S.ENG_BF16 else 4)
+  sc.timing = True
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+  for _ in range(3):
+    sc.forward(*args)
+  torch.cuda.synchronize()
+  times = []
+  for _ in range(10):
+    flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # time the kernel launch alone: prepare buffers outside the events
+    out, sv = sc.forward(*args)
+    torch.cuda.synchronize()
+    sv['sumsq'].zero_(); sv['barrier'].zero_()
+    fa = sc.last_args
+    a.record()
+    sc.relaunch(fa)
+    b.record()
+    torch.cuda.synchronize()
+    times.append(a.elapsed_time(b) * 1e-3)
+  t = float(np.median(times))
+  tm = sv['timing'].cpu().numpy().astype(np.int64)
+  d = np.diff(tm[:, :12], axis=1)[8:].mean(0) / 1e3
+  names = ['P4 prologue', 'P4 gemm', 'bar', 'P5', 'bar', 'P1', 'bar', 'P2', 'bar', 'P3', 'bar']
+  print('phase us (CTA 0, mean over steps 8..):', {n + str(i): round(float(x), 2) for i, (n, x) in enumerate(zip(names, d))})
+  print(json.dumps({
+      'kernel': 'rssm_fwd_kernel', 'size': size, 'engine': 'bf16' if engine else 'f32',
+      'B': B, 'T': T, 'ms': t * 1e3, 'us_per_step': t / T * 1e6,
+      'weights_per_step_MB': wbytes / 1e6, 'algorithmic_bytes': wbytes * T,
+      'GBs': wbytes * T / t / 1e9, 'frac_of_measured_peak': wbytes * T / t / 1e9 / PEAK}))
+
+
+if __name__ == '__main__':
+  main()
