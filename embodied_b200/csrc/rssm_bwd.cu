@@ -1,0 +1,369 @@
+// emb_rssm_observe_bwd: back-propagation through time of the fused RSSM scan
+// (the reverse of rssm_fwd.cu; dreamerv3/rssm.py:61-92,135-159 differentiated).
+//
+// Only the sequential chain runs here: per step t = T-1 .. 0 the gradient is
+// pushed back through the five in-scan layers with TRANSPOSED weights, again one
+// HBM pass over every weight per step.  Parameter gradients are NOT formed in the
+// loop: the kernel leaves the per-step upstream gradients of every layer
+// (g_xo, g_logit, g_gates, g_h, g_x0, g_x1, g_x2) in [T][16][..] buffers and the
+// host turns them into dW = A^T G with (B*T)-row tensor-core GEMMs afterwards.
+//
+//   B1  g_stoch = G_stoch[t] + (keep' * g_y1') @ dynin1^T                        (2.1 M)
+//   B2  g_logit = G_logit[t] + unimix-softmax-jacobian(g_stoch) ; g_xo = g_logit @ obslogit^T (2.1 M)
+//   B3  g_deter = G_deter[t] + carry + [g_yobs | keep' * g_y0'] @ [obs0[:D] | dynin0]^T    (16.8 M)
+//       + GRU gate backward in the epilogue -> g_gates
+//   B4  g_h     = g_gates_g @ dyngru[g]^T ; row dots for the rms-norm backward   (25.2 M)
+//   B5  g_in    = g_yhid_g @ dynhid0[g]^T -> carry (deter part), g_x0/g_x1/g_x2 (summed over groups) (33.5 M)
+// (primes = step t+1;  g_y* = rms-norm + silu backward of g_x*, recomputed where
+// it is consumed.)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/embodied_b200.h"
+#include "common.cuh"
+#include "rssm_common.cuh"
+
+namespace {
+
+using namespace rssm;
+
+__device__ __forceinline__ float dsilu(float n) {          // d silu(n) / dn
+  const float sg = 1.0f / (1.0f + expf(-n));
+  return sg * (1.0f + n * (1.0f - sg));
+}
+
+// For every row of a [16][n] layer: rstd = rsqrt(mean(y^2)+eps) and
+// coef = rstd^3 * mean(g_n * s * y) with g_n = g_x * silu'(y*rstd*s), so that
+//   g_y = rstd * s * g_n - y * coef            (rms-norm backward, nets.py:374-383)
+__device__ __forceinline__ void norm_bwd_stats(const float* gx, const float* y, const float* s,
+                                               int n, float eps, float* rstd, float* coef) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < kRows; r += kWarps) {
+    float ss = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float v = ldcg(y + (size_t)r * n + i);
+      ss = fmaf(v, v, ss);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rs = rsqrtf(ss / (float)n + eps);
+    float dot = 0.f;
+    for (int i = lane; i < n; i += 32) {
+      const float v = ldcg(y + (size_t)r * n + i);
+      const float gn = ldcg(gx + (size_t)r * n + i) * dsilu(v * rs * s[i]);
+      dot = fmaf(gn * s[i], v, dot);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    if (lane == 0) { rstd[r] = rs; coef[r] = rs * rs * rs * dot / (float)n; }
+  }
+}
+
+__device__ __forceinline__ float norm_bwd_elem(float gx, float y, float s, float rstd, float coef) {
+  const float gn = gx * dsilu(y * rstd * s);
+  return rstd * s * gn - y * coef;
+}
+
+template <int ENG>
+__global__ void __launch_bounds__(kThreads, 1)
+rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr bool BF = ENG == ENG_BF16;
+  const int B = a.B, T = a.T, D = a.D, H = a.H, S = a.S, C = a.C, G = a.G;
+  const int Dg = D / G, SC = S * C, Kh = Dg + 3 * H;
+  (void)B;
+  float* out = reinterpret_cast<float*>(smem_raw);                   // [16][kMaxTiles*8]
+  float* st = out + kRows * kMaxTiles * 8;                           // 4 x [16] row statistics
+  float *rstd_a = st, *coef_a = st + 16, *rstd_b = st + 32, *coef_b = st + 48;
+  __nv_bfloat16* afrag = reinterpret_cast<__nv_bfloat16*>(st + 64);
+  uint4* afrag4 = reinterpret_cast<uint4*>(afrag);
+  auto red_after = [&](int K) -> float* {
+    return reinterpret_cast<float*>(afrag + (BF ? (size_t)kRows * K : 0));
+  };
+
+  GridBarrier bar{a.barrier, 0};
+  const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
+  const size_t RH = (size_t)kRows * H, RD = (size_t)kRows * D, RSC = (size_t)kRows * SC;
+
+  // work split; must match scan.py pack_bwd()
+  const int tiles_b1 = SC / 8, per_b1 = (tiles_b1 + ncta - 1) / ncta;
+  const int tiles_b2 = H / 8, per_b2 = (tiles_b2 + ncta - 1) / ncta;
+  const int tiles_b3 = D / 8, per_b3 = (tiles_b3 + ncta - 1) / ncta;
+  const int tiles_b4 = D / 8, per_b4 = (tiles_b4 + ncta - 1) / ncta;
+  const int tiles_b5 = G * Kh / 8, per_b5 = (tiles_b5 + ncta - 1) / ncta;
+  const uint2* blk_b1 = reinterpret_cast<const uint2*>(a.wt_in1) + (size_t)cta * (H / 16) * per_b1 * 32;
+  const uint2* blk_b2 = reinterpret_cast<const uint2*>(a.wt_logit) + (size_t)cta * (SC / 16) * per_b2 * 32;
+  const uint2* blk_b3 = reinterpret_cast<const uint2*>(a.wt_ph1) + (size_t)cta * (2 * H / 16) * per_b3 * 32;
+  const uint2* blk_b4 = reinterpret_cast<const uint2*>(a.wt_gru) + (size_t)cta * (3 * Dg / 16) * per_b4 * 32;
+  const uint2* blk_b5 = reinterpret_cast<const uint2*>(a.wt_hid) + (size_t)cta * (Dg / 16) * per_b5 * 32;
+  const float* wf_b1 = reinterpret_cast<const float*>(a.wt_in1);
+  const float* wf_b2 = reinterpret_cast<const float*>(a.wt_logit);
+  const float* wf_b3 = reinterpret_cast<const float*>(a.wt_ph1);
+  const float* wf_b4 = reinterpret_cast<const float*>(a.wt_gru);
+  const float* wf_b5 = reinterpret_cast<const float*>(a.wt_hid);
+
+  for (int t = T - 1; t >= 0; --t) {
+    const float* keep = a.keep + (size_t)t * kRows;
+    const float* keep_next = a.keep + (size_t)(t + 1) * kRows;
+    const float* deter_prev = t == 0 ? a.deter0 : a.deter + (size_t)(t - 1) * RD;
+    const float* y0n = a.y0 + (size_t)(t + 1) * RH;         // step t+1 (zeros at t = T-1)
+    const float* y1n = a.y1 + (size_t)(t + 1) * RH;
+    const float* gx0n = a.g_x0 + (size_t)(t + 1) * RH;
+    const float* gx1n = a.g_x1 + (size_t)(t + 1) * RH;
+    const float* yobs = a.yobs + (size_t)t * RH;
+    const float* yhid = a.yhid + (size_t)t * RD;
+    const float* gates = a.gates + (size_t)t * 4 * RD;
+    float* g_xo = a.g_xo + (size_t)t * RH;
+    float* g_h = a.g_h + (size_t)t * RD;
+    float* g_gates = a.g_gates + (size_t)t * 3 * RD;
+    float* g_logit = a.g_logit + (size_t)t * RSC;
+
+    // ------------------------------------------------------------------ B1
+    // g_stoch[t] = G_stoch[t] + (keep' * g_y1') @ dynin1^T      (scratch: a.g_stoch)
+    {
+      const int u0 = min(tiles_b1, cta * per_b1), u1 = min(tiles_b1, u0 + per_b1);
+      if (u0 < u1) {
+        norm_bwd_stats(gx1n, y1n, a.s1, H, a.eps, rstd_a, coef_a);
+        __syncthreads();
+        auto aval = [&](int r, int k) -> float {
+          return ldcg(keep_next + r) * norm_bwd_elem(
+              ldcg(gx1n + (size_t)r * H + k), ldcg(y1n + (size_t)r * H + k), a.s1[k], rstd_a[r], coef_a[r]);
+        };
+        if (BF) { build_afrag(afrag, H, aval); }
+        for (int base = u0; base < u1; base += kMaxTiles) {
+          const int nt = min(kMaxTiles, u1 - base);
+          tile_gemm<ENG, false>(blk_b1, per_b1, base - u0, wf_b1, base, nt, H, afrag4, aval, out, red_after(H));
+          const int ncols = nt * 8;
+          for (int i = tid; i < kRows * ncols; i += kThreads) {
+            const int r = i / ncols, c = i - r * ncols;
+            const int col = base * 8 + c;
+            a.g_stoch[(size_t)r * SC + col] = out[i] + a.G_stoch[(size_t)t * RSC + (size_t)r * SC + col];
+          }
+          __syncthreads();
+        }
+      }
+    }
+    bar.sync();
+
+    // ------------------------------------------------------------------ B2
+    // g_logit = G_logit + (1-eps) p (g_stoch - sum_c p g_stoch) ;  g_xo = g_logit @ obslogit^T
+    {
+      const int u0 = min(tiles_b2, cta * per_b2), u1 = min(tiles_b2, u0 + per_b2);
+      // every CTA needs the full g_logit rows as its A operand; row r is also
+      // written out (for dW) by CTA ncta-1-r.
+      const bool writer = ncta - 1 - cta >= 0 && ncta - 1 - cta < kRows;
+      if (u0 < u1 || writer) {
+        // bf16 engine: the rows go straight into A fragments; fp32 engine: fp32 rows in shared memory
+        float* gl = reinterpret_cast<float*>(afrag);            // fp32 engine only: [16][SC]
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int grp = warp; grp < kRows * S; grp += kWarps) {
+          const int r = grp / S, sv = grp - r * S;
+          const size_t o = (size_t)r * SC + (size_t)sv * C;
+          float dot = 0.f;
+          for (int c = lane; c < C; c += 32)
+            dot = fmaf(a.probs[(size_t)t * RSC + o + c], ldcg(a.g_stoch + o + c), dot);
+#pragma unroll
+          for (int k = 16; k; k >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, k);
+          for (int c = lane; c < C; c += 32) {
+            const float p = a.probs[(size_t)t * RSC + o + c];
+            const float v = a.G_logit[(size_t)t * RSC + o + c] +
+                (1.0f - a.unimix) * p * (ldcg(a.g_stoch + o + c) - dot);
+            if (BF) afrag[afrag_index(r, sv * C + c)] = __float2bfloat16_rn(v);
+            else gl[o + c] = v;
+            if (ncta - 1 - cta == r) g_logit[o + c] = v;
+          }
+        }
+        __syncthreads();
+        auto aval = [&](int r, int k) -> float { return gl[(size_t)r * SC + k]; };
+        for (int base = u0; base < u1; base += kMaxTiles) {
+          const int nt = min(kMaxTiles, u1 - base);
+          tile_gemm<ENG, false>(blk_b2, per_b2, base - u0, wf_b2, base, nt, SC, afrag4, aval, out, red_after(SC));
+          const int ncols = nt * 8;
+          for (int i = tid; i < kRows * ncols; i += kThreads) {
+            const int r = i / ncols, c = i - r * ncols;
+            g_xo[(size_t)r * H + base * 8 + c] = out[i];
+          }
+          __syncthreads();
+        }
+      }
+    }
+    bar.sync();
+
+    // ------------------------------------------------------------------ B3
+    // g_deter = G_deter[t] + carry + [g_yobs | keep' g_y0'] @ [obs0[:D] | dynin0]^T, then the
+    // GRU backward (rssm.py:152-158) for the same columns.
+    {
+      const int u0 = min(tiles_b3, cta * per_b3), u1 = min(tiles_b3, u0 + per_b3);
+      if (u0 < u1) {
+        norm_bwd_stats(g_xo, yobs, a.s_obs, H, a.eps, rstd_a, coef_a);
+        norm_bwd_stats(gx0n, y0n, a.s0, H, a.eps, rstd_b, coef_b);
+        __syncthreads();
+        auto aval = [&](int r, int k) -> float {
+          if (k < H)
+            return norm_bwd_elem(ldcg(g_xo + (size_t)r * H + k), ldcg(yobs + (size_t)r * H + k),
+                                 a.s_obs[k], rstd_a[r], coef_a[r]);
+          k -= H;
+          return ldcg(keep_next + r) * norm_bwd_elem(
+              ldcg(gx0n + (size_t)r * H + k), ldcg(y0n + (size_t)r * H + k), a.s0[k], rstd_b[r], coef_b[r]);
+        };
+        if (BF) { build_afrag(afrag, 2 * H, aval); }
+        for (int base = u0; base < u1; base += kMaxTiles) {
+          const int nt = min(kMaxTiles, u1 - base);
+          tile_gemm<ENG, false>(blk_b3, per_b3, base - u0, wf_b3, base, nt, 2 * H, afrag4, aval, out, red_after(2 * H));
+          const int ncols = nt * 8;
+          for (int i = tid; i < kRows * ncols; i += kThreads) {
+            const int r = i / ncols, c = i - r * ncols;
+            const int col = base * 8 + c;
+            const size_t at = (size_t)r * D + col;
+            const float gd = out[i] + a.G_deter[(size_t)t * RD + at] + ldcg(a.gd_carry + at);
+            const float rs = gates[at], cand = gates[RD + at], up = gates[2 * RD + at], cpre = gates[3 * RD + at];
+            const float old = ldcg(keep + r) * deter_prev[at];
+            const float g_u = gd * (cand - old), g_c = gd * up;
+            a.gd_tmp[at] = gd * (1.0f - up);                 // direct path into keep*deter_{t-1}
+            const float g_rc = g_c * (1.0f - cand * cand);
+            const int g = col / Dg, jj = col - g * Dg;
+            float* gg = g_gates + (size_t)r * 3 * D + (size_t)g * 3 * Dg + jj;
+            gg[0] = g_rc * cpre * rs * (1.0f - rs);          // reset gate, pre-sigmoid
+            gg[Dg] = g_rc * rs;                              // candidate, pre-tanh
+            gg[2 * Dg] = g_u * up * (1.0f - up);             // update gate, pre-sigmoid
+          }
+          __syncthreads();
+        }
+      }
+    }
+    bar.sync();
+
+    // ------------------------------------------------------------------ B4
+    // g_h_g = g_gates_g @ dyngru[g]^T ; row dots of the dynhid0 norm backward
+    {
+      const int u0 = min(tiles_b4, cta * per_b4), u1 = min(tiles_b4, u0 + per_b4);
+      const int tpg = Dg / 8;
+      if (u0 < u1 && tid < kRows)
+        rstd_a[tid] = rsqrtf(ldcg(a.sumsq + (size_t)t * kRows + tid) / (float)D + a.eps);
+      __syncthreads();
+      for (int tile = u0; tile < u1;) {
+        const int g = tile / tpg;
+        const int seg_end = min(u1, (g + 1) * tpg);
+        auto aval = [&](int r, int k) -> float {
+          return ldcg(g_gates + (size_t)r * 3 * D + (size_t)g * 3 * Dg + k);
+        };
+        if (BF) { build_afrag(afrag, 3 * Dg, aval); }
+        for (int base = tile; base < seg_end; base += kMaxTiles) {
+          const int nt = min(kMaxTiles, seg_end - base);
+          tile_gemm<ENG, false>(blk_b4, per_b4, base - u0, wf_b4, base, nt, 3 * Dg, afrag4, aval, out, red_after(3 * Dg));
+          const int ncols = nt * 8;
+          for (int i = tid; i < kRows * ncols; i += kThreads) {
+            const int r = i / ncols, c = i - r * ncols;
+            const int col = base * 8 + c;
+            const size_t at = (size_t)r * D + col;
+            const float gh = out[i];
+            g_h[at] = gh;
+            const float y = yhid[at], s = a.s_hid[col];
+            out[i] = gh * dsilu(y * rstd_a[r] * s) * s * y;    // g_n * s * y
+          }
+          __syncthreads();
+          if (tid < kRows) {
+            float sum = 0.f;
+            for (int c = 0; c < ncols; ++c) sum += out[tid * ncols + c];
+            atomicAdd(a.dot + (size_t)t * kRows + tid, sum);
+          }
+          __syncthreads();
+        }
+        tile = seg_end;
+      }
+    }
+    bar.sync();
+
+    // ------------------------------------------------------------------ B5
+    // g_in_g = g_yhid_g @ dynhid0[g]^T : deter part -> carry, x0/x1/x2 parts summed over groups
+    {
+      const int u0 = min(tiles_b5, cta * per_b5), u1 = min(tiles_b5, u0 + per_b5);
+      const int tpg = Kh / 8;
+      if (u0 < u1 && tid < kRows) {
+        const float rs = rsqrtf(ldcg(a.sumsq + (size_t)t * kRows + tid) / (float)D + a.eps);
+        rstd_a[tid] = rs;
+        coef_a[tid] = rs * rs * rs * ldcg(a.dot + (size_t)t * kRows + tid) / (float)D;
+      }
+      __syncthreads();
+      for (int tile = u0; tile < u1;) {
+        const int g = tile / tpg;
+        const int seg_end = min(u1, (g + 1) * tpg);
+        auto aval = [&](int r, int k) -> float {
+          const size_t at = (size_t)r * D + (size_t)g * Dg + k;
+          return norm_bwd_elem(ldcg(g_h + at), yhid[at], a.s_hid[g * Dg + k], rstd_a[r], coef_a[r]);
+        };
+        if (BF) { build_afrag(afrag, Dg, aval); }
+        for (int base = tile; base < seg_end; base += kMaxTiles) {
+          const int nt = min(kMaxTiles, seg_end - base);
+          tile_gemm<ENG, false>(blk_b5, per_b5, base - u0, wf_b5, base, nt, Dg, afrag4, aval, out, red_after(Dg));
+          const int ncols = nt * 8;
+          for (int i = tid; i < kRows * ncols; i += kThreads) {
+            const int r = i / ncols, c = i - r * ncols;
+            const int n = (base - g * tpg) * 8 + c;          // column within the group's Kh inputs
+            if (n < Dg) {
+              const size_t at = (size_t)r * D + (size_t)g * Dg + n;
+              a.gd_carry[at] = ldcg(keep + r) * (ldcg(a.gd_tmp + at) + out[i]);
+            } else {
+              const int m = n - Dg;                          // [x0 | x1 | x2]
+              float* dst = m < H ? a.g_x0 : (m < 2 * H ? a.g_x1 : a.g_x2);
+              atomicAdd(dst + (size_t)t * RH + (size_t)r * H + (m % H), out[i]);
+            }
+          }
+          __syncthreads();
+        }
+        tile = seg_end;
+      }
+    }
+    bar.sync();
+  }
+}
+
+size_t bwd_smem_bytes(const emb_rssm_bwd_args& a) {
+  const size_t n = sizeof(float) * (kRows * kMaxTiles * 8 + 64);
+  const int Dg = a.D / a.G, SC = a.S * a.C;
+  if (a.engine != rssm::ENG_BF16) return n + (size_t)kRows * SC * sizeof(float);
+  int kmax = 3 * Dg;
+  if (2 * a.H > kmax) kmax = 2 * a.H;
+  if (SC > kmax) kmax = SC;
+  return n + (size_t)kRows * kmax * 2 + (size_t)kWarps * kRows * kMaxTiles * 8 * sizeof(float);
+}
+
+int g_sms = 0;
+
+}  // namespace
+
+extern "C" int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream) {
+  const char* who = "emb_rssm_observe_bwd";
+  if (!args) return emb::fail(-1, "%s: args is NULL", who);
+  const emb_rssm_bwd_args& a = *args;
+  if (a.B < 1 || a.B > kRows) return emb::fail(-1, "%s: B=%d outside [1,16]", who, a.B);
+  if (a.T < 1) return emb::fail(-1, "%s: T=%d < 1", who, a.T);
+  if (a.G < 1 || a.D % a.G || (a.D / a.G) % 16 || a.H % 16 || (a.S * a.C) % 16 || a.D % 16)
+    return emb::fail(-1, "%s: D/G, H and S*C must be multiples of 16", who);
+  if (a.engine != rssm::ENG_F32 && a.engine != rssm::ENG_BF16)
+    return emb::fail(-1, "%s: engine %d", who, a.engine);
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return emb::fail_cuda(who);
+  }
+  if (a.ncta < 1 || a.ncta > g_sms)
+    return emb::fail(-1, "%s: ncta=%d outside [1, %d SMs] (cooperative grid)", who, a.ncta, g_sms);
+  const size_t smem = bwd_smem_bytes(a);
+  if (smem > 227 * 1024)
+    return emb::fail(-1, "%s: needs %zu bytes of shared memory (> 227 KiB)", who, smem);
+  const void* fn = a.engine == rssm::ENG_BF16 ? (const void*)rssm_bwd_kernel<rssm::ENG_BF16>
+                                              : (const void*)rssm_bwd_kernel<rssm::ENG_F32>;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return emb::fail_cuda(who);
+  emb_rssm_bwd_args copy = a;
+  void* params[] = {&copy};
+  if (cudaLaunchCooperativeKernel(fn, dim3(a.ncta), dim3(kThreads), params, smem,
+                                  (cudaStream_t)stream) != cudaSuccess)
+    return emb::fail_cuda(who);
+  emb::count_launch();
+  return 0;
+}

@@ -339,7 +339,9 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
         for (int i = 0; i < 4; ++i) {
           const int c = lane + 32 * i;
           if (c < d.C) {
-            const float pm = (1.0f - d.unimix) * (e[i] / z) + d.unimix / (float)d.C;
+            const float pr = e[i] / z;
+            a.probs[(size_t)t * RSC + (size_t)r * d.SC + (size_t)sv * d.C + c] = pr;
+            const float pm = (1.0f - d.unimix) * pr + d.unimix / (float)d.C;
             const float v = logf(pm) + gv[i];
             if (v > best) { best = v; arg = c; }
           }

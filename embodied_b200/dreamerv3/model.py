@@ -50,6 +50,11 @@ class Model:
     self.bins = torch.cat([half, -half[:-1].flip(0)], 0).to(self.device)   # heads.py:132-144
     self.ret_lo = torch.zeros((), dtype=f32, device=self.device)
     self.ret_hi = torch.zeros((), dtype=f32, device=self.device)
+    self.scan = None
+    if cfg.get('fused_scan', True) and self.device.type == 'cuda':
+      from . import scan as scanlib
+      engine = scanlib.ENG_BF16 if self.cd == torch.bfloat16 else scanlib.ENG_F32
+      self.scan = scanlib.Scan(cfg, store, engine)
 
   # ---------------------------------------------------------------- primitives
   def W(self, name):
@@ -152,6 +157,8 @@ class Model:
     tok = torch.addmm(bobs, tokens.reshape(B * T, -1), wobs[D:]).reshape(B, T, -1)
     deter, stoch = carry
     deter, stoch = deter.to(self.cd), stoch.to(self.cd)
+    if self.scan is not None and B <= 16:
+      return self.observe_fused(deter, stoch, x2, tok, reset, gumbel)
     deters, stochs, logits = [], [], []
     for t in range(T):
       keep = (~reset[:, t]).to(self.cd)
@@ -165,6 +172,23 @@ class Model:
     feat = dict(deter=torch.stack(deters, 1), stoch=torch.stack(stochs, 1),
                 logit=torch.stack(logits, 1))
     return (deter, stoch), feat
+
+  def observe_fused(self, deter0, stoch0, x2, tok, reset, gumbel):
+    """The T-step scan as one kernel each way (emb_rssm_observe_fwd/bwd).  Step
+    0's dynin0/dynin1 pre-activations are computed here because the carry may
+    be an arbitrary (not one-hot) stoch."""
+    from . import scan as scanlib
+    B, T = reset.shape
+    keep = (~reset).to(f32)
+    k0 = keep[:, 0].to(self.cd)[:, None]
+    y0 = k0 * (deter0 @ self.W('dyn/dynin0/kernel')) + self.W('dyn/dynin0/bias')
+    y1 = k0 * (stoch0.reshape(B, -1) @ self.W('dyn/dynin1/kernel')) + self.W('dyn/dynin1/bias')
+    weights = [self.store.w[n] for n in scanlib.PARAMS]
+    deter, logit, stoch, _ = scanlib.ObserveFn.apply(
+        self.scan, deter0.detach(), y0.to(f32), y1.to(f32), x2.to(f32), tok.to(f32), keep,
+        gumbel, *weights)
+    feat = dict(deter=deter, stoch=stoch, logit=logit)
+    return (deter[:, -1], stoch[:, -1]), feat
 
   def prior(self, deter):                                    # rssm.py:161-171
     x = deter

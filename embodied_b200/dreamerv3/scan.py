@@ -30,7 +30,7 @@ class FwdArgs(ctypes.Structure):
           'b0', 'b1', 'b_hid', 'b_gru', 'b_logit', 's0', 's1', 's_hid', 's_obs',
           'deter0', 'x2', 'pre_tok', 'keep', 'gumbel',
           'deter', 'logit', 'index',
-          'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'deterA', 'barrier', 'timing')])
+          'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'probs', 'deterA', 'barrier', 'timing')])
 
 
 def _bind(lib):
@@ -117,6 +117,8 @@ class Scan:
     _bind(self.lib)
     self.packed = None
     self.packed_step = -1
+    self.packed_bwd = None
+    self.packed_bwd_step = -1
     self.timing = False
     self.ncta = int(self.lib.emb_device_sm_count())
     if self.ncta <= 0:
@@ -152,11 +154,14 @@ class Scan:
         gumbel=time_major(gumbel.reshape(B, T, S * C), B),
         deter=z(T, ROWS, D), logit=z(T, ROWS, S * C),
         index=torch.zeros((T, ROWS, S), dtype=torch.int32, device=dev),
-        y0=z(T + 1, ROWS, H), y1=z(T + 1, ROWS, H), yhid=z(T, ROWS, D),
+        y0=torch.zeros((T + 1, ROWS, H), dtype=f32, device=dev),
+        y1=torch.zeros((T + 1, ROWS, H), dtype=f32, device=dev), yhid=z(T, ROWS, D),
+        probs=torch.zeros((T, ROWS, S * C), dtype=f32, device=dev),
         gates=z(T, 4, ROWS, D), yobs=z(T, ROWS, H),
         sumsq=torch.zeros((T, ROWS), dtype=f32, device=dev),
         deterA=torch.empty(2 * ROWS * D + ROWS * H, dtype=torch.bfloat16, device=dev),
         barrier=torch.zeros(4, dtype=torch.int32, device=dev))
+    sv['x2_f32'] = sv['x2']
     if self.engine == ENG_BF16:
       sv['x2'] = a_fragments(sv['x2'])
     sv['y0'][0] = rows16(y0.to(f32), B)
@@ -171,6 +176,8 @@ class Scan:
     if self.timing:
       sv['timing'] = torch.zeros((T, 16), dtype=torch.int64, device=dev)
     for k, v in {**w, **vec, **sv}.items():
+      if k == 'x2_f32':
+        continue
       assert v.is_contiguous(), k
       setattr(args, k, v.data_ptr())
     stream = torch.cuda.current_stream(dev).cuda_stream
@@ -181,3 +188,188 @@ class Scan:
         logit=sv['logit'][:, :B].transpose(0, 1).reshape(B, T, S, C),
         index=sv['index'][:, :B].transpose(0, 1))
     return out, sv
+
+
+# ---------------------------------------------------------------------- backward
+class BwdArgs(ctypes.Structure):
+  _fields_ = (
+      [(n, _i32) for n in ('B', 'T', 'D', 'H', 'S', 'C', 'G', 'engine', 'ncta', 'pad_')] +
+      [('unimix', _fl), ('eps', _fl)] +
+      [(n, _vp) for n in (
+          'wt_in1', 'wt_logit', 'wt_ph1', 'wt_gru', 'wt_hid', 's0', 's1', 's_hid', 's_obs',
+          'keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates', 'sumsq', 'probs',
+          'G_deter', 'G_logit', 'G_stoch',
+          'g_xo', 'g_logit', 'g_gates', 'g_h', 'g_x0', 'g_x1', 'g_x2',
+          'g_stoch', 'gd_carry', 'gd_tmp', 'dot', 'barrier')])
+
+
+@torch.no_grad()
+def pack_bwd(store, cfg, engine, ncta):
+  """Transposed copies for the backward scan (same packed layouts)."""
+  D, G, H = cfg.deter, cfg.blocks, cfg.hidden
+  Dg = D // G
+  m = lambda n: store.view('master', n)
+  wobs = m('dyn/obs0/kernel')
+  ph1 = torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1)              # (D, 2H)
+  gru = m('dyn/dyngru/kernel')                                        # (G, Dg, 3Dg) -> (3Dg, G*Dg)
+  gru_t = gru.permute(2, 0, 1).reshape(3 * Dg, D)
+  hid = m('dyn/dynhid0/kernel')                                       # (G, Kh, Dg) -> (Dg, G*Kh)
+  hid_t = hid.permute(2, 0, 1).reshape(Dg, G * hid.shape[1])
+  return dict(
+      wt_in1=pack_matrix(m('dyn/dynin1/kernel').t(), engine, ncta),
+      wt_logit=pack_matrix(m('dyn/obslogit/kernel').t(), engine, ncta),
+      wt_ph1=pack_matrix(ph1.t(), engine, ncta),
+      wt_gru=pack_matrix(gru_t, engine, ncta),
+      wt_hid=pack_matrix(hid_t, engine, ncta))
+
+
+def _bind_bwd(lib):
+  if getattr(lib, '_rssm_bwd_bound', False):
+    return
+  lib.emb_rssm_observe_bwd.argtypes = [ctypes.POINTER(BwdArgs), _vp]
+  lib.emb_rssm_observe_bwd.restype = ctypes.c_int
+  lib._rssm_bwd_bound = True
+
+
+def _silu(x):
+  return x * torch.sigmoid(x)
+
+
+def _dsilu(n):
+  sg = torch.sigmoid(n)
+  return sg * (1 + n * (1 - sg))
+
+
+def _norm_bwd(gx, y, s, eps=1e-4):
+  """Through x = silu(rms(y) * s): returns (g_y, g_s, x)."""
+  rstd = torch.rsqrt(y.square().mean(-1, keepdim=True) + eps)
+  yhat = y * rstd
+  n = yhat * s
+  gn = gx * _dsilu(n)
+  gs = (gn * yhat).reshape(-1, y.shape[-1]).sum(0)
+  gy = rstd * s * gn - yhat * rstd * (gn * s * yhat).mean(-1, keepdim=True)
+  return gy, gs, _silu(n)
+
+
+@torch.no_grad()
+def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
+  """Runs emb_rssm_observe_bwd and forms every parameter / input gradient.
+  G_*: batch-major upstream gradients (B, T, ..).  Returns (input grads, param grads)."""
+  cfg, dev, lib = scan.cfg, G_deter.device, scan.lib
+  _bind_bwd(lib)
+  T = sv['keep'].shape[0] - 1
+  D, H, S, C, G = cfg.deter, cfg.hidden, cfg.stoch, cfg.classes, cfg.blocks
+  Dg, SC, Kh = D // G, S * C, D // G + 3 * H
+  if scan.packed_bwd is None or scan.packed_bwd_step != scan.store.version:
+    scan.packed_bwd = pack_bwd(scan.store, cfg, scan.engine, scan.ncta)
+    scan.packed_bwd_step = scan.store.version
+  m = lambda n: scan.store.view('master', n)
+  zeros = lambda *s: torch.zeros(s, dtype=f32, device=dev)
+  empty = lambda *s: torch.empty(s, dtype=f32, device=dev)
+  x2f = sv['x2_f32']
+  buf = dict(
+      G_deter=time_major(G_deter, B), G_logit=time_major(G_logit.reshape(B, T, SC), B),
+      G_stoch=time_major(G_stoch.reshape(B, T, SC), B),
+      g_xo=empty(T, ROWS, H), g_logit=zeros(T, ROWS, SC), g_gates=empty(T, ROWS, 3 * D),
+      g_h=empty(T, ROWS, D), g_x0=zeros(T + 1, ROWS, H), g_x1=zeros(T + 1, ROWS, H),
+      g_x2=zeros(T, ROWS, H), g_stoch=empty(ROWS, SC), gd_carry=zeros(ROWS, D),
+      gd_tmp=empty(ROWS, D), dot=zeros(T, ROWS),
+      barrier=torch.zeros(4, dtype=torch.int32, device=dev))
+  vec = dict(s0=m('dyn/dynin0norm/scale'), s1=m('dyn/dynin1norm/scale'),
+             s_hid=m('dyn/dynhid0norm/scale'), s_obs=m('dyn/obs0norm/scale'))
+  saved = {k: sv[k] for k in ('keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates',
+                              'sumsq', 'probs')}
+  args = BwdArgs(B=B, T=T, D=D, H=H, S=S, C=C, G=G, engine=scan.engine, ncta=scan.ncta,
+                 unimix=cfg.unimix, eps=1e-4)
+  for k, v in {**scan.packed_bwd, **vec, **saved, **buf}.items():
+    assert v.is_contiguous(), k
+    setattr(args, k, v.data_ptr())
+  stream = torch.cuda.current_stream(dev).cuda_stream
+  _lib.check(lib.emb_rssm_observe_bwd(ctypes.byref(args), stream))
+
+  # ---- parameter gradients: (T*16)-row GEMMs over the per-step layer gradients
+  cd = torch.bfloat16 if scan.engine == ENG_BF16 else f32
+  mm = lambda a, b: (a.to(cd).t() @ b.to(cd)).to(f32)
+  keep = sv['keep'][:T]                                               # (T, 16)
+  deter = sv['deter']
+  dprev = torch.cat([sv['deter0'][None], deter[:-1]], 0) * keep[..., None]
+  R = T * ROWS
+  s0, s1, s_hid, s_obs = vec['s0'], vec['s1'], vec['s_hid'], vec['s_obs']
+  g_y0, g_s0, x0 = _norm_bwd(buf['g_x0'][:T], sv['y0'][:T], s0)
+  g_y1, g_s1, x1 = _norm_bwd(buf['g_x1'][:T], sv['y1'][:T], s1)
+  g_yhid, g_shid, h = _norm_bwd(buf['g_h'], sv['yhid'], s_hid)
+  g_yobs, g_sobs, xo = _norm_bwd(buf['g_xo'], sv['yobs'], s_obs)
+  pg = {}
+  # dynin0 / dynin1: steps >= 1 run inside the kernel (step 0 is an input)
+  pg['dyn/dynin0/kernel'] = mm(dprev[1:].reshape(-1, D), g_y0[1:].reshape(-1, H))
+  pg['dyn/dynin0/bias'] = g_y0[1:].reshape(-1, H).sum(0)
+  pg['dyn/dynin0norm/scale'] = g_s0
+  w1 = torch.zeros((SC, H), dtype=f32, device=dev)
+  if T > 1:
+    idx = sv['index'][:T - 1].long()                                  # (T-1, 16, S): stoch of step t-1
+    rows = (idx + torch.arange(S, device=dev) * C)                    # row of dynin1 per latent
+    contrib = (g_y1[1:] * keep[1:, :, None])[:, :, None, :].expand(-1, -1, S, -1)
+    valid = torch.zeros(ROWS, dtype=torch.bool, device=dev)
+    valid[:B] = True
+    contrib = contrib * valid[None, :, None, None]
+    w1.index_add_(0, rows.reshape(-1), contrib.reshape(-1, H))
+  pg['dyn/dynin1/kernel'] = w1
+  pg['dyn/dynin1/bias'] = g_y1[1:].reshape(-1, H).sum(0)
+  pg['dyn/dynin1norm/scale'] = g_s1
+  x012 = torch.cat([x0, x1, x2f], -1)                                 # (T, 16, 3H)
+  inp = torch.cat([dprev.reshape(T, ROWS, G, Dg),
+                   x012[:, :, None, :].expand(-1, -1, G, -1)], -1)    # (T, 16, G, Kh)
+  gyh = g_yhid.reshape(R, G, Dg)
+  pg['dyn/dynhid0/kernel'] = torch.einsum(
+      'rgk,rgj->gkj', inp.reshape(R, G, Kh).to(cd), gyh.to(cd)).to(f32)
+  pg['dyn/dynhid0/bias'] = g_yhid.reshape(R, D).sum(0)
+  pg['dyn/dynhid0norm/scale'] = g_shid
+  gg = buf['g_gates'].reshape(R, G, 3 * Dg)
+  pg['dyn/dyngru/kernel'] = torch.einsum(
+      'rgk,rgn->gkn', h.reshape(R, G, Dg).to(cd), gg.to(cd)).to(f32)
+  pg['dyn/dyngru/bias'] = gg.reshape(R, 3 * D).sum(0)
+  wobs = torch.zeros_like(m('dyn/obs0/kernel'))
+  wobs[:D] = mm(deter.reshape(R, D), g_yobs.reshape(R, H))
+  pg['dyn/obs0/kernel'] = wobs
+  pg['dyn/obs0norm/scale'] = g_sobs
+  pg['dyn/obslogit/kernel'] = mm(xo.reshape(R, H), buf['g_logit'].reshape(R, SC))
+  pg['dyn/obslogit/bias'] = buf['g_logit'].reshape(R, SC).sum(0)
+  bm = lambda x: x[:, :B].transpose(0, 1)
+  ig = dict(y0=g_y0[0, :B], y1=g_y1[0, :B], x2=bm(buf['g_x2']), pre_tok=bm(g_yobs))
+  return ig, pg, buf
+
+
+PARAMS = (
+    'dyn/dynin0/kernel', 'dyn/dynin0/bias', 'dyn/dynin0norm/scale',
+    'dyn/dynin1/kernel', 'dyn/dynin1/bias', 'dyn/dynin1norm/scale',
+    'dyn/dynhid0/kernel', 'dyn/dynhid0/bias', 'dyn/dynhid0norm/scale',
+    'dyn/dyngru/kernel', 'dyn/dyngru/bias',
+    'dyn/obs0/kernel', 'dyn/obs0norm/scale',
+    'dyn/obslogit/kernel', 'dyn/obslogit/bias')
+
+
+class ObserveFn(torch.autograd.Function):
+  """deter, logit, stoch = RSSM.observe over T steps, one kernel each way."""
+
+  @staticmethod
+  def forward(ctx, scan, deter0, y0, y1, x2, pre_tok, keep, gumbel, *weights):
+    out, sv = scan.forward(deter0, y0, y1, x2, pre_tok, keep, gumbel)
+    cfg = scan.cfg
+    B = keep.shape[0]
+    ctx.scan, ctx.sv, ctx.B = scan, sv, B
+    stoch = torch.nn.functional.one_hot(out['index'].long(), cfg.classes).to(deter0.dtype)
+    ctx.mark_non_differentiable(out['index'])
+    return out['deter'].to(deter0.dtype), out['logit'], stoch, out['index']
+
+  @staticmethod
+  def backward(ctx, G_deter, G_logit, G_stoch, _):
+    scan, sv, B = ctx.scan, ctx.sv, ctx.B
+    T = sv['keep'].shape[0] - 1
+    cfg = scan.cfg
+    z = lambda g, *s: torch.zeros((B, T, *s), dtype=f32, device=sv['deter'].device) \
+        if g is None else g.to(f32)
+    ig, pg, _ = scan_backward(
+        scan, sv, B, z(G_deter, cfg.deter), z(G_logit, cfg.stoch, cfg.classes),
+        z(G_stoch, cfg.stoch, cfg.classes))
+    return (None, None, ig['y0'], ig['y1'], ig['x2'], ig['pre_tok'], None, None,
+            *[pg[n] for n in PARAMS])

@@ -161,6 +161,7 @@ typedef struct emb_rssm_fwd_args {
   float* gates;          /* [T][4][16][D] reset, cand, update after their nonlinearity; cand before tanh/reset */
   float* yobs;           /* [T][16][H]   pre-norm obs0 */
   float* sumsq;          /* [T][16]      row sums of yhid^2; ZEROED by the caller */
+  float* probs;          /* [T][16][S*C] softmax(logit) before unimix; rows < B written */
   /* scratch */
   void* deterA;          /* bf16 engine scratch: (2*16*D + 16*H) bf16, A-fragment order */
   uint32_t* barrier;     /* one ZEROED u32 */
@@ -168,6 +169,44 @@ typedef struct emb_rssm_fwd_args {
 } emb_rssm_fwd_args;
 
 int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream);
+
+/* Back-propagation through time of the same scan (embodied_b200/csrc/rssm_bwd.cu).
+ * Consumes the activations emb_rssm_observe_fwd saved and the upstream
+ * gradients of its three outputs; produces, per step, the upstream gradient of
+ * every in-scan layer, from which the caller forms all parameter gradients
+ * with (B*T)-row GEMMs.  Weights are the TRANSPOSED matrices in the same packed
+ * layouts as the forward pass. */
+typedef struct emb_rssm_bwd_args {
+  int32_t B, T, D, H, S, C, G;
+  int32_t engine, ncta, pad_;
+  float unimix, eps;
+  const void* wt_in1;    /* [H][S*C]        dynin1/kernel^T                              */
+  const void* wt_logit;  /* [S*C][H]        obslogit/kernel^T                            */
+  const void* wt_ph1;    /* [2H][D]         (obs0/kernel[:D] | dynin0/kernel)^T          */
+  const void* wt_gru;    /* [3D/G][D]       column (g, j) = dyngru/kernel[g][j][:]       */
+  const void* wt_hid;    /* [D/G][G*(D/G+3H)] column (g, n) = dynhid0/kernel[g][n][:]    */
+  const float *s0, *s1, *s_hid, *s_obs;
+  /* saved by the forward pass */
+  const float *keep, *deter0, *deter, *y0, *y1, *yobs, *yhid, *gates, *sumsq, *probs;
+  /* upstream gradients of the forward outputs, [T][16][..], rows >= B zero */
+  const float *G_deter, *G_logit, *G_stoch;
+  /* per-step layer gradients (outputs) */
+  float* g_xo;           /* [T][16][H]    wrt silu(rms(obs0))                    */
+  float* g_logit;        /* [T][16][S*C]  wrt obslogit's output (total)          */
+  float* g_gates;        /* [T][16][3D]   wrt dyngru's output, (g, gate, j) order */
+  float* g_h;            /* [T][16][D]    wrt silu(rms(dynhid0))                 */
+  float* g_x0;           /* [T+1][16][H]  wrt silu(rms(dynin0)); ZEROED          */
+  float* g_x1;           /* [T+1][16][H]  wrt silu(rms(dynin1)); ZEROED          */
+  float* g_x2;           /* [T][16][H]    wrt the hoisted action branch; ZEROED  */
+  /* scratch */
+  float* g_stoch;        /* [16][S*C] */
+  float* gd_carry;       /* [16][D] ZEROED; ends as the gradient wrt keep_0 * deter0 */
+  float* gd_tmp;         /* [16][D] */
+  float* dot;            /* [T][16] ZEROED */
+  uint32_t* barrier;     /* one ZEROED u32 */
+} emb_rssm_bwd_args;
+
+int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream);
 
 #ifdef __cplusplus
 }

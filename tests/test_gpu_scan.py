@@ -106,3 +106,48 @@ def test_forward_bf16_engine_tracks_oracle(name, over, B, T):
   # until the first sampled latent differs the trajectories coincide to bf16 accuracy
   assert rel(out['deter'][:, 0], feat['deter'][:, 0]) < 2e-2
   assert rel(out['logit'][:, 0], feat['logit'][:, 0]) < 3e-2
+
+
+def _functional(ocfg, B, T, seed):
+  g = torch.Generator().manual_seed(seed)
+  return (torch.randn(B, T, ocfg.deter, generator=g),
+          torch.randn(B, T, ocfg.stoch, ocfg.classes, generator=g),
+          torch.randn(B, T, ocfg.stoch, ocfg.classes, generator=g))
+
+
+@pytest.mark.parametrize('name,over,B,T', [CASES[0], CASES[1], CASES[3]])
+def test_backward_fp32_engine_matches_oracle_autograd(name, over, B, T):
+  """Gradients of a random linear functional of (deter, logit, stoch) with respect to
+  every parameter the scan touches, through emb_rssm_observe_bwd + the host's
+  parameter-gradient GEMMs, against torch autograd of the oracle's per-step loop."""
+  from embodied_b200.dreamerv3 import model as modellib
+  ocfg = do.tiny_config(**over)
+  vals, oracle, tokens, action, reset, deter0, stoch0, gumbel = setup(ocfg, B, T, 2)
+  Rd, Rl, Rs = _functional(ocfg, B, T, 7)
+  names = [k for k in vals if k.startswith('dyn/') and 'prior' not in k]
+  leaves = {k: vals[k].clone().requires_grad_(True) for k in names}
+  oracle.p = {**vals, **leaves}
+  tok_leaf = tokens.clone().requires_grad_(True)
+  _, feat = oracle.observe(dict(deter=deter0, stoch=stoch0), tok_leaf, action, reset, gumbel)
+  loss = (feat['deter'] * Rd).sum() + (feat['logit'] * Rl).sum() + (feat['stoch'] * Rs).sum()
+  loss.backward()
+
+  cfg = cases.product_config(ocfg)
+  store = paramlib.ParamStore(cfg, 'cuda', torch.float32, 0, {k: v.numpy() for k, v in vals.items()})
+  torch.backends.cuda.matmul.allow_tf32 = False
+  model = modellib.Model(cfg, store)
+  assert model.scan is not None
+  c = lambda x: x.cuda()
+  tok_dev = c(tokens).requires_grad_(True)
+  _, f2 = model.observe((c(deter0), c(stoch0)), tok_dev, c(action), c(reset), c(gumbel))
+  assert torch.equal(f2['stoch'].argmax(-1).cpu(), feat['stoch'].argmax(-1))
+  assert rel(f2['deter'], feat['deter']) < 1e-5
+  l2 = (f2['deter'] * c(Rd)).sum() + (f2['logit'] * c(Rl)).sum() + (f2['stoch'] * c(Rs)).sum()
+  l2.backward()
+  worst = []
+  for k in names:
+    a, b = store.view('grad', k).cpu().double(), leaves[k].grad.double()
+    worst.append((float((a - b).norm() / (b.norm() + 1e-30)), k))
+  assert max(worst)[0] < 1e-4, sorted(worst)[-5:]
+  a, b = tok_dev.grad.cpu().double(), tok_leaf.grad.double()
+  assert float((a - b).norm() / b.norm()) < 1e-4
