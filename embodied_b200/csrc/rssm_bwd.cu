@@ -29,41 +29,37 @@ namespace {
 
 using namespace rssm;
 
+template <bool FAST>
 __device__ __forceinline__ float dsilu(float n) {          // d silu(n) / dn
-  const float sg = 1.0f / (1.0f + expf(-n));
+  const float sg = FAST ? __fdividef(1.0f, 1.0f + __expf(-n)) : 1.0f / (1.0f + expf(-n));
   return sg * (1.0f + n * (1.0f - sg));
 }
 
-// For every row of a [16][n] layer: rstd = rsqrt(mean(y^2)+eps) and
-// coef = rstd^3 * mean(g_n * s * y) with g_n = g_x * silu'(y*rstd*s), so that
-//   g_y = rstd * s * g_n - y * coef            (rms-norm backward, nets.py:374-383)
-__device__ __forceinline__ void norm_bwd_stats(const float* gx, const float* y, const float* s,
-                                               int n, float eps, float* rstd, float* coef) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int r = warp; r < kRows; r += kWarps) {
-    float ss = 0.f;
-    for (int i = lane; i < n; i += 32) {
-      const float v = ldcg(y + (size_t)r * n + i);
-      ss = fmaf(v, v, ss);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-    const float rs = rsqrtf(ss / (float)n + eps);
-    float dot = 0.f;
-    for (int i = lane; i < n; i += 32) {
-      const float v = ldcg(y + (size_t)r * n + i);
-      const float gn = ldcg(gx + (size_t)r * n + i) * dsilu(v * rs * s[i]);
-      dot = fmaf(gn * s[i], v, dot);
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    if (lane == 0) { rstd[r] = rs; coef[r] = rs * rs * rs * dot / (float)n; }
-  }
+// rms-norm + silu backward (nets.py:374-383):  with n = y * rstd * s,
+//   g_n = g_x * silu'(n),   g_y = rstd * s * g_n - y * coef,   coef = rstd^3 * mean_k(g_n s y)
+// The row statistic `dot = sum_k g_n s y` is accumulated by the PRODUCER of g_x
+// (atomics into a.dots), so consumers apply this element-wise.
+template <bool FAST>
+__device__ __forceinline__ float norm_bwd_elem(float gx, float y, float s, float rstd, float coef) {
+  const float gn = gx * dsilu<FAST>(y * rstd * s);
+  return rstd * s * gn - y * coef;
 }
 
-__device__ __forceinline__ float norm_bwd_elem(float gx, float y, float s, float rstd, float coef) {
-  const float gn = gx * dsilu(y * rstd * s);
-  return rstd * s * gn - y * coef;
+// A fragments from two fp32 [16][n] sources: f(r, k, v1, v2), four k per thread.
+template <typename F>
+__device__ __forceinline__ void build_part2(__nv_bfloat16* afrag, int koff, const float* s1, int ld1,
+                                            const float* s2, int ld2, int n, F f) {
+  const int n4 = n >> 2;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < kRows * n4; i += kThreads) {
+    const int r = i / n4, k = (i - r * n4) << 2;
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(s1 + (size_t)r * ld1 + k));
+    const float4 w = __ldcg(reinterpret_cast<const float4*>(s2 + (size_t)r * ld2 + k));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k)) =
+        __floats2bfloat162_rn(f(r, k, v.x, w.x), f(r, k + 1, v.y, w.y));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k + 2)) =
+        __floats2bfloat162_rn(f(r, k + 2, v.z, w.z), f(r, k + 3, v.w, w.w));
+  }
 }
 
 template <int ENG>
@@ -71,9 +67,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool BF = ENG == ENG_BF16;
-  const int B = a.B, T = a.T, D = a.D, H = a.H, S = a.S, C = a.C, G = a.G;
+  const int T = a.T, D = a.D, H = a.H, S = a.S, C = a.C, G = a.G;
   const int Dg = D / G, SC = S * C, Kh = Dg + 3 * H;
-  (void)B;
   float* out = reinterpret_cast<float*>(smem_raw);                   // [16][kMaxTiles*8]
   float* st = out + kRows * kMaxTiles * 8;                           // 4 x [16] row statistics
   float *rstd_a = st, *coef_a = st + 16, *rstd_b = st + 32, *coef_b = st + 48;
@@ -104,10 +99,29 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   const float* wf_b4 = reinterpret_cast<const float*>(a.wt_gru);
   const float* wf_b5 = reinterpret_cast<const float*>(a.wt_hid);
 
+  // row statistics of a normalised layer at step `ts`: slot 0 x0, 1 x1, 2 xo
+  auto load_stats = [&](int ts, int slot, int n, float* rstd, float* coef) {
+    if (tid < kRows) {
+      const float rs = a.rstd[(size_t)ts * 3 * kRows + slot * kRows + tid];
+      rstd[tid] = rs;
+      coef[tid] = rs * rs * rs * ldcg(a.dots + ((size_t)ts * 4 + slot) * kRows + tid) / (float)n;
+    }
+  };
+  // sum out[r][c0..c1) per row and add it to a.dots[ts][slot][r]
+  auto add_row_dots = [&](int ts, int slot, int ncols, int c0, int c1) {
+    if (tid < kRows && c0 < c1) {
+      float sum = 0.f;
+      for (int c = c0; c < c1; ++c) sum += out[tid * ncols + c];
+      atomicAdd(a.dots + ((size_t)ts * 4 + slot) * kRows + tid, sum);
+    }
+  };
+
   for (int t = T - 1; t >= 0; --t) {
     const float* keep = a.keep + (size_t)t * kRows;
     const float* keep_next = a.keep + (size_t)(t + 1) * kRows;
     const float* deter_prev = t == 0 ? a.deter0 : a.deter + (size_t)(t - 1) * RD;
+    const float* y0 = a.y0 + (size_t)t * RH;
+    const float* y1 = a.y1 + (size_t)t * RH;
     const float* y0n = a.y0 + (size_t)(t + 1) * RH;         // step t+1 (zeros at t = T-1)
     const float* y1n = a.y1 + (size_t)(t + 1) * RH;
     const float* gx0n = a.g_x0 + (size_t)(t + 1) * RH;
@@ -125,13 +139,17 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     {
       const int u0 = min(tiles_b1, cta * per_b1), u1 = min(tiles_b1, u0 + per_b1);
       if (u0 < u1) {
-        norm_bwd_stats(gx1n, y1n, a.s1, H, a.eps, rstd_a, coef_a);
+        load_stats(t + 1, 1, H, rstd_a, coef_a);
         __syncthreads();
         auto aval = [&](int r, int k) -> float {
-          return ldcg(keep_next + r) * norm_bwd_elem(
-              ldcg(gx1n + (size_t)r * H + k), ldcg(y1n + (size_t)r * H + k), a.s1[k], rstd_a[r], coef_a[r]);
+          return ldcg(keep_next + r) * norm_bwd_elem<false>(
+              ldcg(gx1n + (size_t)r * H + k), y1n[(size_t)r * H + k], a.s1[k], rstd_a[r], coef_a[r]);
         };
-        if (BF) { build_afrag(afrag, H, aval); }
+        if (BF) {
+          build_part2(afrag, 0, gx1n, H, y1n, H, H, [&](int r, int k, float gx, float y) {
+            return ldcg(keep_next + r) * norm_bwd_elem<true>(gx, y, a.s1[k], rstd_a[r], coef_a[r]); });
+          __syncthreads();
+        }
         for (int base = u0; base < u1; base += kMaxTiles) {
           const int nt = min(kMaxTiles, u1 - base);
           tile_gemm<ENG, false>(blk_b1, per_b1, base - u0, wf_b1, base, nt, H, afrag4, aval, out, red_after(H));
@@ -153,28 +171,41 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
       const int u0 = min(tiles_b2, cta * per_b2), u1 = min(tiles_b2, u0 + per_b2);
       // every CTA needs the full g_logit rows as its A operand; row r is also
       // written out (for dW) by CTA ncta-1-r.
-      const bool writer = ncta - 1 - cta >= 0 && ncta - 1 - cta < kRows;
-      if (u0 < u1 || writer) {
+      const int wrow = ncta - 1 - cta;
+      if (u0 < u1 || (wrow >= 0 && wrow < kRows)) {
         // bf16 engine: the rows go straight into A fragments; fp32 engine: fp32 rows in shared memory
         float* gl = reinterpret_cast<float*>(afrag);            // fp32 engine only: [16][SC]
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int grp = warp; grp < kRows * S; grp += kWarps) {
+        const float* pr = a.probs + (size_t)t * RSC;
+        const float* Gl = a.G_logit + (size_t)t * RSC;
+        // one thread per (row, latent): all loads are independent 16-byte loads
+        for (int grp = tid; grp < kRows * S; grp += kThreads) {
           const int r = grp / S, sv = grp - r * S;
           const size_t o = (size_t)r * SC + (size_t)sv * C;
           float dot = 0.f;
-          for (int c = lane; c < C; c += 32)
-            dot = fmaf(a.probs[(size_t)t * RSC + o + c], ldcg(a.g_stoch + o + c), dot);
-#pragma unroll
-          for (int k = 16; k; k >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, k);
-          for (int c = lane; c < C; c += 32) {
-            const float p = a.probs[(size_t)t * RSC + o + c];
-            const float v = a.G_logit[(size_t)t * RSC + o + c] +
-                (1.0f - a.unimix) * p * (ldcg(a.g_stoch + o + c) - dot);
-            if (BF) afrag[afrag_index(r, sv * C + c)] = __float2bfloat16_rn(v);
-            else gl[o + c] = v;
-            if (ncta - 1 - cta == r) g_logit[o + c] = v;
+          for (int c = 0; c < C; c += 4) {
+            const float4 p = *reinterpret_cast<const float4*>(pr + o + c);
+            const float4 g = __ldcg(reinterpret_cast<const float4*>(a.g_stoch + o + c));
+            dot += p.x * g.x + p.y * g.y + p.z * g.z + p.w * g.w;
+          }
+          for (int c = 0; c < C; c += 4) {
+            const float4 p = *reinterpret_cast<const float4*>(pr + o + c);
+            const float4 g = __ldcg(reinterpret_cast<const float4*>(a.g_stoch + o + c));
+            const float4 e = *reinterpret_cast<const float4*>(Gl + o + c);
+            const float um = 1.0f - a.unimix;
+            float4 v;
+            v.x = e.x + um * p.x * (g.x - dot); v.y = e.y + um * p.y * (g.y - dot);
+            v.z = e.z + um * p.z * (g.z - dot); v.w = e.w + um * p.w * (g.w - dot);
+            if (BF) {
+              const int k = sv * C + c;
+              *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k)) = __floats2bfloat162_rn(v.x, v.y);
+              *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k + 2)) = __floats2bfloat162_rn(v.z, v.w);
+            } else {
+              *reinterpret_cast<float4*>(gl + o + c) = v;
+            }
+            if (wrow == r) *reinterpret_cast<float4*>(g_logit + o + c) = v;
           }
         }
+        if (u0 < u1) load_stats(t, 2, H, rstd_a, coef_a);       // only rstd is used here
         __syncthreads();
         auto aval = [&](int r, int k) -> float { return gl[(size_t)r * SC + k]; };
         for (int base = u0; base < u1; base += kMaxTiles) {
@@ -183,8 +214,14 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
           const int ncols = nt * 8;
           for (int i = tid; i < kRows * ncols; i += kThreads) {
             const int r = i / ncols, c = i - r * ncols;
-            g_xo[(size_t)r * H + base * 8 + c] = out[i];
+            const int col = base * 8 + c;
+            const float gx = out[i];
+            g_xo[(size_t)r * H + col] = gx;
+            const float y = yobs[(size_t)r * H + col], sc = a.s_obs[col];
+            out[i] = gx * dsilu<BF>(y * rstd_a[r] * sc) * sc * y;      // g_n * s * y
           }
+          __syncthreads();
+          add_row_dots(t, 2, ncols, 0, ncols);
           __syncthreads();
         }
       }
@@ -197,18 +234,24 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     {
       const int u0 = min(tiles_b3, cta * per_b3), u1 = min(tiles_b3, u0 + per_b3);
       if (u0 < u1) {
-        norm_bwd_stats(g_xo, yobs, a.s_obs, H, a.eps, rstd_a, coef_a);
-        norm_bwd_stats(gx0n, y0n, a.s0, H, a.eps, rstd_b, coef_b);
+        load_stats(t, 2, H, rstd_a, coef_a);
+        load_stats(t + 1, 0, H, rstd_b, coef_b);
         __syncthreads();
         auto aval = [&](int r, int k) -> float {
           if (k < H)
-            return norm_bwd_elem(ldcg(g_xo + (size_t)r * H + k), ldcg(yobs + (size_t)r * H + k),
-                                 a.s_obs[k], rstd_a[r], coef_a[r]);
+            return norm_bwd_elem<false>(ldcg(g_xo + (size_t)r * H + k), yobs[(size_t)r * H + k],
+                                        a.s_obs[k], rstd_a[r], coef_a[r]);
           k -= H;
-          return ldcg(keep_next + r) * norm_bwd_elem(
-              ldcg(gx0n + (size_t)r * H + k), ldcg(y0n + (size_t)r * H + k), a.s0[k], rstd_b[r], coef_b[r]);
+          return ldcg(keep_next + r) * norm_bwd_elem<false>(
+              ldcg(gx0n + (size_t)r * H + k), y0n[(size_t)r * H + k], a.s0[k], rstd_b[r], coef_b[r]);
         };
-        if (BF) { build_afrag(afrag, 2 * H, aval); }
+        if (BF) {
+          build_part2(afrag, 0, g_xo, H, yobs, H, H, [&](int r, int k, float gx, float y) {
+            return norm_bwd_elem<true>(gx, y, a.s_obs[k], rstd_a[r], coef_a[r]); });
+          build_part2(afrag, H, gx0n, H, y0n, H, H, [&](int r, int k, float gx, float y) {
+            return ldcg(keep_next + r) * norm_bwd_elem<true>(gx, y, a.s0[k], rstd_b[r], coef_b[r]); });
+          __syncthreads();
+        }
         for (int base = u0; base < u1; base += kMaxTiles) {
           const int nt = min(kMaxTiles, u1 - base);
           tile_gemm<ENG, false>(blk_b3, per_b3, base - u0, wf_b3, base, nt, 2 * H, afrag4, aval, out, red_after(2 * H));
@@ -241,15 +284,17 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
       const int u0 = min(tiles_b4, cta * per_b4), u1 = min(tiles_b4, u0 + per_b4);
       const int tpg = Dg / 8;
       if (u0 < u1 && tid < kRows)
-        rstd_a[tid] = rsqrtf(ldcg(a.sumsq + (size_t)t * kRows + tid) / (float)D + a.eps);
+        rstd_a[tid] = rsqrtf(a.sumsq[(size_t)t * kRows + tid] / (float)D + a.eps);
       __syncthreads();
       for (int tile = u0; tile < u1;) {
         const int g = tile / tpg;
         const int seg_end = min(u1, (g + 1) * tpg);
-        auto aval = [&](int r, int k) -> float {
-          return ldcg(g_gates + (size_t)r * 3 * D + (size_t)g * 3 * Dg + k);
-        };
-        if (BF) { build_afrag(afrag, 3 * Dg, aval); }
+        const float* src = g_gates + (size_t)g * 3 * Dg;
+        auto aval = [&](int r, int k) -> float { return ldcg(src + (size_t)r * 3 * D + k); };
+        if (BF) {
+          build_part(afrag, 0, src, 3 * Dg, 3 * D, [&](int, int, float v) { return v; });
+          __syncthreads();
+        }
         for (int base = tile; base < seg_end; base += kMaxTiles) {
           const int nt = min(kMaxTiles, seg_end - base);
           tile_gemm<ENG, false>(blk_b4, per_b4, base - u0, wf_b4, base, nt, 3 * Dg, afrag4, aval, out, red_after(3 * Dg));
@@ -260,15 +305,11 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
             const size_t at = (size_t)r * D + col;
             const float gh = out[i];
             g_h[at] = gh;
-            const float y = yhid[at], s = a.s_hid[col];
-            out[i] = gh * dsilu(y * rstd_a[r] * s) * s * y;    // g_n * s * y
+            const float y = yhid[at], sc = a.s_hid[col];
+            out[i] = gh * dsilu<BF>(y * rstd_a[r] * sc) * sc * y;    // g_n * s * y
           }
           __syncthreads();
-          if (tid < kRows) {
-            float sum = 0.f;
-            for (int c = 0; c < ncols; ++c) sum += out[tid * ncols + c];
-            atomicAdd(a.dot + (size_t)t * kRows + tid, sum);
-          }
+          add_row_dots(t, 3, ncols, 0, ncols);
           __syncthreads();
         }
         tile = seg_end;
@@ -282,9 +323,11 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
       const int u0 = min(tiles_b5, cta * per_b5), u1 = min(tiles_b5, u0 + per_b5);
       const int tpg = Kh / 8;
       if (u0 < u1 && tid < kRows) {
-        const float rs = rsqrtf(ldcg(a.sumsq + (size_t)t * kRows + tid) / (float)D + a.eps);
+        const float rs = rsqrtf(a.sumsq[(size_t)t * kRows + tid] / (float)D + a.eps);
         rstd_a[tid] = rs;
-        coef_a[tid] = rs * rs * rs * ldcg(a.dot + (size_t)t * kRows + tid) / (float)D;
+        coef_a[tid] = rs * rs * rs * ldcg(a.dots + ((size_t)t * 4 + 3) * kRows + tid) / (float)D;
+        rstd_b[tid] = a.rstd[(size_t)t * 3 * kRows + tid];             // y0[t]
+        coef_b[tid] = a.rstd[(size_t)t * 3 * kRows + kRows + tid];     // y1[t] (rstd, not a coef)
       }
       __syncthreads();
       for (int tile = u0; tile < u1;) {
@@ -292,25 +335,46 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
         const int seg_end = min(u1, (g + 1) * tpg);
         auto aval = [&](int r, int k) -> float {
           const size_t at = (size_t)r * D + (size_t)g * Dg + k;
-          return norm_bwd_elem(ldcg(g_h + at), yhid[at], a.s_hid[g * Dg + k], rstd_a[r], coef_a[r]);
+          return norm_bwd_elem<false>(ldcg(g_h + at), yhid[at], a.s_hid[g * Dg + k], rstd_a[r], coef_a[r]);
         };
-        if (BF) { build_afrag(afrag, Dg, aval); }
+        if (BF) {
+          build_part2(afrag, 0, g_h + (size_t)g * Dg, D, yhid + (size_t)g * Dg, D, Dg,
+                      [&](int r, int k, float gx, float y) {
+            return norm_bwd_elem<true>(gx, y, a.s_hid[g * Dg + k], rstd_a[r], coef_a[r]); });
+          __syncthreads();
+        }
         for (int base = tile; base < seg_end; base += kMaxTiles) {
           const int nt = min(kMaxTiles, seg_end - base);
           tile_gemm<ENG, false>(blk_b5, per_b5, base - u0, wf_b5, base, nt, Dg, afrag4, aval, out, red_after(Dg));
           const int ncols = nt * 8;
+          const int n0 = (base - g * tpg) * 8;               // first column within the group's Kh inputs
           for (int i = tid; i < kRows * ncols; i += kThreads) {
             const int r = i / ncols, c = i - r * ncols;
-            const int n = (base - g * tpg) * 8 + c;          // column within the group's Kh inputs
+            const int n = n0 + c;
+            const float v = out[i];
+            float prod = 0.f;
             if (n < Dg) {
               const size_t at = (size_t)r * D + (size_t)g * Dg + n;
-              a.gd_carry[at] = ldcg(keep + r) * (ldcg(a.gd_tmp + at) + out[i]);
+              a.gd_carry[at] = ldcg(keep + r) * (ldcg(a.gd_tmp + at) + v);
             } else {
               const int m = n - Dg;                          // [x0 | x1 | x2]
-              float* dst = m < H ? a.g_x0 : (m < 2 * H ? a.g_x1 : a.g_x2);
-              atomicAdd(dst + (size_t)t * RH + (size_t)r * H + (m % H), out[i]);
+              const int which = m / H, k = m - which * H;
+              float* dst = which == 0 ? a.g_x0 : (which == 1 ? a.g_x1 : a.g_x2);
+              atomicAdd(dst + (size_t)t * RH + (size_t)r * H + k, v);
+              if (which == 0) {
+                const float y = y0[(size_t)r * H + k], sc = a.s0[k];
+                prod = v * dsilu<BF>(y * rstd_b[r] * sc) * sc * y;
+              } else if (which == 1) {
+                const float y = y1[(size_t)r * H + k], sc = a.s1[k];
+                prod = v * dsilu<BF>(y * coef_b[r] * sc) * sc * y;
+              }
             }
+            out[i] = prod;
           }
+          __syncthreads();
+          // columns [Dg, Dg+H) feed dots slot 0 (x0), [Dg+H, Dg+2H) slot 1 (x1)
+          add_row_dots(t, 0, ncols, max(0, Dg - n0), min(ncols, Dg + H - n0));
+          add_row_dots(t, 1, ncols, max(0, Dg + H - n0), min(ncols, Dg + 2 * H - n0));
           __syncthreads();
         }
         tile = seg_end;

@@ -69,7 +69,7 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   __nv_bfloat16* x0A = deterA + 2 * RD;                       // [16*H] x0 fragments
   // x0 = silu(rms(y0)) is built ONCE per step, row r by CTA ncta-1-r, instead
   // of by every CTA in its P4 prologue.
-  auto build_x0 = [&](const float* y0v) {
+  auto build_x0 = [&](const float* y0v, int tsave) {
     const int r = ncta - 1 - cta;
     if (!BF || r < 0 || r >= kRows) return;
     float s = 0.f;
@@ -84,6 +84,7 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
     float tot = 0.f;
     for (int w = 0; w < kWarps; ++w) tot += out[w];
     const float rstd = rsqrtf(tot / (float)d.H + d.eps);
+    if (tid == 0) a.rstd[(size_t)tsave * 3 * kRows + r] = rstd;
     for (int k = tid * 2; k < d.H; k += kThreads * 2) {
       const float2 v = __ldcg(reinterpret_cast<const float2*>(y0v + (size_t)r * d.H + k));
       *reinterpret_cast<__nv_bfloat162*>(x0A + afrag_index(r, k)) = __floats2bfloat162_rn(
@@ -98,7 +99,7 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
       const int r = (int)(i / d.D), k = (int)(i - (size_t)r * d.D);
       deterA[RD + afrag_index(r, k)] = __float2bfloat16_rn(a.deter0[i]);
     }
-    build_x0(a.y0);
+    build_x0(a.y0, 0);
     bar.sync();
   }
 
@@ -127,6 +128,10 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
         if (!BF) row_rstd(y0, d.H, d.eps, rstd_a);
         row_rstd(y1, d.H, d.eps, rstd_b);
         __syncthreads();
+        if (cta == 0 && tid < kRows) {
+          if (!BF) a.rstd[(size_t)t * 3 * kRows + tid] = rstd_a[tid];
+          a.rstd[(size_t)t * 3 * kRows + kRows + tid] = rstd_b[tid];
+        }
         if (BF) {   // the group-independent part of A: x0 (prebuilt), x1, x2 (prebuilt by the host)
           copy_frags(afrag4 + (d.Dg / 16) * 32, reinterpret_cast<const uint4*>(x0A), (d.H / 16) * 32);
           build_part(afrag, d.Dg + d.H, y1, d.H, d.H, [&](int r, int k, float v) {
@@ -279,6 +284,7 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
       if (u0 < u1) {
         row_rstd(yobs, d.H, d.eps, rstd_a);
         __syncthreads();
+        if (cta == 0 && tid < kRows) a.rstd[(size_t)t * 3 * kRows + 2 * kRows + tid] = rstd_a[tid];
         auto aval = [&](int r, int k) -> float {
           return silu_f(ldcg(yobs + (size_t)r * d.H + k) * (rstd_a[r] * a.s_obs[k]));
         };
@@ -300,7 +306,7 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
         }
       }
     }
-    if (!last) build_x0(a.y0 + (size_t)(t + 1) * RH);
+    if (!last) build_x0(a.y0 + (size_t)(t + 1) * RH, t + 1);
     MARK(8)
     bar.sync();
     MARK(9)

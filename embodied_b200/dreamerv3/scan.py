@@ -30,7 +30,7 @@ class FwdArgs(ctypes.Structure):
           'b0', 'b1', 'b_hid', 'b_gru', 'b_logit', 's0', 's1', 's_hid', 's_obs',
           'deter0', 'x2', 'pre_tok', 'keep', 'gumbel',
           'deter', 'logit', 'index',
-          'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'probs', 'deterA', 'barrier', 'timing')])
+          'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'probs', 'rstd', 'deterA', 'barrier', 'timing')])
 
 
 def _bind(lib):
@@ -157,6 +157,7 @@ class Scan:
         y0=torch.zeros((T + 1, ROWS, H), dtype=f32, device=dev),
         y1=torch.zeros((T + 1, ROWS, H), dtype=f32, device=dev), yhid=z(T, ROWS, D),
         probs=torch.zeros((T, ROWS, S * C), dtype=f32, device=dev),
+        rstd=torch.zeros((T + 1, 3, ROWS), dtype=f32, device=dev),
         gates=z(T, 4, ROWS, D), yobs=z(T, ROWS, H),
         sumsq=torch.zeros((T, ROWS), dtype=f32, device=dev),
         deterA=torch.empty(2 * ROWS * D + ROWS * H, dtype=torch.bfloat16, device=dev),
@@ -197,10 +198,10 @@ class BwdArgs(ctypes.Structure):
       [('unimix', _fl), ('eps', _fl)] +
       [(n, _vp) for n in (
           'wt_in1', 'wt_logit', 'wt_ph1', 'wt_gru', 'wt_hid', 's0', 's1', 's_hid', 's_obs',
-          'keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates', 'sumsq', 'probs',
+          'keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates', 'sumsq', 'probs', 'rstd',
           'G_deter', 'G_logit', 'G_stoch',
           'g_xo', 'g_logit', 'g_gates', 'g_h', 'g_x0', 'g_x1', 'g_x2',
-          'g_stoch', 'gd_carry', 'gd_tmp', 'dot', 'barrier')])
+          'g_stoch', 'gd_carry', 'gd_tmp', 'dots', 'barrier')])
 
 
 @torch.no_grad()
@@ -273,19 +274,26 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
       g_xo=empty(T, ROWS, H), g_logit=zeros(T, ROWS, SC), g_gates=empty(T, ROWS, 3 * D),
       g_h=empty(T, ROWS, D), g_x0=zeros(T + 1, ROWS, H), g_x1=zeros(T + 1, ROWS, H),
       g_x2=zeros(T, ROWS, H), g_stoch=empty(ROWS, SC), gd_carry=zeros(ROWS, D),
-      gd_tmp=empty(ROWS, D), dot=zeros(T, ROWS),
+      gd_tmp=empty(ROWS, D), dots=zeros(T + 1, 4, ROWS),
       barrier=torch.zeros(4, dtype=torch.int32, device=dev))
   vec = dict(s0=m('dyn/dynin0norm/scale'), s1=m('dyn/dynin1norm/scale'),
              s_hid=m('dyn/dynhid0norm/scale'), s_obs=m('dyn/obs0norm/scale'))
   saved = {k: sv[k] for k in ('keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates',
-                              'sumsq', 'probs')}
+                              'sumsq', 'probs', 'rstd')}
   args = BwdArgs(B=B, T=T, D=D, H=H, S=S, C=C, G=G, engine=scan.engine, ncta=scan.ncta,
                  unimix=cfg.unimix, eps=1e-4)
   for k, v in {**scan.packed_bwd, **vec, **saved, **buf}.items():
     assert v.is_contiguous(), k
     setattr(args, k, v.data_ptr())
   stream = torch.cuda.current_stream(dev).cuda_stream
+  ev = getattr(scan, 'bwd_events', None)
+  if ev is not None:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
   _lib.check(lib.emb_rssm_observe_bwd(ctypes.byref(args), stream))
+  if ev is not None:
+    e1.record()
+    ev.append((e0, e1))
 
   # ---- parameter gradients: (T*16)-row GEMMs over the per-step layer gradients
   cd = torch.bfloat16 if scan.engine == ENG_BF16 else f32

@@ -162,6 +162,7 @@ typedef struct emb_rssm_fwd_args {
   float* yobs;           /* [T][16][H]   pre-norm obs0 */
   float* sumsq;          /* [T][16]      row sums of yhid^2; ZEROED by the caller */
   float* probs;          /* [T][16][S*C] softmax(logit) before unimix; rows < B written */
+  float* rstd;           /* [T+1][3][16] rsqrt(mean(y^2)+eps) of y0[t], y1[t], yobs[t] */
   /* scratch */
   void* deterA;          /* bf16 engine scratch: (2*16*D + 16*H) bf16, A-fragment order */
   uint32_t* barrier;     /* one ZEROED u32 */
@@ -187,7 +188,7 @@ typedef struct emb_rssm_bwd_args {
   const void* wt_hid;    /* [D/G][G*(D/G+3H)] column (g, n) = dynhid0/kernel[g][n][:]    */
   const float *s0, *s1, *s_hid, *s_obs;
   /* saved by the forward pass */
-  const float *keep, *deter0, *deter, *y0, *y1, *yobs, *yhid, *gates, *sumsq, *probs;
+  const float *keep, *deter0, *deter, *y0, *y1, *yobs, *yhid, *gates, *sumsq, *probs, *rstd;
   /* upstream gradients of the forward outputs, [T][16][..], rows >= B zero */
   const float *G_deter, *G_logit, *G_stoch;
   /* per-step layer gradients (outputs) */
@@ -202,7 +203,7 @@ typedef struct emb_rssm_bwd_args {
   float* g_stoch;        /* [16][S*C] */
   float* gd_carry;       /* [16][D] ZEROED; ends as the gradient wrt keep_0 * deter0 */
   float* gd_tmp;         /* [16][D] */
-  float* dot;            /* [T][16] ZEROED */
+  float* dots;           /* [T+1][4][16] ZEROED: row dots of the norm backward of x0, x1, xo, h */
   uint32_t* barrier;     /* one ZEROED u32 */
 } emb_rssm_bwd_args;
 

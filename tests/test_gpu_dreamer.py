@@ -15,8 +15,10 @@ from oracle import dreamer_oracle as do                   # noqa: E402
 import dreamer_cases as cases                             # noqa: E402
 
 RTOL = 1e-5       # forward quantities: loss, deter, logits, per-(B,T) losses, latents
-GTOL = 1e-4       # gradients and post-update parameters: sums over B*T*... terms in a
-                  # different order on the GPU, then g / sqrt(nu) amplifies small g
+GTOL = 3e-4       # gradients and post-update parameters (relative L2 per tensor): sums
+                  # over B*T*... terms in a different (and, with the scan kernels' atomics,
+                  # run-to-run varying) order, cancellation-heavy for the norm scales,
+                  # then g / sqrt(nu) amplifies small g
 
 
 def rel(a, b):

@@ -61,6 +61,28 @@ def main():
       'B': B, 'T': T, 'ms': t * 1e3, 'us_per_step': t / T * 1e6,
       'weights_per_step_MB': wbytes / 1e6, 'algorithmic_bytes': wbytes * T,
       'GBs': wbytes * T / t / 1e9, 'frac_of_measured_peak': wbytes * T / t / 1e9 / PEAK}))
+  bench_bwd(sc, args, B, T, cfg, wbytes, size, engine)
+
+
+def bench_bwd(sc, args, B, T, cfg, wbytes, size, engine):
+  sc.timing = False
+  sc.bwd_events = []
+  g = torch.Generator(device='cuda').manual_seed(1)
+  r = lambda *s: torch.randn(s, generator=g, device='cuda') * 0.01
+  Gd, Gl, Gs = r(B, T, cfg.deter), r(B, T, cfg.stoch, cfg.classes), r(B, T, cfg.stoch, cfg.classes)
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+  for i in range(8):
+    out, sv = sc.forward(*args)
+    flush.zero_()
+    S.scan_backward(sc, sv, B, Gd, Gl, Gs)
+  torch.cuda.synchronize()
+  times = [a.elapsed_time(b) * 1e-3 for a, b in sc.bwd_events[3:]]
+  t = float(np.median(times))
+  print(json.dumps({
+      'kernel': 'rssm_bwd_kernel', 'size': size, 'engine': 'bf16' if engine else 'f32',
+      'B': B, 'T': T, 'ms': t * 1e3, 'us_per_step': t / T * 1e6,
+      'algorithmic_bytes': wbytes * T, 'GBs': wbytes * T / t / 1e9,
+      'frac_of_measured_peak': wbytes * T / t / 1e9 / PEAK}))
 
 
 if __name__ == '__main__':
