@@ -1,0 +1,259 @@
+// emb_rmsnorm_act_fwd / _bwd: rms-norm (+ silu) over the last axis as ONE pass
+// over HBM each way (embodied/jax/nets.py:361-399 `Norm('rms')` followed by
+// nets.act('silu'), the pattern after every Linear / Conv2D of dreamerv3).
+//
+//   fwd:  n = x * rsqrt(mean(x^2) + eps) * scale ;  y = act(cast(n))
+//   bwd:  g_n = g_y * act'(n) ;  g_scale += sum_rows g_n * xhat ;
+//         g_x = rstd * scale * g_n - xhat * rstd * mean(g_n * scale * xhat)
+//
+// HBM-bound: fwd reads x once and writes y once, bwd reads x and g_y once and
+// writes g_x once (the second and third sweep over a row hit L1/L2: a row is at
+// most 16 KiB).  One warp per row, 16-byte accesses, persistent grid of
+// 2 x SMs CTAs; the per-column scale gradient is reduced warp -> CTA (shared
+// memory) -> global (one atomicAdd per column per CTA).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/embodied_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxCols = 2048;          // bwd keeps cols/32 scale-gradient partials per lane
+constexpr int kMaxPerLane = kMaxCols / 32;
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __device__ static float round(float x) { return x; }
+};
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+      v[2 * i] = __low2float(h); v[2 * i + 1] = __high2float(h);
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static float round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+};
+
+__device__ __forceinline__ float warp_sum(float s) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+__device__ __forceinline__ float silu(float n) { return n / (1.0f + expf(-n)); }
+__device__ __forceinline__ float dsilu(float n) {
+  const float sg = 1.0f / (1.0f + expf(-n));
+  return sg * (1.0f + n * (1.0f - sg));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y,
+                       int64_t rows, int cols, int act, float eps) {
+  constexpr int N = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const T* xr = x + r * cols;
+    T* yr = y + r * cols;
+    float ss = 0.f;
+    for (int c = lane * N; c < cols; c += 32 * N) {
+      float v[N];
+      Vec<T>::load(xr + c, v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) ss = fmaf(v[i], v[i], ss);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)cols + eps);
+    for (int c = lane * N; c < cols; c += 32 * N) {
+      float v[N], o[N];
+      Vec<T>::load(xr + c, v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const float n = Vec<T>::round(v[i] * (rstd * scale[c + i]));   // cast back, then act (nets.py:397)
+        o[i] = act ? silu(n) : n;
+      }
+      Vec<T>::store(yr + c, o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                       const T* __restrict__ gy, T* __restrict__ gx, float* __restrict__ gscale,
+                       int64_t rows, int cols, int act, float eps) {
+  constexpr int N = Vec<T>::N;
+  extern __shared__ float part_raw[];      // [kWarps][cols]
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * kWarps + wid;
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  float gs[kMaxPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) gs[i] = 0.f;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const T* xr = x + r * cols;
+    const T* gr = gy + r * cols;
+    T* or_ = gx + r * cols;
+    float ss = 0.f;
+    for (int c = lane * N; c < cols; c += 32 * N) {
+      float v[N];
+      Vec<T>::load(xr + c, v);
+#pragma unroll
+      for (int i = 0; i < N; ++i) ss = fmaf(v[i], v[i], ss);
+    }
+    const float rstd = rsqrtf(warp_sum(ss) / (float)cols + eps);
+    float dot = 0.f;
+    int slot = 0;
+#pragma unroll
+    for (int j = 0; j < kMaxPerLane / N; ++j) {
+      const int c = lane * N + j * 32 * N;
+      if (c < cols) {
+        float v[N], g[N];
+        Vec<T>::load(xr + c, v);
+        Vec<T>::load(gr + c, g);
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float xh = v[i] * rstd, sc = scale[c + i];
+          const float gn = act ? g[i] * dsilu(Vec<T>::round(xh * sc)) : g[i];
+          gs[j * N + i] = fmaf(gn, xh, gs[j * N + i]);
+          dot = fmaf(gn * sc, xh, dot);
+        }
+      }
+    }
+    (void)slot;
+    const float mean = warp_sum(dot) / (float)cols;
+    for (int c = lane * N; c < cols; c += 32 * N) {
+      float v[N], g[N], o[N];
+      Vec<T>::load(xr + c, v);
+      Vec<T>::load(gr + c, g);
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const float xh = v[i] * rstd, sc = scale[c + i];
+        const float gn = act ? g[i] * dsilu(Vec<T>::round(xh * sc)) : g[i];
+        o[i] = rstd * (sc * gn - xh * mean);
+      }
+      Vec<T>::store(or_ + c, o);
+    }
+  }
+  // scale gradient: lane partials -> shared [warp][col] -> one atomicAdd per column per CTA
+#pragma unroll
+  for (int j = 0; j < kMaxPerLane / N; ++j) {
+    const int c = lane * N + j * 32 * N;
+    if (c < cols) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) part_raw[(size_t)wid * cols + c + i] = gs[j * N + i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += kThreads) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += part_raw[(size_t)w * cols + c];
+    atomicAdd(gscale + c, s);
+  }
+}
+
+int g_sms = 0;
+
+int check(const char* who, const void* x, const void* y, int64_t rows, int cols, int dtype) {
+  if (rows < 0 || cols <= 0) return emb::fail(-1, "%s: rows=%lld cols=%d", who, (long long)rows, cols);
+  if (dtype != 0 && dtype != 1) return emb::fail(-1, "%s: dtype %d (0 = f32, 1 = bf16)", who, dtype);
+  const int n = dtype ? 8 : 4;
+  if (cols % n) return emb::fail(-1, "%s: cols=%d must be a multiple of %d", who, cols, n);
+  if (((uintptr_t)x | (uintptr_t)y) & 15) return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return emb::fail_cuda(who);
+  }
+  return 0;
+}
+
+unsigned grid_for(int64_t rows) {
+  const int64_t want = (rows + kWarps - 1) / kWarps;
+  const int64_t cap = (int64_t)g_sms * 2;
+  return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+}  // namespace
+
+extern "C" int emb_rmsnorm_act_fwd(const void* x, const float* scale, void* y, int64_t rows,
+                                   int32_t cols, int32_t dtype, int32_t act, float eps, void* stream) {
+  const char* who = "emb_rmsnorm_act_fwd";
+  if (int e = check(who, x, y, rows, cols, dtype)) return e;
+  if (rows == 0) return 0;
+  const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps < (int64_t)g_sms * 8
+                                       ? (rows + kWarps - 1) / kWarps : (int64_t)g_sms * 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype)
+    rmsnorm_act_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(
+        (const __nv_bfloat16*)x, scale, (__nv_bfloat16*)y, rows, cols, act, eps);
+  else
+    rmsnorm_act_fwd_kernel<float><<<grid, kThreads, 0, s>>>(
+        (const float*)x, scale, (float*)y, rows, cols, act, eps);
+  emb::count_launch();
+  if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
+  return 0;
+}
+
+extern "C" int emb_rmsnorm_act_bwd(const void* x, const float* scale, const void* gy, void* gx,
+                                   float* gscale, int64_t rows, int32_t cols, int32_t dtype,
+                                   int32_t act, float eps, void* stream) {
+  const char* who = "emb_rmsnorm_act_bwd";
+  if (int e = check(who, x, gx, rows, cols, dtype)) return e;
+  if ((uintptr_t)gy & 15) return emb::fail(-1, "%s: gy must be 16-byte aligned", who);
+  if (cols > kMaxCols) return emb::fail(-1, "%s: cols=%d > %d", who, cols, kMaxCols);
+  if (rows == 0) return 0;
+  const unsigned grid = grid_for(rows);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = (size_t)kWarps * cols * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(rmsnorm_act_bwd_kernel<__nv_bfloat16>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kWarps * kMaxCols * sizeof(float))) != cudaSuccess ||
+        cudaFuncSetAttribute(rmsnorm_act_bwd_kernel<float>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kWarps * kMaxCols * sizeof(float))) != cudaSuccess)
+      return emb::fail_cuda(who);
+    attr_set = true;
+  }
+  if (dtype)
+    rmsnorm_act_bwd_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(
+        (const __nv_bfloat16*)x, scale, (const __nv_bfloat16*)gy, (__nv_bfloat16*)gx, gscale,
+        rows, cols, act, eps);
+  else
+    rmsnorm_act_bwd_kernel<float><<<grid, kThreads, smem, s>>>(
+        (const float*)x, scale, (const float*)gy, (float*)gx, gscale, rows, cols, act, eps);
+  emb::count_launch();
+  if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
+  return 0;
+}

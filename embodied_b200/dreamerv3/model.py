@@ -21,6 +21,8 @@ float32 (parity); norms, softmaxes and losses are always float32
 import torch
 import torch.nn.functional as F
 
+from . import ops
+
 f32 = torch.float32
 
 
@@ -50,6 +52,7 @@ class Model:
     self.bins = torch.cat([half, -half[:-1].flip(0)], 0).to(self.device)   # heads.py:132-144
     self.ret_lo = torch.zeros((), dtype=f32, device=self.device)
     self.ret_hi = torch.zeros((), dtype=f32, device=self.device)
+    self.fused_norm = bool(cfg.get('fused_norm', True)) and self.device.type == 'cuda'
     self.scan = None
     if cfg.get('fused_scan', True) and self.device.type == 'cuda':
       from . import scan as scanlib
@@ -74,6 +77,9 @@ class Model:
 
   def norm(self, x, name, act=True):                         # nets.py:369-399 'rms', eps 1e-4
     scale = self.store.w[f'{name}/scale']
+    need_grad = torch.is_grad_enabled() and (x.requires_grad or scale.requires_grad)
+    if self.fused_norm and ops.rmsnorm_supported(x, need_grad):
+      return ops.rmsnorm_act(x, scale, act)                  # one kernel each way
     xf = x.to(f32)
     y = xf * (torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-4) * scale)
     y = y.to(self.cd)

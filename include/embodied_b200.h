@@ -209,6 +209,17 @@ typedef struct emb_rssm_bwd_args {
 
 int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream);
 
+/* rms-norm (+ silu) over the last axis, one HBM pass each way
+ * (embodied/jax/nets.py:361-399 Norm('rms') followed by act, eps 1e-4).
+ * x, y, gy, gx: [rows][cols] contiguous, dtype 0 = fp32 / 1 = bf16, 16-byte
+ * aligned, cols % (16 / elem size) == 0; scale / gscale fp32 [cols].
+ * bwd ADDS the scale gradient into gscale and needs cols <= 2048. */
+int emb_rmsnorm_act_fwd(const void* x, const float* scale, void* y, int64_t rows,
+                        int32_t cols, int32_t dtype, int32_t act, float eps, void* stream);
+int emb_rmsnorm_act_bwd(const void* x, const float* scale, const void* gy, void* gx,
+                        float* gscale, int64_t rows, int32_t cols, int32_t dtype,
+                        int32_t act, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

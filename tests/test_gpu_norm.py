@@ -1,0 +1,58 @@
+"""emb_rmsnorm_act_fwd/bwd against the plain PyTorch fp32 formula of the
+reference's Norm('rms') + silu (embodied/jax/nets.py:361-399).  fp32: 1e-5
+relative (max-abs / max-abs); bf16: one bf16 ulp (2^-8) of the fp32 result."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+from embodied_b200.dreamerv3 import ops      # noqa: E402
+
+
+def reference(x, scale, act, dtype):
+  xf = x.float()
+  y = xf * (torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-4) * scale)
+  y = y.to(dtype)
+  return torch.nn.functional.silu(y) if act else y
+
+
+def rel(a, b):
+  return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize('rows,cols', [(1, 8), (7, 64), (1000, 128), (33, 1024), (4, 2048), (5, 8192)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('act', [True, False])
+def test_forward(rows, cols, dtype, act):
+  g = torch.Generator(device='cuda').manual_seed(rows * cols)
+  x = (torch.randn(rows, cols, generator=g, device='cuda') * 3).to(dtype)
+  scale = torch.rand(cols, generator=g, device='cuda') + 0.5
+  got = ops.rmsnorm_act(x, scale, act)
+  want = reference(x, scale, act, dtype)
+  assert got.dtype == dtype
+  assert rel(got, want) < (1e-5 if dtype == torch.float32 else 2 ** -7)
+
+
+@pytest.mark.parametrize('shape', [(3, 8), (2, 5, 64), (1000, 128), (9, 4, 4, 256), (4, 2048)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('act', [True, False])
+def test_backward(shape, dtype, act):
+  g = torch.Generator(device='cuda').manual_seed(len(shape) * shape[-1])
+  x = (torch.randn(*shape, generator=g, device='cuda') * 2).to(dtype)
+  scale = torch.rand(shape[-1], generator=g, device='cuda') + 0.5
+  gy = torch.randn(*shape, generator=g, device='cuda').to(dtype)
+  x1, s1 = x.clone().requires_grad_(True), scale.clone().requires_grad_(True)
+  ops.rmsnorm_act(x1, s1, act).backward(gy)
+  # fp32 reference of the same function (no bf16 rounding of intermediates)
+  x2, s2 = x.float().clone().requires_grad_(True), scale.clone().requires_grad_(True)
+  reference(x2, s2, act, torch.float32).backward(gy.float())
+  tol = 2e-5 if dtype == torch.float32 else 3e-2
+  assert rel(x1.grad, x2.grad) < tol
+  assert rel(s1.grad, s2.grad) < tol
+
+
+def test_unsupported_shapes_fall_back():
+  x = torch.randn(3, 12, device='cuda', dtype=torch.bfloat16)
+  assert not ops.rmsnorm_supported(x, False)
+  assert ops.rmsnorm_supported(torch.randn(3, 8192, device='cuda'), False)
+  assert not ops.rmsnorm_supported(torch.randn(3, 8192, device='cuda'), True)
