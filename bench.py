@@ -45,6 +45,8 @@ DETER, STOCH = 8192, (32, 64)       # size200m latents stored in replay (dreamer
 CLASSES = 5
 ROW_BYTES = 12288 + 32768 + 8192 + 20 + 4 + 4 + 3      # image, deter, stoch, stepid, reward, action, 3 flags
 TRAINS_PER_STEP = TRAIN_RATIO * NENVS // (B * T)        # 8
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/)
+NCU_TRAFFIC = {'rssm_fwd': 9898184000 + 181489920}
 
 
 def peaks():
@@ -219,6 +221,7 @@ def run_b200(args):
   assert world == args.gpus, (world, args.gpus)
   from embodied_b200 import _lib
   from embodied_b200.core import store as storelib
+  from embodied_b200.dreamerv3 import scan as scanlib
   peak, peak_src = peaks()
 
   capacity = int(args.capacity)
@@ -242,6 +245,7 @@ def run_b200(args):
       fn()
     barrier()
     storelib.PROFILE = [] if profile else None
+    scanlib.PROFILE = [] if profile else None
     launches0 = _lib.launch_count()
     total = 0.0
     for _ in range(steps):
@@ -257,6 +261,9 @@ def run_b200(args):
     barrier()
     launches = _lib.launch_count() - launches0
     prof, storelib.PROFILE = storelib.PROFILE, None
+    if scanlib.PROFILE:
+      prof = (prof or []) + [(k, a, b) for k, a, b, _ in scanlib.PROFILE]
+    scanlib.PROFILE = None
     t = torch.tensor([total], device='cuda', dtype=torch.float64)
     if world > 1:
       dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -267,11 +274,37 @@ def run_b200(args):
     t_e2e, _, _ = timed(loop.step_e2e, args.steps, args.warmup)
   clk = clocks.summary()
 
-  # dominant kernel: the replay gather launch (2 x B x L x row bytes per launch)
-  gather_us = [a.elapsed_time(b) * 1e3 for kind, a, b in prof if kind == 'gather']
+  # per-kernel live timings (CUDA events on the launching stream, inside the timed region)
+  def kernel_line(kind, name, nbytes, traffic):
+    us = [a.elapsed_time(b) * 1e3 for k, a, b in prof if k == kind]
+    if not us:
+      return None
+    t = float(np.mean(us))
+    ach = nbytes / (t * 1e-6) / 1e9
+    return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'peak_source': peak_src,
+            'unit': 'GB/s', 'frac': ach / peak, 'us_per_launch': t, 'launches_timed': len(us),
+            'algorithmic_bytes': nbytes, 'traffic': traffic}
   gather_bytes = 2 * B * L * (ROW_BYTES + 4)        # + the int32 consec key
-  g_us = float(np.mean(gather_us)) if gather_us else float('nan')
-  achieved = gather_bytes / (g_us * 1e-6) / 1e9
+  kernels = [kernel_line('gather', 'rows_kernel (emb_replay_gather, B=16 L=65)', gather_bytes,
+                         64950000)]                  # profiles/r01_rows_kernel_gather_B16_L65.md
+  if args.agent != 'feed':
+    cfg = loop.agent.cfg
+    Dg = cfg.deter // cfg.blocks
+    nw = (cfg.deter * 2 * cfg.hidden + cfg.hidden * cfg.stoch * cfg.classes +
+          cfg.deter * (Dg + 3 * cfg.hidden) + cfg.deter * 3 * Dg)
+    wbytes = nw * (2 if args.dtype == 'bfloat16' else 4) * T    # every in-scan weight once per step
+    # DRAM traffic per launch from ncu (profiles/r01_rssm_*_kernel.md), bf16 size200m only
+    known = args.dtype == 'bfloat16' and args.size == 'size200m'
+    kernels.append(kernel_line('rssm_bwd', 'rssm_bwd_kernel (emb_rssm_observe_bwd, B=16 T=64)', wbytes,
+                               NCU_TRAFFIC.get('rssm_bwd') if known else None))
+    kernels.append(kernel_line('rssm_fwd', 'rssm_fwd_kernel (emb_rssm_observe_fwd, B=16 T=64)', wbytes,
+                               NCU_TRAFFIC.get('rssm_fwd') if known else None))
+  kernels = [k for k in kernels if k]
+  # the roofline line is the hand-written kernel with the largest share of the step
+  share = lambda k: k['us_per_launch'] * k['launches_timed']
+  roofline = max(kernels, key=share)
+  for k in kernels:
+    k['share_of_step'] = share(k) * 1e-6 / t_dev
 
   env_steps = world * NENVS * args.steps
   h2d = NENVS * (12288 + 4 + 3 + 20 + 8) + TRAINS_PER_STEP * (B * L * 8 + B * T * 8)
@@ -294,11 +327,7 @@ def run_b200(args):
               'ms_per_step': t_e2e / args.steps * 1e3,
               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
       'gpu_launches': launches,
-      'roofline': {'kernel': 'rows_kernel (emb_replay_gather, B=16 L=65)', 'bound': 'hbm',
-                   'achieved': achieved, 'peak': peak, 'peak_source': peak_src,
-                   'unit': 'GB/s', 'frac': achieved / peak, 'us_per_launch': g_us,
-                   'launches_timed': len(gather_us), 'algorithmic_bytes': gather_bytes,
-                   'traffic': 64950000},   # profiles/r01_rows_kernel_gather_B16_L65.md
+      'roofline': roofline, 'kernels': kernels,
       'clocks': clk,
   }
   if rank == 0:

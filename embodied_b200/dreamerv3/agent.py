@@ -68,7 +68,6 @@ class Agent(base.Agent):
     if torch.distributed.is_available() and torch.distributed.is_initialized():
       self.world = torch.distributed.get_world_size()
       self.rank = torch.distributed.get_rank()
-      self.model.reduce_percentiles = self._gathered_percentiles
     self.gen = torch.Generator(device=self.device)
     self.gen.manual_seed(cfg.seed * 1000003 + self.rank)     # transform.py:84-85 fold_in(rank)
     self.updates = 0
@@ -201,11 +200,3 @@ class Agent(base.Agent):
       self.model.ret_lo = torch.as_tensor(data['retnorm/lo'], device=self.device)
       self.model.ret_hi = torch.as_tensor(data['retnorm/hi'], device=self.device)
     self.updates = int(data.get('updates', 0))
-
-  def _gathered_percentiles(self, q, x):                     # utils.py:83-88
-    cfg = self.cfg
-    parts = [torch.empty_like(x) for _ in range(self.world)]
-    torch.distributed.all_gather(parts, x.contiguous())
-    allx = torch.cat(parts)
-    return torch.quantile(allx, torch.tensor(
-        [cfg.perclo / 100, cfg.perchi / 100], device=x.device, dtype=f32))

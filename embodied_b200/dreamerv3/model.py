@@ -319,9 +319,16 @@ class Model:
     return self.ret_lo, torch.clamp(self.ret_hi - self.ret_lo, min=cfg.retnorm_limit)
 
   def reduce_percentiles(self, q, x):
-    """Multi-rank hook: utils.py:83-88 all_gathers the returns before the
-    percentile.  Replaced by the Agent when world_size > 1."""
-    return q
+    """utils.py:83-88: with data-parallel ranks the returns of ALL ranks are
+    gathered before the percentile, so every rank normalises identically."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+      return q
+    cfg = self.cfg
+    parts = [torch.empty_like(x) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, x.contiguous())
+    return torch.quantile(torch.cat(parts), torch.tensor(
+        [cfg.perclo / 100, cfg.perchi / 100], device=x.device, dtype=f32))
 
   # ----------------------------------------------------------------- imagination
   @torch.no_grad()

@@ -15,6 +15,9 @@ import torch
 from .. import _lib
 
 f32 = torch.float32
+# bench.py sets this to a list to collect (name, start, end) CUDA event triples
+# around the scan launches (live per-launch timing for the roofline line).
+PROFILE = None
 ROWS = 16
 ENG_F32, ENG_BF16 = 0, 1
 
@@ -182,7 +185,14 @@ class Scan:
       assert v.is_contiguous(), k
       setattr(args, k, v.data_ptr())
     stream = torch.cuda.current_stream(dev).cuda_stream
+    prof = PROFILE
+    if prof is not None:
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
     _lib.check(self.lib.emb_rssm_observe_fwd(ctypes.byref(args), stream))
+    if prof is not None:
+      e1.record()
+      prof.append(('rssm_fwd', e0, e1, T))
     self.last_args = args
     out = dict(
         deter=sv['deter'][:, :B].transpose(0, 1),
@@ -287,13 +297,17 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
     setattr(args, k, v.data_ptr())
   stream = torch.cuda.current_stream(dev).cuda_stream
   ev = getattr(scan, 'bwd_events', None)
-  if ev is not None:
+  prof = PROFILE
+  if ev is not None or prof is not None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
   _lib.check(lib.emb_rssm_observe_bwd(ctypes.byref(args), stream))
-  if ev is not None:
+  if ev is not None or prof is not None:
     e1.record()
-    ev.append((e0, e1))
+    if ev is not None:
+      ev.append((e0, e1))
+    if prof is not None:
+      prof.append(('rssm_bwd', e0, e1, T))
 
   # ---- parameter gradients: (T*16)-row GEMMs over the per-step layer gradients
   cd = torch.bfloat16 if scan.engine == ENG_BF16 else f32
