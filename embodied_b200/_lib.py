@@ -42,6 +42,10 @@ EXPORTS = (
     'emb_device_sm_count', 'emb_rows_copy', 'emb_replay_gather',
     'emb_replay_append_rows', 'emb_replay_scatter_update',
     'emb_driver_stage_obs', 'emb_driver_scatter_mask_actions',
+    # learner (bound where they are used: dreamerv3/scan.py, ops.py, optim.py)
+    'emb_rssm_observe_fwd', 'emb_rssm_observe_bwd', 'emb_rmsnorm_act_fwd',
+    'emb_rmsnorm_act_bwd', 'emb_opt_agc_rms_momentum', 'emb_maxpool2_nhwc_fwd',
+    'emb_maxpool2_nhwc_bwd', 'emb_upsample2_nhwc_fwd', 'emb_upsample2_nhwc_bwd',
 )
 
 
@@ -68,7 +72,7 @@ def load():
     for name in ('emb_replay_append_rows', 'emb_replay_scatter_update',
                  'emb_driver_stage_obs', 'emb_driver_scatter_mask_actions'):
       getattr(lib, name).argtypes = [kp, ctypes.c_int, vp, i64, vp]
-    for name in EXPORTS[4:]:
+    for name in EXPORTS[4:10]:
       getattr(lib, name).restype = ctypes.c_int
     _LIB = lib
     return lib

@@ -10,7 +10,7 @@ import subprocess
 ROOT = pathlib.Path(__file__).resolve().parent
 CSRC = ROOT / 'csrc'
 LIB = ROOT / 'libembodied_b200.so'
-SOURCES = ['abi.cu', 'rows.cu', 'rssm_fwd.cu', 'rssm_bwd.cu', 'norm.cu']
+SOURCES = ['abi.cu', 'rows.cu', 'rssm_fwd.cu', 'rssm_bwd.cu', 'norm.cu', 'optim.cu', 'spatial.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
     '-std=c++17', '-Xcompiler', '-fPIC', '-shared',

@@ -60,10 +60,16 @@ template <> struct Vec<__nv_bfloat16> {
   __device__ static float round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 };
 
-__device__ __forceinline__ float warp_sum(float s) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+// sum over the `gs` (power of two) consecutive lanes that share a row
+__device__ __forceinline__ float group_sum(float s, int gs) {
+  for (int o = gs >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return s;
+}
+// lanes per row: the smallest power of two covering cols / N vectors, at most a warp
+__device__ __forceinline__ int group_size(int cols, int n) {
+  int gs = 1;
+  while (gs < 32 && gs * n < cols) gs <<= 1;
+  return gs;
 }
 
 __device__ __forceinline__ float silu(float n) { return n / (1.0f + expf(-n)); }
@@ -77,21 +83,25 @@ __global__ void __launch_bounds__(kThreads)
 rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y,
                        int64_t rows, int cols, int act, float eps) {
   constexpr int N = Vec<T>::N;
-  const int lane = threadIdx.x & 31;
+  const int gs = group_size(cols, N), rpw = 32 / gs;          // narrow rows: several per warp
+  const int lane = threadIdx.x & 31, lg = lane % gs, grp = lane / gs;
   const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    const T* xr = x + r * cols;
-    T* yr = y + r * cols;
+  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
+    const int64_t r = r0 + grp;
+    const bool live = r < rows;
+    const T* xr = x + (live ? r : 0) * cols;
+    T* yr = y + (live ? r : 0) * cols;
     float ss = 0.f;
-    for (int c = lane * N; c < cols; c += 32 * N) {
+    for (int c = lg * N; c < cols; c += gs * N) {
       float v[N];
       Vec<T>::load(xr + c, v);
 #pragma unroll
       for (int i = 0; i < N; ++i) ss = fmaf(v[i], v[i], ss);
     }
-    const float rstd = rsqrtf(warp_sum(ss) / (float)cols + eps);
-    for (int c = lane * N; c < cols; c += 32 * N) {
+    const float rstd = rsqrtf(group_sum(ss, gs) / (float)cols + eps);
+    if (!live) continue;
+    for (int c = lg * N; c < cols; c += gs * N) {
       float v[N], o[N];
       Vec<T>::load(xr + c, v);
 #pragma unroll
@@ -111,29 +121,31 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                        int64_t rows, int cols, int act, float eps) {
   constexpr int N = Vec<T>::N;
   extern __shared__ float part_raw[];      // [kWarps][cols]
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int gs_ = group_size(cols, N), rpw = 32 / gs_;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lg = lane % gs_, grp = lane / gs_;
   const int64_t warp = (int64_t)blockIdx.x * kWarps + wid;
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
-  float gs[kMaxPerLane];
+  float gsc[kMaxPerLane];                  // scale-gradient partials of this lane's columns
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) gs[i] = 0.f;
-  for (int64_t r = warp; r < rows; r += nwarps) {
-    const T* xr = x + r * cols;
-    const T* gr = gy + r * cols;
-    T* or_ = gx + r * cols;
+  for (int i = 0; i < kMaxPerLane; ++i) gsc[i] = 0.f;
+  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
+    const int64_t r = r0 + grp;
+    const bool live = r < rows;
+    const T* xr = x + (live ? r : 0) * cols;
+    const T* gr = gy + (live ? r : 0) * cols;
+    T* or_ = gx + (live ? r : 0) * cols;
     float ss = 0.f;
-    for (int c = lane * N; c < cols; c += 32 * N) {
+    for (int c = lg * N; c < cols; c += gs_ * N) {
       float v[N];
       Vec<T>::load(xr + c, v);
 #pragma unroll
       for (int i = 0; i < N; ++i) ss = fmaf(v[i], v[i], ss);
     }
-    const float rstd = rsqrtf(warp_sum(ss) / (float)cols + eps);
+    const float rstd = rsqrtf(group_sum(ss, gs_) / (float)cols + eps);
     float dot = 0.f;
-    int slot = 0;
 #pragma unroll
     for (int j = 0; j < kMaxPerLane / N; ++j) {
-      const int c = lane * N + j * 32 * N;
+      const int c = lg * N + j * gs_ * N;
       if (c < cols) {
         float v[N], g[N];
         Vec<T>::load(xr + c, v);
@@ -142,14 +154,14 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
         for (int i = 0; i < N; ++i) {
           const float xh = v[i] * rstd, sc = scale[c + i];
           const float gn = act ? g[i] * dsilu(Vec<T>::round(xh * sc)) : g[i];
-          gs[j * N + i] = fmaf(gn, xh, gs[j * N + i]);
+          if (live) gsc[j * N + i] = fmaf(gn, xh, gsc[j * N + i]);
           dot = fmaf(gn * sc, xh, dot);
         }
       }
     }
-    (void)slot;
-    const float mean = warp_sum(dot) / (float)cols;
-    for (int c = lane * N; c < cols; c += 32 * N) {
+    const float mean = group_sum(dot, gs_) / (float)cols;
+    if (!live) continue;
+    for (int c = lg * N; c < cols; c += gs_ * N) {
       float v[N], g[N], o[N];
       Vec<T>::load(xr + c, v);
       Vec<T>::load(gr + c, g);
@@ -162,13 +174,16 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
       Vec<T>::store(or_ + c, o);
     }
   }
-  // scale gradient: lane partials -> shared [warp][col] -> one atomicAdd per column per CTA
+  // scale gradient: row groups of a warp -> lane group 0 (shuffles) -> shared [warp][col]
+  // -> one atomicAdd per column per CTA
 #pragma unroll
   for (int j = 0; j < kMaxPerLane / N; ++j) {
-    const int c = lane * N + j * 32 * N;
-    if (c < cols) {
+    const int c = lg * N + j * gs_ * N;
 #pragma unroll
-      for (int i = 0; i < N; ++i) part_raw[(size_t)wid * cols + c + i] = gs[j * N + i];
+    for (int i = 0; i < N; ++i) {
+      float v = gsc[j * N + i];
+      for (int o = gs_; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (c < cols && grp == 0) part_raw[(size_t)wid * cols + c + i] = v;
     }
   }
   __syncthreads();

@@ -53,6 +53,7 @@ class Model:
     self.ret_lo = torch.zeros((), dtype=f32, device=self.device)
     self.ret_hi = torch.zeros((), dtype=f32, device=self.device)
     self.fused_norm = bool(cfg.get('fused_norm', True)) and self.device.type == 'cuda'
+    self.fused_spatial = bool(cfg.get('fused_spatial', True)) and self.device.type == 'cuda'
     self.scan = None
     if cfg.get('fused_scan', True) and self.device.type == 'cuda':
       from . import scan as scanlib
@@ -110,7 +111,7 @@ class Model:
     x = x.reshape(-1, *x.shape[-3:]).to(self.cd)
     for i in range(len(cfg.mults)):
       x = self.conv(x, f'enc/cnn{i}')
-      x = F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+      x = self.pool(x)
       x = self.norm(x, f'enc/cnn{i}norm')
     return x.reshape(*lead, -1)
 
@@ -243,10 +244,16 @@ class Model:
     x = torch.sigmoid(self.conv(self.upsample(x), 'dec/imgout').to(f32))
     return x.reshape(*lead, *x.shape[1:])
 
-  @staticmethod
-  def upsample(x):                                           # x.repeat(2,-2).repeat(2,-3)
+  def upsample(self, x):                                     # x.repeat(2,-2).repeat(2,-3), NHWC
+    if self.fused_spatial and ops.spatial_supported(x):
+      return ops.Upsample2.apply(x)
     y = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode='nearest')
     return y.permute(0, 2, 3, 1)
+
+  def pool(self, x):                                         # rssm.py:239-240, NHWC
+    if self.fused_spatial and ops.spatial_supported(x):
+      return ops.MaxPool2.apply(x)
+    return F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
 
   # ---------------------------------------------------------------------- heads
   def feat2tensor(self, deter, stoch):                       # agent.py:51-53

@@ -19,6 +19,12 @@ def _lib_bound():
     lib.emb_rmsnorm_act_fwd.restype = ctypes.c_int
     lib.emb_rmsnorm_act_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _fl, _vp]
     lib.emb_rmsnorm_act_bwd.restype = ctypes.c_int
+    for name in ('emb_maxpool2_nhwc_fwd', 'emb_maxpool2_nhwc_bwd'):
+      getattr(lib, name).argtypes = [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]
+      getattr(lib, name).restype = ctypes.c_int
+    for name in ('emb_upsample2_nhwc_fwd', 'emb_upsample2_nhwc_bwd'):
+      getattr(lib, name).argtypes = [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]
+      getattr(lib, name).restype = ctypes.c_int
     _bound = True
   return lib
 
@@ -73,3 +79,71 @@ class RmsNormAct(torch.autograd.Function):
 
 def rmsnorm_act(x, scale, act=True, eps=1e-4):
   return RmsNormAct.apply(x, scale, act, eps)
+
+
+def spatial_supported(x):
+  """x: NHWC, contiguous, fp32 / bf16, channels a multiple of one 16-byte vector."""
+  if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 4:
+    return False
+  per = 4 if x.dtype == torch.float32 else 8
+  return x.shape[-1] % per == 0 and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0
+
+
+class MaxPool2(torch.autograd.Function):
+  """(N, 2H, 2W, C) -> (N, H, W, C), NHWC (dreamerv3/rssm.py:239-240)."""
+
+  @staticmethod
+  def forward(ctx, x):
+    lib = _lib_bound()
+    x = x.contiguous()
+    n, h2, w2, c = x.shape
+    h, w = h2 // 2, w2 // 2
+    y = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+    per = 4 if x.dtype == torch.float32 else 8
+    idx = torch.empty(n * h * w * (c // per),
+                      dtype=torch.uint8 if per == 4 else torch.int16, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(lib.emb_maxpool2_nhwc_fwd(
+        x.data_ptr(), y.data_ptr(), idx.data_ptr(), n, h, w, c, _dtype_code(x), stream))
+    ctx.save_for_backward(idx)
+    ctx.shape = (n, h, w, c)
+    return y
+
+  @staticmethod
+  def backward(ctx, gy):
+    lib = _lib_bound()
+    idx, = ctx.saved_tensors
+    n, h, w, c = ctx.shape
+    gy = gy.contiguous()
+    gx = torch.empty((n, 2 * h, 2 * w, c), dtype=gy.dtype, device=gy.device)
+    stream = torch.cuda.current_stream(gy.device).cuda_stream
+    _lib.check(lib.emb_maxpool2_nhwc_bwd(
+        gy.data_ptr(), idx.data_ptr(), gx.data_ptr(), n, h, w, c, _dtype_code(gy), stream))
+    return gx
+
+
+class Upsample2(torch.autograd.Function):
+  """(N, H, W, C) -> (N, 2H, 2W, C) nearest, NHWC (dreamerv3/rssm.py:336,349)."""
+
+  @staticmethod
+  def forward(ctx, x):
+    lib = _lib_bound()
+    x = x.contiguous()
+    n, h, w, c = x.shape
+    y = torch.empty((n, 2 * h, 2 * w, c), dtype=x.dtype, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(lib.emb_upsample2_nhwc_fwd(
+        x.data_ptr(), y.data_ptr(), n, h, w, c, _dtype_code(x), stream))
+    ctx.shape = (n, h, w, c)
+    return y
+
+  @staticmethod
+  def backward(ctx, gy):
+    lib = _lib_bound()
+    n, h, w, c = ctx.shape
+    gy = gy.contiguous()
+    gx = torch.empty((n, h, w, c), dtype=gy.dtype, device=gy.device)
+    stream = torch.cuda.current_stream(gy.device).cuda_stream
+    _lib.check(lib.emb_upsample2_nhwc_bwd(
+        gy.data_ptr(), gx.data_ptr(), n, h, w, c, _dtype_code(gy), stream))
+    return gx

@@ -11,7 +11,12 @@
 
 and SlowModel.update (embodied/jax/utils.py:113-119): slow = r*val + (1-r)*slow.
 """
+import ctypes
+
+import numpy as np
 import torch
+
+CHUNK = 4096
 
 
 class Optimizer:
@@ -20,6 +25,9 @@ class Optimizer:
     self.cfg = cfg
     self.store = store
     names = list(store.specs)
+    self.fused = bool(cfg.get('fused_opt', True)) and store.device.type == 'cuda'
+    if self.fused:
+      self._init_fused(names)
     self._grads = [store.view('grad', n) for n in names]
     self._params = [store.view('master', n) for n in names]
     self._slow_pairs = [
@@ -32,12 +40,60 @@ class Optimizer:
       return cfg.lr * count / cfg.warmup
     return cfg.lr
 
+  def _init_fused(self, names):
+    from .. import _lib
+    st = self.store
+    self._lib = _lib
+    self.lib = _lib.load()
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    self.lib.emb_opt_agc_rms_momentum.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, vp, vp]
+    self.lib.emb_opt_agc_rms_momentum.restype = ctypes.c_int
+    rows = []
+    for ti, n in enumerate(names):
+      off, size = st.offsets[n], int(np.prod(st.specs[n][0]))
+      for b in range(0, size, CHUNK):
+        rows.append((off + b, min(CHUNK, size - b), ti))
+    table = np.zeros(len(rows), dtype=[('begin', '<i8'), ('count', '<i4'), ('tensor', '<i4')])
+    table['begin'], table['count'], table['tensor'] = zip(*rows)
+    self.nchunks, self.ntensors = len(rows), len(names)
+    self.chunks = torch.from_numpy(table.view(np.uint8).copy()).to(st.device)
+    self.norms = torch.zeros(2 * len(names), dtype=torch.float32, device=st.device)
+    self.hyper_host = torch.zeros(8, dtype=torch.float32, pin_memory=True)
+    self.hyper = torch.zeros(8, dtype=torch.float32, device=st.device)
+
+  def set_hyper(self):
+    """Step-dependent scalars -> device (outside any CUDA graph)."""
+    cfg, st = self.cfg, self.store
+    count = st.step
+    t = count + 1
+    h = self.hyper_host
+    h[0] = self.learning_rate(count)
+    h[1] = 1 / (1 - cfg.beta1 ** t)
+    h[2] = 1 / (1 - cfg.beta2 ** t)
+    h[3], h[4], h[5], h[6], h[7] = cfg.beta1, cfg.beta2, cfg.eps, cfg.agc, cfg.pmin
+    self.hyper.copy_(h, non_blocking=True)
+
+  def launch(self):
+    """The two optimiser kernels on the current stream (graph-capturable)."""
+    st = self.store
+    stream = torch.cuda.current_stream(st.device).cuda_stream
+    self._lib.check(self.lib.emb_opt_agc_rms_momentum(
+        st.grad.data_ptr(), st.master.data_ptr(), st.nu.data_ptr(), st.mu.data_ptr(),
+        self.chunks.data_ptr(), self.nchunks, self.norms.data_ptr(), self.ntensors,
+        self.hyper.data_ptr(), stream))
+
   @torch.no_grad()
   def step(self):
     cfg, st = self.cfg, self.store
     count = st.step
     t = count + 1
     lr = self.learning_rate(count)
+    if self.fused:
+      self.set_hyper()
+      self.launch()
+      st.step = t
+      st.version += 1
+      return {'opt/grad_norm': self.norms[0::2].sum().sqrt(), 'opt/updates': t, 'opt/lr': lr}
     gn = torch.stack(torch._foreach_norm(self._grads))
     pn = torch.stack(torch._foreach_norm(self._params))
     upper = cfg.agc * torch.clamp(pn, min=cfg.pmin)
@@ -56,5 +112,4 @@ class Optimizer:
   @torch.no_grad()
   def update_slow(self):
     r = self.cfg.slowrate
-    for slow, src in self._slow_pairs:
-      slow.mul_(1 - r).add_(src, alpha=r)
+    torch._foreach_lerp_([s for s, _ in self._slow_pairs], [v for _, v in self._slow_pairs], r)

@@ -220,6 +220,39 @@ int emb_rmsnorm_act_bwd(const void* x, const float* scale, const void* gy, void*
                         float* gscale, int64_t rows, int32_t cols, int32_t dtype,
                         int32_t act, float eps, void* stream);
 
+/* The optimiser chain of dreamerv3 on the flat parameter buffer, two HBM passes
+ * (dreamerv3/agent.py:342-379; embodied/jax/opt.py:109-164: clip_by_agc ->
+ * scale_by_rms -> scale_by_momentum -> learning rate).  `chunks` cuts the flat
+ * buffers into <= 4096-element pieces that lie inside one tensor (16-byte
+ * aligned begins); `norms` is scratch [ntensors][2] = (|g|^2, |w|^2) and is
+ * left filled (grad-norm metric).  hyper (DEVICE) = {lr, 1/(1-b1^t), 1/(1-b2^t),
+ * b1, b2, eps, agc clip, pmin}. */
+typedef struct emb_opt_chunk {
+  int64_t begin;
+  int32_t count;
+  int32_t tensor;
+} emb_opt_chunk;
+
+int emb_opt_agc_rms_momentum(const float* grad, float* param, float* nu, float* mu,
+                             const emb_opt_chunk* chunks, int32_t nchunks,
+                             float* norms, int32_t ntensors, const float* hyper,
+                             void* stream);
+
+/* Spatial glue of the dreamerv3 encoder / decoder on NHWC tensors, one HBM pass
+ * each (dreamerv3/rssm.py:239-240 2x2 max-pool; :336,349 nearest x2 up-sampling).
+ * (n, h, w, c) always describe the SMALL tensor (pool output / up-sample input);
+ * dtype 0 = fp32 / 1 = bf16; c % (16 / elem size) == 0; 16-byte aligned.
+ * idx: one u8 (fp32) / u16 (bf16) per 16-byte output vector, 2-bit argmax per
+ * element (first maximum in (dy, dx) row-major order). */
+int emb_maxpool2_nhwc_fwd(const void* x, void* y, void* idx, int64_t n, int32_t h, int32_t w,
+                          int32_t c, int32_t dtype, void* stream);
+int emb_maxpool2_nhwc_bwd(const void* gy, const void* idx, void* gx, int64_t n, int32_t h,
+                          int32_t w, int32_t c, int32_t dtype, void* stream);
+int emb_upsample2_nhwc_fwd(const void* x, void* y, int64_t n, int32_t h, int32_t w, int32_t c,
+                           int32_t dtype, void* stream);
+int emb_upsample2_nhwc_bwd(const void* gy, void* gx, int64_t n, int32_t h, int32_t w, int32_t c,
+                           int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -137,4 +137,5 @@ def test_save_load_roundtrip():
   other.load(blob)
   a = agent.train(agent.init_train(B), data, noise)[2]['loss']
   b = other.train(other.init_train(B), data, noise)[2]['loss']
-  assert float(a) == float(b)
+  # the scan kernels sum with atomics: equal up to summation order, not bit for bit
+  assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
