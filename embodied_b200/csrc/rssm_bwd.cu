@@ -86,13 +86,16 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   const int tiles_b1 = SC / 8, per_b1 = (tiles_b1 + ncta - 1) / ncta;
   const int tiles_b2 = H / 8, per_b2 = (tiles_b2 + ncta - 1) / ncta;
   const int tiles_b3 = D / 8, per_b3 = (tiles_b3 + ncta - 1) / ncta;
-  const int tiles_b4 = D / 8, per_b4 = (tiles_b4 + ncta - 1) / ncta;
-  const int tiles_b5 = G * Kh / 8, per_b5 = (tiles_b5 + ncta - 1) / ncta;
+  const GroupSplit sp_b4 = group_split(Dg / 8, G), sp_b5 = group_split(Kh / 8, G);
+  const int per_b4 = sp_b4.per, per_b5 = sp_b5.per;
   const uint2* blk_b1 = reinterpret_cast<const uint2*>(a.wt_in1) + (size_t)cta * (H / 16) * per_b1 * 32;
   const uint2* blk_b2 = reinterpret_cast<const uint2*>(a.wt_logit) + (size_t)cta * (SC / 16) * per_b2 * 32;
   const uint2* blk_b3 = reinterpret_cast<const uint2*>(a.wt_ph1) + (size_t)cta * (2 * H / 16) * per_b3 * 32;
   const uint2* blk_b4 = reinterpret_cast<const uint2*>(a.wt_gru) + (size_t)cta * (3 * Dg / 16) * per_b4 * 32;
   const uint2* blk_b5 = reinterpret_cast<const uint2*>(a.wt_hid) + (size_t)cta * (Dg / 16) * per_b5 * 32;
+  const size_t bytes_b1 = (size_t)(H / 16) * per_b1 * 256, bytes_b2 = (size_t)(SC / 16) * per_b2 * 256;
+  const size_t bytes_b3 = (size_t)(2 * H / 16) * per_b3 * 256, bytes_b4 = (size_t)(3 * Dg / 16) * per_b4 * 256;
+  const size_t bytes_b5 = (size_t)(Dg / 16) * per_b5 * 256;
   const float* wf_b1 = reinterpret_cast<const float*>(a.wt_in1);
   const float* wf_b2 = reinterpret_cast<const float*>(a.wt_logit);
   const float* wf_b3 = reinterpret_cast<const float*>(a.wt_ph1);
@@ -137,6 +140,7 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     // ------------------------------------------------------------------ B1
     // g_stoch[t] = G_stoch[t] + (keep' * g_y1') @ dynin1^T      (scratch: a.g_stoch)
     {
+      if (BF) { prefetch_l2(blk_b2, bytes_b2); prefetch_l2(blk_b3, bytes_b3); }   // one phase ahead
       const int u0 = min(tiles_b1, cta * per_b1), u1 = min(tiles_b1, u0 + per_b1);
       if (u0 < u1) {
         load_stats(t + 1, 1, H, rstd_a, coef_a);
@@ -232,6 +236,7 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     // g_deter = G_deter[t] + carry + [g_yobs | keep' g_y0'] @ [obs0[:D] | dynin0]^T, then the
     // GRU backward (rssm.py:152-158) for the same columns.
     {
+      if (BF) prefetch_l2(blk_b4, bytes_b4);
       const int u0 = min(tiles_b3, cta * per_b3), u1 = min(tiles_b3, u0 + per_b3);
       if (u0 < u1) {
         load_stats(t, 2, H, rstd_a, coef_a);
@@ -281,7 +286,8 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     // ------------------------------------------------------------------ B4
     // g_h_g = g_gates_g @ dyngru[g]^T ; row dots of the dynhid0 norm backward
     {
-      const int u0 = min(tiles_b4, cta * per_b4), u1 = min(tiles_b4, u0 + per_b4);
+      if (BF) prefetch_l2(blk_b5, bytes_b5);
+      const int u0 = sp_b4.u0, u1 = sp_b4.u1;
       const int tpg = Dg / 8;
       if (u0 < u1 && tid < kRows)
         rstd_a[tid] = rsqrtf(a.sumsq[(size_t)t * kRows + tid] / (float)D + a.eps);
@@ -320,7 +326,8 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     // ------------------------------------------------------------------ B5
     // g_in_g = g_yhid_g @ dynhid0[g]^T : deter part -> carry, x0/x1/x2 parts summed over groups
     {
-      const int u0 = min(tiles_b5, cta * per_b5), u1 = min(tiles_b5, u0 + per_b5);
+      if (BF && t > 0) prefetch_l2(blk_b1, bytes_b1);
+      const int u0 = sp_b5.u0, u1 = sp_b5.u1;
       const int tpg = Kh / 8;
       if (u0 < u1 && tid < kRows) {
         const float rs = rsqrtf(a.sumsq[(size_t)t * kRows + tid] / (float)D + a.eps);

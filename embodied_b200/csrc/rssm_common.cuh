@@ -232,6 +232,15 @@ __device__ __forceinline__ void tile_gemm(
   __syncthreads();
 }
 
+// Ask the memory system to pull this CTA's NEXT weight block (contiguous `bytes`)
+// from HBM into L2 while the current phase, its barrier and the next prologue run:
+// the block is then streamed at L2 latency, and HBM stays busy across barriers.
+__device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes) {
+  const char* c = reinterpret_cast<const char*>(p);
+  for (size_t off = (size_t)threadIdx.x * 128; off < bytes; off += (size_t)kThreads * 128)
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(c + off));
+}
+
 // Copy `n16` A fragments (uint4) from global (L2) to shared memory.
 __device__ __forceinline__ void copy_frags(uint4* dst, const uint4* src, int n16) {
 #pragma unroll 4
@@ -270,6 +279,23 @@ __device__ __forceinline__ void build_afrag(__nv_bfloat16* afrag, int K, AVal av
 struct NoVal {
   __device__ __forceinline__ float operator()(int, int) const { return 0.f; }
 };
+
+// Block-diagonal layers: CTA c works inside ONE group (ncta / groups CTAs per
+// group), on a run of `per` units of that group.  Same formulas as scan.py
+// tile_assignment().  Returns the global unit range [u0, u1).
+struct GroupSplit {
+  int per, u0, u1;
+};
+__device__ __forceinline__ GroupSplit group_split(int units_per_group, int groups) {
+  const int cpg = max(1, (int)gridDim.x / groups);
+  GroupSplit s;
+  s.per = (units_per_group + cpg - 1) / cpg;
+  const int g = blockIdx.x / cpg, j = blockIdx.x - g * cpg;
+  if (g >= groups) { s.u0 = s.u1 = 0; return s; }
+  s.u0 = g * units_per_group + min(units_per_group, j * s.per);
+  s.u1 = g * units_per_group + min(units_per_group, (j + 1) * s.per);
+  return s;
+}
 
 // CTA c's share [begin, end) of `total` work units.
 __device__ __forceinline__ void cta_range(int total, int& begin, int& end) {

@@ -53,8 +53,8 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   const size_t RH = (size_t)kRows * d.H, RD = (size_t)kRows * d.D, RSC = (size_t)kRows * d.SC;
 
   // static work split (must match scan.py pack(): per = ceil(tiles / ncta))
-  const int tiles_hid = d.D / 8, per_hid = (tiles_hid + ncta - 1) / ncta;
-  const int units_gru = d.D / 8, per_gru = (units_gru + ncta - 1) / ncta;
+  const GroupSplit sp_hid = group_split(d.Dg / 8, d.G), sp_gru = group_split(d.Dg / 8, d.G);
+  const int per_hid = sp_hid.per, per_gru = sp_gru.per;
   const int tiles_ph1 = 2 * d.H / 8, per_ph1 = (tiles_ph1 + ncta - 1) / ncta;
   const int tiles_log = d.SC / 8, per_log = (tiles_log + ncta - 1) / ncta;
   const uint2* blk_hid = reinterpret_cast<const uint2*>(a.w_hid) + (size_t)cta * (Kh / 16) * per_hid * 32;
@@ -66,6 +66,8 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   const float* wf_ph1 = reinterpret_cast<const float*>(a.w_ph1);
   const float* wf_log = reinterpret_cast<const float*>(a.w_logit);
   __nv_bfloat16* deterA = reinterpret_cast<__nv_bfloat16*>(a.deterA);
+  const size_t bytes_hid = (size_t)(Kh / 16) * per_hid * 256, bytes_gru = (size_t)(d.Dg / 16) * per_gru * 3 * 256;
+  const size_t bytes_ph1 = (size_t)(d.D / 16) * per_ph1 * 256, bytes_log = (size_t)(d.H / 16) * per_log * 256;
   __nv_bfloat16* x0A = deterA + 2 * RD;                       // [16*H] x0 fragments
   // x0 = silu(rms(y0)) is built ONCE per step, row r by CTA ncta-1-r, instead
   // of by every CTA in its P4 prologue.
@@ -100,6 +102,7 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
       deterA[RD + afrag_index(r, k)] = __float2bfloat16_rn(a.deter0[i]);
     }
     build_x0(a.y0, 0);
+    prefetch_l2(blk_hid, bytes_hid);
     bar.sync();
   }
 
@@ -122,7 +125,8 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
 
     // ------------------------------------------------------------------ P4
     {
-      const int u0 = min(tiles_hid, cta * per_hid), u1 = min(tiles_hid, u0 + per_hid);
+      if (BF) prefetch_l2(blk_gru, bytes_gru);                // P5's weights, one phase ahead
+      const int u0 = sp_hid.u0, u1 = sp_hid.u1;
       const int tpg = d.Dg / 8;                   // tiles per group
       if (u0 < u1) {
         if (!BF) row_rstd(y0, d.H, d.eps, rstd_a);
@@ -195,7 +199,8 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
     // ------------------------------------------------------------------ P5
     float* deter = a.deter + (size_t)t * RD;
     {
-      const int u0 = min(units_gru, cta * per_gru), u1 = min(units_gru, u0 + per_gru);
+      if (BF) prefetch_l2(blk_ph1, bytes_ph1);
+      const int u0 = sp_gru.u0, u1 = sp_gru.u1;
       const int upg = d.Dg / 8;
       if (u0 < u1) {
         if (tid < kRows)
@@ -251,6 +256,7 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
     // ------------------------------------------------------------------ P1
     float* yobs = a.yobs + (size_t)t * RH;
     {
+      if (BF) { prefetch_l2(blk_log, bytes_log); if (!last) prefetch_l2(blk_hid, bytes_hid); }
       const int total = (last ? d.H : 2 * d.H) / 8;
       const int u0 = min(total, cta * per_ph1), u1 = min(total, u0 + per_ph1);
       auto aval = [&](int r, int k) -> float { return ldcg(deter + (size_t)r * d.D + k); };
@@ -364,12 +370,39 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
           if (kn != 0.f) {
             const size_t row = (size_t)sv * d.C + arg;
             float* dst = a.y1 + (size_t)(t + 1) * RH + (size_t)r * d.H;
-#pragma unroll 8
-            for (int c = lane; c < d.H; c += 32) {
-              const float w = BF
-                  ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.w_in1)[row * d.H + c])
-                  : reinterpret_cast<const float*>(a.w_in1)[row * d.H + c];
-              atomicAdd(dst + c, kn * w);
+            // all loads of the 2 KiB row first (it may have left L2), then the adds
+            for (int c0 = 0; c0 < d.H; c0 += 32 * 32) {
+              float wv[32];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = c0 + (j * 32 + lane) * 8;
+                if (c < d.H) {
+                  if (BF) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(
+                        reinterpret_cast<const __nv_bfloat16*>(a.w_in1) + row * d.H + c);
+                    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                      const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&w4[i]);
+                      wv[j * 8 + 2 * i] = __low2float(h2); wv[j * 8 + 2 * i + 1] = __high2float(h2);
+                    }
+                  } else {
+                    const float* src = reinterpret_cast<const float*>(a.w_in1) + row * d.H + c;
+                    const float4 q0 = *reinterpret_cast<const float4*>(src);
+                    const float4 q1 = *reinterpret_cast<const float4*>(src + 4);
+                    wv[j * 8] = q0.x; wv[j * 8 + 1] = q0.y; wv[j * 8 + 2] = q0.z; wv[j * 8 + 3] = q0.w;
+                    wv[j * 8 + 4] = q1.x; wv[j * 8 + 5] = q1.y; wv[j * 8 + 6] = q1.z; wv[j * 8 + 7] = q1.w;
+                  }
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int c = c0 + (j * 32 + lane) * 8;
+                if (c < d.H) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) atomicAdd(dst + c + i, kn * wv[j * 8 + i]);
+                }
+              }
             }
           }
         }
@@ -386,18 +419,19 @@ size_t fwd_smem_bytes(const emb_rssm_fwd_args& a) {
   size_t n = sizeof(float) * (kRows * kMaxTiles * 8 + 2 * kRows);
   if (a.engine != rssm::ENG_BF16) return n;
   auto cdiv = [](int x, int y) { return (x + y - 1) / y; };
-  auto tiles = [&](int total, int unit) {
-    int per = cdiv(total / unit, a.ncta) * unit;
+  auto tiles = [&](int total, int unit, int groups) {     // n8 tiles one pass of this layer handles
+    const int cpg = groups > 1 ? (a.ncta / groups > 1 ? a.ncta / groups : 1) : a.ncta;
+    const int per = cdiv(total / groups / unit, cpg) * unit;
     return per < kMaxTiles ? per : (kMaxTiles / unit) * unit;
   };
   auto need = [&](int K, int nt) {
     return (size_t)kRows * K * 2 + (size_t)kWarps * kRows * nt * 8 * sizeof(float);
   };
   const int Dg = a.D / a.G, Kh = Dg + 3 * a.H;
-  size_t m = need(Kh, tiles(a.D / 8, 1));
-  size_t v = need(Dg, tiles(3 * a.D / 8, 3)); if (v > m) m = v;
-  v = need(0, tiles(2 * a.H / 8, 1)); if (v > m) m = v;
-  v = need(a.H, tiles(a.S * a.C / 8, 1)); if (v > m) m = v;
+  size_t m = need(Kh, tiles(a.D / 8, 1, a.G));
+  size_t v = need(Dg, tiles(3 * a.D / 8, 3, a.G)); if (v > m) m = v;
+  v = need(0, tiles(2 * a.H / 8, 1, 1)); if (v > m) m = v;
+  v = need(a.H, tiles(a.S * a.C / 8, 1, 1)); if (v > m) m = v;
   return n + m;
 }
 

@@ -44,24 +44,49 @@ def _bind(lib):
   lib._rssm_bound = True
 
 
-def pack_matrix(w, engine, ncta, unit=1):
+def tile_assignment(tiles, ncta, unit=1, groups=1):
+  """Which n8 column tiles each CTA owns: (per, ids[ncta][per]) with -1 = padding.
+
+  groups == 1: CTA c owns the run [c*per, (c+1)*per), per = ceil(tiles/unit/ncta)*unit.
+  groups  > 1 (block-diagonal layers): every CTA stays inside ONE group, so it
+  builds a single A operand per phase: ncta // groups CTAs per group, each a run
+  of per = ceil(tiles_per_group/unit / ctas_per_group)*unit tiles of that group.
+  The kernels (rssm_fwd.cu / rssm_bwd.cu) use the same formulas."""
+  ids = []
+  if groups == 1:
+    per = -(-(tiles // unit) // ncta) * unit
+    for c in range(ncta):
+      run = list(range(c * per, min(tiles, (c + 1) * per)))
+      ids.append(run + [-1] * (per - len(run)))
+    return per, ids
+  tpg = tiles // groups
+  cpg = max(1, ncta // groups)
+  per = -(-(tpg // unit) // cpg) * unit
+  for c in range(ncta):
+    g, j = divmod(c, cpg)
+    run = list(range(g * tpg + j * per, g * tpg + min(tpg, (j + 1) * per))) if g < groups else []
+    ids.append(run + [-1] * (per - len(run)))
+  return per, ids
+
+
+def pack_matrix(w, engine, ncta, unit=1, groups=1):
   """w: (K, N) fp32 -> the engine's streaming layout (rssm_common.cuh).
 
-  bf16: the N/8 column tiles are dealt to `ncta` CTAs in runs of `per` =
-  ceil(tiles / unit / ncta) * unit (the kernel uses the same formula); every
-  CTA's tiles are stored as one contiguous block [K/16][per][32 lanes][4 bf16]
-  in mma.m16n8k16 B-fragment order: element (k, n) of a 16 x 8 tile sits in
-  lane (n%8)*4 + (k%8)/2, register k/8, half k%2.
+  bf16: every CTA's n8 column tiles (see tile_assignment) are stored as one
+  contiguous block [K/16][per][32 lanes][4 bf16] in mma.m16n8k16 B-fragment
+  order: element (k, n) of a 16 x 8 tile sits in lane (n%8)*4 + (k%8)/2,
+  register k/8, half k%2.
   fp32: [N/8][K][8]."""
   K, N = w.shape
   assert K % 16 == 0 and N % 8 == 0, (K, N)
   if engine != ENG_BF16:
     return w.reshape(K, N // 8, 8).transpose(0, 1).contiguous()
-  tiles = N // 8
-  per = -(-(tiles // unit) // ncta) * unit
-  padded = torch.zeros((K, ncta * per * 8), dtype=torch.bfloat16, device=w.device)
-  padded[:, :N] = w
-  x = padded.reshape(K // 16, 2, 4, 2, ncta, per, 8)      # kstep, reg, kq, half, cta, tile, nn
+  per, ids = tile_assignment(N // 8, ncta, unit, groups)
+  ids = torch.tensor(ids, dtype=torch.long, device=w.device)          # (ncta, per)
+  wt = torch.cat([w.reshape(K, N // 8, 8).to(torch.bfloat16),
+                  torch.zeros((K, 1, 8), dtype=torch.bfloat16, device=w.device)], 1)
+  x = wt[:, ids.reshape(-1)]                                          # (K, ncta*per, 8); -1 -> zero tile
+  x = x.reshape(K // 16, 2, 4, 2, ncta, per, 8)           # kstep, reg, kq, half, cta, tile, nn
   return x.permute(4, 0, 5, 6, 2, 1, 3).contiguous()      # cta, kstep, tile, nn, kq, reg, half
 
 
@@ -83,8 +108,8 @@ def pack(store, cfg, engine, ncta):
   return dict(
       w_ph1=pack_matrix(torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1), engine, ncta),
       w_logit=pack_matrix(m('dyn/obslogit/kernel'), engine, ncta),
-      w_hid=pack_matrix(hid, engine, ncta),
-      w_gru=pack_matrix(gru, engine, ncta, unit=3),
+      w_hid=pack_matrix(hid, engine, ncta, groups=G),
+      w_gru=pack_matrix(gru, engine, ncta, unit=3, groups=G),
       w_in1=m('dyn/dynin1/kernel').to(cd).contiguous())
 
 
@@ -230,8 +255,8 @@ def pack_bwd(store, cfg, engine, ncta):
       wt_in1=pack_matrix(m('dyn/dynin1/kernel').t(), engine, ncta),
       wt_logit=pack_matrix(m('dyn/obslogit/kernel').t(), engine, ncta),
       wt_ph1=pack_matrix(ph1.t(), engine, ncta),
-      wt_gru=pack_matrix(gru_t, engine, ncta),
-      wt_hid=pack_matrix(hid_t, engine, ncta))
+      wt_gru=pack_matrix(gru_t, engine, ncta, groups=G),
+      wt_hid=pack_matrix(hid_t, engine, ncta, groups=G))
 
 
 def _bind_bwd(lib):
