@@ -43,6 +43,37 @@ torch.cuda.synchronize()
 print(f'train step: {(time.perf_counter() - t0) / 3 * 1e3:.1f} ms   loss {float(mets["loss"]):.3f}')
 print(f'max memory: {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB')
 
+# host enqueue time vs device time of one step: is the step launch-bound?
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+t0 = time.perf_counter()
+e0.record()
+carry, outs, mets = agent.train(carry, data)
+e1.record()
+t_host = time.perf_counter() - t0
+torch.cuda.synchronize()
+print(f'host enqueue {t_host * 1e3:.1f} ms   device span {e0.elapsed_time(e1):.1f} ms')
+
+# phases of the step (CUDA events): replay context + noise, forward, backward, optimiser
+def phases():
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+  c, obs_, pa, sid = agent._apply_replay_context(carry, data)
+  ev[0].record()
+  noise = agent.make_noise(B, T)
+  agent.store.begin_step(); agent.store.grad.zero_()
+  ev[1].record()
+  total, c2, o2, m2 = agent.model.loss(c, obs_, pa, noise, update=True)
+  ev[2].record()
+  total.backward()
+  ev[3].record()
+  agent.opt.step(); agent.opt.update_slow(); agent.store.begin_step()
+  ev[4].record()
+  torch.cuda.synchronize()
+  return [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
+phases()
+ph = phases()
+print('phases ms: noise %.2f  forward %.2f  backward %.2f  optimiser %.2f' % tuple(ph))
+
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
   carry, outs, mets = agent.train(carry, data)
