@@ -225,6 +225,7 @@ def run_b200(args):
   peak, peak_src = peaks()
 
   capacity = int(args.capacity)
+  scanlib.GRAPH_TIMERS = {}       # stopwatches recorded inside the captured train step
   loop = Loop(torch, rank, capacity, args.agent, args.size, args.dtype)
   flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
@@ -248,6 +249,7 @@ def run_b200(args):
     scanlib.PROFILE = [] if profile else None
     launches0 = _lib.launch_count()
     total = 0.0
+    graph_us = []
     for _ in range(steps):
       flush.zero_()                                  # L2 flush, untimed
       a = torch.cuda.Event(enable_timing=True)
@@ -258,11 +260,15 @@ def run_b200(args):
       b.record()
       torch.cuda.synchronize()
       total += a.elapsed_time(b) * 1e-3
+      if profile:                                    # the step's last replay of the captured graph
+        graph_us += [(k, w.ms() * 1e3) for k, w in scanlib.GRAPH_TIMERS.items()]
     barrier()
     launches = _lib.launch_count() - launches0
     prof, storelib.PROFILE = storelib.PROFILE, None
+    prof = [(k, a.elapsed_time(b) * 1e3) for k, a, b in (prof or [])]
     if scanlib.PROFILE:
-      prof = (prof or []) + [(k, a, b) for k, a, b, _ in scanlib.PROFILE]
+      prof += [(k, a.elapsed_time(b) * 1e3) for k, a, b, _ in scanlib.PROFILE]
+    prof += graph_us
     scanlib.PROFILE = None
     t = torch.tensor([total], device='cuda', dtype=torch.float64)
     if world > 1:
@@ -276,7 +282,7 @@ def run_b200(args):
 
   # per-kernel live timings (CUDA events on the launching stream, inside the timed region)
   def kernel_line(kind, name, nbytes, traffic):
-    us = [a.elapsed_time(b) * 1e3 for k, a, b in prof if k == kind]
+    us = [t for k, t in prof if k == kind]
     if not us:
       return None
     t = float(np.mean(us))
@@ -301,7 +307,9 @@ def run_b200(args):
                                NCU_TRAFFIC.get('rssm_fwd') if known else None))
   kernels = [k for k in kernels if k]
   # the roofline line is the hand-written kernel with the largest share of the step
-  share = lambda k: k['us_per_launch'] * k['launches_timed']
+  per_step = {'rows_kernel': TRAINS_PER_STEP, 'rssm_bwd_kernel': TRAINS_PER_STEP,
+              'rssm_fwd_kernel': TRAINS_PER_STEP}
+  share = lambda k: k['us_per_launch'] * per_step[k['kernel'].split()[0]] * args.steps
   roofline = max(kernels, key=share)
   for k in kernels:
     k['share_of_step'] = share(k) * 1e-6 / t_dev

@@ -38,7 +38,7 @@ _LIB = None
 _LOCK = threading.Lock()
 
 EXPORTS = (
-    'emb_last_error', 'emb_abi_version', 'emb_launch_count',
+    'emb_last_error', 'emb_abi_version', 'emb_launch_count', 'emb_launch_count_add',
     'emb_device_sm_count', 'emb_rows_copy', 'emb_replay_gather',
     'emb_replay_append_rows', 'emb_replay_scatter_update',
     'emb_driver_stage_obs', 'emb_driver_scatter_mask_actions',
@@ -46,6 +46,7 @@ EXPORTS = (
     'emb_rssm_observe_fwd', 'emb_rssm_observe_bwd', 'emb_rmsnorm_act_fwd',
     'emb_rmsnorm_act_bwd', 'emb_opt_agc_rms_momentum', 'emb_maxpool2_nhwc_fwd',
     'emb_maxpool2_nhwc_bwd', 'emb_upsample2_nhwc_fwd', 'emb_upsample2_nhwc_bwd',
+    'emb_event_create', 'emb_event_record', 'emb_event_elapsed_ms', 'emb_event_destroy',
 )
 
 
@@ -66,13 +67,21 @@ def load():
     lib.emb_last_error.restype = ctypes.c_char_p
     lib.emb_abi_version.restype = ctypes.c_int
     lib.emb_launch_count.restype = ctypes.c_uint64
+    lib.emb_launch_count_add.argtypes = [ctypes.c_uint64]
+    lib.emb_launch_count_add.restype = None
     lib.emb_device_sm_count.restype = ctypes.c_int
     lib.emb_rows_copy.argtypes = [kp, ctypes.c_int, vp, vp, i64, i32, vp]
     lib.emb_replay_gather.argtypes = [kp, ctypes.c_int, vp, i64, i32, vp]
     for name in ('emb_replay_append_rows', 'emb_replay_scatter_update',
                  'emb_driver_stage_obs', 'emb_driver_scatter_mask_actions'):
       getattr(lib, name).argtypes = [kp, ctypes.c_int, vp, i64, vp]
-    for name in EXPORTS[4:10]:
+    for name in EXPORTS[5:11]:
+      getattr(lib, name).restype = ctypes.c_int
+    lib.emb_event_create.argtypes = [ctypes.POINTER(vp)]
+    lib.emb_event_record.argtypes = [vp, vp]
+    lib.emb_event_elapsed_ms.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_float)]
+    lib.emb_event_destroy.argtypes = [vp]
+    for name in EXPORTS[-4:]:
       getattr(lib, name).restype = ctypes.c_int
     _LIB = lib
     return lib
@@ -88,7 +97,34 @@ def launch_count():
   return int(load().emb_launch_count())
 
 
+def launch_count_add(n):
+  load().emb_launch_count_add(int(n))
+
+
 def keys_array(keys):
   if len(keys) > MAX_KEYS:
     raise ValueError(f'{len(keys)} keys > EMB_MAX_KEYS={MAX_KEYS}')
   return (Key * len(keys))(*keys)
+
+
+class Stopwatch:
+  """A pair of CUDA events around a launch, usable inside a stream capture
+  (include/embodied_b200.h emb_event_*): `start(stream)`, `stop(stream)`, and
+  after a synchronise `ms()`.  Inside a CUDA graph every replay re-records."""
+
+  def __init__(self):
+    lib = load()
+    self.a, self.b = ctypes.c_void_p(), ctypes.c_void_p()
+    check(lib.emb_event_create(ctypes.byref(self.a)))
+    check(lib.emb_event_create(ctypes.byref(self.b)))
+
+  def start(self, stream):
+    check(load().emb_event_record(self.a, stream))
+
+  def stop(self, stream):
+    check(load().emb_event_record(self.b, stream))
+
+  def ms(self):
+    out = ctypes.c_float()
+    check(load().emb_event_elapsed_ms(self.a, self.b, ctypes.byref(out)))
+    return out.value

@@ -37,6 +37,7 @@ extern "C" {
 const char* emb_last_error(void) { return g_err; }
 int emb_abi_version(void) { return EMB_ABI_VERSION; }
 uint64_t emb_launch_count(void) { return g_launches.load(); }
+void emb_launch_count_add(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int emb_device_sm_count(void) {
   int dev = 0, sms = 0;
@@ -44,6 +45,38 @@ int emb_device_sm_count(void) {
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     return emb::fail_cuda("emb_device_sm_count");
   return sms;
+}
+
+/* CUDA-event stopwatch that also works inside a stream capture: when `stream`
+ * is capturing, the record becomes an event-record NODE of the graph
+ * (cudaEventRecordExternal), re-recorded at every replay. */
+int emb_event_create(void** ev) {
+  cudaEvent_t e;
+  if (!ev || cudaEventCreate(&e) != cudaSuccess) return emb::fail_cuda("emb_event_create");
+  *ev = (void*)e;
+  return 0;
+}
+
+int emb_event_record(void* ev, void* stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing((cudaStream_t)stream, &st) != cudaSuccess)
+    return emb::fail_cuda("emb_event_record");
+  const unsigned flags = st == cudaStreamCaptureStatusActive ? cudaEventRecordExternal
+                                                             : cudaEventRecordDefault;
+  if (cudaEventRecordWithFlags((cudaEvent_t)ev, (cudaStream_t)stream, flags) != cudaSuccess)
+    return emb::fail_cuda("emb_event_record");
+  return 0;
+}
+
+int emb_event_elapsed_ms(void* a, void* b, float* ms) {
+  if (cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess)
+    return emb::fail_cuda("emb_event_elapsed_ms");
+  return 0;
+}
+
+int emb_event_destroy(void* ev) {
+  if (cudaEventDestroy((cudaEvent_t)ev) != cudaSuccess) return emb::fail_cuda("emb_event_destroy");
+  return 0;
 }
 
 }  // extern "C"

@@ -71,6 +71,7 @@ class Agent(base.Agent):
     self.gen = torch.Generator(device=self.device)
     self.gen.manual_seed(cfg.seed * 1000003 + self.rank)     # transform.py:84-85 fold_in(rank)
     self.updates = 0
+    self._graphs, self._graph_seen, self._graph_ok = {}, {}, self.opt.fused
 
   # --------------------------------------------------------------- plugin props
   @property
@@ -139,35 +140,146 @@ class Agent(base.Agent):
     obs = {k: v[:, K:] for k, v in obs.items()}
     return (deter, stoch), obs, pa, data['stepid'][:, K:]
 
-  def make_noise(self, B, T):
+  def make_noise(self, B, T, out=None):
+    """Gumbel noise of one train step (an explicit input).  With
+    `out` the static buffers of the captured step are refilled in place."""
     cfg, dev, H = self.cfg, self.device, self.cfg.imag_length
-    return dict(
-        observe=modellib.gumbel_like((B, T, cfg.stoch, cfg.classes), dev, self.gen),
-        imag_stoch=modellib.gumbel_like((B * T, H, cfg.stoch, cfg.classes), dev, self.gen),
-        imag_act=modellib.gumbel_like((B * T, H + 1, cfg.actions), dev, self.gen))
+    shapes = dict(observe=(B, T, cfg.stoch, cfg.classes),
+                  imag_stoch=(B * T, H, cfg.stoch, cfg.classes),
+                  imag_act=(B * T, H + 1, cfg.actions))
+    if out is None:
+      return {k: modellib.gumbel_like(s, dev, self.gen) for k, s in shapes.items()}
+    for k in shapes:
+      modellib.gumbel_(out[k], self.gen)
+    return out
 
-  def train(self, carry, data, noise=None):                  # agent.py:137-154, opt.py:31-81
+  # The device work of one update, split where the data-parallel gradient
+  # all-reduce sits (embodied/jax/opt.py:52-54): `_fwd_bwd` = replay context,
+  # loss, backward into the flat gradient buffer; `_apply` = optimiser chain,
+  # slow critic, outputs.  Both are pure stream work (no host reads), so each is
+  # captured ONCE into a CUDA graph and replayed: the ~2500 launches of a step
+  # cost one cudaGraphLaunch instead of ~64 ms of host enqueue time.
+  def _fwd_bwd(self, carry, data, noise):
     carry, obs, prevact, stepid = self._apply_replay_context(carry, data)
-    B, T = obs['is_first'].shape
-    if noise is None:
-      noise = self.make_noise(B, T)
     self.store.begin_step()
     self.store.grad.zero_()
     total, carry, outs, metrics = self.model.loss(carry, obs, prevact, noise, update=True)
     total.backward()
-    if self.world > 1:
-      torch.distributed.all_reduce(self.store.grad, op=torch.distributed.ReduceOp.AVG)
-    metrics.update(self.opt.step())
+    return total, carry, outs, metrics, stepid
+
+  def _apply(self, total, carry, outs, metrics, stepid, data):
+    metrics = dict(metrics)
+    metrics['opt/grad_norm'] = self.opt.launch()
     self.opt.update_slow()
     self.store.begin_step()
-    self.updates += 1
     metrics['loss'] = total.detach()
     feat = outs['feat']
     replay = {'stepid': stepid, 'dyn/deter': feat['deter'].detach().to(f32),
               'dyn/stoch': feat['stoch'].detach().to(f32)}
+    carry = (carry[0].detach(), carry[1].detach(), data['action'][:, -1].clone())
+    return carry, replay, metrics
+
+  def _allreduce(self):
+    if self.world > 1:
+      torch.distributed.all_reduce(self.store.grad, op=torch.distributed.ReduceOp.AVG)
+
+  def train(self, carry, data, noise=None):                  # agent.py:137-154, opt.py:31-81
+    mode = self.cfg.get('graph', 'auto')
+    if mode and mode != 'off' and self._graph_ok:
+      key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(data.items()))
+      st = self._graphs.get(key)
+      if st is None:
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        if seen >= self.GRAPH_WARMUP:
+          st = self._capture(key, carry, data)
+      if st is not None:
+        return self._train_graphed(st, carry, data, noise)
+    return self._train_eager(carry, data, noise)
+
+  GRAPH_WARMUP = 2     # eager steps before capture (cuDNN / cuBLAS / NCCL initialisation)
+
+  def _train_eager(self, carry, data, noise=None):
+    B, T = data['is_first'].shape[0], data['is_first'].shape[1] - self.cfg.replay_context
+    if noise is None:
+      noise = self.make_noise(B, T)
+    total, carry, outs, metrics, stepid = self._fwd_bwd(carry, data, noise)
+    self._allreduce()
+    extra = self.opt.begin_update()
+    carry, replay, metrics = self._apply(total, carry, outs, metrics, stepid, data)
+    metrics.update(extra)
+    self.opt.end_update()
+    self.updates += 1
     self.last_outs = outs
-    carry = (carry[0].detach(), carry[1].detach(), data['action'][:, -1])
     return carry, {'replay': replay}, metrics
+
+  def _capture(self, key, carry, data):
+    """Capture the two halves of the update for this batch signature.  Returns
+    None (and disables graphs, loudly) if the stream capture is refused."""
+    import types
+    B, T = data['is_first'].shape[0], data['is_first'].shape[1] - self.cfg.replay_context
+    st = types.SimpleNamespace()
+    st.data = {k: v.clone() for k, v in data.items()}
+    st.carry = tuple(c.clone() for c in carry)
+    st.noise = self.make_noise(B, T)
+    scan = self.model.scan
+    if scan is not None:
+      scan.invalidate()          # the weight packing must be recorded inside the graph
+    pool = torch.cuda.graph_pool_handle()
+    st.ga, st.gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    from .. import _lib
+    launched = _lib.launch_count()
+    try:
+      torch.cuda.synchronize()
+      with torch.cuda.graph(st.ga, pool=pool):
+        mid = self._fwd_bwd(st.carry, st.data, st.noise)
+      with torch.cuda.graph(st.gb, pool=pool):
+        carry_out, replay, metrics = self._apply(*mid, st.data)
+        names = [k for k, v in metrics.items() if isinstance(v, torch.Tensor)]
+        mvec = torch.stack([metrics[k].to(f32).reshape(()) for k in names])
+      torch.cuda.synchronize()
+    except Exception as e:      # noqa: BLE001 -- capture refused: stay on the eager path
+      import warnings
+      warnings.warn(f'dreamerv3.Agent: CUDA graph capture of the train step failed ({e!r}); '
+                    'continuing with eager launches')
+      self._graph_ok = False
+      self.store.begin_step()
+      if scan is not None:
+        scan.invalidate()
+      return None
+    st.outs, st.carry_out, st.replay = mid[2], carry_out, replay
+    st.names, st.mvec = names, mvec
+    st.launches = _lib.launch_count() - launched     # our kernels inside the two graphs
+    _lib.launch_count_add((1 << 64) - st.launches)    # recorded, not executed, by the capture
+    self._lib = _lib
+    if scan is not None:
+      scan.invalidate()
+    self._graphs[key] = st
+    # The capture itself did not execute anything: the caller replays it now.
+    return st
+
+  def _train_graphed(self, st, carry, data, noise=None):
+    for a, b in zip(st.carry, carry):      # carry first: it may alias last step's outputs
+      a.copy_(b)
+    for k, v in st.data.items():
+      v.copy_(data[k])
+    if noise is None:
+      self.make_noise(*st.noise['observe'].shape[:2], out=st.noise)
+    else:
+      for k, v in st.noise.items():
+        v.copy_(noise[k])
+    st.ga.replay()
+    self._allreduce()
+    extra = self.opt.begin_update()
+    st.gb.replay()
+    self._lib.launch_count_add(st.launches)
+    self.opt.end_update()
+    self.updates += 1
+    self.last_outs = st.outs
+    mv = st.mvec.clone()
+    metrics = {k: mv[i] for i, k in enumerate(st.names)}
+    metrics.update(extra)
+    return st.carry_out, {'replay': st.replay}, metrics
 
   @torch.no_grad()
   def report(self, carry, data, noise=None):                 # agent.py:247-310 (metrics part)
@@ -197,6 +309,7 @@ class Agent(base.Agent):
   def load(self, data, regex=None):
     self.store.load_state_dict(data)
     if 'retnorm/lo' in data:
-      self.model.ret_lo = torch.as_tensor(data['retnorm/lo'], device=self.device)
-      self.model.ret_hi = torch.as_tensor(data['retnorm/hi'], device=self.device)
+      self.model.ret_lo.copy_(torch.as_tensor(data['retnorm/lo']))
+      self.model.ret_hi.copy_(torch.as_tensor(data['retnorm/hi']))
     self.updates = int(data.get('updates', 0))
+    self.opt.sync_count()

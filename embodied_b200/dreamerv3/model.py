@@ -34,10 +34,30 @@ def symexp(x):
   return torch.sign(x) * torch.expm1(torch.abs(x))
 
 
-def gumbel_like(shape, device, generator=None):
-  u = torch.rand(shape, device=device, dtype=f32, generator=generator)
+def gumbel_(u, generator=None):
+  """Fill `u` (fp32) with Gumbel(0, 1) noise in place."""
+  u.uniform_(0, 1, generator=generator)
   u.clamp_(1e-20, 1 - 1e-7)
-  return -torch.log(-torch.log(u))
+  return u.log_().neg_().log_().neg_()
+
+
+def gumbel_like(shape, device, generator=None):
+  return gumbel_(torch.empty(shape, device=device, dtype=f32), generator)
+
+
+def percentiles(x, qs):
+  """torch.quantile(x, qs) with linear interpolation for a flat fp32 `x`, as
+  sort + two gathers: pure stream work (CUDA-graph capturable), positions
+  computed on the host from the static length."""
+  n = x.numel()
+  s = torch.sort(x).values
+  out = []
+  for q in qs:
+    pos = q * (n - 1)
+    lo = min(int(pos), n - 1)
+    hi = min(lo + 1, n - 1)
+    out.append(torch.lerp(s[lo], s[hi], pos - lo))
+  return torch.stack(out)
 
 
 class Model:
@@ -317,25 +337,23 @@ class Model:
     cfg = self.cfg
     if update:
       x = ret.detach().to(f32).flatten()
-      q = torch.quantile(x, torch.tensor(
-          [cfg.perclo / 100, cfg.perchi / 100], device=x.device, dtype=f32))
-      q = self.reduce_percentiles(q, x)
+      q = percentiles(self.gather_returns(x), [cfg.perclo / 100, cfg.perchi / 100])
       r = cfg.retnorm_rate
-      self.ret_lo = (1 - r) * self.ret_lo + r * q[0]
-      self.ret_hi = (1 - r) * self.ret_hi + r * q[1]
-    return self.ret_lo, torch.clamp(self.ret_hi - self.ret_lo, min=cfg.retnorm_limit)
+      # in place: the EMA state keeps its address across CUDA-graph replays
+      self.ret_lo.mul_(1 - r).add_(q[0], alpha=r)
+      self.ret_hi.mul_(1 - r).add_(q[1], alpha=r)
+    lo, hi = self.ret_lo.clone(), self.ret_hi.clone()
+    return lo, torch.clamp(hi - lo, min=cfg.retnorm_limit)
 
-  def reduce_percentiles(self, q, x):
+  def gather_returns(self, x):
     """utils.py:83-88: with data-parallel ranks the returns of ALL ranks are
     gathered before the percentile, so every rank normalises identically."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-      return q
-    cfg = self.cfg
-    parts = [torch.empty_like(x) for _ in range(dist.get_world_size())]
-    dist.all_gather(parts, x.contiguous())
-    return torch.quantile(torch.cat(parts), torch.tensor(
-        [cfg.perclo / 100, cfg.perchi / 100], device=x.device, dtype=f32))
+      return x
+    parts = torch.empty((dist.get_world_size(), x.numel()), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(parts, x.contiguous())
+    return parts.flatten()
 
   # ----------------------------------------------------------------- imagination
   @torch.no_grad()

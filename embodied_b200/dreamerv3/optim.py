@@ -58,42 +58,52 @@ class Optimizer:
     self.nchunks, self.ntensors = len(rows), len(names)
     self.chunks = torch.from_numpy(table.view(np.uint8).copy()).to(st.device)
     self.norms = torch.zeros(2 * len(names), dtype=torch.float32, device=st.device)
-    self.hyper_host = torch.zeros(8, dtype=torch.float32, pin_memory=True)
-    self.hyper = torch.zeros(8, dtype=torch.float32, device=st.device)
-
-  def set_hyper(self):
-    """Step-dependent scalars -> device (outside any CUDA graph)."""
-    cfg, st = self.cfg, self.store
-    count = st.step
-    t = count + 1
-    h = self.hyper_host
-    h[0] = self.learning_rate(count)
-    h[1] = 1 / (1 - cfg.beta1 ** t)
-    h[2] = 1 / (1 - cfg.beta2 ** t)
-    h[3], h[4], h[5], h[6], h[7] = cfg.beta1, cfg.beta2, cfg.eps, cfg.agc, cfg.pmin
-    self.hyper.copy_(h, non_blocking=True)
-
-  def launch(self):
-    """The two optimiser kernels on the current stream (graph-capturable)."""
-    st = self.store
-    stream = torch.cuda.current_stream(st.device).cuda_stream
-    self._lib.check(self.lib.emb_opt_agc_rms_momentum(
-        st.grad.data_ptr(), st.master.data_ptr(), st.nu.data_ptr(), st.mu.data_ptr(),
-        self.chunks.data_ptr(), self.nchunks, self.norms.data_ptr(), self.ntensors,
-        self.hyper.data_ptr(), stream))
+    cfg = self.cfg
+    self.hyper = torch.tensor(
+        [0, 0, 0, cfg.beta1, cfg.beta2, cfg.eps, cfg.agc, cfg.pmin],
+        dtype=torch.float32, device=st.device)
+    self.count = torch.full((), float(st.step), dtype=torch.float64, device=st.device)
 
   @torch.no_grad()
-  def step(self):
-    cfg, st = self.cfg, self.store
-    count = st.step
+  def device_hyper(self):
+    """Step-dependent scalars from the DEVICE update counter (float64), so the
+    whole update is stream work and can live inside a CUDA graph.  optax
+    evaluates the schedule at the count before the increment."""
+    cfg = self.cfg
+    count = self.count
     t = count + 1
-    lr = self.learning_rate(count)
+    if cfg.warmup:
+      lr = cfg.lr * torch.clamp(count / cfg.warmup, max=1.0)
+    else:
+      lr = torch.full_like(count, cfg.lr)
+    h = torch.stack([lr, 1 / (1 - cfg.beta1 ** t), 1 / (1 - cfg.beta2 ** t)])
+    self.hyper[:3].copy_(h)
+    self.count.add_(1)
+
+  def begin_update(self):
+    """Host-side bookkeeping of one update; returns the scalar metrics."""
+    count = self.store.step
+    self._lr, self._t = self.learning_rate(count), count + 1
+    return {'opt/updates': self._t, 'opt/lr': self._lr}
+
+  def end_update(self):
+    self.store.step += 1
+    self.store.version += 1
+
+  @torch.no_grad()
+  def launch(self):
+    """The optimiser chain on the current stream; returns the gradient norm.
+    Fused: hyper-parameter scalars + the two kernels (graph-capturable)."""
+    cfg, st = self.cfg, self.store
     if self.fused:
-      self.set_hyper()
-      self.launch()
-      st.step = t
-      st.version += 1
-      return {'opt/grad_norm': self.norms[0::2].sum().sqrt(), 'opt/updates': t, 'opt/lr': lr}
+      self.device_hyper()
+      stream = torch.cuda.current_stream(st.device).cuda_stream
+      self._lib.check(self.lib.emb_opt_agc_rms_momentum(
+          st.grad.data_ptr(), st.master.data_ptr(), st.nu.data_ptr(), st.mu.data_ptr(),
+          self.chunks.data_ptr(), self.nchunks, self.norms.data_ptr(), self.ntensors,
+          self.hyper.data_ptr(), stream))
+      return self.norms[0::2].sum().sqrt()
+    t, lr = self._t, self._lr
     gn = torch.stack(torch._foreach_norm(self._grads))
     pn = torch.stack(torch._foreach_norm(self._params))
     upper = cfg.agc * torch.clamp(pn, min=cfg.pmin)
@@ -104,10 +114,20 @@ class Optimizer:
     u = g / ((st.nu / (1 - cfg.beta2 ** t)).sqrt_() + cfg.eps)
     st.mu.mul_(cfg.beta1).add_(u, alpha=1 - cfg.beta1)
     st.master.add_(st.mu, alpha=-lr / (1 - cfg.beta1 ** t))
-    st.step = t
-    st.version += 1
-    return {'opt/grad_norm': torch.linalg.vector_norm(gn), 'opt/updates': t,
-            'opt/lr': lr}
+    return torch.linalg.vector_norm(gn)
+
+  @torch.no_grad()
+  def step(self):
+    """One eager update (begin_update + launch + end_update)."""
+    mets = self.begin_update()
+    mets['opt/grad_norm'] = self.launch()
+    self.end_update()
+    return mets
+
+  def sync_count(self):
+    """After loading a checkpoint: device counter <- host counter."""
+    if self.fused:
+      self.count.fill_(float(self.store.step))
 
   @torch.no_grad()
   def update_slow(self):

@@ -18,6 +18,9 @@ f32 = torch.float32
 # bench.py sets this to a list to collect (name, start, end) CUDA event triples
 # around the scan launches (live per-launch timing for the roofline line).
 PROFILE = None
+# name -> _lib.Stopwatch recorded around the scan launches INSIDE a captured
+# train step (bench.py sets GRAPH_TIMERS = {} before the agent captures).
+GRAPH_TIMERS = None
 ROWS = 16
 ENG_F32, ENG_BF16 = 0, 1
 
@@ -34,6 +37,15 @@ class FwdArgs(ctypes.Structure):
           'deter0', 'x2', 'pre_tok', 'keep', 'gumbel',
           'deter', 'logit', 'index',
           'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'probs', 'rstd', 'deterA', 'barrier', 'timing')])
+
+
+def _graph_timer(name):
+  if GRAPH_TIMERS is None or not torch.cuda.is_current_stream_capturing():
+    return None
+  watch = GRAPH_TIMERS.get(name)
+  if watch is None:
+    watch = GRAPH_TIMERS[name] = _lib.Stopwatch()
+  return watch
 
 
 def _bind(lib):
@@ -152,6 +164,11 @@ class Scan:
     if self.ncta <= 0:
       _lib.check(self.ncta)
 
+  def invalidate(self):
+    """Forget the packed weight copies (the next use re-packs; a CUDA-graph
+    capture calls this so that the packing is recorded inside the graph)."""
+    self.packed = self.packed_bwd = None
+
   def weights(self):
     if self.packed is None or self.packed_step != self.store.version:
       self.packed = pack(self.store, self.cfg, self.engine, self.ncta)
@@ -210,11 +227,16 @@ class Scan:
       assert v.is_contiguous(), k
       setattr(args, k, v.data_ptr())
     stream = torch.cuda.current_stream(dev).cuda_stream
-    prof = PROFILE
+    prof = None if torch.cuda.is_current_stream_capturing() else PROFILE
     if prof is not None:
       e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e0.record()
+    watch = _graph_timer('rssm_fwd')
+    if watch:
+      watch.start(stream)
     _lib.check(self.lib.emb_rssm_observe_fwd(ctypes.byref(args), stream))
+    if watch:
+      watch.stop(stream)
     if prof is not None:
       e1.record()
       prof.append(('rssm_fwd', e0, e1, T))
@@ -321,12 +343,18 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
     assert v.is_contiguous(), k
     setattr(args, k, v.data_ptr())
   stream = torch.cuda.current_stream(dev).cuda_stream
-  ev = getattr(scan, 'bwd_events', None)
-  prof = PROFILE
+  capturing = torch.cuda.is_current_stream_capturing()
+  ev = None if capturing else getattr(scan, 'bwd_events', None)
+  prof = None if capturing else PROFILE
   if ev is not None or prof is not None:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+  watch = _graph_timer('rssm_bwd')
+  if watch:
+    watch.start(stream)
   _lib.check(lib.emb_rssm_observe_bwd(ctypes.byref(args), stream))
+  if watch:
+    watch.stop(stream)
   if ev is not None or prof is not None:
     e1.record()
     if ev is not None:

@@ -72,8 +72,19 @@ const char* emb_last_error(void);
 int emb_abi_version(void);
 /* Number of kernels this library has launched in this process (gpu_launches). */
 uint64_t emb_launch_count(void);
+/* Account for launches this library recorded into a CUDA graph that the caller
+ * has just replayed (a replay does not pass through the entry points). */
+void emb_launch_count_add(uint64_t n);
 /* SM count of the current device (grid sizing), <0 on error. */
 int emb_device_sm_count(void);
+
+/* CUDA-event stopwatch for per-kernel timing on the launching stream.  Inside a
+ * stream capture the record becomes an event-record node of the graph and is
+ * re-recorded by every replay (bench.py reads it after the step's sync). */
+int emb_event_create(void** ev);
+int emb_event_record(void* ev, void* stream);
+int emb_event_elapsed_ms(void* a, void* b, float* ms);
+int emb_event_destroy(void* ev);
 
 /* The row engine.  For r in [0, nrows):
  *     srow(r) = src_rows ? src_rows[r] : r        drow(r) = dst_rows ? dst_rows[r] : r

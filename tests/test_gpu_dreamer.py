@@ -85,7 +85,7 @@ def test_gradients_match_oracle_fp32():
   B, T = 2, 5
   data, noise = cases.batch(ocfg, B, T, seed=5), do.make_noise(ocfg, B, T, seed=6)
   _, _, _, ograds, _ = oracle.train(data, noise)
-  agent.opt.step = lambda: {}            # keep the raw gradients in the buffer
+  agent.opt.launch = lambda: torch.zeros(())      # keep the raw gradients in the buffer
   agent.train(agent.init_train(B), cases.to_device(data), cases.to_device(noise))
   for k, g in ograds.items():
     assert rel2(agent.store.view('grad', k), g) < GTOL, k
@@ -139,3 +139,39 @@ def test_save_load_roundtrip():
   b = other.train(other.init_train(B), data, noise)[2]['loss']
   # the scan kernels sum with atomics: equal up to summation order, not bit for bit
   assert abs(float(a) - float(b)) <= 1e-5 * abs(float(b))
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'bfloat16'])
+def test_captured_train_step_matches_eager(dtype):
+  """The CUDA-graph replay of the update (agent._capture) against eager
+  launches of the same update: same batch stream, same injected noise."""
+  ocfg = do.tiny_config()
+  vals = do.init_params(ocfg, 2, outscale_override=1.0)
+  obs, act = spaces(ocfg)
+  agents = []
+  for graph in ('auto', 'off'):
+    cfg = cases.product_config(ocfg, dtype)
+    cfg['graph'] = graph
+    agents.append(dreamerv3.Agent(obs, act, cfg, values={k: v.numpy() for k, v in vals.items()}))
+  B, T = 3, 6
+  carries = [a.init_train(B) for a in agents]
+  for it in range(5):
+    data = cases.to_device(cases.batch(ocfg, B, T, seed=10 + it))
+    noise = cases.to_device(do.make_noise(ocfg, B, T, seed=20 + it))
+    res = []
+    for i, a in enumerate(agents):
+      carries[i], outs, mets = a.train(carries[i], data, noise)
+      res.append((outs, {k: float(v) for k, v in mets.items()}))
+    tol = 1e-5 if dtype == 'float32' else 3e-2
+    assert abs(res[0][1]['loss'] - res[1][1]['loss']) <= tol * abs(res[1][1]['loss']), (it, res)
+    assert res[0][1]['opt/updates'] == res[1][1]['opt/updates'] == it + 1
+    assert rel(res[0][0]['replay']['dyn/deter'], res[1][0]['replay']['dyn/deter']) < tol
+  assert len(agents[0]._graphs) == 1 and not agents[1]._graphs
+  assert agents[0]._graph_ok
+  gtol = GTOL if dtype == 'float32' else 5e-2
+  worst = max((rel2(agents[0].store.view('master', k), agents[1].store.view('master', k)), k)
+              for k in agents[0].store.specs)
+  assert worst[0] < gtol, worst
+  # no-noise path: the captured step draws its own noise into the static buffers
+  carries[0], outs, mets = agents[0].train(carries[0], data)
+  assert np.isfinite(float(mets['loss']))

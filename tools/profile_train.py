@@ -66,7 +66,7 @@ def phases():
   ev[2].record()
   total.backward()
   ev[3].record()
-  agent.opt.step(); agent.opt.update_slow(); agent.store.begin_step()
+  agent.opt.step(); agent.opt.update_slow(); agent.store.begin_step()  # eager
   ev[4].record()
   torch.cuda.synchronize()
   return [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
