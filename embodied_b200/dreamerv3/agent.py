@@ -29,6 +29,12 @@ from . import params as paramlib
 f32 = torch.float32
 
 
+def _detach(tree):
+  if isinstance(tree, dict):
+    return {k: _detach(v) for k, v in tree.items()}
+  return tree.detach() if isinstance(tree, torch.Tensor) else tree
+
+
 class Agent(base.Agent):
 
   device_obs = True
@@ -172,7 +178,8 @@ class Agent(base.Agent):
     metrics['opt/grad_norm'] = self.opt.launch()
     self.opt.update_slow()
     self.store.begin_step()
-    metrics['loss'] = total.detach()
+    metrics['loss'] = total
+    metrics = {k: v.detach() if isinstance(v, torch.Tensor) else v for k, v in metrics.items()}
     feat = outs['feat']
     replay = {'stepid': stepid, 'dyn/deter': feat['deter'].detach().to(f32),
               'dyn/stoch': feat['stoch'].detach().to(f32)}
@@ -210,7 +217,9 @@ class Agent(base.Agent):
     metrics.update(extra)
     self.opt.end_update()
     self.updates += 1
-    self.last_outs = outs
+    # detached: a live autograd graph would keep this step's AccumulateGrad
+    # nodes (and their stream) alive into a later stream capture
+    self.last_outs = _detach(outs)
     return carry, {'replay': replay}, metrics
 
   def _capture(self, key, carry, data):
@@ -225,6 +234,7 @@ class Agent(base.Agent):
     scan = self.model.scan
     if scan is not None:
       scan.invalidate()          # the weight packing must be recorded inside the graph
+    self.last_outs = None
     pool = torch.cuda.graph_pool_handle()
     st.ga, st.gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
     from .. import _lib
@@ -247,7 +257,8 @@ class Agent(base.Agent):
       if scan is not None:
         scan.invalidate()
       return None
-    st.outs, st.carry_out, st.replay = mid[2], carry_out, replay
+    st.outs, st.carry_out, st.replay = _detach(mid[2]), carry_out, replay
+    del mid
     st.names, st.mvec = names, mvec
     st.launches = _lib.launch_count() - launched     # our kernels inside the two graphs
     _lib.launch_count_add((1 << 64) - st.launches)    # recorded, not executed, by the capture

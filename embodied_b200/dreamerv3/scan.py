@@ -81,6 +81,9 @@ def tile_assignment(tiles, ncta, unit=1, groups=1):
   return per, ids
 
 
+_IDS = {}
+
+
 def pack_matrix(w, engine, ncta, unit=1, groups=1):
   """w: (K, N) fp32 -> the engine's streaming layout (rssm_common.cuh).
 
@@ -93,8 +96,12 @@ def pack_matrix(w, engine, ncta, unit=1, groups=1):
   assert K % 16 == 0 and N % 8 == 0, (K, N)
   if engine != ENG_BF16:
     return w.reshape(K, N // 8, 8).transpose(0, 1).contiguous()
-  per, ids = tile_assignment(N // 8, ncta, unit, groups)
-  ids = torch.tensor(ids, dtype=torch.long, device=w.device)          # (ncta, per)
+  key = (N // 8, ncta, unit, groups, str(w.device))
+  hit = _IDS.get(key)
+  if hit is None:                      # host -> device once (never inside a stream capture)
+    per, ids = tile_assignment(N // 8, ncta, unit, groups)
+    hit = _IDS[key] = (per, torch.tensor(ids, dtype=torch.long, device=w.device))
+  per, ids = hit                                                      # (ncta, per)
   wt = torch.cat([w.reshape(K, N // 8, 8).to(torch.bfloat16),
                   torch.zeros((K, 1, 8), dtype=torch.bfloat16, device=w.device)], 1)
   x = wt[:, ids.reshape(-1)]                                          # (K, ncta*per, 8); -1 -> zero tile

@@ -17,7 +17,8 @@ S = elements.Space
 obs = {'image': S(np.uint8, (64, 64, 3)), 'reward': S(np.float32), 'is_first': S(bool),
        'is_last': S(bool), 'is_terminal': S(bool)}
 act = {'reset': S(bool), 'action': S(np.int32, (), 0, 5)}
-agent = dreamerv3.Agent(obs, act, dreamerv3.config.make(size, compute_dtype=dtype))
+graph = sys.argv[4] if len(sys.argv) > 4 else 'auto'
+agent = dreamerv3.Agent(obs, act, dreamerv3.config.make(size, compute_dtype=dtype, graph=graph))
 cfg = agent.cfg
 B, T, L = 16, 64, 65
 g = torch.Generator(device='cuda').manual_seed(0)
@@ -75,10 +76,14 @@ ph = phases()
 print('phases ms: noise %.2f  forward %.2f  backward %.2f  optimiser %.2f' % tuple(ph))
 
 from torch.profiler import profile, ProfilerActivity
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=graph == 'off') as prof:
   carry, outs, mets = agent.train(carry, data)
   torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by='cuda_time_total', row_limit=rows, max_name_column_width=90))
+if graph == 'off':
+  print(prof.key_averages(group_by_input_shape=True).table(
+      sort_by='self_cuda_time_total', row_limit=3 * rows, max_name_column_width=60,
+      max_shapes_column_width=90))
 
 pobs = {'image': data['image'][:, 0].repeat(16, 1, 1, 1), 'is_first': torch.zeros(256, dtype=torch.bool, device='cuda')}
 pc = agent.init_policy(256)
