@@ -1,0 +1,224 @@
+// emb_rssm_kl_fwd / _bwd: the KL / free-nats / entropy reduction of RSSM.loss
+// (dreamerv3/rssm.py:120-133) as ONE pass over the posterior and prior logits
+// each way, instead of ~40 element-wise launches:
+//
+//   a = log(unimix(softmax(post)))   b = log(unimix(softmax(prior)))    outs.py:210-216
+//   kl_s = sum_c softmax(a)_c (log_softmax(a)_c - log_softmax(b)_c)     outs.py:236-240
+//   dyn = rep = max(sum_s kl_s, free_nats)  (they differ in where the gradient
+//   goes: dyn -> prior only, rep -> posterior only; rssm.py:125-130)
+//   ent_x = sum_s -sum_c softmax(x)_c log_softmax(x)_c                   rssm.py:131-132
+//
+// One CTA per (b, t) row, one warp per latent (strided when S > warps), the C <= 128
+// classes of a latent spread over the lanes (<= 4 per lane): every reduction over
+// classes is a warp-shuffle butterfly, the sum over latents goes through shared
+// memory.  HBM traffic = the two logit tensors once (fwd) / once + the two
+// gradient tensors (bwd).  Logits are fp32 or bf16 and may be strided views
+// ((b, t) -> b*stride_b + t*stride_t, the S*C classes contiguous).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/embodied_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxPerLane = 4;      // C <= 128
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float load_logit(const void* p, int dtype, int64_t i) {
+  return dtype ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i])
+               : reinterpret_cast<const float*>(p)[i];
+}
+
+// One latent's distribution on a warp: soft = softmax(logit), mixed = unimix(soft),
+// a = log(mixed), norm = softmax(a) = mixed / sum(mixed), la = log_softmax(a).
+struct Dist {
+  float soft[kMaxPerLane], mixed[kMaxPerLane], norm[kMaxPerLane], la[kMaxPerLane];
+};
+
+__device__ __forceinline__ void make_dist(const void* base, int dtype, int64_t off, int C,
+                                          float unimix, int lane, Dist& d) {
+  float x[kMaxPerLane];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const int c = lane + 32 * i;
+    x[i] = c < C ? load_logit(base, dtype, off + c) : -INFINITY;
+    m = fmaxf(m, x[i]);
+  }
+  m = warp_max(m);
+  float z = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    d.soft[i] = lane + 32 * i < C ? expf(x[i] - m) : 0.f;
+    z += d.soft[i];
+  }
+  z = warp_sum(z);
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const bool on = lane + 32 * i < C;
+    d.soft[i] = d.soft[i] / z;
+    d.mixed[i] = on ? (1.0f - unimix) * d.soft[i] + unimix / (float)C : 0.f;
+    tot += d.mixed[i];
+  }
+  tot = warp_sum(tot);
+  const float ltot = logf(tot);
+#pragma unroll
+  for (int i = 0; i < kMaxPerLane; ++i) {
+    const bool on = lane + 32 * i < C;
+    d.norm[i] = d.mixed[i] / tot;
+    d.la[i] = on ? logf(d.mixed[i]) - ltot : 0.f;
+  }
+}
+
+struct Args {
+  const void* post;
+  const void* prior;
+  int dtype_post, dtype_prior;
+  int B, T, S, C;
+  int64_t post_sb, post_st, prior_sb, prior_st;
+  float unimix, free_nats;
+};
+
+__global__ void __launch_bounds__(1024)
+kl_fwd_kernel(Args a, float* __restrict__ dyn, float* __restrict__ rep, float* __restrict__ kl_raw,
+              float* __restrict__ ent_post, float* __restrict__ ent_prior) {
+  __shared__ float acc[3][32];
+  const int row = blockIdx.x, b = row / a.T, t = row - b * a.T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int64_t opost = (int64_t)b * a.post_sb + (int64_t)t * a.post_st;
+  const int64_t oprior = (int64_t)b * a.prior_sb + (int64_t)t * a.prior_st;
+  float kl = 0.f, ep = 0.f, eq = 0.f;
+  for (int s = warp; s < a.S; s += nwarps) {
+    Dist p, q;
+    make_dist(a.post, a.dtype_post, opost + (int64_t)s * a.C, a.C, a.unimix, lane, p);
+    make_dist(a.prior, a.dtype_prior, oprior + (int64_t)s * a.C, a.C, a.unimix, lane, q);
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      kl = fmaf(p.norm[i], p.la[i] - q.la[i], kl);
+      ep = fmaf(-p.norm[i], p.la[i], ep);
+      eq = fmaf(-q.norm[i], q.la[i], eq);
+    }
+  }
+  kl = warp_sum(kl); ep = warp_sum(ep); eq = warp_sum(eq);
+  if (lane == 0) { acc[0][warp] = kl; acc[1][warp] = ep; acc[2][warp] = eq; }
+  __syncthreads();
+  if (warp == 0) {
+    float v0 = lane < nwarps ? acc[0][lane] : 0.f;
+    float v1 = lane < nwarps ? acc[1][lane] : 0.f;
+    float v2 = lane < nwarps ? acc[2][lane] : 0.f;
+    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2);
+    if (lane == 0) {
+      kl_raw[row] = v0;
+      const float clipped = fmaxf(v0, a.free_nats);
+      dyn[row] = clipped;
+      rep[row] = clipped;
+      ent_post[row] = v1;
+      ent_prior[row] = v2;
+    }
+  }
+}
+
+// Gradients: with a = log(mixed(y)), KL = sum_c softmax(a)_c (la_c - lb_c):
+//   dKL/da_j = pa_j (la_j - lb_j - kl_s)            dKL/db_j = qb_j - pa_j
+//   da_j/dy_k = (1-u) t_j (delta_jk - t_k) / mixed_j  (t = softmax(y)), same for b(z)
+__global__ void __launch_bounds__(1024)
+kl_bwd_kernel(Args a, const float* __restrict__ kl_raw, const float* __restrict__ g_dyn,
+              const float* __restrict__ g_rep, float* __restrict__ g_post,
+              float* __restrict__ g_prior) {
+  const int row = blockIdx.x, b = row / a.T, t = row - b * a.T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int64_t opost = (int64_t)b * a.post_sb + (int64_t)t * a.post_st;
+  const int64_t oprior = (int64_t)b * a.prior_sb + (int64_t)t * a.prior_st;
+  // torch.clamp(min=free) passes the gradient where kl >= free
+  const bool open = kl_raw[row] >= a.free_nats;
+  const float gd = open ? g_dyn[row] : 0.f, gr = open ? g_rep[row] : 0.f;
+  for (int s = warp; s < a.S; s += nwarps) {
+    Dist p, q;
+    make_dist(a.post, a.dtype_post, opost + (int64_t)s * a.C, a.C, a.unimix, lane, p);
+    make_dist(a.prior, a.dtype_prior, oprior + (int64_t)s * a.C, a.C, a.unimix, lane, q);
+    float kl = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) kl = fmaf(p.norm[i], p.la[i] - q.la[i], kl);
+    kl = warp_sum(kl);
+    float w[kMaxPerLane], v[kMaxPerLane], sw = 0.f, sv = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const bool on = lane + 32 * i < a.C;
+      const float da = p.norm[i] * (p.la[i] - q.la[i] - kl);
+      const float db = q.norm[i] - p.norm[i];
+      w[i] = on ? da * p.soft[i] / p.mixed[i] : 0.f;
+      v[i] = on ? db * q.soft[i] / q.mixed[i] : 0.f;
+      sw += w[i]; sv += v[i];
+    }
+    sw = warp_sum(sw); sv = warp_sum(sv);
+    const int64_t out = ((int64_t)row * a.S + s) * a.C;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < a.C) {
+        g_post[out + c] = gr * (1.0f - a.unimix) * (w[i] - p.soft[i] * sw);
+        g_prior[out + c] = gd * (1.0f - a.unimix) * (v[i] - q.soft[i] * sv);
+      }
+    }
+  }
+}
+
+int validate(const char* who, const emb_rssm_kl_args* k) {
+  if (!k) return emb::fail(-1, "%s: args is NULL", who);
+  if (k->B < 0 || k->T < 0 || k->S < 1 || k->C < 1)
+    return emb::fail(-1, "%s: B=%d T=%d S=%d C=%d", who, k->B, k->T, k->S, k->C);
+  if (k->C > 32 * kMaxPerLane) return emb::fail(-1, "%s: classes=%d > %d", who, k->C, 32 * kMaxPerLane);
+  if ((k->dtype_post | k->dtype_prior) & ~1)
+    return emb::fail(-1, "%s: dtype must be 0 (f32) or 1 (bf16)", who);
+  return 0;
+}
+
+Args make_args(const emb_rssm_kl_args* k) {
+  return Args{k->post, k->prior, k->dtype_post, k->dtype_prior, k->B, k->T, k->S, k->C,
+              k->post_stride_b, k->post_stride_t, k->prior_stride_b, k->prior_stride_t,
+              k->unimix, k->free_nats};
+}
+
+unsigned threads_for(int S) { return 32u * (unsigned)(S < 32 ? S : 32); }
+
+}  // namespace
+
+extern "C" int emb_rssm_kl_fwd(const emb_rssm_kl_args* k, float* dyn, float* rep, float* kl_raw,
+                               float* ent_post, float* ent_prior, void* stream) {
+  const char* who = "emb_rssm_kl_fwd";
+  if (int e = validate(who, k)) return e;
+  const int64_t rows = (int64_t)k->B * k->T;
+  if (rows == 0) return 0;
+  kl_fwd_kernel<<<(unsigned)rows, threads_for(k->S), 0, (cudaStream_t)stream>>>(
+      make_args(k), dyn, rep, kl_raw, ent_post, ent_prior);
+  emb::count_launch();
+  if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
+  return 0;
+}
+
+extern "C" int emb_rssm_kl_bwd(const emb_rssm_kl_args* k, const float* kl_raw, const float* g_dyn,
+                               const float* g_rep, float* g_post, float* g_prior, void* stream) {
+  const char* who = "emb_rssm_kl_bwd";
+  if (int e = validate(who, k)) return e;
+  const int64_t rows = (int64_t)k->B * k->T;
+  if (rows == 0) return 0;
+  kl_bwd_kernel<<<(unsigned)rows, threads_for(k->S), 0, (cudaStream_t)stream>>>(
+      make_args(k), kl_raw, g_dyn, g_rep, g_post, g_prior);
+  emb::count_launch();
+  if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
+  return 0;
+}

@@ -80,7 +80,8 @@ __device__ __forceinline__ float dsilu(float n) {
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale, T* __restrict__ y,
+rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                       const float* __restrict__ bias, T* __restrict__ y,
                        int64_t rows, int cols, int act, float eps) {
   constexpr int N = Vec<T>::N;
   const int gs = group_size(cols, N), rpw = 32 / gs;          // narrow rows: several per warp
@@ -97,7 +98,10 @@ rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
       float v[N];
       Vec<T>::load(xr + c, v);
 #pragma unroll
-      for (int i = 0; i < N; ++i) ss = fmaf(v[i], v[i], ss);
+      for (int i = 0; i < N; ++i) {
+        if (bias) v[i] += bias[c + i];
+        ss = fmaf(v[i], v[i], ss);
+      }
     }
     const float rstd = rsqrtf(group_sum(ss, gs) / (float)cols + eps);
     if (!live) continue;
@@ -106,6 +110,7 @@ rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
       Vec<T>::load(xr + c, v);
 #pragma unroll
       for (int i = 0; i < N; ++i) {
+        if (bias) v[i] += bias[c + i];
         const float n = Vec<T>::round(v[i] * (rstd * scale[c + i]));   // cast back, then act (nets.py:397)
         o[i] = act ? silu(n) : n;
       }
@@ -114,26 +119,92 @@ rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
+// PL = elements a lane may own of one row.  PL = 8 (cols <= 256: the channel
+// axis of the convolutions, millions of short rows) keeps the row in registers
+// -- one load of x and g_y, two shuffle reductions, one store -- runs at full
+// occupancy and also reduces the bias gradient; PL = 64 (cols <= 2048: dense
+// layers, ~1e3 long rows) re-reads the row from L1 between the sweeps.
+template <typename T, int PL>
+__global__ void __launch_bounds__(kThreads, PL <= 8 ? 6 : 1)
 rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
-                       const T* __restrict__ gy, T* __restrict__ gx, float* __restrict__ gscale,
+                       const float* __restrict__ bias, const T* __restrict__ gy,
+                       T* __restrict__ gx, float* __restrict__ gscale, float* __restrict__ gbias,
                        int64_t rows, int cols, int act, float eps) {
   constexpr int N = Vec<T>::N;
-  extern __shared__ float part_raw[];      // [kWarps][cols]
+  constexpr bool SMALL = PL <= 8;
+  extern __shared__ float part_raw[];      // [kWarps][cols] (x2 with a bias)
   const int gs_ = group_size(cols, N), rpw = 32 / gs_;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lg = lane % gs_, grp = lane / gs_;
   const int64_t warp = (int64_t)blockIdx.x * kWarps + wid;
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
-  float gsc[kMaxPerLane];                  // scale-gradient partials of this lane's columns
+  float gsc[PL];                           // scale-gradient partials of this lane's columns
+  float gbi[SMALL ? PL : 1];               // bias-gradient partials
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; ++i) gsc[i] = 0.f;
+  for (int i = 0; i < PL; ++i) gsc[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < (SMALL ? PL : 1); ++i) gbi[i] = 0.f;
   for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
     const int64_t r = r0 + grp;
     const bool live = r < rows;
     const T* xr = x + (live ? r : 0) * cols;
     const T* gr = gy + (live ? r : 0) * cols;
     T* or_ = gx + (live ? r : 0) * cols;
+    if (SMALL) {
+      float v[PL], g[PL];
+#pragma unroll
+      for (int j = 0; j < PL / N; ++j) {
+        const int c = lg * N + j * gs_ * N;
+        if (c < cols) {
+          Vec<T>::load(xr + c, *reinterpret_cast<float(*)[N]>(&v[j * N]));
+          Vec<T>::load(gr + c, *reinterpret_cast<float(*)[N]>(&g[j * N]));
+        }
+      }
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < PL / N; ++j) {
+        const int c = lg * N + j * gs_ * N;
+        if (c < cols) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            if (bias) v[j * N + i] += bias[c + i];
+            ss = fmaf(v[j * N + i], v[j * N + i], ss);
+          }
+        }
+      }
+      const float rstd = rsqrtf(group_sum(ss, gs_) / (float)cols + eps);
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < PL / N; ++j) {
+        const int c = lg * N + j * gs_ * N;
+        if (c < cols) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const float xh = v[j * N + i] * rstd, sc = scale[c + i];
+            const float gn = act ? g[j * N + i] * dsilu(Vec<T>::round(xh * sc)) : g[j * N + i];
+            if (live) gsc[j * N + i] = fmaf(gn, xh, gsc[j * N + i]);
+            dot = fmaf(gn * sc, xh, dot);
+            v[j * N + i] = xh;
+            g[j * N + i] = gn * sc;
+          }
+        }
+      }
+      const float mean = group_sum(dot, gs_) / (float)cols;
+      if (!live) continue;
+#pragma unroll
+      for (int j = 0; j < PL / N; ++j) {
+        const int c = lg * N + j * gs_ * N;
+        if (c < cols) {
+          float o[N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            o[i] = rstd * (g[j * N + i] - v[j * N + i] * mean);
+            gbi[j * N + i] += o[i];
+          }
+          Vec<T>::store(or_ + c, o);
+        }
+      }
+      continue;
+    }
     float ss = 0.f;
     for (int c = lg * N; c < cols; c += gs_ * N) {
       float v[N];
@@ -144,7 +215,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
     const float rstd = rsqrtf(group_sum(ss, gs_) / (float)cols + eps);
     float dot = 0.f;
 #pragma unroll
-    for (int j = 0; j < kMaxPerLane / N; ++j) {
+    for (int j = 0; j < PL / N; ++j) {
       const int c = lg * N + j * gs_ * N;
       if (c < cols) {
         float v[N], g[N];
@@ -174,16 +245,22 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
       Vec<T>::store(or_ + c, o);
     }
   }
-  // scale gradient: row groups of a warp -> lane group 0 (shuffles) -> shared [warp][col]
-  // -> one atomicAdd per column per CTA
+  // scale (and bias) gradient: row groups of a warp -> lane group 0 (shuffles) ->
+  // shared [warp][col] -> one atomicAdd per column per CTA
+  float* part_b = part_raw + (size_t)kWarps * cols;
 #pragma unroll
-  for (int j = 0; j < kMaxPerLane / N; ++j) {
+  for (int j = 0; j < PL / N; ++j) {
     const int c = lg * N + j * gs_ * N;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       float v = gsc[j * N + i];
       for (int o = gs_; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (c < cols && grp == 0) part_raw[(size_t)wid * cols + c + i] = v;
+      if (SMALL && gbias) {
+        float w = gbi[j * N + i];
+        for (int o = gs_; o < 32; o <<= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (c < cols && grp == 0) part_b[(size_t)wid * cols + c + i] = w;
+      }
     }
   }
   __syncthreads();
@@ -192,6 +269,12 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) s += part_raw[(size_t)w * cols + c];
     atomicAdd(gscale + c, s);
+    if (SMALL && gbias) {
+      float sb = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) sb += part_b[(size_t)w * cols + c];
+      atomicAdd(gbias + c, sb);
+    }
   }
 }
 
@@ -212,62 +295,77 @@ int check(const char* who, const void* x, const void* y, int64_t rows, int cols,
   return 0;
 }
 
-unsigned grid_for(int64_t rows) {
+constexpr int kSmallCols = 256;           // PL = 8: 32 lanes x 8 elements
+
+unsigned grid_for(int64_t rows, int per_sm) {
   const int64_t want = (rows + kWarps - 1) / kWarps;
-  const int64_t cap = (int64_t)g_sms * 2;
+  const int64_t cap = (int64_t)g_sms * per_sm;
   return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+template <typename T, int PL>
+int launch_bwd(const char* who, const void* x, const float* scale, const float* bias, const void* gy,
+               void* gx, float* gscale, float* gbias, int64_t rows, int cols, int act, float eps,
+               cudaStream_t s) {
+  auto fn = rmsnorm_act_bwd_kernel<T, PL>;
+  static bool attr_set = false;
+  const int max_cols = PL <= 8 ? kSmallCols : kMaxCols;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(2 * kWarps * max_cols * sizeof(float))) != cudaSuccess)
+      return emb::fail_cuda(who);
+    attr_set = true;
+  }
+  const size_t smem = (size_t)(gbias ? 2 : 1) * kWarps * cols * sizeof(float);
+  fn<<<grid_for(rows, PL <= 8 ? 6 : 2), kThreads, smem, s>>>(
+      (const T*)x, scale, bias, (const T*)gy, (T*)gx, gscale, gbias, rows, cols, act, eps);
+  return 0;
 }
 
 }  // namespace
 
-extern "C" int emb_rmsnorm_act_fwd(const void* x, const float* scale, void* y, int64_t rows,
-                                   int32_t cols, int32_t dtype, int32_t act, float eps, void* stream) {
+extern "C" int emb_rmsnorm_act_fwd(const void* x, const float* scale, const float* bias, void* y,
+                                   int64_t rows, int32_t cols, int32_t dtype, int32_t act, float eps,
+                                   void* stream) {
   const char* who = "emb_rmsnorm_act_fwd";
   if (int e = check(who, x, y, rows, cols, dtype)) return e;
   if (rows == 0) return 0;
-  const unsigned grid = (unsigned)((rows + kWarps - 1) / kWarps < (int64_t)g_sms * 8
-                                       ? (rows + kWarps - 1) / kWarps : (int64_t)g_sms * 8);
+  const unsigned grid = grid_for(rows, 8);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype)
     rmsnorm_act_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(
-        (const __nv_bfloat16*)x, scale, (__nv_bfloat16*)y, rows, cols, act, eps);
+        (const __nv_bfloat16*)x, scale, bias, (__nv_bfloat16*)y, rows, cols, act, eps);
   else
     rmsnorm_act_fwd_kernel<float><<<grid, kThreads, 0, s>>>(
-        (const float*)x, scale, (float*)y, rows, cols, act, eps);
+        (const float*)x, scale, bias, (float*)y, rows, cols, act, eps);
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;
 }
 
-extern "C" int emb_rmsnorm_act_bwd(const void* x, const float* scale, const void* gy, void* gx,
-                                   float* gscale, int64_t rows, int32_t cols, int32_t dtype,
-                                   int32_t act, float eps, void* stream) {
+extern "C" int emb_rmsnorm_act_bwd(const void* x, const float* scale, const float* bias,
+                                   const void* gy, void* gx, float* gscale, float* gbias,
+                                   int64_t rows, int32_t cols, int32_t dtype, int32_t act, float eps,
+                                   void* stream) {
   const char* who = "emb_rmsnorm_act_bwd";
   if (int e = check(who, x, gx, rows, cols, dtype)) return e;
   if ((uintptr_t)gy & 15) return emb::fail(-1, "%s: gy must be 16-byte aligned", who);
   if (cols > kMaxCols) return emb::fail(-1, "%s: cols=%d > %d", who, cols, kMaxCols);
+  if ((bias || gbias) && cols > kSmallCols)
+    return emb::fail(-1, "%s: a bias needs cols <= %d (got %d)", who, kSmallCols, cols);
+  if ((bias == nullptr) != (gbias == nullptr))
+    return emb::fail(-1, "%s: bias and gbias must be given together", who);
   if (rows == 0) return 0;
-  const unsigned grid = grid_for(rows);
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t smem = (size_t)kWarps * cols * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(rmsnorm_act_bwd_kernel<__nv_bfloat16>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(kWarps * kMaxCols * sizeof(float))) != cudaSuccess ||
-        cudaFuncSetAttribute(rmsnorm_act_bwd_kernel<float>,
-                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(kWarps * kMaxCols * sizeof(float))) != cudaSuccess)
-      return emb::fail_cuda(who);
-    attr_set = true;
+  int e;
+  if (cols <= kSmallCols) {
+    e = dtype ? launch_bwd<__nv_bfloat16, 8>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s)
+              : launch_bwd<float, 8>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s);
+  } else {
+    e = dtype ? launch_bwd<__nv_bfloat16, 64>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s)
+              : launch_bwd<float, 64>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s);
   }
-  if (dtype)
-    rmsnorm_act_bwd_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(
-        (const __nv_bfloat16*)x, scale, (const __nv_bfloat16*)gy, (__nv_bfloat16*)gx, gscale,
-        rows, cols, act, eps);
-  else
-    rmsnorm_act_bwd_kernel<float><<<grid, kThreads, smem, s>>>(
-        (const float*)x, scale, (const float*)gy, (float*)gx, gscale, rows, cols, act, eps);
+  if (e) return e;
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;

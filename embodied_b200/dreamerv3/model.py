@@ -96,19 +96,25 @@ class Model:
     y = torch.bmm(x, w).transpose(0, 1)                      # (M, g, out/g)
     return y.reshape(*lead, -1) + b
 
-  def norm(self, x, name, act=True):                         # nets.py:369-399 'rms', eps 1e-4
+  def norm(self, x, name, act=True, bias=None):              # nets.py:369-399 'rms', eps 1e-4
+    """`bias`: (fp32 leaf) bias of the convolution that produced x, added here
+    instead of in a separate pass over the conv output."""
     scale = self.store.w[f'{name}/scale']
     need_grad = torch.is_grad_enabled() and (x.requires_grad or scale.requires_grad)
-    if self.fused_norm and ops.rmsnorm_supported(x, need_grad):
-      return ops.rmsnorm_act(x, scale, act)                  # one kernel each way
+    if self.fused_norm and ops.rmsnorm_supported(x, need_grad, bias is not None):
+      return ops.rmsnorm_act(x, scale, act, bias=bias)       # one kernel each way
+    if bias is not None:
+      x = x + bias.to(x.dtype)
     xf = x.to(f32)
     y = xf * (torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-4) * scale)
     y = y.to(self.cd)
     return silu(y) if act else y
 
-  def conv(self, x, name):                                   # nets.py:298-323; x is NHWC
+  def conv(self, x, name, bias=True):                        # nets.py:298-323; x is NHWC
+    """bias=False: the caller adds the bias inside the following fused norm
+    (after the 2x2 max-pool, with which a per-channel constant commutes)."""
     w = self.W(f'{name}/kernel').permute(3, 2, 0, 1)         # HWIO -> OIHW
-    b = self.W(f'{name}/bias')
+    b = self.W(f'{name}/bias') if bias else None
     y = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=w.shape[-1] // 2)
     return y.permute(0, 2, 3, 1)                             # NHWC view (channels_last memory)
 
@@ -130,9 +136,9 @@ class Model:
     lead = x.shape[:-3]
     x = x.reshape(-1, *x.shape[-3:]).to(self.cd)
     for i in range(len(cfg.mults)):
-      x = self.conv(x, f'enc/cnn{i}')
+      x = self.conv(x, f'enc/cnn{i}', bias=False)
       x = self.pool(x)
-      x = self.norm(x, f'enc/cnn{i}norm')
+      x = self.norm(x, f'enc/cnn{i}norm', bias=self.store.w[f'enc/cnn{i}/bias'])
     return x.reshape(*lead, -1)
 
   # ----------------------------------------------------------------------- rssm
@@ -228,6 +234,10 @@ class Model:
     """dyn = max(KL(sg(post) || prior), free), rep = max(KL(post || sg(prior)), free),
     both on unimixed distributions, summed over the S latents."""
     cfg = self.cfg
+    if self.fused_norm and post_logit.dim() == 4 and ops.kl_supported(post_logit, prior_logit):
+      dyn, rep, ent_post, ent_prior = ops.rssm_kl(
+          post_logit, prior_logit, cfg.unimix, cfg.free_nats)
+      return dyn, rep, dict(dyn_ent=ent_prior.mean(), rep_ent=ent_post.mean())
     post = torch.log(self.unimix(post_logit))
     prior = torch.log(self.unimix(prior_logit))
 
@@ -260,7 +270,8 @@ class Model:
     x = self.norm(x0 + x1, 'dec/spnorm')
     for i in reversed(range(len(depths) - 1)):
       x = self.upsample(x)
-      x = self.norm(self.conv(x, f'dec/conv{i}'), f'dec/conv{i}norm')
+      x = self.norm(self.conv(x, f'dec/conv{i}', bias=False), f'dec/conv{i}norm',
+                    bias=self.store.w[f'dec/conv{i}/bias'])
     x = torch.sigmoid(self.conv(self.upsample(x), 'dec/imgout').to(f32))
     return x.reshape(*lead, *x.shape[1:])
 

@@ -15,10 +15,16 @@ def _lib_bound():
   global _bound
   lib = _lib.load()
   if not _bound:
-    lib.emb_rmsnorm_act_fwd.argtypes = [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _fl, _vp]
+    lib.emb_rmsnorm_act_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _fl, _vp]
     lib.emb_rmsnorm_act_fwd.restype = ctypes.c_int
-    lib.emb_rmsnorm_act_bwd.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _fl, _vp]
+    lib.emb_rmsnorm_act_bwd.argtypes = [
+        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _fl, _vp]
     lib.emb_rmsnorm_act_bwd.restype = ctypes.c_int
+    kp = ctypes.POINTER(KlArgs)
+    lib.emb_rssm_kl_fwd.argtypes = [kp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.emb_rssm_kl_fwd.restype = ctypes.c_int
+    lib.emb_rssm_kl_bwd.argtypes = [kp, _vp, _vp, _vp, _vp, _vp, _vp]
+    lib.emb_rssm_kl_bwd.restype = ctypes.c_int
     for name in ('emb_maxpool2_nhwc_fwd', 'emb_maxpool2_nhwc_bwd'):
       getattr(lib, name).argtypes = [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]
       getattr(lib, name).restype = ctypes.c_int
@@ -33,21 +39,22 @@ def _dtype_code(t):
   return {torch.float32: 0, torch.bfloat16: 1}[t.dtype]
 
 
-def rmsnorm_supported(x, need_grad):
+def rmsnorm_supported(x, need_grad, bias=False):
   if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
     return False
   cols = x.shape[-1]
   per = 4 if x.dtype == torch.float32 else 8
-  if cols % per or (need_grad and cols > 2048):
+  if cols % per or (need_grad and cols > 2048) or (bias and cols > 256):
     return False
   return True
 
 
 class RmsNormAct(torch.autograd.Function):
-  """y = act(rms_norm(x) * scale) over the last axis (nets.py:361-399 + act)."""
+  """y = act(rms_norm(x + bias) * scale) over the last axis (nets.py:361-399 +
+  act; `bias` = the bias of the preceding convolution, or None)."""
 
   @staticmethod
-  def forward(ctx, x, scale, act, eps):
+  def forward(ctx, x, scale, bias, act, eps):
     lib = _lib_bound()
     x = x.contiguous()
     y = torch.empty_like(x)
@@ -55,30 +62,103 @@ class RmsNormAct(torch.autograd.Function):
     rows = x.numel() // cols
     stream = torch.cuda.current_stream(x.device).cuda_stream
     _lib.check(lib.emb_rmsnorm_act_fwd(
-        x.data_ptr(), scale.data_ptr(), y.data_ptr(), rows, cols, _dtype_code(x), int(act),
-        eps, stream))
-    ctx.save_for_backward(x, scale)
+        x.data_ptr(), scale.data_ptr(), None if bias is None else bias.data_ptr(), y.data_ptr(),
+        rows, cols, _dtype_code(x), int(act), eps, stream))
+    ctx.save_for_backward(x, scale, bias)
     ctx.act, ctx.eps = int(act), eps
     return y
 
   @staticmethod
   def backward(ctx, gy):
     lib = _lib_bound()
-    x, scale = ctx.saved_tensors
+    x, scale, bias = ctx.saved_tensors
     gy = gy.contiguous()
     gx = torch.empty_like(x)
     gscale = torch.zeros_like(scale)
+    gbias = None if bias is None else torch.zeros_like(bias)
     cols = x.shape[-1]
     rows = x.numel() // cols
     stream = torch.cuda.current_stream(x.device).cuda_stream
     _lib.check(lib.emb_rmsnorm_act_bwd(
-        x.data_ptr(), scale.data_ptr(), gy.data_ptr(), gx.data_ptr(), gscale.data_ptr(),
+        x.data_ptr(), scale.data_ptr(), None if bias is None else bias.data_ptr(), gy.data_ptr(),
+        gx.data_ptr(), gscale.data_ptr(), None if bias is None else gbias.data_ptr(),
         rows, cols, _dtype_code(x), ctx.act, ctx.eps, stream))
-    return gx, gscale, None, None
+    return gx, gscale, gbias, None, None
 
 
-def rmsnorm_act(x, scale, act=True, eps=1e-4):
-  return RmsNormAct.apply(x, scale, act, eps)
+def rmsnorm_act(x, scale, act=True, eps=1e-4, bias=None):
+  if bias is not None:
+    bias = bias.to(torch.float32)
+  return RmsNormAct.apply(x, scale, bias, act, eps)
+
+
+# ------------------------------------------------------------------ KL reduction
+class KlArgs(ctypes.Structure):
+  _fields_ = [('post', _vp), ('prior', _vp), ('dtype_post', _i32), ('dtype_prior', _i32),
+              ('B', _i32), ('T', _i32), ('S', _i32), ('C', _i32),
+              ('post_stride_b', _i64), ('post_stride_t', _i64),
+              ('prior_stride_b', _i64), ('prior_stride_t', _i64),
+              ('unimix', _fl), ('free_nats', _fl)]
+
+
+def _kl_view(x):
+  """(B, T, S, C) with the last two axes dense -> (tensor, stride_b, stride_t)."""
+  S, C = x.shape[-2:]
+  if x.stride(-1) != 1 or x.stride(-2) != C:
+    x = x.contiguous()
+  return x, x.stride(0), x.stride(1)
+
+
+def kl_supported(post, prior):
+  ok = lambda x: x.is_cuda and x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)
+  return ok(post) and ok(prior) and post.shape == prior.shape and post.shape[-1] <= 128
+
+
+class RssmKl(torch.autograd.Function):
+  """dyn, rep, ent_post, ent_prior = RSSM.loss's KL block (rssm.py:123-132) for
+  logits (B, T, S, C): one kernel each way (emb_rssm_kl_fwd / _bwd)."""
+
+  @staticmethod
+  def forward(ctx, post, prior, unimix, free_nats):
+    lib = _lib_bound()
+    post, psb, pst = _kl_view(post)
+    prior, qsb, qst = _kl_view(prior)
+    B, T, S, C = post.shape
+    out = torch.empty((5, B, T), dtype=f32, device=post.device)
+    args = KlArgs(post.data_ptr(), prior.data_ptr(), _dtype_code(post), _dtype_code(prior),
+                  B, T, S, C, psb, pst, qsb, qst, unimix, free_nats)
+    stream = torch.cuda.current_stream(post.device).cuda_stream
+    p = [out[i].data_ptr() for i in range(5)]
+    _lib.check(lib.emb_rssm_kl_fwd(ctypes.byref(args), p[0], p[1], p[2], p[3], p[4], stream))
+    ctx.save_for_backward(post, prior, out[2])
+    ctx.consts = (unimix, free_nats)
+    ctx.mark_non_differentiable(out[3], out[4])
+    return out[0], out[1], out[3], out[4]
+
+  @staticmethod
+  def backward(ctx, g_dyn, g_rep, _a, _b):
+    lib = _lib_bound()
+    post, prior, kl_raw = ctx.saved_tensors
+    post, psb, pst = _kl_view(post)
+    prior, qsb, qst = _kl_view(prior)
+    B, T, S, C = post.shape
+    unimix, free_nats = ctx.consts
+    zero = lambda g: torch.zeros((B, T), dtype=f32, device=post.device) if g is None \
+        else g.to(f32).contiguous()
+    g_dyn, g_rep = zero(g_dyn), zero(g_rep)
+    g_post = torch.empty((B, T, S, C), dtype=f32, device=post.device)
+    g_prior = torch.empty((B, T, S, C), dtype=f32, device=post.device)
+    args = KlArgs(post.data_ptr(), prior.data_ptr(), _dtype_code(post), _dtype_code(prior),
+                  B, T, S, C, psb, pst, qsb, qst, unimix, free_nats)
+    stream = torch.cuda.current_stream(post.device).cuda_stream
+    _lib.check(lib.emb_rssm_kl_bwd(
+        ctypes.byref(args), kl_raw.data_ptr(), g_dyn.data_ptr(), g_rep.data_ptr(),
+        g_post.data_ptr(), g_prior.data_ptr(), stream))
+    return g_post.to(post.dtype), g_prior.to(prior.dtype), None, None
+
+
+def rssm_kl(post, prior, unimix, free_nats):
+  return RssmKl.apply(post, prior, float(unimix), float(free_nats))
 
 
 def spatial_supported(x):

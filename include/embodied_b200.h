@@ -220,16 +220,44 @@ typedef struct emb_rssm_bwd_args {
 
 int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream);
 
+/* The KL / free-nats / entropy reduction of RSSM.loss (dreamerv3/rssm.py:120-133,
+ * embodied/jax/outs.py:208-240) as one pass over the posterior and prior logits
+ * each way (embodied_b200/csrc/kl.cu).  Logits: fp32 (dtype 0) or bf16 (1); row
+ * (b, t) starts at element b*stride_b + t*stride_t, its S*C classes contiguous.
+ * Outputs are dense fp32 [B*T] (fwd) / [B*T][S][C] (bwd).
+ *   dyn = rep = max(KL(post || prior), free_nats) on the unimixed distributions,
+ *   kl_raw the unclipped sum (the clip mask of the backward pass),
+ *   ent_post / ent_prior the entropies summed over the S latents.
+ * bwd: g_prior = g_dyn * dKL/dprior, g_post = g_rep * dKL/dpost (the two stop-
+ * gradients of rssm.py:125-128), zero where kl_raw < free_nats. */
+typedef struct emb_rssm_kl_args {
+  const void* post;
+  const void* prior;
+  int32_t dtype_post, dtype_prior;
+  int32_t B, T, S, C;
+  int64_t post_stride_b, post_stride_t, prior_stride_b, prior_stride_t;
+  float unimix, free_nats;
+} emb_rssm_kl_args;
+
+int emb_rssm_kl_fwd(const emb_rssm_kl_args* args, float* dyn, float* rep, float* kl_raw,
+                    float* ent_post, float* ent_prior, void* stream);
+int emb_rssm_kl_bwd(const emb_rssm_kl_args* args, const float* kl_raw, const float* g_dyn,
+                    const float* g_rep, float* g_post, float* g_prior, void* stream);
+
 /* rms-norm (+ silu) over the last axis, one HBM pass each way
- * (embodied/jax/nets.py:361-399 Norm('rms') followed by act, eps 1e-4).
+ * (embodied/jax/nets.py:361-399 Norm('rms') followed by act, eps 1e-4), with the
+ * preceding layer's bias folded in:  y = act(rms_norm(x + bias) * scale).
  * x, y, gy, gx: [rows][cols] contiguous, dtype 0 = fp32 / 1 = bf16, 16-byte
- * aligned, cols % (16 / elem size) == 0; scale / gscale fp32 [cols].
- * bwd ADDS the scale gradient into gscale and needs cols <= 2048. */
-int emb_rmsnorm_act_fwd(const void* x, const float* scale, void* y, int64_t rows,
-                        int32_t cols, int32_t dtype, int32_t act, float eps, void* stream);
-int emb_rmsnorm_act_bwd(const void* x, const float* scale, const void* gy, void* gx,
-                        float* gscale, int64_t rows, int32_t cols, int32_t dtype,
-                        int32_t act, float eps, void* stream);
+ * aligned, cols % (16 / elem size) == 0; scale / gscale / bias / gbias fp32 [cols].
+ * bias / gbias may be NULL (no bias); a bias needs cols <= 256 (the channel
+ * axis of the convolutions -- dense layers add theirs in the GEMM epilogue).
+ * bwd ADDS the scale / bias gradients into gscale / gbias and needs cols <= 2048. */
+int emb_rmsnorm_act_fwd(const void* x, const float* scale, const float* bias, void* y,
+                        int64_t rows, int32_t cols, int32_t dtype, int32_t act, float eps,
+                        void* stream);
+int emb_rmsnorm_act_bwd(const void* x, const float* scale, const float* bias, const void* gy,
+                        void* gx, float* gscale, float* gbias, int64_t rows, int32_t cols,
+                        int32_t dtype, int32_t act, float eps, void* stream);
 
 /* The optimiser chain of dreamerv3 on the flat parameter buffer, two HBM passes
  * (dreamerv3/agent.py:342-379; embodied/jax/opt.py:109-164: clip_by_agc ->

@@ -1,0 +1,69 @@
+"""emb_rssm_kl_fwd/bwd (the fused KL / free-nats / entropy reduction of
+RSSM.loss, dreamerv3/rssm.py:120-133) against the oracle's restatement
+(oracle/dreamer_oracle.py unimix_logits / cat_kl / cat_entropy) with torch
+autograd for the gradients.  fp32 tolerance 1e-5 (max-abs relative)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+from embodied_b200.dreamerv3 import ops      # noqa: E402
+from oracle import dreamer_oracle as do      # noqa: E402
+
+
+def oracle_kl(post, prior, unimix, free):
+  q = do.unimix_logits(prior.float(), unimix)
+  p = do.unimix_logits(post.float(), unimix)
+  dyn = torch.clamp(do.cat_kl(p.detach(), q), min=free)
+  rep = torch.clamp(do.cat_kl(p, q.detach()), min=free)
+  return dyn, rep, do.cat_entropy(p).sum(-1), do.cat_entropy(q).sum(-1)
+
+
+def rel(a, b):
+  return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize('B,T,S,C', [(1, 1, 1, 4), (3, 5, 6, 8), (16, 64, 32, 64), (2, 3, 40, 96),
+                                     (2, 2, 4, 128)])
+@pytest.mark.parametrize('free', [0.0, 1.0])
+def test_matches_oracle_fp32(B, T, S, C, free):
+  g = torch.Generator().manual_seed(B * T + S * C)
+  # a spread of scales so that some rows fall below and some above free_nats
+  scale = torch.rand(B, T, 1, 1, generator=g) * 3
+  post = (torch.randn(B, T, S, C, generator=g) * scale)
+  prior = (torch.randn(B, T, S, C, generator=g) * scale)
+  gd, gr = torch.randn(B, T, generator=g), torch.randn(B, T, generator=g)
+  p0, q0 = post.clone().requires_grad_(True), prior.clone().requires_grad_(True)
+  dyn0, rep0, ep0, eq0 = oracle_kl(p0, q0, 0.01, free)
+  ((dyn0 * gd).sum() + (rep0 * gr).sum()).backward()
+  p1 = post.cuda().requires_grad_(True)
+  q1 = prior.cuda().requires_grad_(True)
+  assert ops.kl_supported(p1, q1)
+  dyn1, rep1, ep1, eq1 = ops.rssm_kl(p1, q1, 0.01, free)
+  ((dyn1 * gd.cuda()).sum() + (rep1 * gr.cuda()).sum()).backward()
+  for a, b in ((dyn1, dyn0), (rep1, rep0), (ep1, ep0), (eq1, eq0)):
+    assert rel(a.cpu(), b) < 1e-5
+  assert rel(p1.grad.cpu(), p0.grad) < 2e-5
+  assert rel(q1.grad.cpu(), q0.grad) < 2e-5
+
+
+def test_strided_views_and_bf16_prior():
+  """The posterior logits arrive as a (B, T) transposed view of the scan's
+  time-major buffer, the prior logits in the compute dtype."""
+  T, R, B, S, C = 7, 16, 5, 32, 64
+  g = torch.Generator().manual_seed(3)
+  buf = torch.randn(T, R, S * C, generator=g).cuda()
+  post = buf[:, :B].transpose(0, 1).reshape(B, T, S, C)
+  prior = torch.randn(B, T, S, C, generator=g).cuda().to(torch.bfloat16)
+  assert not post.is_contiguous()
+  dyn, rep, ep, eq = ops.rssm_kl(post, prior, 0.01, 1.0)
+  dyn0, rep0, ep0, eq0 = oracle_kl(post.cpu().contiguous(), prior.cpu().float(), 0.01, 1.0)
+  assert rel(dyn.cpu(), dyn0) < 1e-5 and rel(eq.cpu(), eq0) < 1e-5 and rel(ep.cpu(), ep0) < 1e-5
+
+
+def test_argument_validation():
+  lib = ops._lib_bound()
+  args = ops.KlArgs(None, None, 0, 0, 1, 1, 1, 200, 0, 0, 0, 0, 0.01, 1.0)
+  import ctypes
+  assert lib.emb_rssm_kl_fwd(ctypes.byref(args), None, None, None, None, None, None) == -1
+  assert b'classes' in lib.emb_last_error()

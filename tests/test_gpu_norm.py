@@ -56,3 +56,30 @@ def test_unsupported_shapes_fall_back():
   assert not ops.rmsnorm_supported(x, False)
   assert ops.rmsnorm_supported(torch.randn(3, 8192, device='cuda'), False)
   assert not ops.rmsnorm_supported(torch.randn(3, 8192, device='cuda'), True)
+
+
+@pytest.mark.parametrize('shape', [(5, 8), (1000, 128), (77, 192), (9, 4, 4, 256)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_bias_folded_into_the_norm(shape, dtype):
+  """y = silu(rms(x + bias) * scale): the convolution bias added inside the
+  norm kernel (values and all three gradients) against the fp32 formula."""
+  g = torch.Generator(device='cuda').manual_seed(shape[-1])
+  x = (torch.randn(*shape, generator=g, device='cuda') * 2).to(dtype)
+  scale = torch.rand(shape[-1], generator=g, device='cuda') + 0.5
+  bias = torch.randn(shape[-1], generator=g, device='cuda')
+  gy = torch.randn(*shape, generator=g, device='cuda').to(dtype)
+  x1 = x.clone().requires_grad_(True)
+  s1, b1 = scale.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+  assert ops.rmsnorm_supported(x1, True, True)
+  y1 = ops.rmsnorm_act(x1, s1, True, bias=b1)
+  y1.backward(gy)
+  x2 = x.float().clone().requires_grad_(True)
+  s2, b2 = scale.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+  y2 = reference(x2 + b2, s2, True, torch.float32)
+  y2.backward(gy.float())
+  tol = 2e-5 if dtype == torch.float32 else 3e-2
+  assert rel(y1, y2) < (1e-5 if dtype == torch.float32 else 2 ** -6)
+  assert rel(x1.grad, x2.grad) < tol
+  assert rel(s1.grad, s2.grad) < tol
+  assert rel(b1.grad, b2.grad) < tol
+  assert not ops.rmsnorm_supported(torch.randn(3, 512, device='cuda'), True, True)
