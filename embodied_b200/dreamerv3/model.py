@@ -149,13 +149,21 @@ class Model:
     return a * (~reset)[..., None].to(self.cd)
 
   def core(self, deter, stoch_flat, x2):                     # rssm.py:135-159
-    """x2 = silu(rms(dynin2(action))) is precomputed by the caller."""
+    """x2 = silu(rms(dynin2(action))) is precomputed by the caller.  dynhid0's
+    input is [deter_g, x0, x1, x2] per group (rssm.py:147-148); instead of
+    materialising the g-fold repeat, its kernel is applied in two batched
+    GEMMs: deter_g @ W[g, :Dg] + x012 @ W[g, Dg:] (x012 broadcast over g)."""
     g = self.cfg.blocks
+    M = len(deter)
     x0 = self.norm(self.dense(deter, 'dyn/dynin0'), 'dyn/dynin0norm')
     x1 = self.norm(self.dense(stoch_flat, 'dyn/dynin1'), 'dyn/dynin1norm')
-    x = torch.cat([x0, x1, x2], -1)[:, None, :].expand(-1, g, -1)
-    x = torch.cat([deter.reshape(len(deter), g, -1), x], -1).reshape(len(deter), -1)
-    x = self.norm(self.block(x, 'dyn/dynhid0'), 'dyn/dynhid0norm')
+    x012 = torch.cat([x0, x1, x2], -1)
+    w, b = self.W('dyn/dynhid0/kernel'), self.W('dyn/dynhid0/bias')
+    Dg = deter.shape[-1] // g
+    y = torch.bmm(deter.reshape(M, g, Dg).transpose(0, 1), w[:, :Dg])
+    y = torch.baddbmm(y, x012[None].expand(g, -1, -1), w[:, Dg:])
+    x = y.transpose(0, 1).reshape(M, -1) + b
+    x = self.norm(x, 'dyn/dynhid0norm')
     x = self.block(x, 'dyn/dyngru')
     reset, cand, update = [
         y.reshape(len(x), -1) for y in x.reshape(len(x), g, -1).chunk(3, -1)]
@@ -370,22 +378,26 @@ class Model:
   @torch.no_grad()
   def imagine(self, deter, stoch, noise_stoch, noise_act):   # rssm.py:94-118, agent.py:188-200
     """From B*K start states roll H steps with the policy in the loop.  Returns
-    deter (BK,H+1,D), stoch (BK,H+1,S,C), action (BK,H+1)."""
+    the features (BK, H+1, D + S*C) -- deter | flat stoch, written in place step
+    by step -- and the actions (BK, H+1)."""
     cfg = self.cfg
-    H = cfg.imag_length
+    H, D = cfg.imag_length, cfg.deter
     n = len(deter)
     never = torch.zeros(n, dtype=torch.bool, device=deter.device)
-    deters, stochs, acts = [deter], [stoch], []
-    for h in range(H):
-      logits = self.head(self.feat2tensor(deter, stoch), 'pol', cfg.pol_layers, 'action/logits')
+    feat = torch.empty((n, H + 1, D + cfg.stoch * cfg.classes), dtype=self.cd, device=deter.device)
+    acts = []
+    for h in range(H + 1):
+      feat[:, h, :D] = deter
+      feat[:, h, D:] = stoch.reshape(n, -1)
+      logits = self.head(feat[:, h], 'pol', cfg.pol_layers, 'action/logits')
       a = torch.argmax(logits + noise_act[:, h], -1)
+      acts.append(a)
+      if h == H:
+        break
       x2 = self.act_branch(a, never)
       deter = self.core(deter, stoch.reshape(n, -1), x2)
       stoch = self.sample_stoch(self.prior(deter), noise_stoch[:, h])
-      acts.append(a); deters.append(deter); stochs.append(stoch)
-    logits = self.head(self.feat2tensor(deter, stoch), 'pol', cfg.pol_layers, 'action/logits')
-    acts.append(torch.argmax(logits + noise_act[:, H], -1))
-    return torch.stack(deters, 1), torch.stack(stochs, 1), torch.stack(acts, 1)
+    return feat, torch.stack(acts, 1)
 
   # ------------------------------------------------------------------------ loss
   def loss(self, carry, obs, prevact, noise, update=True):   # agent.py:156-245
@@ -411,11 +423,13 @@ class Model:
     losses['image'] = (recon - target).square().sum((-3, -2, -1))
 
     K, H = T, cfg.imag_length
-    imgdeter, imgstoch, imgact = self.imagine(
+    imgfeat, imgact = self.imagine(
         feat['deter'].detach().reshape(B * K, -1),
         feat['stoch'].detach().reshape(B * K, cfg.stoch, cfg.classes),
         noise['imag_stoch'], noise['imag_act'])
-    los, ret, mets = self.imag_loss(imgact, self.feat2tensor(imgdeter, imgstoch), update)
+    imgdeter = imgfeat[..., :cfg.deter]
+    imgstoch = imgfeat[..., cfg.deter:].reshape(B * K, H + 1, cfg.stoch, cfg.classes)
+    los, ret, mets = self.imag_loss(imgact, imgfeat, update)
     losses.update({k: v.mean(1).reshape(B, K) for k, v in los.items()})
     metrics.update(mets)
 
