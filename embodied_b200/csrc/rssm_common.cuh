@@ -25,6 +25,8 @@ constexpr int kRows = 16;          // padded batch rows (one m16 tile)
 constexpr int kMaxTiles = 24;      // n8 tiles accumulated per pass
 constexpr int ENG_F32 = 0;
 constexpr int ENG_BF16 = 1;
+constexpr int ENG_TMA = 1;          // ABI engine ids: 1 = bf16 + TMA ring, 2 = bf16 register-staged
+constexpr int ENG_LEGACY = 2;
 
 __device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
 

@@ -417,7 +417,7 @@ rssm_fwd_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
 
 size_t fwd_smem_bytes(const emb_rssm_fwd_args& a) {
   size_t n = sizeof(float) * (kRows * kMaxTiles * 8 + 2 * kRows);
-  if (a.engine != rssm::ENG_BF16) return n;
+  if (a.engine == rssm::ENG_F32) return n;
   auto cdiv = [](int x, int y) { return (x + y - 1) / y; };
   auto tiles = [&](int total, int unit, int groups) {     // n8 tiles one pass of this layer handles
     const int cpg = groups > 1 ? (a.ncta / groups > 1 ? a.ncta / groups : 1) : a.ncta;
@@ -439,6 +439,10 @@ int g_sms = 0;
 
 }  // namespace
 
+namespace emb_tma {
+int launch_fwd(const emb_rssm_fwd_args& a, void* stream);   // rssm_fwd_tma.cu
+}
+
 extern "C" int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream) {
   const char* who = "emb_rssm_observe_fwd";
   if (!args) return emb::fail(-1, "%s: args is NULL", who);
@@ -449,8 +453,9 @@ extern "C" int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream)
   if (a.G < 1 || a.D % a.G || (a.D / a.G) % 16 || a.H % 16 || (a.S * a.C) % 16 || a.D % 16)
     return emb::fail(-1, "%s: D/G, H and S*C must be multiples of 16 (D=%d G=%d H=%d S=%d C=%d)",
                      who, a.D, a.G, a.H, a.S, a.C);
-  if (a.engine != rssm::ENG_F32 && a.engine != rssm::ENG_BF16)
+  if (a.engine != rssm::ENG_F32 && a.engine != rssm::ENG_TMA && a.engine != rssm::ENG_LEGACY)
     return emb::fail(-1, "%s: engine %d", who, a.engine);
+  if (a.engine == rssm::ENG_TMA) return emb_tma::launch_fwd(a, stream);
   if (g_sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -462,8 +467,8 @@ extern "C" int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream)
   const size_t smem = fwd_smem_bytes(a);
   if (smem > 227 * 1024)
     return emb::fail(-1, "%s: needs %zu bytes of shared memory (> 227 KiB)", who, smem);
-  const void* fn = a.engine == rssm::ENG_BF16 ? (const void*)rssm_fwd_kernel<rssm::ENG_BF16>
-                                              : (const void*)rssm_fwd_kernel<rssm::ENG_F32>;
+  const void* fn = a.engine != rssm::ENG_F32 ? (const void*)rssm_fwd_kernel<rssm::ENG_BF16>
+                                             : (const void*)rssm_fwd_kernel<rssm::ENG_F32>;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return emb::fail_cuda(who);
   emb_rssm_fwd_args copy = a;

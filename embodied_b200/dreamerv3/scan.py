@@ -22,21 +22,22 @@ PROFILE = None
 # train step (bench.py sets GRAPH_TIMERS = {} before the agent captures).
 GRAPH_TIMERS = None
 ROWS = 16
-ENG_F32, ENG_BF16 = 0, 1
+ENG_F32, ENG_BF16, ENG_LEGACY = 0, 1, 2     # fp32 FFMA | bf16 mma + TMA ring | bf16 register-staged
 
 _vp, _i32, _fl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_float
 
 
 class FwdArgs(ctypes.Structure):
   _fields_ = (
-      [(n, _i32) for n in ('B', 'T', 'D', 'H', 'S', 'C', 'G', 'engine', 'ncta', 'pad_')] +
+      [(n, _i32) for n in ('B', 'T', 'D', 'H', 'S', 'C', 'G', 'engine', 'ncta', 'tma_cfg')] +
       [('unimix', _fl), ('eps', _fl)] +
       [(n, _vp) for n in (
           'w_ph1', 'w_logit', 'w_hid', 'w_gru', 'w_in1',
           'b0', 'b1', 'b_hid', 'b_gru', 'b_logit', 's0', 's1', 's_hid', 's_obs',
           'deter0', 'x2', 'pre_tok', 'keep', 'gumbel',
           'deter', 'logit', 'index',
-          'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'probs', 'rstd', 'deterA', 'barrier', 'timing')])
+          'y0', 'y1', 'yhid', 'gates', 'yobs', 'sumsq', 'probs', 'rstd', 'deterA', 'barrier', 'timing',
+          'hid_pre', 'sumsq_obs')])
 
 
 def _graph_timer(name):
@@ -84,6 +85,21 @@ def tile_assignment(tiles, ncta, unit=1, groups=1):
 _IDS = {}
 
 
+def tile_groups(per):
+  """rssm_tma.cuh tile_groups(): tile groups the 8 consumer warps form."""
+  tg = 1
+  while tg < 8 and tg * 4 <= per:
+    tg *= 2
+  return tg
+
+
+def pad_tiles(per, unit=1):
+  """rssm_tma.cuh pad_tiles(): tiles per CTA block of the TMA engine."""
+  while per % tile_groups(per):
+    per += unit
+  return per
+
+
 def pack_matrix(w, engine, ncta, unit=1, groups=1):
   """w: (K, N) fp32 -> the engine's streaming layout (rssm_common.cuh).
 
@@ -94,12 +110,16 @@ def pack_matrix(w, engine, ncta, unit=1, groups=1):
   fp32: [N/8][K][8]."""
   K, N = w.shape
   assert K % 16 == 0 and N % 8 == 0, (K, N)
-  if engine != ENG_BF16:
+  if engine == ENG_F32:
     return w.reshape(K, N // 8, 8).transpose(0, 1).contiguous()
-  key = (N // 8, ncta, unit, groups, str(w.device))
+  key = (N // 8, ncta, unit, groups, engine, str(w.device))
   hit = _IDS.get(key)
   if hit is None:                      # host -> device once (never inside a stream capture)
     per, ids = tile_assignment(N // 8, ncta, unit, groups)
+    if engine == ENG_BF16:          # TMA engine: zero tiles up to a multiple of the tile groups
+      padded = pad_tiles(per, unit)
+      ids = [row + [-1] * (padded - per) for row in ids]
+      per = padded
     hit = _IDS[key] = (per, torch.tensor(ids, dtype=torch.long, device=w.device))
   per, ids = hit                                                      # (ncta, per)
   wt = torch.cat([w.reshape(K, N // 8, 8).to(torch.bfloat16),
@@ -120,11 +140,19 @@ def pack(store, cfg, engine, ncta):
   m = lambda n: store.view('master', n)
   wobs = m('dyn/obs0/kernel')
   hid = m('dyn/dynhid0/kernel')                             # (G, Kh, Dg)
+  extra = {}
+  if engine == ENG_BF16:
+    # the action branch leaves the scan: rows [deter_g | x0 | x1] stay in the
+    # streamed block, rows of x2 become one (B*T)-row GEMM (hid_pre)
+    keep_rows = Dg + 2 * cfg.hidden
+    extra['w_hid_x2'] = hid[:, keep_rows:].permute(1, 0, 2).reshape(-1, D).to(torch.bfloat16)
+    hid = hid[:, :keep_rows]
   hid = hid.permute(1, 0, 2).reshape(hid.shape[1], D)
   gru = m('dyn/dyngru/kernel')                              # (G, Dg, 3*Dg), columns (gate, j)
   gru = gru.reshape(G, Dg, 3, Dg // 8, 8).permute(1, 0, 3, 2, 4).reshape(Dg, 3 * D)
-  cd = torch.bfloat16 if engine == ENG_BF16 else f32
+  cd = f32 if engine == ENG_F32 else torch.bfloat16
   return dict(
+      **extra,
       w_ph1=pack_matrix(torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1), engine, ncta),
       w_logit=pack_matrix(m('dyn/obslogit/kernel'), engine, ncta),
       w_hid=pack_matrix(hid, engine, ncta, groups=G),
@@ -212,11 +240,17 @@ class Scan:
         rstd=torch.zeros((T + 1, 3, ROWS), dtype=f32, device=dev),
         gates=z(T, 4, ROWS, D), yobs=z(T, ROWS, H),
         sumsq=torch.zeros((T, ROWS), dtype=f32, device=dev),
-        deterA=torch.empty(2 * ROWS * D + ROWS * H, dtype=torch.bfloat16, device=dev),
+        sumsq_obs=torch.zeros((T, ROWS), dtype=f32, device=dev),
+        deterA=torch.zeros(2 * ROWS * D + 2 * ROWS * H, dtype=torch.bfloat16, device=dev),
         barrier=torch.zeros(4, dtype=torch.int32, device=dev))
     sv['x2_f32'] = sv['x2']
-    if self.engine == ENG_BF16:
+    if self.engine == ENG_LEGACY:
       sv['x2'] = a_fragments(sv['x2'])
+    if self.engine == ENG_BF16:
+      # hoisted action branch of dynhid0 (+ its bias): one (T*16)-row GEMM
+      # (bf16 operands, fp32 accumulation and output -- what the in-scan mma did)
+      sv['hid_pre'] = (torch.mm(sv['x2'].reshape(T * ROWS, H).to(torch.bfloat16), w['w_hid_x2'],
+                                out_dtype=f32) + m('dyn/dynhid0/bias')).reshape(T, ROWS, D)
     sv['y0'][0] = rows16(y0.to(f32), B)
     sv['y1'][0] = rows16(y1.to(f32), B)
     vec = dict(
@@ -227,9 +261,9 @@ class Scan:
     args = FwdArgs(B=B, T=T, D=D, H=H, S=S, C=C, G=G, engine=self.engine, ncta=self.ncta,
                    unimix=cfg.unimix, eps=1e-4)
     if self.timing:
-      sv['timing'] = torch.zeros((T, 16), dtype=torch.int64, device=dev)
+      sv['timing'] = torch.zeros((2, T, 16), dtype=torch.int64, device=dev)
     for k, v in {**w, **vec, **sv}.items():
-      if k == 'x2_f32':
+      if k in ('x2_f32', 'w_hid_x2'):
         continue
       assert v.is_contiguous(), k
       setattr(args, k, v.data_ptr())

@@ -86,6 +86,14 @@ int emb_event_record(void* ev, void* stream);
 int emb_event_elapsed_ms(void* a, void* b, float* ms);
 int emb_event_destroy(void* ev);
 
+/* Diagnostic: stream `bytes` of `src` out of HBM with a persistent grid of `ncta`
+ * CTAs (contiguous slice per CTA).  mode 0: the scan kernels' weight path -- TMA
+ * bulk copies into an `nstages` x `stage_bytes` shared-memory ring; mode 1: plain
+ * 16-byte loads.  Timed by the caller (tools/probe_read.py) to place the read-only
+ * roofline of the scan next to the measured copy peak. */
+int emb_probe_read(const void* src, uint64_t bytes, int32_t ncta, int32_t mode,
+                   int32_t nstages, int32_t stage_bytes, void* sink, void* stream);
+
 /* The row engine.  For r in [0, nrows):
  *     srow(r) = src_rows ? src_rows[r] : r        drow(r) = dst_rows ? dst_rows[r] : r
  *   rows with srow(r) < 0 or drow(r) < 0 are skipped (evicted chunk,
@@ -138,9 +146,10 @@ int emb_driver_scatter_mask_actions(const emb_key_t* keys, int nkeys,
  * emb_rssm_pack), engine 0 = fp32 FFMA (parity). */
 typedef struct emb_rssm_fwd_args {
   int32_t B, T, D, H, S, C, G;   /* batch rows (<=16), steps, deter, hidden, stoch, classes, blocks */
-  int32_t engine;                /* 0 fp32, 1 bf16 */
+  int32_t engine;                /* 0 fp32 FFMA (parity), 1 bf16 mma + TMA weight ring,
+                                  * 2 bf16 mma with register-staged weight loads (first version) */
   int32_t ncta;                  /* grid size the weights were packed for (<= SM count) */
-  int32_t pad_;
+  int32_t tma_cfg;               /* set by the library (ring stages | tiles << 8) */
   float unimix, eps;             /* 0.01, 1e-4 (embodied/jax/outs.py:210-216, nets.py:364) */
   /* packed weights.  bf16: per CTA a contiguous block [K/16][per][32 lanes][2 u32] of mma B
    * fragments, per = ceil((N/8) / ncta) n8 tiles, CTA c owning tiles [c*per, (c+1)*per);
@@ -175,9 +184,14 @@ typedef struct emb_rssm_fwd_args {
   float* probs;          /* [T][16][S*C] softmax(logit) before unimix; rows < B written */
   float* rstd;           /* [T+1][3][16] rsqrt(mean(y^2)+eps) of y0[t], y1[t], yobs[t] */
   /* scratch */
-  void* deterA;          /* bf16 engine scratch: (2*16*D + 16*H) bf16, A-fragment order */
+  void* deterA;          /* bf16 engines scratch: (2*16*D + 2*16*H) bf16, A-fragment order */
   uint32_t* barrier;     /* one ZEROED u32 */
   uint64_t* timing;      /* optional [T][16] globaltimer marks of CTA 0 (NULL = off) */
+  /* engine 1 only: the action branch is hoisted out of the scan entirely.  w_hid then
+   * holds rows [deter_g | x0 | x1] of dynhid0 ([G][D/G+2H][D/G]) and the caller passes
+   * hid_pre[T][16][D] = x2 @ dynhid0[g][D/G+2H:] + bias (one (B*T)-row GEMM); x2 is unused. */
+  const float* hid_pre;
+  float* sumsq_obs;      /* engine 1: [T][16] row sums of yobs^2; ZEROED by the caller */
 } emb_rssm_fwd_args;
 
 int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream);

@@ -83,8 +83,10 @@ def test_forward_fp32_engine_matches_oracle(name, over, B, T):
   assert rel(out['logit'], feat['logit']) < 1e-5
 
 
-@pytest.mark.parametrize('name,over,B,T', CASES[:2] + CASES[3:])
-def test_forward_bf16_engine_tracks_oracle(name, over, B, T):
+@pytest.mark.parametrize('engine', ['ENG_BF16', 'ENG_LEGACY'])
+@pytest.mark.parametrize('name,over,B,T', CASES[:2] + CASES[3:] + [
+    ('wide', dict(deter=2048, hidden=256, stoch=16, classes=32, blocks=8), 16, 6)])
+def test_forward_bf16_engine_tracks_oracle(name, over, B, T, engine):
   ocfg = do.tiny_config(**over)
   vals, oracle, tokens, action, reset, deter0, stoch0, gumbel = setup(ocfg, B, T, 1)
   # the oracle with bf16-rounded in-scan weights isolates the kernel's own error
@@ -100,7 +102,7 @@ def test_forward_bf16_engine_tracks_oracle(name, over, B, T):
   with torch.no_grad():
     _, feat = oracle_r.observe(dict(deter=deter0, stoch=stoch0), tokens, action, reset, gumbel)
     hs = hoisted(oracle, ocfg, tokens, action, reset, deter0, stoch0)
-  out, saved, _ = run_kernel(ocfg, vals, scanlib.ENG_BF16, B, T, *hs, deter0, gumbel)
+  out, saved, _ = run_kernel(ocfg, vals, getattr(scanlib, engine), B, T, *hs, deter0, gumbel)
   agree = (out['index'].cpu().long() == feat['stoch'].argmax(-1)).float().mean()
   assert agree > 0.9, (name, float(agree))
   # until the first sampled latent differs the trajectories coincide to bf16 accuracy

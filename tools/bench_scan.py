@@ -20,7 +20,8 @@ except Exception:
 
 def main():
   size = sys.argv[1] if len(sys.argv) > 1 else 'size200m'
-  engine = S.ENG_BF16 if (len(sys.argv) <= 2 or sys.argv[2] == 'bf16') else S.ENG_F32
+  ename = sys.argv[2] if len(sys.argv) > 2 else 'bf16'
+  engine = {'bf16': S.ENG_BF16, 'legacy': S.ENG_LEGACY, 'f32': S.ENG_F32}[ename]
   B, T = 16, 64
   cfg = C.make(size)
   store = P.ParamStore(cfg, 'cuda', torch.float32, 0)
@@ -30,8 +31,9 @@ def main():
   r = lambda *s: torch.randn(s, generator=g, device='cuda')
   args = (r(B, D) * 0.3, r(B, H), r(B, H), r(B, T, H), r(B, T, H),
           torch.ones(B, T, device='cuda'), r(B, T, Sx, Cx))
-  nw = D * 2 * H + H * Sx * Cx + D * (D // G + 3 * H) + D * 3 * (D // G)
-  wbytes = nw * (2 if engine == S.ENG_BF16 else 4)
+  # in-scan weights streamed per step (the TMA engine hoists the action rows of dynhid0)
+  nw = D * 2 * H + H * Sx * Cx + D * (D // G + (2 if engine == S.ENG_BF16 else 3) * H) + D * 3 * (D // G)
+  wbytes = nw * (4 if engine == S.ENG_F32 else 2)
   sc.timing = True
   flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
   for _ in range(3):
@@ -52,16 +54,23 @@ def main():
     torch.cuda.synchronize()
     times.append(a.elapsed_time(b) * 1e-3)
   t = float(np.median(times))
-  tm = sv['timing'].cpu().numpy().astype(np.int64)
-  d = np.diff(tm[:, :12], axis=1)[8:].mean(0) / 1e3
+  tm = sv['timing'].cpu().numpy().astype(np.int64).reshape(-1, T, 16)
   names = ['P4 prologue', 'P4 gemm', 'bar', 'P5', 'bar', 'P1', 'bar', 'P2', 'bar', 'P3', 'bar']
-  print('phase us (CTA 0, mean over steps 8..):', {n + str(i): round(float(x), 2) for i, (n, x) in enumerate(zip(names, d))})
+  for which, tmx in enumerate(tm):
+    d = np.diff(tmx[:, :12], axis=1)[8:].mean(0) / 1e3
+    print(f'phase us (CTA set {which}, mean over steps 8..):',
+          {n + str(i): round(float(x), 2) for i, (n, x) in enumerate(zip(names, d))})
+    if tmx[:, 12:].any():
+      x = tmx[8:]
+      sub = {'P5 A-build': x[:, 12] - x[:, 3], 'P5 gemm': x[:, 13] - x[:, 12], 'P5 epilogue': x[:, 4] - x[:, 13],
+             'P2 A-build': x[:, 14] - x[:, 7], 'P2 gemm': x[:, 15] - x[:, 14], 'P2 rest': x[:, 8] - x[:, 15]}
+      print('   ', {k: round(float(v.mean()) / 1e3, 2) for k, v in sub.items()})
   print(json.dumps({
-      'kernel': 'rssm_fwd_kernel', 'size': size, 'engine': 'bf16' if engine else 'f32',
+      'kernel': 'rssm_fwd_kernel', 'size': size, 'engine': ename,
       'B': B, 'T': T, 'ms': t * 1e3, 'us_per_step': t / T * 1e6,
       'weights_per_step_MB': wbytes / 1e6, 'algorithmic_bytes': wbytes * T,
       'GBs': wbytes * T / t / 1e9, 'frac_of_measured_peak': wbytes * T / t / 1e9 / PEAK}))
-  bench_bwd(sc, args, B, T, cfg, wbytes, size, engine)
+  bench_bwd(sc, args, B, T, cfg, wbytes, size, ename)
 
 
 def bench_bwd(sc, args, B, T, cfg, wbytes, size, engine):
@@ -79,7 +88,7 @@ def bench_bwd(sc, args, B, T, cfg, wbytes, size, engine):
   times = [a.elapsed_time(b) * 1e-3 for a, b in sc.bwd_events[3:]]
   t = float(np.median(times))
   print(json.dumps({
-      'kernel': 'rssm_bwd_kernel', 'size': size, 'engine': 'bf16' if engine else 'f32',
+      'kernel': 'rssm_bwd_kernel', 'size': size, 'engine': engine,
       'B': B, 'T': T, 'ms': t * 1e3, 'us_per_step': t / T * 1e6,
       'algorithmic_bytes': wbytes * T, 'GBs': wbytes * T / t / 1e9,
       'frac_of_measured_peak': wbytes * T / t / 1e9 / PEAK}))
