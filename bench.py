@@ -46,7 +46,7 @@ CLASSES = 5
 ROW_BYTES = 12288 + 32768 + 8192 + 20 + 4 + 4 + 3      # image, deter, stoch, stepid, reward, action, 3 flags
 TRAINS_PER_STEP = TRAIN_RATIO * NENVS // (B * T)        # 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/)
-NCU_TRAFFIC = {'rssm_fwd': 9898184000 + 181489920}
+NCU_TRAFFIC = {'rssm_fwd': 8951381000 + 319277312, 'rssm_bwd': 10436836000 + 142067712}
 
 
 def peaks():
@@ -296,14 +296,17 @@ def run_b200(args):
   if args.agent != 'feed':
     cfg = loop.agent.cfg
     Dg = cfg.deter // cfg.blocks
-    nw = (cfg.deter * 2 * cfg.hidden + cfg.hidden * cfg.stoch * cfg.classes +
-          cfg.deter * (Dg + 3 * cfg.hidden) + cfg.deter * 3 * Dg)
-    wbytes = nw * (2 if args.dtype == 'bfloat16' else 4) * T    # every in-scan weight once per step
+    # every in-scan weight once per step; the forward bf16 kernel hoists the action
+    # rows of dynhid0 out of the scan (Dg + 2H input rows instead of Dg + 3H)
+    fixed = cfg.deter * 2 * cfg.hidden + cfg.hidden * cfg.stoch * cfg.classes + cfg.deter * 3 * Dg
+    esz = 2 if args.dtype == 'bfloat16' else 4
+    wbytes = (fixed + cfg.deter * (Dg + 3 * cfg.hidden)) * esz * T
+    wbytes_fwd = (fixed + cfg.deter * (Dg + (2 if args.dtype == 'bfloat16' else 3) * cfg.hidden)) * esz * T
     # DRAM traffic per launch from ncu (profiles/r01_rssm_*_kernel.md), bf16 size200m only
     known = args.dtype == 'bfloat16' and args.size == 'size200m'
     kernels.append(kernel_line('rssm_bwd', 'rssm_bwd_kernel (emb_rssm_observe_bwd, B=16 T=64)', wbytes,
                                NCU_TRAFFIC.get('rssm_bwd') if known else None))
-    kernels.append(kernel_line('rssm_fwd', 'rssm_fwd_kernel (emb_rssm_observe_fwd, B=16 T=64)', wbytes,
+    kernels.append(kernel_line('rssm_fwd', 'rssm_fwd_kernel (emb_rssm_observe_fwd, TMA weight ring, B=16 T=64)', wbytes_fwd,
                                NCU_TRAFFIC.get('rssm_fwd') if known else None))
   kernels = [k for k in kernels if k]
   # the roofline line is the hand-written kernel with the largest share of the step

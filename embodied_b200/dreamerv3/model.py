@@ -370,9 +370,9 @@ class Model:
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
       return x
-    parts = torch.empty((dist.get_world_size(), x.numel()), dtype=x.dtype, device=x.device)
+    parts = torch.empty(dist.get_world_size() * x.numel(), dtype=x.dtype, device=x.device)
     dist.all_gather_into_tensor(parts, x.contiguous())
-    return parts.flatten()
+    return parts
 
   # ----------------------------------------------------------------- imagination
   @torch.no_grad()
