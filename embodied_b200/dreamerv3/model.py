@@ -118,6 +118,29 @@ class Model:
     y = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=w.shape[-1] // 2)
     return y.permute(0, 2, 3, 1)                             # NHWC view (channels_last memory)
 
+  def conv_thin_in(self, x, name):
+    """SAME conv with <= 4 input channels (the image): rows of patches times the
+    (k*k*Cin, Cout) kernel -- one skinny tensor-core GEMM over all pixels instead
+    of a library convolution (ops.ConvPatches).  No bias (see conv())."""
+    w = self.W(f'{name}/kernel')                             # HWIO
+    k, _, cin, cout = w.shape
+    n, h, ww, _ = x.shape
+    kp = ops.patch_columns(k, cin)
+    w2 = F.pad(w.reshape(k * k * cin, cout), (0, 0, 0, kp - k * k * cin))
+    return (ops.ConvPatches.apply(x, k) @ w2).reshape(n, h, ww, cout)
+
+  def conv_thin_out(self, x, name, up=1):
+    """SAME conv with <= 4 output channels (the decoder's image head), optionally
+    preceded by a nearest x2 up-sampling: z = x @ W[Cin, k*k*Cout] on the input
+    grid, then the tap sum (+ bias) gathers the k*k shifted columns."""
+    w = self.W(f'{name}/kernel')                             # HWIO
+    k, _, cin, cout = w.shape
+    n, h, ww, _ = x.shape
+    kp = ops.patch_columns(k, cout)
+    w2 = F.pad(w.permute(2, 0, 1, 3).reshape(cin, k * k * cout), (0, kp - k * k * cout))
+    z = x.reshape(n * h * ww, cin) @ w2
+    return ops.ConvTapSum.apply(z, self.store.w[f'{name}/bias'], (n, h * up, ww * up, cout), k, up)
+
   def mlp(self, x, name, layers, params=None):               # nets.py:580-587
     for i in range(layers):
       x = self.dense(x, f'{name}/mlp/linear{i}')
@@ -136,7 +159,10 @@ class Model:
     lead = x.shape[:-3]
     x = x.reshape(-1, *x.shape[-3:]).to(self.cd)
     for i in range(len(cfg.mults)):
-      x = self.conv(x, f'enc/cnn{i}', bias=False)
+      if self.fused_spatial and ops.thin_conv_supported(x, x.shape[-1], cfg.depth * cfg.mults[i]):
+        x = self.conv_thin_in(x, f'enc/cnn{i}')
+      else:
+        x = self.conv(x, f'enc/cnn{i}', bias=False)
       x = self.pool(x)
       x = self.norm(x, f'enc/cnn{i}norm', bias=self.store.w[f'enc/cnn{i}/bias'])
     return x.reshape(*lead, -1)
@@ -280,7 +306,11 @@ class Model:
       x = self.upsample(x)
       x = self.norm(self.conv(x, f'dec/conv{i}', bias=False), f'dec/conv{i}norm',
                     bias=self.store.w[f'dec/conv{i}/bias'])
-    x = torch.sigmoid(self.conv(self.upsample(x), 'dec/imgout').to(f32))
+    if self.fused_spatial and ops.thin_conv_supported(x, x.shape[-1], cfg.image[2]):
+      x = self.conv_thin_out(x, 'dec/imgout', up=2)          # up-sampling folded in
+    else:
+      x = self.conv(self.upsample(x), 'dec/imgout')
+    x = torch.sigmoid(x.to(f32))
     return x.reshape(*lead, *x.shape[1:])
 
   def upsample(self, x):                                     # x.repeat(2,-2).repeat(2,-3), NHWC

@@ -31,6 +31,10 @@ def _lib_bound():
     for name in ('emb_upsample2_nhwc_fwd', 'emb_upsample2_nhwc_bwd'):
       getattr(lib, name).argtypes = [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp]
       getattr(lib, name).restype = ctypes.c_int
+    lib.emb_conv_patches_nhwc.argtypes = [_vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
+    lib.emb_conv_patches_nhwc.restype = ctypes.c_int
+    lib.emb_conv_tapsum_nhwc.argtypes = [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
+    lib.emb_conv_tapsum_nhwc.restype = ctypes.c_int
     _bound = True
   return lib
 
@@ -227,3 +231,68 @@ class Upsample2(torch.autograd.Function):
     _lib.check(lib.emb_upsample2_nhwc_bwd(
         gy.data_ptr(), gx.data_ptr(), n, h, w, c, _dtype_code(gy), stream))
     return gx
+
+
+# ------------------------------------------------------------ thin convolutions
+def patch_columns(k, c):
+  """Row width of the patch / tap matrices: k*k*c rounded up to 8."""
+  return (k * k * c + 7) // 8 * 8
+
+
+def _patches(x, shape, k, kp, sign, up):
+  """x NHWC on the (h*up, w*up) grid -> (n*h*w, kp); see emb_conv_patches_nhwc."""
+  lib = _lib_bound()
+  n, h, w, c = shape
+  x = x.contiguous()
+  out = torch.empty((n * h * w, kp), dtype=x.dtype, device=x.device)
+  stream = torch.cuda.current_stream(x.device).cuda_stream
+  _lib.check(lib.emb_conv_patches_nhwc(
+      x.data_ptr(), out.data_ptr(), n, h, w, c, k, kp, sign, up, _dtype_code(x), stream))
+  return out
+
+
+class ConvPatches(torch.autograd.Function):
+  """(N, H, W, C) image -> (N*H*W, kp) rows of its k x k SAME patches (zero
+  padded).  The input is a constant of the graph (the observation)."""
+
+  @staticmethod
+  def forward(ctx, x, k):
+    n, h, w, c = x.shape
+    return _patches(x, (n, h, w, c), k, patch_columns(k, c), 1, 1)
+
+  @staticmethod
+  def backward(ctx, g):
+    return None, None
+
+
+class ConvTapSum(torch.autograd.Function):
+  """y[p, ch] = bias[ch] + sum over the k x k taps of z[p + offset, tap*C + ch]:
+  the second half of a SAME convolution with few output channels computed as
+  z = x @ W[Cin, k*k*C].  up = 2: z lives on the half-resolution grid (nearest
+  up-sampling folded in)."""
+
+  @staticmethod
+  def forward(ctx, z, bias, shape, k, up):
+    lib = _lib_bound()
+    n, h, w, c = shape
+    z = z.contiguous()
+    y = torch.empty(shape, dtype=z.dtype, device=z.device)
+    stream = torch.cuda.current_stream(z.device).cuda_stream
+    _lib.check(lib.emb_conv_tapsum_nhwc(
+        z.data_ptr(), None if bias is None else bias.data_ptr(), y.data_ptr(), n, h, w, c, k,
+        z.shape[-1], up, _dtype_code(z), stream))
+    ctx.cfg = (shape, k, up, z.shape[-1], bias is not None)
+    return y
+
+  @staticmethod
+  def backward(ctx, gy):
+    (n, h, w, c), k, up, kp, has_bias = ctx.cfg
+    gz = _patches(gy, (n, h // up, w // up, c), k, kp, -1, up)
+    gb = gy.reshape(-1, c).sum(0, dtype=f32) if has_bias else None
+    return gz, gb, None, None, None
+
+
+def thin_conv_supported(x, cin, cout):
+  if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 4:
+    return False
+  return min(cin, cout) <= 4

@@ -306,6 +306,25 @@ int emb_upsample2_nhwc_fwd(const void* x, void* y, int64_t n, int32_t h, int32_t
 int emb_upsample2_nhwc_bwd(const void* gy, void* gx, int64_t n, int32_t h, int32_t w, int32_t c,
                            int32_t dtype, void* stream);
 
+/* The two thin 5x5 convolutions of dreamerv3 (3 image channels in: encoder layer 0,
+ * dreamerv3/rssm.py:233-238; 3 channels out: decoder image head, rssm.py:349-352;
+ * embodied/jax/nets.py:298-323 Conv2D SAME) as a skinny GEMM over all pixels plus one
+ * HBM-bound rearrangement (embodied_b200/csrc/thinconv.cu).  NHWC, k odd, rows of
+ * `out` / `z` have `kp` columns (multiple of 8, >= k*k*c); dtype 0 = fp32 / 1 = bf16.
+ *   patches: out[p][(dy*k+dx)*c + ch] = x[p + sign*(dy-k/2, dx-k/2)][ch], zero outside
+ *            the image and in the padding columns (sign = +1 forward, -1 = the
+ *            backward of tapsum);
+ *   tapsum:  y[p][ch] = bias[ch] + sum_{dy,dx} z[p + (dy-k/2, dx-k/2)][(dy*k+dx)*c + ch].
+ * (n, h, w) always describe the OUTPUT grid.  up = 2 folds a nearest x2 up-sampling in
+ * front of the convolution into the rearrangement: tapsum reads z on the (h/2, w/2)
+ * grid at (p + offset) / 2; patches (sign = -1, its backward) reads x on the (2h, 2w)
+ * grid and sums the 2x2 block of every output pixel. */
+int emb_conv_patches_nhwc(const void* x, void* out, int64_t n, int32_t h, int32_t w, int32_t c,
+                          int32_t k, int32_t kp, int32_t sign, int32_t up, int32_t dtype,
+                          void* stream);
+int emb_conv_tapsum_nhwc(const void* z, const float* bias, void* y, int64_t n, int32_t h, int32_t w,
+                         int32_t c, int32_t k, int32_t kp, int32_t up, int32_t dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,3 +51,57 @@ def test_upsample(shape, dtype):
 def test_odd_channels_not_supported():
   assert not ops.spatial_supported(torch.zeros(1, 4, 4, 12, device='cuda', dtype=torch.bfloat16))
   assert ops.spatial_supported(torch.zeros(1, 4, 4, 12, device='cuda'))
+
+
+# ------------------------------------------------------------ thin convolutions
+def _conv_ref(x, w, b=None):
+  """NHWC x, HWIO w, SAME -- the reference's Conv2D (embodied/jax/nets.py:298-323)."""
+  torch.backends.cudnn.allow_tf32 = False
+  y = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(3, 2, 0, 1), b, padding=w.shape[0] // 2)
+  return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout,k', [(2, 8, 8, 3, 16, 5), (3, 6, 10, 1, 8, 3), (1, 64, 64, 3, 128, 5)])
+def test_thin_input_conv_matches_conv2d(n, h, w, cin, cout, k):
+  g = torch.Generator(device='cuda').manual_seed(n * h + cout)
+  x = torch.randn(n, h, w, cin, generator=g, device='cuda')
+  wt = (torch.randn(k, k, cin, cout, generator=g, device='cuda') * 0.2).requires_grad_(True)
+  kp = ops.patch_columns(k, cin)
+  w2 = torch.nn.functional.pad(wt.reshape(k * k * cin, cout), (0, 0, 0, kp - k * k * cin))
+  y = (ops.ConvPatches.apply(x, k) @ w2).reshape(n, h, w, cout)
+  wr = wt.detach().clone().requires_grad_(True)
+  yr = _conv_ref(x, wr)
+  assert float((y - yr).abs().max()) < 1e-4 * float(yr.abs().max())
+  gy = torch.randn_like(y)
+  y.backward(gy)
+  yr.backward(gy)
+  assert float((wt.grad - wr.grad).abs().max()) < 1e-4 * float(wr.grad.abs().max())
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize('n,h,w,cin,cout,k,up', [(2, 8, 8, 16, 3, 5, 1), (2, 4, 6, 8, 3, 5, 2),
+                                                   (1, 32, 32, 128, 3, 5, 2), (3, 6, 6, 8, 1, 3, 2)])
+def test_thin_output_conv_matches_conv2d(n, h, w, cin, cout, k, up, dtype):
+  """x (n, h, w, cin) -> [nearest x`up`] -> SAME conv to cout channels + bias,
+  values and all three gradients against upsample + conv2d in fp32."""
+  g = torch.Generator(device='cuda').manual_seed(h * w + cin)
+  x = torch.randn(n, h, w, cin, generator=g, device='cuda').to(dtype)
+  wt = (torch.randn(k, k, cin, cout, generator=g, device='cuda') * 0.2).to(dtype)
+  b = torch.randn(cout, generator=g, device='cuda')
+  x1, w1, b1 = (t.clone().requires_grad_(True) for t in (x, wt, b))
+  kp = ops.patch_columns(k, cout)
+  w2 = torch.nn.functional.pad(w1.permute(2, 0, 1, 3).reshape(cin, k * k * cout), (0, kp - k * k * cout))
+  z = x1.reshape(n * h * w, cin) @ w2
+  y = ops.ConvTapSum.apply(z, b1, (n, h * up, w * up, cout), k, up)
+  # float64 reference: cuDNN's fp32 wgrad for 3 output channels is only ~4e-3 accurate
+  x2, w3, b2 = (t.double().clone().requires_grad_(True) for t in (x, wt, b))
+  xu = x2.repeat_interleave(up, 1).repeat_interleave(up, 2) if up > 1 else x2
+  yr = _conv_ref(xu, w3, b2)
+  tol = 1e-4 if dtype == torch.float32 else 3e-2
+  assert float((y.double() - yr).abs().max()) < tol * float(yr.abs().max())
+  gy = torch.randn(*yr.shape, generator=g, device='cuda')
+  y.backward(gy.to(dtype))
+  yr.backward(gy.double())
+  for name, a, r in (('x', x1.grad, x2.grad), ('w', w1.grad, w3.grad), ('b', b1.grad, b2.grad)):
+    err = float((a.double() - r).abs().max()) / float(r.abs().max())
+    assert err < tol, (name, err)
