@@ -32,68 +32,81 @@ namespace {
 constexpr int kThreads = 256;
 
 // one thread = one 16-byte vector of the output row (VEC elements)
-// (H, W) = the OUTPUT grid; x lives on the (H*up, W*up) grid.
-template <typename T, int VEC>
+// (H, W) = the OUTPUT grid; x lives on the (H*up, W*up) grid.  One thread = one
+// 16-byte vector of the output row; 32-bit index arithmetic, K a compile-time
+// constant (divisions by K become multiplies), (tap, channel) advanced incrementally.
+template <typename T, int VEC, int K>
 __global__ void __launch_bounds__(kThreads)
-patches_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t nvec, int H, int W, int C,
-               int K, int KP, int sign, int up) {
-  const int vpr = KP / VEC, taps = K * K, half = K / 2;
+patches_kernel(const T* __restrict__ x, T* __restrict__ out, uint32_t nvec, int H, int W, int C,
+               int KP, int sign, int up) {
+  const uint32_t vpr = KP / VEC;
+  constexpr int taps = K * K, half = K / 2;
   const int HX = H * up, WX = W * up;
-  for (int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x; o < nvec;
-       o += (int64_t)gridDim.x * kThreads) {
-    const int64_t p = o / vpr;
-    const int v = (int)(o - p * vpr);
-    const int xx = (int)(p % W), yy = (int)((p / W) % H);
-    const int64_t img = p / ((int64_t)W * H);
+  for (uint32_t o = blockIdx.x * kThreads + threadIdx.x; o < nvec; o += gridDim.x * kThreads) {
+    const uint32_t p = o / vpr, v = o - p * vpr;
+    const uint32_t row = p / W;
+    const int xx = (int)(p - row * W), yy = (int)(row % H);
+    const uint32_t img = row / H;
+    const T* xi = x + (size_t)img * HX * WX * C;
+    int tap = (int)(v * VEC) / C, c = (int)(v * VEC) - tap * C;
     T vals[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      const int e = v * VEC + i;
-      const int tap = e / C, c = e - tap * C;
       float val = 0.f;
       if (tap < taps) {
         const int dy = tap / K - half, dx = tap % K - half;
-        for (int uy = 0; uy < up; ++uy) {
-          const int sy = yy * up + uy + sign * dy;
-          if (sy < 0 || sy >= HX) continue;
-          for (int ux = 0; ux < up; ++ux) {
-            const int sx = xx * up + ux + sign * dx;
-            if (sx >= 0 && sx < WX) val += (float)x[((img * HX + sy) * WX + sx) * C + c];
+        if (up == 1) {
+          const int sy = yy + sign * dy, sx = xx + sign * dx;
+          if (sy >= 0 && sy < HX && sx >= 0 && sx < WX) val = (float)xi[(sy * WX + sx) * C + c];
+        } else {
+          for (int uy = 0; uy < 2; ++uy) {
+            const int sy = yy * 2 + uy + sign * dy;
+            if (sy < 0 || sy >= HX) continue;
+            for (int ux = 0; ux < 2; ++ux) {
+              const int sx = xx * 2 + ux + sign * dx;
+              if (sx >= 0 && sx < WX) val += (float)xi[(sy * WX + sx) * C + c];
+            }
           }
         }
       }
       vals[i] = T(val);
+      if (++c == C) { c = 0; ++tap; }
     }
-    *reinterpret_cast<uint4*>(out + p * KP + (int64_t)v * VEC) = *reinterpret_cast<const uint4*>(vals);
+    *reinterpret_cast<uint4*>(out + (size_t)p * KP + v * VEC) = *reinterpret_cast<const uint4*>(vals);
   }
 }
 
-// one thread = one output element (pixel, channel); fp32 accumulation
-// (H, W) = the OUTPUT grid; z lives on the (H/up, W/up) grid.
-template <typename T>
+// (H, W) = the OUTPUT grid; z lives on the (H/up, W/up) grid.  One thread = one
+// output pixel, all C <= 4 channels (fp32 accumulation).
+template <typename T, int K>
 __global__ void __launch_bounds__(kThreads)
 tapsum_kernel(const T* __restrict__ z, const float* __restrict__ bias, T* __restrict__ y,
-              int64_t total, int H, int W, int C, int K, int KP, int up) {
-  const int half = K / 2;
+              uint32_t pixels, int H, int W, int C, int KP, int up) {
+  constexpr int half = K / 2;
   const int HZ = H / up, WZ = W / up;
-  for (int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x; o < total;
-       o += (int64_t)gridDim.x * kThreads) {
-    const int64_t p = o / C;
-    const int c = (int)(o - p * C);
-    const int xx = (int)(p % W), yy = (int)((p / W) % H);
-    const int64_t img = p / ((int64_t)W * H);
-    float acc = bias ? bias[c] : 0.f;
+  for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < pixels; p += gridDim.x * kThreads) {
+    const uint32_t row = p / W;
+    const int xx = (int)(p - row * W), yy = (int)(row % H);
+    const uint32_t img = row / H;
+    const T* zi = z + (size_t)img * HZ * WZ * KP;
+    float acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = (bias && c < C) ? bias[c] : 0.f;
+#pragma unroll
     for (int dy = 0; dy < K; ++dy) {
       const int sy = yy + dy - half;
       if (sy < 0 || sy >= H) continue;
+#pragma unroll
       for (int dx = 0; dx < K; ++dx) {
         const int sx = xx + dx - half;
         if (sx < 0 || sx >= W) continue;
-        const int64_t q = (img * HZ + sy / up) * WZ + sx / up;
-        acc += (float)z[q * KP + (dy * K + dx) * C + c];
+        const T* q = zi + (size_t)((sy / up) * WZ + sx / up) * KP + (dy * K + dx) * C;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < C) acc[c] += (float)q[c];
       }
     }
-    y[o] = T(acc);
+    for (int c = 0; c < C; ++c) y[(size_t)p * C + c] = T(acc[c]);
   }
 }
 
@@ -103,6 +116,10 @@ int prepare(const char* who, int64_t n, int h, int w, int c, int k, int kp, int 
   if (n < 0 || h < 1 || w < 1 || c < 1 || k < 1 || !(k & 1))
     return emb::fail(-1, "%s: n=%lld h=%d w=%d c=%d k=%d", who, (long long)n, h, w, c, k);
   if (dtype != 0 && dtype != 1) return emb::fail(-1, "%s: dtype %d (0 = f32, 1 = bf16)", who, dtype);
+  if (k != 3 && k != 5) return emb::fail(-1, "%s: k=%d (3 or 5)", who, k);
+  if (n * (int64_t)h * w * kp >= ((int64_t)1 << 31))
+    return emb::fail(-1, "%s: %lld x %d patch elements exceed the 32-bit index range", who,
+                     (long long)(n * h * w), kp);
   if (kp % 8 || kp < k * k * c)
     return emb::fail(-1, "%s: kp=%d must be a multiple of 8 and >= k*k*c=%d", who, kp, k * k * c);
   if (g_sms == 0) {
@@ -134,12 +151,14 @@ extern "C" int emb_conv_patches_nhwc(const void* x, void* out, int64_t n, int32_
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype) {
     const int64_t nvec = pixels * (kp / 8);
-    patches_kernel<__nv_bfloat16, 8><<<grid_for(nvec), kThreads, 0, s>>>(
-        (const __nv_bfloat16*)x, (__nv_bfloat16*)out, nvec, h, w, c, k, kp, sign, up);
+    auto fn = k == 5 ? patches_kernel<__nv_bfloat16, 8, 5> : patches_kernel<__nv_bfloat16, 8, 3>;
+    fn<<<grid_for(nvec), kThreads, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, (uint32_t)nvec,
+                                           h, w, c, kp, sign, up);
   } else {
     const int64_t nvec = pixels * (kp / 4);
-    patches_kernel<float, 4><<<grid_for(nvec), kThreads, 0, s>>>(
-        (const float*)x, (float*)out, nvec, h, w, c, k, kp, sign, up);
+    auto fn = k == 5 ? patches_kernel<float, 4, 5> : patches_kernel<float, 4, 3>;
+    fn<<<grid_for(nvec), kThreads, 0, s>>>((const float*)x, (float*)out, (uint32_t)nvec, h, w, c, kp,
+                                           sign, up);
   }
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
@@ -152,15 +171,19 @@ extern "C" int emb_conv_tapsum_nhwc(const void* z, const float* bias, void* y, i
   const char* who = "emb_conv_tapsum_nhwc";
   if (int e = prepare(who, n, h, w, c, k, kp, dtype)) return e;
   if ((up != 1 && up != 2) || h % up || w % up) return emb::fail(-1, "%s: up=%d h=%d w=%d", who, up, h, w);
-  const int64_t total = n * h * w * c;
+  if (c > 4) return emb::fail(-1, "%s: c=%d > 4 output channels", who, c);
+  const int64_t total = n * h * w;
   if (total == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype)
-    tapsum_kernel<__nv_bfloat16><<<grid_for(total), kThreads, 0, s>>>(
-        (const __nv_bfloat16*)z, bias, (__nv_bfloat16*)y, total, h, w, c, k, kp, up);
-  else
-    tapsum_kernel<float><<<grid_for(total), kThreads, 0, s>>>(
-        (const float*)z, bias, (float*)y, total, h, w, c, k, kp, up);
+  if (dtype) {
+    auto fn = k == 5 ? tapsum_kernel<__nv_bfloat16, 5> : tapsum_kernel<__nv_bfloat16, 3>;
+    fn<<<grid_for(total), kThreads, 0, s>>>((const __nv_bfloat16*)z, bias, (__nv_bfloat16*)y,
+                                            (uint32_t)total, h, w, c, kp, up);
+  } else {
+    auto fn = k == 5 ? tapsum_kernel<float, 5> : tapsum_kernel<float, 3>;
+    fn<<<grid_for(total), kThreads, 0, s>>>((const float*)z, bias, (float*)y, (uint32_t)total, h, w, c,
+                                            kp, up);
+  }
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;

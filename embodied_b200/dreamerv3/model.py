@@ -188,6 +188,13 @@ class Model:
     Dg = deter.shape[-1] // g
     y = torch.bmm(deter.reshape(M, g, Dg).transpose(0, 1), w[:, :Dg])
     y = torch.baddbmm(y, x012[None].expand(g, -1, -1), w[:, Dg:])
+    if self.fused_norm and ops.core_fused_supported(deter, g):
+      # no-gradient path (imagination, policy): stay in the (group, row, column) layout of
+      # the batched GEMMs; bias + norm + silu and the GRU gate chain are one kernel each
+      sw = self.store.w
+      x = ops.rmsnorm_grouped(y, sw['dyn/dynhid0norm/scale'], sw['dyn/dynhid0/bias'])
+      pre = torch.bmm(x, self.W('dyn/dyngru/kernel'))
+      return ops.gru_gates(pre, sw['dyn/dyngru/bias'], deter)
     x = y.transpose(0, 1).reshape(M, -1) + b
     x = self.norm(x, 'dyn/dynhid0norm')
     x = self.block(x, 'dyn/dyngru')

@@ -35,6 +35,10 @@ def _lib_bound():
     lib.emb_conv_patches_nhwc.restype = ctypes.c_int
     lib.emb_conv_tapsum_nhwc.argtypes = [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
     lib.emb_conv_tapsum_nhwc.restype = ctypes.c_int
+    lib.emb_rmsnorm_grouped_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _fl, _vp]
+    lib.emb_rmsnorm_grouped_fwd.restype = ctypes.c_int
+    lib.emb_gru_gates_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]
+    lib.emb_gru_gates_fwd.restype = ctypes.c_int
     _bound = True
   return lib
 
@@ -296,3 +300,39 @@ def thin_conv_supported(x, cin, cout):
   if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16) or x.dim() != 4:
     return False
   return min(cin, cout) <= 4
+
+
+# ------------------------------------------- forward-only block-GRU fusions
+def core_fused_supported(deter, groups):
+  if torch.is_grad_enabled() or not deter.is_cuda or deter.dtype not in (torch.float32, torch.bfloat16):
+    return False
+  per = 4 if deter.dtype == torch.float32 else 8
+  D = deter.shape[-1]
+  return D % groups == 0 and (D // groups) % per == 0 and D // per <= 16 * 256
+
+
+@torch.no_grad()
+def rmsnorm_grouped(x, scale, bias, act=True, eps=1e-4):
+  """x (g, M, Dg) contiguous -> same layout, norm over the full row (g*Dg)."""
+  lib = _lib_bound()
+  g, M, Dg = x.shape
+  y = torch.empty_like(x)
+  stream = torch.cuda.current_stream(x.device).cuda_stream
+  _lib.check(lib.emb_rmsnorm_grouped_fwd(
+      x.data_ptr(), scale.data_ptr(), None if bias is None else bias.data_ptr(), y.data_ptr(),
+      M, g, Dg, _dtype_code(x), int(act), eps, stream))
+  return y
+
+
+@torch.no_grad()
+def gru_gates(pre, bias, deter):
+  """pre (g, M, 3*Dg) contiguous, bias fp32 (3*D,), deter (M, D) -> new deter (M, D)."""
+  lib = _lib_bound()
+  g, M, Dg3 = pre.shape
+  deter = deter.contiguous()
+  out = torch.empty_like(deter)
+  stream = torch.cuda.current_stream(pre.device).cuda_stream
+  _lib.check(lib.emb_gru_gates_fwd(
+      pre.data_ptr(), bias.data_ptr(), deter.data_ptr(), out.data_ptr(), M, g, Dg3 // 3,
+      _dtype_code(pre), stream))
+  return out

@@ -306,6 +306,20 @@ int emb_upsample2_nhwc_fwd(const void* x, void* y, int64_t n, int32_t h, int32_t
 int emb_upsample2_nhwc_bwd(const void* gy, void* gx, int64_t n, int32_t h, int32_t w, int32_t c,
                            int32_t dtype, void* stream);
 
+/* Forward-only fusions of the block-GRU core (dreamerv3/rssm.py:147-158) for the
+ * no-gradient batched paths (imagination, policy); embodied_b200/csrc/gru.cu.  x / y /
+ * pre are GROUPED [g][m][..] as the batched GEMMs produce them; scale / bias fp32 in
+ * the reference's flat layout; dtype 0 = fp32 / 1 = bf16.
+ *   rmsnorm_grouped: y[g][m][:] = act(rms_norm over the full row m of (x + bias) * scale)
+ *   gru_gates: out[m][g*dg + j] = u * tanh(r * c) + (1 - u) * deter[m][g*dg + j] with
+ *       (r, c, u) = pre[g][m][{0,1,2}*dg + j] + bias[g*3*dg + {0,1,2}*dg + j],
+ *       r = sigmoid(r), u = sigmoid(u - 1). */
+int emb_rmsnorm_grouped_fwd(const void* x, const float* scale, const float* bias, void* y,
+                            int64_t m, int32_t g, int32_t dg, int32_t dtype, int32_t act, float eps,
+                            void* stream);
+int emb_gru_gates_fwd(const void* pre, const float* bias, const void* deter, void* out, int64_t m,
+                      int32_t g, int32_t dg, int32_t dtype, void* stream);
+
 /* The two thin 5x5 convolutions of dreamerv3 (3 image channels in: encoder layer 0,
  * dreamerv3/rssm.py:233-238; 3 channels out: decoder image head, rssm.py:349-352;
  * embodied/jax/nets.py:298-323 Conv2D SAME) as a skinny GEMM over all pixels plus one

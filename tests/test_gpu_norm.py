@@ -83,3 +83,33 @@ def test_bias_folded_into_the_norm(shape, dtype):
   assert rel(s1.grad, s2.grad) < tol
   assert rel(b1.grad, b2.grad) < tol
   assert not ops.rmsnorm_supported(torch.randn(3, 512, device='cuda'), True, True)
+
+
+@pytest.mark.parametrize('g,M,Dg', [(8, 5, 64), (4, 33, 16), (8, 1024, 1024), (1, 3, 8)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_grouped_norm_and_gru_gates_forward(g, M, Dg, dtype):
+  """emb_rmsnorm_grouped_fwd / emb_gru_gates_fwd (the no-gradient block-GRU path)
+  against the reference's op-by-op formulation (dreamerv3/rssm.py:147-158)."""
+  gen = torch.Generator(device='cuda').manual_seed(g * M + Dg)
+  D = g * Dg
+  y = torch.randn(g, M, Dg, generator=gen, device='cuda').to(dtype)
+  scale = torch.rand(D, generator=gen, device='cuda') + 0.5
+  bias = torch.randn(D, generator=gen, device='cuda') * 0.3
+  with torch.no_grad():
+    got = ops.rmsnorm_grouped(y, scale, bias)
+    flat = (y.transpose(0, 1).reshape(M, D) + bias.to(dtype))
+    want = reference(flat, scale, True, dtype).reshape(M, g, Dg).transpose(0, 1)
+    tol = 1e-5 if dtype == torch.float32 else 2 ** -6
+    assert rel(got, want) < tol
+    pre = torch.randn(g, M, 3 * Dg, generator=gen, device='cuda').to(dtype)
+    b3 = torch.randn(3 * D, generator=gen, device='cuda') * 0.3
+    deter = torch.randn(M, D, generator=gen, device='cuda').to(dtype)
+    out = ops.gru_gates(pre, b3, deter)
+    x = pre.transpose(0, 1).reshape(M, -1) + b3.to(dtype)
+    r, c, u = [t.reshape(M, -1) for t in x.reshape(M, g, -1).chunk(3, -1)]
+    r = torch.sigmoid(r)
+    c = torch.tanh(r * c)
+    u = torch.sigmoid(u - 1)
+    ref = u * c + (1 - u) * deter
+    assert rel(out, ref) < (1e-5 if dtype == torch.float32 else 3e-2)
+  assert not ops.core_fused_supported(deter, g)      # grad mode: the differentiable path runs
