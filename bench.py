@@ -160,7 +160,8 @@ class Loop:
       env = make_env(0)
       self.agent = dreamerv3.Agent(
           env.obs_space, env.act_space,
-          dreamerv3.config.make(size, compute_dtype=dtype, seed=0))
+          dreamerv3.config.make(size, compute_dtype=dtype, seed=0,
+                                graph=os.environ.get('EMB_GRAPH', 'auto')))
     base = embodied.streams.Stateless(self.replay.sample, B, 'train')
     self.stream = iter(embodied.streams.Consec(
         base, length=T, consec=1, prefix=PREFIX, strict=True, contiguous=True))
@@ -346,7 +347,13 @@ def run_b200(args):
       line['cpu_baseline'] = cpu_baseline(args)
     print(json.dumps(line), flush=True)
   if world > 1:
-    dist.destroy_process_group()
+    # Captured CUDA graphs hold NCCL work: destroy_process_group() blocks on them.  All
+    # ranks have finished (barrier) and rank 0 has printed; leave without the teardown.
+    sys.stdout.flush()
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
 
 
 def workload_name(args):
@@ -510,6 +517,9 @@ def run_reference(args):
 
 
 def main():
+  if os.environ.get('EMB_BENCH_DEBUG'):       # hang diagnosis: dump all stacks periodically
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ['EMB_BENCH_DEBUG']), repeat=True, file=sys.stderr)
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=10)

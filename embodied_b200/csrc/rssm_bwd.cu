@@ -68,7 +68,7 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr bool BF = ENG == ENG_BF16;
   const int T = a.T, D = a.D, H = a.H, S = a.S, C = a.C, G = a.G;
-  const int Dg = D / G, SC = S * C, Kh = Dg + 3 * H;
+  const int Dg = D / G, SC = S * C, Kh = Dg + (a.hoist_x2 ? 2 : 3) * H;
   float* out = reinterpret_cast<float*>(smem_raw);                   // [16][kMaxTiles*8]
   float* st = out + kRows * kMaxTiles * 8;                           // 4 x [16] row statistics
   float *rstd_a = st, *coef_a = st + 16, *rstd_b = st + 32, *coef_b = st + 48;
@@ -394,7 +394,7 @@ rssm_bwd_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
 size_t bwd_smem_bytes(const emb_rssm_bwd_args& a) {
   const size_t n = sizeof(float) * (kRows * kMaxTiles * 8 + 64);
   const int Dg = a.D / a.G, SC = a.S * a.C;
-  if (a.engine != rssm::ENG_BF16) return n + (size_t)kRows * SC * sizeof(float);
+  if (a.engine == rssm::ENG_F32) return n + (size_t)kRows * SC * sizeof(float);
   int kmax = 3 * Dg;
   if (2 * a.H > kmax) kmax = 2 * a.H;
   if (SC > kmax) kmax = SC;
@@ -413,7 +413,7 @@ extern "C" int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream)
   if (a.T < 1) return emb::fail(-1, "%s: T=%d < 1", who, a.T);
   if (a.G < 1 || a.D % a.G || (a.D / a.G) % 16 || a.H % 16 || (a.S * a.C) % 16 || a.D % 16)
     return emb::fail(-1, "%s: D/G, H and S*C must be multiples of 16", who);
-  if (a.engine != rssm::ENG_F32 && a.engine != rssm::ENG_BF16)
+  if (a.engine != rssm::ENG_F32 && a.engine != rssm::ENG_TMA && a.engine != rssm::ENG_LEGACY)
     return emb::fail(-1, "%s: engine %d", who, a.engine);
   if (g_sms == 0) {
     int dev = 0;
@@ -426,8 +426,8 @@ extern "C" int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream)
   const size_t smem = bwd_smem_bytes(a);
   if (smem > 227 * 1024)
     return emb::fail(-1, "%s: needs %zu bytes of shared memory (> 227 KiB)", who, smem);
-  const void* fn = a.engine == rssm::ENG_BF16 ? (const void*)rssm_bwd_kernel<rssm::ENG_BF16>
-                                              : (const void*)rssm_bwd_kernel<rssm::ENG_F32>;
+  const void* fn = a.engine != rssm::ENG_F32 ? (const void*)rssm_bwd_kernel<rssm::ENG_BF16>
+                                             : (const void*)rssm_bwd_kernel<rssm::ENG_F32>;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return emb::fail_cuda(who);
   emb_rssm_bwd_args copy = a;

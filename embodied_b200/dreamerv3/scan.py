@@ -292,7 +292,7 @@ class Scan:
 # ---------------------------------------------------------------------- backward
 class BwdArgs(ctypes.Structure):
   _fields_ = (
-      [(n, _i32) for n in ('B', 'T', 'D', 'H', 'S', 'C', 'G', 'engine', 'ncta', 'pad_')] +
+      [(n, _i32) for n in ('B', 'T', 'D', 'H', 'S', 'C', 'G', 'engine', 'ncta', 'hoist_x2')] +
       [('unimix', _fl), ('eps', _fl)] +
       [(n, _vp) for n in (
           'wt_in1', 'wt_logit', 'wt_ph1', 'wt_gru', 'wt_hid', 's0', 's1', 's_hid', 's_obs',
@@ -304,22 +304,32 @@ class BwdArgs(ctypes.Structure):
 
 @torch.no_grad()
 def pack_bwd(store, cfg, engine, ncta):
-  """Transposed copies for the backward scan (same packed layouts)."""
+  """Transposed copies for the backward scan (register-staged layouts: the
+  backward kernel streams with plain loads, no tile padding).  With the bf16
+  engines the action rows of dynhid0 are left out -- their input gradient is one
+  (B*T)-row GEMM after the scan (hoisted like in the forward pass)."""
   D, G, H = cfg.deter, cfg.blocks, cfg.hidden
   Dg = D // G
+  lay = ENG_F32 if engine == ENG_F32 else ENG_LEGACY
   m = lambda n: store.view('master', n)
   wobs = m('dyn/obs0/kernel')
   ph1 = torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1)              # (D, 2H)
   gru = m('dyn/dyngru/kernel')                                        # (G, Dg, 3Dg) -> (3Dg, G*Dg)
   gru_t = gru.permute(2, 0, 1).reshape(3 * Dg, D)
   hid = m('dyn/dynhid0/kernel')                                       # (G, Kh, Dg) -> (Dg, G*Kh)
+  extra = {}
+  if engine != ENG_F32:
+    keep_rows = Dg + 2 * H
+    extra['w_hid_x2'] = hid[:, keep_rows:].permute(1, 0, 2).reshape(-1, D).to(torch.bfloat16)  # (H, D)
+    hid = hid[:, :keep_rows]
   hid_t = hid.permute(2, 0, 1).reshape(Dg, G * hid.shape[1])
   return dict(
-      wt_in1=pack_matrix(m('dyn/dynin1/kernel').t(), engine, ncta),
-      wt_logit=pack_matrix(m('dyn/obslogit/kernel').t(), engine, ncta),
-      wt_ph1=pack_matrix(ph1.t(), engine, ncta),
-      wt_gru=pack_matrix(gru_t, engine, ncta, groups=G),
-      wt_hid=pack_matrix(hid_t, engine, ncta, groups=G))
+      **extra,
+      wt_in1=pack_matrix(m('dyn/dynin1/kernel').t(), lay, ncta),
+      wt_logit=pack_matrix(m('dyn/obslogit/kernel').t(), lay, ncta),
+      wt_ph1=pack_matrix(ph1.t(), lay, ncta),
+      wt_gru=pack_matrix(gru_t, lay, ncta, groups=G),
+      wt_hid=pack_matrix(hid_t, lay, ncta, groups=G))
 
 
 def _bind_bwd(lib):
@@ -378,9 +388,12 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
              s_hid=m('dyn/dynhid0norm/scale'), s_obs=m('dyn/obs0norm/scale'))
   saved = {k: sv[k] for k in ('keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates',
                               'sumsq', 'probs', 'rstd')}
+  hoist = scan.engine != ENG_F32
   args = BwdArgs(B=B, T=T, D=D, H=H, S=S, C=C, G=G, engine=scan.engine, ncta=scan.ncta,
-                 unimix=cfg.unimix, eps=1e-4)
+                 hoist_x2=int(hoist), unimix=cfg.unimix, eps=1e-4)
   for k, v in {**scan.packed_bwd, **vec, **saved, **buf}.items():
+    if k == 'w_hid_x2':
+      continue
     assert v.is_contiguous(), k
     setattr(args, k, v.data_ptr())
   stream = torch.cuda.current_stream(dev).cuda_stream
@@ -404,7 +417,7 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
       prof.append(('rssm_bwd', e0, e1, T))
 
   # ---- parameter gradients: (T*16)-row GEMMs over the per-step layer gradients
-  cd = torch.bfloat16 if scan.engine == ENG_BF16 else f32
+  cd = f32 if scan.engine == ENG_F32 else torch.bfloat16
   mm = lambda a, b: (a.to(cd).t() @ b.to(cd)).to(f32)
   keep = sv['keep'][:T]                                               # (T, 16)
   deter = sv['deter']
@@ -451,7 +464,11 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
   pg['dyn/obslogit/kernel'] = mm(xo.reshape(R, H), buf['g_logit'].reshape(R, SC))
   pg['dyn/obslogit/bias'] = buf['g_logit'].reshape(R, SC).sum(0)
   bm = lambda x: x[:, :B].transpose(0, 1)
-  ig = dict(y0=g_y0[0, :B], y1=g_y1[0, :B], x2=bm(buf['g_x2']), pre_tok=bm(g_yobs))
+  g_x2 = buf['g_x2']
+  if hoist:      # the action rows of dynhid0, hoisted: g_x2 = g_yhid @ W[g][Dg+2H:]^T summed over groups
+    g_x2 = torch.mm(g_yhid.reshape(R, D).to(torch.bfloat16), scan.packed_bwd['w_hid_x2'].t(),
+                    out_dtype=f32).reshape(T, ROWS, H)
+  ig = dict(y0=g_y0[0, :B], y1=g_y1[0, :B], x2=bm(g_x2), pre_tok=bm(g_yobs))
   return ig, pg, buf
 
 

@@ -153,3 +153,40 @@ def test_backward_fp32_engine_matches_oracle_autograd(name, over, B, T):
   assert max(worst)[0] < 1e-4, sorted(worst)[-5:]
   a, b = tok_dev.grad.cpu().double(), tok_leaf.grad.double()
   assert float((a - b).norm() / b.norm()) < 1e-4
+
+
+@pytest.mark.parametrize('size,B,T', [('size12m', 16, 4), ('size200m', 5, 3)])
+def test_backward_bf16_engine_tracks_fp32_engine(size, B, T):
+  """emb_rssm_observe_bwd with the bf16 engine (mma, packed transposed weights,
+  hoisted action rows) against the fp32 parity engine at the reference's real
+  layer shapes -- where the per-CTA tile counts are not trivial.  The Gumbel noise
+  is a large one-hot so that both engines sample the same latents."""
+  from embodied_b200.dreamerv3 import config as C
+  cfg = C.make(size)
+  store = paramlib.ParamStore(cfg, 'cuda', torch.float32, 0)
+  g = torch.Generator(device='cuda').manual_seed(5)
+  r = lambda *s: torch.randn(s, generator=g, device='cuda')
+  D, H, S, Cc = cfg.deter, cfg.hidden, cfg.stoch, cfg.classes
+  pick = torch.randint(0, Cc, (B, T, S), generator=g, device='cuda')
+  noise = 1000.0 * torch.nn.functional.one_hot(pick, Cc).float()       # decides every arg-max
+  inputs = (r(B, D) * 0.3, r(B, H), r(B, H), r(B, T, H), r(B, T, H),
+            (torch.rand(B, T, generator=g, device='cuda') > 0.2).float(), noise)
+  Gd, Gl, Gs = r(B, T, D) * 0.1, r(B, T, S, Cc) * 0.1, r(B, T, S, Cc) * 0.1
+  res = {}
+  for name, engine in (('f32', scanlib.ENG_F32), ('bf16', scanlib.ENG_BF16)):
+    sc = scanlib.Scan(cfg, store, engine)
+    out, sv = sc.forward(*inputs)
+    ig, pg, _ = scanlib.scan_backward(sc, sv, B, Gd, Gl, Gs)
+    torch.cuda.synchronize()
+    res[name] = (out, ig, pg)
+  assert torch.equal(res['f32'][0]['index'], res['bf16'][0]['index'])
+  assert rel(res['bf16'][0]['deter'], res['f32'][0]['deter']) < 3e-2
+  def rel2(a, b):
+    return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+  worst = []
+  for k, v in res['f32'][1].items():
+    worst.append((rel2(res['bf16'][1][k], v), 'input ' + k))
+  for k, v in res['f32'][2].items():
+    if float(v.abs().max()) > 0:
+      worst.append((rel2(res['bf16'][2][k], v), k))
+  assert max(worst)[0] < 6e-2, sorted(worst)[-6:]
