@@ -405,6 +405,10 @@ int g_sms = 0;
 
 }  // namespace
 
+namespace emb_tma {
+int launch_bwd(const emb_rssm_bwd_args& a, void* stream);   // rssm_bwd_tma.cu
+}
+
 extern "C" int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream) {
   const char* who = "emb_rssm_observe_bwd";
   if (!args) return emb::fail(-1, "%s: args is NULL", who);
@@ -415,6 +419,7 @@ extern "C" int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream)
     return emb::fail(-1, "%s: D/G, H and S*C must be multiples of 16", who);
   if (a.engine != rssm::ENG_F32 && a.engine != rssm::ENG_TMA && a.engine != rssm::ENG_LEGACY)
     return emb::fail(-1, "%s: engine %d", who, a.engine);
+  if (a.engine == rssm::ENG_TMA) return emb_tma::launch_bwd(a, stream);
   if (g_sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||

@@ -1,0 +1,434 @@
+// emb_rssm_observe_bwd, bf16 engine: back-propagation through time of the fused
+// RSSM scan (the reverse of rssm_fwd_tma.cu; dreamerv3/rssm.py:61-92,135-159
+// differentiated) with the weight stream on the TMA ring of rssm_tma.cuh.
+//
+// Per step t = T-1 .. 0 the gradient is pushed back through the five in-scan
+// layers with TRANSPOSED packed weights (one HBM pass over every weight per
+// step, evict-first in L2); parameter gradients are formed afterwards by the
+// host from the per-step layer gradients this kernel leaves behind
+// (embodied_b200/dreamerv3/scan.py scan_backward).
+//
+//   B1  g_stoch = G_stoch[t] + (keep' * g_y1') @ dynin1^T                        (2.1 M)
+//   B2  g_logit = G_logit[t] + unimix-softmax-jacobian(g_stoch) ; g_xo = g_logit @ obslogit^T (2.1 M)
+//   B3  g_deter = G_deter[t] + carry + [g_yobs | keep' * g_y0'] @ [obs0[:D] | dynin0]^T    (16.8 M)
+//       + GRU gate backward in the epilogue -> g_gates
+//   B4  g_h     = g_gates_g @ dyngru[g]^T ; row dots for the rms-norm backward   (25.2 M)
+//   B5  g_in    = g_yhid_g @ dynhid0[g][:Dg+2H]^T -> carry (deter part), g_x0 / g_x1 (25.2 M;
+//       the action rows are hoisted: the host forms g_x2 with one GEMM)
+// (primes = step t+1;  g_y* = rms-norm + silu backward of g_x*.)
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "../../include/embodied_b200.h"
+#include "common.cuh"
+#include "rssm_common.cuh"
+#include "rssm_tma.cuh"
+
+namespace {
+
+using namespace rssm;
+using namespace rssm_tma;
+
+__device__ __forceinline__ float dsilu_fast(float n) {          // d silu(n) / dn
+  const float sg = __fdividef(1.0f, 1.0f + __expf(-n));
+  return sg * (1.0f + n * (1.0f - sg));
+}
+// rms-norm + silu backward (nets.py:374-383): with n = y * rstd * s,
+//   g_n = g_x * silu'(n),   g_y = rstd * s * g_n - y * coef,   coef = rstd^3 * mean_k(g_n s y)
+__device__ __forceinline__ float norm_bwd_elem(float gx, float y, float s, float rstd, float coef) {
+  const float gn = gx * dsilu_fast(y * rstd * s);
+  return rstd * s * gn - y * coef;
+}
+
+// A fragments (shared) from two fp32 [16][n] global sources: f(r, k, v1, v2)
+template <typename F>
+__device__ __forceinline__ void build2(__nv_bfloat16* afrag, int koff, const float* s1, int ld1,
+                                       const float* s2, int ld2, int n, F f) {
+  const int n4 = n >> 2;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < kRows * n4; i += kCThreads) {
+    const int r = i / n4, k = (i - r * n4) << 2;
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(s1 + (size_t)r * ld1 + k));
+    const float4 w = __ldcg(reinterpret_cast<const float4*>(s2 + (size_t)r * ld2 + k));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k)) =
+        __floats2bfloat162_rn(f(r, k, v.x, w.x), f(r, k + 1, v.y, w.y));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k + 2)) =
+        __floats2bfloat162_rn(f(r, k + 2, v.z, w.z), f(r, k + 3, v.w, w.w));
+  }
+}
+template <typename F>
+__device__ __forceinline__ void build1(__nv_bfloat16* afrag, int koff, const float* src, int n, int ld, F f) {
+  const int n4 = n >> 2;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < kRows * n4; i += kCThreads) {
+    const int r = i / n4, k = (i - r * n4) << 2;
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)r * ld + k));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k)) =
+        __floats2bfloat162_rn(f(r, k, v.x), f(r, k + 1, v.y));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k + 2)) =
+        __floats2bfloat162_rn(f(r, k + 2, v.z), f(r, k + 3, v.w));
+  }
+}
+
+struct Plan {
+  int per[5], ks[5], u0[5], u1[5];        // B1..B5: padded tiles per CTA, k16 steps, owned tiles
+  const unsigned char* blk[5];
+};
+
+__device__ __forceinline__ Plan make_plan(const emb_rssm_bwd_args& a) {
+  Plan p;
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int D = a.D, H = a.H, Dg = D / a.G, SC = a.S * a.C, Kh = Dg + 2 * H;
+  const int tiles[3] = {SC / 8, H / 8, D / 8};
+  const int kdim[5] = {H, SC, 2 * H, 3 * Dg, Dg};
+  const void* w[5] = {a.wt_in1, a.wt_logit, a.wt_ph1, a.wt_gru, a.wt_hid};
+  for (int i = 0; i < 3; ++i) {
+    const int raw = (tiles[i] + ncta - 1) / ncta;
+    p.per[i] = pad_tiles(raw, 1);
+    p.u0[i] = min(tiles[i], cta * raw);
+    p.u1[i] = min(tiles[i], p.u0[i] + raw);
+  }
+  const GroupSplit s4 = group_split(Dg / 8, a.G), s5 = group_split(Kh / 8, a.G);
+  p.per[3] = pad_tiles(s4.per, 1); p.u0[3] = s4.u0; p.u1[3] = s4.u1;
+  p.per[4] = pad_tiles(s5.per, 1); p.u0[4] = s5.u0; p.u1[4] = s5.u1;
+  for (int i = 0; i < 5; ++i) {
+    p.ks[i] = kdim[i] / 16;
+    p.blk[i] = reinterpret_cast<const unsigned char*>(w[i]) + (size_t)cta * p.ks[i] * p.per[i] * 256;
+  }
+  return p;
+}
+
+__global__ void __launch_bounds__(kAllThreads, 1)
+rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int T = a.T, D = a.D, H = a.H, S = a.S, C = a.C, G = a.G;
+  const int Dg = D / G, SC = S * C, Kh = Dg + 2 * H;
+  const int tid = threadIdx.x;
+  const size_t RH = (size_t)kRows * H, RD = (size_t)kRows * D, RSC = (size_t)kRows * SC;
+
+  // ---- shared memory: [barriers 256 B][out 16 x maxper*8 f32][4 x 16 row statistics][A region][ring]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* out = reinterpret_cast<float*>(smem_raw + 256);
+  const int maxper = (a.hoist_x2 >> 8) & 0xff;
+  float* st = out + kRows * maxper * 8;
+  float *rstd_a = st, *coef_a = st + 16, *rstd_b = st + 32, *coef_b = st + 48;
+  unsigned char* abase = reinterpret_cast<unsigned char*>(st + 64);
+  __nv_bfloat16* afrag = reinterpret_cast<__nv_bfloat16*>(abase);
+  uint4* afrag4 = reinterpret_cast<uint4*>(abase);
+  int kmax = 3 * Dg;
+  if (2 * H > kmax) kmax = 2 * H;
+  if (SC > kmax) kmax = SC;
+  Ring ring;
+  ring.nstages = a.hoist_x2 & 0xff;
+  ring.stage_bytes = (a.hoist_x2 >> 16) * 1024;
+  ring.stage = 0;
+  ring.phase = 0;
+  ring.full = bars;
+  ring.empty = bars + 12;
+  ring.data = abase + (((size_t)kRows * kmax * 2 + 127) & ~(size_t)127);
+  if (tid == 0) {
+    for (int i = 0; i < ring.nstages; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], kCWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const Plan p = make_plan(a);
+
+  // =========================================================== producer warp
+  if (tid >= kCThreads) {
+    if (tid == kCThreads) {
+      for (int t = T - 1; t >= 0; --t)
+        for (int i = 0; i < 5; ++i)
+          if (p.u0[i] < p.u1[i]) produce(ring, p.blk[i], p.per[i], p.ks[i], false);
+    }
+    return;
+  }
+
+  // ========================================================== consumer warps
+  GridBarrierC bar{a.barrier, 0};
+  const int cta = blockIdx.x, ncta = gridDim.x;
+
+  // row statistics of a normalised layer at step `ts`: slot 0 x0, 1 x1, 2 xo
+  auto load_stats = [&](int ts, int slot, int n, float* rstd, float* coef) {
+    if (tid < kRows) {
+      const float rs = a.rstd[(size_t)ts * 3 * kRows + slot * kRows + tid];
+      rstd[tid] = rs;
+      coef[tid] = rs * rs * rs * ldcg(a.dots + ((size_t)ts * 4 + slot) * kRows + tid) / (float)n;
+    }
+  };
+  // sum out[r][c0..c1) per row (16 threads per row) and add it to a.dots[ts][slot][r]
+  auto add_row_dots = [&](int ts, int slot, int ncols, int c0, int c1) {
+    const int r = tid >> 4, l = tid & 15;
+    float sum = 0.f;
+    for (int c = c0 + l; c < c1; c += 16) sum += out[r * ncols + c];
+#pragma unroll
+    for (int o = 8; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (l == 0 && c0 < c1) atomicAdd(a.dots + ((size_t)ts * 4 + slot) * kRows + r, sum);
+  };
+
+  for (int t = T - 1; t >= 0; --t) {
+    const float* keep = a.keep + (size_t)t * kRows;
+    const float* keep_next = a.keep + (size_t)(t + 1) * kRows;
+    const float* deter_prev = t == 0 ? a.deter0 : a.deter + (size_t)(t - 1) * RD;
+    const float* y0 = a.y0 + (size_t)t * RH;
+    const float* y1 = a.y1 + (size_t)t * RH;
+    const float* y0n = a.y0 + (size_t)(t + 1) * RH;         // step t+1 (zeros at t = T-1)
+    const float* y1n = a.y1 + (size_t)(t + 1) * RH;
+    const float* gx0n = a.g_x0 + (size_t)(t + 1) * RH;
+    const float* gx1n = a.g_x1 + (size_t)(t + 1) * RH;
+    const float* yobs = a.yobs + (size_t)t * RH;
+    const float* yhid = a.yhid + (size_t)t * RD;
+    const float* gates = a.gates + (size_t)t * 4 * RD;
+    float* g_xo = a.g_xo + (size_t)t * RH;
+    float* g_h = a.g_h + (size_t)t * RD;
+    float* g_gates = a.g_gates + (size_t)t * 3 * RD;
+    float* g_logit = a.g_logit + (size_t)t * RSC;
+
+    // ------------------------------------------------------------------ B1
+    if (p.u0[0] < p.u1[0]) {
+      load_stats(t + 1, 1, H, rstd_a, coef_a);
+      cbar();
+      build2(afrag, 0, gx1n, H, y1n, H, H, [&](int r, int k, float gx, float y) {
+        return ldcg(keep_next + r) * norm_bwd_elem(gx, y, a.s1[k], rstd_a[r], coef_a[r]); });
+      cbar();
+      EMB_CONSUME(false, ring, p.per[0], p.ks[0], afrag4, nullptr, out, true)
+      const int ncols = p.per[0] * 8, nvalid = (p.u1[0] - p.u0[0]) * 8;
+      for (int i = tid; i < kRows * ncols; i += kCThreads) {
+        const int r = i / ncols, c = i - r * ncols;
+        if (c >= nvalid) continue;
+        const int col = p.u0[0] * 8 + c;
+        a.g_stoch[(size_t)r * SC + col] = out[i] + a.G_stoch[(size_t)t * RSC + (size_t)r * SC + col];
+      }
+    }
+    bar.sync();
+
+    // ------------------------------------------------------------------ B2
+    // g_logit = G_logit + (1-eps) p (g_stoch - sum_c p g_stoch) ;  g_xo = g_logit @ obslogit^T
+    {
+      const bool on = p.u0[1] < p.u1[1];
+      const int wrow = ncta - 1 - cta;               // row r of g_logit is also written out by CTA ncta-1-r
+      if (on || (wrow >= 0 && wrow < kRows)) {
+        const float* pr = a.probs + (size_t)t * RSC;
+        const float* Gl = a.G_logit + (size_t)t * RSC;
+        for (int grp = tid; grp < kRows * S; grp += kCThreads) {
+          const int r = grp / S, sv = grp - r * S;
+          const size_t o = (size_t)r * SC + (size_t)sv * C;
+          float dot = 0.f;
+          for (int c = 0; c < C; c += 4) {
+            const float4 pv = *reinterpret_cast<const float4*>(pr + o + c);
+            const float4 g = __ldcg(reinterpret_cast<const float4*>(a.g_stoch + o + c));
+            dot += pv.x * g.x + pv.y * g.y + pv.z * g.z + pv.w * g.w;
+          }
+          for (int c = 0; c < C; c += 4) {
+            const float4 pv = *reinterpret_cast<const float4*>(pr + o + c);
+            const float4 g = __ldcg(reinterpret_cast<const float4*>(a.g_stoch + o + c));
+            const float4 e = *reinterpret_cast<const float4*>(Gl + o + c);
+            const float um = 1.0f - a.unimix;
+            float4 v;
+            v.x = e.x + um * pv.x * (g.x - dot); v.y = e.y + um * pv.y * (g.y - dot);
+            v.z = e.z + um * pv.z * (g.z - dot); v.w = e.w + um * pv.w * (g.w - dot);
+            const int k = sv * C + c;
+            *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k)) = __floats2bfloat162_rn(v.x, v.y);
+            *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k + 2)) = __floats2bfloat162_rn(v.z, v.w);
+            if (wrow == r) *reinterpret_cast<float4*>(g_logit + o + c) = v;
+          }
+        }
+        if (on) load_stats(t, 2, H, rstd_a, coef_a);       // only rstd is used here
+        cbar();
+        if (on) {
+          EMB_CONSUME(false, ring, p.per[1], p.ks[1], afrag4, nullptr, out, true)
+          const int ncols = p.per[1] * 8, nvalid = (p.u1[1] - p.u0[1]) * 8;
+          for (int i = tid; i < kRows * ncols; i += kCThreads) {
+            const int r = i / ncols, c = i - r * ncols;
+            float prod = 0.f;
+            if (c < nvalid) {
+              const int col = p.u0[1] * 8 + c;
+              const float gx = out[i];
+              g_xo[(size_t)r * H + col] = gx;
+              const float y = yobs[(size_t)r * H + col], sc = a.s_obs[col];
+              prod = gx * dsilu_fast(y * rstd_a[r] * sc) * sc * y;      // g_n * s * y
+            }
+            out[i] = prod;
+          }
+          cbar();
+          add_row_dots(t, 2, ncols, 0, nvalid);
+        }
+      }
+    }
+    bar.sync();
+
+    // ------------------------------------------------------------------ B3
+    if (p.u0[2] < p.u1[2]) {
+      load_stats(t, 2, H, rstd_a, coef_a);
+      load_stats(t + 1, 0, H, rstd_b, coef_b);
+      cbar();
+      build2(afrag, 0, g_xo, H, yobs, H, H, [&](int r, int k, float gx, float y) {
+        return norm_bwd_elem(gx, y, a.s_obs[k], rstd_a[r], coef_a[r]); });
+      build2(afrag, H, gx0n, H, y0n, H, H, [&](int r, int k, float gx, float y) {
+        return ldcg(keep_next + r) * norm_bwd_elem(gx, y, a.s0[k], rstd_b[r], coef_b[r]); });
+      cbar();
+      EMB_CONSUME(false, ring, p.per[2], p.ks[2], afrag4, nullptr, out, true)
+      const int ncols = p.per[2] * 8, nvalid = (p.u1[2] - p.u0[2]) * 8;
+      for (int i = tid; i < kRows * ncols; i += kCThreads) {
+        const int r = i / ncols, c = i - r * ncols;
+        if (c >= nvalid) continue;
+        const int col = p.u0[2] * 8 + c;
+        const size_t at = (size_t)r * D + col;
+        const float gd = out[i] + a.G_deter[(size_t)t * RD + at] + ldcg(a.gd_carry + at);
+        const float rs = gates[at], cand = gates[RD + at], up = gates[2 * RD + at], cpre = gates[3 * RD + at];
+        const float old = ldcg(keep + r) * deter_prev[at];
+        const float g_u = gd * (cand - old), g_c = gd * up;
+        a.gd_tmp[at] = gd * (1.0f - up);                 // direct path into keep*deter_{t-1}
+        const float g_rc = g_c * (1.0f - cand * cand);
+        const int g = col / Dg, jj = col - g * Dg;
+        float* gg = g_gates + (size_t)r * 3 * D + (size_t)g * 3 * Dg + jj;
+        gg[0] = g_rc * cpre * rs * (1.0f - rs);          // reset gate, pre-sigmoid
+        gg[Dg] = g_rc * rs;                              // candidate, pre-tanh
+        gg[2 * Dg] = g_u * up * (1.0f - up);             // update gate, pre-sigmoid
+      }
+    }
+    bar.sync();
+
+    // ------------------------------------------------------------------ B4
+    if (p.u0[3] < p.u1[3]) {
+      const int tpg = Dg / 8;
+      const int g = p.u0[3] / tpg;
+      if (tid < kRows) rstd_a[tid] = rsqrtf(a.sumsq[(size_t)t * kRows + tid] / (float)D + a.eps);
+      const float* src = g_gates + (size_t)g * 3 * Dg;
+      build1(afrag, 0, src, 3 * Dg, 3 * D, [&](int, int, float v) { return v; });
+      cbar();
+      EMB_CONSUME(false, ring, p.per[3], p.ks[3], afrag4, nullptr, out, true)
+      const int ncols = p.per[3] * 8, nvalid = (p.u1[3] - p.u0[3]) * 8;
+      for (int i = tid; i < kRows * ncols; i += kCThreads) {
+        const int r = i / ncols, c = i - r * ncols;
+        float prod = 0.f;
+        if (c < nvalid) {
+          const int col = p.u0[3] * 8 + c;
+          const size_t at = (size_t)r * D + col;
+          const float gh = out[i];
+          g_h[at] = gh;
+          const float y = yhid[at], sc = a.s_hid[col];
+          prod = gh * dsilu_fast(y * rstd_a[r] * sc) * sc * y;    // g_n * s * y
+        }
+        out[i] = prod;
+      }
+      cbar();
+      add_row_dots(t, 3, ncols, 0, nvalid);
+    }
+    bar.sync();
+
+    // ------------------------------------------------------------------ B5
+    if (p.u0[4] < p.u1[4]) {
+      const int tpg = Kh / 8;
+      const int g = p.u0[4] / tpg;
+      if (tid < kRows) {
+        const float rs = rsqrtf(a.sumsq[(size_t)t * kRows + tid] / (float)D + a.eps);
+        rstd_a[tid] = rs;
+        coef_a[tid] = rs * rs * rs * ldcg(a.dots + ((size_t)t * 4 + 3) * kRows + tid) / (float)D;
+        rstd_b[tid] = a.rstd[(size_t)t * 3 * kRows + tid];             // y0[t]
+        coef_b[tid] = a.rstd[(size_t)t * 3 * kRows + kRows + tid];     // y1[t] (rstd, not a coef)
+      }
+      cbar();
+      build2(afrag, 0, g_h + (size_t)g * Dg, D, yhid + (size_t)g * Dg, D, Dg,
+             [&](int r, int k, float gx, float y) {
+        return norm_bwd_elem(gx, y, a.s_hid[g * Dg + k], rstd_a[r], coef_a[r]); });
+      cbar();
+      EMB_CONSUME(false, ring, p.per[4], p.ks[4], afrag4, nullptr, out, true)
+      const int ncols = p.per[4] * 8, nvalid = (p.u1[4] - p.u0[4]) * 8;
+      const int n0 = (p.u0[4] - g * tpg) * 8;            // first column within the group's Kh inputs
+      for (int i = tid; i < kRows * ncols; i += kCThreads) {
+        const int r = i / ncols, c = i - r * ncols;
+        float prod = 0.f;
+        if (c < nvalid) {
+          const int n = n0 + c;
+          const float v = out[i];
+          if (n < Dg) {
+            const size_t at = (size_t)r * D + (size_t)g * Dg + n;
+            a.gd_carry[at] = ldcg(keep + r) * (ldcg(a.gd_tmp + at) + v);
+          } else {
+            const int m = n - Dg;                          // [x0 | x1]
+            const int which = m / H, k = m - which * H;
+            float* dst = which == 0 ? a.g_x0 : a.g_x1;
+            atomicAdd(dst + (size_t)t * RH + (size_t)r * H + k, v);
+            if (which == 0) {
+              const float y = y0[(size_t)r * H + k], sc = a.s0[k];
+              prod = v * dsilu_fast(y * rstd_b[r] * sc) * sc * y;
+            } else {
+              const float y = y1[(size_t)r * H + k], sc = a.s1[k];
+              prod = v * dsilu_fast(y * coef_b[r] * sc) * sc * y;
+            }
+          }
+        }
+        out[i] = prod;
+      }
+      cbar();
+      // columns [Dg, Dg+H) feed dots slot 0 (x0), [Dg+H, Dg+2H) slot 1 (x1)
+      add_row_dots(t, 0, ncols, max(0, Dg - n0), min(nvalid, Dg + H - n0));
+      add_row_dots(t, 1, ncols, max(0, Dg + H - n0), min(nvalid, Dg + 2 * H - n0));
+    }
+    bar.sync();
+  }
+}
+
+int g_sms_bwd = 0;
+
+}  // namespace
+
+namespace emb_tma {
+
+int launch_bwd(const emb_rssm_bwd_args& a, void* stream) {
+  const char* who = "emb_rssm_observe_bwd";
+  const int Dg = a.D / a.G, SC = a.S * a.C, Kh = Dg + 2 * a.H;
+  if (!a.hoist_x2) return emb::fail(-1, "%s: the bf16 TMA engine needs hoist_x2 = 1", who);
+  if (g_sms_bwd == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_sms_bwd, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return emb::fail_cuda(who);
+  }
+  if (a.ncta < rssm::kRows || a.ncta > g_sms_bwd)
+    return emb::fail(-1, "%s: ncta=%d outside [16, %d SMs] (cooperative grid)", who, a.ncta, g_sms_bwd);
+  auto cdiv = [](int x, int y) { return (x + y - 1) / y; };
+  const int cpg = a.ncta / a.G > 1 ? a.ncta / a.G : 1;
+  const int per[5] = {rssm_tma::pad_tiles(cdiv(SC / 8, a.ncta), 1), rssm_tma::pad_tiles(cdiv(a.H / 8, a.ncta), 1),
+                      rssm_tma::pad_tiles(cdiv(a.D / 8, a.ncta), 1), rssm_tma::pad_tiles(cdiv(Dg / 8, cpg), 1),
+                      rssm_tma::pad_tiles(cdiv(Kh / 8, cpg), 1)};
+  int maxper = 0;
+  for (int i = 0; i < 5; ++i) {
+    if (per[i] > rssm_tma::kMaxPer)
+      return emb::fail(-1, "%s: %d tiles per CTA exceed %d (model too wide for %d CTAs)", who, per[i],
+                       rssm_tma::kMaxPer, a.ncta);
+    if (per[i] > maxper) maxper = per[i];
+  }
+  int stage_bytes = rssm_tma::kStageBytesDefault, stage_cap = 0;
+  if (const char* e = getenv("EMB_TMA_STAGE_KB")) stage_bytes = atoi(e) * 1024;
+  if (const char* e = getenv("EMB_TMA_STAGES")) stage_cap = atoi(e);
+  if (stage_bytes < 8192 || stage_bytes > 65536 || stage_bytes % 1024)
+    return emb::fail(-1, "%s: EMB_TMA_STAGE_KB out of range", who);
+  int kmax = 3 * Dg;
+  if (2 * a.H > kmax) kmax = 2 * a.H;
+  if (SC > kmax) kmax = SC;
+  size_t fixed = 256 + sizeof(float) * (rssm::kRows * maxper * 8 + 64);
+  fixed += ((size_t)rssm::kRows * kmax * 2 + 127) & ~(size_t)127;
+  const size_t cap = 227 * 1024 - 128;
+  int n = fixed + 2 * (size_t)stage_bytes <= cap ? (int)((cap - fixed) / stage_bytes) : 0;
+  if (n > 12) n = 12;
+  if (stage_cap > 0 && stage_cap < n) n = stage_cap;
+  if (n < 2) return emb::fail(-1, "%s: no room for the weight ring (A operand of %d columns)", who, kmax);
+  const size_t smem = fixed + (size_t)n * stage_bytes + 128;
+  emb_rssm_bwd_args copy = a;
+  copy.hoist_x2 = n | (maxper << 8) | ((stage_bytes / 1024) << 16);      // kernel-side ring configuration
+  const void* fn = (const void*)rssm_bwd_tma_kernel;
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return emb::fail_cuda(who);
+  void* params[] = {&copy};
+  if (cudaLaunchCooperativeKernel(fn, dim3(a.ncta), dim3(rssm_tma::kAllThreads), params, smem,
+                                  (cudaStream_t)stream) != cudaSuccess)
+    return emb::fail_cuda(who);
+  emb::count_launch();
+  return 0;
+}
+
+}  // namespace emb_tma

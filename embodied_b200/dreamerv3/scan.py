@@ -304,13 +304,12 @@ class BwdArgs(ctypes.Structure):
 
 @torch.no_grad()
 def pack_bwd(store, cfg, engine, ncta):
-  """Transposed copies for the backward scan (register-staged layouts: the
-  backward kernel streams with plain loads, no tile padding).  With the bf16
-  engines the action rows of dynhid0 are left out -- their input gradient is one
+  """Transposed copies for the backward scan, in the same packed layouts as the
+  forward pass.  With the bf16 engines the action rows of dynhid0 are left out -- their input gradient is one
   (B*T)-row GEMM after the scan (hoisted like in the forward pass)."""
   D, G, H = cfg.deter, cfg.blocks, cfg.hidden
   Dg = D // G
-  lay = ENG_F32 if engine == ENG_F32 else ENG_LEGACY
+  lay = engine       # fp32 [tile][K][8] | bf16 padded blocks (TMA ring) | bf16 plain blocks
   m = lambda n: store.view('master', n)
   wobs = m('dyn/obs0/kernel')
   ph1 = torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1)              # (D, 2H)
