@@ -46,7 +46,7 @@ CLASSES = 5
 ROW_BYTES = 12288 + 32768 + 8192 + 20 + 4 + 4 + 3      # image, deter, stoch, stepid, reward, action, 3 flags
 TRAINS_PER_STEP = TRAIN_RATIO * NENVS // (B * T)        # 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/)
-NCU_TRAFFIC = {'rssm_fwd': 8951381000 + 319277312, 'rssm_bwd': 10436836000 + 142067712}
+NCU_TRAFFIC = {'rssm_fwd': 8866361000 + 194415104}     # profiles/r01_rssm_fwd_tma_kernel.md
 
 
 def peaks():
@@ -305,7 +305,7 @@ def run_b200(args):
     wbytes_fwd = (fixed + cfg.deter * (Dg + (2 if args.dtype == 'bfloat16' else 3) * cfg.hidden)) * esz * T
     # DRAM traffic per launch from ncu (profiles/r01_rssm_*_kernel.md), bf16 size200m only
     known = args.dtype == 'bfloat16' and args.size == 'size200m'
-    kernels.append(kernel_line('rssm_bwd', 'rssm_bwd_kernel (emb_rssm_observe_bwd, B=16 T=64)', wbytes,
+    kernels.append(kernel_line('rssm_bwd', 'rssm_bwd_kernel (emb_rssm_observe_bwd, TMA weight ring, B=16 T=64)', wbytes_fwd,
                                NCU_TRAFFIC.get('rssm_bwd') if known else None))
     kernels.append(kernel_line('rssm_fwd', 'rssm_fwd_kernel (emb_rssm_observe_fwd, TMA weight ring, B=16 T=64)', wbytes_fwd,
                                NCU_TRAFFIC.get('rssm_fwd') if known else None))

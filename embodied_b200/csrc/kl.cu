@@ -222,3 +222,42 @@ extern "C" int emb_rssm_kl_bwd(const emb_rssm_kl_args* k, const float* kl_raw, c
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;
 }
+
+// ---------------------------------------------------------------- lambda returns
+// emb_lambda_return: the reversed recurrence of dreamerv3/agent.py:482-490 as one
+// launch (one thread per row) instead of 3 element-wise launches per time step:
+//   live = (1 - term[:, 1:]) * disc ;  cont = (1 - last[:, 1:]) * lam
+//   ret[:, t] = rew[:, t+1] + (1 - cont_t) live_t boot[:, t+1] + live_t cont_t ret[:, t+1],
+//   ret[:, L-1] := boot[:, L-1]  (not stored).  All inputs fp32 [rows][L]; ret [rows][L-1].
+namespace {
+__global__ void lambda_return_kernel(const float* __restrict__ last, const float* __restrict__ term,
+                                     const float* __restrict__ rew, const float* __restrict__ boot,
+                                     float* __restrict__ ret, int64_t rows, int L, float disc, float lam) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float* la = last + r * L;
+  const float* te = term + r * L;
+  const float* re = rew + r * L;
+  const float* bo = boot + r * L;
+  float acc = bo[L - 1];
+  for (int t = L - 2; t >= 0; --t) {
+    const float live = (1.0f - te[t + 1]) * disc;
+    const float cont = (1.0f - la[t + 1]) * lam;
+    acc = (re[t + 1] + (1.0f - cont) * live * bo[t + 1]) + live * cont * acc;
+    ret[r * (L - 1) + t] = acc;
+  }
+}
+}  // namespace
+
+extern "C" int emb_lambda_return(const float* last, const float* term, const float* rew,
+                                 const float* boot, float* ret, int64_t rows, int32_t length,
+                                 float disc, float lam, void* stream) {
+  const char* who = "emb_lambda_return";
+  if (rows < 0 || length < 1) return emb::fail(-1, "%s: rows=%lld length=%d", who, (long long)rows, length);
+  if (rows == 0 || length == 1) return 0;
+  lambda_return_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      last, term, rew, boot, ret, rows, length, disc, lam);
+  emb::count_launch();
+  if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
+  return 0;
+}

@@ -302,14 +302,15 @@ struct GridBarrierC {
     fence_proxy_async();
     cbar();
     if (threadIdx.x == 0) {
+      // release / acquire at gpu scope instead of two full fences: the bar.sync above
+      // orders the CTA's writes before thread 0's release, the one below hands the
+      // acquired view to the other threads (cross-CTA data is read through L2)
       epoch += gridDim.x;
-      __threadfence();
-      atomicAdd(counter, 1u);
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(counter) : "memory");
       unsigned v;
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
       } while ((int)(v - epoch) < 0);
-      __threadfence();
     }
     cbar();
   }

@@ -381,6 +381,8 @@ class Model:
 
   @staticmethod
   def lambda_return(last, term, rew, val, boot, disc, lam):  # agent.py:482-490
+    if rew.is_cuda and rew.dim() == 2:                        # one launch; feeds detached targets only
+      return ops.lambda_return(last, term, rew, boot, disc, lam)
     live = (1 - term.to(f32))[:, 1:] * disc
     cont = (1 - last.to(f32))[:, 1:] * lam
     interm = rew[:, 1:] + (1 - cont) * live * boot[:, 1:]

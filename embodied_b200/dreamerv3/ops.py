@@ -39,6 +39,8 @@ def _lib_bound():
     lib.emb_rmsnorm_grouped_fwd.restype = ctypes.c_int
     lib.emb_gru_gates_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]
     lib.emb_gru_gates_fwd.restype = ctypes.c_int
+    lib.emb_lambda_return.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _fl, _fl, _vp]
+    lib.emb_lambda_return.restype = ctypes.c_int
     _bound = True
   return lib
 
@@ -336,3 +338,19 @@ def gru_gates(pre, bias, deter):
       pre.data_ptr(), bias.data_ptr(), deter.data_ptr(), out.data_ptr(), M, g, Dg3 // 3,
       _dtype_code(pre), stream))
   return out
+
+
+@torch.no_grad()
+def lambda_return(last, term, rew, boot, disc, lam):
+  """dreamerv3/agent.py:482-490 for (rows, L) inputs -> (rows, L-1); one launch.
+  The result only ever feeds stop-gradient targets, so there is no backward."""
+  lib = _lib_bound()
+  f = lambda x: x.detach().to(f32).contiguous()
+  last, term, rew, boot = f(last), f(term), f(rew), f(boot)
+  rows, L = rew.shape
+  ret = torch.empty((rows, L - 1), dtype=f32, device=rew.device)
+  stream = torch.cuda.current_stream(rew.device).cuda_stream
+  _lib.check(lib.emb_lambda_return(
+      last.data_ptr(), term.data_ptr(), rew.data_ptr(), boot.data_ptr(), ret.data_ptr(), rows, L,
+      float(disc), float(lam), stream))
+  return ret

@@ -259,6 +259,11 @@ int emb_rssm_kl_fwd(const emb_rssm_kl_args* args, float* dyn, float* rep, float*
 int emb_rssm_kl_bwd(const emb_rssm_kl_args* args, const float* kl_raw, const float* g_dyn,
                     const float* g_rep, float* g_post, float* g_prior, void* stream);
 
+/* The lambda-return recurrence (dreamerv3/agent.py:482-490) as one launch, one thread
+ * per row.  last / term / rew / boot: fp32 [rows][length]; ret: fp32 [rows][length-1]. */
+int emb_lambda_return(const float* last, const float* term, const float* rew, const float* boot,
+                      float* ret, int64_t rows, int32_t length, float disc, float lam, void* stream);
+
 /* rms-norm (+ silu) over the last axis, one HBM pass each way
  * (embodied/jax/nets.py:361-399 Norm('rms') followed by act, eps 1e-4), with the
  * preceding layer's bias folded in:  y = act(rms_norm(x + bias) * scale).

@@ -67,3 +67,25 @@ def test_argument_validation():
   import ctypes
   assert lib.emb_rssm_kl_fwd(ctypes.byref(args), None, None, None, None, None, None) == -1
   assert b'classes' in lib.emb_last_error()
+
+
+@pytest.mark.parametrize('rows,L', [(1, 2), (16, 64), (1024, 16), (5, 1)])
+def test_lambda_return_kernel_matches_recurrence(rows, L):
+  """emb_lambda_return against the reference's reversed Python recurrence
+  (dreamerv3/agent.py:482-490)."""
+  g = torch.Generator().manual_seed(rows + L)
+  last = (torch.rand(rows, L, generator=g) < 0.1).float()
+  term = (torch.rand(rows, L, generator=g) < 0.1).float()
+  rew, boot = torch.randn(rows, L, generator=g), torch.randn(rows, L, generator=g)
+  disc, lam = 1 - 1 / 333, 0.95
+  live = (1 - term)[:, 1:] * disc
+  cont = (1 - last)[:, 1:] * lam
+  interm = rew[:, 1:] + (1 - cont) * live * boot[:, 1:]
+  rets = [boot[:, -1]]
+  for t in reversed(range(live.shape[1])):
+    rets.append(interm[:, t] + live[:, t] * cont[:, t] * rets[-1])
+  want = torch.stack(list(reversed(rets))[:-1], 1) if L > 1 else torch.zeros(rows, 0)
+  got = ops.lambda_return(last.cuda(), term.cuda(), rew.cuda(), boot.cuda(), disc, lam).cpu()
+  assert got.shape == want.shape
+  if L > 1:
+    assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
