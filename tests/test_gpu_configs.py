@@ -101,3 +101,42 @@ def test_config3_dreamerv3_on_96x96x1():
   assert rel(mets['loss'], omets['loss']) < 1e-5
   assert rel(outs['replay']['dyn/deter'], oouts['replay']['dyn/deter']) < 1e-5
   assert torch.equal(agent.last_outs['imgact'].cpu(), oo['imgact'])
+
+
+def test_config4_proprio_continuous_actions_driver_and_replay():
+  """DMC-proprio-shaped dummy (vector observations, one f32[6] action in [-1, 1]),
+  many envs, a host policy (the director agent's role): the Driver's stacked
+  observations, masked actions and the replay contents equal the oracle's."""
+  import functools
+  from embodied_b200.envs import synthetic
+  n, L = 64, 6                                   # a slice of the 512 envs
+  mk = lambda i: synthetic.SyntheticProprio(i, length=7 + i % 5)
+  elements.UUID.reset(debug=True)
+  try:
+    replay = embodied.Replay(L, 512, chunksize=16, online=True, seed=0, staging_rows=n)
+    driver = embodied.Driver([functools.partial(mk, i) for i in range(n)], parallel=False)
+    driver.on_step(replay.add)
+    oenvs = [mk(i) for i in range(n)]
+    oreplay = host_oracle.OracleReplay(L, 512, 16, True, 0, ids=itertools.count(1))
+    odriver = host_oracle.OracleDriver(oenvs, oenvs[0].act_space)
+    odriver.callbacks.append(lambda row, w: oreplay.add(row, w))
+
+    def policy(carry, obs, **kw):
+      ori = np.asarray(obs['orientations'].cpu() if hasattr(obs['orientations'], 'cpu') else obs['orientations'])
+      act = np.tanh(ori[:, :6] * 2).astype(np.float32)
+      return carry, {'action': act}, {}
+    driver.reset(lambda k: ())
+    for it in range(20):
+      driver(policy, steps=n)
+      odriver.step(lambda carry, obs: policy(carry, obs))
+      for k, v in odriver.acts.items():
+        assert driver.acts[k].dtype == v.dtype and (np.asarray(driver.acts[k]) == v).all(), (it, k)
+      assert len(replay) == len(oreplay)
+    a, b = replay.sample(16), oreplay.sample(16)
+    assert sorted(a) == sorted(b)
+    for k in b:
+      got = a[k].cpu().numpy()
+      assert got.dtype == b[k].dtype and got.tobytes() == b[k].tobytes(), k
+    assert a['action'].shape == (16, L, 6) and a['orientations'].shape == (16, L, 14)
+  finally:
+    elements.UUID.reset(debug=False)
