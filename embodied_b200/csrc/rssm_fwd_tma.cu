@@ -171,6 +171,21 @@ __device__ __forceinline__ void build_a(__nv_bfloat16* afrag, const float* src, 
   }
 }
 
+// A fragments (shared) of f(y[r][k]) from a [16][n] fp32 tile ALREADY staged in
+// shared memory by TMA (one bulk-copy round trip instead of dependent L2 loads).
+template <typename F>
+__device__ __forceinline__ void convert_staged(__nv_bfloat16* afrag, const float* stage, int n, F f) {
+  const int n4 = n >> 2;
+  for (int i = threadIdx.x; i < kRows * n4; i += kCThreads) {
+    const int r = i / n4, k = (i - r * n4) << 2;
+    const float4 v = reinterpret_cast<const float4*>(stage)[i];
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k)) =
+        __floats2bfloat162_rn(f(r, k, v.x), f(r, k + 1, v.y));
+    *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k + 2)) =
+        __floats2bfloat162_rn(f(r, k + 2, v.z), f(r, k + 3, v.w));
+  }
+}
+
 __global__ void __launch_bounds__(kAllThreads, 1)
 rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -203,12 +218,14 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   ring.empty = bars + 12;
   uint64_t* afull01 = bars + 24;                                 // P4's A: deter slice + x0 landed
   uint64_t* afull2 = bars + 25;                                  // P4's A: x1 landed
+  uint64_t* astage = bars + 26;                                  // fp32 tile of yhid / yobs landed
   ring.data = abase + emb_tma::a_region_bytes(a);
 
   if (tid == 0) {
     for (int i = 0; i < ring.nstages; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], kCWarps); }
     mbar_init(afull01, 1);
     mbar_init(afull2, 1);
+    mbar_init(astage, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -246,8 +263,12 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
 
   // ========================================================== consumer warps
   GridBarrierC bar{a.barrier, 0};
-  uint32_t aphase = 0;
+  uint32_t aphase = 0, sphase = 0;
   const int warp = tid >> 5, lane = tid & 31;
+  // TMA staging of the fp32 tiles the dyngru / obslogit operands are built from:
+  // fragments in the first 32 n bytes of the A region, the fp32 tile behind them
+  const size_t aregion = emb_tma::a_region_bytes(a);
+  const bool stage_hid = aregion >= (size_t)kRows * Dg * 6, stage_obs = aregion >= (size_t)kRows * H * 6;
   const int myrow = ncta - 1 - cta;                  // rows 0..15 are served by the LAST 16 CTAs
   const bool rowcta = myrow >= 0 && myrow < kRows;
   const int gh = p.on_hid ? p.u0_hid / (Dg / 8) : 0;
@@ -362,11 +383,24 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
     if (p.on_gru) {
       const int upg = Dg / 8;
       const int g = p.u0_gru / upg;
+      float* stage = reinterpret_cast<float*>(abase + (size_t)kRows * Dg * 2);
+      if (stage_hid && tid == 0) {          // this group's slice of yhid: 16 row segments by TMA
+        mbar_expect_tx(astage, (uint32_t)kRows * Dg * 4);
+        for (int r = 0; r < kRows; ++r)
+          bulk_g2s(stage + (size_t)r * Dg, yhid + (size_t)r * D + g * Dg, (uint32_t)Dg * 4, astage);
+      }
       if (tid < kRows)
         rstd_a[tid] = rsqrtf(ldcg(a.sumsq + (size_t)t * kRows + tid) / (float)D + a.eps);
       cbar();
-      build_a(afrag, yhid + g * Dg, Dg, D, [&](int r, int k, float v) {
-        return silu_fast(v * (rstd_a[r] * c_shid[k])); });
+      if (stage_hid) {
+        mbar_wait(astage, sphase);
+        sphase ^= 1u;
+        convert_staged(afrag, stage, Dg, [&](int r, int k, float v) {
+          return silu_fast(v * (rstd_a[r] * c_shid[k])); });
+      } else {
+        build_a(afrag, yhid + g * Dg, Dg, D, [&](int r, int k, float v) {
+          return silu_fast(v * (rstd_a[r] * c_shid[k])); });
+      }
       cbar();
       MARK(12)
       EMB_CONSUME(false, ring, p.per_gru, p.ks_gru, afrag4, nullptr, out, true)
@@ -450,14 +484,26 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
     // ------------------------------------------------------------------ P2
     float* logit = a.logit + (size_t)t * RSC;
     if (p.on_log) {
+      float* stage = reinterpret_cast<float*>(abase + (size_t)kRows * H * 2);
+      if (stage_obs && tid == 0) {          // yobs[t]: one contiguous tile by TMA
+        mbar_expect_tx(astage, (uint32_t)kRows * H * 4);
+        bulk_g2s(stage, yobs, (uint32_t)kRows * H * 4, astage);
+      }
       if (tid < kRows) {
         const float rs = rsqrtf(ldcg(a.sumsq_obs + (size_t)t * kRows + tid) / (float)H + a.eps);
         rstd_a[tid] = rs;
         if (cta == 0) a.rstd[(size_t)t * 3 * kRows + 2 * kRows + tid] = rs;
       }
       cbar();
-      build_a(afrag, yobs, H, H, [&](int r, int k, float v) {
-        return silu_fast(v * (rstd_a[r] * c_sobs[k])); });
+      if (stage_obs) {
+        mbar_wait(astage, sphase);
+        sphase ^= 1u;
+        convert_staged(afrag, stage, H, [&](int r, int k, float v) {
+          return silu_fast(v * (rstd_a[r] * c_sobs[k])); });
+      } else {
+        build_a(afrag, yobs, H, H, [&](int r, int k, float v) {
+          return silu_fast(v * (rstd_a[r] * c_sobs[k])); });
+      }
       cbar();
       MARK(14)
       EMB_CONSUME(false, ring, p.per_log, p.ks_log, afrag4, nullptr, out, true)
@@ -623,10 +669,10 @@ int launch_fwd(const emb_rssm_fwd_args& a, void* stream) {
   if (const char* e = getenv("EMB_TMA_STAGES")) stage_cap = atoi(e);
   if (stage_bytes < 8192 || stage_bytes > 65536 || stage_bytes % 1024)
     return emb::fail(-1, "%s: EMB_TMA_STAGE_KB out of range", who);
-  if ((a.D / 16) % rssm_tma::host_ksteps_per_chunk(stage_bytes, per_ph1, true))
-    return emb::fail(-1, "%s: D/16=%d must be a multiple of the %d k-steps per stage of the "
-                     "deter layer", who, a.D / 16,
-                     rssm_tma::host_ksteps_per_chunk(stage_bytes, per_ph1, true));
+  // deter layer (A in global memory): every consumer warp needs >= 1 k16 step in every stage
+  if ((a.D / 16) % (rssm_tma::kCWarps / rssm_tma::tile_groups(per_ph1)))
+    return emb::fail(-1, "%s: D/16=%d must be a multiple of the %d k-lanes of the deter layer", who,
+                     a.D / 16, rssm_tma::kCWarps / rssm_tma::tile_groups(per_ph1));
   emb_rssm_fwd_args copy = a;
   int nstages = stage_cap, maxper = per_gru > per_hid ? per_gru : per_hid;
   if (per_ph1 > maxper) maxper = per_ph1;

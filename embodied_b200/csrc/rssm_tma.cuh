@@ -23,8 +23,8 @@ constexpr int kCThreads = kCWarps * 32;       // 256
 constexpr int kAllThreads = kCThreads + 32;   // + the producer warp
 constexpr int kStageBytesDefault = 24576;   // bytes per ring stage (Ring::stage_bytes)
 constexpr int kMaxPer = 48;                   // n8 tiles per CTA and layer (6 per warp)
-constexpr int kAGlobal = 4;                   // A fragments per warp and stage when A lives in global memory
-constexpr int kADepth = 6;                    // stages of A a warp keeps in flight (cp.async, private ring)
+constexpr int kAGlobal = 6;                   // A fragments per warp and stage when A lives in global memory
+constexpr int kADepth = 4;                    // stages of A a warp keeps in flight (cp.async, private ring)
 constexpr int kAPrivBytes = kCWarps * kADepth * kAGlobal * 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
