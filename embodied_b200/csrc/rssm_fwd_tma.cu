@@ -538,6 +538,21 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
         const int sub = lane / LP, ll = lane % LP, nsub = 32 / LP;
         const float* gum = a.gumbel + (size_t)t * RSC + (size_t)r * SC;
         const float* lrow = logit + (size_t)r * SC;
+        // the row's logits and noise by TMA into the x1 slot of the A region (free
+        // until the next dynhid0 phase): the sampling rounds then read shared memory
+        const bool staged = aregion >= (size_t)part + xpart + (size_t)SC * 8;
+        if (staged) {
+          float* sl = reinterpret_cast<float*>(abase + part + xpart);
+          if (tid == 0) {
+            mbar_expect_tx(astage, (uint32_t)SC * 8);
+            bulk_g2s(sl, lrow, (uint32_t)SC * 4, astage);
+            bulk_g2s(sl + SC, gum, (uint32_t)SC * 4, astage);
+          }
+          mbar_wait(astage, sphase);
+          sphase ^= 1u;
+          lrow = sl;
+          gum = sl + SC;
+        }
 #pragma unroll 1
         for (int sb = warp * nsub; sb < S; sb += kCWarps * nsub) {
           const int sv = sb + sub;
@@ -547,8 +562,8 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
           for (int i = 0; i < 4; ++i) {
             const int c = ll + LP * i;
             const bool on = lat && c < C;
-            lv[i] = on ? ldcg(lrow + (size_t)sv * C + c) : -INFINITY;
-            gv[i] = on ? ldcg(gum + (size_t)sv * C + c) : 0.f;
+            lv[i] = on ? (staged ? lrow[sv * C + c] : ldcg(lrow + (size_t)sv * C + c)) : -INFINITY;
+            gv[i] = on ? (staged ? gum[sv * C + c] : ldcg(gum + (size_t)sv * C + c)) : 0.f;
           }
           float m = fmaxf(fmaxf(lv[0], lv[1]), fmaxf(lv[2], lv[3]));
           for (int o = LP >> 1; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -591,7 +606,7 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
           const int c = gI * kCThreads * 4 + tid * 4;
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
           if (c < H && kn != 0.f) {
-#pragma unroll 8
+#pragma unroll 16
             for (int sv = 0; sv < S; ++sv) {
               const uint2 q = __ldg(reinterpret_cast<const uint2*>(w1 + ((size_t)sv * C + sidx[sv]) * H + c));
               const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
