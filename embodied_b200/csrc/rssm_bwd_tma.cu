@@ -9,7 +9,10 @@
 // (embodied_b200/dreamerv3/scan.py scan_backward).
 //
 //   B1  g_stoch = G_stoch[t] + (keep' * g_y1') @ dynin1^T                        (2.1 M)
-//   B2  g_logit = G_logit[t] + unimix-softmax-jacobian(g_stoch) ; g_xo = g_logit @ obslogit^T (2.1 M)
+//       every CTA owns WHOLE latents, so the unimix-softmax jacobian runs in its epilogue:
+//       g_logit = G_logit[t] + (1-eps) p (g_stoch - sum_c p g_stoch), left as fp32 and as bf16
+//       A fragments (in the g_stoch scratch buffer)
+//   B2  g_xo = g_logit @ obslogit^T ; the operand is ONE TMA bulk copy of those fragments      (2.1 M)
 //   B3  g_deter = G_deter[t] + carry + [g_yobs | keep' * g_y0'] @ [obs0[:D] | dynin0]^T    (16.8 M)
 //       + GRU gate backward in the epilogue -> g_gates
 //   B4  g_h     = g_gates_g @ dyngru[g]^T ; row dots for the rms-norm backward   (25.2 M)
@@ -85,9 +88,13 @@ __device__ __forceinline__ Plan make_plan(const emb_rssm_bwd_args& a) {
   const int tiles[3] = {SC / 8, H / 8, D / 8};
   const int kdim[5] = {H, SC, 2 * H, 3 * Dg, Dg};
   const void* w[5] = {a.wt_in1, a.wt_logit, a.wt_ph1, a.wt_gru, a.wt_hid};
+  int unit1 = a.C;                                  // tiles per B1 unit = lcm(C, 8) / 8: whole latents
+  while (unit1 % 8) unit1 += a.C;
+  unit1 /= 8;
   for (int i = 0; i < 3; ++i) {
-    const int raw = (tiles[i] + ncta - 1) / ncta;
-    p.per[i] = pad_tiles(raw, 1);
+    const int unit = i == 0 ? unit1 : 1;
+    const int raw = (tiles[i] / unit + ncta - 1) / ncta * unit;
+    p.per[i] = pad_tiles(raw, unit);
     p.u0[i] = min(tiles[i], cta * raw);
     p.u1[i] = min(tiles[i], p.u0[i] + raw);
   }
@@ -128,9 +135,11 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   ring.phase = 0;
   ring.full = bars;
   ring.empty = bars + 12;
+  uint64_t* astage = bars + 24;                       // B2's operand (fragments of g_logit) landed
   ring.data = abase + (((size_t)kRows * kmax * 2 + 127) & ~(size_t)127);
   if (tid == 0) {
     for (int i = 0; i < ring.nstages; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], kCWarps); }
+    mbar_init(astage, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -148,7 +157,8 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
 
   // ========================================================== consumer warps
   GridBarrierC bar{a.barrier, 0};
-  const int cta = blockIdx.x, ncta = gridDim.x;
+  uint32_t sphase = 0;
+  __nv_bfloat16* glA = reinterpret_cast<__nv_bfloat16*>(a.g_stoch);   // [SC/16][32][8] fragments of g_logit
 
   // row statistics of a normalised layer at step `ts`: slot 0 x0, 1 x1, 2 xo
   auto load_stats = [&](int ts, int slot, int n, float* rstd, float* coef) {
@@ -194,68 +204,57 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
         return ldcg(keep_next + r) * norm_bwd_elem(gx, y, a.s1[k], rstd_a[r], coef_a[r]); });
       cbar();
       EMB_CONSUME(false, ring, p.per[0], p.ks[0], afrag4, nullptr, out, true)
+      // epilogue: g_stoch -> g_logit for the owned latents (16 threads per row)
       const int ncols = p.per[0] * 8, nvalid = (p.u1[0] - p.u0[0]) * 8;
-      for (int i = tid; i < kRows * ncols; i += kCThreads) {
-        const int r = i / ncols, c = i - r * ncols;
-        if (c >= nvalid) continue;
-        const int col = p.u0[0] * 8 + c;
-        a.g_stoch[(size_t)r * SC + col] = out[i] + a.G_stoch[(size_t)t * RSC + (size_t)r * SC + col];
+      const int r = tid >> 4, l = tid & 15;
+      const float* pr = a.probs + (size_t)t * RSC + (size_t)r * SC;
+      const float* Gs = a.G_stoch + (size_t)t * RSC + (size_t)r * SC;
+      const float* Gl = a.G_logit + (size_t)t * RSC + (size_t)r * SC;
+      const float um = 1.0f - a.unimix;
+      for (int c0 = 0; c0 < nvalid; c0 += C) {         // one latent at a time
+        const int col0 = p.u0[0] * 8 + c0;
+        float dot = 0.f;
+        for (int c = l; c < C; c += 16)
+          dot = fmaf(pr[col0 + c], out[r * ncols + c0 + c] + Gs[col0 + c], dot);
+#pragma unroll
+        for (int o = 8; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        for (int c = l; c < C; c += 16) {
+          const float g = out[r * ncols + c0 + c] + Gs[col0 + c];
+          const float v = Gl[col0 + c] + um * pr[col0 + c] * (g - dot);
+          g_logit[(size_t)r * SC + col0 + c] = v;
+          glA[afrag_index(r, col0 + c)] = __float2bfloat16_rn(v);
+        }
       }
     }
     bar.sync();
 
     // ------------------------------------------------------------------ B2
-    // g_logit = G_logit + (1-eps) p (g_stoch - sum_c p g_stoch) ;  g_xo = g_logit @ obslogit^T
-    {
-      const bool on = p.u0[1] < p.u1[1];
-      const int wrow = ncta - 1 - cta;               // row r of g_logit is also written out by CTA ncta-1-r
-      if (on || (wrow >= 0 && wrow < kRows)) {
-        const float* pr = a.probs + (size_t)t * RSC;
-        const float* Gl = a.G_logit + (size_t)t * RSC;
-        for (int grp = tid; grp < kRows * S; grp += kCThreads) {
-          const int r = grp / S, sv = grp - r * S;
-          const size_t o = (size_t)r * SC + (size_t)sv * C;
-          float dot = 0.f;
-          for (int c = 0; c < C; c += 4) {
-            const float4 pv = *reinterpret_cast<const float4*>(pr + o + c);
-            const float4 g = __ldcg(reinterpret_cast<const float4*>(a.g_stoch + o + c));
-            dot += pv.x * g.x + pv.y * g.y + pv.z * g.z + pv.w * g.w;
-          }
-          for (int c = 0; c < C; c += 4) {
-            const float4 pv = *reinterpret_cast<const float4*>(pr + o + c);
-            const float4 g = __ldcg(reinterpret_cast<const float4*>(a.g_stoch + o + c));
-            const float4 e = *reinterpret_cast<const float4*>(Gl + o + c);
-            const float um = 1.0f - a.unimix;
-            float4 v;
-            v.x = e.x + um * pv.x * (g.x - dot); v.y = e.y + um * pv.y * (g.y - dot);
-            v.z = e.z + um * pv.z * (g.z - dot); v.w = e.w + um * pv.w * (g.w - dot);
-            const int k = sv * C + c;
-            *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k)) = __floats2bfloat162_rn(v.x, v.y);
-            *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, k + 2)) = __floats2bfloat162_rn(v.z, v.w);
-            if (wrow == r) *reinterpret_cast<float4*>(g_logit + o + c) = v;
-          }
-        }
-        if (on) load_stats(t, 2, H, rstd_a, coef_a);       // only rstd is used here
-        cbar();
-        if (on) {
-          EMB_CONSUME(false, ring, p.per[1], p.ks[1], afrag4, nullptr, out, true)
-          const int ncols = p.per[1] * 8, nvalid = (p.u1[1] - p.u0[1]) * 8;
-          for (int i = tid; i < kRows * ncols; i += kCThreads) {
-            const int r = i / ncols, c = i - r * ncols;
-            float prod = 0.f;
-            if (c < nvalid) {
-              const int col = p.u0[1] * 8 + c;
-              const float gx = out[i];
-              g_xo[(size_t)r * H + col] = gx;
-              const float y = yobs[(size_t)r * H + col], sc = a.s_obs[col];
-              prod = gx * dsilu_fast(y * rstd_a[r] * sc) * sc * y;      // g_n * s * y
-            }
-            out[i] = prod;
-          }
-          cbar();
-          add_row_dots(t, 2, ncols, 0, nvalid);
-        }
+    // g_xo = g_logit @ obslogit^T ; row dots of the obs0 norm backward
+    if (p.u0[1] < p.u1[1]) {
+      if (tid == 0) {
+        mbar_expect_tx(astage, (uint32_t)kRows * SC * 2);
+        bulk_g2s(abase, glA, (uint32_t)kRows * SC * 2, astage);
       }
+      load_stats(t, 2, H, rstd_a, coef_a);       // only rstd is used here
+      cbar();
+      mbar_wait(astage, sphase);
+      sphase ^= 1u;
+      EMB_CONSUME(false, ring, p.per[1], p.ks[1], afrag4, nullptr, out, true)
+      const int ncols = p.per[1] * 8, nvalid = (p.u1[1] - p.u0[1]) * 8;
+      for (int i = tid; i < kRows * ncols; i += kCThreads) {
+        const int r = i / ncols, c = i - r * ncols;
+        float prod = 0.f;
+        if (c < nvalid) {
+          const int col = p.u0[1] * 8 + c;
+          const float gx = out[i];
+          g_xo[(size_t)r * H + col] = gx;
+          const float y = yobs[(size_t)r * H + col], sc = a.s_obs[col];
+          prod = gx * dsilu_fast(y * rstd_a[r] * sc) * sc * y;      // g_n * s * y
+        }
+        out[i] = prod;
+      }
+      cbar();
+      add_row_dots(t, 2, ncols, 0, nvalid);
     }
     bar.sync();
 
@@ -392,7 +391,12 @@ int launch_bwd(const emb_rssm_bwd_args& a, void* stream) {
     return emb::fail(-1, "%s: ncta=%d outside [16, %d SMs] (cooperative grid)", who, a.ncta, g_sms_bwd);
   auto cdiv = [](int x, int y) { return (x + y - 1) / y; };
   const int cpg = a.ncta / a.G > 1 ? a.ncta / a.G : 1;
-  const int per[5] = {rssm_tma::pad_tiles(cdiv(SC / 8, a.ncta), 1), rssm_tma::pad_tiles(cdiv(a.H / 8, a.ncta), 1),
+  int unit1 = a.C;
+  while (unit1 % 8) unit1 += a.C;
+  unit1 /= 8;
+  if ((SC / 8) % unit1) return emb::fail(-1, "%s: S*C/8=%d is not a multiple of %d tiles", who, SC / 8, unit1);
+  const int per[5] = {rssm_tma::pad_tiles(cdiv(SC / 8 / unit1, a.ncta) * unit1, unit1),
+                      rssm_tma::pad_tiles(cdiv(a.H / 8, a.ncta), 1),
                       rssm_tma::pad_tiles(cdiv(a.D / 8, a.ncta), 1), rssm_tma::pad_tiles(cdiv(Dg / 8, cpg), 1),
                       rssm_tma::pad_tiles(cdiv(Kh / 8, cpg), 1)};
   int maxper = 0;

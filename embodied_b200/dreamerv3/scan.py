@@ -9,6 +9,7 @@ recurrent state (action branch, token half of obs0, step 0's dynin0/dynin1) is
 computed by the caller with ordinary (B*T)-row GEMMs and passed in.
 """
 import ctypes
+import math
 
 import torch
 
@@ -324,7 +325,10 @@ def pack_bwd(store, cfg, engine, ncta):
   hid_t = hid.permute(2, 0, 1).reshape(Dg, G * hid.shape[1])
   return dict(
       **extra,
-      wt_in1=pack_matrix(m('dyn/dynin1/kernel').t(), lay, ncta),
+      # whole latents per CTA (unit = lcm(C, 8) / 8 tiles) with the TMA engine: the softmax
+      # jacobian then runs in the phase's epilogue
+      wt_in1=pack_matrix(m('dyn/dynin1/kernel').t(), lay, ncta,
+                         unit=(math.lcm(cfg.classes, 8) // 8 if engine == ENG_BF16 else 1)),
       wt_logit=pack_matrix(m('dyn/obslogit/kernel').t(), lay, ncta),
       wt_ph1=pack_matrix(ph1.t(), lay, ncta),
       wt_gru=pack_matrix(gru_t, lay, ncta, groups=G),
