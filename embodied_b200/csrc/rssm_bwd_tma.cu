@@ -30,6 +30,19 @@
 #include "rssm_common.cuh"
 #include "rssm_tma.cuh"
 
+namespace emb_tma {
+// A region of the backward kernel: the widest operand (3Dg, 2H or SC columns of bf16
+// fragments), B3's [U | g_y0' | Y] (6H bytes per row) and B5's [U | Y] (4Dg).
+__host__ __device__ inline size_t bwd_a_region_bytes(int D, int G, int H, int SC) {
+  const int Dg = D / G;
+  size_t n = (size_t)rssm::kRows * 3 * Dg * 2;
+  const size_t cands[4] = {(size_t)rssm::kRows * 2 * H * 2, (size_t)rssm::kRows * SC * 2,
+                           (size_t)rssm::kRows * H * 6, (size_t)rssm::kRows * Dg * 4};
+  for (int i = 0; i < 4; ++i) if (cands[i] > n) n = cands[i];
+  return (n + 127) & ~(size_t)127;
+}
+}  // namespace emb_tma
+
 namespace {
 
 using namespace rssm;
@@ -73,6 +86,29 @@ __device__ __forceinline__ void build1(__nv_bfloat16* afrag, int koff, const flo
         __floats2bfloat162_rn(f(r, k, v.x), f(r, k + 1, v.y));
     *reinterpret_cast<__nv_bfloat162*>(afrag + afrag_index(r, koff + k + 2)) =
         __floats2bfloat162_rn(f(r, k + 2, v.z), f(r, k + 3, v.w));
+  }
+}
+
+// A = U - coef[row] * Y on `n16` 16-byte fragment vectors in shared memory (in place in
+// U).  Fragment layout (rssm_common.cuh afrag_index): within a k16 block lane = vec % 32,
+// the four 32-bit registers hold rows (lane/4, lane/4 + 8, lane/4, lane/4 + 8).
+__device__ __forceinline__ void combine_frags(uint4* u, const uint4* y, int n16, const float* coef) {
+  for (int i = threadIdx.x; i < n16; i += kCThreads) {
+    const int r0 = (i & 31) >> 2;
+    const float c0 = coef[r0], c1 = coef[r0 + 8];
+    uint4 uv = u[i];
+    const uint4 yv = y[i];
+    uint32_t* up = reinterpret_cast<uint32_t*>(&uv);
+    const uint32_t* yp = reinterpret_cast<const uint32_t*>(&yv);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float c = (q & 1) ? c1 : c0;
+      const float2 uf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&up[q]));
+      const float2 yf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yp[q]));
+      const __nv_bfloat162 o = __floats2bfloat162_rn(uf.x - c * yf.x, uf.y - c * yf.y);
+      up[q] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    u[i] = uv;
   }
 }
 
@@ -125,9 +161,6 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   unsigned char* abase = reinterpret_cast<unsigned char*>(st + 64);
   __nv_bfloat16* afrag = reinterpret_cast<__nv_bfloat16*>(abase);
   uint4* afrag4 = reinterpret_cast<uint4*>(abase);
-  int kmax = 3 * Dg;
-  if (2 * H > kmax) kmax = 2 * H;
-  if (SC > kmax) kmax = SC;
   Ring ring;
   ring.nstages = a.hoist_x2 & 0xff;
   ring.stage_bytes = (a.hoist_x2 >> 16) * 1024;
@@ -136,7 +169,7 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   ring.full = bars;
   ring.empty = bars + 12;
   uint64_t* astage = bars + 24;                       // B2's operand (fragments of g_logit) landed
-  ring.data = abase + (((size_t)kRows * kmax * 2 + 127) & ~(size_t)127);
+  ring.data = abase + emb_tma::bwd_a_region_bytes(D, G, H, SC);
   if (tid == 0) {
     for (int i = 0; i < ring.nstages; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], kCWarps); }
     mbar_init(astage, 1);
@@ -159,6 +192,18 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   GridBarrierC bar{a.barrier, 0};
   uint32_t sphase = 0;
   __nv_bfloat16* glA = reinterpret_cast<__nv_bfloat16*>(a.g_stoch);   // [SC/16][32][8] fragments of g_logit
+  // bf16 fragment hand-offs between phases (a.frag_scratch): producers' epilogues leave the
+  // next phase's A operand ready, consumers fetch it with TMA bulk copies.  For a normalised
+  // layer the operand is g_y = U - coef * Y (U = rstd s g_n, Y = y): U and Y are written
+  // before the row dots (coef) are complete and combined in shared memory afterwards.
+  __nv_bfloat16* ggA = reinterpret_cast<__nv_bfloat16*>(a.frag_scratch);   // [G][3Dg] x 16 rows: g_gates
+  __nv_bfloat16* UhA = ggA + 3 * RD;                                       // [D]   dynhid0 norm: U
+  __nv_bfloat16* YhA = UhA + RD;                                           // [D]   dynhid0 norm: Y
+  __nv_bfloat16* UoA = YhA + RD;                                           // [H]   obs0 norm: U
+  __nv_bfloat16* YoA = UoA + RH;                                           // [H]   obs0 norm: Y
+  __nv_bfloat16* gy0A = YoA + RH;                                          // [H]   keep' * g_y0'
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int myrow = ncta - 1 - cta;                  // rows 0..15 are served by the LAST 16 CTAs
 
   // row statistics of a normalised layer at step `ts`: slot 0 x0, 1 x1, 2 xo
   auto load_stats = [&](int ts, int slot, int n, float* rstd, float* coef) {
@@ -197,6 +242,23 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     float* g_logit = a.g_logit + (size_t)t * RSC;
 
     // ------------------------------------------------------------------ B1
+    // (16 otherwise idle CTAs prepare row r of keep' * g_y0' -- the second half of B3's
+    // operand -- as fragments; g_x0[t+1] and its row dot are complete since the last barrier)
+    if (myrow >= 0 && myrow < kRows) {
+      const int r = myrow;
+      const float rs = a.rstd[(size_t)(t + 1) * 3 * kRows + r];
+      const float cf = rs * rs * rs * ldcg(a.dots + ((size_t)(t + 1) * 4 + 0) * kRows + r) / (float)H;
+      const float kn = ldcg(keep_next + r);
+      for (int k = tid * 4; k < H; k += kCThreads * 4) {
+        const float4 gx = __ldcg(reinterpret_cast<const float4*>(gx0n + (size_t)r * H + k));
+        const float4 y = __ldcg(reinterpret_cast<const float4*>(y0n + (size_t)r * H + k));
+        const float4 sc = *reinterpret_cast<const float4*>(a.s0 + k);
+        *reinterpret_cast<__nv_bfloat162*>(gy0A + afrag_index(r, k)) = __floats2bfloat162_rn(
+            kn * norm_bwd_elem(gx.x, y.x, sc.x, rs, cf), kn * norm_bwd_elem(gx.y, y.y, sc.y, rs, cf));
+        *reinterpret_cast<__nv_bfloat162*>(gy0A + afrag_index(r, k + 2)) = __floats2bfloat162_rn(
+            kn * norm_bwd_elem(gx.z, y.z, sc.z, rs, cf), kn * norm_bwd_elem(gx.w, y.w, sc.w, rs, cf));
+      }
+    }
     if (p.u0[0] < p.u1[0]) {
       load_stats(t + 1, 1, H, rstd_a, coef_a);
       cbar();
@@ -249,7 +311,10 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
           const float gx = out[i];
           g_xo[(size_t)r * H + col] = gx;
           const float y = yobs[(size_t)r * H + col], sc = a.s_obs[col];
-          prod = gx * dsilu_fast(y * rstd_a[r] * sc) * sc * y;      // g_n * s * y
+          const float gn = gx * dsilu_fast(y * rstd_a[r] * sc);
+          prod = gn * sc * y;                                       // g_n * s * y
+          UoA[afrag_index(r, col)] = __float2bfloat16_rn(rstd_a[r] * sc * gn);
+          YoA[afrag_index(r, col)] = __float2bfloat16_rn(y);
         }
         out[i] = prod;
       }
@@ -260,13 +325,18 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
 
     // ------------------------------------------------------------------ B3
     if (p.u0[2] < p.u1[2]) {
+      // operand [g_yobs | keep' g_y0']: U_obs, keep' g_y0' and Y_obs by TMA (Y behind the 2H columns)
+      if (tid == 0) {
+        mbar_expect_tx(astage, (uint32_t)RH * 2 * 3);
+        bulk_g2s(abase, UoA, (uint32_t)RH * 2, astage);
+        bulk_g2s(abase + RH * 2, gy0A, (uint32_t)RH * 2, astage);
+        bulk_g2s(abase + RH * 4, YoA, (uint32_t)RH * 2, astage);
+      }
       load_stats(t, 2, H, rstd_a, coef_a);
-      load_stats(t + 1, 0, H, rstd_b, coef_b);
       cbar();
-      build2(afrag, 0, g_xo, H, yobs, H, H, [&](int r, int k, float gx, float y) {
-        return norm_bwd_elem(gx, y, a.s_obs[k], rstd_a[r], coef_a[r]); });
-      build2(afrag, H, gx0n, H, y0n, H, H, [&](int r, int k, float gx, float y) {
-        return ldcg(keep_next + r) * norm_bwd_elem(gx, y, a.s0[k], rstd_b[r], coef_b[r]); });
+      mbar_wait(astage, sphase);
+      sphase ^= 1u;
+      combine_frags(afrag4, reinterpret_cast<const uint4*>(abase + RH * 4), (H / 16) * 32, coef_a);
       cbar();
       EMB_CONSUME(false, ring, p.per[2], p.ks[2], afrag4, nullptr, out, true)
       const int ncols = p.per[2] * 8, nvalid = (p.u1[2] - p.u0[2]) * 8;
@@ -283,9 +353,14 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
         const float g_rc = g_c * (1.0f - cand * cand);
         const int g = col / Dg, jj = col - g * Dg;
         float* gg = g_gates + (size_t)r * 3 * D + (size_t)g * 3 * Dg + jj;
-        gg[0] = g_rc * cpre * rs * (1.0f - rs);          // reset gate, pre-sigmoid
-        gg[Dg] = g_rc * rs;                              // candidate, pre-tanh
-        gg[2 * Dg] = g_u * up * (1.0f - up);             // update gate, pre-sigmoid
+        const float g0 = g_rc * cpre * rs * (1.0f - rs);  // reset gate, pre-sigmoid
+        const float g1 = g_rc * rs;                       // candidate, pre-tanh
+        const float g2 = g_u * up * (1.0f - up);          // update gate, pre-sigmoid
+        gg[0] = g0; gg[Dg] = g1; gg[2 * Dg] = g2;
+        __nv_bfloat16* ga = ggA + (size_t)g * 3 * Dg * kRows;         // B4's operand, group g
+        ga[afrag_index(r, jj)] = __float2bfloat16_rn(g0);
+        ga[afrag_index(r, Dg + jj)] = __float2bfloat16_rn(g1);
+        ga[afrag_index(r, 2 * Dg + jj)] = __float2bfloat16_rn(g2);
       }
     }
     bar.sync();
@@ -294,10 +369,14 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     if (p.u0[3] < p.u1[3]) {
       const int tpg = Dg / 8;
       const int g = p.u0[3] / tpg;
+      if (tid == 0) {
+        mbar_expect_tx(astage, (uint32_t)kRows * 3 * Dg * 2);
+        bulk_g2s(abase, ggA + (size_t)g * 3 * Dg * kRows, (uint32_t)kRows * 3 * Dg * 2, astage);
+      }
       if (tid < kRows) rstd_a[tid] = rsqrtf(a.sumsq[(size_t)t * kRows + tid] / (float)D + a.eps);
-      const float* src = g_gates + (size_t)g * 3 * Dg;
-      build1(afrag, 0, src, 3 * Dg, 3 * D, [&](int, int, float v) { return v; });
       cbar();
+      mbar_wait(astage, sphase);
+      sphase ^= 1u;
       EMB_CONSUME(false, ring, p.per[3], p.ks[3], afrag4, nullptr, out, true)
       const int ncols = p.per[3] * 8, nvalid = (p.u1[3] - p.u0[3]) * 8;
       for (int i = tid; i < kRows * ncols; i += kCThreads) {
@@ -309,7 +388,10 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
           const float gh = out[i];
           g_h[at] = gh;
           const float y = yhid[at], sc = a.s_hid[col];
-          prod = gh * dsilu_fast(y * rstd_a[r] * sc) * sc * y;    // g_n * s * y
+          const float gn = gh * dsilu_fast(y * rstd_a[r] * sc);
+          prod = gn * sc * y;                                     // g_n * s * y
+          UhA[afrag_index(r, col)] = __float2bfloat16_rn(rstd_a[r] * sc * gn);
+          YhA[afrag_index(r, col)] = __float2bfloat16_rn(y);
         }
         out[i] = prod;
       }
@@ -329,10 +411,15 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
         rstd_b[tid] = a.rstd[(size_t)t * 3 * kRows + tid];             // y0[t]
         coef_b[tid] = a.rstd[(size_t)t * 3 * kRows + kRows + tid];     // y1[t] (rstd, not a coef)
       }
+      if (tid == 0) {       // this group's slices of U and Y (fragment order: contiguous)
+        mbar_expect_tx(astage, (uint32_t)kRows * Dg * 2 * 2);
+        bulk_g2s(abase, UhA + (size_t)g * Dg * kRows, (uint32_t)kRows * Dg * 2, astage);
+        bulk_g2s(abase + (size_t)kRows * Dg * 2, YhA + (size_t)g * Dg * kRows, (uint32_t)kRows * Dg * 2, astage);
+      }
       cbar();
-      build2(afrag, 0, g_h + (size_t)g * Dg, D, yhid + (size_t)g * Dg, D, Dg,
-             [&](int r, int k, float gx, float y) {
-        return norm_bwd_elem(gx, y, a.s_hid[g * Dg + k], rstd_a[r], coef_a[r]); });
+      mbar_wait(astage, sphase);
+      sphase ^= 1u;
+      combine_frags(afrag4, reinterpret_cast<const uint4*>(abase + (size_t)kRows * Dg * 2), (Dg / 16) * 32, coef_a);
       cbar();
       EMB_CONSUME(false, ring, p.per[4], p.ks[4], afrag4, nullptr, out, true)
       const int ncols = p.per[4] * 8, nvalid = (p.u1[4] - p.u0[4]) * 8;
@@ -411,16 +498,14 @@ int launch_bwd(const emb_rssm_bwd_args& a, void* stream) {
   if (const char* e = getenv("EMB_TMA_STAGES")) stage_cap = atoi(e);
   if (stage_bytes < 8192 || stage_bytes > 65536 || stage_bytes % 1024)
     return emb::fail(-1, "%s: EMB_TMA_STAGE_KB out of range", who);
-  int kmax = 3 * Dg;
-  if (2 * a.H > kmax) kmax = 2 * a.H;
-  if (SC > kmax) kmax = SC;
   size_t fixed = 256 + sizeof(float) * (rssm::kRows * maxper * 8 + 64);
-  fixed += ((size_t)rssm::kRows * kmax * 2 + 127) & ~(size_t)127;
+  fixed += bwd_a_region_bytes(a.D, a.G, a.H, SC);
   const size_t cap = 227 * 1024 - 128;
   int n = fixed + 2 * (size_t)stage_bytes <= cap ? (int)((cap - fixed) / stage_bytes) : 0;
   if (n > 12) n = 12;
   if (stage_cap > 0 && stage_cap < n) n = stage_cap;
-  if (n < 2) return emb::fail(-1, "%s: no room for the weight ring (A operand of %d columns)", who, kmax);
+  if (n < 2) return emb::fail(-1, "%s: no room for the weight ring next to the A operands", who);
+  if (!a.frag_scratch) return emb::fail(-1, "%s: the bf16 TMA engine needs frag_scratch", who);
   const size_t smem = fixed + (size_t)n * stage_bytes + 128;
   emb_rssm_bwd_args copy = a;
   copy.hoist_x2 = n | (maxper << 8) | ((stage_bytes / 1024) << 16);      // kernel-side ring configuration

@@ -300,7 +300,7 @@ class BwdArgs(ctypes.Structure):
           'keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates', 'sumsq', 'probs', 'rstd',
           'G_deter', 'G_logit', 'G_stoch',
           'g_xo', 'g_logit', 'g_gates', 'g_h', 'g_x0', 'g_x1', 'g_x2',
-          'g_stoch', 'gd_carry', 'gd_tmp', 'dots', 'barrier')])
+          'g_stoch', 'gd_carry', 'gd_tmp', 'dots', 'barrier', 'frag_scratch')])
 
 
 @torch.no_grad()
@@ -386,7 +386,8 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
       g_h=empty(T, ROWS, D), g_x0=zeros(T + 1, ROWS, H), g_x1=zeros(T + 1, ROWS, H),
       g_x2=zeros(T, ROWS, H), g_stoch=empty(ROWS, SC), gd_carry=zeros(ROWS, D),
       gd_tmp=empty(ROWS, D), dots=zeros(T + 1, 4, ROWS),
-      barrier=torch.zeros(4, dtype=torch.int32, device=dev))
+      barrier=torch.zeros(4, dtype=torch.int32, device=dev),
+      frag_scratch=torch.zeros(ROWS * (5 * D + 3 * H), dtype=torch.bfloat16, device=dev))
   vec = dict(s0=m('dyn/dynin0norm/scale'), s1=m('dyn/dynin1norm/scale'),
              s_hid=m('dyn/dynhid0norm/scale'), s_obs=m('dyn/obs0norm/scale'))
   saved = {k: sv[k] for k in ('keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates',

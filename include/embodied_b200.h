@@ -231,6 +231,8 @@ typedef struct emb_rssm_bwd_args {
   float* gd_tmp;         /* [16][D] */
   float* dots;           /* [T+1][4][16] ZEROED: row dots of the norm backward of x0, x1, xo, h */
   uint32_t* barrier;     /* one ZEROED u32 */
+  void* frag_scratch;    /* engine 1: 16 * (5*D + 3*H) bf16 -- operand fragments handed from
+                          * one phase's epilogue to the next phase's TMA fetch */
 } emb_rssm_bwd_args;
 
 int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream);
