@@ -261,3 +261,80 @@ extern "C" int emb_lambda_return(const float* last, const float* term, const flo
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;
 }
+
+// ------------------------------------------------------------- one-hot sampling
+// emb_onehot_sample: stoch = one_hot(argmax(log(unimix(softmax(logit))) + gumbel))
+// (embodied/jax/outs.py:210-216,252-270, forward value of the straight-through
+// sample) for the no-gradient paths (imagination, policy): one launch instead of
+// softmax / unimix / log / add / argmax / one_hot / casts.  One CTA per row, one warp
+// per latent (warp-shuffle max / sum / arg-max over the classes).
+namespace {
+__global__ void __launch_bounds__(1024)
+onehot_sample_kernel(const void* __restrict__ logit, int dtype, int64_t logit_stride,
+                     const float* __restrict__ gumbel, int S, int C, float unimix,
+                     void* __restrict__ out, int out_dtype, int64_t out_stride,
+                     int32_t* __restrict__ index) {
+  const int row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int s = warp; s < S; s += nwarps) {
+    const int64_t off = (int64_t)row * logit_stride + (int64_t)s * C;
+    const float* gn = gumbel + ((int64_t)row * S + s) * C;
+    float x[kMaxPerLane];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = c < C ? load_logit(logit, dtype, off + c) : -INFINITY;
+      m = fmaxf(m, x[i]);
+    }
+    m = warp_max(m);
+    float e[kMaxPerLane], z = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) { e[i] = lane + 32 * i < C ? expf(x[i] - m) : 0.f; z += e[i]; }
+    z = warp_sum(z);
+    float best = -INFINITY;
+    int arg = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        const float v = logf((1.0f - unimix) * (e[i] / z) + unimix / (float)C) + gn[c];
+        if (v > best) { best = v; arg = c; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
+      if (ob > best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (index && lane == 0) index[(int64_t)row * S + s] = arg;
+    const int64_t oo = (int64_t)row * out_stride + (int64_t)s * C;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        const float v = c == arg ? 1.f : 0.f;
+        if (out_dtype) reinterpret_cast<__nv_bfloat16*>(out)[oo + c] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(out)[oo + c] = v;
+      }
+    }
+  }
+}
+}  // namespace
+
+extern "C" int emb_onehot_sample(const void* logit, int32_t dtype, int64_t logit_stride,
+                                 const float* gumbel, int64_t rows, int32_t S, int32_t C,
+                                 float unimix, void* out, int32_t out_dtype, int64_t out_stride,
+                                 int32_t* index, void* stream) {
+  const char* who = "emb_onehot_sample";
+  if (rows < 0 || S < 1 || C < 1 || C > 32 * kMaxPerLane)
+    return emb::fail(-1, "%s: rows=%lld S=%d C=%d", who, (long long)rows, S, C);
+  if ((dtype | out_dtype) & ~1) return emb::fail(-1, "%s: dtype must be 0 (f32) or 1 (bf16)", who);
+  if (rows == 0) return 0;
+  onehot_sample_kernel<<<(unsigned)rows, threads_for(S), 0, (cudaStream_t)stream>>>(
+      logit, dtype, logit_stride, gumbel, S, C, unimix, out, out_dtype, out_stride, index);
+  emb::count_launch();
+  if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
+  return 0;
+}

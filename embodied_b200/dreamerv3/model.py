@@ -210,12 +210,20 @@ class Model:
     return (1 - self.cfg.unimix) * probs + self.cfg.unimix / probs.shape[-1]
 
   def sample_stoch(self, logit, gumbel):                     # outs.py:252-270
+    if (self.fused_norm and not torch.is_grad_enabled() and logit.is_cuda and logit.dim() == 3
+        and logit.shape[-1] <= 128 and logit.dtype in (f32, torch.bfloat16)):
+      return ops.onehot_sample(logit, gumbel, self.cfg.unimix, self.cd)   # one launch
     probs = self.unimix(logit)
     index = torch.argmax(torch.log(probs) + gumbel, -1)
     value = F.one_hot(index, probs.shape[-1]).to(f32)
     return (value + (probs - probs.detach())).to(self.cd)
 
   def act_branch(self, action, reset):
+    if not torch.is_grad_enabled() and action.dim() == 1:
+      # one-hot @ kernel is a row lookup; rows of reset steps see a zero action (bias only)
+      w, b = self.W('dyn/dynin2/kernel'), self.W('dyn/dynin2/bias')
+      y = w[action.long()] * (~reset)[:, None].to(w.dtype) + b
+      return self.norm(y, 'dyn/dynin2norm')
     a = self.action_embed(action, reset)
     return self.norm(self.dense(a, 'dyn/dynin2'), 'dyn/dynin2norm')
 

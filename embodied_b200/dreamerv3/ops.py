@@ -39,6 +39,8 @@ def _lib_bound():
     lib.emb_rmsnorm_grouped_fwd.restype = ctypes.c_int
     lib.emb_gru_gates_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]
     lib.emb_gru_gates_fwd.restype = ctypes.c_int
+    lib.emb_onehot_sample.argtypes = [_vp, _i32, _i64, _vp, _i64, _i32, _i32, _fl, _vp, _i32, _i64, _vp, _vp]
+    lib.emb_onehot_sample.restype = ctypes.c_int
     lib.emb_lambda_return.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _fl, _fl, _vp]
     lib.emb_lambda_return.restype = ctypes.c_int
     _bound = True
@@ -354,3 +356,19 @@ def lambda_return(last, term, rew, boot, disc, lam):
       last.data_ptr(), term.data_ptr(), rew.data_ptr(), boot.data_ptr(), ret.data_ptr(), rows, L,
       float(disc), float(lam), stream))
   return ret
+
+
+@torch.no_grad()
+def onehot_sample(logit, gumbel, unimix, out_dtype):
+  """logit (n, S, C) fp32 / bf16, gumbel (n, S, C) fp32 -> one-hot (n, S, C) in
+  `out_dtype`: the sampled value of outs.OneHot (no straight-through term)."""
+  lib = _lib_bound()
+  n, S, C = logit.shape
+  logit = logit.contiguous()
+  gumbel = gumbel.to(f32).contiguous()
+  out = torch.empty((n, S, C), dtype=out_dtype, device=logit.device)
+  stream = torch.cuda.current_stream(logit.device).cuda_stream
+  _lib.check(lib.emb_onehot_sample(
+      logit.data_ptr(), _dtype_code(logit), S * C, gumbel.data_ptr(), n, S, C, float(unimix),
+      out.data_ptr(), _dtype_code(out), S * C, None, stream))
+  return out

@@ -261,6 +261,15 @@ int emb_rssm_kl_fwd(const emb_rssm_kl_args* args, float* dyn, float* rep, float*
 int emb_rssm_kl_bwd(const emb_rssm_kl_args* args, const float* kl_raw, const float* g_dyn,
                     const float* g_rep, float* g_post, float* g_prior, void* stream);
 
+/* Forward value of the straight-through one-hot sample (embodied/jax/outs.py:210-216,
+ * 252-270) for the no-gradient paths: out[row][s*C + c] = (c == argmax_c(log(unimix(
+ * softmax(logit[row][s]))) + gumbel[row][s][c])).  logit fp32 / bf16 with `logit_stride`
+ * elements between rows, gumbel dense fp32, out fp32 / bf16 with `out_stride`; index
+ * (optional) int32 [rows][S]. */
+int emb_onehot_sample(const void* logit, int32_t dtype, int64_t logit_stride, const float* gumbel,
+                      int64_t rows, int32_t S, int32_t C, float unimix, void* out,
+                      int32_t out_dtype, int64_t out_stride, int32_t* index, void* stream);
+
 /* The lambda-return recurrence (dreamerv3/agent.py:482-490) as one launch, one thread
  * per row.  last / term / rew / boot: fp32 [rows][length]; ret: fp32 [rows][length-1]. */
 int emb_lambda_return(const float* last, const float* term, const float* rew, const float* boot,

@@ -89,3 +89,18 @@ def test_lambda_return_kernel_matches_recurrence(rows, L):
   assert got.shape == want.shape
   if L > 1:
     assert float((got - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.parametrize('n,S,C', [(3, 8, 4), (256, 32, 64), (5, 16, 96)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_onehot_sample_kernel_matches_formula(n, S, C, dtype):
+  """emb_onehot_sample against argmax(log(unimix(softmax(logit))) + gumbel)
+  (embodied/jax/outs.py:210-216,252-270)."""
+  g = torch.Generator().manual_seed(n + S + C)
+  logit = (torch.randn(n, S, C, generator=g) * 2).to(dtype)
+  gumbel = do.make_noise(do.tiny_config(stoch=S, classes=C), n, 1, seed=3)['observe'][:, 0]
+  lg = do.unimix_logits(logit.float(), 0.01)
+  want = torch.nn.functional.one_hot(torch.argmax(lg + gumbel, -1), C).float()
+  got = ops.onehot_sample(logit.cuda(), gumbel.cuda(), 0.01, dtype)
+  assert got.dtype == dtype and got.shape == (n, S, C)
+  assert torch.equal(got.float().cpu(), want)
