@@ -144,6 +144,20 @@ __device__ __forceinline__ void produce(Ring& r, const unsigned char* blk, int p
   }
 }
 
+// explicit shared-space loads: inside the non-inlined consume() the compiler cannot prove
+// that the ring / operand pointers are shared memory and would emit generic loads
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 r;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
 __device__ __forceinline__ void mma_bf16_nv(float (&c)[4], const uint4& a, const uint2& b) {
   asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 "
       "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -191,6 +205,7 @@ __device__ __noinline__ uint32_t consume(Ring r, int per, int ksteps, const uint
   int stage = r.stage;
   uint32_t phase = r.phase;
   const int nstages = r.nstages;
+  const uint32_t data_s = smem_u32(r.data);
   const int total = (ksteps - kl + KW - 1) / KW;                     // this warp's k16 steps in all
   const int per_chunk = kc / KW;
   if (A_GLOBAL) {
@@ -214,18 +229,18 @@ __device__ __noinline__ uint32_t consume(Ring r, int per, int ksteps, const uint
       issue(c + kADepth - 1);
       cp_async_wait<kADepth - 1>();
       mbar_wait(&r.full[stage], phase);
-      const unsigned char* st = r.data + (size_t)stage * r.stage_bytes + wofs;
-      const unsigned char* as = mine + cslot * slot_bytes;
+      const uint32_t st = data_s + (uint32_t)stage * (uint32_t)r.stage_bytes + wofs;
+      const uint32_t as = smem_u32(mine) + cslot * slot_bytes;
 #pragma unroll
       for (int i = 0; i < kAGlobal; ++i) {
         // fragments beyond the chunk are zero: the multiply is harmless, its B
         // address is clamped into the stage
         const bool on = i < per_chunk && c * per_chunk + i < total;
-        const uint4 av = on ? *reinterpret_cast<const uint4*>(as + i * 512) : make_uint4(0, 0, 0, 0);
-        const uint2* bp = reinterpret_cast<const uint2*>(st + (size_t)(on ? i : 0) * kstride);
+        const uint4 av = on ? lds_u4(as + i * 512) : make_uint4(0, 0, 0, 0);
+        const uint32_t bp = st + (uint32_t)(on ? i : 0) * kstride;
         uint2 b[TW];
 #pragma unroll
-        for (int j = 0; j < TW; ++j) b[j] = bp[j * 32];
+        for (int j = 0; j < TW; ++j) b[j] = lds_u2(bp + j * 256);
 #pragma unroll
         for (int j = 0; j < TW; ++j) mma_bf16_nv(acc[j], av, b[j]);
       }
@@ -239,15 +254,15 @@ __device__ __noinline__ uint32_t consume(Ring r, int per, int ksteps, const uint
     for (int j0 = 0; j0 * KW < ksteps; j0 += per_chunk) {
       const int n = min(per_chunk, total - j0);                      // <= 0 for a lane past the tail
       mbar_wait(&r.full[stage], phase);
-      const unsigned char* st = r.data + (size_t)stage * r.stage_bytes + wofs;
-      const uint4* a0 = ap + (size_t)j0 * astride;
+      const uint32_t st = data_s + (uint32_t)stage * (uint32_t)r.stage_bytes + wofs;
+      const uint32_t a0 = smem_u32(ap) + (uint32_t)j0 * (uint32_t)astride * 16u;
 #pragma unroll 2
       for (int i = 0; i < n; ++i) {
-        const uint4 av = a0[(size_t)i * astride];
-        const uint2* bp = reinterpret_cast<const uint2*>(st + (size_t)i * kstride);
+        const uint4 av = lds_u4(a0 + (uint32_t)i * (uint32_t)astride * 16u);
+        const uint32_t bp = st + (uint32_t)i * kstride;
         uint2 b[TW];
 #pragma unroll
-        for (int j = 0; j < TW; ++j) b[j] = bp[j * 32];
+        for (int j = 0; j < TW; ++j) b[j] = lds_u2(bp + j * 256);
 #pragma unroll
         for (int j = 0; j < TW; ++j) mma_bf16_nv(acc[j], av, b[j]);
       }
