@@ -112,6 +112,8 @@ __device__ __forceinline__ void combine_frags(uint4* u, const uint4* y, int n16,
   }
 }
 
+constexpr int kRowGroups = 4;         // a row CTA holds H <= 4096 columns, 4 per thread and group
+
 struct Plan {
   int per[5], ks[5], u0[5], u1[5];        // B1..B5: padded tiles per CTA, k16 steps, owned tiles
   const unsigned char* blk[5];
@@ -202,6 +204,9 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   __nv_bfloat16* UoA = YhA + RD;                                           // [H]   obs0 norm: U
   __nv_bfloat16* YoA = UoA + RH;                                           // [H]   obs0 norm: Y
   __nv_bfloat16* gy0A = YoA + RH;                                          // [H]   keep' * g_y0'
+  __nv_bfloat16* gy1A = gy0A + RH;                                         // [H]   keep' * g_y1'
+  float* gxp = a.gx_part;                            // [G][16][2H] per-group partials of g_[x0|x1]
+  unsigned* row_flag = a.barrier + 1;                // rows whose g_y0' / g_y1' fragments are ready
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int myrow = ncta - 1 - cta;                  // rows 0..15 are served by the LAST 16 CTAs
 
@@ -223,7 +228,90 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     if (l == 0 && c0 < c1) atomicAdd(a.dots + ((size_t)ts * 4 + slot) * kRows + r, sum);
   };
 
+  // Row r of the gradients that came back through dynhid0 at step `ts`: sum the per-group
+  // partials (no atomics), store g_x0 / g_x1 [ts] for the host, and -- with the complete row
+  // in registers, so the row dots need no cross-CTA reduction either -- leave keep * g_y0 and
+  // keep * g_y1 (rms-norm + silu backward) as operand fragments for B3 and B1.
+  auto row_work = [&](int ts, bool frags) {
+    const int r = myrow;
+    const float* part0 = gxp + (size_t)r * 2 * H;
+    const size_t gstride = (size_t)kRows * 2 * H;
+    const float rs0 = a.rstd[(size_t)ts * 3 * kRows + r], rs1 = a.rstd[(size_t)ts * 3 * kRows + kRows + r];
+    const float kn = ldcg(a.keep + (size_t)ts * kRows + r);
+    float d0 = 0.f, d1 = 0.f;
+    float4 gx0[kRowGroups], gx1[kRowGroups], y0v[kRowGroups], y1v[kRowGroups];
+#pragma unroll
+    for (int q = 0; q < kRowGroups; ++q) {
+      const int k = q * kCThreads * 4 + tid * 4;
+      gx0[q] = gx1[q] = y0v[q] = y1v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < H) {
+        for (int g = 0; g < G; ++g) {
+          const float4 u = __ldcg(reinterpret_cast<const float4*>(part0 + g * gstride + k));
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(part0 + g * gstride + H + k));
+          gx0[q].x += u.x; gx0[q].y += u.y; gx0[q].z += u.z; gx0[q].w += u.w;
+          gx1[q].x += v.x; gx1[q].y += v.y; gx1[q].z += v.z; gx1[q].w += v.w;
+        }
+        *reinterpret_cast<float4*>(a.g_x0 + (size_t)ts * RH + (size_t)r * H + k) = gx0[q];
+        *reinterpret_cast<float4*>(a.g_x1 + (size_t)ts * RH + (size_t)r * H + k) = gx1[q];
+        if (frags) {
+          y0v[q] = *reinterpret_cast<const float4*>(a.y0 + (size_t)ts * RH + (size_t)r * H + k);
+          y1v[q] = *reinterpret_cast<const float4*>(a.y1 + (size_t)ts * RH + (size_t)r * H + k);
+          const float4 s0 = *reinterpret_cast<const float4*>(a.s0 + k);
+          const float4 s1 = *reinterpret_cast<const float4*>(a.s1 + k);
+          // g_n * s * y, g_n = g_x * silu'(y * rstd * s)
+          d0 += gx0[q].x * dsilu_fast(y0v[q].x * rs0 * s0.x) * s0.x * y0v[q].x +
+                gx0[q].y * dsilu_fast(y0v[q].y * rs0 * s0.y) * s0.y * y0v[q].y +
+                gx0[q].z * dsilu_fast(y0v[q].z * rs0 * s0.z) * s0.z * y0v[q].z +
+                gx0[q].w * dsilu_fast(y0v[q].w * rs0 * s0.w) * s0.w * y0v[q].w;
+          d1 += gx1[q].x * dsilu_fast(y1v[q].x * rs1 * s1.x) * s1.x * y1v[q].x +
+                gx1[q].y * dsilu_fast(y1v[q].y * rs1 * s1.y) * s1.y * y1v[q].y +
+                gx1[q].z * dsilu_fast(y1v[q].z * rs1 * s1.z) * s1.z * y1v[q].z +
+                gx1[q].w * dsilu_fast(y1v[q].w * rs1 * s1.w) * s1.w * y1v[q].w;
+        }
+      }
+    }
+    if (!frags) return;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+    }
+    cbar();
+    if ((tid & 31) == 0) { st[tid >> 5] = d0; st[8 + (tid >> 5)] = d1; }     // rstd_a / coef_a slots
+    cbar();
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCWarps; ++w) { t0 += st[w]; t1 += st[8 + w]; }
+    const float c0 = rs0 * rs0 * rs0 * t0 / (float)H, c1 = rs1 * rs1 * rs1 * t1 / (float)H;
+#pragma unroll
+    for (int q = 0; q < kRowGroups; ++q) {
+      const int k = q * kCThreads * 4 + tid * 4;
+      if (k < H) {
+        const float4 s0 = *reinterpret_cast<const float4*>(a.s0 + k);
+        const float4 s1 = *reinterpret_cast<const float4*>(a.s1 + k);
+        *reinterpret_cast<__nv_bfloat162*>(gy0A + afrag_index(r, k)) = __floats2bfloat162_rn(
+            kn * norm_bwd_elem(gx0[q].x, y0v[q].x, s0.x, rs0, c0), kn * norm_bwd_elem(gx0[q].y, y0v[q].y, s0.y, rs0, c0));
+        *reinterpret_cast<__nv_bfloat162*>(gy0A + afrag_index(r, k + 2)) = __floats2bfloat162_rn(
+            kn * norm_bwd_elem(gx0[q].z, y0v[q].z, s0.z, rs0, c0), kn * norm_bwd_elem(gx0[q].w, y0v[q].w, s0.w, rs0, c0));
+        *reinterpret_cast<__nv_bfloat162*>(gy1A + afrag_index(r, k)) = __floats2bfloat162_rn(
+            kn * norm_bwd_elem(gx1[q].x, y1v[q].x, s1.x, rs1, c1), kn * norm_bwd_elem(gx1[q].y, y1v[q].y, s1.y, rs1, c1));
+        *reinterpret_cast<__nv_bfloat162*>(gy1A + afrag_index(r, k + 2)) = __floats2bfloat162_rn(
+            kn * norm_bwd_elem(gx1[q].z, y1v[q].z, s1.z, rs1, c1), kn * norm_bwd_elem(gx1[q].w, y1v[q].w, s1.w, rs1, c1));
+      }
+    }
+    fence_proxy_async();
+    cbar();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(row_flag) : "memory");
+  };
+
+#define MARK(i)                                                              \
+  if (a.timing && blockIdx.x == 0 && tid == 0) {                             \
+    unsigned long long now_;                                                 \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                  \
+    a.timing[(size_t)t * 16 + (i)] = now_;                                   \
+  }
   for (int t = T - 1; t >= 0; --t) {
+    MARK(0)
     const float* keep = a.keep + (size_t)t * kRows;
     const float* keep_next = a.keep + (size_t)(t + 1) * kRows;
     const float* deter_prev = t == 0 ? a.deter0 : a.deter + (size_t)(t - 1) * RD;
@@ -242,53 +330,83 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
     float* g_logit = a.g_logit + (size_t)t * RSC;
 
     // ------------------------------------------------------------------ B1
-    // (16 otherwise idle CTAs prepare row r of keep' * g_y0' -- the second half of B3's
-    // operand -- as fragments; g_x0[t+1] and its row dot are complete since the last barrier)
-    if (myrow >= 0 && myrow < kRows) {
-      const int r = myrow;
-      const float rs = a.rstd[(size_t)(t + 1) * 3 * kRows + r];
-      const float cf = rs * rs * rs * ldcg(a.dots + ((size_t)(t + 1) * 4 + 0) * kRows + r) / (float)H;
-      const float kn = ldcg(keep_next + r);
-      for (int k = tid * 4; k < H; k += kCThreads * 4) {
-        const float4 gx = __ldcg(reinterpret_cast<const float4*>(gx0n + (size_t)r * H + k));
-        const float4 y = __ldcg(reinterpret_cast<const float4*>(y0n + (size_t)r * H + k));
-        const float4 sc = *reinterpret_cast<const float4*>(a.s0 + k);
-        *reinterpret_cast<__nv_bfloat162*>(gy0A + afrag_index(r, k)) = __floats2bfloat162_rn(
-            kn * norm_bwd_elem(gx.x, y.x, sc.x, rs, cf), kn * norm_bwd_elem(gx.y, y.y, sc.y, rs, cf));
-        *reinterpret_cast<__nv_bfloat162*>(gy0A + afrag_index(r, k + 2)) = __floats2bfloat162_rn(
-            kn * norm_bwd_elem(gx.z, y.z, sc.z, rs, cf), kn * norm_bwd_elem(gx.w, y.w, sc.w, rs, cf));
-      }
-    }
+    // 16 otherwise idle CTAs first finish step t+1's gradients wrt x0 / x1 (row_work); the
+    // CTAs owning latents wait for the 16 rows (release / acquire counter) and fetch their
+    // operand keep' * g_y1' by TMA.
+    if (myrow >= 0 && myrow < kRows) row_work(t + 1, true);
     if (p.u0[0] < p.u1[0]) {
-      load_stats(t + 1, 1, H, rstd_a, coef_a);
-      cbar();
-      build2(afrag, 0, gx1n, H, y1n, H, H, [&](int r, int k, float gx, float y) {
-        return ldcg(keep_next + r) * norm_bwd_elem(gx, y, a.s1[k], rstd_a[r], coef_a[r]); });
-      cbar();
-      EMB_CONSUME(false, ring, p.per[0], p.ks[0], afrag4, nullptr, out, true)
-      // epilogue: g_stoch -> g_logit for the owned latents (16 threads per row)
+      // epilogue inputs first: their L2 latency hides behind the flag wait and the GEMM
       const int ncols = p.per[0] * 8, nvalid = (p.u1[0] - p.u0[0]) * 8;
       const int r = tid >> 4, l = tid & 15;
       const float* pr = a.probs + (size_t)t * RSC + (size_t)r * SC;
       const float* Gs = a.G_stoch + (size_t)t * RSC + (size_t)r * SC;
       const float* Gl = a.G_logit + (size_t)t * RSC + (size_t)r * SC;
+      constexpr int kPre = 8;                      // C <= 128: 8 classes per thread and latent
+      float ppre[kPre], gspre[kPre], glpre[kPre];
+      const bool one_latent = nvalid == C;
+      if (one_latent) {
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+          const int c = l + 16 * i, col = p.u0[0] * 8 + c;
+          ppre[i] = c < C ? pr[col] : 0.f;
+          gspre[i] = c < C ? Gs[col] : 0.f;
+          glpre[i] = c < C ? Gl[col] : 0.f;
+        }
+      }
+      if (tid == 0) {
+        const unsigned target = (unsigned)kRows * (unsigned)(T - t);
+        unsigned v;
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(row_flag) : "memory");
+        } while ((int)(v - target) < 0);
+        fence_proxy_async();
+        mbar_expect_tx(astage, (uint32_t)RH * 2);
+        bulk_g2s(abase, gy1A, (uint32_t)RH * 2, astage);
+      }
+      mbar_wait(astage, sphase);
+      sphase ^= 1u;
+      EMB_CONSUME(false, ring, p.per[0], p.ks[0], afrag4, nullptr, out, true)
+      // epilogue: g_stoch -> g_logit for the owned latents (16 threads per row)
       const float um = 1.0f - a.unimix;
-      for (int c0 = 0; c0 < nvalid; c0 += C) {         // one latent at a time
-        const int col0 = p.u0[0] * 8 + c0;
+      if (one_latent) {
+        const int col0 = p.u0[0] * 8;
         float dot = 0.f;
-        for (int c = l; c < C; c += 16)
-          dot = fmaf(pr[col0 + c], out[r * ncols + c0 + c] + Gs[col0 + c], dot);
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+          const int c = l + 16 * i;
+          if (c < C) { gspre[i] += out[r * ncols + c]; dot = fmaf(ppre[i], gspre[i], dot); }
+        }
 #pragma unroll
         for (int o = 8; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-        for (int c = l; c < C; c += 16) {
-          const float g = out[r * ncols + c0 + c] + Gs[col0 + c];
-          const float v = Gl[col0 + c] + um * pr[col0 + c] * (g - dot);
-          g_logit[(size_t)r * SC + col0 + c] = v;
-          glA[afrag_index(r, col0 + c)] = __float2bfloat16_rn(v);
+#pragma unroll
+        for (int i = 0; i < kPre; ++i) {
+          const int c = l + 16 * i;
+          if (c < C) {
+            const float v = glpre[i] + um * ppre[i] * (gspre[i] - dot);
+            g_logit[(size_t)r * SC + col0 + c] = v;
+            glA[afrag_index(r, col0 + c)] = __float2bfloat16_rn(v);
+          }
+        }
+      } else {
+        for (int c0 = 0; c0 < nvalid; c0 += C) {         // one latent at a time
+          const int col0 = p.u0[0] * 8 + c0;
+          float dot = 0.f;
+          for (int c = l; c < C; c += 16)
+            dot = fmaf(pr[col0 + c], out[r * ncols + c0 + c] + Gs[col0 + c], dot);
+#pragma unroll
+          for (int o = 8; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          for (int c = l; c < C; c += 16) {
+            const float g = out[r * ncols + c0 + c] + Gs[col0 + c];
+            const float v = Gl[col0 + c] + um * pr[col0 + c] * (g - dot);
+            g_logit[(size_t)r * SC + col0 + c] = v;
+            glA[afrag_index(r, col0 + c)] = __float2bfloat16_rn(v);
+          }
         }
       }
     }
+    MARK(1)
     bar.sync();
+    MARK(2)
 
     // ------------------------------------------------------------------ B2
     // g_xo = g_logit @ obslogit^T ; row dots of the obs0 norm backward
@@ -321,7 +439,9 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
       cbar();
       add_row_dots(t, 2, ncols, 0, nvalid);
     }
+    MARK(3)
     bar.sync();
+    MARK(4)
 
     // ------------------------------------------------------------------ B3
     if (p.u0[2] < p.u1[2]) {
@@ -363,7 +483,9 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
         ga[afrag_index(r, 2 * Dg + jj)] = __float2bfloat16_rn(g2);
       }
     }
+    MARK(5)
     bar.sync();
+    MARK(6)
 
     // ------------------------------------------------------------------ B4
     if (p.u0[3] < p.u1[3]) {
@@ -398,7 +520,9 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
       cbar();
       add_row_dots(t, 3, ncols, 0, nvalid);
     }
+    MARK(7)
     bar.sync();
+    MARK(8)
 
     // ------------------------------------------------------------------ B5
     if (p.u0[4] < p.u1[4]) {
@@ -408,8 +532,6 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
         const float rs = rsqrtf(a.sumsq[(size_t)t * kRows + tid] / (float)D + a.eps);
         rstd_a[tid] = rs;
         coef_a[tid] = rs * rs * rs * ldcg(a.dots + ((size_t)t * 4 + 3) * kRows + tid) / (float)D;
-        rstd_b[tid] = a.rstd[(size_t)t * 3 * kRows + tid];             // y0[t]
-        coef_b[tid] = a.rstd[(size_t)t * 3 * kRows + kRows + tid];     // y1[t] (rstd, not a coef)
       }
       if (tid == 0) {       // this group's slices of U and Y (fragment order: contiguous)
         mbar_expect_tx(astage, (uint32_t)kRows * Dg * 2 * 2);
@@ -426,36 +548,24 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
       const int n0 = (p.u0[4] - g * tpg) * 8;            // first column within the group's Kh inputs
       for (int i = tid; i < kRows * ncols; i += kCThreads) {
         const int r = i / ncols, c = i - r * ncols;
-        float prod = 0.f;
-        if (c < nvalid) {
-          const int n = n0 + c;
-          const float v = out[i];
-          if (n < Dg) {
-            const size_t at = (size_t)r * D + (size_t)g * Dg + n;
-            a.gd_carry[at] = ldcg(keep + r) * (ldcg(a.gd_tmp + at) + v);
-          } else {
-            const int m = n - Dg;                          // [x0 | x1]
-            const int which = m / H, k = m - which * H;
-            float* dst = which == 0 ? a.g_x0 : a.g_x1;
-            atomicAdd(dst + (size_t)t * RH + (size_t)r * H + k, v);
-            if (which == 0) {
-              const float y = y0[(size_t)r * H + k], sc = a.s0[k];
-              prod = v * dsilu_fast(y * rstd_b[r] * sc) * sc * y;
-            } else {
-              const float y = y1[(size_t)r * H + k], sc = a.s1[k];
-              prod = v * dsilu_fast(y * coef_b[r] * sc) * sc * y;
-            }
-          }
+        if (c >= nvalid) continue;
+        const int n = n0 + c;
+        const float v = out[i];
+        if (n < Dg) {
+          const size_t at = (size_t)r * D + (size_t)g * Dg + n;
+          a.gd_carry[at] = ldcg(keep + r) * (ldcg(a.gd_tmp + at) + v);
+        } else {
+          // [x0 | x1] columns: this group's partial; the row CTAs sum the G partials next phase
+          gxp[((size_t)g * kRows + r) * 2 * H + (n - Dg)] = v;
         }
-        out[i] = prod;
       }
-      cbar();
-      // columns [Dg, Dg+H) feed dots slot 0 (x0), [Dg+H, Dg+2H) slot 1 (x1)
-      add_row_dots(t, 0, ncols, max(0, Dg - n0), min(nvalid, Dg + H - n0));
-      add_row_dots(t, 1, ncols, max(0, Dg + H - n0), min(nvalid, Dg + 2 * H - n0));
     }
+    MARK(9)
     bar.sync();
+    MARK(10)
   }
+  if (myrow >= 0 && myrow < kRows) row_work(0, false);      // gradients wrt step 0's x0 / x1 (inputs)
+#undef MARK
 }
 
 int g_sms_bwd = 0;
@@ -505,7 +615,9 @@ int launch_bwd(const emb_rssm_bwd_args& a, void* stream) {
   if (n > 12) n = 12;
   if (stage_cap > 0 && stage_cap < n) n = stage_cap;
   if (n < 2) return emb::fail(-1, "%s: no room for the weight ring next to the A operands", who);
-  if (!a.frag_scratch) return emb::fail(-1, "%s: the bf16 TMA engine needs frag_scratch", who);
+  if (!a.frag_scratch || !a.gx_part)
+    return emb::fail(-1, "%s: the bf16 TMA engine needs frag_scratch and gx_part", who);
+  if (a.H > 4096 || a.H % 4) return emb::fail(-1, "%s: hidden=%d must be <= 4096 and a multiple of 4", who, a.H);
   const size_t smem = fixed + (size_t)n * stage_bytes + 128;
   emb_rssm_bwd_args copy = a;
   copy.hoist_x2 = n | (maxper << 8) | ((stage_bytes / 1024) << 16);      // kernel-side ring configuration

@@ -300,7 +300,7 @@ class BwdArgs(ctypes.Structure):
           'keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates', 'sumsq', 'probs', 'rstd',
           'G_deter', 'G_logit', 'G_stoch',
           'g_xo', 'g_logit', 'g_gates', 'g_h', 'g_x0', 'g_x1', 'g_x2',
-          'g_stoch', 'gd_carry', 'gd_tmp', 'dots', 'barrier', 'frag_scratch')])
+          'g_stoch', 'gd_carry', 'gd_tmp', 'dots', 'barrier', 'frag_scratch', 'gx_part', 'timing')])
 
 
 @torch.no_grad()
@@ -387,7 +387,8 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
       g_x2=zeros(T, ROWS, H), g_stoch=empty(ROWS, SC), gd_carry=zeros(ROWS, D),
       gd_tmp=empty(ROWS, D), dots=zeros(T + 1, 4, ROWS),
       barrier=torch.zeros(4, dtype=torch.int32, device=dev),
-      frag_scratch=torch.zeros(ROWS * (5 * D + 3 * H), dtype=torch.bfloat16, device=dev))
+      frag_scratch=torch.zeros(ROWS * (5 * D + 4 * H), dtype=torch.bfloat16, device=dev),
+      gx_part=torch.zeros((G, ROWS, 2 * H), dtype=f32, device=dev))
   vec = dict(s0=m('dyn/dynin0norm/scale'), s1=m('dyn/dynin1norm/scale'),
              s_hid=m('dyn/dynhid0norm/scale'), s_obs=m('dyn/obs0norm/scale'))
   saved = {k: sv[k] for k in ('keep', 'deter0', 'deter', 'y0', 'y1', 'yobs', 'yhid', 'gates',
@@ -395,6 +396,9 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
   hoist = scan.engine != ENG_F32
   args = BwdArgs(B=B, T=T, D=D, H=H, S=S, C=C, G=G, engine=scan.engine, ncta=scan.ncta,
                  hoist_x2=int(hoist), unimix=cfg.unimix, eps=1e-4)
+  if scan.timing:
+    buf['timing'] = torch.zeros((T, 16), dtype=torch.int64, device=dev)
+  scan.last_bwd_buf = buf
   for k, v in {**scan.packed_bwd, **vec, **saved, **buf}.items():
     if k == 'w_hid_x2':
       continue

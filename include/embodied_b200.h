@@ -231,8 +231,11 @@ typedef struct emb_rssm_bwd_args {
   float* gd_tmp;         /* [16][D] */
   float* dots;           /* [T+1][4][16] ZEROED: row dots of the norm backward of x0, x1, xo, h */
   uint32_t* barrier;     /* one ZEROED u32 */
-  void* frag_scratch;    /* engine 1: 16 * (5*D + 3*H) bf16 -- operand fragments handed from
+  void* frag_scratch;    /* engine 1: 16 * (5*D + 4*H) bf16 -- operand fragments handed from
                           * one phase's epilogue to the next phase's TMA fetch */
+  float* gx_part;        /* engine 1: [G][16][2H] fp32, ZEROED -- per-group partials of the
+                          * gradients wrt x0 | x1 (summed by row CTAs, no atomics) */
+  uint64_t* timing;      /* optional [T][16] globaltimer marks of CTA 0 (NULL = off) */
 } emb_rssm_bwd_args;
 
 int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream);

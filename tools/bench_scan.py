@@ -74,7 +74,7 @@ def main():
 
 
 def bench_bwd(sc, args, B, T, cfg, wbytes, size, engine):
-  sc.timing = False
+  sc.timing = engine == 'bf16'
   sc.bwd_events = []
   g = torch.Generator(device='cuda').manual_seed(1)
   r = lambda *s: torch.randn(s, generator=g, device='cuda') * 0.01
@@ -87,6 +87,11 @@ def bench_bwd(sc, args, B, T, cfg, wbytes, size, engine):
   torch.cuda.synchronize()
   times = [a.elapsed_time(b) * 1e-3 for a, b in sc.bwd_events[3:]]
   t = float(np.median(times))
+  if 'timing' in getattr(sc, 'last_bwd_buf', {}):
+    tm = sc.last_bwd_buf['timing'].cpu().numpy().astype(np.int64)
+    d = np.diff(tm[:, :11], axis=1)[4:-4].mean(0) / 1e3
+    names = ['B1', 'bar', 'B2', 'bar', 'B3', 'bar', 'B4', 'bar', 'B5', 'bar']
+    print('bwd phase us (CTA 0):', {n + str(i): round(float(x), 2) for i, (n, x) in enumerate(zip(names, d))})
   print(json.dumps({
       'kernel': 'rssm_bwd_kernel', 'size': size, 'engine': engine,
       'B': B, 'T': T, 'ms': t * 1e3, 'us_per_step': t / T * 1e6,
