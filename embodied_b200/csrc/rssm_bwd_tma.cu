@@ -459,28 +459,53 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
       combine_frags(afrag4, reinterpret_cast<const uint4*>(abase + RH * 4), (H / 16) * 32, coef_a);
       cbar();
       EMB_CONSUME(false, ring, p.per[2], p.ks[2], afrag4, nullptr, out, true)
+      // epilogue: GRU backward (rssm.py:152-158) for this CTA's columns.  Compact element
+      // index over the valid columns; the eight inputs of kE elements are requested before any
+      // is used (one L2 round trip per batch).
       const int ncols = p.per[2] * 8, nvalid = (p.u1[2] - p.u0[2]) * 8;
-      for (int i = tid; i < kRows * ncols; i += kCThreads) {
-        const int r = i / ncols, c = i - r * ncols;
-        if (c >= nvalid) continue;
-        const int col = p.u0[2] * 8 + c;
-        const size_t at = (size_t)r * D + col;
-        const float gd = out[i] + a.G_deter[(size_t)t * RD + at] + ldcg(a.gd_carry + at);
-        const float rs = gates[at], cand = gates[RD + at], up = gates[2 * RD + at], cpre = gates[3 * RD + at];
-        const float old = ldcg(keep + r) * deter_prev[at];
-        const float g_u = gd * (cand - old), g_c = gd * up;
-        a.gd_tmp[at] = gd * (1.0f - up);                 // direct path into keep*deter_{t-1}
-        const float g_rc = g_c * (1.0f - cand * cand);
-        const int g = col / Dg, jj = col - g * Dg;
-        float* gg = g_gates + (size_t)r * 3 * D + (size_t)g * 3 * Dg + jj;
-        const float g0 = g_rc * cpre * rs * (1.0f - rs);  // reset gate, pre-sigmoid
-        const float g1 = g_rc * rs;                       // candidate, pre-tanh
-        const float g2 = g_u * up * (1.0f - up);          // update gate, pre-sigmoid
-        gg[0] = g0; gg[Dg] = g1; gg[2 * Dg] = g2;
-        __nv_bfloat16* ga = ggA + (size_t)g * 3 * Dg * kRows;         // B4's operand, group g
-        ga[afrag_index(r, jj)] = __float2bfloat16_rn(g0);
-        ga[afrag_index(r, Dg + jj)] = __float2bfloat16_rn(g1);
-        ga[afrag_index(r, 2 * Dg + jj)] = __float2bfloat16_rn(g2);
+      const int count = kRows * nvalid;
+      constexpr int kE = 4;
+      for (int base = 0; base < count; base += kCThreads * kE) {
+        float in[kE][8];
+#pragma unroll
+        for (int e = 0; e < kE; ++e) {
+          const int i = base + e * kCThreads + tid;
+          if (i < count) {
+            const int r = i / nvalid, c = i - r * nvalid;
+            const size_t at = (size_t)r * D + p.u0[2] * 8 + c;
+            in[e][0] = a.G_deter[(size_t)t * RD + at];
+            in[e][1] = ldcg(a.gd_carry + at);
+            in[e][2] = gates[at]; in[e][3] = gates[RD + at]; in[e][4] = gates[2 * RD + at];
+            in[e][5] = gates[3 * RD + at];
+            in[e][6] = deter_prev[at];
+            in[e][7] = ldcg(keep + r);
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < kE; ++e) {
+          const int i = base + e * kCThreads + tid;
+          if (i < count) {
+            const int r = i / nvalid, c = i - r * nvalid;
+            const int col = p.u0[2] * 8 + c;
+            const size_t at = (size_t)r * D + col;
+            const float gd = out[r * ncols + c] + in[e][0] + in[e][1];
+            const float rs = in[e][2], cand = in[e][3], up = in[e][4], cpre = in[e][5];
+            const float old = in[e][7] * in[e][6];
+            const float g_u = gd * (cand - old), g_c = gd * up;
+            a.gd_tmp[at] = gd * (1.0f - up);                 // direct path into keep*deter_{t-1}
+            const float g_rc = g_c * (1.0f - cand * cand);
+            const int g = col / Dg, jj = col - g * Dg;
+            float* gg = g_gates + (size_t)r * 3 * D + (size_t)g * 3 * Dg + jj;
+            const float g0 = g_rc * cpre * rs * (1.0f - rs);  // reset gate, pre-sigmoid
+            const float g1 = g_rc * rs;                       // candidate, pre-tanh
+            const float g2 = g_u * up * (1.0f - up);          // update gate, pre-sigmoid
+            gg[0] = g0; gg[Dg] = g1; gg[2 * Dg] = g2;
+            __nv_bfloat16* ga = ggA + (size_t)g * 3 * Dg * kRows;         // B4's operand, group g
+            ga[afrag_index(r, jj)] = __float2bfloat16_rn(g0);
+            ga[afrag_index(r, Dg + jj)] = __float2bfloat16_rn(g1);
+            ga[afrag_index(r, 2 * Dg + jj)] = __float2bfloat16_rn(g2);
+          }
+        }
       }
     }
     MARK(5)
@@ -501,21 +526,38 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
       sphase ^= 1u;
       EMB_CONSUME(false, ring, p.per[3], p.ks[3], afrag4, nullptr, out, true)
       const int ncols = p.per[3] * 8, nvalid = (p.u1[3] - p.u0[3]) * 8;
-      for (int i = tid; i < kRows * ncols; i += kCThreads) {
-        const int r = i / ncols, c = i - r * ncols;
-        float prod = 0.f;
-        if (c < nvalid) {
-          const int col = p.u0[3] * 8 + c;
-          const size_t at = (size_t)r * D + col;
-          const float gh = out[i];
-          g_h[at] = gh;
-          const float y = yhid[at], sc = a.s_hid[col];
-          const float gn = gh * dsilu_fast(y * rstd_a[r] * sc);
-          prod = gn * sc * y;                                     // g_n * s * y
-          UhA[afrag_index(r, col)] = __float2bfloat16_rn(rstd_a[r] * sc * gn);
-          YhA[afrag_index(r, col)] = __float2bfloat16_rn(y);
+      {
+        constexpr int kE = 4;
+        const int total = kRows * ncols;
+        for (int base = 0; base < total; base += kCThreads * kE) {
+          float yv[kE], sv[kE];
+#pragma unroll
+          for (int e = 0; e < kE; ++e) {
+            const int i = base + e * kCThreads + tid;
+            const int r = i / ncols, c = i - r * ncols;
+            const bool on = i < total && c < nvalid;
+            yv[e] = on ? yhid[(size_t)r * D + p.u0[3] * 8 + c] : 0.f;
+            sv[e] = on ? a.s_hid[p.u0[3] * 8 + c] : 0.f;
+          }
+#pragma unroll
+          for (int e = 0; e < kE; ++e) {
+            const int i = base + e * kCThreads + tid;
+            if (i >= total) continue;
+            const int r = i / ncols, c = i - r * ncols;
+            float prod = 0.f;
+            if (c < nvalid) {
+              const int col = p.u0[3] * 8 + c;
+              const size_t at = (size_t)r * D + col;
+              const float gh = out[i];
+              g_h[at] = gh;
+              const float gn = gh * dsilu_fast(yv[e] * rstd_a[r] * sv[e]);
+              prod = gn * sv[e] * yv[e];                              // g_n * s * y
+              UhA[afrag_index(r, col)] = __float2bfloat16_rn(rstd_a[r] * sv[e] * gn);
+              YhA[afrag_index(r, col)] = __float2bfloat16_rn(yv[e]);
+            }
+            out[i] = prod;
+          }
         }
-        out[i] = prod;
       }
       cbar();
       add_row_dots(t, 3, ncols, 0, nvalid);
