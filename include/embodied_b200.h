@@ -205,7 +205,9 @@ int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream);
 typedef struct emb_rssm_bwd_args {
   int32_t B, T, D, H, S, C, G;
   int32_t engine, ncta;
-  int32_t hoist_x2;      /* 1: wt_hid has no action rows ([D/G][G*(D/G+2H)]); the caller forms g_x2 */
+  int32_t hoist_x2;      /* 1: wt_hid has no action rows ([D/G][G*(D/G+2H)]); the caller forms g_x2
+                          * (engine 1 requires it; the library's private copy re-uses the slot
+                          * for its ring configuration) */
   float unimix, eps;
   const void* wt_in1;    /* [H][S*C]        dynin1/kernel^T                              */
   const void* wt_logit;  /* [S*C][H]        obslogit/kernel^T                            */
