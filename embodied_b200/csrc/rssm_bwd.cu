@@ -405,8 +405,11 @@ int g_sms = 0;
 
 }  // namespace
 
+namespace emb_legacy {
+size_t bwd_smem(const emb_rssm_bwd_args& a) { return bwd_smem_bytes(a); }
+}
 namespace emb_tma {
-int launch_bwd(const emb_rssm_bwd_args& a, void* stream);   // rssm_bwd_tma.cu
+int launch_bwd(const emb_rssm_bwd_args& a, void* stream, bool dry);   // rssm_bwd_tma.cu
 }
 
 extern "C" int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream) {
@@ -419,7 +422,7 @@ extern "C" int emb_rssm_observe_bwd(const emb_rssm_bwd_args* args, void* stream)
     return emb::fail(-1, "%s: D/G, H and S*C must be multiples of 16", who);
   if (a.engine != rssm::ENG_F32 && a.engine != rssm::ENG_TMA && a.engine != rssm::ENG_LEGACY)
     return emb::fail(-1, "%s: engine %d", who, a.engine);
-  if (a.engine == rssm::ENG_TMA) return emb_tma::launch_bwd(a, stream);
+  if (a.engine == rssm::ENG_TMA) return emb_tma::launch_bwd(a, stream, false);
   if (g_sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||

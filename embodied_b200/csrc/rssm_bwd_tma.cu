@@ -616,7 +616,7 @@ int g_sms_bwd = 0;
 
 namespace emb_tma {
 
-int launch_bwd(const emb_rssm_bwd_args& a, void* stream) {
+int launch_bwd(const emb_rssm_bwd_args& a, void* stream, bool dry) {
   const char* who = "emb_rssm_observe_bwd";
   const int Dg = a.D / a.G, SC = a.S * a.C, Kh = Dg + 2 * a.H;
   if (!a.hoist_x2) return emb::fail(-1, "%s: the bf16 TMA engine needs hoist_x2 = 1", who);
@@ -663,6 +663,7 @@ int launch_bwd(const emb_rssm_bwd_args& a, void* stream) {
   const size_t smem = fixed + (size_t)n * stage_bytes + 128;
   emb_rssm_bwd_args copy = a;
   copy.hoist_x2 = n | (maxper << 8) | ((stage_bytes / 1024) << 16);      // kernel-side ring configuration
+  if (dry) return 0;                      // emb_rssm_tma_fits: validation and sizing only
   const void* fn = (const void*)rssm_bwd_tma_kernel;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return emb::fail_cuda(who);

@@ -439,8 +439,12 @@ int g_sms = 0;
 
 }  // namespace
 
+namespace emb_legacy {
+size_t bwd_smem(const emb_rssm_bwd_args& a);     // rssm_bwd.cu
+}
 namespace emb_tma {
-int launch_fwd(const emb_rssm_fwd_args& a, void* stream);   // rssm_fwd_tma.cu
+int launch_fwd(const emb_rssm_fwd_args& a, void* stream, bool dry);   // rssm_fwd_tma.cu
+int launch_bwd(const emb_rssm_bwd_args& a, void* stream, bool dry);   // rssm_bwd_tma.cu
 }
 
 extern "C" int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream) {
@@ -455,7 +459,7 @@ extern "C" int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream)
                      who, a.D, a.G, a.H, a.S, a.C);
   if (a.engine != rssm::ENG_F32 && a.engine != rssm::ENG_TMA && a.engine != rssm::ENG_LEGACY)
     return emb::fail(-1, "%s: engine %d", who, a.engine);
-  if (a.engine == rssm::ENG_TMA) return emb_tma::launch_fwd(a, stream);
+  if (a.engine == rssm::ENG_TMA) return emb_tma::launch_fwd(a, stream, false);
   if (g_sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -478,4 +482,37 @@ extern "C" int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream)
     return emb::fail_cuda(who);
   emb::count_launch();
   return 0;
+}
+
+/* 1 if the register-staged bf16 engine (engine 2) of both scan kernels fits (operands +
+ * per-warp partial sums within 227 KiB of shared memory), else 0. */
+extern "C" int emb_rssm_legacy_fits(int32_t D, int32_t H, int32_t S, int32_t C, int32_t G, int32_t ncta) {
+  if (D < 16 || H < 16 || S < 1 || C < 1 || G < 1 || D % G || (D / G) % 16 || H % 16 || (S * C) % 16 || ncta < 1)
+    return emb::fail(0, "emb_rssm_legacy_fits: D=%d H=%d S=%d C=%d G=%d", D, H, S, C, G);
+  emb_rssm_fwd_args f = {};
+  f.D = D; f.H = H; f.S = S; f.C = C; f.G = G; f.engine = rssm::ENG_LEGACY; f.ncta = ncta;
+  emb_rssm_bwd_args b = {};
+  b.D = D; b.H = H; b.S = S; b.C = C; b.G = G; b.engine = rssm::ENG_LEGACY; b.ncta = ncta; b.hoist_x2 = 1;
+  const size_t cap = 227 * 1024;
+  if (fwd_smem_bytes(f) > cap || emb_legacy::bwd_smem(b) > cap)
+    return emb::fail(0, "emb_rssm_legacy_fits: operands of D=%d H=%d exceed 227 KiB of shared memory", D, H);
+  return 1;
+}
+
+/* 1 if the bf16 TMA engine (engine 1) of both scan kernels fits this model on `ncta`
+ * CTAs (tiles per CTA within the consumers' accumulators, operands + a weight ring of >= 2
+ * stages within 227 KiB of shared memory), else 0 with the reason in emb_last_error(). */
+extern "C" int emb_rssm_tma_fits(int32_t D, int32_t H, int32_t S, int32_t C, int32_t G, int32_t ncta) {
+  if (D < 16 || H < 16 || S < 1 || C < 1 || G < 1 || D % G || (D / G) % 16 || H % 16 || (S * C) % 16)
+    return emb::fail(0, "emb_rssm_tma_fits: D=%d H=%d S=%d C=%d G=%d", D, H, S, C, G);
+  static float dummy_f = 0.f;
+  emb_rssm_fwd_args f = {};
+  f.B = 1; f.T = 1; f.D = D; f.H = H; f.S = S; f.C = C; f.G = G; f.engine = rssm::ENG_TMA; f.ncta = ncta;
+  f.hid_pre = &dummy_f; f.sumsq_obs = &dummy_f;
+  if (emb_tma::launch_fwd(f, nullptr, true) != 0) return 0;
+  emb_rssm_bwd_args b = {};
+  b.B = 1; b.T = 1; b.D = D; b.H = H; b.S = S; b.C = C; b.G = G; b.engine = rssm::ENG_TMA; b.ncta = ncta;
+  b.hoist_x2 = 1; b.frag_scratch = &dummy_f; b.gx_part = &dummy_f;
+  if (emb_tma::launch_bwd(b, nullptr, true) != 0) return 0;
+  return 1;
 }

@@ -652,7 +652,7 @@ size_t fwd_smem_bytes(const emb_rssm_fwd_args& a, int maxper, int stage_bytes, i
   return fixed + (size_t)n * stage_bytes + 128;
 }
 
-int launch_fwd(const emb_rssm_fwd_args& a, void* stream) {
+int launch_fwd(const emb_rssm_fwd_args& a, void* stream, bool dry) {
   const char* who = "emb_rssm_observe_fwd";
   const int Dg = a.D / a.G;
   if (!a.hid_pre) return emb::fail(-1, "%s: the bf16 engine needs hid_pre (hoisted action branch)", who);
@@ -696,6 +696,7 @@ int launch_fwd(const emb_rssm_fwd_args& a, void* stream) {
   if (nstages < 2)
     return emb::fail(-1, "%s: A operand (%d columns) leaves no room for the weight ring", who, Dg + 2 * a.H);
   copy.tma_cfg = nstages | (maxper << 8) | ((stage_bytes / 1024) << 16);
+  if (dry) return 0;                      // emb_rssm_tma_fits: validation and sizing only
   const void* fn = (const void*)rssm_fwd_tma_kernel;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return emb::fail_cuda(who);

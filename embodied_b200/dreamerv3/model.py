@@ -239,7 +239,7 @@ class Model:
     tok = torch.addmm(bobs, tokens.reshape(B * T, -1), wobs[D:]).reshape(B, T, -1)
     deter, stoch = carry
     deter, stoch = deter.to(self.cd), stoch.to(self.cd)
-    if self.scan is not None and B <= 16:
+    if self.scan is not None and self.scan.supported and B <= 16:
       return self.observe_fused(deter, stoch, x2, tok, reset, gumbel)
     deters, stochs, logits = [], [], []
     for t in range(T):

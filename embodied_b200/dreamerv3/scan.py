@@ -196,9 +196,21 @@ class Scan:
     self.packed_bwd = None
     self.packed_bwd_step = -1
     self.timing = False
+    self.supported = True       # False: the model is too wide for either fused engine
     self.ncta = int(self.lib.emb_device_sm_count())
     if self.ncta <= 0:
       _lib.check(self.ncta)
+    if self.engine == ENG_BF16:
+      # very wide models leave no shared memory for the TMA ring next to the operands:
+      # the register-staged bf16 kernels (engine 2) take over
+      self.lib.emb_rssm_tma_fits.argtypes = [_i32] * 6
+      self.lib.emb_rssm_tma_fits.restype = ctypes.c_int
+      dims = (cfg.deter, cfg.hidden, cfg.stoch, cfg.classes, cfg.blocks, self.ncta)
+      self.lib.emb_rssm_legacy_fits.argtypes = [_i32] * 6
+      self.lib.emb_rssm_legacy_fits.restype = ctypes.c_int
+      if not self.lib.emb_rssm_tma_fits(*dims):
+        self.engine = ENG_LEGACY
+        self.supported = bool(self.lib.emb_rssm_legacy_fits(*dims))
 
   def invalidate(self):
     """Forget the packed weight copies (the next use re-packs; a CUDA-graph

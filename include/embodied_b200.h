@@ -196,6 +196,12 @@ typedef struct emb_rssm_fwd_args {
 
 int emb_rssm_observe_fwd(const emb_rssm_fwd_args* args, void* stream);
 
+/* 1 if engine 1 (bf16, TMA weight ring) of both scan kernels fits this model on `ncta` CTAs,
+ * else 0 (reason in emb_last_error()); callers then use engine 2. */
+int emb_rssm_tma_fits(int32_t D, int32_t H, int32_t S, int32_t C, int32_t G, int32_t ncta);
+/* The same question for engine 2; if neither fits the caller runs the scan step by step. */
+int emb_rssm_legacy_fits(int32_t D, int32_t H, int32_t S, int32_t C, int32_t G, int32_t ncta);
+
 /* Back-propagation through time of the same scan (embodied_b200/csrc/rssm_bwd.cu).
  * Consumes the activations emb_rssm_observe_fwd saved and the upstream
  * gradients of its three outputs; produces, per step, the upstream gradient of

@@ -190,3 +190,18 @@ def test_backward_bf16_engine_tracks_fp32_engine(size, B, T):
     if float(v.abs().max()) > 0:
       worst.append((rel2(res['bf16'][2][k], v), k))
   assert max(worst)[0] < 6e-2, sorted(worst)[-6:]
+
+
+def test_engine_selection_by_model_size():
+  """size200m runs on the TMA engine; size400m's operands leave no room for either fused
+  engine in 227 KiB of shared memory, and the model falls back to the step-by-step scan."""
+  from embodied_b200.dreamerv3 import config as C
+
+  class Store:      # Scan.__init__ only probes the library
+    version = 0
+  s200 = scanlib.Scan(C.make('size200m'), Store(), scanlib.ENG_BF16)
+  assert s200.engine == scanlib.ENG_BF16 and s200.supported
+  s400 = scanlib.Scan(C.make('size400m'), Store(), scanlib.ENG_BF16)
+  assert not s400.supported
+  s12 = scanlib.Scan(C.make('size12m'), Store(), scanlib.ENG_BF16)
+  assert s12.engine == scanlib.ENG_BF16 and s12.supported
