@@ -58,9 +58,21 @@ template <> struct Vec<__nv_bfloat16> {
 
 __device__ __forceinline__ float silu(float n) { return n / (1.0f + expf(-n)); }
 __device__ __forceinline__ float sigmoid(float n) { return 1.0f / (1.0f + expf(-n)); }
+// bf16 outputs (8 mantissa bits): fast intrinsics are far inside the rounding error
+template <typename T> __device__ __forceinline__ float sigmoid_t(float n) { return sigmoid(n); }
+template <> __device__ __forceinline__ float sigmoid_t<__nv_bfloat16>(float n) {
+  return __fdividef(1.0f, 1.0f + __expf(-n));
+}
+template <typename T> __device__ __forceinline__ float tanh_t(float n) { return tanhf(n); }
+template <> __device__ __forceinline__ float tanh_t<__nv_bfloat16>(float n) {
+  const float e = __expf(-2.0f * fabsf(n));
+  return copysignf(__fdividef(1.0f - e, 1.0f + e), n);
+}
 
-// one CTA per row m; column c = gi*Dg + j lives at x[(gi*M + m)*Dg + j]
-template <typename T>
+// one CTA per row m; column c = gi*Dg + j lives at x[(gi*M + m)*Dg + j].  NV = vectors a
+// thread owns (compile-time: the row stays in registers at a register count that lets
+// several CTAs share an SM -- the kernel is latency-bound, not bandwidth-bound).
+template <typename T, int NV>
 __global__ void __launch_bounds__(kThreads)
 rmsnorm_grouped_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                        const float* __restrict__ bias, T* __restrict__ y, int M, int G, int Dg,
@@ -68,18 +80,31 @@ rmsnorm_grouped_kernel(const T* __restrict__ x, const float* __restrict__ scale,
   constexpr int N = Vec<T>::N;
   __shared__ float red[kThreads / 32];
   const int m = blockIdx.x, D = G * Dg, nvec = D / N;
-  float v[kMaxVec][N];
+  float v[NV][N];
   float ss = 0.f;
 #pragma unroll
-  for (int k = 0; k < kMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = threadIdx.x + k * kThreads;
     if (vi < nvec) {
       const int c = vi * N, gi = c / Dg, j = c - gi * Dg;
       Vec<T>::load(x + ((size_t)gi * M + m) * Dg + j, v[k]);
+    }
+  }
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        if (bias) v[k][i] = Vec<T>::round(v[k][i] + bias[c + i]);
-        ss = fmaf(v[k][i], v[k][i], ss);
+  for (int k = 0; k < NV; ++k) {
+    const int vi = threadIdx.x + k * kThreads;
+    if (vi < nvec) {
+      const int c = vi * N;
+#pragma unroll
+      for (int i = 0; i < N; i += 4) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b = *reinterpret_cast<const float4*>(bias + c + i);
+        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (bias) v[k][i + q] = Vec<T>::round(v[k][i + q] + bb[q]);
+          ss = fmaf(v[k][i + q], v[k][i + q], ss);
+        }
       }
     }
   }
@@ -92,19 +117,38 @@ rmsnorm_grouped_kernel(const T* __restrict__ x, const float* __restrict__ scale,
   for (int w = 0; w < kThreads / 32; ++w) tot += red[w];
   const float rstd = rsqrtf(tot / (float)D + eps);
 #pragma unroll
-  for (int k = 0; k < kMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int vi = threadIdx.x + k * kThreads;
     if (vi < nvec) {
       const int c = vi * N, gi = c / Dg, j = c - gi * Dg;
       float o[N];
 #pragma unroll
-      for (int i = 0; i < N; ++i) {
-        const float n = Vec<T>::round(v[k][i] * (rstd * scale[c + i]));
-        o[i] = act ? silu(n) : n;
+      for (int i = 0; i < N; i += 4) {
+        const float4 s4 = *reinterpret_cast<const float4*>(scale + c + i);
+        const float sc[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float n = Vec<T>::round(v[k][i + q] * (rstd * sc[q]));
+          o[i + q] = act ? silu(n) : n;
+        }
       }
       Vec<T>::store(y + ((size_t)gi * M + m) * Dg + j, o);
     }
   }
+}
+
+template <typename T>
+void launch_grouped(int nv, const void* x, const float* scale, const float* bias, void* y, int m, int g,
+                    int dg, int act, float eps, cudaStream_t s) {
+#define EMB_NV(NV)                                                                              \
+  rmsnorm_grouped_kernel<T, NV><<<(unsigned)m, kThreads, 0, s>>>((const T*)x, scale, bias, (T*)y, m, \
+                                                                  g, dg, act, eps)
+  if (nv <= 1) EMB_NV(1);
+  else if (nv <= 2) EMB_NV(2);
+  else if (nv <= 4) EMB_NV(4);
+  else if (nv <= 8) EMB_NV(8);
+  else EMB_NV(16);
+#undef EMB_NV
 }
 
 // one thread per vector of the (M, D) state
@@ -127,9 +171,9 @@ gru_gates_kernel(const T* __restrict__ pre, const float* __restrict__ bias, cons
     Vec<T>::load(deter + (size_t)m * G * Dg + c, d);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const float rs = sigmoid(Vec<T>::round(r[i] + b[i]));
-      const float cand = tanhf(Vec<T>::round(rs * Vec<T>::round(cd[i] + b[Dg + i])));
-      const float up = sigmoid(Vec<T>::round(u[i] + b[2 * Dg + i]) - 1.0f);
+      const float rs = sigmoid_t<T>(Vec<T>::round(r[i] + b[i]));
+      const float cand = tanh_t<T>(Vec<T>::round(rs * Vec<T>::round(cd[i] + b[Dg + i])));
+      const float up = sigmoid_t<T>(Vec<T>::round(u[i] + b[2 * Dg + i]) - 1.0f);
       res[i] = up * cand + (1.0f - up) * d[i];
     }
     Vec<T>::store(out + (size_t)m * G * Dg + c, res);
@@ -163,12 +207,9 @@ extern "C" int emb_rmsnorm_grouped_fwd(const void* x, const float* scale, const 
     return emb::fail(-1, "%s: row of %d columns exceeds %d", who, g * dg, kMaxVec * kThreads * n);
   if (m == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype)
-    rmsnorm_grouped_kernel<__nv_bfloat16><<<(unsigned)m, kThreads, 0, s>>>(
-        (const __nv_bfloat16*)x, scale, bias, (__nv_bfloat16*)y, (int)m, g, dg, act, eps);
-  else
-    rmsnorm_grouped_kernel<float><<<(unsigned)m, kThreads, 0, s>>>(
-        (const float*)x, scale, bias, (float*)y, (int)m, g, dg, act, eps);
+  const int nv = (int)(((int64_t)g * dg / n + kThreads - 1) / kThreads);
+  if (dtype) launch_grouped<__nv_bfloat16>(nv, x, scale, bias, y, (int)m, g, dg, act, eps, s);
+  else launch_grouped<float>(nv, x, scale, bias, y, (int)m, g, dg, act, eps, s);
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;

@@ -119,6 +119,116 @@ rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
   }
 }
 
+// Rows of up to 32 * NV vectors (dense layers: 1024 .. 2048 columns): one warp per row,
+// the row read ONCE into registers (the generic kernel above sweeps it twice).
+template <typename T, int NV>
+__global__ void __launch_bounds__(kThreads)
+rmsnorm_act_fwd_reg_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                           const float* __restrict__ bias, T* __restrict__ y,
+                           int64_t rows, int cols, int act, float eps) {
+  constexpr int N = Vec<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const T* xr = x + r * cols;
+    T* yr = y + r * cols;
+    float v[NV][N];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (lane + 32 * k) * N;
+      if (c < cols) Vec<T>::load(xr + c, v[k]);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (lane + 32 * k) * N;
+      if (c < cols) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          if (bias) v[k][i] += bias[c + i];
+          ss = fmaf(v[k][i], v[k][i], ss);
+        }
+      }
+    }
+    const float rstd = rsqrtf(group_sum(ss, 32) / (float)cols + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (lane + 32 * k) * N;
+      if (c < cols) {
+        float o[N];
+#pragma unroll
+        for (int i = 0; i < N; i += 4) {
+          const float4 s4 = *reinterpret_cast<const float4*>(scale + c + i);
+          const float sc[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float n = Vec<T>::round(v[k][i + q] * (rstd * sc[q]));
+            o[i + q] = act ? silu(n) : n;
+          }
+        }
+        Vec<T>::store(yr + c, o);
+      }
+    }
+  }
+}
+
+// Short rows (<= 256 columns: the channel axis of the convolutions, millions of rows):
+// gs = power-of-two lanes per row, 32 / gs rows per warp, NV vectors per lane, the row
+// read once into registers; bias of the producing convolution folded in.
+template <typename T, int NV>
+__global__ void __launch_bounds__(kThreads)
+rmsnorm_act_fwd_short_kernel(const T* __restrict__ x, const float* __restrict__ scale,
+                             const float* __restrict__ bias, T* __restrict__ y,
+                             int64_t rows, int cols, int act, float eps) {
+  constexpr int N = Vec<T>::N;
+  const int gs = group_size((cols + NV - 1) / NV, N), rpw = 32 / gs;
+  const int lane = threadIdx.x & 31, lg = lane % gs, grp = lane / gs;
+  const int64_t warp = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kWarps;
+  float sc[NV][N], bi[NV][N];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = (lg + gs * k) * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      sc[k][i] = c < cols ? scale[c + i] : 0.f;
+      bi[k][i] = (bias && c < cols) ? bias[c + i] : 0.f;
+    }
+  }
+  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
+    const int64_t r = r0 + grp;
+    const bool live = r < rows;
+    const T* xr = x + (live ? r : 0) * cols;
+    float v[NV][N];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (lg + gs * k) * N;
+      if (c < cols) {
+        Vec<T>::load(xr + c, v[k]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) { v[k][i] += bi[k][i]; ss = fmaf(v[k][i], v[k][i], ss); }
+      }
+    }
+    const float rstd = rsqrtf(group_sum(ss, gs) / (float)cols + eps);
+    if (!live) continue;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c = (lg + gs * k) * N;
+      if (c < cols) {
+        float o[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float n = Vec<T>::round(v[k][i] * (rstd * sc[k][i]));
+          o[i] = act ? silu(n) : n;
+        }
+        Vec<T>::store(y + r * cols + c, o);
+      }
+    }
+  }
+}
+
 // PL = elements a lane may own of one row.  PL = 8 (cols <= 256: the channel
 // axis of the convolutions, millions of short rows) keeps the row in registers
 // -- one load of x and g_y, two shuffle reductions, one store -- runs at full
@@ -332,7 +442,26 @@ extern "C" int emb_rmsnorm_act_fwd(const void* x, const float* scale, const floa
   if (rows == 0) return 0;
   const unsigned grid = grid_for(rows, 8);
   cudaStream_t s = (cudaStream_t)stream;
-  if (dtype)
+  const int vec = dtype ? 8 : 4, nv = (cols / vec + 31) / 32;
+  if (cols >= 32 * vec && nv <= 8) {          // one warp per row, the row in registers
+#define EMB_REG(T, NV) rmsnorm_act_fwd_reg_kernel<T, NV><<<grid, kThreads, 0, s>>>( \
+      (const T*)x, scale, bias, (T*)y, rows, cols, act, eps)
+    if (dtype) {
+      if (nv <= 1) EMB_REG(__nv_bfloat16, 1); else if (nv <= 2) EMB_REG(__nv_bfloat16, 2);
+      else if (nv <= 4) EMB_REG(__nv_bfloat16, 4); else EMB_REG(__nv_bfloat16, 8);
+    } else {
+      if (nv <= 1) EMB_REG(float, 1); else if (nv <= 2) EMB_REG(float, 2);
+      else if (nv <= 4) EMB_REG(float, 4); else EMB_REG(float, 8);
+    }
+#undef EMB_REG
+  } else if (cols <= kSmallCols) {            // short rows: packed per warp, in registers
+    if (dtype)
+      rmsnorm_act_fwd_short_kernel<__nv_bfloat16, 1><<<grid, kThreads, 0, s>>>(
+          (const __nv_bfloat16*)x, scale, bias, (__nv_bfloat16*)y, rows, cols, act, eps);
+    else
+      rmsnorm_act_fwd_short_kernel<float, 2><<<grid, kThreads, 0, s>>>(
+          (const float*)x, scale, bias, (float*)y, rows, cols, act, eps);
+  } else if (dtype)
     rmsnorm_act_fwd_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(
         (const __nv_bfloat16*)x, scale, bias, (__nv_bfloat16*)y, rows, cols, act, eps);
   else
