@@ -235,24 +235,25 @@ rmsnorm_act_fwd_short_kernel(const T* __restrict__ x, const float* __restrict__ 
 // occupancy and also reduces the bias gradient; PL = 64 (cols <= 2048: dense
 // layers, ~1e3 long rows) re-reads the row from L1 between the sweeps.
 template <typename T, int PL>
-__global__ void __launch_bounds__(kThreads, PL <= 8 ? 6 : 1)
+__global__ void __launch_bounds__(kThreads, PL <= 8 ? 6 : (PL <= 32 ? 2 : 1))
 rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                        const float* __restrict__ bias, const T* __restrict__ gy,
                        T* __restrict__ gx, float* __restrict__ gscale, float* __restrict__ gbias,
                        int64_t rows, int cols, int act, float eps) {
   constexpr int N = Vec<T>::N;
-  constexpr bool SMALL = PL <= 8;
+  constexpr bool SMALL = PL <= 32;         // the row (x and g_y) stays in registers
+  constexpr bool BIAS = PL <= 8;           // bias gradient (convolution channels only)
   extern __shared__ float part_raw[];      // [kWarps][cols] (x2 with a bias)
   const int gs_ = group_size(cols, N), rpw = 32 / gs_;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lg = lane % gs_, grp = lane / gs_;
   const int64_t warp = (int64_t)blockIdx.x * kWarps + wid;
   const int64_t nwarps = (int64_t)gridDim.x * kWarps;
   float gsc[PL];                           // scale-gradient partials of this lane's columns
-  float gbi[SMALL ? PL : 1];               // bias-gradient partials
+  float gbi[BIAS ? PL : 1];                // bias-gradient partials
 #pragma unroll
   for (int i = 0; i < PL; ++i) gsc[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < (SMALL ? PL : 1); ++i) gbi[i] = 0.f;
+  for (int i = 0; i < (BIAS ? PL : 1); ++i) gbi[i] = 0.f;
   for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
     const int64_t r = r0 + grp;
     const bool live = r < rows;
@@ -276,7 +277,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
         if (c < cols) {
 #pragma unroll
           for (int i = 0; i < N; ++i) {
-            if (bias) v[j * N + i] += bias[c + i];
+            if (BIAS && bias) v[j * N + i] += bias[c + i];
             ss = fmaf(v[j * N + i], v[j * N + i], ss);
           }
         }
@@ -308,7 +309,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
 #pragma unroll
           for (int i = 0; i < N; ++i) {
             o[i] = rstd * (g[j * N + i] - v[j * N + i] * mean);
-            gbi[j * N + i] += o[i];
+            if (BIAS) gbi[j * N + i] += o[i];
           }
           Vec<T>::store(or_ + c, o);
         }
@@ -366,7 +367,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
       float v = gsc[j * N + i];
       for (int o = gs_; o < 32; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (c < cols && grp == 0) part_raw[(size_t)wid * cols + c + i] = v;
-      if (SMALL && gbias) {
+      if (BIAS && gbias) {
         float w = gbi[j * N + i];
         for (int o = gs_; o < 32; o <<= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
         if (c < cols && grp == 0) part_b[(size_t)wid * cols + c + i] = w;
@@ -379,7 +380,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) s += part_raw[(size_t)w * cols + c];
     atomicAdd(gscale + c, s);
-    if (SMALL && gbias) {
+    if (BIAS && gbias) {
       float sb = 0.f;
 #pragma unroll
       for (int w = 0; w < kWarps; ++w) sb += part_b[(size_t)w * cols + c];
@@ -419,7 +420,7 @@ int launch_bwd(const char* who, const void* x, const float* scale, const float* 
                cudaStream_t s) {
   auto fn = rmsnorm_act_bwd_kernel<T, PL>;
   static bool attr_set = false;
-  const int max_cols = PL <= 8 ? kSmallCols : kMaxCols;
+  const int max_cols = PL <= 8 ? kSmallCols : (PL <= 32 ? 1024 : kMaxCols);
   if (!attr_set) {
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(2 * kWarps * max_cols * sizeof(float))) != cudaSuccess)
@@ -427,7 +428,7 @@ int launch_bwd(const char* who, const void* x, const float* scale, const float* 
     attr_set = true;
   }
   const size_t smem = (size_t)(gbias ? 2 : 1) * kWarps * cols * sizeof(float);
-  fn<<<grid_for(rows, PL <= 8 ? 6 : 2), kThreads, smem, s>>>(
+  fn<<<grid_for(rows, PL <= 8 ? 6 : (PL <= 32 ? 4 : 2)), kThreads, smem, s>>>(
       (const T*)x, scale, bias, (const T*)gy, (T*)gx, gscale, gbias, rows, cols, act, eps);
   return 0;
 }
@@ -490,6 +491,9 @@ extern "C" int emb_rmsnorm_act_bwd(const void* x, const float* scale, const floa
   if (cols <= kSmallCols) {
     e = dtype ? launch_bwd<__nv_bfloat16, 8>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s)
               : launch_bwd<float, 8>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s);
+  } else if (cols <= 1024) {
+    e = dtype ? launch_bwd<__nv_bfloat16, 32>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s)
+              : launch_bwd<float, 32>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s);
   } else {
     e = dtype ? launch_bwd<__nv_bfloat16, 64>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s)
               : launch_bwd<float, 64>(who, x, scale, bias, gy, gx, gscale, gbias, rows, cols, act, eps, s);

@@ -11,6 +11,7 @@ computed by the caller with ordinary (B*T)-row GEMMs and passed in.
 import ctypes
 import math
 
+import numpy as np
 import torch
 
 from .. import _lib
@@ -130,6 +131,126 @@ def pack_matrix(w, engine, ncta, unit=1, groups=1):
   return x.permute(4, 0, 5, 6, 2, 1, 3).contiguous()      # cta, kstep, tile, nn, kq, reg, half
 
 
+# ---------------------------------------------------------------- fused packing
+FUSED_PACK = True      # False: the op-by-op torch formulation below (tests compare the two)
+# The bf16 engines pack straight from the flat fp32 parameter buffer with one
+# kernel per matrix (emb_pack_tiles, csrc/pack.cu).  A logical (K, N) matrix is
+# described per n8 column tile by (element offset of (k=0, n=8t), k stride,
+# n stride) -- block-diagonal layers, gate-interleaved column orders, column
+# concatenations and transposes are all just different tables.
+
+def _tiles_rowmajor(off, N, cols=None, first=0):
+  """Columns [first, first+cols) of a row-major (K, N) tensor at `off`."""
+  cols = N if cols is None else cols
+  t = np.arange(cols // 8, dtype=np.int64)
+  return off + first + 8 * t, np.full(len(t), N, np.int32), np.ones(len(t), np.int32)
+
+
+def _tiles_transposed(off, rows, K):
+  """The transpose of a row-major (rows, K) tensor at `off`: logical (K, rows)."""
+  t = np.arange(rows // 8, dtype=np.int64)
+  return off + 8 * t * K, np.ones(len(t), np.int32), np.full(len(t), K, np.int32)
+
+
+def _cat_tiles(*parts):
+  return tuple(np.concatenate([p[i] for p in parts]) for i in range(3))
+
+
+def slot_tables(segments, engine, ncta, unit=1, groups=1):
+  """Per CTA slot (cta*per + tile) the (offset, k stride, n stride) of its tile,
+  offset -1 for padding: (per, [(first k-step, k-steps, off, kstride, nstride)])."""
+  tiles = len(segments[0][2][0])
+  per, ids = tile_assignment(tiles, ncta, unit, groups)
+  if engine == ENG_BF16:          # TMA engine: zero tiles up to a multiple of the tile groups
+    padded = pad_tiles(per, unit)
+    ids = [row + [-1] * (padded - per) for row in ids]
+    per = padded
+  ids = np.asarray(ids, np.int64).reshape(-1)
+  real = np.maximum(ids, 0)
+  tabs = []
+  for first, count, (off, ks, ns) in segments:
+    assert len(off) == tiles, (len(off), tiles)
+    tabs.append((first, count, np.where(ids >= 0, off[real], -1).astype(np.int64),
+                 ks[real].astype(np.int32), ns[real].astype(np.int32)))
+  return per, tabs
+
+
+def pack_tiles(store, name, ksteps, segments, engine, ncta, unit=1, groups=1):
+  """segments: [(first k-step, k-steps, (off, kstride, nstride) per logical tile)];
+  every segment covers all N/8 tiles.  Returns the same bytes as pack_matrix()."""
+  lib = _lib.load()
+  dev = store.master.device
+  tables = store.__dict__.setdefault('_pack_tables', {})    # offsets belong to this store
+  key = (name, ncta, unit, groups, engine)
+  hit = tables.get(key)
+  if hit is None:                      # host -> device once (never inside a stream capture)
+    per, tabs = slot_tables(segments, engine, ncta, unit, groups)
+    tabs = [(first, count) + tuple(torch.from_numpy(x).to(dev) for x in rest)
+            for first, count, *rest in tabs]
+    lib.emb_pack_tiles.argtypes = [_vp, _vp, _vp, _vp, _vp, ctypes.c_int64] + [ctypes.c_int32] * 4 + [_vp]
+    lib.emb_pack_tiles.restype = ctypes.c_int
+    hit = tables[key] = (per, tabs)
+  per, tabs = hit
+  dst = torch.empty((ncta, ksteps, per, 8, 4, 2, 2), dtype=torch.bfloat16, device=dev)
+  stream = torch.cuda.current_stream(dev).cuda_stream
+  for first, count, off, ks, ns in tabs:
+    _lib.check(lib.emb_pack_tiles(
+        store.master.data_ptr(), off.data_ptr(), ks.data_ptr(), ns.data_ptr(), dst.data_ptr(),
+        ncta * per, per, first, count, ksteps, stream))
+  return dst
+
+
+def _pack_fused(store, cfg, engine, ncta, pack_tiles=pack_tiles):
+  D, G, H, SC = cfg.deter, cfg.blocks, cfg.hidden, cfg.stoch * cfg.classes
+  Dg = D // G
+  o = store.offsets
+  Kh = store.specs['dyn/dynhid0/kernel'][0][1]
+  keep = Dg + 2 * H if engine == ENG_BF16 else Kh     # the TMA engine hoists the action rows
+  g = np.arange(G, dtype=np.int64)
+  # dynhid0 (G, Kh, Dg) -> (keep, D): column g*Dg + j
+  hid = (np.repeat(o['dyn/dynhid0/kernel'] + g * Kh * Dg, Dg // 8) + np.tile(8 * np.arange(Dg // 8), G),
+         np.full(D // 8, Dg, np.int32), np.ones(D // 8, np.int32))
+  # dyngru (G, Dg, 3Dg) -> (Dg, 3D): tiles ordered (group, j/8, gate)
+  gg, j8, gate = np.meshgrid(g, np.arange(Dg // 8), np.arange(3), indexing='ij')
+  gru = ((o['dyn/dyngru/kernel'] + gg * Dg * 3 * Dg + gate * Dg + 8 * j8).reshape(-1).astype(np.int64),
+         np.full(3 * D // 8, 3 * Dg, np.int32), np.ones(3 * D // 8, np.int32))
+  ph1 = _cat_tiles(_tiles_rowmajor(o['dyn/obs0/kernel'], H), _tiles_rowmajor(o['dyn/dynin0/kernel'], H))
+  logit = _tiles_rowmajor(o['dyn/obslogit/kernel'], SC)
+  pk = lambda name, K, tiles, **kw: pack_tiles(store, name, K // 16, [(0, K // 16, tiles)], engine, ncta, **kw)
+  return dict(
+      w_ph1=pk('w_ph1', D, ph1), w_logit=pk('w_logit', H, logit),
+      w_hid=pk('w_hid', keep, hid, groups=G), w_gru=pk('w_gru', Dg, gru, unit=3, groups=G))
+
+
+def _pack_bwd_fused(store, cfg, engine, ncta, pack_tiles=pack_tiles):
+  D, G, H, SC = cfg.deter, cfg.blocks, cfg.hidden, cfg.stoch * cfg.classes
+  Dg = D // G
+  o = store.offsets
+  Kh = store.specs['dyn/dynhid0/kernel'][0][1]
+  keep = Dg + 2 * H
+  g = np.arange(G, dtype=np.int64)
+  # gru_t (3Dg, D): element (k, g*Dg + i) = dyngru[g, i, k]
+  gi, i8 = np.meshgrid(g, np.arange(Dg // 8), indexing='ij')
+  gru_t = ((o['dyn/dyngru/kernel'] + gi * Dg * 3 * Dg + 8 * i8 * 3 * Dg).reshape(-1).astype(np.int64),
+           np.ones(D // 8, np.int32), np.full(D // 8, 3 * Dg, np.int32))
+  # hid_t (Dg, G*keep): element (k, g*keep + r) = dynhid0[g, r, k]
+  gr, r8 = np.meshgrid(g, np.arange(keep // 8), indexing='ij')
+  hid_t = ((o['dyn/dynhid0/kernel'] + gr * Kh * Dg + 8 * r8 * Dg).reshape(-1).astype(np.int64),
+           np.ones(G * keep // 8, np.int32), np.full(G * keep // 8, Dg, np.int32))
+  pk = lambda name, K, tiles, **kw: pack_tiles(store, name, K // 16, [(0, K // 16, tiles)], engine, ncta, **kw)
+  # ph1_t (2H, D): rows [0, H) from obs0[:D], rows [H, 2H) from dynin0
+  wt_ph1 = pack_tiles(store, 'wt_ph1', 2 * H // 16, [
+      (0, H // 16, _tiles_transposed(o['dyn/obs0/kernel'], D, H)),
+      (H // 16, H // 16, _tiles_transposed(o['dyn/dynin0/kernel'], D, H))], engine, ncta)
+  return dict(
+      wt_in1=pk('wt_in1', H, _tiles_transposed(o['dyn/dynin1/kernel'], SC, H),
+                unit=(math.lcm(cfg.classes, 8) // 8 if engine == ENG_BF16 else 1)),
+      wt_logit=pk('wt_logit', SC, _tiles_transposed(o['dyn/obslogit/kernel'], H, SC)),
+      wt_ph1=wt_ph1,
+      wt_gru=pk('wt_gru', 3 * Dg, gru_t, groups=G),
+      wt_hid=pk('wt_hid', Dg, hid_t, groups=G))
+
+
 @torch.no_grad()
 def pack(store, cfg, engine, ncta):
   """The packed copies of the in-scan weights (dreamerv3/rssm.py:135-159, 81-86).
@@ -152,6 +273,9 @@ def pack(store, cfg, engine, ncta):
   gru = m('dyn/dyngru/kernel')                              # (G, Dg, 3*Dg), columns (gate, j)
   gru = gru.reshape(G, Dg, 3, Dg // 8, 8).permute(1, 0, 3, 2, 4).reshape(Dg, 3 * D)
   cd = f32 if engine == ENG_F32 else torch.bfloat16
+  if engine != ENG_F32 and FUSED_PACK:
+    return dict(**extra, **_pack_fused(store, cfg, engine, ncta),
+                w_in1=m('dyn/dynin1/kernel').to(cd).contiguous())
   return dict(
       **extra,
       w_ph1=pack_matrix(torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1), engine, ncta),
@@ -334,6 +458,8 @@ def pack_bwd(store, cfg, engine, ncta):
     keep_rows = Dg + 2 * H
     extra['w_hid_x2'] = hid[:, keep_rows:].permute(1, 0, 2).reshape(-1, D).to(torch.bfloat16)  # (H, D)
     hid = hid[:, :keep_rows]
+  if engine != ENG_F32 and FUSED_PACK:
+    return dict(**extra, **_pack_bwd_fused(store, cfg, engine, ncta))
   hid_t = hid.permute(2, 0, 1).reshape(Dg, G * hid.shape[1])
   return dict(
       **extra,

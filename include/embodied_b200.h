@@ -367,6 +367,19 @@ int emb_conv_patches_nhwc(const void* x, void* out, int64_t n, int32_t h, int32_
 int emb_conv_tapsum_nhwc(const void* z, const float* bias, void* y, int64_t n, int32_t h, int32_t w,
                          int32_t c, int32_t k, int32_t kp, int32_t up, int32_t dtype, void* stream);
 
+/* Weight packing for the RSSM scan kernels (embodied_b200/csrc/pack.cu): n8 column
+ * tiles of fp32 matrices living in one flat parameter buffer (the in-scan layers of
+ * dreamerv3/rssm.py:135-159, 81-86) -> per-CTA bf16 blocks in mma.m16n8k16 B-fragment
+ * order, the layout rssm_fwd_tma.cu / rssm_bwd_tma.cu stream:
+ *   dst[cta][ks_begin + kstep][tile][lane = nn*4 + kq][reg][half] =
+ *       bf16(base[slot_off[s] + k*slot_kstride[s] + nn*slot_nstride[s]]),  s = cta*per + tile,
+ *       k = kstep*16 + reg*8 + kq*2 + half, kstep in [0, ks_count); zeros where slot_off < 0.
+ * dst holds ks_total k-steps per CTA; several calls with different (base offsets,
+ * ks_begin) fill a matrix whose rows come from more than one tensor. */
+int emb_pack_tiles(const float* base, const int64_t* slot_off, const int32_t* slot_kstride,
+                   const int32_t* slot_nstride, void* dst, int64_t nslots, int32_t per,
+                   int32_t ks_begin, int32_t ks_count, int32_t ks_total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

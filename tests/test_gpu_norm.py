@@ -33,7 +33,7 @@ def test_forward(rows, cols, dtype, act):
   assert rel(got, want) < (1e-5 if dtype == torch.float32 else 2 ** -7)
 
 
-@pytest.mark.parametrize('shape', [(3, 8), (2, 5, 64), (1000, 128), (9, 4, 4, 256), (4, 2048)])
+@pytest.mark.parametrize('shape', [(3, 8), (2, 5, 64), (1000, 128), (9, 4, 4, 256), (300, 512), (37, 640), (2000, 1024), (4, 2048)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize('act', [True, False])
 def test_backward(shape, dtype, act):

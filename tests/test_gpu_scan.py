@@ -205,3 +205,26 @@ def test_engine_selection_by_model_size():
   assert not s400.supported
   s12 = scanlib.Scan(C.make('size12m'), Store(), scanlib.ENG_BF16)
   assert s12.engine == scanlib.ENG_BF16 and s12.supported
+
+
+@pytest.mark.parametrize('size', ['size12m', 'size200m'])
+@pytest.mark.parametrize('engine', ['ENG_BF16', 'ENG_LEGACY'])
+def test_pack_kernel_equals_the_torch_formulation(size, engine):
+  """emb_pack_tiles (csrc/pack.cu) straight from the flat master buffer vs the
+  cast + concat + gather + permute chain, bit for bit, for every in-scan matrix
+  (forward and transposed layouts, padded and plain blocks)."""
+  from embodied_b200.dreamerv3 import config as C
+  cfg = C.make(size)
+  engine = getattr(scanlib, engine)
+  store = paramlib.ParamStore(cfg, 'cuda', torch.float32, 5)
+  ncta = torch.cuda.get_device_properties(0).multi_processor_count
+  scanlib.FUSED_PACK = False
+  try:
+    want = {**scanlib.pack(store, cfg, engine, ncta), **scanlib.pack_bwd(store, cfg, engine, ncta)}
+  finally:
+    scanlib.FUSED_PACK = True
+  got = {**scanlib.pack(store, cfg, engine, ncta), **scanlib.pack_bwd(store, cfg, engine, ncta)}
+  assert set(got) == set(want)
+  for name in want:
+    assert got[name].shape == want[name].shape, name
+    assert torch.equal(got[name], want[name]), name
