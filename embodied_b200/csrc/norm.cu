@@ -36,6 +36,11 @@ template <> struct Vec<float> {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
   __device__ static float round(float x) { return x; }
+  __device__ static float silu(float n) { return n / (1.0f + expf(-n)); }
+  __device__ static float dsilu(float n) {
+    const float sg = 1.0f / (1.0f + expf(-n));
+    return sg * (1.0f + n * (1.0f - sg));
+  }
 };
 template <> struct Vec<__nv_bfloat16> {
   static constexpr int N = 8;
@@ -58,6 +63,12 @@ template <> struct Vec<__nv_bfloat16> {
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   __device__ static float round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+  // results are rounded to bf16 (2^-9): the fast exponential and reciprocal are exact enough
+  __device__ static float silu(float n) { return __fdividef(n, 1.0f + __expf(-n)); }
+  __device__ static float dsilu(float n) {
+    const float sg = __fdividef(1.0f, 1.0f + __expf(-n));
+    return sg * fmaf(n, 1.0f - sg, 1.0f);
+  }
 };
 
 // sum over the `gs` (power of two) consecutive lanes that share a row
@@ -72,11 +83,6 @@ __device__ __forceinline__ int group_size(int cols, int n) {
   return gs;
 }
 
-__device__ __forceinline__ float silu(float n) { return n / (1.0f + expf(-n)); }
-__device__ __forceinline__ float dsilu(float n) {
-  const float sg = 1.0f / (1.0f + expf(-n));
-  return sg * (1.0f + n * (1.0f - sg));
-}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -112,7 +118,7 @@ rmsnorm_act_fwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
       for (int i = 0; i < N; ++i) {
         if (bias) v[i] += bias[c + i];
         const float n = Vec<T>::round(v[i] * (rstd * scale[c + i]));   // cast back, then act (nets.py:397)
-        o[i] = act ? silu(n) : n;
+        o[i] = act ? Vec<T>::silu(n) : n;
       }
       Vec<T>::store(yr + c, o);
     }
@@ -164,7 +170,7 @@ rmsnorm_act_fwd_reg_kernel(const T* __restrict__ x, const float* __restrict__ sc
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float n = Vec<T>::round(v[k][i + q] * (rstd * sc[q]));
-            o[i + q] = act ? silu(n) : n;
+            o[i + q] = act ? Vec<T>::silu(n) : n;
           }
         }
         Vec<T>::store(yr + c, o);
@@ -196,34 +202,48 @@ rmsnorm_act_fwd_short_kernel(const T* __restrict__ x, const float* __restrict__ 
       bi[k][i] = (bias && c < cols) ? bias[c + i] : 0.f;
     }
   }
-  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
-    const int64_t r = r0 + grp;
-    const bool live = r < rows;
-    const T* xr = x + (live ? r : 0) * cols;
-    float v[NV][N];
-    float ss = 0.f;
+  constexpr int U = NV == 1 ? 2 : 1;      // row sets in flight per warp iteration
+  for (int64_t r0 = warp * rpw * U; r0 < rows; r0 += nwarps * rpw * U) {
+    float v[U][NV][N], rstd[U];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = (lg + gs * k) * N;
-      if (c < cols) {
-        Vec<T>::load(xr + c, v[k]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * rpw + grp;
+      const T* xr = x + (r < rows ? r : 0) * cols;
 #pragma unroll
-        for (int i = 0; i < N; ++i) { v[k][i] += bi[k][i]; ss = fmaf(v[k][i], v[k][i], ss); }
+      for (int k = 0; k < NV; ++k) {
+        const int c = (lg + gs * k) * N;
+        if (c < cols) Vec<T>::load(xr + c, v[u][k]);
       }
     }
-    const float rstd = rsqrtf(group_sum(ss, gs) / (float)cols + eps);
-    if (!live) continue;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c = (lg + gs * k) * N;
-      if (c < cols) {
-        float o[N];
+    for (int u = 0; u < U; ++u) {
+      float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const float n = Vec<T>::round(v[k][i] * (rstd * sc[k][i]));
-          o[i] = act ? silu(n) : n;
+      for (int k = 0; k < NV; ++k) {
+        const int c = (lg + gs * k) * N;
+        if (c < cols) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) { v[u][k][i] += bi[k][i]; ss = fmaf(v[u][k][i], v[u][k][i], ss); }
         }
-        Vec<T>::store(y + r * cols + c, o);
+      }
+      rstd[u] = rsqrtf(group_sum(ss, gs) / (float)cols + eps);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t r = r0 + u * rpw + grp;
+      if (r >= rows) continue;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c = (lg + gs * k) * N;
+        if (c < cols) {
+          float o[N];
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            const float n = Vec<T>::round(v[u][k][i] * (rstd[u] * sc[k][i]));
+            o[i] = act ? Vec<T>::silu(n) : n;
+          }
+          Vec<T>::store(y + r * cols + c, o);
+        }
       }
     }
   }
@@ -235,7 +255,7 @@ rmsnorm_act_fwd_short_kernel(const T* __restrict__ x, const float* __restrict__ 
 // occupancy and also reduces the bias gradient; PL = 64 (cols <= 2048: dense
 // layers, ~1e3 long rows) re-reads the row from L1 between the sweeps.
 template <typename T, int PL>
-__global__ void __launch_bounds__(kThreads, PL <= 8 ? 6 : (PL <= 32 ? 2 : 1))
+__global__ void __launch_bounds__(kThreads, PL <= 8 ? 3 : (PL <= 32 ? 2 : 1))
 rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                        const float* __restrict__ bias, const T* __restrict__ gy,
                        T* __restrict__ gx, float* __restrict__ gscale, float* __restrict__ gbias,
@@ -243,6 +263,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
   constexpr int N = Vec<T>::N;
   constexpr bool SMALL = PL <= 32;         // the row (x and g_y) stays in registers
   constexpr bool BIAS = PL <= 8;           // bias gradient (convolution channels only)
+  constexpr int U = PL <= 8 ? 2 : 1;       // row sets in flight per warp iteration
   extern __shared__ float part_raw[];      // [kWarps][cols] (x2 with a bias)
   const int gs_ = group_size(cols, N), rpw = 32 / gs_;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, lg = lane % gs_, grp = lane / gs_;
@@ -254,64 +275,94 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
   for (int i = 0; i < PL; ++i) gsc[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < (BIAS ? PL : 1); ++i) gbi[i] = 0.f;
-  for (int64_t r0 = warp * rpw; r0 < rows; r0 += nwarps * rpw) {
+  // convolution channels: scale and bias of this lane's columns live in registers
+  float scr[BIAS ? PL : 1], bir[BIAS ? PL : 1];
+  if (BIAS) {
+#pragma unroll
+    for (int j = 0; j < PL / N; ++j) {
+      const int c = lg * N + j * gs_ * N;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        scr[j * N + i] = c < cols ? scale[c + i] : 0.f;
+        bir[j * N + i] = (bias && c < cols) ? bias[c + i] : 0.f;
+      }
+    }
+  }
+  for (int64_t r0 = warp * rpw * U; r0 < rows; r0 += nwarps * rpw * U) {
     const int64_t r = r0 + grp;
     const bool live = r < rows;
     const T* xr = x + (live ? r : 0) * cols;
     const T* gr = gy + (live ? r : 0) * cols;
     T* or_ = gx + (live ? r : 0) * cols;
     if (SMALL) {
-      float v[PL], g[PL];
+      // U row sets per iteration: all loads are issued before the first reduction
+      float v[U][PL], g[U][PL], rstd[U];
 #pragma unroll
-      for (int j = 0; j < PL / N; ++j) {
-        const int c = lg * N + j * gs_ * N;
-        if (c < cols) {
-          Vec<T>::load(xr + c, *reinterpret_cast<float(*)[N]>(&v[j * N]));
-          Vec<T>::load(gr + c, *reinterpret_cast<float(*)[N]>(&g[j * N]));
-        }
-      }
-      float ss = 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int64_t ru = r0 + u * rpw + grp;
+        const int64_t rr = ru < rows ? ru : 0;
 #pragma unroll
-      for (int j = 0; j < PL / N; ++j) {
-        const int c = lg * N + j * gs_ * N;
-        if (c < cols) {
-#pragma unroll
-          for (int i = 0; i < N; ++i) {
-            if (BIAS && bias) v[j * N + i] += bias[c + i];
-            ss = fmaf(v[j * N + i], v[j * N + i], ss);
+        for (int j = 0; j < PL / N; ++j) {
+          const int c = lg * N + j * gs_ * N;
+          if (c < cols) {
+            Vec<T>::load(x + rr * cols + c, *reinterpret_cast<float(*)[N]>(&v[u][j * N]));
+            Vec<T>::load(gy + rr * cols + c, *reinterpret_cast<float(*)[N]>(&g[u][j * N]));
           }
         }
       }
-      const float rstd = rsqrtf(group_sum(ss, gs_) / (float)cols + eps);
-      float dot = 0.f;
 #pragma unroll
-      for (int j = 0; j < PL / N; ++j) {
-        const int c = lg * N + j * gs_ * N;
-        if (c < cols) {
+      for (int u = 0; u < U; ++u) {
+        float ss = 0.f;
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            const float xh = v[j * N + i] * rstd, sc = scale[c + i];
-            const float gn = act ? g[j * N + i] * dsilu(Vec<T>::round(xh * sc)) : g[j * N + i];
-            if (live) gsc[j * N + i] = fmaf(gn, xh, gsc[j * N + i]);
-            dot = fmaf(gn * sc, xh, dot);
-            v[j * N + i] = xh;
-            g[j * N + i] = gn * sc;
+        for (int j = 0; j < PL / N; ++j) {
+          const int c = lg * N + j * gs_ * N;
+          if (c < cols) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              if (BIAS) v[u][j * N + i] += bir[j * N + i];
+              ss = fmaf(v[u][j * N + i], v[u][j * N + i], ss);
+            }
           }
         }
+        rstd[u] = rsqrtf(group_sum(ss, gs_) / (float)cols + eps);
       }
-      const float mean = group_sum(dot, gs_) / (float)cols;
-      if (!live) continue;
 #pragma unroll
-      for (int j = 0; j < PL / N; ++j) {
-        const int c = lg * N + j * gs_ * N;
-        if (c < cols) {
-          float o[N];
+      for (int u = 0; u < U; ++u) {
+        const bool live_u = r0 + u * rpw + grp < rows;
+        float dot = 0.f;
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            o[i] = rstd * (g[j * N + i] - v[j * N + i] * mean);
-            if (BIAS) gbi[j * N + i] += o[i];
+        for (int j = 0; j < PL / N; ++j) {
+          const int c = lg * N + j * gs_ * N;
+          if (c < cols) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              const float xh = v[u][j * N + i] * rstd[u];
+              const float sc = BIAS ? scr[j * N + i] : scale[c + i];
+              const float gn = act ? g[u][j * N + i] * Vec<T>::dsilu(Vec<T>::round(xh * sc))
+                                   : g[u][j * N + i];
+              if (live_u) gsc[j * N + i] = fmaf(gn, xh, gsc[j * N + i]);
+              dot = fmaf(gn * sc, xh, dot);
+              v[u][j * N + i] = xh;
+              g[u][j * N + i] = gn * sc;
+            }
           }
-          Vec<T>::store(or_ + c, o);
+        }
+        const float mean = group_sum(dot, gs_) / (float)cols;
+        if (live_u) {
+          T* out = gx + (r0 + u * rpw + grp) * cols;
+#pragma unroll
+          for (int j = 0; j < PL / N; ++j) {
+            const int c = lg * N + j * gs_ * N;
+            if (c < cols) {
+              float o[N];
+#pragma unroll
+              for (int i = 0; i < N; ++i) {
+                o[i] = rstd[u] * (g[u][j * N + i] - v[u][j * N + i] * mean);
+                if (BIAS) gbi[j * N + i] += o[i];
+              }
+              Vec<T>::store(out + c, o);
+            }
+          }
         }
       }
       continue;
@@ -335,7 +386,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const float xh = v[i] * rstd, sc = scale[c + i];
-          const float gn = act ? g[i] * dsilu(Vec<T>::round(xh * sc)) : g[i];
+          const float gn = act ? g[i] * Vec<T>::dsilu(Vec<T>::round(xh * sc)) : g[i];
           if (live) gsc[j * N + i] = fmaf(gn, xh, gsc[j * N + i]);
           dot = fmaf(gn * sc, xh, dot);
         }
@@ -350,7 +401,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
 #pragma unroll
       for (int i = 0; i < N; ++i) {
         const float xh = v[i] * rstd, sc = scale[c + i];
-        const float gn = act ? g[i] * dsilu(Vec<T>::round(xh * sc)) : g[i];
+        const float gn = act ? g[i] * Vec<T>::dsilu(Vec<T>::round(xh * sc)) : g[i];
         o[i] = rstd * (sc * gn - xh * mean);
       }
       Vec<T>::store(or_ + c, o);
@@ -428,7 +479,7 @@ int launch_bwd(const char* who, const void* x, const float* scale, const float* 
     attr_set = true;
   }
   const size_t smem = (size_t)(gbias ? 2 : 1) * kWarps * cols * sizeof(float);
-  fn<<<grid_for(rows, PL <= 8 ? 6 : (PL <= 32 ? 4 : 2)), kThreads, smem, s>>>(
+  fn<<<grid_for(rows, PL <= 8 ? 3 : (PL <= 32 ? 4 : 2)), kThreads, smem, s>>>(
       (const T*)x, scale, bias, (const T*)gy, (T*)gx, gscale, gbias, rows, cols, act, eps);
   return 0;
 }

@@ -31,82 +31,166 @@ namespace {
 
 constexpr int kThreads = 256;
 
-// one thread = one 16-byte vector of the output row (VEC elements)
-// (H, W) = the OUTPUT grid; x lives on the (H*up, W*up) grid.  One thread = one
-// 16-byte vector of the output row; 32-bit index arithmetic, K a compile-time
-// constant (divisions by K become multiplies), (tap, channel) advanced incrementally.
-template <typename T, int VEC, int K>
+// Both kernels work a group of R output rows of one image at a time: the input rows
+// the group touches are staged in shared memory with a zero halo (coalesced reads,
+// no bounds checks afterwards, each input row read ~once instead of K times), and
+// the output rows are written as consecutive vectors.  Everything that depends only
+// on the column of the output row -- which tile cells a thread's vector gathers --
+// is computed once per kernel: these kernels are bound by instruction issue, not by
+// HBM, unless the per-element work is a handful of instructions.
+
+// (H, W) = the OUTPUT grid; x lives on the (H*UP, W*UP) grid.  Tile = the
+// R*UP + K - 1 input rows [yy0*UP - K/2, ..] x (W*UP + K - 1) pixels x C, followed by
+// UP rows of zeros that the padding columns (>= K*K*C) read.  Thread t owns vector
+// column t % (KP/VEC) of the pixels t / (KP/VEC) + i * (threads / (KP/VEC)).
+template <typename T, int VEC, int K, int UP>
 __global__ void __launch_bounds__(kThreads)
-patches_kernel(const T* __restrict__ x, T* __restrict__ out, uint32_t nvec, int H, int W, int C,
-               int KP, int sign, int up) {
-  const uint32_t vpr = KP / VEC;
+patches_kernel(const T* __restrict__ x, T* __restrict__ out, int groups_total, int H, int W, int C,
+               int KP, int sign, int R) {
+  extern __shared__ __align__(16) unsigned char tile_raw[];
+  T* tile = reinterpret_cast<T*>(tile_raw);
   constexpr int taps = K * K, half = K / 2;
-  const int HX = H * up, WX = W * up;
-  for (uint32_t o = blockIdx.x * kThreads + threadIdx.x; o < nvec; o += gridDim.x * kThreads) {
-    const uint32_t p = o / vpr, v = o - p * vpr;
-    const uint32_t row = p / W;
-    const int xx = (int)(p - row * W), yy = (int)(row % H);
-    const uint32_t img = row / H;
-    const T* xi = x + (size_t)img * HX * WX * C;
-    int tap = (int)(v * VEC) / C, c = (int)(v * VEC) - tap * C;
-    T vals[VEC];
+  const int HX = H * UP, WX = W * UP;
+  const int TWC = (WX + 2 * half) * C;
+  const int TR = R * UP + K - 1;           // real rows of the tile
+  const int vpr = KP / VEC, ppp = kThreads / vpr;
+  const int v = threadIdx.x % vpr, px0 = threadIdx.x / vpr;
+  const int gpi = (H + R - 1) / R;         // groups per image
+  int offs[VEC];
+  {
+    int tap = (v * VEC) / C, c = v * VEC - tap * C;
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
-      float val = 0.f;
       if (tap < taps) {
-        const int dy = tap / K - half, dx = tap % K - half;
-        if (up == 1) {
-          const int sy = yy + sign * dy, sx = xx + sign * dx;
-          if (sy >= 0 && sy < HX && sx >= 0 && sx < WX) val = (float)xi[(sy * WX + sx) * C + c];
-        } else {
-          for (int uy = 0; uy < 2; ++uy) {
-            const int sy = yy * 2 + uy + sign * dy;
-            if (sy < 0 || sy >= HX) continue;
-            for (int ux = 0; ux < 2; ++ux) {
-              const int sx = xx * 2 + ux + sign * dx;
-              if (sx >= 0 && sx < WX) val += (float)xi[(sy * WX + sx) * C + c];
-            }
-          }
-        }
+        const int dyi = tap / K, dxi = tap - dyi * K;
+        offs[i] = (half + sign * (dyi - half)) * TWC + (half + sign * (dxi - half)) * C + c;
+      } else {
+        offs[i] = -1;                      // padding column
       }
-      vals[i] = T(val);
       if (++c == C) { c = 0; ++tap; }
     }
-    *reinterpret_cast<uint4*>(out + (size_t)p * KP + v * VEC) = *reinterpret_cast<const uint4*>(vals);
+  }
+  for (int j = threadIdx.x; j < UP * TWC; j += kThreads) tile[TR * TWC + j] = T(0.f);
+  for (int g = blockIdx.x; g < groups_total; g += gridDim.x) {
+    const int img = g / gpi, yy0 = (g - img * gpi) * R;
+    const int nrows = min(R, H - yy0);
+    const T* xi = x + (size_t)img * HX * WX * C;
+    const int y0 = yy0 * UP - half;
+    __syncthreads();                       // the previous group's readers are done
+    for (int tr = 0; tr < nrows * UP + K - 1; ++tr) {
+      const int sy = y0 + tr;
+      const bool row_ok = sy >= 0 && sy < HX;
+      const T* src = xi + (size_t)(row_ok ? sy : 0) * WX * C;
+      for (int j = threadIdx.x; j < TWC; j += kThreads) {
+        const int jj = j - half * C;
+        tile[tr * TWC + j] = (row_ok && jj >= 0 && jj < WX * C) ? src[jj] : T(0.f);
+      }
+    }
+    __syncthreads();
+    if (px0 < ppp) {
+      T* orow = out + ((size_t)img * H + yy0) * W * KP + v * VEC;
+      int ry = 0, xx = px0;
+      while (xx >= W) { xx -= W; ++ry; }
+      while (ry < nrows) {
+        const T* q = tile + ry * UP * TWC + xx * UP * C;
+        const T* qz = tile + TR * TWC + xx * UP * C;      // same column of the zero rows
+        T vals[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const T* qi = offs[i] >= 0 ? q + offs[i] : qz;
+          if (UP == 1) {
+            vals[i] = qi[0];
+          } else {                         // the 2x2 block of this low-resolution pixel
+            float val = (float)qi[0];
+            val += (float)qi[C];
+            val += (float)qi[TWC];
+            val += (float)qi[TWC + C];
+            vals[i] = T(val);
+          }
+        }
+        *reinterpret_cast<uint4*>(orow + ((size_t)ry * W + xx) * KP) = *reinterpret_cast<const uint4*>(vals);
+        xx += ppp;
+        while (xx >= W) { xx -= W; ++ry; }
+      }
+    }
   }
 }
 
-// (H, W) = the OUTPUT grid; z lives on the (H/up, W/up) grid.  One thread = one
-// output pixel, all C <= 4 channels (fp32 accumulation).
-template <typename T, int K>
+// (H, W) = the OUTPUT grid; z lives on the (H/UP, W/UP) grid.  Tile = the z rows the
+// group's taps reach x (W/UP pixels + halo) x KP columns, copied as 4-element vectors;
+// pixels are KP + 4 elements apart in the tile so that the threads of a warp (one
+// output pixel each, same tap) read different banks.  One thread = one output pixel,
+// all C <= 4 channels, taps summed (dy, dx)-major in fp32.
+template <typename T> struct Quad;
+template <> struct Quad<float> { using type = float4; };
+template <> struct Quad<__nv_bfloat16> { using type = uint2; };
+
+template <typename T, int K, int UP>
 __global__ void __launch_bounds__(kThreads)
 tapsum_kernel(const T* __restrict__ z, const float* __restrict__ bias, T* __restrict__ y,
-              uint32_t pixels, int H, int W, int C, int KP, int up) {
+              int groups_total, int H, int W, int C, int KP, int R) {
+  using Q = typename Quad<T>::type;
+  extern __shared__ __align__(16) unsigned char tile_raw[];
+  T* tile = reinterpret_cast<T*>(tile_raw);
   constexpr int half = K / 2;
-  const int HZ = H / up, WZ = W / up;
-  for (uint32_t p = blockIdx.x * kThreads + threadIdx.x; p < pixels; p += gridDim.x * kThreads) {
-    const uint32_t row = p / W;
-    const int xx = (int)(p - row * W), yy = (int)(row % H);
-    const uint32_t img = row / H;
+  constexpr int hal = (half + UP - 1) / UP;  // z pixels / rows reached past either end
+  const int HZ = H / UP, WZ = W / UP;
+  const int TS = KP + 4, KV = KP / 4;        // tile pixel stride (elements), quads per pixel
+  const int TW = WZ + 2 * hal, TWS = TW * TS;
+  const int gpi = (H + R - 1) / R;
+  // this thread's walk over a tile row in steps of kThreads quads: (pixel, quad) pairs
+  const int tx0 = threadIdx.x / KV, e0 = threadIdx.x - tx0 * KV;
+  const int dtx = kThreads / KV, de = kThreads - dtx * KV;
+  float b[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) b[c] = (bias && c < C) ? bias[c] : 0.f;
+  for (int g = blockIdx.x; g < groups_total; g += gridDim.x) {
+    const int img = g / gpi, yy0 = (g - img * gpi) * R;
+    const int nrows = min(R, H - yy0);
     const T* zi = z + (size_t)img * HZ * WZ * KP;
-    float acc[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c] = (bias && c < C) ? bias[c] : 0.f;
-#pragma unroll
-    for (int dy = 0; dy < K; ++dy) {
-      const int sy = yy + dy - half;
-      if (sy < 0 || sy >= H) continue;
-#pragma unroll
-      for (int dx = 0; dx < K; ++dx) {
-        const int sx = xx + dx - half;
-        if (sx < 0 || sx >= W) continue;
-        const T* q = zi + (size_t)((sy / up) * WZ + sx / up) * KP + (dy * K + dx) * C;
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-          if (c < C) acc[c] += (float)q[c];
+    const int zr0 = (yy0 - half + UP * hal) / UP - hal;          // first z row (may be < 0)
+    const int nz = (yy0 + nrows - 1 + half) / UP - zr0 + 1;
+    __syncthreads();
+    for (int zr = 0; zr < nz; ++zr) {
+      const int zy = zr0 + zr;
+      const bool row_ok = zy >= 0 && zy < HZ;
+      const T* src = zi + (size_t)(row_ok ? zy : 0) * WZ * KP;
+      int tx = tx0, e = e0;
+      for (int j = threadIdx.x; j < TW * KV; j += kThreads) {
+        const int zx = tx - hal;
+        Q val = {};
+        if (row_ok && zx >= 0 && zx < WZ) val = *reinterpret_cast<const Q*>(src + zx * KP + e * 4);
+        *reinterpret_cast<Q*>(tile + zr * TWS + tx * TS + e * 4) = val;
+        tx += dtx; e += de;
+        if (e >= KV) { e -= KV; ++tx; }
       }
     }
-    for (int c = 0; c < C; ++c) y[(size_t)p * C + c] = T(acc[c]);
+    __syncthreads();
+    int ry = 0, xx = threadIdx.x;
+    while (xx >= W) { xx -= W; ++ry; }
+    while (ry < nrows) {
+      const int yy = yy0 + ry;
+      float acc[4] = {b[0], b[1], b[2], b[3]};
+#pragma unroll
+      for (int dyi = 0; dyi < K; ++dyi) {
+        const int sy = yy + dyi - half;
+        if (sy < 0 || sy >= H) continue;
+        const T* q = tile + (sy / UP - zr0) * TWS + dyi * K * C;
+#pragma unroll
+        for (int dxi = 0; dxi < K; ++dxi) {
+          const T* qq = q + ((xx + dxi - half + UP * hal) / UP) * TS + dxi * C;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < C) acc[c] += (float)qq[c];
+        }
+      }
+      T* o = y + (((size_t)img * H + yy) * W + xx) * C;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) o[c] = T(acc[c]);
+      xx += kThreads;
+      while (xx >= W) { xx -= W; ++ry; }
+    }
   }
 }
 
@@ -131,9 +215,30 @@ int prepare(const char* who, int64_t n, int h, int w, int c, int k, int kp, int 
   return 0;
 }
 
-unsigned grid_for(int64_t items) {
-  const int64_t want = (items + kThreads - 1) / kThreads, cap = (int64_t)g_sms * 16;
-  return (unsigned)(want < cap ? (want < 1 ? 1 : want) : cap);
+constexpr size_t kMaxTile = 48 * 1024;     // shared-memory tile of one row group
+constexpr int kMaxGroupRows = 8;
+
+unsigned grid_for(int64_t groups) {
+  const int64_t cap = (int64_t)g_sms * 8;
+  return (unsigned)(groups < cap ? (groups < 1 ? 1 : groups) : cap);
+}
+
+size_t patches_tile(int r, int w, int c, int k, int up, int dtype) {
+  return (size_t)(r * up + k - 1 + up) * (w * up + k - 1) * c * (dtype ? 2 : 4);
+}
+
+size_t tapsum_tile(int r, int w, int kp, int k, int up, int dtype) {
+  const int hal = (k / 2 + up - 1) / up;
+  const int nz = (r + k - 1 + up - 1) / up + 1;      // z rows a group can touch (upper bound)
+  return (size_t)nz * (w / up + 2 * hal) * (kp + 4) * (dtype ? 2 : 4);
+}
+
+// rows per group: as many as the tile budget allows, at most kMaxGroupRows; 0 = none fit
+template <typename F>
+int group_rows(int h, F tile_bytes) {
+  int r = h < kMaxGroupRows ? h : kMaxGroupRows;
+  while (r > 0 && tile_bytes(r) > kMaxTile) r >>= 1;
+  return r;
 }
 
 }  // namespace
@@ -146,19 +251,24 @@ extern "C" int emb_conv_patches_nhwc(const void* x, void* out, int64_t n, int32_
   if (sign != 1 && sign != -1) return emb::fail(-1, "%s: sign=%d", who, sign);
   if (up != 1 && up != 2) return emb::fail(-1, "%s: up=%d", who, up);
   if ((uintptr_t)out & 15) return emb::fail(-1, "%s: out must be 16-byte aligned", who);
-  const int64_t pixels = n * h * w;
-  if (pixels == 0) return 0;
+  if (n * h == 0) return 0;
+  if (kp / (dtype ? 8 : 4) > kThreads) return emb::fail(-1, "%s: kp=%d too wide", who, kp);
+  const int r = group_rows(h, [&](int rr) { return patches_tile(rr, w, c, k, up, dtype); });
+  if (r == 0)
+    return emb::fail(-1, "%s: one %d-pixel row of %d channels does not fit a %zu-byte tile", who,
+                     w * up, c, kMaxTile);
+  const size_t tile = patches_tile(r, w, c, k, up, dtype);
+  const int64_t rows = n * ((h + r - 1) / r);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype) {
-    const int64_t nvec = pixels * (kp / 8);
-    auto fn = k == 5 ? patches_kernel<__nv_bfloat16, 8, 5> : patches_kernel<__nv_bfloat16, 8, 3>;
-    fn<<<grid_for(nvec), kThreads, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, (uint32_t)nvec,
-                                           h, w, c, kp, sign, up);
+    using B = __nv_bfloat16;
+    auto fn = k == 5 ? (up == 2 ? patches_kernel<B, 8, 5, 2> : patches_kernel<B, 8, 5, 1>)
+                     : (up == 2 ? patches_kernel<B, 8, 3, 2> : patches_kernel<B, 8, 3, 1>);
+    fn<<<grid_for(rows), kThreads, tile, s>>>((const B*)x, (B*)out, (int)rows, h, w, c, kp, sign, r);
   } else {
-    const int64_t nvec = pixels * (kp / 4);
-    auto fn = k == 5 ? patches_kernel<float, 4, 5> : patches_kernel<float, 4, 3>;
-    fn<<<grid_for(nvec), kThreads, 0, s>>>((const float*)x, (float*)out, (uint32_t)nvec, h, w, c, kp,
-                                           sign, up);
+    auto fn = k == 5 ? (up == 2 ? patches_kernel<float, 4, 5, 2> : patches_kernel<float, 4, 5, 1>)
+                     : (up == 2 ? patches_kernel<float, 4, 3, 2> : patches_kernel<float, 4, 3, 1>);
+    fn<<<grid_for(rows), kThreads, tile, s>>>((const float*)x, (float*)out, (int)rows, h, w, c, kp, sign, r);
   }
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
@@ -171,18 +281,25 @@ extern "C" int emb_conv_tapsum_nhwc(const void* z, const float* bias, void* y, i
   const char* who = "emb_conv_tapsum_nhwc";
   if (int e = prepare(who, n, h, w, c, k, kp, dtype)) return e;
   if ((up != 1 && up != 2) || h % up || w % up) return emb::fail(-1, "%s: up=%d h=%d w=%d", who, up, h, w);
-  if (c > 4) return emb::fail(-1, "%s: c=%d > 4 output channels", who, c);
-  const int64_t total = n * h * w;
-  if (total == 0) return 0;
+  if (n * h == 0) return 0;
+  const int r = group_rows(h, [&](int rr) { return tapsum_tile(rr, w, kp, k, up, dtype); });
+  if (r == 0)
+    return emb::fail(-1, "%s: one %d-pixel row of %d channels does not fit a %zu-byte tile", who, w,
+                     c, kMaxTile);
+  const size_t tile = tapsum_tile(r, w, kp, k, up, dtype);
+  const int64_t rows = n * ((h + r - 1) / r);
   cudaStream_t s = (cudaStream_t)stream;
+  if (kp / 4 > kThreads) return emb::fail(-1, "%s: kp=%d too wide", who, kp);
+  if ((uintptr_t)z & 15) return emb::fail(-1, "%s: z must be 16-byte aligned", who);
   if (dtype) {
-    auto fn = k == 5 ? tapsum_kernel<__nv_bfloat16, 5> : tapsum_kernel<__nv_bfloat16, 3>;
-    fn<<<grid_for(total), kThreads, 0, s>>>((const __nv_bfloat16*)z, bias, (__nv_bfloat16*)y,
-                                            (uint32_t)total, h, w, c, kp, up);
+    using B = __nv_bfloat16;
+    auto fn = k == 5 ? (up == 2 ? tapsum_kernel<B, 5, 2> : tapsum_kernel<B, 5, 1>)
+                     : (up == 2 ? tapsum_kernel<B, 3, 2> : tapsum_kernel<B, 3, 1>);
+    fn<<<grid_for(rows), kThreads, tile, s>>>((const B*)z, bias, (B*)y, (int)rows, h, w, c, kp, r);
   } else {
-    auto fn = k == 5 ? tapsum_kernel<float, 5> : tapsum_kernel<float, 3>;
-    fn<<<grid_for(total), kThreads, 0, s>>>((const float*)z, bias, (float*)y, (uint32_t)total, h, w, c,
-                                            kp, up);
+    auto fn = k == 5 ? (up == 2 ? tapsum_kernel<float, 5, 2> : tapsum_kernel<float, 5, 1>)
+                     : (up == 2 ? tapsum_kernel<float, 3, 2> : tapsum_kernel<float, 3, 1>);
+    fn<<<grid_for(rows), kThreads, tile, s>>>((const float*)z, bias, (float*)y, (int)rows, h, w, c, kp, r);
   }
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
