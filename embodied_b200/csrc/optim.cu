@@ -12,6 +12,7 @@
 // once and writes nu, mu, w.  28 bytes per parameter + 8 for the norms: HBM-bound.
 // Step-dependent scalars (lr, c1, c2) are read from DEVICE memory so the launch
 // can sit inside a CUDA graph.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -57,8 +58,9 @@ opt_norms_kernel(const float* __restrict__ g, const float* __restrict__ w,
 
 __global__ void __launch_bounds__(kThreads)
 opt_update_kernel(const float* __restrict__ g, float* __restrict__ w, float* __restrict__ nu,
-                  float* __restrict__ mu, const emb_opt_chunk* __restrict__ chunks,
-                  const float* __restrict__ norms, const float* __restrict__ hyper) {
+                  float* __restrict__ mu, __nv_bfloat16* __restrict__ low,
+                  const emb_opt_chunk* __restrict__ chunks, const float* __restrict__ norms,
+                  const float* __restrict__ hyper) {
   const emb_opt_chunk c = chunks[blockIdx.x];
   const float lr = hyper[0], c1 = hyper[1], c2 = hyper[2], b1 = hyper[3], b2 = hyper[4];
   const float eps = hyper[5], clip = hyper[6], pmin = hyper[7];
@@ -83,21 +85,29 @@ opt_update_kernel(const float* __restrict__ g, float* __restrict__ w, float* __r
     one(gi.x, wi.x, ni.x, mi.x); one(gi.y, wi.y, ni.y, mi.y);
     one(gi.z, wi.z, ni.z, mi.z); one(gi.w, wi.w, ni.w, mi.w);
     w4[i] = wi; nu4[i] = ni; mu4[i] = mi;
+    if (low) {                             // the compute-dtype copy the next forward pass reads
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(wi.x, wi.y), hi = __floats2bfloat162_rn(wi.z, wi.w);
+      uint2 packed;
+      packed.x = *reinterpret_cast<const uint32_t*>(&lo);
+      packed.y = *reinterpret_cast<const uint32_t*>(&hi);
+      reinterpret_cast<uint2*>(low + c.begin)[i] = packed;
+    }
   }
   for (int i = (n4 << 2) + threadIdx.x; i < c.count; i += kThreads) {
     const int64_t at = c.begin + i;
     float wi = w[at], ni = nu[at], mi = mu[at];
     one(g[at], wi, ni, mi);
     w[at] = wi; nu[at] = ni; mu[at] = mi;
+    if (low) low[at] = __float2bfloat16_rn(wi);
   }
 }
 
 }  // namespace
 
-extern "C" int emb_opt_agc_rms_momentum(const float* grad, float* param, float* nu, float* mu,
-                                        const emb_opt_chunk* chunks, int32_t nchunks,
-                                        float* norms, int32_t ntensors, const float* hyper,
-                                        void* stream) {
+extern "C" int emb_opt_agc_rms_momentum_cast(const float* grad, float* param, float* nu, float* mu,
+                                             void* param_bf16, const emb_opt_chunk* chunks,
+                                             int32_t nchunks, float* norms, int32_t ntensors,
+                                             const float* hyper, void* stream) {
   const char* who = "emb_opt_agc_rms_momentum";
   if (nchunks < 0 || ntensors < 0) return emb::fail(-1, "%s: negative sizes", who);
   if (nchunks == 0) return 0;
@@ -105,13 +115,24 @@ extern "C" int emb_opt_agc_rms_momentum(const float* grad, float* param, float* 
     return emb::fail(-1, "%s: NULL argument", who);
   if (((uintptr_t)grad | (uintptr_t)param | (uintptr_t)nu | (uintptr_t)mu) & 15)
     return emb::fail(-1, "%s: buffers must be 16-byte aligned", who);
+  if ((uintptr_t)param_bf16 & 7) return emb::fail(-1, "%s: param_bf16 must be 8-byte aligned", who);
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(norms, 0, sizeof(float) * 2 * ntensors, s) != cudaSuccess)
     return emb::fail_cuda(who);
   opt_norms_kernel<<<nchunks, kThreads, 0, s>>>(grad, param, chunks, norms);
   emb::count_launch();
-  opt_update_kernel<<<nchunks, kThreads, 0, s>>>(grad, param, nu, mu, chunks, norms, hyper);
+  opt_update_kernel<<<nchunks, kThreads, 0, s>>>(grad, param, nu, mu,
+                                                 reinterpret_cast<__nv_bfloat16*>(param_bf16), chunks,
+                                                 norms, hyper);
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;
+}
+
+extern "C" int emb_opt_agc_rms_momentum(const float* grad, float* param, float* nu, float* mu,
+                                        const emb_opt_chunk* chunks, int32_t nchunks,
+                                        float* norms, int32_t ntensors, const float* hyper,
+                                        void* stream) {
+  return emb_opt_agc_rms_momentum_cast(grad, param, nu, mu, nullptr, chunks, nchunks, norms,
+                                       ntensors, hyper, stream);
 }

@@ -46,8 +46,8 @@ class Optimizer:
     self._lib = _lib
     self.lib = _lib.load()
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
-    self.lib.emb_opt_agc_rms_momentum.argtypes = [vp, vp, vp, vp, vp, i32, vp, i32, vp, vp]
-    self.lib.emb_opt_agc_rms_momentum.restype = ctypes.c_int
+    self.lib.emb_opt_agc_rms_momentum_cast.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp]
+    self.lib.emb_opt_agc_rms_momentum_cast.restype = ctypes.c_int
     rows = []
     for ti, n in enumerate(names):
       off, size = st.offsets[n], int(np.prod(st.specs[n][0]))
@@ -98,10 +98,15 @@ class Optimizer:
     if self.fused:
       self.device_hyper()
       stream = torch.cuda.current_stream(st.device).cuda_stream
-      self._lib.check(self.lib.emb_opt_agc_rms_momentum(
+      # the kernel also writes the bf16 copy of the new parameters (ParamStore.get)
+      low = st.low_buffer() if st.compute_dtype == torch.bfloat16 else None
+      self._lib.check(self.lib.emb_opt_agc_rms_momentum_cast(
           st.grad.data_ptr(), st.master.data_ptr(), st.nu.data_ptr(), st.mu.data_ptr(),
+          None if low is None else low.data_ptr(),
           self.chunks.data_ptr(), self.nchunks, self.norms.data_ptr(), self.ntensors,
           self.hyper.data_ptr(), stream))
+      if low is not None:
+        st.low_is_fresh()
       return self.norms[0::2].sum().sqrt()
     t, lr = self._t, self._lr
     gn = torch.stack(torch._foreach_norm(self._grads))
@@ -114,6 +119,7 @@ class Optimizer:
     u = g / ((st.nu / (1 - cfg.beta2 ** t)).sqrt_() + cfg.eps)
     st.mu.mul_(cfg.beta1).add_(u, alpha=1 - cfg.beta1)
     st.master.add_(st.mu, alpha=-lr / (1 - cfg.beta1 ** t))
+    st.refresh_low()
     return torch.linalg.vector_norm(gn)
 
   @torch.no_grad()

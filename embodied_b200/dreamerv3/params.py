@@ -84,6 +84,22 @@ def shapes(cfg):
   return out
 
 
+class _CastParam(torch.autograd.Function):
+  """leaf (f32 master view) -> its compute-dtype copy `low`; backward accumulates
+  into the leaf's slice of the flat gradient buffer in one mixed-precision add
+  (what the cast's backward + AccumulateGrad would do in two kernels)."""
+
+  @staticmethod
+  def forward(ctx, leaf, low, grad):
+    ctx.grad = grad
+    return low.view(low.shape)
+
+  @staticmethod
+  def backward(ctx, g):
+    ctx.grad.add_(g)
+    return None, None, None
+
+
 class ParamStore:
 
   def __init__(self, cfg, device, compute_dtype, seed=0, values=None):
@@ -119,9 +135,11 @@ class ParamStore:
       leaf.grad = self._view(self.grad, name)
       self.w[name] = leaf
     self._cast = {}
+    self.low, self._low_seen = None, -1      # flat compute-dtype copy of master (get())
     # slow value network (utils.py:94-127): a separate small buffer
     self.slow = {n.replace('val/', 'slowval/', 1): self.view('master', n).clone()
                  for n in names if n.startswith('val/')}
+    self.refresh_low()       # allocated here, never inside a stream capture
 
   def _view(self, buf, name):
     shape = self.specs[name][0]
@@ -148,15 +166,39 @@ class ParamStore:
       self.view('master', name).copy_(x)
 
   def get(self, name):
-    """The parameter in the compute dtype (cast once per step; the cast is part
-    of the autograd graph, so bf16 gradients land in the f32 buffer as in
-    embodied/jax/nets.py:243)."""
+    """The parameter in the compute dtype (embodied/jax/nets.py:243: parameters
+    are cast to the compute dtype where they are used, gradients arrive in f32).
+    The low-precision values are views of ONE flat copy of `master`, refreshed
+    by a single kernel after every update; the backward of the cast adds the
+    low-precision gradient straight into the flat f32 gradient buffer."""
     if self.compute_dtype == torch.float32:
       return self.w[name]
     hit = self._cast.get(name)
     if hit is None:
-      hit = self._cast[name] = self.w[name].to(self.compute_dtype)
+      if self.master._version != self._low_seen:   # master was written through torch
+        self.refresh_low()
+      low = self._view(self.low, name)
+      if torch.is_grad_enabled():
+        low = _CastParam.apply(self.w[name], low, self._view(self.grad, name))
+      hit = self._cast[name] = low
     return hit
+
+  @torch.no_grad()
+  def refresh_low(self):
+    """master -> the flat compute-dtype copy (after the optimiser wrote master)."""
+    if self.compute_dtype == torch.float32:
+      return
+    self.low_buffer().copy_(self.master)
+    self._low_seen = self.master._version
+
+  def low_buffer(self):
+    if self.low is None:
+      self.low = torch.zeros(self.total, dtype=self.compute_dtype, device=self.device)
+    return self.low
+
+  def low_is_fresh(self):
+    """A raw-pointer writer (the fused optimiser kernel) updated master AND low."""
+    self._low_seen = self.master._version
 
   def begin_step(self):
     self._cast.clear()
@@ -182,4 +224,5 @@ class ParamStore:
       self.mu.copy_(torch.as_tensor(data['opt/mu']))
       self.step = int(data['opt/step'])
     self._cast.clear()
+    self.refresh_low()
     self.version += 1

@@ -318,6 +318,13 @@ int emb_opt_agc_rms_momentum(const float* grad, float* param, float* nu, float* 
                              const emb_opt_chunk* chunks, int32_t nchunks,
                              float* norms, int32_t ntensors, const float* hyper,
                              void* stream);
+/* Same update; additionally writes the new parameters rounded to bf16 into the flat
+ * buffer `param_bf16` (same element offsets; NULL = skip) -- the compute-dtype copy
+ * the next forward pass reads (embodied/jax/nets.py:243 casts parameters at use). */
+int emb_opt_agc_rms_momentum_cast(const float* grad, float* param, float* nu, float* mu,
+                                  void* param_bf16, const emb_opt_chunk* chunks, int32_t nchunks,
+                                  float* norms, int32_t ntensors, const float* hyper,
+                                  void* stream);
 
 /* Spatial glue of the dreamerv3 encoder / decoder on NHWC tensors, one HBM pass
  * each (dreamerv3/rssm.py:239-240 2x2 max-pool; :336,349 nearest x2 up-sampling).
