@@ -76,6 +76,15 @@ __device__ __forceinline__ float group_sum(float s, int gs) {
   for (int o = gs >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return s;
 }
+// the same sum without a data-dependent loop: five shuffles, strides >= gs masked out
+__device__ __forceinline__ float group_sum_flat(float s, int gs) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float other = __shfl_xor_sync(0xffffffffu, s, o);
+    s += o < gs ? other : 0.f;
+  }
+  return s;
+}
 // lanes per row: the smallest power of two covering cols / N vectors, at most a warp
 __device__ __forceinline__ int group_size(int cols, int n) {
   int gs = 1;
@@ -203,6 +212,7 @@ rmsnorm_act_fwd_short_kernel(const T* __restrict__ x, const float* __restrict__ 
     }
   }
   constexpr int U = NV == 1 ? 2 : 1;      // row sets in flight per warp iteration
+  const float inv_cols = 1.0f / (float)cols;
   for (int64_t r0 = warp * rpw * U; r0 < rows; r0 += nwarps * rpw * U) {
     float v[U][NV][N], rstd[U];
 #pragma unroll
@@ -226,7 +236,7 @@ rmsnorm_act_fwd_short_kernel(const T* __restrict__ x, const float* __restrict__ 
           for (int i = 0; i < N; ++i) { v[u][k][i] += bi[k][i]; ss = fmaf(v[u][k][i], v[u][k][i], ss); }
         }
       }
-      rstd[u] = rsqrtf(group_sum(ss, gs) / (float)cols + eps);
+      rstd[u] = rsqrtf(group_sum_flat(ss, gs) * inv_cols + eps);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -275,6 +285,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
   for (int i = 0; i < PL; ++i) gsc[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < (BIAS ? PL : 1); ++i) gbi[i] = 0.f;
+  const float inv_cols = 1.0f / (float)cols;
   // convolution channels: scale and bias of this lane's columns live in registers
   float scr[BIAS ? PL : 1], bir[BIAS ? PL : 1];
   if (BIAS) {
@@ -324,7 +335,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
             }
           }
         }
-        rstd[u] = rsqrtf(group_sum(ss, gs_) / (float)cols + eps);
+        rstd[u] = rsqrtf(group_sum_flat(ss, gs_) * inv_cols + eps);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -347,7 +358,7 @@ rmsnorm_act_bwd_kernel(const T* __restrict__ x, const float* __restrict__ scale,
             }
           }
         }
-        const float mean = group_sum(dot, gs_) / (float)cols;
+        const float mean = group_sum_flat(dot, gs_) * inv_cols;
         if (live_u) {
           T* out = gx + (r0 + u * rpw + grp) * cols;
 #pragma unroll
