@@ -173,14 +173,15 @@ class ParamStore:
     low-precision gradient straight into the flat f32 gradient buffer."""
     if self.compute_dtype == torch.float32:
       return self.w[name]
-    hit = self._cast.get(name)
+    tracked = torch.is_grad_enabled()    # a no-grad caller must not decide what a later one gets
+    hit = self._cast.get((name, tracked))
     if hit is None:
       if self.master._version != self._low_seen:   # master was written through torch
         self.refresh_low()
       low = self._view(self.low, name)
-      if torch.is_grad_enabled():
+      if tracked:
         low = _CastParam.apply(self.w[name], low, self._view(self.grad, name))
-      hit = self._cast[name] = low
+      hit = self._cast[(name, tracked)] = low
     return hit
 
   @torch.no_grad()

@@ -20,9 +20,10 @@ def _grads(plain):
   store = P.ParamStore(cfg, 'cpu', torch.bfloat16, 0, {k: v.numpy() for k, v in vals.items()})
   if plain:
     def get(name):
-      hit = store._cast.get(name)
+      key = (name, torch.is_grad_enabled())
+      hit = store._cast.get(key)
       if hit is None:
-        hit = store._cast[name] = store.w[name].to(torch.bfloat16)
+        hit = store._cast[key] = store.w[name].to(torch.bfloat16)
       return hit
     store.get = get
   model = M.Model(cfg, store)
@@ -58,3 +59,16 @@ def test_low_precision_copy_follows_master():
     assert torch.equal(store.get(name), store.view('master', name).to(torch.bfloat16))
   store.refresh_low()
   assert torch.equal(store.low, store.master.to(torch.bfloat16))
+
+
+def test_a_no_grad_use_does_not_hide_the_parameter_from_autograd():
+  store, _ = _grads(plain=False)
+  name = 'dyn/obslogit/kernel'
+  store.begin_step()
+  store.grad.zero_()
+  with torch.no_grad():
+    a = store.get(name)
+  b = store.get(name)
+  assert not a.requires_grad and b.requires_grad
+  b.float().sum().backward()
+  assert float(store.view('grad', name).min()) == 1.0
