@@ -581,13 +581,18 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
   pg['dyn/dynin0norm/scale'] = g_s0
   w1 = torch.zeros((SC, H), dtype=f32, device=dev)
   if T > 1:
-    idx = sv['index'][:T - 1].long()                                  # (T-1, 16, S): stoch of step t-1
-    rows = (idx + torch.arange(S, device=dev) * C)                    # row of dynin1 per latent
-    contrib = (g_y1[1:] * keep[1:, :, None])[:, :, None, :].expand(-1, -1, S, -1)
-    valid = torch.zeros(ROWS, dtype=torch.bool, device=dev)
-    valid[:B] = True
-    contrib = contrib * valid[None, :, None, None]
-    w1.index_add_(0, rows.reshape(-1), contrib.reshape(-1, H))
+    # x1_pre = sum over latents of dynin1[latent*C + class]: its weight gradient is
+    # multihot^T @ g_y1 -- one small GEMM instead of a 32x expanded scatter-add
+    # (row block t pairs stoch[t] with g_y1[t+1]; the last block is zero so that the
+    # GEMM's inner dimension stays T*16 like every other weight-gradient GEMM here)
+    idx = sv['index'][:T].long()                                      # (T, 16, S)
+    rows = (idx + torch.arange(S, device=dev) * C).reshape(-1, S)     # row of dynin1 per latent
+    hot = torch.zeros((R, SC), dtype=cd, device=dev).scatter_(1, rows, 1.0)
+    valid = torch.zeros(ROWS, dtype=f32, device=dev)
+    valid[:B] = 1.0
+    contrib = torch.zeros((T, ROWS, H), dtype=f32, device=dev)
+    contrib[:T - 1] = g_y1[1:] * (keep[1:] * valid[None, :])[:, :, None]
+    w1 = mm(hot, contrib.reshape(R, H))
   pg['dyn/dynin1/kernel'] = w1
   pg['dyn/dynin1/bias'] = g_y1[1:].reshape(-1, H).sum(0)
   pg['dyn/dynin1norm/scale'] = g_s1

@@ -180,3 +180,37 @@ def test_captured_train_step_matches_eager(dtype):
   # no-noise path: the captured step draws its own noise into the static buffers
   carries[0], outs, mets = agents[0].train(carries[0], data)
   assert np.isfinite(float(mets['loss']))
+
+
+def test_bf16_update_reaches_every_tensor_the_fp32_update_reaches():
+  """Parameters are cast to bf16 where they are used; a tensor whose first use in a step
+  is under no_grad (the policy head inside the imagination roll-out) must still receive
+  its gradient.  Every tensor with an fp32 gradient needs a bf16 gradient of the same
+  direction."""
+  ocfg = do.tiny_config()
+  vals = do.init_params(ocfg, 6, outscale_override=1.0)
+  obs, act = spaces(ocfg)
+  agents = []
+  for dtype in ('float32', 'bfloat16'):
+    cfg = cases.product_config(ocfg, dtype)
+    cfg['graph'] = 'off'
+    agents.append(dreamerv3.Agent(obs, act, cfg, values={k: v.numpy() for k, v in vals.items()}))
+  B, T = 4, 6
+  data = cases.to_device(cases.batch(ocfg, B, T, seed=50))
+  noise = cases.to_device(do.make_noise(ocfg, B, T, seed=51))
+  for a in agents:
+    a.train(a.init_train(B), data, noise)
+  f, h = agents[0].store, agents[1].store
+  missing, off = [], []
+  for k in f.specs:
+    gf, gh = f.view('grad', k).double(), h.view('grad', k).double()
+    if float(gf.norm()) == 0:
+      continue
+    if float(gh.norm()) == 0:
+      missing.append(k)
+      continue
+    cos = float((gf * gh).sum() / (gf.norm() * gh.norm()))
+    if cos < 0.9:
+      off.append((k, cos))
+  assert not missing, missing
+  assert len(off) <= len(f.specs) // 10, off     # bf16 noise may turn a few tiny tensors
