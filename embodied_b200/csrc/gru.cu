@@ -155,7 +155,8 @@ void launch_grouped(int nv, const void* x, const float* scale, const float* bias
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 gru_gates_kernel(const T* __restrict__ pre, const float* __restrict__ bias, const T* __restrict__ deter,
-                 T* __restrict__ out, int64_t nvec, int M, int G, int Dg) {
+                 T* __restrict__ out, int64_t nvec, int M, int G, int Dg, int64_t dstride,
+                 int64_t ostride) {
   constexpr int N = Vec<T>::N;
   const int vpr = G * Dg / N;
   for (int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x; o < nvec;
@@ -168,7 +169,7 @@ gru_gates_kernel(const T* __restrict__ pre, const float* __restrict__ bias, cons
     Vec<T>::load(p, r);
     Vec<T>::load(p + Dg, cd);
     Vec<T>::load(p + 2 * Dg, u);
-    Vec<T>::load(deter + (size_t)m * G * Dg + c, d);
+    Vec<T>::load(deter + (size_t)m * dstride + c, d);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       const float rs = sigmoid_t<T>(Vec<T>::round(r[i] + b[i]));
@@ -176,7 +177,7 @@ gru_gates_kernel(const T* __restrict__ pre, const float* __restrict__ bias, cons
       const float up = sigmoid_t<T>(Vec<T>::round(u[i] + b[2 * Dg + i]) - 1.0f);
       res[i] = up * cand + (1.0f - up) * d[i];
     }
-    Vec<T>::store(out + (size_t)m * G * Dg + c, res);
+    Vec<T>::store(out + (size_t)m * ostride + c, res);
   }
 }
 
@@ -216,20 +217,31 @@ extern "C" int emb_rmsnorm_grouped_fwd(const void* x, const float* scale, const 
 }
 
 extern "C" int emb_gru_gates_fwd(const void* pre, const float* bias, const void* deter, void* out,
-                                 int64_t m, int32_t g, int32_t dg, int32_t dtype, void* stream) {
+                                 int64_t m, int32_t g, int32_t dg, int32_t dtype,
+                                 int64_t deter_stride, int64_t out_stride, void* stream) {
   const char* who = "emb_gru_gates_fwd";
   if (int e = common(who, m, g, dg, dtype)) return e;
   if (m == 0) return 0;
+  const int64_t width = (int64_t)g * dg, per = dtype ? 8 : 4;
+  if (deter_stride == 0) deter_stride = width;
+  if (out_stride == 0) out_stride = width;
+  if (deter_stride < width || out_stride < width || deter_stride % per || out_stride % per)
+    return emb::fail(-1, "%s: row strides %lld / %lld (>= %lld, multiples of %lld)", who,
+                     (long long)deter_stride, (long long)out_stride, (long long)width, (long long)per);
+  if (((uintptr_t)deter | (uintptr_t)out | (uintptr_t)pre) & 15)
+    return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
   const int64_t nvec = m * g * dg / (dtype ? 8 : 4);
   const int64_t want = (nvec + kThreads - 1) / kThreads, cap = (int64_t)g_sms * 16;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype)
     gru_gates_kernel<__nv_bfloat16><<<grid, kThreads, 0, s>>>(
-        (const __nv_bfloat16*)pre, bias, (const __nv_bfloat16*)deter, (__nv_bfloat16*)out, nvec, (int)m, g, dg);
+        (const __nv_bfloat16*)pre, bias, (const __nv_bfloat16*)deter, (__nv_bfloat16*)out, nvec, (int)m, g, dg,
+        deter_stride, out_stride);
   else
     gru_gates_kernel<float><<<grid, kThreads, 0, s>>>(
-        (const float*)pre, bias, (const float*)deter, (float*)out, nvec, (int)m, g, dg);
+        (const float*)pre, bias, (const float*)deter, (float*)out, nvec, (int)m, g, dg, deter_stride,
+        out_stride);
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;

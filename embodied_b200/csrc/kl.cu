@@ -271,14 +271,15 @@ extern "C" int emb_lambda_return(const float* last, const float* term, const flo
 namespace {
 __global__ void __launch_bounds__(1024)
 onehot_sample_kernel(const void* __restrict__ logit, int dtype, int64_t logit_stride,
-                     const float* __restrict__ gumbel, int S, int C, float unimix,
+                     const float* __restrict__ gumbel, int64_t gumbel_stride, int S, int C,
+                     float unimix,
                      void* __restrict__ out, int out_dtype, int64_t out_stride,
                      int32_t* __restrict__ index) {
   const int row = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int s = warp; s < S; s += nwarps) {
     const int64_t off = (int64_t)row * logit_stride + (int64_t)s * C;
-    const float* gn = gumbel + ((int64_t)row * S + s) * C;
+    const float* gn = gumbel + (int64_t)row * gumbel_stride + (int64_t)s * C;
     float x[kMaxPerLane];
     float m = -INFINITY;
 #pragma unroll
@@ -324,7 +325,8 @@ onehot_sample_kernel(const void* __restrict__ logit, int dtype, int64_t logit_st
 }  // namespace
 
 extern "C" int emb_onehot_sample(const void* logit, int32_t dtype, int64_t logit_stride,
-                                 const float* gumbel, int64_t rows, int32_t S, int32_t C,
+                                 const float* gumbel, int64_t gumbel_stride, int64_t rows,
+                                 int32_t S, int32_t C,
                                  float unimix, void* out, int32_t out_dtype, int64_t out_stride,
                                  int32_t* index, void* stream) {
   const char* who = "emb_onehot_sample";
@@ -332,8 +334,9 @@ extern "C" int emb_onehot_sample(const void* logit, int32_t dtype, int64_t logit
     return emb::fail(-1, "%s: rows=%lld S=%d C=%d", who, (long long)rows, S, C);
   if ((dtype | out_dtype) & ~1) return emb::fail(-1, "%s: dtype must be 0 (f32) or 1 (bf16)", who);
   if (rows == 0) return 0;
+  if (gumbel_stride == 0) gumbel_stride = (int64_t)S * C;
   onehot_sample_kernel<<<(unsigned)rows, threads_for(S), 0, (cudaStream_t)stream>>>(
-      logit, dtype, logit_stride, gumbel, S, C, unimix, out, out_dtype, out_stride, index);
+      logit, dtype, logit_stride, gumbel, gumbel_stride, S, C, unimix, out, out_dtype, out_stride, index);
   emb::count_launch();
   if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
   return 0;

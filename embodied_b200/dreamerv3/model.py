@@ -174,11 +174,12 @@ class Model:
     a = F.one_hot(action.long(), self.cfg.actions).to(self.cd)
     return a * (~reset)[..., None].to(self.cd)
 
-  def core(self, deter, stoch_flat, x2):                     # rssm.py:135-159
+  def core(self, deter, stoch_flat, x2, out=None):           # rssm.py:135-159
     """x2 = silu(rms(dynin2(action))) is precomputed by the caller.  dynhid0's
     input is [deter_g, x0, x1, x2] per group (rssm.py:147-148); instead of
     materialising the g-fold repeat, its kernel is applied in two batched
-    GEMMs: deter_g @ W[g, :Dg] + x012 @ W[g, Dg:] (x012 broadcast over g)."""
+    GEMMs: deter_g @ W[g, :Dg] + x012 @ W[g, Dg:] (x012 broadcast over g).
+    `out` (no-gradient callers): a row-strided (M, D) view that receives the result."""
     g = self.cfg.blocks
     M = len(deter)
     x0 = self.norm(self.dense(deter, 'dyn/dynin0'), 'dyn/dynin0norm')
@@ -194,7 +195,7 @@ class Model:
       sw = self.store.w
       x = ops.rmsnorm_grouped(y, sw['dyn/dynhid0norm/scale'], sw['dyn/dynhid0/bias'])
       pre = torch.bmm(x, self.W('dyn/dyngru/kernel'))
-      return ops.gru_gates(pre, sw['dyn/dyngru/bias'], deter)
+      return ops.gru_gates(pre, sw['dyn/dyngru/bias'], deter, out=out)
     x = y.transpose(0, 1).reshape(M, -1) + b
     x = self.norm(x, 'dyn/dynhid0norm')
     x = self.block(x, 'dyn/dyngru')
@@ -203,20 +204,29 @@ class Model:
     reset = torch.sigmoid(reset)
     cand = torch.tanh(reset * cand)
     update = torch.sigmoid(update - 1)
-    return update * cand + (1 - update) * deter
+    new = update * cand + (1 - update) * deter
+    if out is not None:
+      out.copy_(new)
+      return out
+    return new
 
   def unimix(self, logit):                                   # outs.py:210-216
     probs = torch.softmax(logit.to(f32), -1)
     return (1 - self.cfg.unimix) * probs + self.cfg.unimix / probs.shape[-1]
 
-  def sample_stoch(self, logit, gumbel):                     # outs.py:252-270
+  def sample_stoch(self, logit, gumbel, out=None):           # outs.py:252-270
+    """`out` (no-gradient callers): a row-strided (n, S*C) view that receives the sample."""
     if (self.fused_norm and not torch.is_grad_enabled() and logit.is_cuda and logit.dim() == 3
         and logit.shape[-1] <= 128 and logit.dtype in (f32, torch.bfloat16)):
-      return ops.onehot_sample(logit, gumbel, self.cfg.unimix, self.cd)   # one launch
+      return ops.onehot_sample(logit, gumbel, self.cfg.unimix, self.cd, out=out)   # one launch
     probs = self.unimix(logit)
     index = torch.argmax(torch.log(probs) + gumbel, -1)
     value = F.one_hot(index, probs.shape[-1]).to(f32)
-    return (value + (probs - probs.detach())).to(self.cd)
+    value = (value + (probs - probs.detach())).to(self.cd)
+    if out is not None:
+      out.copy_(value.reshape(out.shape))
+      return out
+    return value
 
   def act_branch(self, action, reset):
     if not torch.is_grad_enabled() and action.dim() == 1:
@@ -432,18 +442,20 @@ class Model:
     n = len(deter)
     never = torch.zeros(n, dtype=torch.bool, device=deter.device)
     feat = torch.empty((n, H + 1, D + cfg.stoch * cfg.classes), dtype=self.cd, device=deter.device)
+    feat[:, 0, :D] = deter
+    feat[:, 0, D:] = stoch.reshape(n, -1)
     acts = []
     for h in range(H + 1):
-      feat[:, h, :D] = deter
-      feat[:, h, D:] = stoch.reshape(n, -1)
-      logits = self.head(feat[:, h], 'pol', cfg.pol_layers, 'action/logits')
+      cur = feat[:, h]                  # (n, D + S*C) rows of the buffer: no per-step copies,
+      logits = self.head(cur, 'pol', cfg.pol_layers, 'action/logits')
       a = torch.argmax(logits + noise_act[:, h], -1)
       acts.append(a)
       if h == H:
         break
       x2 = self.act_branch(a, never)
-      deter = self.core(deter, stoch.reshape(n, -1), x2)
-      stoch = self.sample_stoch(self.prior(deter), noise_stoch[:, h])
+      nxt = feat[:, h + 1]              # the next state is written where it is kept
+      self.core(cur[:, :D], cur[:, D:], x2, out=nxt[:, :D])
+      self.sample_stoch(self.prior(nxt[:, :D]), noise_stoch[:, h], out=nxt[:, D:])
     return feat, torch.stack(acts, 1)
 
   # ------------------------------------------------------------------------ loss

@@ -37,9 +37,9 @@ def _lib_bound():
     lib.emb_conv_tapsum_nhwc.restype = ctypes.c_int
     lib.emb_rmsnorm_grouped_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _fl, _vp]
     lib.emb_rmsnorm_grouped_fwd.restype = ctypes.c_int
-    lib.emb_gru_gates_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]
+    lib.emb_gru_gates_fwd.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i64, _i64, _vp]
     lib.emb_gru_gates_fwd.restype = ctypes.c_int
-    lib.emb_onehot_sample.argtypes = [_vp, _i32, _i64, _vp, _i64, _i32, _i32, _fl, _vp, _i32, _i64, _vp, _vp]
+    lib.emb_onehot_sample.argtypes = [_vp, _i32, _i64, _vp, _i64, _i64, _i32, _i32, _fl, _vp, _i32, _i64, _vp, _vp]
     lib.emb_onehot_sample.restype = ctypes.c_int
     lib.emb_lambda_return.argtypes = [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _fl, _fl, _vp]
     lib.emb_lambda_return.restype = ctypes.c_int
@@ -329,17 +329,30 @@ def rmsnorm_grouped(x, scale, bias, act=True, eps=1e-4):
 
 
 @torch.no_grad()
-def gru_gates(pre, bias, deter):
-  """pre (g, M, 3*Dg) contiguous, bias fp32 (3*D,), deter (M, D) -> new deter (M, D)."""
+def _rows_ok(x):
+  """2-D view whose rows are contiguous and 16-byte aligned (any row stride)."""
+  return (x.dim() == 2 and x.stride(1) == 1 and x.data_ptr() % 16 == 0 and
+          (x.stride(0) * x.element_size()) % 16 == 0)
+
+
+def gru_gates(pre, bias, deter, out=None):
+  """pre (g, M, 3*Dg) contiguous, bias fp32 (3*D,), deter (M, D) -> new deter (M, D).
+  deter and `out` may be row-strided views (columns of a wider buffer)."""
   lib = _lib_bound()
   g, M, Dg3 = pre.shape
-  deter = deter.contiguous()
-  out = torch.empty_like(deter)
+  if not _rows_ok(deter):
+    deter = deter.contiguous()
+  dst = out if out is not None and _rows_ok(out) else torch.empty(
+      (M, g * Dg3 // 3), dtype=deter.dtype, device=deter.device)
+  assert dst.shape == deter.shape and dst.dtype == deter.dtype == pre.dtype
   stream = torch.cuda.current_stream(pre.device).cuda_stream
   _lib.check(lib.emb_gru_gates_fwd(
-      pre.data_ptr(), bias.data_ptr(), deter.data_ptr(), out.data_ptr(), M, g, Dg3 // 3,
-      _dtype_code(pre), stream))
-  return out
+      pre.data_ptr(), bias.data_ptr(), deter.data_ptr(), dst.data_ptr(), M, g, Dg3 // 3,
+      _dtype_code(pre), deter.stride(0), dst.stride(0), stream))
+  if out is not None and dst is not out:
+    out.copy_(dst)
+    return out
+  return dst
 
 
 @torch.no_grad()
@@ -359,16 +372,25 @@ def lambda_return(last, term, rew, boot, disc, lam):
 
 
 @torch.no_grad()
-def onehot_sample(logit, gumbel, unimix, out_dtype):
+def onehot_sample(logit, gumbel, unimix, out_dtype, out=None):
   """logit (n, S, C) fp32 / bf16, gumbel (n, S, C) fp32 -> one-hot (n, S, C) in
-  `out_dtype`: the sampled value of outs.OneHot (no straight-through term)."""
+  `out_dtype`: the sampled value of outs.OneHot (no straight-through term).
+  gumbel may be a row-strided view (one step of a (n, H, S, C) buffer); `out`, if
+  given, is a (n, S*C) row-strided view that receives the sample."""
   lib = _lib_bound()
   n, S, C = logit.shape
   logit = logit.contiguous()
-  gumbel = gumbel.to(f32).contiguous()
-  out = torch.empty((n, S, C), dtype=out_dtype, device=logit.device)
+  gumbel = gumbel.to(f32)
+  if not (gumbel.stride(2) == 1 and gumbel.stride(1) == C):
+    gumbel = gumbel.contiguous()
+  if out is None:
+    res = torch.empty((n, S, C), dtype=out_dtype, device=logit.device)
+    flat = res.view(n, S * C)
+  else:
+    assert out.shape == (n, S * C) and out.stride(1) == 1 and out.dtype == out_dtype
+    res = flat = out
   stream = torch.cuda.current_stream(logit.device).cuda_stream
   _lib.check(lib.emb_onehot_sample(
-      logit.data_ptr(), _dtype_code(logit), S * C, gumbel.data_ptr(), n, S, C, float(unimix),
-      out.data_ptr(), _dtype_code(out), S * C, None, stream))
-  return out
+      logit.data_ptr(), _dtype_code(logit), S * C, gumbel.data_ptr(), gumbel.stride(0), n, S, C,
+      float(unimix), flat.data_ptr(), _dtype_code(flat), flat.stride(0), None, stream))
+  return res

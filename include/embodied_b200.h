@@ -275,11 +275,13 @@ int emb_rssm_kl_bwd(const emb_rssm_kl_args* args, const float* kl_raw, const flo
 /* Forward value of the straight-through one-hot sample (embodied/jax/outs.py:210-216,
  * 252-270) for the no-gradient paths: out[row][s*C + c] = (c == argmax_c(log(unimix(
  * softmax(logit[row][s]))) + gumbel[row][s][c])).  logit fp32 / bf16 with `logit_stride`
- * elements between rows, gumbel dense fp32, out fp32 / bf16 with `out_stride`; index
- * (optional) int32 [rows][S]. */
+ * elements between rows, gumbel fp32 with `gumbel_stride` (0 = dense S*C), out fp32 / bf16
+ * with `out_stride` (the imagination roll-out samples straight into its feature buffer);
+ * index (optional) int32 [rows][S]. */
 int emb_onehot_sample(const void* logit, int32_t dtype, int64_t logit_stride, const float* gumbel,
-                      int64_t rows, int32_t S, int32_t C, float unimix, void* out,
-                      int32_t out_dtype, int64_t out_stride, int32_t* index, void* stream);
+                      int64_t gumbel_stride, int64_t rows, int32_t S, int32_t C, float unimix,
+                      void* out, int32_t out_dtype, int64_t out_stride, int32_t* index,
+                      void* stream);
 
 /* The lambda-return recurrence (dreamerv3/agent.py:482-490) as one launch, one thread
  * per row.  last / term / rew / boot: fp32 [rows][length]; ret: fp32 [rows][length-1]. */
@@ -348,12 +350,15 @@ int emb_upsample2_nhwc_bwd(const void* gy, void* gx, int64_t n, int32_t h, int32
  *   rmsnorm_grouped: y[g][m][:] = act(rms_norm over the full row m of (x + bias) * scale)
  *   gru_gates: out[m][g*dg + j] = u * tanh(r * c) + (1 - u) * deter[m][g*dg + j] with
  *       (r, c, u) = pre[g][m][{0,1,2}*dg + j] + bias[g*3*dg + {0,1,2}*dg + j],
- *       r = sigmoid(r), u = sigmoid(u - 1). */
+ *       r = sigmoid(r), u = sigmoid(u - 1).  deter / out rows are `deter_stride` /
+ *       `out_stride` elements apart (0 = dense g*dg): the roll-out reads and writes the
+ *       deter columns of its (rows, steps, deter | stoch) feature buffer in place. */
 int emb_rmsnorm_grouped_fwd(const void* x, const float* scale, const float* bias, void* y,
                             int64_t m, int32_t g, int32_t dg, int32_t dtype, int32_t act, float eps,
                             void* stream);
 int emb_gru_gates_fwd(const void* pre, const float* bias, const void* deter, void* out, int64_t m,
-                      int32_t g, int32_t dg, int32_t dtype, void* stream);
+                      int32_t g, int32_t dg, int32_t dtype, int64_t deter_stride, int64_t out_stride,
+                      void* stream);
 
 /* The two thin 5x5 convolutions of dreamerv3 (3 image channels in: encoder layer 0,
  * dreamerv3/rssm.py:233-238; 3 channels out: decoder image head, rssm.py:349-352;

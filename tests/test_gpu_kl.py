@@ -104,3 +104,11 @@ def test_onehot_sample_kernel_matches_formula(n, S, C, dtype):
   got = ops.onehot_sample(logit.cuda(), gumbel.cuda(), 0.01, dtype)
   assert got.dtype == dtype and got.shape == (n, S, C)
   assert torch.equal(got.float().cpu(), want)
+  # row-strided noise (one step of a (n, H, S, C) buffer) and output (columns of a wider row)
+  noise = torch.zeros(n, 3, S, C, device='cuda')
+  noise[:, 1] = gumbel.cuda()
+  wide = torch.full((n, 5 + S * C), 7.0, device='cuda').to(dtype)
+  res = ops.onehot_sample(logit.cuda(), noise[:, 1], 0.01, dtype, out=wide[:, 5:])
+  assert res.data_ptr() == wide[:, 5:].data_ptr()
+  assert torch.equal(wide[:, 5:].float().cpu().reshape(n, S, C), want)
+  assert float((wide[:, :5] - 7).abs().max()) == 0

@@ -112,4 +112,12 @@ def test_grouped_norm_and_gru_gates_forward(g, M, Dg, dtype):
     u = torch.sigmoid(u - 1)
     ref = u * c + (1 - u) * deter
     assert rel(out, ref) < (1e-5 if dtype == torch.float32 else 3e-2)
+    # row-strided operands: deter read from, and the result written into, the deter
+    # columns of a wider (rows, steps, deter | stoch) buffer, as the roll-out does
+    buf = torch.full((M, 3, D + 24), 7.0, device='cuda').to(dtype)
+    buf[:, 0, :D] = deter
+    res = ops.gru_gates(pre, b3, buf[:, 0, :D], out=buf[:, 1, :D])
+    assert res.data_ptr() == buf[:, 1, :D].data_ptr()
+    assert torch.equal(buf[:, 1, :D], out)
+    assert float((buf[:, 1, D:] - 7).abs().max()) == 0 and float((buf[:, 2] - 7).abs().max()) == 0
   assert not ops.core_fused_supported(deter, g)      # grad mode: the differentiable path runs
