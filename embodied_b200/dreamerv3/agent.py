@@ -66,6 +66,10 @@ class Agent(base.Agent):
       # parity mode: strict IEEE fp32 GEMMs and convolutions
       torch.backends.cuda.matmul.allow_tf32 = False
       torch.backends.cudnn.allow_tf32 = False
+    elif cfg.get('cudnn_benchmark', True):
+      # the mid convolutions run on the library: let it time its algorithms for the
+      # (few, fixed) shapes during the eager warm-up steps that precede graph capture
+      torch.backends.cudnn.benchmark = True
     self.store = paramlib.ParamStore(cfg, self.device, self.cd, cfg.seed, values)
     self.model = modellib.Model(cfg, self.store)
     self.opt = optim.Optimizer(cfg, self.store)
