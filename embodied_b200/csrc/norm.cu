@@ -23,7 +23,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxCols = 2048;          // bwd keeps cols/32 scale-gradient partials per lane
-constexpr int kMaxPerLane = kMaxCols / 32;
 
 template <typename T> struct Vec;
 template <> struct Vec<float> {
