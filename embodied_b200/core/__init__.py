@@ -1,12 +1,15 @@
-from .base import Agent, Env, Stream
-from .clock import LocalClock
-from .driver import Driver
-from .random import RandomAgent
-from .replay import Replay
-from .wrappers import Wrapper
+"""embodied_b200.core: the names ``embodied.core`` exports (embodied/core/__init__.py:1-14)
+-- the three protocols, Driver, Replay, RandomAgent, Wrapper, LocalClock -- and the
+submodules the run loop and the factories reach into."""
+from . import base, clock, driver, limiters, random, replay, selectors, streams, wrappers
 
-from . import clock
-from . import limiters
-from . import selectors
-from . import streams
-from . import wrappers
+Agent, Env, Stream = base.Agent, base.Env, base.Stream
+Driver = driver.Driver
+Replay = replay.Replay
+RandomAgent = random.RandomAgent
+Wrapper = wrappers.Wrapper
+LocalClock = clock.LocalClock
+
+__all__ = [
+    'Agent', 'Env', 'Stream', 'Driver', 'Replay', 'RandomAgent', 'Wrapper', 'LocalClock',
+    'base', 'clock', 'driver', 'limiters', 'random', 'replay', 'selectors', 'streams', 'wrappers']

@@ -22,12 +22,18 @@ import time
 import numpy as np
 
 from .. import elements
+from . import base
 
 
 class _SerialEnvs:
 
   def __init__(self, fns):
     self.envs = [fn() for fn in fns]
+    for env in self.envs:           # not a drop-in Env: say so before any device work
+      lacking = base.implements_env(env)
+      if lacking:
+        raise TypeError(f'{type(env).__name__} does not implement the Env protocol '
+                        f'(embodied/core/base.py:34-58): missing {lacking}')
     self.act_space = self.envs[0].act_space
     self.obs_space = self.envs[0].obs_space
 

@@ -1,18 +1,35 @@
-"""Env wrappers applied by ``wrap_env`` (dreamerv3/main.py:249-258):
-NormalizeAction, UnifyDtypes, CheckSpaces, ClipAction, plus TimeLimit.
-Semantics follow embodied/core/wrappers.py:8-118,204-270.  These run inside the
-environment (host Python by definition)."""
-import functools
-
+"""Environment wrappers that sit between a simulator and the Driver -- the ones the
+shipped configs stack in ``wrap_env`` (dreamerv3/main.py:249-258: NormalizeAction,
+UnifyDtypes, CheckSpaces, ClipAction) plus TimeLimit.  Behaviour is pinned against
+the reference's own classes (embodied/core/wrappers.py:8-55, 76-110, 204-270) by
+``tests/test_wrappers_host.py``; the implementation is this project's: every
+wrapper is a ``Wrapper`` with two optional hooks, ``map_action`` (outer -> inner
+action dict) and ``map_obs`` (inner -> outer observation dict), and ``step`` is
+written once.  These run inside the environment process, host Python by
+definition; nothing here touches the device.
+"""
 import numpy as np
 
 from .. import elements
 
+_PLAIN_VALUES = (np.ndarray, np.generic, list, tuple, int, float, bool)
+
 
 class Wrapper:
+  """Transparent proxy around an env.  Attribute lookups fall through to the
+  wrapped env; a name the whole stack lacks raises ValueError (as the reference
+  does, so that ``hasattr`` on a wrapped env keeps meaning "implemented")."""
 
   def __init__(self, env):
     self.env = env
+
+  def __getattr__(self, name):
+    if name.startswith('__') or 'env' not in self.__dict__:
+      raise AttributeError(name)
+    try:
+      return getattr(self.env, name)
+    except AttributeError:
+      raise ValueError(name) from None
 
   def __len__(self):
     return len(self.env)
@@ -20,137 +37,156 @@ class Wrapper:
   def __bool__(self):
     return bool(self.env)
 
-  def __getattr__(self, name):
-    if name.startswith('__'):
-      raise AttributeError(name)
-    try:
-      return getattr(self.env, name)
-    except AttributeError:
-      raise ValueError(name)
+  # hooks -----------------------------------------------------------------
+  def map_action(self, action):
+    return action
+
+  def map_obs(self, obs):
+    return obs
+
+  def step(self, action):
+    return self.map_obs(self.env.step(self.map_action(action)))
 
 
 class TimeLimit(Wrapper):
+  """Ends an episode after `duration` steps (0 = never).  When the episode is over --
+  by the limit, by the env, or because the caller asks for a reset -- the next step
+  starts a new one: with ``reset=True`` the env is really reset, otherwise it keeps
+  running and the step is merely labelled ``is_first``.  The caller's action dict
+  is updated in place, as in the reference (the Driver reuses it)."""
 
   def __init__(self, env, duration, reset=True):
     super().__init__(env)
-    self._duration, self._reset = duration, reset
-    self._step, self._done = 0, False
+    self._limit = duration
+    self._hard = reset
+    self._elapsed = 0
+    self._over = False
 
   def step(self, action):
-    if action['reset'] or self._done:
-      self._step, self._done = 0, False
-      if self._reset:
-        action.update(reset=True)
-        return self.env.step(action)
-      action.update(reset=False)
+    if action['reset'] or self._over:
+      self._elapsed, self._over = 0, False
+      action['reset'] = bool(self._hard)
       obs = self.env.step(action)
-      obs['is_first'] = True
+      if not self._hard:
+        obs['is_first'] = True
       return obs
-    self._step += 1
+    self._elapsed += 1
     obs = self.env.step(action)
-    if self._duration and self._step >= self._duration:
+    if self._limit and self._elapsed >= self._limit:
       obs['is_last'] = True
-    self._done = obs['is_last']
+    self._over = obs['is_last']
     return obs
 
 
 class ClipAction(Wrapper):
+  """Clips one action key into [low, high] before the env sees it."""
 
   def __init__(self, env, key='action', low=-1, high=1):
     super().__init__(env)
-    self._key, self._low, self._high = key, low, high
+    self._key, self._bounds = key, (low, high)
 
-  def step(self, action):
-    clipped = np.clip(action[self._key], self._low, self._high)
-    return self.env.step({**action, self._key: clipped})
+  def map_action(self, action):
+    return {**action, self._key: np.clip(action[self._key], *self._bounds)}
 
 
 class NormalizeAction(Wrapper):
-  """Rescales bounded continuous actions to [-1, 1]."""
+  """Presents the bounded dimensions of a continuous action as [-1, 1] and maps
+  them back affinely; unbounded dimensions pass through unchanged."""
 
   def __init__(self, env, key='action'):
     super().__init__(env)
-    self._key = key
-    self._space = env.act_space[key]
-    self._mask = np.isfinite(self._space.low) & np.isfinite(self._space.high)
-    self._low = np.where(self._mask, self._space.low, -1)
-    self._high = np.where(self._mask, self._space.high, 1)
+    inner = env.act_space[key]
+    bounded = np.isfinite(inner.low) & np.isfinite(inner.high)
+    self._key, self._bounded = key, bounded
+    self._lo = np.where(bounded, inner.low, -1)
+    self._hi = np.where(bounded, inner.high, 1)
+    unit = np.ones_like(self._lo)
+    self._outer = elements.Space(
+        np.float32, inner.shape,
+        np.where(bounded, -unit, self._lo), np.where(bounded, unit, self._hi))
 
-  @functools.cached_property
+  @property
   def act_space(self):
-    low = np.where(self._mask, -np.ones_like(self._low), self._low)
-    high = np.where(self._mask, np.ones_like(self._low), self._high)
-    space = elements.Space(np.float32, self._space.shape, low, high)
-    return {**self.env.act_space, self._key: space}
+    return {**self.env.act_space, self._key: self._outer}
 
-  def step(self, action):
-    orig = (action[self._key] + 1) / 2 * (self._high - self._low) + self._low
-    orig = np.where(self._mask, orig, action[self._key])
-    return self.env.step({**action, self._key: orig})
+  def map_action(self, action):
+    value = action[self._key]
+    # same operation order as the reference: the result is bit-identical
+    restored = (value + 1) / 2 * (self._hi - self._lo) + self._lo
+    return {**action, self._key: np.where(self._bounded, restored, value)}
+
+
+def _unified(dtype):
+  """float* -> float32, uint8 stays, other integers -> int32, anything else stays."""
+  if np.issubdtype(dtype, np.floating):
+    return np.float32
+  if np.issubdtype(dtype, np.uint8):
+    return np.uint8
+  if np.issubdtype(dtype, np.integer):
+    return np.int32
+  return dtype
 
 
 class UnifyDtypes(Wrapper):
-  """floats -> float32, uint8 stays, other ints -> int32."""
+  """One dtype per kind on the outside (see `_unified`); actions are cast back to
+  what the env declared before it sees them."""
 
   def __init__(self, env):
     super().__init__(env)
-    self._obs_space, _, self._obs_outer = self._convert(env.obs_space)
-    self._act_space, self._act_inner, _ = self._convert(env.act_space)
+    self._inner_act = {k: s.dtype for k, s in env.act_space.items()}
+    self._outer_obs = {k: _unified(s.dtype) for k, s in env.obs_space.items()}
+    recast = lambda spaces: {
+        k: elements.Space(_unified(s.dtype), s.shape, s.low, s.high) for k, s in spaces.items()}
+    self._spaces = recast(env.obs_space), recast(env.act_space)
 
   @property
   def obs_space(self):
-    return self._obs_space
+    return self._spaces[0]
 
   @property
   def act_space(self):
-    return self._act_space
+    return self._spaces[1]
 
-  def step(self, action):
-    action = action.copy()
-    for key, dtype in self._act_inner.items():
+  def map_action(self, action):
+    action = dict(action)
+    for key, dtype in self._inner_act.items():
       action[key] = np.asarray(action[key], dtype)
-    obs = self.env.step(action)
-    for key, dtype in self._obs_outer.items():
+    return action
+
+  def map_obs(self, obs):
+    for key, dtype in self._outer_obs.items():
       obs[key] = np.asarray(obs[key], dtype)
     return obs
 
-  def _convert(self, spaces):
-    results, befores, afters = {}, {}, {}
-    for key, space in spaces.items():
-      before = after = space.dtype
-      if np.issubdtype(before, np.floating):
-        after = np.float32
-      elif np.issubdtype(before, np.uint8):
-        after = np.uint8
-      elif np.issubdtype(before, np.integer):
-        after = np.int32
-      befores[key], afters[key] = before, after
-      results[key] = elements.Space(after, space.shape, space.low, space.high)
-    return results, befores, afters
-
 
 class CheckSpaces(Wrapper):
+  """Every value that crosses the env boundary must lie in its declared space;
+  observation and action keys must not collide (they share one transition dict)."""
 
   def __init__(self, env):
-    overlap = env.obs_space.keys() & env.act_space.keys()
-    assert not overlap, overlap
+    shared = set(env.obs_space) & set(env.act_space)
+    assert not shared, f'keys used as both observation and action: {sorted(shared)}'
     super().__init__(env)
 
-  def step(self, action):
+  def map_action(self, action):
+    spaces = self.env.act_space
     for key, value in action.items():
-      self._check(value, self.env.act_space[key], key)
-    obs = self.env.step(action)
+      self._require(key, value, spaces[key])
+    return action
+
+  def map_obs(self, obs):
+    spaces = self.env.obs_space
     for key, value in obs.items():
-      self._check(value, self.env.obs_space[key], key)
+      self._require(key, value, spaces[key])
     return obs
 
-  def _check(self, value, space, key):
-    if not isinstance(value, (
-        np.ndarray, np.generic, list, tuple, int, float, bool)):
+  @staticmethod
+  def _require(key, value, space):
+    if not isinstance(value, _PLAIN_VALUES):
       raise TypeError(f'Invalid type {type(value)} for key {key}.')
     if value in space:
       return
-    arr = np.array(value)
+    arr = np.asarray(value)
     raise ValueError(
         f"Value for '{key}' with dtype {arr.dtype}, shape {arr.shape}, "
-        f"lowest {arr.min()}, highest {arr.max()} is not in {space}.")
+        f'lowest {arr.min()}, highest {arr.max()} is not in {space}.')

@@ -51,45 +51,6 @@ class SyntheticImage(base.Env):
 
 
 class SyntheticProprio(base.Env):
-  """DMC-walker-shaped proprioceptive obs (config 4)."""
-
-  def __init__(self, index=0, length=500):
-    self.length = length
-    self.rng = np.random.default_rng(1000 + index)
-    self.t = 0
-    self.done = False
-
-  @property
-  def obs_space(self):
-    S = elements.Space
-    return {
-        'orientations': S(np.float32, (14,)), 'height': S(np.float32),
-        'velocity': S(np.float32, (9,)), 'reward': S(np.float32),
-        'is_first': S(bool), 'is_last': S(bool), 'is_terminal': S(bool),
-    }
-
-  @property
-  def act_space(self):
-    S = elements.Space
-    return {'reset': S(bool), 'action': S(np.float32, (6,), -1, 1)}
-
-  def step(self, action):
-    if action['reset'] or self.done:
-      self.t, self.done, first = 0, False, True
-    else:
-      self.t += 1
-      first = False
-    self.done = self.t >= self.length
-    r = self.rng
-    return dict(
-        orientations=r.standard_normal(14).astype(np.float32),
-        height=np.float32(r.standard_normal()),
-        velocity=r.standard_normal(9).astype(np.float32),
-        reward=np.float32(r.standard_normal()),
-        is_first=first, is_last=self.done, is_terminal=self.done)
-
-
-class SyntheticProprio(base.Env):
   """DMC-proprio-shaped synthetic env (BASELINE config 4; dm_control walker
   layout): orientations f32[14], height f32[], velocity f32[9],
   one continuous action f32[6] in [-1, 1].  The next observation depends on the

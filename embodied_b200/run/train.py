@@ -24,6 +24,7 @@ import pickle
 import numpy as np
 
 from .. import elements
+from ..core import base as baselib
 from ..core import clock
 from ..core import driver as driverlib
 
@@ -69,6 +70,10 @@ class _EpisodeStats:
 def train(make_agent, make_replay, make_env, make_stream, make_logger, args):
 
   agent = make_agent()
+  lacking = baselib.implements_agent(agent)
+  if lacking:
+    raise TypeError(f'{type(agent).__name__} does not implement the Agent protocol '
+                    f'(embodied/core/base.py:1-31): missing {lacking}')
   replay = make_replay()
   logger = make_logger()
 
