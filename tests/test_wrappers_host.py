@@ -143,3 +143,27 @@ def test_normalize_and_unify_shapes():
   assert inner['action'].dtype == np.float64 and inner['choice'].dtype == np.int64
   assert np.allclose(inner['action'], [4.0, 0.7, 0.0])      # bounded dims mapped back, free dim untouched
   assert obs['vec'].dtype == np.float32 and obs['count'].dtype == np.int32
+
+
+@needs_ref
+@pytest.mark.parametrize('size,length', [((64, 64), 4), ((8, 8), 1), ((5, 7), 3)])
+def test_dummy_env_equals_the_reference(size, length):
+  """embodied_b200.envs.dummy.Dummy against embodied/envs/dummy.py:6-59: spaces (order,
+  dtype, shape, bounds) and every value of a reset-laden episode stream."""
+  from embodied_b200.envs import dummy
+  ref = refload.load()
+  renv, menv = ref.dummy.Dummy('disc', size=size, length=length), dummy.Dummy('disc', size=size, length=length)
+  for name in ('obs_space', 'act_space'):
+    rs, ms = getattr(renv, name), getattr(menv, name)
+    assert list(rs) == list(ms), name
+    for k in rs:
+      assert same_space(rs[k], ms[k]), (name, k, rs[k], ms[k])
+  rng = np.random.default_rng(5)
+  for i in range(40):
+    reset = bool(i == 0 or rng.random() < 0.15)
+    act = {'reset': reset, 'act_disc': np.int32(1), 'act_cont': np.zeros(6, np.float32)}
+    ro, mo = renv.step(dict(act)), menv.step(dict(act))
+    assert list(ro) == list(mo)
+    for k in ro:
+      x, y = np.asarray(ro[k]), np.asarray(mo[k])
+      assert x.dtype == y.dtype and x.shape == y.shape and np.array_equal(x, y), (i, k, x, y)
