@@ -62,14 +62,11 @@ class Agent(base.Agent):
     self.device = torch.device(device if device is not None else
                                f'cuda:{torch.cuda.current_device()}')
     self.cd = {'bfloat16': torch.bfloat16, 'float32': f32}[cfg.compute_dtype]
-    if self.cd == f32:
-      # parity mode: strict IEEE fp32 GEMMs and convolutions
-      torch.backends.cuda.matmul.allow_tf32 = False
-      torch.backends.cudnn.allow_tf32 = False
-    elif cfg.get('cudnn_benchmark', True):
-      # the mid convolutions run on the library: let it time its algorithms for the
-      # (few, fixed) shapes during the eager warm-up steps that precede graph capture
-      torch.backends.cudnn.benchmark = True
+    # bf16: the mid convolutions run on the library -- let it time its algorithms for the
+    # (few, fixed) shapes during the eager warm-up steps that precede graph capture.
+    # fp32 = parity mode: strict IEEE GEMMs / convolutions and the default heuristics.
+    self._tune_convs = self.cd != f32 and bool(cfg.get('cudnn_benchmark', True))
+    self._backend_flags()
     self.store = paramlib.ParamStore(cfg, self.device, self.cd, cfg.seed, values)
     self.model = modellib.Model(cfg, self.store)
     self.opt = optim.Optimizer(cfg, self.store)
@@ -106,7 +103,16 @@ class Agent(base.Agent):
 
   # --------------------------------------------------------------------- policy
   @torch.no_grad()
+  def _backend_flags(self):
+    """The library switches are process-wide: every entry point sets what THIS agent's
+    mode needs, so agents of both modes can live in one process (the test suite)."""
+    if self.cd == f32:
+      torch.backends.cuda.matmul.allow_tf32 = False
+      torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = self._tune_convs
+
   def policy(self, carry, obs, mode='train', noise=None):    # agent.py:115-135
+    self._backend_flags()
     cfg, m = self.cfg, self.model
     deter, stoch, prevact = carry
     image = obs['image']
@@ -195,6 +201,7 @@ class Agent(base.Agent):
       torch.distributed.all_reduce(self.store.grad, op=torch.distributed.ReduceOp.AVG)
 
   def train(self, carry, data, noise=None):                  # agent.py:137-154, opt.py:31-81
+    self._backend_flags()
     mode = self.cfg.get('graph', 'auto')
     if mode and mode != 'off' and self._graph_ok:
       key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(data.items()))
@@ -298,6 +305,7 @@ class Agent(base.Agent):
 
   @torch.no_grad()
   def report(self, carry, data, noise=None):                 # agent.py:247-310 (metrics part)
+    self._backend_flags()
     carry, obs, prevact, _ = self._apply_replay_context(carry, data)
     B, T = obs['is_first'].shape
     if noise is None:
