@@ -262,8 +262,12 @@ def run_b200(args):
       b.record()
       torch.cuda.synchronize()
       total += a.elapsed_time(b) * 1e-3
-      if profile:                                    # the step's last replay of the captured graph
-        graph_us += [(k, w.ms() * 1e3) for k, w in scanlib.GRAPH_TIMERS.items()]
+      if profile and getattr(loop.agent, '_graphs', None):
+        for k, w in list(scanlib.GRAPH_TIMERS.items()):   # the step's last replay of the captured graph
+          try:
+            graph_us.append((k, w.ms() * 1e3))
+          except RuntimeError:                       # never recorded (capture refused): eager events cover it
+            scanlib.GRAPH_TIMERS.pop(k, None)
     barrier()
     launches = _lib.launch_count() - launches0
     prof, storelib.PROFILE = storelib.PROFILE, None

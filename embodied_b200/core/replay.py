@@ -496,7 +496,10 @@ class Replay:
       chunk = self.chunks.get(uuid)
       if chunk is None:
         return (uuid, index + steps)    # gone: _rows_of raises KeyError later
-      room = chunk.size - index
+      # a chunk that save() completed early is shorter than its slab: its
+      # successor starts right after `length`, not after `size`
+      full = chunk.length if chunk.succ != elements.UUID(0) else chunk.size
+      room = full - index
       if steps < room:
         return (uuid, index + steps)
       steps -= room
@@ -559,6 +562,10 @@ class Replay:
       for name, arrays in read:
         time, uuid, succ, length = elements.Path(name).stem.split('-')
         length = int(length)
+        if length > self.chunksize:
+          raise ValueError(
+              f'chunk {name} holds {length} steps but this buffer was created with '
+              f'chunksize={self.chunksize}; load it with chunksize >= {length}')
         if not self.store.configured:
           first = {k: v[0] for k, v in arrays.items() if k != 'stepid'}
           self._configure(first)

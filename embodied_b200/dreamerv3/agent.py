@@ -101,8 +101,6 @@ class Agent(base.Agent):
   init_train = init_policy
   init_report = init_policy
 
-  # --------------------------------------------------------------------- policy
-  @torch.no_grad()
   def _backend_flags(self):
     """The library switches are process-wide: every entry point sets what THIS agent's
     mode needs, so agents of both modes can live in one process (the test suite)."""
@@ -111,6 +109,8 @@ class Agent(base.Agent):
       torch.backends.cudnn.allow_tf32 = False
     torch.backends.cudnn.benchmark = self._tune_convs
 
+  # --------------------------------------------------------------------- policy
+  @torch.no_grad()
   def policy(self, carry, obs, mode='train', noise=None):    # agent.py:115-135
     self._backend_flags()
     cfg, m = self.cfg, self.model
@@ -267,6 +267,13 @@ class Agent(base.Agent):
       self.store.begin_step()
       if scan is not None:
         scan.invalidate()
+        from . import scan as scanlib
+        if scanlib.GRAPH_TIMERS:         # stopwatches of the refused capture never record
+          scanlib.GRAPH_TIMERS.clear()
+      try:                               # the failed capture may leave a sticky error behind
+        torch.cuda.synchronize()
+      except Exception:                  # noqa: BLE001
+        pass
       return None
     st.outs, st.carry_out, st.replay = _detach(mid[2]), carry_out, replay
     del mid
@@ -301,7 +308,12 @@ class Agent(base.Agent):
     mv = st.mvec.clone()
     metrics = {k: mv[i] for i, k in enumerate(st.names)}
     metrics.update(extra)
-    return st.carry_out, {'replay': st.replay}, metrics
+    # stepid: the view of the batch Replay.sample returned (same bytes as the static copy),
+    # so that Replay.update recognises its own tensor and needs no device read
+    replay = dict(st.replay)
+    K = self.cfg.replay_context
+    replay['stepid'] = data['stepid'][:, K:] if K else data['stepid']
+    return st.carry_out, {'replay': replay}, metrics
 
   @torch.no_grad()
   def report(self, carry, data, noise=None):                 # agent.py:247-310 (metrics part)

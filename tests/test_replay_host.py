@@ -302,3 +302,27 @@ def test_update_overlapping_windows_last_writer_wins():
       assert got['lat'][b, t, 0] == want[int(got['step'][b, t])]
   kinds = [k for k, _ in replay.store.launches]
   assert kinds.count('scatter') == 1
+
+
+def test_shift_crosses_chunk_completed_early_by_save(tmp_path):
+  """save() completes the current chunk early (length < size, successor set); a window
+  offset that crosses it must land in the successor, not past the chunk's length
+  (Replay._shift used chunk.size)."""
+  replay = make(6, 100, chunksize=32, directory=str(tmp_path), save_wait=True)
+  for step in range(20):
+    replay.add({'step': np.int32(step), 'lat': np.zeros(1, np.float32)})
+  replay.save()
+  for step in range(20, 40):
+    replay.add({'step': np.int32(step), 'lat': np.zeros(1, np.float32)})
+  (c0, _) = replay.items[0]
+  chunk = replay.chunks[c0]
+  assert chunk.length == 20 and chunk.succ != elements.UUID(0)
+  assert replay._shift((c0, 15), 4) == (c0, 19)
+  assert replay._shift((c0, 15), 5) == (chunk.succ, 0)
+  assert replay._shift((c0, 15), 6) == (chunk.succ, 1)
+  rows = replay._rows_of(*replay._shift((c0, 15), 6), 2)
+  assert len(rows) == 2
+  # a chunk still being written (no successor) keeps the slab size as its room
+  cur = replay.chunks[chunk.succ]
+  assert cur.succ == elements.UUID(0)
+  assert replay._shift((cur.uuid, 3), 10) == (cur.uuid, 13)
