@@ -1,0 +1,366 @@
+// emb_conv5x5_nhwc_tc: the 5x5 SAME convolutions of the dreamerv3 encoder / decoder
+// (dreamerv3/rssm.py:233-240, 336-352; embodied/jax/nets.py:298-323 Conv2D) as an
+// implicit GEMM on the 5th-generation tensor cores.
+//
+//   out[p][co] = sum_{tap=(ky,kx)} sum_ci  in[p + (ky-2, kx-2)][ci] * w[tap][co][ci]
+//
+// One persistent CTA per SM walks 128-pixel output tiles (whole image rows, so the
+// 128 pixels are contiguous in NHWC memory).  Per (tap, 64-channel block):
+//   A = the 128 x 64 window of the input shifted by the tap, fetched by ONE 4-D TMA
+//       tile copy (cp.async.bulk.tensor, 128-byte swizzle); the SAME padding is the
+//       TMA's out-of-bounds zero fill -- no halo handling in the kernel;
+//   B = the tap's [Cout][64] weight slice (K-major, packed once per optimiser step);
+//   D += A @ B^T by tcgen05.mma (M = 128, N = Cout <= 256, K = 16 per instruction),
+//       fp32 accumulators in TENSOR MEMORY, two accumulator buffers of 256 columns
+//       so that the epilogue of tile i overlaps the MMAs of tile i + 1.
+// Warp roles: warp 0 = TMA producer (one lane), warp 1 = MMA issuer (one lane; owns the
+// TMEM allocation), warps 2..5 = epilogue (tcgen05.ld 32 lanes x 32 columns -> bf16 ->
+// 64-byte stores per thread).  smem ring: 4 stages x (16 KiB A + 32 KiB B).
+// The same kernel is the data-gradient of the convolution (flipped taps, channels
+// swapped -- a different weight packing, see dreamerv3/ops.py).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/embodied_b200.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kABytes = 128 * 128;          // 128 pixels x 64 bf16
+constexpr int kBBytes = 256 * 128;          // <= 256 output channels x 64 bf16
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+
+struct ConvShape {
+  int tiles;           // 128-pixel output tiles
+  int hw;              // H * W
+  int w;               // W
+  int kblocks;         // Cin / 64
+  int cout;
+  int taps;            // k * k
+  int ksize;           // k
+  int act;             // epilogue: 0 = store, (reserved)
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5}], [%6];"
+      :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4}], [%5];"
+      :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// tcgen05 shared-memory matrix descriptor, K-major operand, 128-byte swizzle: rows of
+// 128 bytes (64 bf16 of K), 8-row swizzle atoms 1024 bytes apart (cute UMMA::SmemDescriptor:
+// start >> 4 [0,14) | LBO >> 4 [16,30) | SBO >> 4 [32,46) | version 1 [46,48) | layout [61,64)).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                      // leading byte offset: unused with swizzled K-major
+  d |= (uint64_t)(1024 >> 4) << 32;            // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                      // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                      // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor (cute UMMA::InstrDescriptor): D = f32, A = B = bf16, both K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on `bar` once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+               :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 32 lanes x 32 consecutive fp32 columns of tensor memory -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16(uint32_t lo, uint32_t hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(lo), __uint_as_float(hi));
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
+               __nv_bfloat16* __restrict__ out, const float* __restrict__ bias, const ConvShape s) {
+  extern __shared__ unsigned char smem_raw[];
+  // 128-byte swizzle atoms are anchored on 1024-byte boundaries of the shared window
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                 // [kStages]  TMA -> MMA
+  uint64_t* empty = bars + kStages;      // [kStages]  MMA -> TMA
+  uint64_t* tfull = bars + 2 * kStages;  // [2]        MMA -> epilogue (accumulator ready)
+  uint64_t* tempty = tfull + 2;          // [2]        epilogue -> MMA (accumulator drained)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_in) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_w) : "memory");
+  }
+  if (warp == 1) {                        // one warp allocates (and later frees) tensor memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int iters = s.taps * s.kblocks;
+  const uint32_t stage_tx = (uint32_t)kABytes + (uint32_t)s.cout * 128u;
+  const int half = s.ksize >> 1;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < s.tiles; tile += gridDim.x) {
+        const int pix0 = tile * 128;
+        const int n0 = pix0 / s.hw, h0 = (pix0 - n0 * s.hw) / s.w;
+        for (int tap = 0; tap < s.taps; ++tap) {
+          const int ky = tap / s.ksize, kx = tap - ky * s.ksize;
+          for (int kb = 0; kb < s.kblocks; ++kb) {
+            mbar_wait(&empty[stage], phase ^ 1u);
+            mbar_expect_tx(&full[stage], stage_tx);
+            tma_load_4d(sA + stage * kABytes, &map_in, kb * 64, kx - half, h0 + ky - half, n0, &full[stage]);
+            tma_load_3d(sB + stage * kBBytes, &map_w, kb * 64, 0, tap, &full[stage]);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, s.cout);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t accphase = 0;
+      for (int tile = blockIdx.x; tile < s.tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], accphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)acc * 256u;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytes));
+          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * kBBytes));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)     // 4 x (K = 16): +32 bytes inside the swizzle atom
+            umma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+          umma_commit(&empty[stage]);      // the stage is free once these MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull[acc]);          // accumulator complete
+        acc ^= 1;
+        if (acc == 0) accphase ^= 1u;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3;                // a warp reads TMEM lanes [32 * (warp % 4), +32)
+    int acc = 0;
+    uint32_t accphase = 0;
+    for (int tile = blockIdx.x; tile < s.tiles; tile += gridDim.x) {
+      mbar_wait(&tfull[acc], accphase);
+      tc_fence_after();
+      const int m = q * 32 + lane;
+      __nv_bfloat16* orow = out + ((size_t)tile * 128 + m) * s.cout;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
+      for (int c0 = 0; c0 < s.cout; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + c0 + j));
+        }
+        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) accphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 :: "r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- host side ----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+int g_sms = 0;
+
+}  // namespace
+
+extern "C" int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const float* bias, void* out,
+                                   int64_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                                   int32_t ksize, void* stream) {
+  const char* who = "emb_conv5x5_nhwc_tc";
+  if (n <= 0) return 0;
+  if (!in || !w_packed || !out) return emb::fail(-1, "%s: null pointer", who);
+  if (ksize != 5 && ksize != 3 && ksize != 1) return emb::fail(-1, "%s: kernel size %d not in {1, 3, 5}", who, ksize);
+  if (cin % 64) return emb::fail(-1, "%s: cin=%d must be a multiple of 64 (128-byte swizzled K blocks)", who, cin);
+  if (cout % 32 || cout < 32 || cout > 256)
+    return emb::fail(-1, "%s: cout=%d must be a multiple of 32 in [32, 256]", who, cout);
+  // a tile = 128 consecutive pixels = whole rows of one image, or whole images
+  int wt = w, ht, nt;
+  if (w > 128 || 128 % w) return emb::fail(-1, "%s: width %d must divide 128", who, w);
+  if (h * w >= 128) {
+    ht = 128 / w; nt = 1;
+    if (h % ht) return emb::fail(-1, "%s: height %d must be a multiple of %d rows per tile", who, h, ht);
+  } else {
+    ht = h; nt = 128 / (h * w);
+    if (128 % (h * w) || n % nt) return emb::fail(-1, "%s: %dx%d images must pack into 128-pixel tiles", who, h, w);
+  }
+  if ((n * h * w) % 128) return emb::fail(-1, "%s: n*h*w must be a multiple of 128", who);
+  if (((uintptr_t)in | (uintptr_t)w_packed | (uintptr_t)out) & 15)
+    return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return emb::fail(-1, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return emb::fail_cuda(who);
+  }
+  CUtensorMap map_in, map_w;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)w * cin * 2, (cuuint64_t)h * w * cin * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)wt, (cuuint32_t)ht, (cuuint32_t)nt};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&map_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides,
+                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled(input) failed with %d", who, (int)r);
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)(ksize * ksize)};
+    const cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
+    const cuuint32_t box[3] = {64, (cuuint32_t)cout, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled(weights) failed with %d", who, (int)r);
+  }
+  ConvShape s;
+  s.tiles = (int)(n * h * w / 128);
+  s.hw = h * w;
+  s.w = w;
+  s.kblocks = cin / 64;
+  s.cout = cout;
+  s.taps = ksize * ksize;
+  s.ksize = ksize;
+  s.act = 0;
+  const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute((const void*)conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess)
+      return emb::fail_cuda(who);
+    attr_set = true;
+  }
+  const int grid = s.tiles < g_sms ? s.tiles : g_sms;
+  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+      map_in, map_w, reinterpret_cast<__nv_bfloat16*>(out), bias, s);
+  if (cudaGetLastError() != cudaSuccess) return emb::fail_cuda(who);
+  emb::count_launch();
+  return 0;
+}

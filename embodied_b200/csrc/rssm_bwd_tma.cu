@@ -154,9 +154,9 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   const int tid = threadIdx.x;
   const size_t RH = (size_t)kRows * H, RD = (size_t)kRows * D, RSC = (size_t)kRows * SC;
 
-  // ---- shared memory: [barriers 256 B][out 16 x maxper*8 f32][4 x 16 row statistics][A region][ring]
+  // ---- shared memory: [barriers 256 B][segment table 256 B][out 16 x maxper*8 f32][4 x 16 row statistics][A region][ring]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  float* out = reinterpret_cast<float*>(smem_raw + 256);
+  float* out = reinterpret_cast<float*>(smem_raw + 512);   // [256, 512): the producer's segment table
   const int maxper = (a.hoist_x2 >> 8) & 0xff;
   float* st = out + kRows * maxper * 8;
   float *rstd_a = st, *coef_a = st + 16, *rstd_b = st + 32, *coef_b = st + 48;
@@ -165,7 +165,7 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   uint4* afrag4 = reinterpret_cast<uint4*>(abase);
   Ring ring;
   ring.nstages = a.hoist_x2 & 0xff;
-  ring.stage_bytes = (a.hoist_x2 >> 16) * 1024;
+  ring.stage_bytes = ((a.hoist_x2 >> 16) & 0xff) * 1024;
   ring.stage = 0;
   ring.phase = 0;
   ring.full = bars;
@@ -181,14 +181,14 @@ rssm_bwd_tma_kernel(const __grid_constant__ emb_rssm_bwd_args a) {
   const Plan p = make_plan(a);
 
   // =========================================================== producer warp
-  if (tid >= kCThreads) {
-    if (tid == kCThreads) {
-      for (int t = T - 1; t >= 0; --t)
-        for (int i = 0; i < 5; ++i)
-          if (p.u0[i] < p.u1[i]) produce(ring, p.blk[i], p.per[i], p.ks[i], false);
-    }
-    return;
+  Seg* segs = reinterpret_cast<Seg*>(smem_raw + 256);
+  if (tid == kCThreads) {
+    int n = 0;
+    for (int i = 0; i < 5; ++i)
+      if (p.u0[i] < p.u1[i]) segs[n++] = Seg{p.blk[i], p.per[i], p.ks[i], 0};
+    run_producer(ring, segs, n, T, 0u, (a.hoist_x2 >> 24) & 0x7f);
   }
+  if (tid >= kCThreads) return;
 
   // ========================================================== consumer warps
   GridBarrierC bar{a.barrier, 0};
@@ -650,7 +650,7 @@ int launch_bwd(const emb_rssm_bwd_args& a, void* stream, bool dry) {
   if (const char* e = getenv("EMB_TMA_STAGES")) stage_cap = atoi(e);
   if (stage_bytes < 8192 || stage_bytes > 65536 || stage_bytes % 1024)
     return emb::fail(-1, "%s: EMB_TMA_STAGE_KB out of range", who);
-  size_t fixed = 256 + sizeof(float) * (rssm::kRows * maxper * 8 + 64);
+  size_t fixed = 512 + sizeof(float) * (rssm::kRows * maxper * 8 + 64);
   fixed += bwd_a_region_bytes(a.D, a.G, a.H, SC);
   const size_t cap = 227 * 1024 - 128;
   int n = fixed + 2 * (size_t)stage_bytes <= cap ? (int)((cap - fixed) / stage_bytes) : 0;
@@ -662,7 +662,14 @@ int launch_bwd(const emb_rssm_bwd_args& a, void* stream, bool dry) {
   if (a.H > 4096 || a.H % 4) return emb::fail(-1, "%s: hidden=%d must be <= 4096 and a multiple of 4", who, a.H);
   const size_t smem = fixed + (size_t)n * stage_bytes + 128;
   emb_rssm_bwd_args copy = a;
-  copy.hoist_x2 = n | (maxper << 8) | ((stage_bytes / 1024) << 16);      // kernel-side ring configuration
+  // L2 prefetch distance in ring chunks.  Measured (r02, size200m): 0 -> 61.5 us/step, 8 -> 68.2,
+  // 16 -> 69.0, 32 -> 71.2: the stalls are latency chains, not a starved stream, and the
+  // prefetched lines displace the activations the phases exchange through L2.  Off by default.
+  int ahead = 0;
+  if (const char* e = getenv("EMB_TMA_PREFETCH")) ahead = atoi(e);
+  if (ahead < 0) ahead = 0;
+  if (ahead > 127) ahead = 127;
+  copy.hoist_x2 = n | (maxper << 8) | ((stage_bytes / 1024) << 16) | (ahead << 24);   // kernel-side ring configuration
   if (dry) return 0;                      // emb_rssm_tma_fits: validation and sizing only
   const void* fn = (const void*)rssm_bwd_tma_kernel;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

@@ -194,9 +194,9 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   const int tid = threadIdx.x, cta = blockIdx.x, ncta = gridDim.x;
   const size_t RH = (size_t)kRows * H, RD = (size_t)kRows * D, RSC = (size_t)kRows * SC;
 
-  // ---- shared memory: [barriers 256 B][out 16 x maxper*8 f32][stats][A region][ring]
+  // ---- shared memory: [barriers 256 B][segment table 256 B][out 16 x maxper*8 f32][stats][A region][ring]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  float* out = reinterpret_cast<float*>(smem_raw + 256);
+  float* out = reinterpret_cast<float*>(smem_raw + 512);   // [256, 512): the producer's segment table
   const int maxper = (a.tma_cfg >> 8) & 0xff;
   float* rstd_a = out + kRows * maxper * 8;
   float* red = rstd_a + kRows;                                   // [kCWarps] + scratch
@@ -211,7 +211,7 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   uint4* afrag4 = reinterpret_cast<uint4*>(abase);
   Ring ring;
   ring.nstages = a.tma_cfg & 0xff;
-  ring.stage_bytes = (a.tma_cfg >> 16) * 1024;
+  ring.stage_bytes = ((a.tma_cfg >> 16) & 0xff) * 1024;
   ring.stage = 0;
   ring.phase = 0;
   ring.full = bars;
@@ -244,22 +244,28 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   const int ks01 = (Dg + H) / 16, ks2 = H / 16;                  // P4's two k ranges
 
   // =========================================================== producer warp
-  if (tid >= kCThreads) {
-    if (tid == kCThreads) {
-      for (int t = 0; t < T; ++t) {
-        if (p.on_hid) {
-          produce(ring, p.blk_hid, p.per_hid, ks01, false);
-          produce(ring, p.blk_hid + (size_t)ks01 * p.per_hid * 256, p.per_hid, ks2, false);
-        }
-        if (p.on_gru) produce(ring, p.blk_gru, p.per_gru, p.ks_gru, false);
-        int u0, u1;
-        ph1_range(a, p, t + 1 == T, u0, u1);
-        if (u0 < u1) produce(ring, p.blk_ph1, p.per_ph1, p.ks_ph1, true);
-        if (p.on_log) produce(ring, p.blk_log, p.per_log, p.ks_log, false);
-      }
+  // (the per-step schedule is static: see rssm_tma.cuh run_producer; the obs0 | dynin0 block
+  //  of a CTA that only owns y0' columns is left out of the last step, like its consumers)
+  Seg* segs = reinterpret_cast<Seg*>(smem_raw + 256);
+  if (tid == kCThreads) {
+    int n = 0;
+    uint32_t skip_last = 0;
+    if (p.on_hid) {
+      segs[n++] = Seg{p.blk_hid, p.per_hid, ks01, 0};
+      segs[n++] = Seg{p.blk_hid + (size_t)ks01 * p.per_hid * 256, p.per_hid, ks2, 0};
     }
-    return;
+    if (p.on_gru) segs[n++] = Seg{p.blk_gru, p.per_gru, p.ks_gru, 0};
+    int u0, u1, l0, l1;
+    ph1_range(a, p, false, u0, u1);
+    ph1_range(a, p, true, l0, l1);
+    if (u0 < u1) {
+      if (!(l0 < l1)) skip_last |= 1u << n;
+      segs[n++] = Seg{p.blk_ph1, p.per_ph1, p.ks_ph1, 1};
+    }
+    if (p.on_log) segs[n++] = Seg{p.blk_log, p.per_log, p.ks_log, 0};
+    run_producer(ring, segs, n, T, skip_last, (a.tma_cfg >> 24) & 0x7f);
   }
+  if (tid >= kCThreads) return;
 
   // ========================================================== consumer warps
   GridBarrierC bar{a.barrier, 0};
@@ -640,7 +646,7 @@ int g_sms_tma = 0;
 namespace emb_tma {
 
 size_t fwd_smem_bytes(const emb_rssm_fwd_args& a, int maxper, int stage_bytes, int* nstages) {
-  size_t fixed = 256 + sizeof(float) * (rssm::kRows * maxper * 8 + rssm::kRows + 32) + 128 * sizeof(int);
+  size_t fixed = 512 + sizeof(float) * (rssm::kRows * maxper * 8 + rssm::kRows + 32) + 128 * sizeof(int);
   fixed += sizeof(float) * (4 * (a.D / a.G) + a.H);             // staged constants
   fixed = (fixed + 127) & ~(size_t)127;
   fixed += a_region_bytes(a);
@@ -695,7 +701,14 @@ int launch_fwd(const emb_rssm_fwd_args& a, void* stream, bool dry) {
   const size_t smem = fwd_smem_bytes(a, maxper, stage_bytes, &nstages);
   if (nstages < 2)
     return emb::fail(-1, "%s: A operand (%d columns) leaves no room for the weight ring", who, Dg + 2 * a.H);
-  copy.tma_cfg = nstages | (maxper << 8) | ((stage_bytes / 1024) << 16);
+  // L2 prefetch distance in ring chunks.  Measured (r02, size200m): 0 -> 61.5 us/step, 8 -> 68.2,
+  // 16 -> 69.0, 32 -> 71.2: the stalls are latency chains, not a starved stream, and the
+  // prefetched lines displace the activations the phases exchange through L2.  Off by default.
+  int ahead = 0;
+  if (const char* e = getenv("EMB_TMA_PREFETCH")) ahead = atoi(e);
+  if (ahead < 0) ahead = 0;
+  if (ahead > 127) ahead = 127;
+  copy.tma_cfg = nstages | (maxper << 8) | ((stage_bytes / 1024) << 16) | (ahead << 24);
   if (dry) return 0;                      // emb_rssm_tma_fits: validation and sizing only
   const void* fn = (const void*)rssm_fwd_tma_kernel;
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

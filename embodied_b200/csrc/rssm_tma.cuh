@@ -144,6 +144,69 @@ __device__ __forceinline__ void produce(Ring& r, const unsigned char* blk, int p
   }
 }
 
+// ---- look-ahead producer ------------------------------------------------------
+// The ring holds only a few microseconds of stream, so HBM used to idle whenever
+// the consumers sat in a grid barrier, an operand build or an epilogue.  The
+// schedule is static, so the producer also runs an L2 PREFETCH cursor `ahead`
+// chunks in front of the ring's load cursor (cp.async.bulk.prefetch.L2): HBM keeps
+// filling L2 (126 MB) through every stall, and the ring then refills at L2 rate.
+struct Seg {                 // one weight block streamed per step
+  const unsigned char* blk;
+  int per, ksteps, a_global;
+};
+constexpr int kMaxSegs = 6;
+static_assert(sizeof(Seg) * kMaxSegs <= 256, "segment table must fit its 256-byte slot");
+struct Cursor { int t, s, k0; };
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src), "r"(bytes) : "memory");
+}
+
+// Next chunk of the periodic schedule (`nseg` segments per step, `steps` steps; segment s is
+// left out of the LAST step when bit s of skip_last is set).  False at the end.
+__device__ __forceinline__ bool next_chunk(Cursor& c, const Seg* segs, int nseg, int steps,
+                                           uint32_t skip_last, int stage_bytes,
+                                           const unsigned char*& ptr, uint32_t& bytes) {
+  for (;;) {
+    if (c.t >= steps) return false;
+    if (c.s >= nseg) { c.s = 0; c.k0 = 0; ++c.t; continue; }
+    const Seg g = segs[c.s];
+    const bool skip = (c.t + 1 == steps) && ((skip_last >> c.s) & 1u);
+    if (skip || c.k0 >= g.ksteps) { ++c.s; c.k0 = 0; continue; }
+    const int kc = ksteps_per_chunk(stage_bytes, g.per, g.a_global != 0);
+    const int n = min(kc, g.ksteps - c.k0);
+    const uint32_t step_bytes = (uint32_t)g.per * 256u;
+    ptr = g.blk + (size_t)c.k0 * step_bytes;
+    bytes = (uint32_t)n * step_bytes;
+    c.k0 += kc;
+    return true;
+  }
+}
+
+// The producer thread's whole life: `segs` lives in shared memory.
+static __device__ __noinline__ void run_producer(Ring r, const Seg* segs, int nseg, int steps,
+                                          uint32_t skip_last, int ahead) {
+  Cursor ld{0, 0, 0}, pf{0, 0, 0};
+  const unsigned char *ptr, *pp;
+  uint32_t bytes, pb;
+  bool pf_on = ahead > 0;
+  for (int i = 0; i < ahead && pf_on; ++i) {
+    pf_on = next_chunk(pf, segs, nseg, steps, skip_last, r.stage_bytes, pp, pb);
+    if (pf_on && i >= r.nstages) bulk_prefetch_l2(pp, pb);    // the first chunks go straight to the ring
+  }
+  const uint64_t pol = policy_evict_first();
+  while (next_chunk(ld, segs, nseg, steps, skip_last, r.stage_bytes, ptr, bytes)) {
+    if (pf_on) {
+      pf_on = next_chunk(pf, segs, nseg, steps, skip_last, r.stage_bytes, pp, pb);
+      if (pf_on) bulk_prefetch_l2(pp, pb);
+    }
+    mbar_wait(&r.empty[r.stage], r.phase ^ 1u);
+    mbar_expect_tx(&r.full[r.stage], bytes);
+    bulk_g2s_hint(r.data + (size_t)r.stage * r.stage_bytes, ptr, bytes, &r.full[r.stage], pol);
+    if (++r.stage == r.nstages) { r.stage = 0; r.phase ^= 1u; }
+  }
+}
+
 // explicit shared-space loads: inside the non-inlined consume() the compiler cannot prove
 // that the ring / operand pointers are shared memory and would emit generic loads
 __device__ __forceinline__ uint2 lds_u2(uint32_t addr) {

@@ -76,6 +76,7 @@ class Model:
     self.ret_hi = torch.zeros((), dtype=f32, device=self.device)
     self.fused_norm = bool(cfg.get('fused_norm', True)) and self.device.type == 'cuda'
     self.fused_spatial = bool(cfg.get('fused_spatial', True)) and self.device.type == 'cuda'
+    self.tc_conv = bool(cfg.get('tc_conv', True)) and self.device.type == 'cuda'
     self.scan = None
     if cfg.get('fused_scan', True) and self.device.type == 'cuda':
       from . import scan as scanlib
@@ -115,7 +116,11 @@ class Model:
   def conv(self, x, name, bias=True):                        # nets.py:298-323; x is NHWC
     """bias=False: the caller adds the bias inside the following fused norm
     (after the 2x2 max-pool, with which a per-channel constant commutes)."""
-    w = self.W(f'{name}/kernel').permute(3, 2, 0, 1)         # HWIO -> OIHW
+    w = self.W(f'{name}/kernel')
+    if (self.tc_conv and not bias and
+        ops.conv_tc_supported(x, w.shape[2], w.shape[3], w.shape[0])):
+      return ops.ConvTC.apply(x, w)                          # tcgen05 implicit GEMM (csrc/conv_tc.cu)
+    w = w.permute(3, 2, 0, 1)                                # HWIO -> OIHW
     b = self.W(f'{name}/bias') if bias else None
     y = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=w.shape[-1] // 2)
     return y.permute(0, 2, 3, 1)                             # NHWC view (channels_last memory)

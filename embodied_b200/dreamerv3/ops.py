@@ -394,3 +394,80 @@ def onehot_sample(logit, gumbel, unimix, out_dtype, out=None):
       logit.data_ptr(), _dtype_code(logit), S * C, gumbel.data_ptr(), gumbel.stride(0), n, S, C,
       float(unimix), flat.data_ptr(), _dtype_code(flat), flat.stride(0), None, stream))
   return res
+
+
+# ------------------------------------------- tcgen05 implicit-GEMM convolutions
+def conv_tc_supported(x, cin, cout, k=5):
+  """emb_conv5x5_nhwc_tc: bf16 NHWC, 64-channel K blocks, whole-row 128-pixel tiles."""
+  if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4 or k not in (1, 3, 5):
+    return False
+  n, h, w, c = x.shape
+  if c != cin or cin % 64 or cout % 32 or not 32 <= cout <= 256 or w > 128 or 128 % w:
+    return False
+  if h * w >= 128:
+    return h % (128 // w) == 0
+  return 128 % (h * w) == 0 and n % (128 // (h * w)) == 0
+
+
+def pack_conv_weight(w, data_grad=False):
+  """HWIO kernel (k, k, cin, cout) -> the bf16 [k*k][N][K] layout of emb_conv5x5_nhwc_tc.
+  Forward: N = cout, K = cin.  data_grad: the spatially flipped kernel with the channel
+  roles exchanged (N = cin, K = cout), so that the same launch computes the input gradient."""
+  k, _, cin, cout = w.shape
+  if data_grad:
+    return w.flip(0, 1).reshape(k * k, cin, cout).to(torch.bfloat16).contiguous()
+  return w.permute(0, 1, 3, 2).reshape(k * k, cout, cin).to(torch.bfloat16).contiguous()
+
+
+def conv_tc(x, wp, bias=None, k=5):
+  """x (N, H, W, Cin) bf16 NHWC, wp = pack_conv_weight(...) -> (N, H, W, Cout) bf16."""
+  lib = _lib.load()
+  if not getattr(lib, '_conv_tc_bound', False):
+    lib.emb_conv5x5_nhwc_tc.argtypes = [_vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]
+    lib.emb_conv5x5_nhwc_tc.restype = ctypes.c_int
+    lib._conv_tc_bound = True
+  x = x.contiguous()
+  n, h, w, cin = x.shape
+  taps, cout, kk = wp.shape
+  assert taps == k * k and kk == cin and wp.dtype == torch.bfloat16 and wp.is_contiguous(), (wp.shape, x.shape)
+  out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+  stream = torch.cuda.current_stream(x.device).cuda_stream
+  _lib.check(lib.emb_conv5x5_nhwc_tc(
+      x.data_ptr(), wp.data_ptr(), None if bias is None else bias.data_ptr(), out.data_ptr(),
+      n, h, w, cin, cout, k, stream))
+  return out
+
+
+class ConvTC(torch.autograd.Function):
+  """y = conv_same(x, w): x (N, H, W, Cin) bf16 NHWC, w (k, k, Cin, Cout) HWIO
+  (nets.py:298-323).  Forward and input gradient are the same tcgen05 launch with two
+  weight packings; the weight gradient is `wgrad` below."""
+
+  @staticmethod
+  def forward(ctx, x, w):
+    k = w.shape[0]
+    x = x.contiguous()
+    y = conv_tc(x, pack_conv_weight(w), k=k)
+    ctx.save_for_backward(x, w)
+    return y
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, w = ctx.saved_tensors
+    k = w.shape[0]
+    gy = gy.contiguous()
+    gx = gw = None
+    if ctx.needs_input_grad[0]:
+      gx = conv_tc(gy, pack_conv_weight(w, data_grad=True), k=k)
+    if ctx.needs_input_grad[1]:
+      gw = conv_wgrad(x, gy, k).to(w.dtype)
+    return gx, gw
+
+
+def conv_wgrad(x, gy, k):
+  """dL/dw (k, k, Cin, Cout) of a SAME convolution from x (N, H, W, Cin) and
+  gy (N, H, W, Cout), both NHWC."""
+  cin, cout = x.shape[-1], gy.shape[-1]
+  g = torch.nn.grad.conv2d_weight(
+      x.permute(0, 3, 1, 2), (cout, cin, k, k), gy.permute(0, 3, 1, 2), padding=k // 2)
+  return g.permute(2, 3, 1, 0)

@@ -392,6 +392,23 @@ int emb_pack_tiles(const float* base, const int64_t* slot_off, const int32_t* sl
                    const int32_t* slot_nstride, void* dst, int64_t nslots, int32_t per,
                    int32_t ks_begin, int32_t ks_count, int32_t ks_total, void* stream);
 
+/* The 5x5 SAME convolutions of the dreamerv3 encoder / decoder on 64..256 channels
+ * (dreamerv3/rssm.py:233-240 conv -> pool -> norm -> act; :336-352 up-sample -> conv -> norm;
+ * embodied/jax/nets.py:298-323 Conv2D, NHWC activations, HWIO kernels) as an implicit GEMM on
+ * the tcgen05 tensor cores with TMEM accumulators and TMA (cp.async.bulk.tensor) operand tiles
+ * (embodied_b200/csrc/conv_tc.cu).  bf16 in / out, fp32 accumulation.
+ *   out[n][y][x][co] = bias[co] + sum_{ky,kx,ci} in[n][y+ky-k/2][x+kx-k/2][ci] * w_packed[ky*k+kx][co][ci]
+ * with zeros outside the image.  w_packed: [k*k][cout][cin] bf16 (the HWIO kernel with its last
+ * two axes swapped); packing the spatially flipped kernel with channels exchanged
+ * ([24-tap][cin][cout]) makes the same launch the convolution's DATA GRADIENT.
+ * Constraints: k in {1, 3, 5}; cin % 64 == 0; cout % 32 == 0, 32 <= cout <= 256; 128 % w == 0 and
+ * the images tile into 128-pixel runs of whole rows (h*w >= 128: h % (128/w) == 0; smaller
+ * images: 128 % (h*w) == 0 and n % (128/(h*w)) == 0); 16-byte aligned pointers.  bias (fp32
+ * [cout]) may be NULL. */
+int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const float* bias, void* out,
+                        int64_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,89 @@
+"""emb_conv5x5_nhwc_tc (tcgen05 implicit-GEMM convolution) against an fp32
+convolution of the same bf16-rounded operands.  Tolerance: the kernel accumulates
+bf16 products in fp32 (exact products, different summation order) and rounds the
+result to bf16 once: |err| <= 2^-8 |y| + a few fp32 ulps of the accumulated magnitude."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+import torch.nn.functional as F                      # noqa: E402
+from embodied_b200.dreamerv3 import ops              # noqa: E402
+
+SHAPES = [  # n, h, w, cin, cout, k  -- the dreamerv3 size200m layers (rssm.py:233-240, 336-352) + edge cases
+    (4, 32, 32, 128, 192, 5), (4, 16, 16, 192, 256, 5), (4, 8, 8, 256, 256, 5),
+    (2, 16, 16, 256, 192, 5), (2, 32, 32, 192, 128, 5),
+    (2, 8, 8, 64, 32, 5), (3, 32, 32, 64, 64, 3), (8, 4, 4, 64, 96, 5), (8, 4, 8, 128, 64, 1),
+    (150, 16, 16, 64, 64, 5),       # more tiles than SMs: every CTA loops, both accumulator buffers reused
+]
+
+
+def reference(x, w, bias=None):
+  y = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(3, 2, 0, 1),
+               None if bias is None else bias, padding=w.shape[0] // 2)
+  return y.permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout,k', SHAPES)
+def test_forward_matches_fp32_convolution(n, h, w, cin, cout, k):
+  g = torch.Generator(device='cuda').manual_seed(n * 1000 + cin + cout + k)
+  x = torch.randn((n, h, w, cin), generator=g, device='cuda').to(torch.bfloat16)
+  wt = (torch.randn((k, k, cin, cout), generator=g, device='cuda') / (k * cin ** 0.5)).to(torch.bfloat16)
+  assert ops.conv_tc_supported(x, cin, cout, k)
+  y = ops.conv_tc(x, ops.pack_conv_weight(wt), k=k)
+  ref = reference(x, wt)
+  err = (y.float() - ref).abs()
+  tol = 2.0 ** -8 * ref.abs() + 1e-3 * ref.abs().max()
+  assert bool((err <= tol).all()), float((err - tol).max())
+  # the borders are where the TMA's zero fill stands in for the SAME padding
+  for sl in (y[:, 0], y[:, -1], y[:, :, 0], y[:, :, -1]):
+    assert float(sl.float().abs().max()) > 0
+
+
+def test_bias_and_data_gradient_packing():
+  n, h, w, cin, cout, k = 2, 16, 16, 128, 192, 5
+  g = torch.Generator(device='cuda').manual_seed(0)
+  x = torch.randn((n, h, w, cin), generator=g, device='cuda').to(torch.bfloat16)
+  wt = (torch.randn((k, k, cin, cout), generator=g, device='cuda') / 50).to(torch.bfloat16)
+  bias = torch.randn(cout, generator=g, device='cuda')
+  y = ops.conv_tc(x, ops.pack_conv_weight(wt), bias=bias, k=k)
+  ref = reference(x, wt, bias)
+  assert float((y.float() - ref).abs().max()) <= 2.0 ** -7 * float(ref.abs().max())
+  # input gradient of sum(conv(x) * gy) = the same launch on gy with the flipped, transposed kernel
+  gy = torch.randn((n, h, w, cout), generator=g, device='cuda').to(torch.bfloat16)
+  xf = x.float().requires_grad_(True)
+  (reference(xf, wt) * gy.float()).sum().backward()
+  gx = ops.conv_tc(gy, ops.pack_conv_weight(wt, data_grad=True), k=k)
+  assert gx.shape == x.shape
+  assert float((gx.float() - xf.grad).abs().max()) <= 2.0 ** -7 * float(xf.grad.abs().max())
+
+
+def test_rejects_unsupported_shapes():
+  x = torch.zeros((2, 8, 8, 48), dtype=torch.bfloat16, device='cuda')
+  assert not ops.conv_tc_supported(x, 48, 64)
+  wp = torch.zeros((25, 64, 48), dtype=torch.bfloat16, device='cuda')
+  with pytest.raises(RuntimeError, match='multiple of 64'):
+    ops.conv_tc(x, wp)
+
+
+def test_autograd_function_matches_library_convolution():
+  """ops.ConvTC (forward + both gradients) against torch's bf16 convolution of the same
+  operands: outputs to bf16 rounding, gradients to 1e-2 relative L2."""
+  n, h, w, cin, cout, k = 8, 16, 16, 192, 256, 5
+  g = torch.Generator(device='cuda').manual_seed(3)
+  x0 = torch.randn((n, h, w, cin), generator=g, device='cuda').to(torch.bfloat16)
+  w0 = (torch.randn((k, k, cin, cout), generator=g, device='cuda') / 70).to(torch.bfloat16)
+  gy = torch.randn((n, h, w, cout), generator=g, device='cuda').to(torch.bfloat16)
+  res = []
+  for own in (True, False):
+    x, wt = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+    if own:
+      y = ops.ConvTC.apply(x, wt)
+    else:
+      y = F.conv2d(x.permute(0, 3, 1, 2), wt.permute(3, 2, 0, 1), padding=k // 2).permute(0, 2, 3, 1)
+    (y.float() * gy.float()).sum().backward()
+    res.append((y.detach().float(), x.grad.float(), wt.grad.float()))
+  rel2 = lambda a, b: float((a - b).norm() / b.norm())
+  assert rel2(res[0][0], res[1][0]) < 1e-2
+  assert rel2(res[0][1], res[1][1]) < 1e-2
+  assert rel2(res[0][2], res[1][2]) < 1e-2

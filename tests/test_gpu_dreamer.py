@@ -214,3 +214,43 @@ def test_bf16_update_reaches_every_tensor_the_fp32_update_reaches():
       off.append((k, cos))
   assert not missing, missing
   assert len(off) <= len(f.specs) // 10, off     # bf16 noise may turn a few tiny tensors
+
+
+def test_tc_convolutions_track_library_convolutions_at_size200m_widths():
+  """The tcgen05 convolution path (bf16, 128..256 channels: only reached at the benchmark's
+  model width) against the same update with library convolutions: same loss to bf16 accuracy,
+  and every conv kernel receives a gradient of the same direction."""
+  from embodied_b200.dreamerv3 import config as C
+  obs = {'image': elements.Space(np.uint8, (64, 64, 3)), 'reward': elements.Space(np.float32),
+         'is_first': elements.Space(bool), 'is_last': elements.Space(bool),
+         'is_terminal': elements.Space(bool)}
+  act = {'reset': elements.Space(bool), 'action': elements.Space(np.int32, (), 0, 5)}
+  agents = []
+  for tc in (True, False):
+    cfg = C.make('size12m', depth=64, compute_dtype='bfloat16', graph='off', tc_conv=tc, seed=3)
+    agents.append(dreamerv3.Agent(obs, act, cfg))
+  assert agents[0].model.tc_conv and not agents[1].model.tc_conv
+  cfg = agents[0].cfg
+  B, T = 2, 4
+  g = torch.Generator().manual_seed(0)
+  L = T + cfg.replay_context
+  data = cases.to_device({
+      'image': torch.randint(0, 256, (B, L, 64, 64, 3), generator=g, dtype=torch.uint8),
+      'reward': torch.randn(B, L, generator=g),
+      'is_first': torch.zeros(B, L, dtype=torch.bool), 'is_last': torch.zeros(B, L, dtype=torch.bool),
+      'is_terminal': torch.zeros(B, L, dtype=torch.bool),
+      'action': torch.randint(0, 5, (B, L), generator=g, dtype=torch.int32),
+      'dyn/deter': torch.zeros(B, L, cfg.deter), 'dyn/stoch': torch.zeros(B, L, cfg.stoch, cfg.classes),
+      'stepid': torch.zeros(B, L, 20, dtype=torch.uint8), 'consec': torch.zeros(B, L, dtype=torch.int32)})
+  noise = agents[0].make_noise(B, T)
+  losses = []
+  for a in agents:
+    a.opt.launch = lambda: torch.zeros(())          # keep the raw gradients in the buffer
+    _, _, mets = a.train(a.init_train(B), data, {k: v.clone() for k, v in noise.items()})
+    losses.append(float(mets['loss']))
+  assert abs(losses[0] - losses[1]) <= 2e-2 * abs(losses[1]), losses
+  for k in agents[0].store.specs:
+    if '/cnn' in k or '/conv' in k:
+      ga, gb = agents[0].store.view('grad', k).double(), agents[1].store.view('grad', k).double()
+      cos = float((ga * gb).sum() / (ga.norm() * gb.norm() + 1e-30))
+      assert cos > 0.98, (k, cos)
