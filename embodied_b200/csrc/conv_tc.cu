@@ -43,7 +43,7 @@ struct ConvShape {
   int cout;
   int taps;            // k * k
   int ksize;           // k
-  int act;             // epilogue: 0 = store, (reserved)
+  int msub;            // 128-pixel sub-tiles per tile that share one weight tile (2 when cout <= 128)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -140,14 +140,13 @@ __device__ __forceinline__ uint32_t pack_bf16(uint32_t lo, uint32_t hi) {
   return *reinterpret_cast<const uint32_t*>(&v);
 }
 
+template <int MSUB>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_w,
                __nv_bfloat16* __restrict__ out, const float* __restrict__ bias, const ConvShape s) {
   extern __shared__ unsigned char smem_raw[];
   // 128-byte swizzle atoms are anchored on 1024-byte boundaries of the shared window
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  unsigned char* sA = smem;
-  unsigned char* sB = smem + kStages * kABytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
   uint64_t* full = bars;                 // [kStages]  TMA -> MMA
   uint64_t* empty = bars + kStages;      // [kStages]  MMA -> TMA
@@ -174,7 +173,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int iters = s.taps * s.kblocks;
-  const uint32_t stage_tx = (uint32_t)kABytes + (uint32_t)s.cout * 128u;
+  // stage = [msub x 16 KiB of A | weight tile]: 48 KiB either way (cout <= 128 with two sub-tiles)
+  constexpr uint32_t a_bytes = (uint32_t)MSUB * kABytes;
+  const uint32_t stage_tx = a_bytes + (uint32_t)s.cout * 128u;
   const int half = s.ksize >> 1;
 
   if (warp == 0) {
@@ -183,17 +184,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < s.tiles; tile += gridDim.x) {
-        const int pix0 = tile * 128;
-        const int n0 = pix0 / s.hw, h0 = (pix0 - n0 * s.hw) / s.w;
+        int n0[MSUB], h0[MSUB];
+#pragma unroll
+        for (int sub = 0; sub < MSUB; ++sub) {
+          const int pix0 = (tile * MSUB + sub) * 128;
+          n0[sub] = pix0 / s.hw;
+          h0[sub] = (pix0 - n0[sub] * s.hw) / s.w;
+        }
+        int ky = 0, kx = 0;
         for (int tap = 0; tap < s.taps; ++tap) {
-          const int ky = tap / s.ksize, kx = tap - ky * s.ksize;
           for (int kb = 0; kb < s.kblocks; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1u);
             mbar_expect_tx(&full[stage], stage_tx);
-            tma_load_4d(sA + stage * kABytes, &map_in, kb * 64, kx - half, h0 + ky - half, n0, &full[stage]);
-            tma_load_3d(sB + stage * kBBytes, &map_w, kb * 64, 0, tap, &full[stage]);
+            unsigned char* base = smem + stage * kStageBytes;
+#pragma unroll
+            for (int sub = 0; sub < MSUB; ++sub)
+              tma_load_4d(base + sub * kABytes, &map_in, kb * 64, kx - half, h0[sub] + ky - half, n0[sub],
+                          &full[stage]);
+            tma_load_3d(base + a_bytes, &map_w, kb * 64, 0, tap, &full[stage]);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
           }
+          if (++kx == s.ksize) { kx = 0; ++ky; }
         }
       }
     }
@@ -212,11 +223,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint64_t ad = umma_desc_sw128(smem_u32(sA + stage * kABytes));
-          const uint64_t bd = umma_desc_sw128(smem_u32(sB + stage * kBBytes));
+          const uint32_t base = smem_u32(smem + stage * kStageBytes);
+          const uint64_t bd = umma_desc_sw128(base + a_bytes);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)     // 4 x (K = 16): +32 bytes inside the swizzle atom
-            umma_bf16(d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+          for (int sub = 0; sub < MSUB; ++sub) {
+            const uint64_t ad = umma_desc_sw128(base + sub * kABytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // 4 x (K = 16): +32 bytes inside the swizzle atom
+              umma_bf16(d + (uint32_t)sub * 128u, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                        (it | k) ? 1u : 0u);
+          }
           umma_commit(&empty[stage]);      // the stage is free once these MMAs have read it
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -233,27 +249,181 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
     for (int tile = blockIdx.x; tile < s.tiles; tile += gridDim.x) {
       mbar_wait(&tfull[acc], accphase);
       tc_fence_after();
-      const int m = q * 32 + lane;
-      __nv_bfloat16* orow = out + ((size_t)tile * 128 + m) * s.cout;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u;
-      for (int c0 = 0; c0 < s.cout; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + c0 + j));
+      for (int sub = 0; sub < MSUB; ++sub) {
+        const int m = q * 32 + lane;
+        __nv_bfloat16* orow = out + ((size_t)(tile * MSUB + sub) * 128 + m) * s.cout;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)sub * 128u;
+        for (int c0 = 0; c0 < s.cout; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + c0 + j));
+          }
+          uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
         }
-        uint4* dst = reinterpret_cast<uint4*>(orow + c0);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                              pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
       acc ^= 1;
       if (acc == 0) accphase ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 :: "r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---- weight gradient ------------------------------------------------------------
+// dW[tap][ci][co] = sum over pixels p of in[p + shift(tap)][ci] * gy[p][co]: per tap a GEMM whose
+// reduction axis is the PIXEL axis.  Both operands are read in their natural NHWC layout by the same
+// TMA boxes as above ([64 pixels][64 channels], 128-byte swizzle) and enter the tensor core as
+// MN-major operands (cute Layout_MN_SW128_Atom: the 64-channel slabs LBO bytes apart, 8-pixel
+// groups SBO = 1024 bytes apart).  D = [M = 128 or 256 channels of one tensor][N <= 256 channels of
+// the other], fp32 in tensor memory for the CTA's whole pixel range; red.global.add at the end.
+// CTA = (tap, split): the 25 taps of a split walk the same pixels at the same time, so every
+// activation tile comes from HBM once and is then served by L2 to the other 24 taps.
+constexpr int kWSlab = 64 * 128;                 // one TMA box: 64 pixels x 64 channels bf16
+constexpr int kWRingSlabs = 24;                  // 192 KiB ring: 24 / SLABS stages of SLABS = (M + N) / 64 slabs
+// (Measured, r02: an L2 look-ahead by the centre tap of every split -- cp.async.bulk.prefetch.tensor
+//  12 chunks ahead -- and a ring of 4-6 smaller stages made every layer 1.7-2x SLOWER; the ring is
+//  bound by bytes in flight per SM, not by HBM latency of a leader.)
+
+struct WgradShape {
+  int chunks;          // 64-pixel chunks in all
+  int splits;          // CTAs per tap
+  int hw, w;           // H*W, W
+  int m, n;            // channels on the M / N side (m in {128, 256})
+  int ksize;
+  int m_shifted;       // 1: the M-side tensor is the convolution input (shifted per tap)
+  int h, ht, nt;       // image height; rows / images per 64-pixel chunk
+};
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // between 64-element slabs along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;                   // between 8-row groups along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(dst), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)), "f"(__uint_as_float(c)),
+                  "f"(__uint_as_float(d)) : "memory");
+}
+
+template <int SLABS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n,
+                     float* __restrict__ dw, const WgradShape s) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kWStages = kWRingSlabs / SLABS;
+  constexpr int kWStageBytes = SLABS * kWSlab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWRingSlabs * kWSlab);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWStages;
+  uint64_t* done = bars + 2 * kWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_m) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_n) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = s.ksize * s.ksize, half = s.ksize >> 1;
+  const int tap = blockIdx.x % taps, split = blockIdx.x / taps;
+  const int ky = tap / s.ksize, kx = tap - ky * s.ksize;
+  const int c_begin = (int)((long long)s.chunks * split / s.splits);
+  const int c_end = (int)((long long)s.chunks * (split + 1) / s.splits);
+  const int mslabs = s.m / 64, nslabs = s.n / 64, mtiles = s.m / 128;
+  const uint32_t stage_tx = (uint32_t)(mslabs + nslabs) * kWSlab;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      // (no divisions inside the loop: the producer's issue latency is on the critical path)
+      int n0 = c_begin * 64 / s.hw, h0 = (c_begin * 64 - n0 * s.hw) / s.w;
+      const int dmh = s.m_shifted ? ky - half : 0, mw = s.m_shifted ? kx - half : 0;
+      const int dnh = s.m_shifted ? 0 : ky - half, nw = s.m_shifted ? 0 : kx - half;
+      for (int c = c_begin; c < c_end; ++c) {
+        const int mh = h0 + dmh, nh = h0 + dnh;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_expect_tx(&full[stage], stage_tx);
+        unsigned char* base = smem + stage * kWStageBytes;
+        for (int j = 0; j < mslabs; ++j) tma_load_4d(base + j * kWSlab, &map_m, j * 64, mw, mh, n0, &full[stage]);
+        for (int j = 0; j < nslabs; ++j)
+          tma_load_4d(base + (mslabs + j) * kWSlab, &map_n, j * 64, nw, nh, n0, &full[stage]);
+        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+        h0 += s.ht;
+        if (h0 >= s.h) { h0 = 0; n0 += s.nt; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, s.n) | (1u << 15) | (1u << 16);   // both MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + stage * kWStageBytes);
+        for (int mt = 0; mt < mtiles; ++mt) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {     // K = 16 pixels = two 8-row groups = 2048 bytes
+            const uint64_t ad = umma_desc_mn_sw128(base + mt * 2 * kWSlab + k * 2048, kWSlab);
+            const uint64_t bd = umma_desc_mn_sw128(base + mslabs * kWSlab + k * 2048, kWSlab);
+            umma_bf16(tmem_base + (uint32_t)mt * 256u, ad, bd, idesc, (c > c_begin || k) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else if (c_begin < c_end) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    for (int mt = 0; mt < mtiles; ++mt) {
+      const int m = mt * 128 + q * 32 + lane;
+      float* drow = dw + ((size_t)tap * s.m + m) * s.n;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)mt * 256u;
+      for (int c0 = 0; c0 < s.n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red_add_v4(drow + c0 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
     }
   }
 
@@ -341,25 +511,112 @@ extern "C" int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const f
     if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled(weights) failed with %d", who, (int)r);
   }
   ConvShape s;
-  s.tiles = (int)(n * h * w / 128);
+  s.msub = (cout <= 128 && (n * h * w) % 256 == 0) ? 2 : 1;
+  s.tiles = (int)(n * h * w / (128 * s.msub));
   s.hw = h * w;
   s.w = w;
   s.kblocks = cin / 64;
   s.cout = cout;
   s.taps = ksize * ksize;
   s.ksize = ksize;
-  s.act = 0;
   const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute((const void*)conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute((const void*)conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute((const void*)conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess)
       return emb::fail_cuda(who);
     attr_set = true;
   }
   const int grid = s.tiles < g_sms ? s.tiles : g_sms;
-  conv_tc_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-      map_in, map_w, reinterpret_cast<__nv_bfloat16*>(out), bias, s);
+  if (s.msub == 2)
+    conv_tc_kernel<2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+        map_in, map_w, reinterpret_cast<__nv_bfloat16*>(out), bias, s);
+  else
+    conv_tc_kernel<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
+        map_in, map_w, reinterpret_cast<__nv_bfloat16*>(out), bias, s);
+  if (cudaGetLastError() != cudaSuccess) return emb::fail_cuda(who);
+  emb::count_launch();
+  return 0;
+}
+
+// dw[tap][m][n] (fp32, accumulated into) for the SAME convolution whose input is `x` (n, h, w, cin)
+// and whose output gradient is `gy` (n, h, w, cout).  m_is_in = 1: m = cin, n = cout (dw is HWIO);
+// 0: m = cout, n = cin.
+extern "C" int emb_conv5x5_wgrad_tc(const void* x, const void* gy, float* dw, int64_t n, int32_t h,
+                                    int32_t w, int32_t cin, int32_t cout, int32_t ksize,
+                                    int32_t m_is_in, void* stream) {
+  const char* who = "emb_conv5x5_wgrad_tc";
+  if (n <= 0) return 0;
+  if (!x || !gy || !dw) return emb::fail(-1, "%s: null pointer", who);
+  if (ksize != 5 && ksize != 3 && ksize != 1) return emb::fail(-1, "%s: kernel size %d not in {1, 3, 5}", who, ksize);
+  const int m = m_is_in ? cin : cout, nn = m_is_in ? cout : cin;
+  if (m != 128 && m != 256) return emb::fail(-1, "%s: the M side has %d channels, need 128 or 256", who, m);
+  if (nn % 64 || nn < 64 || nn > 256) return emb::fail(-1, "%s: the N side has %d channels, need a multiple of 64 <= 256", who, nn);
+  if (w > 64 || 64 % w) return emb::fail(-1, "%s: width %d must divide 64", who, w);
+  int ht, nt;
+  if (h * w >= 64) {
+    ht = 64 / w; nt = 1;
+    if (h % ht) return emb::fail(-1, "%s: height %d must be a multiple of %d rows per chunk", who, h, ht);
+  } else {
+    ht = h; nt = 64 / (h * w);
+    if (64 % (h * w) || n % nt) return emb::fail(-1, "%s: %dx%d images must pack into 64-pixel chunks", who, h, w);
+  }
+  if (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)dw) & 15)
+    return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return emb::fail(-1, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
+  if (g_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return emb::fail_cuda(who);
+  }
+  CUtensorMap maps[2];
+  const void* ptrs[2] = {m_is_in ? x : gy, m_is_in ? gy : x};
+  const int chans[2] = {m, nn};
+  for (int i = 0; i < 2; ++i) {
+    const cuuint64_t c = (cuuint64_t)chans[i];
+    const cuuint64_t dims[4] = {c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[3] = {c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)w, (cuuint32_t)ht, (cuuint32_t)nt};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptrs[i]), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled failed with %d", who, (int)r);
+  }
+  WgradShape s;
+  s.chunks = (int)(n * h * w / 64);
+  const int taps = ksize * ksize;
+  s.splits = g_sms / taps > 0 ? g_sms / taps : 1;
+  if (s.splits > s.chunks) s.splits = s.chunks;
+  s.hw = h * w;
+  s.w = w;
+  s.m = m;
+  s.n = nn;
+  s.ksize = ksize;
+  s.m_shifted = m_is_in ? 1 : 0;
+  s.h = h;
+  s.ht = ht;
+  s.nt = nt;
+  const size_t smem = (size_t)kWRingSlabs * kWSlab + 1024 + 256;
+  const void* fn = nullptr;
+  switch ((m + nn) / 64) {
+    case 3: fn = (const void*)conv_wgrad_tc_kernel<3>; break;
+    case 4: fn = (const void*)conv_wgrad_tc_kernel<4>; break;
+    case 5: fn = (const void*)conv_wgrad_tc_kernel<5>; break;
+    case 6: fn = (const void*)conv_wgrad_tc_kernel<6>; break;
+    case 7: fn = (const void*)conv_wgrad_tc_kernel<7>; break;
+    default: fn = (const void*)conv_wgrad_tc_kernel<8>; break;
+  }
+  if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return emb::fail_cuda(who);
+  void* params[] = {&maps[0], &maps[1], &dw, &s};
+  if (cudaLaunchKernel(fn, dim3(taps * s.splits), dim3(kThreads), params, smem, (cudaStream_t)stream) !=
+      cudaSuccess)
+    return emb::fail_cuda(who);
   if (cudaGetLastError() != cudaSuccess) return emb::fail_cuda(who);
   emb::count_launch();
   return 0;

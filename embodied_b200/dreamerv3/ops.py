@@ -464,10 +464,41 @@ class ConvTC(torch.autograd.Function):
     return gx, gw
 
 
+def conv_wgrad_tc_supported(x, gy, k):
+  if not (x.is_cuda and x.dtype == gy.dtype == torch.bfloat16 and x.dim() == 4 and k in (1, 3, 5)):
+    return False
+  n, h, w, cin = x.shape
+  cout = gy.shape[-1]
+  if not ((cin in (128, 256) and cout % 64 == 0 and 64 <= cout <= 256) or
+          (cout in (128, 256) and cin % 64 == 0 and 64 <= cin <= 256)):
+    return False
+  if w > 64 or 64 % w:
+    return False
+  if h * w >= 64:
+    return h % (64 // w) == 0
+  return 64 % (h * w) == 0 and n % (64 // (h * w)) == 0
+
+
 def conv_wgrad(x, gy, k):
-  """dL/dw (k, k, Cin, Cout) of a SAME convolution from x (N, H, W, Cin) and
-  gy (N, H, W, Cout), both NHWC."""
+  """dL/dw (k, k, Cin, Cout), fp32, of a SAME convolution from x (N, H, W, Cin) and
+  gy (N, H, W, Cout), both NHWC: emb_conv5x5_wgrad_tc where the shape fits its tiles."""
   cin, cout = x.shape[-1], gy.shape[-1]
+  if conv_wgrad_tc_supported(x, gy, k):
+    lib = _lib.load()
+    if not getattr(lib, '_conv_wgrad_bound', False):
+      lib.emb_conv5x5_wgrad_tc.argtypes = [_vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp]
+      lib.emb_conv5x5_wgrad_tc.restype = ctypes.c_int
+      lib._conv_wgrad_bound = True
+    x, gy = x.contiguous(), gy.contiguous()
+    n, h, w, _ = x.shape
+    m_is_in = cin in (128, 256)
+    dw = torch.zeros((k * k, cin, cout) if m_is_in else (k * k, cout, cin), dtype=f32, device=x.device)
+    stream = torch.cuda.current_stream(x.device).cuda_stream
+    _lib.check(lib.emb_conv5x5_wgrad_tc(
+        x.data_ptr(), gy.data_ptr(), dw.data_ptr(), n, h, w, cin, cout, k, int(m_is_in), stream))
+    if not m_is_in:
+      dw = dw.transpose(1, 2)
+    return dw.reshape(k, k, cin, cout)
   g = torch.nn.grad.conv2d_weight(
       x.permute(0, 3, 1, 2), (cout, cin, k, k), gy.permute(0, 3, 1, 2), padding=k // 2)
   return g.permute(2, 3, 1, 0)

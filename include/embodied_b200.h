@@ -409,6 +409,16 @@ int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const float* bias,
                         int64_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize,
                         void* stream);
 
+/* Weight gradient of the same convolutions: dw[tap][m][n] += sum over pixels of
+ * x[p + (ky-k/2, kx-k/2)][ci] * gy[p][co] (fp32, red.global.add: dw must hold zeros or the running
+ * gradient).  The reduction axis is the pixel axis, so both NHWC tensors feed the tcgen05 MMAs
+ * as MN-major operands straight from their TMA tiles.  m_is_in = 1: m = cin, n = cout (dw is the
+ * HWIO gradient); 0: m = cout, n = cin (dw = its transpose per tap).  The M side must have 128 or
+ * 256 channels, the N side a multiple of 64 <= 256; 64 % w == 0 and images tile into 64-pixel runs
+ * of whole rows. */
+int emb_conv5x5_wgrad_tc(const void* x, const void* gy, float* dw, int64_t n, int32_t h, int32_t w,
+                         int32_t cin, int32_t cout, int32_t ksize, int32_t m_is_in, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -87,3 +87,25 @@ def test_autograd_function_matches_library_convolution():
   assert rel2(res[0][0], res[1][0]) < 1e-2
   assert rel2(res[0][1], res[1][1]) < 1e-2
   assert rel2(res[0][2], res[1][2]) < 1e-2
+
+
+WSHAPES = [  # n, h, w, cin, cout, k
+    (8, 32, 32, 128, 192, 5), (8, 16, 16, 192, 256, 5), (8, 8, 8, 256, 256, 5),
+    (8, 16, 16, 256, 192, 5), (8, 32, 32, 192, 128, 5), (4, 16, 16, 128, 64, 3), (300, 8, 8, 128, 128, 5),
+]
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout,k', WSHAPES)
+def test_weight_gradient_matches_fp32(n, h, w, cin, cout, k):
+  """emb_conv5x5_wgrad_tc: exact bf16 products accumulated in fp32 (tensor memory, then
+  red.global.add across the pixel splits) against fp32 autograd of the same operands."""
+  g = torch.Generator(device='cuda').manual_seed(n + cin + cout)
+  x = torch.randn((n, h, w, cin), generator=g, device='cuda').to(torch.bfloat16)
+  gy = torch.randn((n, h, w, cout), generator=g, device='cuda').to(torch.bfloat16)
+  assert ops.conv_wgrad_tc_supported(x, gy, k)
+  dw = ops.conv_wgrad(x, gy, k)
+  assert dw.shape == (k, k, cin, cout) and dw.dtype == torch.float32
+  wt = torch.zeros((k, k, cin, cout), device='cuda', requires_grad=True)
+  (reference(x, wt) * gy.float()).sum().backward()
+  err = float((dw - wt.grad).abs().max())
+  assert err <= 1e-4 * float(wt.grad.abs().max()), err

@@ -11,6 +11,7 @@ import torch.nn.functional as F
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 from embodied_b200.dreamerv3 import ops  # noqa: E402
 
+WG = True
 LAYERS = [('enc/cnn1', 32, 128, 192), ('enc/cnn2', 16, 192, 256), ('enc/cnn3', 8, 256, 256),
           ('dec/conv2', 8, 256, 256), ('dec/conv1', 16, 256, 192), ('dec/conv0', 32, 192, 128)]
 
@@ -41,9 +42,15 @@ def main():
     t_tc = timeit(lambda: ops.conv_tc(x, wp), flush)
     t_lib = timeit(lambda: F.conv2d(xc, wc, padding=2), flush)
     flops = 2.0 * n * hw * hw * 25 * cin * cout
+    gy = torch.randn((n, hw, hw, cout), device='cuda').to(torch.bfloat16)
+    gyc = gy.permute(0, 3, 1, 2)
+    t_wg = timeit(lambda: ops.conv_wgrad(x, gy, 5), flush)
+    t_wg_lib = timeit(lambda: torch.nn.grad.conv2d_weight(xc, (cout, cin, 5, 5), gyc, padding=2), flush)
     print(json.dumps({'layer': name, 'n': n, 'hw': hw, 'cin': cin, 'cout': cout,
                       'tc_ms': t_tc, 'tc_tflops': flops / t_tc / 1e9,
-                      'cudnn_ms': t_lib, 'cudnn_tflops': flops / t_lib / 1e9}))
+                      'cudnn_ms': t_lib, 'cudnn_tflops': flops / t_lib / 1e9,
+                      'wgrad_tc_ms': t_wg, 'wgrad_tc_tflops': flops / t_wg / 1e9,
+                      'wgrad_cudnn_ms': t_wg_lib, 'wgrad_cudnn_tflops': flops / t_wg_lib / 1e9}))
 
 
 if __name__ == '__main__':
