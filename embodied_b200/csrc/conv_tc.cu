@@ -44,6 +44,10 @@ struct ConvShape {
   int taps;            // k * k
   int ksize;           // k
   int msub;            // 128-pixel sub-tiles per tile that share one weight tile (2 when cout <= 128)
+  int groups;          // 1, or 4: K also runs over the 2x2 phases of an input stored on the doubled grid
+  int cin;             // channels per phase
+  int out_up;          // 1, or 2: the output is phase (out_py, out_px) of a tensor on the doubled grid
+  int out_py, out_px;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -77,6 +81,17 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, i
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
       "[%0], [%1, {%2, %3, %4, %5}], [%6];"
       :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+// Activations are always described as 5-D tensors {channels', x, phase, y, image}: a plain NHWC tensor
+// has a phase axis of length 1; the four 2x2 phases of a tensor stored on the doubled grid
+// (n, 2h, 2w, c) are {channels' = 2c with px*c as the channel offset, x (stride 2c), py, y, n}.
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            int c3, int c4, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      :: "r"(smem_u32(dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2,
@@ -172,7 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int iters = s.taps * s.kblocks;
+  const int iters = s.groups * s.taps * s.kblocks;
   // stage = [msub x 16 KiB of A | weight tile]: 48 KiB either way (cout <= 128 with two sub-tiles)
   constexpr uint32_t a_bytes = (uint32_t)MSUB * kABytes;
   const uint32_t stage_tx = a_bytes + (uint32_t)s.cout * 128u;
@@ -191,20 +206,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
           n0[sub] = pix0 / s.hw;
           h0[sub] = (pix0 - n0[sub] * s.hw) / s.w;
         }
-        int ky = 0, kx = 0;
-        for (int tap = 0; tap < s.taps; ++tap) {
-          for (int kb = 0; kb < s.kblocks; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1u);
-            mbar_expect_tx(&full[stage], stage_tx);
-            unsigned char* base = smem + stage * kStageBytes;
+        for (int g = 0; g < s.groups; ++g) {
+          const int gpy = g >> 1, gch = (g & 1) * s.cin;
+          int ky = 0, kx = 0;
+          for (int tap = 0; tap < s.taps; ++tap) {
+            for (int kb = 0; kb < s.kblocks; ++kb) {
+              mbar_wait(&empty[stage], phase ^ 1u);
+              mbar_expect_tx(&full[stage], stage_tx);
+              unsigned char* base = smem + stage * kStageBytes;
 #pragma unroll
-            for (int sub = 0; sub < MSUB; ++sub)
-              tma_load_4d(base + sub * kABytes, &map_in, kb * 64, kx - half, h0[sub] + ky - half, n0[sub],
-                          &full[stage]);
-            tma_load_3d(base + a_bytes, &map_w, kb * 64, 0, tap, &full[stage]);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+              for (int sub = 0; sub < MSUB; ++sub)
+                tma_load_5d(base + sub * kABytes, &map_in, gch + kb * 64, kx - half, gpy, h0[sub] + ky - half,
+                            n0[sub], &full[stage]);
+              tma_load_3d(base + a_bytes, &map_w, kb * 64, 0, g * s.taps + tap, &full[stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+            if (++kx == s.ksize) { kx = 0; ++ky; }
           }
-          if (++kx == s.ksize) { kx = 0; ++ky; }
         }
       }
     }
@@ -252,7 +270,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
 #pragma unroll
       for (int sub = 0; sub < MSUB; ++sub) {
         const int m = q * 32 + lane;
-        __nv_bfloat16* orow = out + ((size_t)(tile * MSUB + sub) * 128 + m) * s.cout;
+        size_t opix = (size_t)(tile * MSUB + sub) * 128 + m;
+        if (s.out_up == 2) {                 // pixel (n, y, x) -> (n, 2y + py, 2x + px) of the doubled grid
+          const int pn = (int)(opix / s.hw), pr = (int)(opix - (size_t)pn * s.hw);
+          const int py = pr / s.w, px = pr - py * s.w;
+          opix = ((size_t)pn * 2 * (s.hw / s.w) + 2 * py + s.out_py) * (2 * s.w) + 2 * px + s.out_px;
+        }
+        __nv_bfloat16* orow = out + opix * s.cout;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 256u + (uint32_t)sub * 128u;
         for (int c0 = 0; c0 < s.cout; c0 += 32) {
           uint32_t v[32];
@@ -308,6 +332,7 @@ struct WgradShape {
   int ksize;
   int m_shifted;       // 1: the M-side tensor is the convolution input (shifted per tap)
   int h, ht, nt;       // image height; rows / images per 64-pixel chunk
+  int gy_py, gy_ch;    // phase row and channel offset (px * cout) of gy on a doubled grid, else 0
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -374,14 +399,18 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_con
       int n0 = c_begin * 64 / s.hw, h0 = (c_begin * 64 - n0 * s.hw) / s.w;
       const int dmh = s.m_shifted ? ky - half : 0, mw = s.m_shifted ? kx - half : 0;
       const int dnh = s.m_shifted ? 0 : ky - half, nw = s.m_shifted ? 0 : kx - half;
+      // the unshifted side is gy: possibly one phase of a tensor on the doubled grid
+      const int mpy = s.m_shifted ? 0 : s.gy_py, mch = s.m_shifted ? 0 : s.gy_ch;
+      const int npy = s.m_shifted ? s.gy_py : 0, nch = s.m_shifted ? s.gy_ch : 0;
       for (int c = c_begin; c < c_end; ++c) {
         const int mh = h0 + dmh, nh = h0 + dnh;
         mbar_wait(&empty[stage], phase ^ 1u);
         mbar_expect_tx(&full[stage], stage_tx);
         unsigned char* base = smem + stage * kWStageBytes;
-        for (int j = 0; j < mslabs; ++j) tma_load_4d(base + j * kWSlab, &map_m, j * 64, mw, mh, n0, &full[stage]);
+        for (int j = 0; j < mslabs; ++j)
+          tma_load_5d(base + j * kWSlab, &map_m, mch + j * 64, mw, mpy, mh, n0, &full[stage]);
         for (int j = 0; j < nslabs; ++j)
-          tma_load_4d(base + (mslabs + j) * kWSlab, &map_n, j * 64, nw, nh, n0, &full[stage]);
+          tma_load_5d(base + (mslabs + j) * kWSlab, &map_n, nch + j * 64, nw, npy, nh, n0, &full[stage]);
         if (++stage == kWStages) { stage = 0; phase ^= 1u; }
         h0 += s.ht;
         if (h0 >= s.h) { h0 = 0; n0 += s.nt; }
@@ -458,56 +487,81 @@ int g_sms = 0;
 
 }  // namespace
 
-extern "C" int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const float* bias, void* out,
-                                   int64_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
-                                   int32_t ksize, void* stream) {
-  const char* who = "emb_conv5x5_nhwc_tc";
-  if (n <= 0) return 0;
-  if (!in || !w_packed || !out) return emb::fail(-1, "%s: null pointer", who);
-  if (ksize != 5 && ksize != 3 && ksize != 1) return emb::fail(-1, "%s: kernel size %d not in {1, 3, 5}", who, ksize);
-  if (cin % 64) return emb::fail(-1, "%s: cin=%d must be a multiple of 64 (128-byte swizzled K blocks)", who, cin);
-  if (cout % 32 || cout < 32 || cout > 256)
-    return emb::fail(-1, "%s: cout=%d must be a multiple of 32 in [32, 256]", who, cout);
-  // a tile = 128 consecutive pixels = whole rows of one image, or whole images
-  int wt = w, ht, nt;
-  if (w > 128 || 128 % w) return emb::fail(-1, "%s: width %d must divide 128", who, w);
-  if (h * w >= 128) {
-    ht = 128 / w; nt = 1;
-    if (h % ht) return emb::fail(-1, "%s: height %d must be a multiple of %d rows per tile", who, h, ht);
-  } else {
-    ht = h; nt = 128 / (h * w);
-    if (128 % (h * w) || n % nt) return emb::fail(-1, "%s: %dx%d images must pack into 128-pixel tiles", who, h, w);
-  }
-  if ((n * h * w) % 128) return emb::fail(-1, "%s: n*h*w must be a multiple of 128", who);
-  if (((uintptr_t)in | (uintptr_t)w_packed | (uintptr_t)out) & 15)
-    return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
+// 5-D tensor map of an activation tensor with `c` channels whose GEMM pixels live on the (n, h, w)
+// grid: up = 1 plain NHWC; up = 2 the tensor is stored on the doubled grid (n, 2h, 2w, c) and the
+// phase (py, px) is selected by coordinates {px*c + channel, x, py, y, n}.
+static int encode_act(CUtensorMap* map, const void* ptr, int64_t n, int h, int w, int c, int up, int box_w,
+                      int box_h, int box_n, const char* who) {
   EncodeTiledFn enc = encode_fn();
   if (!enc) return emb::fail(-1, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
+  const cuuint64_t u = (cuuint64_t)up, cc = (cuuint64_t)c;
+  const cuuint64_t dims[5] = {u * cc, (cuuint64_t)w, u, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t sx = u * cc * 2, sp = sx * w, sy = sp * u, sn = sy * h;
+  const cuuint64_t strides[4] = {sx, sp, sy, sn};
+  const cuuint32_t box[5] = {64, (cuuint32_t)box_w, 1, (cuuint32_t)box_h, (cuuint32_t)box_n};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box,
+                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled(activations) failed with %d", who, (int)r);
+  return 0;
+}
+
+static int sm_count(const char* who) {
   if (g_sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       return emb::fail_cuda(who);
   }
-  CUtensorMap map_in, map_w;
-  {
-    const cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-    const cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)w * cin * 2, (cuuint64_t)h * w * cin * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)wt, (cuuint32_t)ht, (cuuint32_t)nt};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(&map_in, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides,
-                           box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled(input) failed with %d", who, (int)r);
+  return 0;
+}
+
+// `px` consecutive pixels = whole rows of one image or whole images: box (w, rows, images)
+static int pixel_box(int64_t n, int h, int w, int px, int* ht, int* nt, const char* who) {
+  if (w > px || px % w) return emb::fail(-1, "%s: width %d must divide %d", who, w, px);
+  if (h * w >= px) {
+    *ht = px / w; *nt = 1;
+    if (h % *ht) return emb::fail(-1, "%s: height %d must be a multiple of %d rows per tile", who, h, *ht);
+  } else {
+    *ht = h; *nt = px / (h * w);
+    if (px % (h * w) || n % *nt) return emb::fail(-1, "%s: %dx%d images must pack into %d-pixel tiles", who, h, w, px);
   }
+  return 0;
+}
+
+extern "C" int emb_conv_nhwc_tc(const emb_conv_tc_args* a, void* stream) {
+  const char* who = "emb_conv_nhwc_tc";
+  if (!a) return emb::fail(-1, "%s: null args", who);
+  const int64_t n = a->n;
+  const int h = a->h, w = a->w, cin = a->cin, cout = a->cout, ksize = a->ksize;
+  if (n <= 0) return 0;
+  if (!a->in || !a->w_packed || !a->out) return emb::fail(-1, "%s: null pointer", who);
+  if (ksize != 5 && ksize != 3 && ksize != 1) return emb::fail(-1, "%s: kernel size %d not in {1, 3, 5}", who, ksize);
+  if (cin % 64) return emb::fail(-1, "%s: cin=%d must be a multiple of 64 (128-byte swizzled K blocks)", who, cin);
+  if (cout % 32 || cout < 32 || cout > 256)
+    return emb::fail(-1, "%s: cout=%d must be a multiple of 32 in [32, 256]", who, cout);
+  if ((a->in_up != 1 && a->in_up != 2) || (a->out_up != 1 && a->out_up != 2) || a->out_phase < 0 ||
+      a->out_phase > 3)
+    return emb::fail(-1, "%s: in_up / out_up must be 1 or 2, out_phase in [0, 4)", who);
+  int ht, nt;
+  if (int e = pixel_box(n, h, w, 128, &ht, &nt, who)) return e;
+  if ((n * h * w) % 128) return emb::fail(-1, "%s: n*h*w must be a multiple of 128", who);
+  if (((uintptr_t)a->in | (uintptr_t)a->w_packed | (uintptr_t)a->out) & 15)
+    return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
+  if (int e = sm_count(who)) return e;
+  const int groups = a->in_up == 2 ? 4 : 1;
+  CUtensorMap map_in, map_w;
+  if (int e = encode_act(&map_in, a->in, n, h, w, cin, a->in_up, w, ht, nt, who)) return e;
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)(ksize * ksize)};
+    const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)cout, (cuuint64_t)(groups * ksize * ksize)};
     const cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)cout * cin * 2};
     const cuuint32_t box[3] = {64, (cuuint32_t)cout, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w_packed), dims,
-                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = encode_fn()(&map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(a->w_packed),
+                                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled(weights) failed with %d", who, (int)r);
   }
   ConvShape s;
@@ -519,6 +573,11 @@ extern "C" int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const f
   s.cout = cout;
   s.taps = ksize * ksize;
   s.ksize = ksize;
+  s.groups = groups;
+  s.cin = cin;
+  s.out_up = a->out_up;
+  s.out_py = a->out_phase >> 1;
+  s.out_px = a->out_phase & 1;
   const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -530,63 +589,51 @@ extern "C" int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const f
     attr_set = true;
   }
   const int grid = s.tiles < g_sms ? s.tiles : g_sms;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(a->out);
   if (s.msub == 2)
-    conv_tc_kernel<2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        map_in, map_w, reinterpret_cast<__nv_bfloat16*>(out), bias, s);
+    conv_tc_kernel<2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_in, map_w, out, a->bias, s);
   else
-    conv_tc_kernel<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(
-        map_in, map_w, reinterpret_cast<__nv_bfloat16*>(out), bias, s);
+    conv_tc_kernel<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(map_in, map_w, out, a->bias, s);
   if (cudaGetLastError() != cudaSuccess) return emb::fail_cuda(who);
   emb::count_launch();
   return 0;
 }
 
+extern "C" int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const float* bias, void* out,
+                                   int64_t n, int32_t h, int32_t w, int32_t cin, int32_t cout,
+                                   int32_t ksize, void* stream) {
+  emb_conv_tc_args a;
+  a.in = in; a.w_packed = w_packed; a.bias = bias; a.out = out;
+  a.n = n; a.h = h; a.w = w; a.cin = cin; a.cout = cout; a.ksize = ksize;
+  a.in_up = 1; a.out_up = 1; a.out_phase = 0;
+  return emb_conv_nhwc_tc(&a, stream);
+}
+
 // dw[tap][m][n] (fp32, accumulated into) for the SAME convolution whose input is `x` (n, h, w, cin)
-// and whose output gradient is `gy` (n, h, w, cout).  m_is_in = 1: m = cin, n = cout (dw is HWIO);
-// 0: m = cout, n = cin.
-extern "C" int emb_conv5x5_wgrad_tc(const void* x, const void* gy, float* dw, int64_t n, int32_t h,
-                                    int32_t w, int32_t cin, int32_t cout, int32_t ksize,
-                                    int32_t m_is_in, void* stream) {
-  const char* who = "emb_conv5x5_wgrad_tc";
+// and whose output gradient is `gy`: (n, h, w, cout), or with gy_up = 2 phase gy_phase of
+// (n, 2h, 2w, cout).  m_is_in = 1: m = cin, n = cout (dw is HWIO); 0: m = cout, n = cin.
+extern "C" int emb_conv_wgrad_tc(const emb_conv_wgrad_tc_args* a, void* stream) {
+  const char* who = "emb_conv_wgrad_tc";
+  if (!a) return emb::fail(-1, "%s: null args", who);
+  const int64_t n = a->n;
+  const int h = a->h, w = a->w, cin = a->cin, cout = a->cout, ksize = a->ksize;
   if (n <= 0) return 0;
-  if (!x || !gy || !dw) return emb::fail(-1, "%s: null pointer", who);
+  if (!a->x || !a->gy || !a->dw) return emb::fail(-1, "%s: null pointer", who);
   if (ksize != 5 && ksize != 3 && ksize != 1) return emb::fail(-1, "%s: kernel size %d not in {1, 3, 5}", who, ksize);
-  const int m = m_is_in ? cin : cout, nn = m_is_in ? cout : cin;
+  const int m = a->m_is_in ? cin : cout, nn = a->m_is_in ? cout : cin;
   if (m != 128 && m != 256) return emb::fail(-1, "%s: the M side has %d channels, need 128 or 256", who, m);
   if (nn % 64 || nn < 64 || nn > 256) return emb::fail(-1, "%s: the N side has %d channels, need a multiple of 64 <= 256", who, nn);
-  if (w > 64 || 64 % w) return emb::fail(-1, "%s: width %d must divide 64", who, w);
+  if ((a->gy_up != 1 && a->gy_up != 2) || a->gy_phase < 0 || a->gy_phase > 3)
+    return emb::fail(-1, "%s: gy_up must be 1 or 2, gy_phase in [0, 4)", who);
   int ht, nt;
-  if (h * w >= 64) {
-    ht = 64 / w; nt = 1;
-    if (h % ht) return emb::fail(-1, "%s: height %d must be a multiple of %d rows per chunk", who, h, ht);
-  } else {
-    ht = h; nt = 64 / (h * w);
-    if (64 % (h * w) || n % nt) return emb::fail(-1, "%s: %dx%d images must pack into 64-pixel chunks", who, h, w);
-  }
-  if (((uintptr_t)x | (uintptr_t)gy | (uintptr_t)dw) & 15)
+  if (int e = pixel_box(n, h, w, 64, &ht, &nt, who)) return e;
+  if (((uintptr_t)a->x | (uintptr_t)a->gy | (uintptr_t)a->dw) & 15)
     return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
-  EncodeTiledFn enc = encode_fn();
-  if (!enc) return emb::fail(-1, "%s: cuTensorMapEncodeTiled is not available from this driver", who);
-  if (g_sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      return emb::fail_cuda(who);
-  }
-  CUtensorMap maps[2];
-  const void* ptrs[2] = {m_is_in ? x : gy, m_is_in ? gy : x};
-  const int chans[2] = {m, nn};
-  for (int i = 0; i < 2; ++i) {
-    const cuuint64_t c = (cuuint64_t)chans[i];
-    const cuuint64_t dims[4] = {c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-    const cuuint64_t strides[3] = {c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)w, (cuuint32_t)ht, (cuuint32_t)nt};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptrs[i]), dims,
-                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled failed with %d", who, (int)r);
-  }
+  if (int e = sm_count(who)) return e;
+  CUtensorMap map_x, map_gy;
+  if (int e = encode_act(&map_x, a->x, n, h, w, cin, 1, w, ht, nt, who)) return e;
+  if (int e = encode_act(&map_gy, a->gy, n, h, w, cout, a->gy_up, w, ht, nt, who)) return e;
+  CUtensorMap* maps[2] = {a->m_is_in ? &map_x : &map_gy, a->m_is_in ? &map_gy : &map_x};
   WgradShape s;
   s.chunks = (int)(n * h * w / 64);
   const int taps = ksize * ksize;
@@ -597,10 +644,12 @@ extern "C" int emb_conv5x5_wgrad_tc(const void* x, const void* gy, float* dw, in
   s.m = m;
   s.n = nn;
   s.ksize = ksize;
-  s.m_shifted = m_is_in ? 1 : 0;
+  s.m_shifted = a->m_is_in ? 1 : 0;
   s.h = h;
   s.ht = ht;
   s.nt = nt;
+  s.gy_py = a->gy_up == 2 ? a->gy_phase >> 1 : 0;
+  s.gy_ch = a->gy_up == 2 ? (a->gy_phase & 1) * cout : 0;
   const size_t smem = (size_t)kWRingSlabs * kWSlab + 1024 + 256;
   const void* fn = nullptr;
   switch ((m + nn) / 64) {
@@ -613,11 +662,21 @@ extern "C" int emb_conv5x5_wgrad_tc(const void* x, const void* gy, float* dw, in
   }
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return emb::fail_cuda(who);
-  void* params[] = {&maps[0], &maps[1], &dw, &s};
+  float* dw = a->dw;
+  void* params[] = {maps[0], maps[1], &dw, &s};
   if (cudaLaunchKernel(fn, dim3(taps * s.splits), dim3(kThreads), params, smem, (cudaStream_t)stream) !=
       cudaSuccess)
     return emb::fail_cuda(who);
-  if (cudaGetLastError() != cudaSuccess) return emb::fail_cuda(who);
   emb::count_launch();
   return 0;
+}
+
+extern "C" int emb_conv5x5_wgrad_tc(const void* x, const void* gy, float* dw, int64_t n, int32_t h,
+                                    int32_t w, int32_t cin, int32_t cout, int32_t ksize,
+                                    int32_t m_is_in, void* stream) {
+  emb_conv_wgrad_tc_args a;
+  a.x = x; a.gy = gy; a.dw = dw;
+  a.n = n; a.h = h; a.w = w; a.cin = cin; a.cout = cout; a.ksize = ksize;
+  a.m_is_in = m_is_in; a.gy_up = 1; a.gy_phase = 0;
+  return emb_conv_wgrad_tc(&a, stream);
 }

@@ -335,9 +335,13 @@ class Model:
     x1 = self.dense(x1, 'dec/sp2').reshape(-1, minres, minres, depths[-1])
     x = self.norm(x0 + x1, 'dec/spnorm')
     for i in reversed(range(len(depths) - 1)):
-      x = self.upsample(x)
-      x = self.norm(self.conv(x, f'dec/conv{i}', bias=False), f'dec/conv{i}norm',
-                    bias=self.store.w[f'dec/conv{i}/bias'])
+      w = self.W(f'dec/conv{i}/kernel')
+      if self.tc_conv and w.shape[0] == 5 and ops.subpixel_supported(x, w.shape[2], w.shape[3]):
+        # up-sample + 5x5 conv on the LOW-resolution grid: 36 instead of 100 taps per input pixel
+        y = ops.upconv_subpixel(x, w)
+      else:
+        y = self.conv(self.upsample(x), f'dec/conv{i}', bias=False)
+      x = self.norm(y, f'dec/conv{i}norm', bias=self.store.w[f'dec/conv{i}/bias'])
     if self.fused_spatial and ops.thin_conv_supported(x, x.shape[-1], cfg.image[2]):
       x = self.conv_thin_out(x, 'dec/imgout', up=2)          # up-sampling folded in
     else:

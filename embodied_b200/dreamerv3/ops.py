@@ -502,3 +502,114 @@ def conv_wgrad(x, gy, k):
   g = torch.nn.grad.conv2d_weight(
       x.permute(0, 3, 1, 2), (cout, cin, k, k), gy.permute(0, 3, 1, 2), padding=k // 2)
   return g.permute(2, 3, 1, 0)
+
+
+# ----------------------------- sub-pixel form of `nearest x2 up-sampling -> 5x5 conv`
+class _ConvArgs(ctypes.Structure):
+  _fields_ = [('inp', _vp), ('w_packed', _vp), ('bias', _vp), ('out', _vp), ('n', _i64),
+              ('h', _i32), ('w', _i32), ('cin', _i32), ('cout', _i32), ('ksize', _i32),
+              ('in_up', _i32), ('out_up', _i32), ('out_phase', _i32)]
+
+
+class _WgradArgs(ctypes.Structure):
+  _fields_ = [('x', _vp), ('gy', _vp), ('dw', _vp), ('n', _i64),
+              ('h', _i32), ('w', _i32), ('cin', _i32), ('cout', _i32), ('ksize', _i32),
+              ('m_is_in', _i32), ('gy_up', _i32), ('gy_phase', _i32)]
+
+
+def _conv_general(**kw):
+  lib = _lib.load()
+  if not getattr(lib, '_conv_general_bound', False):
+    lib.emb_conv_nhwc_tc.argtypes = [ctypes.POINTER(_ConvArgs), _vp]
+    lib.emb_conv_nhwc_tc.restype = ctypes.c_int
+    lib.emb_conv_wgrad_tc.argtypes = [ctypes.POINTER(_WgradArgs), _vp]
+    lib.emb_conv_wgrad_tc.restype = ctypes.c_int
+    lib._conv_general_bound = True
+  stream = torch.cuda.current_stream().cuda_stream
+  if 'dw' in kw:
+    _lib.check(lib.emb_conv_wgrad_tc(ctypes.byref(_WgradArgs(**kw)), stream))
+  else:
+    _lib.check(lib.emb_conv_nhwc_tc(ctypes.byref(_ConvArgs(**kw)), stream))
+
+
+_SUBPIXEL_FOLD = {}
+
+
+def subpixel_fold(device):
+  """(36, 25) 0/1 matrix F: Weff[(py, px, ty, tx)] = sum_{ky, kx} F[.., (ky, kx)] W[ky, kx].
+  A 5x5 tap dy = ky - 2 applied at output row 2y + py of the up-sampled image reads
+  low-resolution row y + floor((py + dy) / 2): ty = floor((py + ky - 2) / 2) + 1."""
+  key = str(device)
+  if key not in _SUBPIXEL_FOLD:
+    F = torch.zeros((2, 2, 3, 3, 5, 5), dtype=f32)
+    for py in range(2):
+      for px in range(2):
+        for ky in range(5):
+          for kx in range(5):
+            F[py, px, (py + ky - 2) // 2 + 1, (px + kx - 2) // 2 + 1, ky, kx] = 1.0
+    _SUBPIXEL_FOLD[key] = F.reshape(36, 25).to(device)
+  return _SUBPIXEL_FOLD[key]
+
+
+def subpixel_supported(x, cin, cout):
+  """x: the LOW-resolution input (N, h, w, cin) of an up-sample + 5x5 conv stage."""
+  if not conv_tc_supported(x, cin, cout, 3) or cout % 64:       # cout is K of the data gradient
+    return False
+  n, h, w, _ = x.shape
+  if not ((cin in (128, 256) and 64 <= cout <= 256) or (cout in (128, 256) and cin % 64 == 0 and 64 <= cin <= 256)):
+    return False
+  if w > 64 or 64 % w:
+    return False
+  return h % (64 // w) == 0 if h * w >= 64 else (64 % (h * w) == 0 and n % (64 // (h * w)) == 0)
+
+
+class SubpixelConv(torch.autograd.Function):
+  """y (N, 2h, 2w, cout) = conv5x5_same(nearest_up2(x), w) from the low-resolution x (N, h, w, cin)
+  and the folded kernels weff (4, 9, cin, cout) = subpixel_fold @ w: four 3x3 tcgen05 convolutions
+  that write the four output phases, one launch for the input gradient (the reduction runs over
+  the phases as well), four launches for the gradient of weff."""
+
+  @staticmethod
+  def forward(ctx, x, weff):
+    x = x.contiguous()
+    n, h, w, cin = x.shape
+    cout = weff.shape[-1]
+    wp = weff.permute(0, 1, 3, 2).to(torch.bfloat16).contiguous()          # (4, 9, cout, cin)
+    y = torch.empty((n, 2 * h, 2 * w, cout), dtype=torch.bfloat16, device=x.device)
+    for phase in range(4):
+      _conv_general(inp=x.data_ptr(), w_packed=wp[phase].data_ptr(), bias=None, out=y.data_ptr(), n=n,
+                    h=h, w=w, cin=cin, cout=cout, ksize=3, in_up=1, out_up=2, out_phase=phase)
+    ctx.save_for_backward(x, weff)
+    return y
+
+  @staticmethod
+  def backward(ctx, gy):
+    x, weff = ctx.saved_tensors
+    n, h, w, cin = x.shape
+    cout = weff.shape[-1]
+    gy = gy.contiguous()
+    gx = gw = None
+    if ctx.needs_input_grad[0]:
+      wd = weff.flip(1).to(torch.bfloat16).contiguous()                     # (4, 9, cin, cout): N = cin, K = cout
+      gx = torch.empty_like(x)
+      _conv_general(inp=gy.data_ptr(), w_packed=wd.data_ptr(), bias=None, out=gx.data_ptr(), n=n, h=h,
+                    w=w, cin=cout, cout=cin, ksize=3, in_up=2, out_up=1, out_phase=0)
+    if ctx.needs_input_grad[1]:
+      m_is_in = cin in (128, 256)
+      gw = torch.zeros((4, 9, cin, cout) if m_is_in else (4, 9, cout, cin), dtype=f32, device=x.device)
+      for phase in range(4):
+        _conv_general(x=x.data_ptr(), gy=gy.data_ptr(), dw=gw[phase].data_ptr(), n=n, h=h, w=w, cin=cin,
+                      cout=cout, ksize=3, m_is_in=int(m_is_in), gy_up=2, gy_phase=phase)
+      if not m_is_in:
+        gw = gw.transpose(2, 3)
+      gw = gw.to(weff.dtype)
+    return gx, gw
+
+
+def upconv_subpixel(x, w):
+  """nearest x2 up-sampling followed by the SAME 5x5 convolution with HWIO kernel w, computed on
+  the low-resolution grid (dreamerv3/rssm.py:336-340)."""
+  k, _, cin, cout = w.shape
+  assert k == 5
+  weff = (subpixel_fold(w.device) @ w.reshape(25, cin * cout).to(f32)).reshape(4, 9, cin, cout)
+  return SubpixelConv.apply(x, weff)

@@ -409,6 +409,27 @@ int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const float* bias,
                         int64_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize,
                         void* stream);
 
+/* General form of emb_conv5x5_nhwc_tc, used for the decoder's `nearest x2 up-sampling -> 5x5 conv`
+ * stages (dreamerv3/rssm.py:336-352) in their SUB-PIXEL form: output pixel (2y+py, 2x+px) of such a
+ * stage only sees a 3x3 neighbourhood of the low-resolution input, with the 5x5 taps that fall on
+ * the same low-resolution pixel summed -- four 3x3 convolutions on the (h, w) grid, 36 instead of
+ * 100 multiply-adds per low-resolution pixel and channel pair.  (h, w) is always the grid the GEMM's
+ * pixels live on.
+ *   out_up = 2: `out` is (n, 2h, 2w, cout); the launch writes phase out_phase = py*2+px of it.
+ *   in_up  = 2: `in` is (n, 2h, 2w, cin); the reduction also runs over its four phases (phase-major
+ *               weights w_packed[4*k*k][cout][cin]) -- the data gradient of the four phase
+ *               convolutions in one launch. */
+typedef struct emb_conv_tc_args {
+  const void* in;
+  const void* w_packed;
+  const float* bias;
+  void* out;
+  int64_t n;
+  int32_t h, w, cin, cout, ksize;
+  int32_t in_up, out_up, out_phase;
+} emb_conv_tc_args;
+int emb_conv_nhwc_tc(const emb_conv_tc_args* args, void* stream);
+
 /* Weight gradient of the same convolutions: dw[tap][m][n] += sum over pixels of
  * x[p + (ky-k/2, kx-k/2)][ci] * gy[p][co] (fp32, red.global.add: dw must hold zeros or the running
  * gradient).  The reduction axis is the pixel axis, so both NHWC tensors feed the tcgen05 MMAs
@@ -418,6 +439,18 @@ int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const float* bias,
  * of whole rows. */
 int emb_conv5x5_wgrad_tc(const void* x, const void* gy, float* dw, int64_t n, int32_t h, int32_t w,
                          int32_t cin, int32_t cout, int32_t ksize, int32_t m_is_in, void* stream);
+
+/* General form: gy_up = 2 reads phase gy_phase = py*2+px of a gradient stored on the doubled grid
+ * (n, 2h, 2w, cout) -- the weight gradient of one phase convolution of a sub-pixel decoder stage. */
+typedef struct emb_conv_wgrad_tc_args {
+  const void* x;
+  const void* gy;
+  float* dw;
+  int64_t n;
+  int32_t h, w, cin, cout, ksize;
+  int32_t m_is_in, gy_up, gy_phase;
+} emb_conv_wgrad_tc_args;
+int emb_conv_wgrad_tc(const emb_conv_wgrad_tc_args* args, void* stream);
 
 #ifdef __cplusplus
 }

@@ -109,3 +109,28 @@ def test_weight_gradient_matches_fp32(n, h, w, cin, cout, k):
   (reference(x, wt) * gy.float()).sum().backward()
   err = float((dw - wt.grad).abs().max())
   assert err <= 1e-4 * float(wt.grad.abs().max()), err
+
+
+@pytest.mark.parametrize('n,h,w,cin,cout', [(8, 4, 4, 256, 256), (4, 8, 8, 256, 192), (4, 16, 16, 192, 128)])
+def test_subpixel_upconv_matches_upsample_then_conv(n, h, w, cin, cout):
+  """ops.upconv_subpixel (four 3x3 phase convolutions on the low-resolution grid) against
+  nearest x2 up-sampling + 5x5 SAME convolution in fp32 on the same bf16 operands: output, input
+  gradient and kernel gradient.  The folded kernels are sums of up to four bf16 taps rounded to
+  bf16 once, hence relative-L2 tolerances at bf16 resolution."""
+  g = torch.Generator(device='cuda').manual_seed(h + cin)
+  x0 = torch.randn((n, h, w, cin), generator=g, device='cuda').to(torch.bfloat16)
+  w0 = (torch.randn((5, 5, cin, cout), generator=g, device='cuda') / 60).to(torch.bfloat16)
+  gy = torch.randn((n, 2 * h, 2 * w, cout), generator=g, device='cuda').to(torch.bfloat16)
+  x, wt = x0.clone().requires_grad_(True), w0.clone().requires_grad_(True)
+  assert ops.subpixel_supported(x, cin, cout)
+  y = ops.upconv_subpixel(x, wt)
+  (y.float() * gy.float()).sum().backward()
+  xr, wr = x0.float().requires_grad_(True), w0.float().requires_grad_(True)
+  up = F.interpolate(xr.permute(0, 3, 1, 2), scale_factor=2, mode='nearest')
+  yr = F.conv2d(up, wr.permute(3, 2, 0, 1), padding=2).permute(0, 2, 3, 1)
+  (yr * gy.float()).sum().backward()
+  rel2 = lambda a, b: float((a.float() - b).norm() / b.norm())
+  assert y.shape == yr.shape
+  assert rel2(y, yr) < 6e-3, rel2(y, yr)
+  assert rel2(x.grad, xr.grad) < 6e-3, rel2(x.grad, xr.grad)
+  assert rel2(wt.grad, wr.grad) < 6e-3, rel2(wt.grad, wr.grad)
