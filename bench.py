@@ -221,6 +221,12 @@ def run_b200(args):
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
   assert world == args.gpus, (world, args.gpus)
+  if args.scaling == 'strong':
+    # the GLOBAL workload is fixed -- 256 envs and a (16, 64) batch in all; rank r owns
+    # envs {i : i mod R = r} and samples 16 / R windows from its own shard per update
+    global B, NENVS
+    assert 16 % world == 0, f'strong scaling splits B=16 over the ranks; {world} does not divide it'
+    B, NENVS = 16 // world, 256 // world
   from embodied_b200 import _lib
   from embodied_b200.core import store as storelib
   from embodied_b200.dreamerv3 import scan as scanlib
@@ -331,7 +337,7 @@ def run_b200(args):
       'learner_samples_per_sec': env_steps / t_dev * TRAIN_RATIO,
       'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': t_dev / args.steps * 1e3, 'higher_is_better': True,
-      'scaling': 'weak', 'vs_baseline': None,
+      'scaling': args.scaling, 'vs_baseline': None,
       'dtype': 'u8' if args.agent == 'feed' else {'bfloat16': 'bf16', 'float32': 'f32'}[args.dtype],
       'data': 'synthetic',
       'config': {
@@ -339,6 +345,8 @@ def run_b200(args):
           'envs_per_gpu': NENVS, 'batch': [B, T], 'train_ratio': TRAIN_RATIO,
           'learner_steps_per_step': TRAINS_PER_STEP, 'replay_capacity_items': capacity,
           'parallelism': f'dp{world}: envs, replay shard and batch per rank; NCCL grad all-reduce',
+          'precision': 'bf16 compute with fp32 master weights, norms and losses (the reference default, '
+                       'embodied/jax/nets.py:12); the CPU arm (--impl reference, cpu_baseline) computes in fp32',
           'cache': 'L2 flushed (256 MiB write) before every timed step; replay tables > L2'},
       'e2e': {'value': env_steps / t_e2e, 'unit': 'env steps/s',
               'ms_per_step': t_e2e / args.steps * 1e3,
@@ -361,6 +369,117 @@ def run_b200(args):
     os._exit(0)
 
 
+# ------------------------------------------- config 5: replay sample-rate sweep
+SWEEP_B = (8, 16, 32, 64, 128)
+SWEEP_T = (16, 32, 64, 128, 256)
+ROW_KINDS = {                      # bytes per stored step, excluding the 20-byte stepid
+    'image': {'image': (np.uint8, IMAGE)},
+    'default': {'image': (np.uint8, IMAGE), 'dyn/deter': (np.float32, (DETER,)),
+                'dyn/stoch': (np.float32, STOCH), 'reward': (np.float32, ()),
+                'action': (np.int32, ()), 'is_first': (bool, ()), 'is_last': (bool, ()),
+                'is_terminal': (bool, ())},
+}
+
+
+def run_sweep(args):
+  """BASELINE.json config 5: Replay.sample through Stateless -> Consec for
+  B x T windows, image-only rows (12 288 B) and default dreamerv3 rows (53 279 B), buffer
+  pre-filled with 8*B*T steps from 64 workers; one independent shard per rank.  A step is ONE
+  sampled batch: samples/s = B*T / step, GB/s = 2*B*(T+1)*(row bytes + 24) / step."""
+  import torch
+  import torch.distributed as dist
+  import embodied_b200 as embodied
+  from embodied_b200 import _lib
+  rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  peak, peak_src = peaks()
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+  g = torch.Generator(device='cuda').manual_seed(rank)
+  workers = 64
+  points, launches0 = [], _lib.launch_count()
+  grid = [(b, t) for b in SWEEP_B for t in SWEEP_T]
+  if args.sweep_points:
+    grid = [tuple(int(x) for x in p.split('x')) for p in args.sweep_points.split(',')]
+  with ClockSampler(local) as clocks:
+    for kind, spec in ROW_KINDS.items():
+      rowbytes = sum(int(np.dtype(d).itemsize * np.prod(sh, dtype=np.int64)) for d, sh in spec.values())
+      for Bx, Tx in grid:
+        Lx = Tx + PREFIX
+        per_worker = max(8 * Bx * Tx // workers, 2 * Lx)
+        replay = embodied.Replay(Lx, None, chunksize=1024, seed=0, staging_rows=workers, workers=workers)
+        torch_dt = {np.uint8: torch.uint8, np.float32: torch.float32, np.int32: torch.int32, bool: torch.bool}
+        step = {}
+        for k, (d, sh) in spec.items():
+          if d is bool:
+            step[k] = torch.zeros((workers, *sh), dtype=torch.bool, device='cuda')
+          elif d is np.uint8:
+            step[k] = torch.randint(0, 256, (workers, *sh), generator=g, device='cuda', dtype=torch.uint8)
+          elif d is np.int32:
+            step[k] = torch.randint(0, CLASSES, (workers, *sh), generator=g, device='cuda', dtype=torch.int32)
+          else:
+            step[k] = torch.randn((workers, *sh), generator=g, device='cuda')
+        for _ in range(per_worker):
+          replay.add_batch(step)
+        base = embodied.streams.Stateless(replay.sample, Bx, 'train')
+        stream = iter(embodied.streams.Consec(base, length=Tx, consec=1, prefix=PREFIX, strict=True,
+                                              contiguous=True))
+        for _ in range(max(args.warmup, 3)):
+          batch = next(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+          dist.barrier()
+        total = 0.0
+        for _ in range(args.steps):
+          flush.zero_()
+          a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          torch.cuda.synchronize()
+          a.record()
+          batch = next(stream)
+          b.record()
+          torch.cuda.synchronize()
+          total += a.elapsed_time(b) * 1e-3
+        t = torch.tensor([total], device='cuda', dtype=torch.float64)
+        if world > 1:
+          dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item()) / args.steps
+        nbytes = 2 * Bx * Lx * (rowbytes + 20 + 4)
+        points.append({'rows': kind, 'row_bytes': rowbytes, 'B': Bx, 'T': Tx,
+                       'us_per_batch': dt * 1e6, 'samples_per_sec': world * Bx * Tx / dt,
+                       'GBs_per_gpu': nbytes / dt / 1e9, 'frac': nbytes / dt / 1e9 / peak})
+        del replay, stream, base, batch
+        torch.cuda.empty_cache()
+  head = next((p for p in points if p['rows'] == 'default' and (p['B'], p['T']) == (B, T)), points[-1])
+  best = max(points, key=lambda p: p['frac'])
+  line = {
+      'metric': 'replay_samples_per_sec', 'value': head['samples_per_sec'], 'unit': 'samples/s',
+      'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+      'ms_per_step': head['us_per_batch'] * 1e-3, 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+      'config': {'workload': 'config 5: replay sample-rate sweep B in {8..128} x T in {16..256}, 64x64x3 '
+                             'obs, image-only and default dreamerv3 rows; headline = default rows at '
+                             f'B={head["B"]}, T={head["T"]}',
+                 'parallelism': f'{world} independent replay shards, no collective',
+                 'cache': 'L2 flushed (256 MiB write) before every timed batch; host index work + '
+                          'row-id H2D + gather launch inside the timed region'},
+      'roofline': {'kernel': 'rows_kernel (emb_replay_gather)', 'bound': 'hbm',
+                   'achieved': head['GBs_per_gpu'], 'peak': peak, 'peak_source': peak_src, 'unit': 'GB/s',
+                   'frac': head['frac'], 'traffic': None,
+                   'note': 'whole Replay.sample call (host draw + launch), not the bare kernel'},
+      'best_point': best, 'sweep': points,
+      'gpu_launches': _lib.launch_count() - launches0, 'clocks': clocks.summary(),
+      'e2e': {'value': head['samples_per_sec'], 'unit': 'samples/s',
+              'h2d_bytes_per_step': head['B'] * (head['T'] + PREFIX) * 8, 'd2h_bytes_per_step': 0,
+              'note': 'the sampled batch stays in HBM by design (the learner consumes it there); '
+                      'H2D = the int64 row ids'}}
+  if rank == 0:
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def workload_name(args):
   if args.agent == 'feed':
     return ('config 2 PLUMBING ONLY: Driver(256 envs, 64x64x3 u8) + Replay(L=65, 53 299 B rows '
@@ -370,53 +489,75 @@ def workload_name(args):
 
 
 # ------------------------------------------------------ the reference (CPU) arm
-class OracleLoop:
-  """The same iteration on the host with the numpy restatement of the
-  reference's code (oracle/host_oracle.py).  bench.py is one of the few places
+# One benchmark step = 256 env steps + 8 learner updates of (B=16, T=64): ~2 minutes of host time.
+# A SAMPLE is 1/8 of it measured whole, nothing extrapolated: one learner update on a real
+# (B=16, T) batch together with the B*T/32 env steps that trigger it (train_ratio = 32:
+# embodied/run/train.py:25-26), i.e. for T = 64: 32 env steps of Driver + Replay + policy, one
+# replay.sample(16) + Consec view + replay.update, one fp32 dreamerv3 update of 1024 samples.
+# value = env steps in the sample / its wall time.  When more steps are requested than fit the
+# time budget, later samples shorten T (64 -> 32 -> 16 -> 8; every per-sample cost is linear in T
+# except the optimiser pass over the parameters, which makes short samples slightly PESSIMISTIC
+# for the CPU, so the reported figure is the T = 64 sample whenever one was timed).
+class OracleSample:
+  """The host-side restatement (oracle/) of one sample.  bench.py is one of the few places
   allowed to execute oracle/; it is the thing compared against, never shipped."""
 
-  def __init__(self, rank=0):
+  def __init__(self, size, T_s, rank=0, agent='dreamerv3'):
     import itertools
     from oracle import host_oracle as ho
-    self.ho = ho
-    envs = [make_env(rank * NENVS + i) for i in range(NENVS)]
-    self.replay = ho.OracleReplay(L, None, 1024, True, 0, ids=itertools.count(1))
+    self.ho, self.T = ho, T_s
+    self.L = T_s + PREFIX
+    self.nenvs = max(1, B * T_s // TRAIN_RATIO)
+    envs = [make_env(rank * NENVS + i) for i in range(self.nenvs)]
+    self.replay = ho.OracleReplay(self.L, None, 1024, True, 0, ids=itertools.count(1))
     self.driver = ho.OracleDriver(envs, envs[0].act_space)
     self.driver.callbacks.append(lambda row, w: self.replay.add(row, w))
+    self.learner = None if agent == 'feed' else _learner(size)
     rng = np.random.default_rng(rank)
-    self.deter = rng.standard_normal((4, NENVS, DETER), dtype=np.float32)
-    self.stoch = rng.standard_normal((4, NENVS, *STOCH), dtype=np.float32)
-    self.action = rng.integers(0, CLASSES, (4, NENVS)).astype(np.int32)
-    self.t = 0
-    self.learner_on = False
+    deter, stoch = DETER, STOCH
+    if self.learner is not None:
+      deter, stoch = self.learner.cfg.deter, (self.learner.cfg.stoch, self.learner.cfg.classes)
+    self.deter = rng.standard_normal((self.nenvs, deter), dtype=np.float32)
+    self.stoch = rng.standard_normal((self.nenvs, *stoch), dtype=np.float32)
+    self.action = rng.integers(0, CLASSES, self.nenvs).astype(np.int32)
+    self.pcarry = None
+    self.learn = False
+    while len(self.replay) < 4 * B:              # prefill: plumbing only
+      self.driver.step(self._feed_policy)
+    self.learn = True
 
-  def policy(self, carry, obs):
-    i = self.t % 4
-    self.t += 1
-    self.ho.normalize_image(obs['image'])              # rssm.py:230 on the host
-    return carry, {'action': self.action[i]}, {
-        'dyn/deter': self.deter[i], 'dyn/stoch': self.stoch[i]}
+  def _feed_policy(self, carry, obs):
+    self.ho.normalize_image(obs['image'])
+    return carry, {'action': self.action}, {'dyn/deter': self.deter, 'dyn/stoch': self.stoch}
+
+  def _policy(self, carry, obs):
+    """Reference Agent.policy on the host: encoder + one RSSM step + actor (fp32 oracle)."""
+    torch, cfg, n = self.learner.torch, self.learner.cfg, self.nenvs
+    if self.pcarry is None:
+      self.pcarry = dict(deter=torch.zeros(n, cfg.deter), stoch=torch.zeros(n, cfg.stoch, cfg.classes),
+                         action=torch.zeros(n, dtype=torch.int32))
+    noise = dict(stoch=torch.zeros(n, cfg.stoch, cfg.classes), action=torch.zeros(n, cfg.actions))
+    self.pcarry, act, out = self.learner.model.policy(
+        self.pcarry, torch.from_numpy(obs['image']), torch.from_numpy(np.asarray(obs['is_first'])), noise)
+    return carry, {'action': act['action'].numpy()}, {k: v.numpy() for k, v in out.items()}
 
   def step(self):
-    self.driver.step(self.policy)
-    if not self.learner_on:
-      return
-    for _ in range(TRAINS_PER_STEP):
-      batch = self.ho.consec_view(self.replay.sample(B), T, 0, PREFIX)
-      self.replay.update({k: batch[k][:, PREFIX:] for k in ('stepid', 'dyn/deter', 'dyn/stoch')})
+    t0 = time.perf_counter()
+    self.driver.step(self._feed_policy if self.learner is None else self._policy)
+    batch = self.ho.consec_view(self.replay.sample(B), self.T, 0, PREFIX)
+    if self.learner is not None:
+      self.learner.train_on(batch, self.T)
+    self.replay.update({k: batch[k][:, PREFIX:] for k in ('stepid', 'dyn/deter', 'dyn/stoch')})
+    return time.perf_counter() - t0
 
 
-def time_plumbing(steps, warmup):
-  loop = OracleLoop()
-  while len(loop.replay) < 4 * B * L:
-    loop.step()
-  loop.learner_on = True
-  for _ in range(warmup):
-    loop.step()
-  t0 = time.perf_counter()
-  for _ in range(steps):
-    loop.step()
-  return (time.perf_counter() - t0) / steps
+_LEARNERS = {}
+
+
+def _learner(size):
+  if size not in _LEARNERS:
+    _LEARNERS[size] = OracleLearner(size)
+  return _LEARNERS[size]
 
 
 class OracleLearner:
@@ -432,91 +573,74 @@ class OracleLearner:
     torch.set_num_threads(self.threads)
     self.cfg = do.default_config(**C.SIZES[size])
     self.model = do.Dreamer(self.cfg, do.init_params(self.cfg, 0))
+    self.noise = {}
 
-  def batch(self, b):
-    torch, cfg = self.torch, self.cfg
-    g = torch.Generator().manual_seed(b)
-    return {
-        'image': torch.randint(0, 256, (b, L, *IMAGE), generator=g, dtype=torch.uint8),
-        'reward': torch.randn(b, L, generator=g),
-        'is_first': torch.zeros(b, L, dtype=torch.bool),
-        'is_last': torch.zeros(b, L, dtype=torch.bool),
-        'is_terminal': torch.zeros(b, L, dtype=torch.bool),
-        'action': torch.randint(0, CLASSES, (b, L), generator=g, dtype=torch.int32),
-        'dyn/deter': torch.zeros(b, L, cfg.deter),
-        'dyn/stoch': torch.zeros(b, L, cfg.stoch, cfg.classes),
-        'stepid': torch.zeros(b, L, 20, dtype=torch.uint8)}
-
-  def time_train(self, b):
-    data, noise = self.batch(b), self.do.make_noise(self.cfg, b, T, 0)
-    t0 = time.perf_counter()
-    self.model.train(data, noise)
-    return time.perf_counter() - t0
-
-  def time_policy(self, n):
-    torch, cfg = self.torch, self.cfg
-    carry = dict(deter=torch.zeros(n, cfg.deter), stoch=torch.zeros(n, cfg.stoch, cfg.classes),
-                 action=torch.zeros(n, dtype=torch.int32))
-    image = torch.randint(0, 256, (n, *IMAGE), dtype=torch.uint8)
-    noise = dict(stoch=torch.zeros(n, cfg.stoch, cfg.classes), action=torch.zeros(n, cfg.actions))
-    t0 = time.perf_counter()
-    self.model.policy(carry, image, torch.zeros(n, dtype=torch.bool), noise)
-    return time.perf_counter() - t0
+  def train_on(self, batch, T_s):
+    """One full update (forward, backward, optimiser) on a replay batch of numpy arrays."""
+    torch = self.torch
+    data = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in batch.items()}
+    if T_s not in self.noise:
+      self.noise[T_s] = self.do.make_noise(self.cfg, B, T_s, 0)
+    self.model.train(data, self.noise[T_s])
 
 
-def cpu_iteration(args, learner=None):
-  """Seconds per benchmark step on the host, from a bounded sample: the
-  Driver+Replay iteration is timed whole; agent.policy is timed on 64 of the 256
-  envs (x4); agent.train on sub-batches B=1 and B=2 of the (16, 64) batch and
-  extrapolated linearly to B=16 (the per-step weight traffic does not scale
-  with B, so a plain x16 would overstate the CPU time)."""
-  t_plumb = time_plumbing(2, 1)
-  if args.agent == 'feed':
-    return t_plumb, {'plumbing_s': t_plumb}, 1
-  learner = learner or OracleLearner(args.size)
-  t_pol = 4 * learner.time_policy(64)
-  t1 = learner.time_train(1)
-  t2 = learner.time_train(2)
-  t16 = t1 + 15 * max(t2 - t1, 0.0)
-  parts = {'plumbing_s': t_plumb, 'policy_256_s': t_pol, 'train_B1_s': t1, 'train_B2_s': t2,
-           'train_B16_extrapolated_s': t16}
-  return t_plumb + t_pol + TRAINS_PER_STEP * t16, parts, learner.threads
+def cpu_sample_line(size, agent, T_s, seconds, threads):
+  nenv = max(1, B * T_s // TRAIN_RATIO)
+  return {
+      'value': nenv / seconds, 'unit': 'env steps/s', 'cores': threads, 'kind': 'port',
+      'sample': (f'1/{TRAINS_PER_STEP * T // T_s} of one benchmark step, measured whole: {nenv} env steps of the '
+                 f'oracle Driver + Replay + fp32 dreamerv3 policy, replay.sample(16) + Consec + replay.update, '
+                 f'and ONE fp32 dreamerv3 update on the sampled (B=16, T={T_s}) batch ({size}, '
+                 f'{threads} torch threads; the Driver / Replay half is single-threaded Python like the '
+                 f'reference).  oracle/ = restatement of the reference (JAX is not installable here)'
+                 if agent != 'feed' else
+                 f'{nenv} env steps of the oracle Driver + Replay, replay.sample(16) + Consec + update'),
+      'seconds_per_sample': seconds}
 
 
 def cpu_baseline(args):
-  t, parts, threads = cpu_iteration(args)
-  return {'value': NENVS / t, 'unit': 'env steps/s', 'cores': threads, 'kind': 'port',
-          'sample': 'one benchmark step assembled from a bounded sample: oracle Driver+Replay '
-                    'iteration timed whole (1 thread, as in run.train debug mode); oracle '
-                    'dreamerv3 policy on 64/256 envs x4; oracle train step at B=1 and B=2 '
-                    f'(T=64) extrapolated linearly to B=16, x{TRAINS_PER_STEP} (fp32, '
-                    f'{threads} torch threads)', 'ms_per_step': t * 1e3, 'parts': parts}
+  """~15-30 s of host work: one T = 64 sample after a T = 8 warm-up sample."""
+  if args.agent != 'feed':
+    OracleSample(args.size, 8, agent=args.agent).step()         # thread pools, allocator warm-up
+  sample = OracleSample(args.size, T, agent=args.agent)
+  dt = sample.step()
+  threads = sample.learner.threads if sample.learner else 1
+  return cpu_sample_line(args.size, args.agent, T, dt, threads)
 
 
 def run_reference(args):
   if int(os.environ.get('RANK', 0)) != 0:
     return
-  steps = max(1, min(args.steps, 3))
-  warm = min(args.warmup, 1)
-  learner = None if args.agent == 'feed' else OracleLearner(args.size)
-  for _ in range(warm):
-    if learner is not None:
-      learner.time_policy(8)
-  times = [cpu_iteration(args, learner) for _ in range(steps)]
-  t = float(np.mean([x[0] for x in times]))
-  v = NENVS / t
-  threads = times[0][2]
+  budget = float(os.environ.get('EMB_REF_BUDGET_S', 150))
+  total = args.steps + args.warmup
+  samples = {T: OracleSample(args.size, T, agent=args.agent)}
+  t_first = samples[T].step()                       # warm-up step 1 doubles as the calibration
+  # T of the remaining samples: the longest that fits the budget (cost ~ 10 % fixed + 90 % linear in T)
+  T_s = T
+  while T_s > 8 and (total - 1) * t_first * (0.1 + 0.9 * T_s / T) > budget:
+    T_s //= 2
+  if T_s not in samples:
+    samples[T_s] = OracleSample(args.size, T_s, agent=args.agent)
+  for _ in range(args.warmup - 1):
+    samples[T_s].step()
+  times = [samples[T_s].step() for _ in range(args.steps)]
+  t = float(np.mean(times))
+  nenv = samples[T_s].nenvs
+  threads = samples[T].learner.threads if samples[T].learner else 1
+  line = cpu_sample_line(args.size, args.agent, T_s, t, threads)
+  v = nenv / t
   print(json.dumps({
       'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': v, 'unit': 'env steps/s',
       'learner_samples_per_sec': v * TRAIN_RATIO,
-      'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': workload_name(args) + ' -- CPU restatement of the reference '
-                             '(oracle/), see cpu_baseline.sample', 'envs': NENVS, 'batch': [B, T]},
-      'cpu_baseline': {'value': v, 'unit': 'env steps/s', 'cores': threads, 'kind': 'port',
-                       'sample': cpu_iteration.__doc__.strip().replace('\n  ', ' '),
-                       'parts': times[-1][1]},
+      'config': {'workload': workload_name(args) + ' -- CPU restatement of the reference (oracle/); a '
+                             'reference-arm step is a bounded sample of the benchmark step, see '
+                             'cpu_baseline.sample', 'envs': NENVS, 'batch': [B, T],
+                 'sample_T': T_s, 'env_steps_per_sample': nenv},
+      'cpu_baseline': dict(line, value=v, first_sample_T64_seconds=t_first,
+                           first_sample_T64_value=samples[T].nenvs / t_first),
       'e2e': {'value': v, 'unit': 'env steps/s', 'h2d_bytes_per_step': 0,
               'd2h_bytes_per_step': 0}}), flush=True)
 
@@ -535,10 +659,17 @@ def main():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--capacity', type=float, default=2e5)
   ap.add_argument('--no-cpu', action='store_true')
+  ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                  help='weak: 256 envs and a (16, 64) batch PER GPU; strong: in all (SURVEY 8e)')
+  ap.add_argument('--workload', default='train', choices=['train', 'replay_sweep'],
+                  help='train = BASELINE config 2 (the headline); replay_sweep = config 5')
+  ap.add_argument('--sweep-points', default='', help='e.g. 16x64,128x256 (default: the full 5x5 grid)')
   args = ap.parse_args()
-  args.warmup = max(args.warmup, 3)
+  args.warmup = max(args.warmup, 3 if args.impl != 'reference' else 1)
   if args.impl == 'reference':
     run_reference(args)
+  elif args.workload == 'replay_sweep':
+    run_sweep(args)
   else:
     run_b200(args)
 

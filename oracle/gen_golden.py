@@ -159,6 +159,43 @@ def gen_consec(ns):
   ns.elements.UUID.reset(debug=False)
 
 
+CHUNKDIR_SPEC = dict(length=6, capacity=60, chunksize=8, workers=3, steps=26, batch=5, seed=2)
+
+
+def fill_chunkdir_stream(replay, spec, save_at=(11,)):
+  """The seeded stream behind tests/golden/ref_chunks: `save()` is also called mid-stream, so the
+  directory holds chunks that were completed early (length < chunksize, successor set)."""
+  rng = np.random.default_rng(4321)
+  for t in range(spec['steps']):
+    for w in range(spec['workers']):
+      replay.add(transition(rng, w, t, SHAPES), w)
+    if t in save_at:
+      replay.save()
+  replay.save()
+
+
+def gen_chunkdir(ns):
+  """A replay directory written by the REFERENCE's own Replay.save (chunk.py:64-74) plus what
+  the reference samples after loading it back into a fresh buffer (replay.py:312-359)."""
+  import shutil
+  out = OUT / 'ref_chunks'
+  shutil.rmtree(out, ignore_errors=True)
+  sp = CHUNKDIR_SPEC
+  ns.elements.UUID.reset(debug=True)
+  replay = ns.replay.Replay(length=sp['length'], capacity=sp['capacity'], chunksize=sp['chunksize'],
+                            directory=str(out), seed=sp['seed'], save_wait=True)
+  fill_chunkdir_stream(replay, sp)
+  fresh = ns.replay.Replay(length=sp['length'], capacity=sp['capacity'], chunksize=sp['chunksize'],
+                           directory=str(out), seed=sp['seed'])
+  fresh.load()
+  res = {'len': np.int64(len(fresh))}
+  for i in range(3):
+    for k, v in fresh.sample(sp['batch']).items():
+      res[f'sample{i}/{k}'] = v
+  np.savez_compressed(OUT / 'ref_chunks_expected.npz', **res)
+  ns.elements.UUID.reset(debug=False)
+
+
 def main():
   OUT.mkdir(parents=True, exist_ok=True)
   ns = refload.load()
@@ -167,6 +204,7 @@ def main():
   gen_uniform(ns)
   gen_driver(ns)
   gen_consec(ns)
+  gen_chunkdir(ns)
   for p in sorted(OUT.glob('*.npz')):
     print(p.name, p.stat().st_size)
 

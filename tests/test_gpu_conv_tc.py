@@ -10,6 +10,20 @@ torch = pytest.importorskip('torch')
 import torch.nn.functional as F                      # noqa: E402
 from embodied_b200.dreamerv3 import ops              # noqa: E402
 
+@pytest.fixture(autouse=True)
+def _strict_fp32_reference():
+  """The fp32 reference convolutions must not run on TF32 tensor cores (other tests in the same
+  process switch the library's algorithm search on, which picks such kernels)."""
+  saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
+           torch.backends.cudnn.benchmark)
+  torch.backends.cudnn.allow_tf32 = False
+  torch.backends.cuda.matmul.allow_tf32 = False
+  torch.backends.cudnn.benchmark = False
+  yield
+  (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32,
+   torch.backends.cudnn.benchmark) = saved
+
+
 SHAPES = [  # n, h, w, cin, cout, k  -- the dreamerv3 size200m layers (rssm.py:233-240, 336-352) + edge cases
     (4, 32, 32, 128, 192, 5), (4, 16, 16, 192, 256, 5), (4, 8, 8, 256, 256, 5),
     (2, 16, 16, 256, 192, 5), (2, 32, 32, 192, 128, 5),

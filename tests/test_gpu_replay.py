@@ -164,3 +164,21 @@ def test_full_size_properties_config2():
       b, t = hit[0]
       assert float(got['dyn/deter'][b, t, 0]) == -3.0
       break
+
+
+def test_device_replay_loads_directory_written_by_the_reference(tmp_path):
+  """tests/golden/ref_chunks was written by the REFERENCE's Replay.save; the HBM-backed product
+  loads it (emb_rows_copy imports every slab) and samples what the reference sampled after
+  loading the same directory (oracle/gen_golden.py gen_chunkdir)."""
+  import shutil
+  from oracle import gen_golden
+  import golden_cases
+  sp = gen_golden.CHUNKDIR_SPEC
+  shutil.copytree(golden_cases.GOLDEN / 'ref_chunks', tmp_path / 'chunks')
+  want = np.load(golden_cases.GOLDEN / 'ref_chunks_expected.npz')
+  replay = embodied.Replay(sp['length'], sp['capacity'], chunksize=sp['chunksize'],
+                           directory=str(tmp_path / 'chunks'), seed=sp['seed'], staging_rows=4)
+  replay.load()
+  assert len(replay) == int(want['len'])
+  for i in range(3):
+    golden_cases.check_batch(replay.sample(sp['batch']), None, f'sample{i}/', want)
