@@ -337,13 +337,21 @@ class Dreamer:
     out = {'dyn/deter': dyn['deter'], 'dyn/stoch': dyn['stoch']}
     return carry, {'action': act}, out
 
-  # -- replay context (agent.py:312-340), K = replay_context, consec == 0 rows ----
-  def apply_replay_context(self, data):
+  # -- replay context (agent.py:312-340), K = replay_context -----------------------------
+  def apply_replay_context(self, data, carry=None):
+    """Rows whose chunk is the first of its window (consec == 0) restart from the latents
+    stored in the replay (`truncate`: the last of the K context steps, rssm.py truncate);
+    the other rows continue from the running `carry` (agent.py:331-339).  For K >= 1 the
+    previous actions are the same in both branches: prepend(prev, act)[:, K:] == act[:, K-1:-1]."""
     K = self.cfg.replay_context
-    carry = dict(deter=data['dyn/deter'][:, K - 1], stoch=data['dyn/stoch'][:, K - 1])
+    rep = dict(deter=data['dyn/deter'][:, K - 1], stoch=data['dyn/stoch'][:, K - 1])
+    if carry is not None and 'consec' in data:
+      first = data['consec'][:, 0] == 0
+      rep = dict(deter=torch.where(first[:, None], rep['deter'], carry['deter']),
+                 stoch=torch.where(first[:, None, None], rep['stoch'], carry['stoch']))
     obs = {k: data[k][:, K:] for k in ('image', 'reward', 'is_first', 'is_last', 'is_terminal')}
     prevact = data['action'][:, K - 1: -1]
-    return carry, obs, prevact, data['stepid'][:, K:]
+    return rep, obs, prevact, data['stepid'][:, K:]
 
   # -- loss (agent.py:156-245) --------------------------------------------------------
   def loss(self, carry, obs, prevact, noise, update=True):
@@ -454,8 +462,8 @@ class Dreamer:
     return lo, torch.clamp(hi - lo, min=cfg.retnorm_limit)
 
   # -- one train step (agent.py:137-154, opt.py:31-81) -----------------------------------
-  def train(self, data, noise):
-    carry, obs, prevact, stepid = self.apply_replay_context(data)
+  def train(self, data, noise, carry=None):
+    carry, obs, prevact, stepid = self.apply_replay_context(data, carry)
     names = list(self.p)
     leaves = [self.p[k].detach().requires_grad_(True) for k in names]
     saved = self.p

@@ -98,3 +98,21 @@ def test_lambda_return_matches_recursion():
     cont = (1 - last[:, t + 1].float()) * 0.95
     want[:, t] = rew[:, t + 1] + live * ((1 - cont) * val[:, t + 1] + cont * want[:, t + 1])
   np.testing.assert_allclose(ret.numpy(), want[:, :-1].numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_oracle_reproduces_its_committed_golden():
+  """tests/golden/dreamer_tiny.npz (oracle/gen_dreamer_golden.py): an edit that changes the
+  oracle's numbers must be deliberate.  fp32 CPU arithmetic differs slightly between BLAS
+  builds / thread counts, hence 1e-5 on floats; sampled indices and actions are exact."""
+  import numpy as np
+  import pathlib
+  from oracle import gen_dreamer_golden as gg
+  want = np.load(pathlib.Path(__file__).parent / 'golden' / 'dreamer_tiny.npz')
+  got = gg.run()
+  assert sorted(got) == sorted(want.files)
+  for k in want.files:
+    a, b = np.asarray(got[k]), want[k]
+    if b.dtype == np.int8:
+      assert (a == b).all(), k
+    else:
+      assert np.allclose(a, b, rtol=1e-5, atol=1e-6 * float(np.abs(b).max() + 1e-30)), k

@@ -254,3 +254,62 @@ def test_tc_convolutions_track_library_convolutions_at_size200m_widths():
       ga, gb = agents[0].store.view('grad', k).double(), agents[1].store.view('grad', k).double()
       cos = float((ga * gb).sum() / (ga.norm() * gb.norm() + 1e-30))
       assert cos > 0.98, (k, cos)
+
+
+def test_consecutive_chunks_continue_from_the_running_carry():
+  """replay_context with consec > 0 (dreamerv3/agent.py:322-339): rows of a first chunk
+  (consec == 0) restart from the latents stored in the replay, rows of later chunks continue
+  from the carry the previous train call returned.  Mixed batch: rows 0 and 2 continue,
+  row 1 restarts; oracle and product fed the same carry."""
+  ocfg, oracle, agent = make_pair(seed=4)
+  B, T = 3, 5
+  d0, n0 = cases.batch(ocfg, B, T, seed=31), do.make_noise(ocfg, B, T, seed=32)
+  ocarry, _, _, _, _ = oracle.train(d0, n0)
+  carry, _, _ = agent.train(agent.init_train(B), cases.to_device(d0), cases.to_device(n0))
+  assert rel(carry[0], ocarry['deter']) < RTOL
+  d1, n1 = cases.batch(ocfg, B, T, seed=33), do.make_noise(ocfg, B, T, seed=34)
+  d1['consec'] = torch.tensor([1, 0, 1], dtype=torch.int32)[:, None].expand(B, T + 1).contiguous()
+  ocarry2, oouts, omets, _, oo = oracle.train(d1, n1, carry=ocarry)
+  carry2, outs, mets = agent.train(carry, cases.to_device(d1), cases.to_device(n1))
+  assert rel(mets['loss'], omets['loss']) < RTOL
+  feat = agent.last_outs['feat']
+  assert torch.equal(feat['stoch'].detach().argmax(-1).cpu(), oo['feat']['stoch'].argmax(-1))
+  assert rel(feat['deter'], oo['feat']['deter']) < RTOL
+  assert rel(carry2[0], ocarry2['deter']) < RTOL
+  # the restart really is a different computation: feeding consec == 0 everywhere changes row 0
+  d1b = dict(d1, consec=torch.zeros(B, T + 1, dtype=torch.int32))
+  _, _, omets_b, _, oo_b = oracle.train(d1b, n1, carry=ocarry)
+  assert rel(oo_b['feat']['deter'][0], oo['feat']['deter'][0]) > 1e-3
+
+
+def test_product_matches_the_committed_oracle_golden():
+  """The same scenario as tests/golden/dreamer_tiny.npz on the GPU: loss, per-term losses and
+  final deter to 1e-5, sampled latents / imagined actions exactly, gradient norms to 3e-4."""
+  import pathlib
+  from oracle import gen_dreamer_golden as gg
+  want = np.load(pathlib.Path(__file__).parent / 'golden' / 'dreamer_tiny.npz')
+  ocfg, _, agent = make_pair(seed=gg.SPEC['seed'])
+  B, T = gg.SPEC['B'], gg.SPEC['T']
+  carry = agent.init_train(B)
+  for it in range(gg.SPEC['steps']):
+    data = cases.batch(ocfg, B, T, seed=10 + it)
+    noise = do.make_noise(ocfg, B, T, seed=it)
+    launch = agent.opt.launch
+    grads = {}
+    def spy():
+      for k in gg.PROBES:
+        grads[k] = float(agent.store.view('grad', k).double().norm())
+      return launch()
+    agent.opt.launch = spy
+    carry, outs, mets = agent.train(carry, cases.to_device(data), cases.to_device(noise))
+    agent.opt.launch = launch
+    close = lambda a, b, tol: abs(float(a) - float(b)) <= tol * abs(float(b)) + 1e-12
+    assert close(mets['loss'], want[f's{it}/loss'], RTOL), it
+    for k, v in agent.last_outs['losses'].items():
+      assert close(v.mean(), want[f's{it}/loss_{k}'], 3 * RTOL), (it, k)
+    feat = agent.last_outs['feat']
+    assert (feat['stoch'].detach().argmax(-1).cpu().numpy() == want[f's{it}/index']).all()
+    assert (agent.last_outs['imgact'].cpu().numpy() == want[f's{it}/imgact']).all()
+    assert rel(carry[0], torch.from_numpy(want[f's{it}/deter_last'])) < RTOL
+    for k in gg.PROBES:
+      assert close(grads[k], want[f's{it}/gradnorm/{k}'], GTOL), (it, k)

@@ -68,9 +68,12 @@ CASES = [
     ('tiny-B1-T1', dict(), 1, 1),
     ('mid', dict(deter=1024, hidden=128, stoch=8, classes=16, blocks=8), 5, 3),
 ]
+# the BENCHMARK's layer shapes (dreamerv3/configs.yaml size200m): the only size at which the
+# per-CTA tile counts, paddings and k ranges of the kernels are the ones bench.py runs
+SIZE200M = dict(deter=8192, hidden=1024, stoch=32, classes=64, blocks=8, depth=64, units=1024)
 
 
-@pytest.mark.parametrize('name,over,B,T', CASES)
+@pytest.mark.parametrize('name,over,B,T', CASES + [('size200m-B16', SIZE200M, 16, 4)])
 def test_forward_fp32_engine_matches_oracle(name, over, B, T):
   ocfg = do.tiny_config(**over)
   vals, oracle, tokens, action, reset, deter0, stoch0, gumbel = setup(ocfg, B, T, 0)
@@ -110,6 +113,41 @@ def test_forward_bf16_engine_tracks_oracle(name, over, B, T, engine):
   assert rel(out['logit'][:, 0], feat['logit'][:, 0]) < 3e-2
 
 
+def test_forward_bf16_tma_engine_at_size200m_tracks_oracle_step_by_step():
+  """The engine bench.py times (bf16, TMA weight ring) at the benchmark's shapes, B = 16, against
+  the oracle run with the same bf16-rounded in-scan weights: every row is compared at EVERY step
+  up to (and including) the first step at which a sampled latent differs -- after that the two
+  trajectories are different samples of the same model and only the agreement rate is checked."""
+  B, T = 16, 6
+  ocfg = do.tiny_config(**SIZE200M)
+  vals, oracle, tokens, action, reset, deter0, stoch0, gumbel = setup(ocfg, B, T, 3)
+  rounded = dict(vals)
+  for k in ('dyn/dynin0/kernel', 'dyn/dynin1/kernel', 'dyn/dynhid0/kernel', 'dyn/dyngru/kernel',
+            'dyn/obslogit/kernel'):
+    rounded[k] = vals[k].bfloat16().float()
+  w = vals['dyn/obs0/kernel'].clone()
+  w[:ocfg.deter] = w[:ocfg.deter].bfloat16().float()
+  rounded['dyn/obs0/kernel'] = w
+  with torch.no_grad():
+    _, feat = do.Dreamer(ocfg, rounded).observe(
+        dict(deter=deter0, stoch=stoch0), tokens, action, reset, gumbel)
+    hs = hoisted(oracle, ocfg, tokens, action, reset, deter0, stoch0)
+  out, saved, sc = run_kernel(ocfg, vals, scanlib.ENG_BF16, B, T, *hs, deter0, gumbel)
+  assert sc.engine == scanlib.ENG_BF16, 'size200m must run on the TMA engine'
+  same = (out['index'].cpu().long() == feat['stoch'].argmax(-1)).all(-1)          # (B, T)
+  assert float((out['index'].cpu().long() == feat['stoch'].argmax(-1)).float().mean()) > 0.9
+  checked = 0
+  for b in range(B):
+    for t in range(T):
+      # bf16 A operands: 2^-8 relative per product, fp32 accumulation over K <= 3072
+      assert rel(out['deter'][b, t], feat['deter'][b, t]) < 2e-2, (b, t)
+      assert rel(out['logit'][b, t], feat['logit'][b, t]) < 4e-2, (b, t)
+      checked += 1
+      if not bool(same[b, t]):
+        break
+  assert checked >= B * 2, checked
+
+
 def _functional(ocfg, B, T, seed):
   g = torch.Generator().manual_seed(seed)
   return (torch.randn(B, T, ocfg.deter, generator=g),
@@ -117,7 +155,7 @@ def _functional(ocfg, B, T, seed):
           torch.randn(B, T, ocfg.stoch, ocfg.classes, generator=g))
 
 
-@pytest.mark.parametrize('name,over,B,T', [CASES[0], CASES[1], CASES[3]])
+@pytest.mark.parametrize('name,over,B,T', [CASES[0], CASES[1], CASES[3], ('size200m-B16', SIZE200M, 16, 2)])
 def test_backward_fp32_engine_matches_oracle_autograd(name, over, B, T):
   """Gradients of a random linear functional of (deter, logit, stoch) with respect to
   every parameter the scan touches, through emb_rssm_observe_bwd + the host's
