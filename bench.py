@@ -373,7 +373,7 @@ def run_b200(args):
 SWEEP_B = (8, 16, 32, 64, 128)
 SWEEP_T = (16, 32, 64, 128, 256)
 ROW_KINDS = {                      # bytes per stored step, excluding the 20-byte stepid
-    'image': {'image': (np.uint8, IMAGE)},
+    'image': {'image': (np.uint8, IMAGE), 'is_first': (bool, ())},     # Consec reads is_first
     'default': {'image': (np.uint8, IMAGE), 'dyn/deter': (np.float32, (DETER,)),
                 'dyn/stoch': (np.float32, STOCH), 'reward': (np.float32, ()),
                 'action': (np.int32, ()), 'is_first': (bool, ()), 'is_last': (bool, ()),
