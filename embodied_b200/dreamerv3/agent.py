@@ -342,6 +342,17 @@ class Agent(base.Agent):
     return data
 
   def load(self, data, regex=None):
+    """`regex`: restore only the parameters whose name matches (embodied/jax/agent.py:343-358,
+    run/train.py:88 from_checkpoint_regex); optimiser state and counters of a partial load
+    stay as initialised."""
+    if regex:
+      import re
+      pattern = re.compile(regex)
+      keep = {k: v for k, v in data.items() if k in self.store.specs and pattern.match(k)}
+      if not keep:
+        raise KeyError(f'no parameter matches {regex!r}')
+      self.store.load_params(keep)
+      return
     self.store.load_state_dict(data)
     if 'retnorm/lo' in data:
       self.model.ret_lo.copy_(torch.as_tensor(data['retnorm/lo']))

@@ -215,6 +215,16 @@ class ParamStore:
     out['opt/step'] = np.asarray(self.step)
     return out
 
+  def load_params(self, data):
+    """Overwrite the named parameters only (partial restore); a slow copy follows its source."""
+    for n, v in data.items():
+      self.view('master', n).copy_(torch.as_tensor(v))
+      if n.startswith('val/') and ('slow' + n) in self.slow:
+        self.slow['slow' + n].copy_(torch.as_tensor(v))
+    self._cast.clear()
+    self.refresh_low()
+    self.version += 1
+
   def load_state_dict(self, data):
     for n in self.specs:
       self.view('master', n).copy_(torch.as_tensor(data[n]))

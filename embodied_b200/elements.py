@@ -550,7 +550,12 @@ class Config(dict):
       node = nested
       *parents, leaf = key.split(cls.SEP)
       for part in parents:
-        node = node.setdefault(part, {})
+        child = node.get(part)
+        if type(child) is not dict:          # absent, or an empty-mapping leaf (`dummy: {}`)
+          child = node[part] = dict(child) if isinstance(child, dict) else {}
+        node = child
+      if isinstance(value, dict) and not value and isinstance(node.get(leaf), dict):
+        continue                             # an empty mapping never erases a populated one
       node[leaf] = value
     return nested
 

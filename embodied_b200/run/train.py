@@ -30,13 +30,14 @@ from ..core import driver as driverlib
 
 
 class _EpisodeStats:
-  """Vectorised logfn (train.py:31-54): score / length / reward_rate per env,
-  `log/` keys aggregated avg/max/sum."""
+  """Vectorised logfn (train.py:31-54): score / length / reward_rate per env; every scalar
+  `log/<k>` key is aggregated over the episode as `log/<k>/avg|max|sum` (elements.Agg with
+  agg=('avg', 'max', 'sum'), train.py:44-46)."""
 
   def __init__(self, logger, epstats):
     self.logger, self.epstats = logger, epstats
     self.score = self.length = self.changes = self.prev = None
-    self.logs = collections.defaultdict(dict)
+    self.logsum, self.logmax = {}, {}
 
   def __call__(self, trans, n):
     reward = np.asarray(trans['reward'], np.float64)
@@ -56,6 +57,16 @@ class _EpisodeStats:
     self.length += 1
     self.prev = reward
     logkeys = [k for k in trans if k.startswith('log/')]
+    for k in logkeys:
+      value = np.asarray(trans[k], np.float64)
+      assert value.shape == (n,), (k, value.shape)       # scalars per env (train.py:45)
+      if k not in self.logsum:
+        self.logsum[k] = np.zeros(n)
+        self.logmax[k] = np.full(n, -np.inf)
+      self.logsum[k][first] = 0
+      self.logmax[k][first] = -np.inf
+      self.logsum[k] += value
+      self.logmax[k] = np.maximum(self.logmax[k], value)
     for i in np.nonzero(last)[0]:
       self.logger.add(
           {'score': self.score[i], 'length': self.length[i]}, prefix='episode')
@@ -63,7 +74,9 @@ class _EpisodeStats:
       if self.length[i] > 1:
         result['reward_rate'] = self.changes[i] / (self.length[i] - 1)
       for k in logkeys:
-        result[k] = trans[k][i]
+        result[f'{k}/avg'] = self.logsum[k][i] / self.length[i]
+        result[f'{k}/max'] = self.logmax[k][i]
+        result[f'{k}/sum'] = self.logsum[k][i]
       self.epstats.add(result)
 
 
@@ -125,7 +138,8 @@ def train(make_agent, make_replay, make_env, make_stream, make_logger, args):
   cp.replay = replay
   if args.from_checkpoint:
     data = pickle.loads(elements.Path(args.from_checkpoint).read(mode='rb'))
-    agent.load(data['agent'])
+    regex = args.get('from_checkpoint_regex', None) if hasattr(args, 'get') else None
+    agent.load(data['agent'], regex=regex) if regex else agent.load(data['agent'])
   cp.load_or_save()
 
   print('Start training loop')

@@ -103,3 +103,30 @@ def test_bench_two_ranks():
                          nproc=2)
   assert line['n_gpus'] == 2 and line['value'] > 0
   assert 'capture of the train step failed' not in err, err[-2000:]
+
+
+def test_config_level_entry_point_trains(tmp_path):
+  """`python -m embodied_b200.dreamerv3.main --configs size1m ...`: YAML-style blocks and flags ->
+  factories -> run.train on the device, a few hundred env steps with learner updates."""
+  from embodied_b200.dreamerv3 import main as mainlib
+  mainlib.main([
+      '--configs', 'size1m', '--task', 'synthetic_img', '--logdir', str(tmp_path),
+      '--batch_size', '4', '--batch_length', '8', '--report_length', '8', '--replay.size', '5000',
+      '--run.envs', '4', '--run.steps', '400', '--run.train_ratio', '16', '--run.log_every', '1',
+      '--run.report_every', '1000', '--run.save_every', '1000', '--env.synthetic.length', '40'])
+  lines = (tmp_path / 'metrics.jsonl').read_text().strip().splitlines()
+  assert lines
+  last = json.loads(lines[-1])
+  assert any(k.startswith('train/loss') for row in map(json.loads, lines) for k in row), last
+  assert (tmp_path / 'config.yaml').exists() and (tmp_path / 'checkpoint.pkl').exists()
+
+
+def test_partial_restore_by_regex():
+  import test_gpu_dreamer as tg
+  ocfg, _, a = tg.make_pair(seed=1)
+  _, _, b = tg.make_pair(seed=2)
+  blob = a.save()
+  b.load(blob, regex=r'enc/.*')
+  for k in b.store.specs:
+    same = torch.equal(b.store.view('master', k), a.store.view('master', k))
+    assert same == k.startswith('enc/'), k

@@ -130,3 +130,26 @@ def test_run_loop(tmpdir):
     stats = agent.stats()
     assert stats['loads'] == 1
     assert np.allclose(stats['env_steps'], args2.steps, 100, 0.1)
+
+
+def test_episode_stats_aggregate_log_keys():
+  """`log/<k>` scalars become `<k>/avg|max|sum` over the episode (embodied/run/train.py:44-46),
+  reset on is_first, emitted when the episode ends."""
+  from embodied_b200.run import train as trainlib
+
+  class Sink:
+    def __init__(self):
+      self.rows = []
+    def add(self, mapping, prefix=None):
+      self.rows.append((prefix, dict(mapping)))
+  logger, epstats = Sink(), Sink()
+  stats = trainlib._EpisodeStats(logger, epstats)
+  vals = np.array([[1.0, 5.0], [3.0, -2.0], [2.0, 4.0]])       # (t, env)
+  for t in range(3):
+    stats({'reward': np.array([1.0, 0.5 * t]), 'is_first': np.array([t == 0, t == 0]),
+           'is_last': np.array([t == 2, t == 1]), 'log/x': vals[t]}, 2)
+  # env 1 ended at t = 1 (two steps), env 0 at t = 2 (three steps)
+  (_, first), (_, second) = epstats.rows
+  assert first['log/x/sum'] == 3.0 and first['log/x/max'] == 5.0 and first['log/x/avg'] == 1.5
+  assert second['log/x/sum'] == 6.0 and second['log/x/max'] == 3.0 and second['log/x/avg'] == 2.0
+  assert [r[1]['length'] for r in logger.rows] == [2, 3]
