@@ -135,7 +135,8 @@ def test_run_loop(tmpdir):
 def test_episode_stats_aggregate_log_keys():
   """`log/<k>` scalars become `<k>/avg|max|sum` over the episode (embodied/run/train.py:44-46),
   reset on is_first, emitted when the episode ends."""
-  from embodied_b200.run import train as trainlib
+  import importlib
+  trainlib = importlib.import_module("embodied_b200.run.train")
 
   class Sink:
     def __init__(self):
