@@ -62,6 +62,10 @@ def percentiles(x, qs):
   return torch.stack(out)
 
 
+def total_fusable(losses):
+  return all(v.is_cuda for v in losses.values()) and len(losses) <= 16
+
+
 class Model:
 
   def __init__(self, cfg, store):
@@ -384,6 +388,8 @@ class Model:
           *x.shape[:-1], -1).to(f32)
 
   def twohot_pred(self, logits):                             # outs.py:285-302 (symmetric sum)
+    if self.fused_norm and not logits.requires_grad and ops.twohot_supported(logits):
+      return ops.twohot_pred(logits, self.bins)              # one launch
     probs = torch.softmax(logits, -1)
     bins = self.bins
     m = (logits.shape[-1] - 1) // 2
@@ -391,7 +397,12 @@ class Model:
     b1, b2, b3 = bins[:m], bins[m: m + 1], bins[m + 1:]
     return (p2 * b2).sum(-1) + ((p1 * b1).flip(-1) + (p3 * b3)).sum(-1)
 
-  def twohot_loss(self, logits, target):                     # outs.py:311-330
+  def twohot_loss(self, logits, target, target2=None, w2=0.0):   # outs.py:311-330
+    """CE against twohot(target) (+ w2 * CE against twohot(target2): the critic's two terms)."""
+    if self.fused_norm and ops.twohot_supported(logits):
+      return ops.twohot_loss(logits, self.bins, target, target2, w2)     # one launch each way
+    if target2 is not None:
+      return self.twohot_loss(logits, target) + w2 * self.twohot_loss(logits, target2)
     bins, n = self.bins, len(self.bins)
     target = target.detach().to(f32)
     below = (bins <= target[..., None]).sum(-1) - 1
@@ -506,20 +517,22 @@ class Model:
     # replay value loss (agent.py:219-235, repl_loss :449-479)
     boot = ret[:, 0].reshape(B, K)
     vlogits = self.head(inp, 'val', cfg.val_layers, 'logits')
-    val = self.twohot_pred(vlogits)
+    val = self.twohot_pred(vlogits.detach())       # only feeds stop-gradient targets (agent.py:462-470)
     slow = self.twohot_pred(self.slow_value_logits(inp.detach()))
     rret = self.lambda_return(
         obs['is_last'], obs['is_terminal'], obs['reward'].to(f32), val, boot,
         1 - 1 / cfg.horizon, cfg.lam)
     padded = torch.cat([rret, 0 * rret[:, -1:]], 1)
     weight = (~obs['is_last']).to(f32)
-    losses['repval'] = weight[:, :-1] * (
-        self.twohot_loss(vlogits, padded) +
-        cfg.slowreg * self.twohot_loss(vlogits, slow))[:, :-1]
+    losses['repval'] = weight[:, :-1] * self.twohot_loss(vlogits, padded, slow, cfg.slowreg)[:, :-1]
 
     assert set(losses) == set(cfg.scales), (sorted(losses), sorted(cfg.scales))
-    metrics.update({f'loss/{k}': v.detach().mean() for k, v in losses.items()})
-    total = sum(v.mean() * cfg.scales[k] for k, v in losses.items())
+    if self.fused_norm and total_fusable(losses):
+      total, means = ops.loss_sum(losses, cfg.scales)        # one launch (agent.py:237-240)
+      metrics.update({f'loss/{k}': v for k, v in means.items()})
+    else:
+      metrics.update({f'loss/{k}': v.detach().mean() for k, v in losses.items()})
+      total = sum(v.mean() * cfg.scales[k] for k, v in losses.items())
     outs = dict(tokens=tokens, feat=feat, losses=losses, recon=recon,
                 imgdeter=imgdeter, imgstoch=imgstoch, imgact=imgact, ret=ret)
     return total, carry, outs, metrics
@@ -532,7 +545,7 @@ class Model:
       slowval = self.twohot_pred(self.slow_value_logits(inp))
     pol = self.head(inp, 'pol', cfg.pol_layers, 'action/logits')
     vlogits = self.head(inp, 'val', cfg.val_layers, 'logits')
-    val = self.twohot_pred(vlogits).detach()
+    val = self.twohot_pred(vlogits.detach())
     disc = 1 if cfg.contdisc else 1 - 1 / cfg.horizon
     weight = torch.cumprod(disc * con, 1) / disc
     ret = self.lambda_return(torch.zeros_like(con), 1 - con, rew, val, val, disc, cfg.lam)
@@ -544,9 +557,7 @@ class Model:
     losses = {}
     losses['policy'] = weight[:, :-1] * -(logpi * adv + cfg.actent * ent)
     padded = torch.cat([ret, 0 * ret[:, -1:]], 1)
-    losses['value'] = weight[:, :-1] * (
-        self.twohot_loss(vlogits, padded) +
-        cfg.slowreg * self.twohot_loss(vlogits, slowval))[:, :-1]
+    losses['value'] = weight[:, :-1] * self.twohot_loss(vlogits, padded, slowval, cfg.slowreg)[:, :-1]
     ret_normed = (ret - roffset) / rscale
     mets = dict(adv=adv.mean(), rew=rew.mean(), con=con.mean(), ret=ret_normed.mean(),
                 val=val.mean(), weight=weight.mean(), ent=ent.detach().mean())

@@ -613,3 +613,125 @@ def upconv_subpixel(x, w):
   assert k == 5
   weff = (subpixel_fold(w.device) @ w.reshape(25, cin * cout).to(f32)).reshape(4, 9, cin, cout)
   return SubpixelConv.apply(x, weff)
+
+
+# ------------------------------------------------------------------ head losses
+def _losses_lib():
+  lib = _lib.load()
+  if not getattr(lib, '_losses_bound', False):
+    lib.emb_twohot_loss_fwd.argtypes = [_vp, _vp, _vp, _fl, _vp, _vp, _vp, _i64, _i32, _vp]
+    lib.emb_twohot_loss_fwd.restype = ctypes.c_int
+    lib.emb_twohot_loss_bwd.argtypes = [_vp, _vp, _vp, _fl, _vp, _vp, _vp, _vp, _i64, _i32, _vp]
+    lib.emb_twohot_loss_bwd.restype = ctypes.c_int
+    lib.emb_twohot_pred.argtypes = [_vp, _vp, _vp, _i64, _i32, _vp]
+    lib.emb_twohot_pred.restype = ctypes.c_int
+    lib.emb_loss_reduce.argtypes = [ctypes.POINTER(_vp), ctypes.POINTER(_i64), ctypes.POINTER(_fl), _i32,
+                                    _vp, _vp, _vp, _vp]
+    lib.emb_loss_reduce.restype = ctypes.c_int
+    lib._losses_bound = True
+  return lib
+
+
+def twohot_supported(logits):
+  return logits.is_cuda and logits.dtype == f32 and 2 <= logits.shape[-1] <= 1024
+
+
+class TwoHotLoss(torch.autograd.Function):
+  """outs.TwoHot.loss (embodied/jax/outs.py:311-330) for fp32 logits (..., nbins) and one or two
+  stop-gradient targets (...): CE(twohot(t1)) + w2 * CE(twohot(t2)), one launch each way."""
+
+  @staticmethod
+  def forward(ctx, logits, bins, target, target2, w2):
+    lib = _losses_lib()
+    logits = logits.contiguous()
+    lead, nb = logits.shape[:-1], logits.shape[-1]
+    rows = logits.numel() // nb
+    t1 = target.detach().to(f32).contiguous()
+    t2 = None if target2 is None else target2.detach().to(f32).contiguous()
+    assert t1.numel() == rows and (t2 is None or t2.numel() == rows), (logits.shape, target.shape)
+    loss = torch.empty(lead, dtype=f32, device=logits.device)
+    lse = torch.empty(lead, dtype=f32, device=logits.device)
+    stream = torch.cuda.current_stream(logits.device).cuda_stream
+    _lib.check(lib.emb_twohot_loss_fwd(
+        logits.data_ptr(), t1.data_ptr(), None if t2 is None else t2.data_ptr(), float(w2),
+        bins.data_ptr(), loss.data_ptr(), lse.data_ptr(), rows, nb, stream))
+    ctx.save_for_backward(logits, bins, t1, t2, lse)
+    ctx.w2 = float(w2)
+    return loss
+
+  @staticmethod
+  def backward(ctx, gloss):
+    lib = _losses_lib()
+    logits, bins, t1, t2, lse = ctx.saved_tensors
+    nb = logits.shape[-1]
+    rows = logits.numel() // nb
+    gloss = gloss.to(f32).contiguous()
+    glogits = torch.empty_like(logits)
+    stream = torch.cuda.current_stream(logits.device).cuda_stream
+    _lib.check(lib.emb_twohot_loss_bwd(
+        logits.data_ptr(), t1.data_ptr(), None if t2 is None else t2.data_ptr(), ctx.w2, bins.data_ptr(),
+        lse.data_ptr(), gloss.data_ptr(), glogits.data_ptr(), rows, nb, stream))
+    return glogits, None, None, None, None
+
+
+def twohot_loss(logits, bins, target, target2=None, w2=0.0):
+  return TwoHotLoss.apply(logits, bins, target, target2, w2)
+
+
+@torch.no_grad()
+def twohot_pred(logits, bins):
+  """outs.TwoHot.pred (outs.py:285-309); only ever feeds stop-gradient quantities."""
+  lib = _losses_lib()
+  logits = logits.contiguous()
+  nb = logits.shape[-1]
+  pred = torch.empty(logits.shape[:-1], dtype=f32, device=logits.device)
+  stream = torch.cuda.current_stream(logits.device).cuda_stream
+  _lib.check(lib.emb_twohot_pred(logits.data_ptr(), bins.data_ptr(), pred.data_ptr(),
+                                 logits.numel() // nb, nb, stream))
+  return pred
+
+
+_TICKETS = {}
+
+
+class LossSum(torch.autograd.Function):
+  """total = sum_i scale_i * mean(term_i) and the per-term means (dreamerv3/agent.py:237-240) in
+  one launch; the backward pass is one constant fill per term."""
+
+  @staticmethod
+  def forward(ctx, scales, *terms):
+    lib = _losses_lib()
+    dev = terms[0].device
+    terms = [t.to(f32).contiguous() for t in terms]
+    n = len(terms)
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    if key not in _TICKETS:
+      _TICKETS[key] = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.empty(n + 1, dtype=f32, device=dev)
+    ptrs = (_vp * n)(*[t.data_ptr() for t in terms])
+    counts = (_i64 * n)(*[t.numel() for t in terms])
+    sc = (_fl * n)(*[float(s) for s in scales])
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(lib.emb_loss_reduce(ptrs, counts, sc, n, out.data_ptr(), out[n:].data_ptr(),
+                                   _TICKETS[key].data_ptr(), stream))
+    ctx.shapes = [t.shape for t in terms]
+    ctx.scales = [float(s) for s in scales]
+    ctx.mark_non_differentiable(out[:n])
+    return out[n], out[:n]
+
+  @staticmethod
+  def backward(ctx, gtotal, _gmeans):
+    grads = []
+    for shape, scale in zip(ctx.shapes, ctx.scales):
+      numel = 1
+      for s in shape:
+        numel *= s
+      grads.append((gtotal * (scale / numel)).expand(shape))
+    return (None, *grads)
+
+
+def loss_sum(losses, scales):
+  """losses: {name: tensor}; returns (total, {name: mean})."""
+  names = list(losses)
+  total, means = LossSum.apply([scales[k] for k in names], *[losses[k] for k in names])
+  return total, {k: means[i] for i, k in enumerate(names)}

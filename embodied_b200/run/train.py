@@ -80,6 +80,46 @@ class _EpisodeStats:
       self.epstats.add(result)
 
 
+class _MetricFetcher:
+  """Device scalars of the learner -> host numbers, ONE STEP DELAYED like the reference's
+  `pending_mets` (embodied/jax/agent.py:291-298): this call's metrics start an asynchronous copy
+  into pinned memory, the previous call's (long complete) are returned -- the train loop never
+  waits for the update it just enqueued."""
+
+  def __init__(self):
+    self.pending = None
+    self.ring, self.turn = [None, None], 0
+
+  def __call__(self, mets):
+    try:
+      import torch
+    except ImportError:                                   # host-only agents
+      return mets
+    dev = {k: v for k, v in mets.items()
+           if isinstance(v, torch.Tensor) and v.is_cuda and v.numel() == 1}
+    out = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v)
+           for k, v in mets.items() if k not in dev}
+    prev, self.pending = self.pending, None
+    if dev:
+      names = list(dev)
+      vec = torch.stack([dev[k].detach().to(torch.float32).reshape(()) for k in names])
+      buf = self.ring[self.turn]
+      if buf is None or buf.numel() < len(names):
+        buf = self.ring[self.turn] = torch.empty(max(64, len(names)), dtype=torch.float32,
+                                                 pin_memory=True)
+      self.turn ^= 1
+      buf[:len(names)].copy_(vec, non_blocking=True)
+      event = torch.cuda.Event()
+      event.record()
+      self.pending = (names, buf, event)
+    if prev:
+      names, buf, event = prev
+      event.synchronize()
+      host = buf[:len(names)].numpy().copy()
+      out.update({k: host[i] for i, k in enumerate(names)})
+    return out
+
+
 def train(make_agent, make_replay, make_env, make_stream, make_logger, args):
 
   agent = make_agent()
@@ -129,7 +169,8 @@ def train(make_agent, make_replay, make_env, make_stream, make_logger, args):
       train_fps.step(batch_steps)
       if 'replay' in outs:
         replay.update(outs['replay'])
-      train_agg.add(mets, prefix='train')
+      train_agg.add(fetch_metrics(mets), prefix='train')
+  fetch_metrics = _MetricFetcher()
   driver.on_batch(after_step)
 
   cp = elements.Checkpoint(logdir / 'checkpoint.pkl')
@@ -153,7 +194,7 @@ def train(make_agent, make_replay, make_env, make_stream, make_logger, args):
       agg = elements.Agg()
       for _ in range(args.get('consec_report', 1) * args.report_batches):
         carry_report, mets = agent.report(carry_report, next(stream_report))
-        agg.add(mets)
+        agg.add({k: (v.cpu().numpy() if hasattr(v, 'cpu') else v) for k, v in mets.items()})
       logger.add(agg.result(), prefix='report')
 
     if should_log(step):

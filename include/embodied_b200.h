@@ -392,6 +392,29 @@ int emb_pack_tiles(const float* base, const int64_t* slot_off, const int32_t* sl
                    const int32_t* slot_nstride, void* dst, int64_t nslots, int32_t per,
                    int32_t ks_begin, int32_t ks_count, int32_t ks_total, void* stream);
 
+/* Head losses (embodied_b200/csrc/losses.cu).
+ * emb_twohot_loss_*: embodied/jax/outs.py:311-330 TwoHot.loss for fp32 logits [rows][nbins] and one
+ * or two fp32 targets per row (target2 may be NULL; the critic's `ret` + slowreg * `slow value`
+ * terms share one softmax, dreamerv3/agent.py:425-431,468-472):
+ *   loss[r] = CE(twohot(target[r]), logits[r]) + weight2 * CE(twohot(target2[r]), logits[r]);
+ *   lse[r]  = logsumexp(logits[r]) (saved for the backward pass);
+ *   glogits = gloss[r] * ((1 + weight2) softmax - twohot(target) - weight2 twohot(target2)).
+ * bins: fp32 [nbins], ascending (embodied/jax/heads.py:132-144); 2 <= nbins <= 1024.
+ * emb_twohot_pred: TwoHot.pred (outs.py:285-309), the symmetric sum around the middle bin.
+ * emb_loss_reduce: total = sum_i scales[i] * mean(terms[i]) and means[i] (dreamerv3/agent.py:237-240)
+ * in one launch; terms / counts / scales are HOST arrays of n <= 16 entries (device pointers inside
+ * `terms`); ticket: one zero-initialised device word the launch leaves at zero. */
+int emb_twohot_loss_fwd(const float* logits, const float* target, const float* target2, float weight2,
+                        const float* bins, float* loss, float* lse, int64_t rows, int32_t nbins,
+                        void* stream);
+int emb_twohot_loss_bwd(const float* logits, const float* target, const float* target2, float weight2,
+                        const float* bins, const float* lse, const float* gloss, float* glogits,
+                        int64_t rows, int32_t nbins, void* stream);
+int emb_twohot_pred(const float* logits, const float* bins, float* pred, int64_t rows, int32_t nbins,
+                    void* stream);
+int emb_loss_reduce(const float* const* terms, const int64_t* counts, const float* scales, int32_t n,
+                    float* means, float* total, uint32_t* ticket, void* stream);
+
 /* The 5x5 SAME convolutions of the dreamerv3 encoder / decoder on 64..256 channels
  * (dreamerv3/rssm.py:233-240 conv -> pool -> norm -> act; :336-352 up-sample -> conv -> norm;
  * embodied/jax/nets.py:298-323 Conv2D, NHWC activations, HWIO kernels) as an implicit GEMM on

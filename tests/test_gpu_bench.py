@@ -128,5 +128,6 @@ def test_partial_restore_by_regex():
   blob = a.save()
   b.load(blob, regex=r'enc/.*')
   for k in b.store.specs:
-    same = torch.equal(b.store.view('master', k), a.store.view('master', k))
-    assert same == k.startswith('enc/'), k
+    if k.endswith('/kernel'):               # biases / scales start identical (zeros / ones)
+      same = torch.equal(b.store.view('master', k), a.store.view('master', k))
+      assert same == k.startswith('enc/'), k
