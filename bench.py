@@ -162,7 +162,9 @@ class Loop:
       self.agent = dreamerv3.Agent(
           env.obs_space, env.act_space,
           dreamerv3.config.make(size, compute_dtype=dtype, seed=0,
-                                graph=os.environ.get('EMB_GRAPH', 'auto')))
+                                graph=os.environ.get('EMB_GRAPH', 'auto'),
+                                grad_buckets={'off': False, 'on': True}.get(
+                                    os.environ.get('EMB_GRAD_BUCKETS', 'auto'), 'auto')))
     base = embodied.streams.Stateless(self.replay.sample, B, 'train')
     self.stream = iter(embodied.streams.Consec(
         base, length=T, consec=1, prefix=PREFIX, strict=True, contiguous=True))

@@ -44,7 +44,7 @@ EXPORTS = (
     'emb_driver_stage_obs', 'emb_driver_scatter_mask_actions',
     # learner (bound where they are used: dreamerv3/scan.py, ops.py, optim.py)
     'emb_rssm_observe_fwd', 'emb_rssm_observe_bwd', 'emb_rssm_tma_fits', 'emb_rssm_legacy_fits', 'emb_rmsnorm_act_fwd',
-    'emb_rmsnorm_act_bwd', 'emb_rssm_kl_fwd', 'emb_rssm_kl_bwd', 'emb_lambda_return', 'emb_onehot_sample', 'emb_opt_agc_rms_momentum', 'emb_opt_agc_rms_momentum_cast', 'emb_maxpool2_nhwc_fwd',
+    'emb_rmsnorm_act_bwd', 'emb_rssm_kl_fwd', 'emb_rssm_kl_bwd', 'emb_lambda_return', 'emb_onehot_sample', 'emb_opt_agc_rms_momentum', 'emb_opt_agc_rms_momentum_cast', 'emb_allreduce_bucket_update', 'emb_maxpool2_nhwc_fwd',
     'emb_maxpool2_nhwc_bwd', 'emb_upsample2_nhwc_fwd', 'emb_upsample2_nhwc_bwd',
     'emb_rmsnorm_grouped_fwd', 'emb_gru_gates_fwd', 'emb_pack_tiles', 'emb_conv_patches_nhwc', 'emb_conv_tapsum_nhwc', 'emb_probe_read', 'emb_twohot_loss_fwd', 'emb_twohot_loss_bwd', 'emb_twohot_pred', 'emb_loss_reduce', 'emb_conv5x5_nhwc_tc', 'emb_conv5x5_wgrad_tc', 'emb_conv_nhwc_tc', 'emb_conv_wgrad_tc', 'emb_event_create', 'emb_event_record', 'emb_event_elapsed_ms', 'emb_event_destroy',
 )

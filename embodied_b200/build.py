@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
     done = list(pool.map(lambda s: _compile(s, force, verbose), SOURCES))
   if verbose:
     print('\n'.join(log for _, log in done if log))
-  cmd = [_nvcc(), '-shared', '-o', str(LIB), *[str(o) for o, _ in done]]
+  cmd = [_nvcc(), '-shared', '-o', str(LIB), *[str(o) for o, _ in done], '-ldl']
   proc = subprocess.run(cmd, capture_output=True, text=True)
   if proc.returncode != 0:
     raise RuntimeError(f'link failed:\n{proc.stdout}\n{proc.stderr}')

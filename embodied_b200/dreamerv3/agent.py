@@ -75,6 +75,14 @@ class Agent(base.Agent):
     if torch.distributed.is_available() and torch.distributed.is_initialized():
       self.world = torch.distributed.get_world_size()
       self.rank = torch.distributed.get_rank()
+    # bucketed gradient exchange + optimiser under the backward pass (exchange.py): on by default
+    # in the bf16 (benchmark) mode and whenever there is more than one rank
+    want = cfg.get('grad_buckets', 'auto')
+    self.exchange = None
+    if self.opt.fused and (want is True or (want == 'auto' and (self.world > 1 or self.cd != f32))):
+      from . import exchange as exchangelib
+      comm = exchangelib.NcclComm(self.device) if self.world > 1 else None
+      self.exchange = exchangelib.GradExchange(self.store, self.opt, comm)
     self.gen = torch.Generator(device=self.device)
     self.gen.manual_seed(cfg.seed * 1000003 + self.rank)     # transform.py:84-85 fold_in(rank)
     self.updates = 0
@@ -180,12 +188,19 @@ class Agent(base.Agent):
     self.store.begin_step()
     self.store.grad.zero_()
     total, carry, outs, metrics = self.model.loss(carry, obs, prevact, noise, update=True)
-    total.backward()
+    if self.exchange is not None:
+      self.exchange.begin()
+      total.backward()
+      metrics = dict(metrics)
+      metrics['opt/grad_norm'] = self.exchange.finish()     # all-reduce + optimiser ran underneath
+    else:
+      total.backward()
     return total, carry, outs, metrics, stepid
 
   def _apply(self, total, carry, outs, metrics, stepid, data):
     metrics = dict(metrics)
-    metrics['opt/grad_norm'] = self.opt.launch()
+    if self.exchange is None:
+      metrics['opt/grad_norm'] = self.opt.launch()
     self.opt.update_slow()
     self.store.begin_step()
     metrics['loss'] = total
@@ -197,7 +212,7 @@ class Agent(base.Agent):
     return carry, replay, metrics
 
   def _allreduce(self):
-    if self.world > 1:
+    if self.world > 1 and self.exchange is None:
       torch.distributed.all_reduce(self.store.grad, op=torch.distributed.ReduceOp.AVG)
 
   def train(self, carry, data, noise=None):                  # agent.py:137-154, opt.py:31-81

@@ -46,7 +46,7 @@ class Optimizer:
     self._lib = _lib
     self.lib = _lib.load()
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
-    self.lib.emb_opt_agc_rms_momentum_cast.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp]
+    self.lib.emb_opt_agc_rms_momentum_cast.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp, i32, vp, vp, vp, vp]
     self.lib.emb_opt_agc_rms_momentum_cast.restype = ctypes.c_int
     rows = []
     for ti, n in enumerate(names):
@@ -58,6 +58,10 @@ class Optimizer:
     self.nchunks, self.ntensors = len(rows), len(names)
     self.chunks = torch.from_numpy(table.view(np.uint8).copy()).to(st.device)
     self.norms = torch.zeros(2 * len(names), dtype=torch.float32, device=st.device)
+    # deterministic per-tensor norms: per-chunk partial sums + the first chunk of every tensor
+    self.partials = torch.zeros(2 * len(rows), dtype=torch.float32, device=st.device)
+    first = np.searchsorted(table['tensor'], np.arange(len(names) + 1)).astype(np.int32)
+    self.tensor_first = torch.from_numpy(first).to(st.device)
     cfg = self.cfg
     self.hyper = torch.tensor(
         [0, 0, 0, cfg.beta1, cfg.beta2, cfg.eps, cfg.agc, cfg.pmin],
@@ -104,7 +108,7 @@ class Optimizer:
           st.grad.data_ptr(), st.master.data_ptr(), st.nu.data_ptr(), st.mu.data_ptr(),
           None if low is None else low.data_ptr(),
           self.chunks.data_ptr(), self.nchunks, self.norms.data_ptr(), self.ntensors,
-          self.hyper.data_ptr(), stream))
+          self.hyper.data_ptr(), self.partials.data_ptr(), self.tensor_first.data_ptr(), stream))
       if low is not None:
         st.low_is_fresh()
       return self.norms[0::2].sum().sqrt()

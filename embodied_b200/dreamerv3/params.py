@@ -90,14 +90,16 @@ class _CastParam(torch.autograd.Function):
   (what the cast's backward + AccumulateGrad would do in two kernels)."""
 
   @staticmethod
-  def forward(ctx, leaf, low, grad):
-    ctx.grad = grad
+  def forward(ctx, leaf, low, grad, store, name):
+    ctx.grad, ctx.store, ctx.name = grad, store, name
     return low.view(low.shape)
 
   @staticmethod
   def backward(ctx, g):
     ctx.grad.add_(g)
-    return None, None, None
+    if ctx.store.on_grad is not None:         # bucketed exchange: this tensor's gradient is final
+      ctx.store.on_grad(ctx.name)
+    return None, None, None, None, None
 
 
 class ParamStore:
@@ -130,9 +132,12 @@ class ParamStore:
     # autograd leaves: float32 views of `master` whose .grad are views of
     # `grad`, so backward accumulates straight into the flat gradient buffer.
     self.w = {}
+    self.on_grad = None       # callback(name) when a tensor's gradient has been accumulated
     for name in names:
       leaf = self._view(self.master, name).requires_grad_(True)
       leaf.grad = self._view(self.grad, name)
+      leaf.register_post_accumulate_grad_hook(
+          lambda p, n=name: self.on_grad(n) if self.on_grad is not None else None)
       self.w[name] = leaf
     self._cast = {}
     self.low, self._low_seen = None, -1      # flat compute-dtype copy of master (get())
@@ -180,7 +185,7 @@ class ParamStore:
         self.refresh_low()
       low = self._view(self.low, name)
       if tracked:
-        low = _CastParam.apply(self.w[name], low, self._view(self.grad, name))
+        low = _CastParam.apply(self.w[name], low, self._view(self.grad, name), self, name)
       hit = self._cast[(name, tracked)] = low
     return hit
 

@@ -319,14 +319,31 @@ typedef struct emb_opt_chunk {
 int emb_opt_agc_rms_momentum(const float* grad, float* param, float* nu, float* mu,
                              const emb_opt_chunk* chunks, int32_t nchunks,
                              float* norms, int32_t ntensors, const float* hyper,
-                             void* stream);
+                             float* partials, const int32_t* tensor_first, void* stream);
 /* Same update; additionally writes the new parameters rounded to bf16 into the flat
  * buffer `param_bf16` (same element offsets; NULL = skip) -- the compute-dtype copy
  * the next forward pass reads (embodied/jax/nets.py:243 casts parameters at use). */
 int emb_opt_agc_rms_momentum_cast(const float* grad, float* param, float* nu, float* mu,
                                   void* param_bf16, const emb_opt_chunk* chunks, int32_t nchunks,
                                   float* norms, int32_t ntensors, const float* hyper,
-                                  void* stream);
+                                  float* partials, const int32_t* tensor_first, void* stream);
+/* partials: DEVICE scratch, 2 floats per chunk; tensor_first: DEVICE int32 [ntensors + 1], index of
+ * every tensor's first chunk.  The per-tensor norms are summed chunk by chunk in a fixed order (no
+ * atomics): data-parallel ranks that hold identical gradients compute bit-identical updates. */
+
+/* One gradient bucket end to end on one stream (embodied/jax/opt.py:52-54 pmean + :109-164 chain):
+ * ncclAllReduce(avg) of grad[elem_begin, elem_begin + elem_count) in place over `nccl_comm`
+ * (an ncclComm_t created by the host; NULL = single process, no exchange), then
+ * emb_opt_agc_rms_momentum_cast restricted to the bucket's tensors: `chunks` / `nchunks` are the
+ * bucket's slice of the chunk table (chunk.begin / chunk.tensor stay GLOBAL offsets / indices),
+ * norms[2*tensor_begin ... ) of its tensor_count tensors are reset and refilled.  Launched from
+ * the backward pass as soon as the bucket's gradients are complete, on a side stream. */
+int emb_allreduce_bucket_update(void* nccl_comm, float* grad, float* param, float* nu, float* mu,
+                                void* param_bf16, int64_t elem_begin, int64_t elem_count,
+                                const emb_opt_chunk* chunks, int32_t nchunks, float* norms,
+                                int32_t tensor_begin, int32_t tensor_count, const float* hyper,
+                                float* partials, const int32_t* tensor_first, int32_t chunk_begin,
+                                void* stream);
 
 /* Spatial glue of the dreamerv3 encoder / decoder on NHWC tensors, one HBM pass
  * each (dreamerv3/rssm.py:239-240 2x2 max-pool; :336,349 nearest x2 up-sampling).
