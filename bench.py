@@ -212,6 +212,47 @@ class Loop:
     self.learn()
 
 
+def conv_lines(torch, cfg, flush):
+  """The tcgen05 convolution kernels (csrc/conv_tc.cu) at this model's layer shapes, B*T = 1024
+  images: each launch timed alone with CUDA events after the timed region (the captured train
+  step replays ~50 of them back to back; a stopwatch node around each would perturb the graph).
+  Tensor-bound: achieved = 2 * pixels * taps * Cin * Cout / time against the measured bf16 peak."""
+  from embodied_b200.dreamerv3 import ops
+  try:
+    peak = float(json.load(open(ROOT / 'MEASURED_PEAKS.json'))['bf16_tflops'])
+    src = 'measured burst (MEASURED_PEAKS.json)'
+  except Exception:
+    peak, src = 1590.0, 'fallback (B200_PROFILING.md)'
+  depths = [cfg.depth * m for m in cfg.mults]
+  n = B * T
+  res = cfg.image[0]
+  layers = []
+  for i in range(1, len(depths)):                     # encoder: conv on the pooled grid of stage i - 1
+    layers.append((f'enc/cnn{i} fwd', res >> i, depths[i - 1], depths[i], 5))
+  out = []
+  for name, hw, cin, cout, k in layers:
+    x = torch.randn((n, hw, hw, cin), device='cuda').to(torch.bfloat16)
+    if not ops.conv_tc_supported(x, cin, cout, k):
+      continue
+    wp = ops.pack_conv_weight((torch.randn((k, k, cin, cout), device='cuda') / 50).to(torch.bfloat16))
+    for _ in range(3):
+      ops.conv_tc(x, wp, k=k)
+    ts = []
+    for _ in range(5):
+      flush.zero_()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record(); ops.conv_tc(x, wp, k=k); b.record()
+      torch.cuda.synchronize()
+      ts.append(a.elapsed_time(b))
+    t = float(np.median(ts)) * 1e-3
+    flops = 2.0 * n * hw * hw * k * k * cin * cout
+    out.append({'kernel': f'conv_tc_kernel ({name}, {hw}x{hw}, {cin}->{cout}, {n} images)',
+                'bound': 'tensor', 'achieved': flops / t / 1e12, 'peak': peak, 'peak_source': src,
+                'unit': 'TFLOP/s', 'frac': flops / t / 1e12 / peak, 'us_per_launch': t * 1e6,
+                'launches_timed': 5, 'timed': 'alone, after the timed region', 'traffic': None})
+  return out
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -322,15 +363,29 @@ def run_b200(args):
                                NCU_TRAFFIC.get('rssm_bwd') if known else None))
     kernels.append(kernel_line('rssm_fwd', 'rssm_fwd_kernel (emb_rssm_observe_fwd, TMA weight ring, B=16 T=64)', wbytes_fwd,
                                NCU_TRAFFIC.get('rssm_fwd') if known else None))
+  if args.agent != 'feed' and args.dtype == 'bfloat16':
+    kernels += conv_lines(torch, loop.agent.cfg, flush)
   kernels = [k for k in kernels if k]
   # the roofline line is the hand-written kernel with the largest share of the step
   per_step = {'rows_kernel': TRAINS_PER_STEP, 'rssm_bwd_kernel': TRAINS_PER_STEP,
               'rssm_fwd_kernel': TRAINS_PER_STEP}
-  share = lambda k: k['us_per_launch'] * per_step[k['kernel'].split()[0]] * args.steps
+  share = lambda k: k['us_per_launch'] * per_step.get(k['kernel'].split()[0], 0) * args.steps
   roofline = max(kernels, key=share)
   for k in kernels:
-    k['share_of_step'] = share(k) * 1e-6 / t_dev
+    if k['kernel'].split()[0] in per_step:
+      k['share_of_step'] = share(k) * 1e-6 / t_dev
 
+  exchange = None
+  ex = getattr(loop.agent, 'exchange', None)
+  if ex is not None:
+    tail = [t for k, t in prof if k == 'exchange_tail']
+    exchange = {
+        'buckets': [{'group': b['group'], 'MB': round(b['elem_count'] * 4 / 1e6, 1)} for b in ex.buckets],
+        'payload_MB_per_update': round(sum(b['elem_count'] for b in ex.buckets) * 4 / 1e6, 1),
+        'exposed_ms_per_update': (float(np.mean([max(t, 0.0) for t in tail])) * 1e-3 if tail else None),
+        'note': 'all-reduce (avg, own NCCL communicator) + optimiser per bucket on a side stream under '
+                'the backward pass; exposed = side-stream end minus backward end, CUDA events inside '
+                'the captured graph, rank 0'}
   env_steps = world * NENVS * args.steps
   h2d = NENVS * (12288 + 4 + 3 + 20 + 8) + TRAINS_PER_STEP * (B * L * 8 + B * T * 8)
   d2h = NENVS * 4 + 4
@@ -354,7 +409,7 @@ def run_b200(args):
               'ms_per_step': t_e2e / args.steps * 1e3,
               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
       'gpu_launches': launches,
-      'roofline': roofline, 'kernels': kernels,
+      'roofline': roofline, 'kernels': kernels, 'exchange': exchange,
       'clocks': clk,
   }
   if rank == 0:

@@ -155,7 +155,15 @@ class GradExchange:
       # the autograd graph changed (e.g. another batch signature): learn again next step
       self.expected = None
     self.active = False
-    torch.cuda.current_stream(self.store.device).wait_stream(self.side)
+    main = torch.cuda.current_stream(self.store.device)
+    # bench.py: how long the main stream will sit in the join below = the part of the exchange +
+    # update that the backward pass did NOT hide (side-stream end minus backward end)
+    from . import scan as scanlib
+    watch = scanlib._graph_timer('exchange_tail')
+    if watch:
+      watch.start(main.cuda_stream)
+      watch.stop(self.side.cuda_stream)
+    main.wait_stream(self.side)
     if self.store.compute_dtype == torch.bfloat16:
       self.store.low_is_fresh()
     return self.opt.norms[0::2].sum().sqrt()
