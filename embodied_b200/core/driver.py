@@ -246,10 +246,20 @@ class Driver:
           views[k][i] = v
     logs = {k: np.stack(v) for k, v in logs.items()}
     obs_keys = [k for k in obs_list[0] if not k.startswith('log/')]
+    # the host half of the reference agent's input checks (embodied/jax/agent.py:223-227): the
+    # staged block is still host memory here, and only floating-point keys can be non-finite
+    for k in obs_keys:
+      if views[k].dtype.kind == 'f':
+        assert np.isfinite(views[k][:n]).all(), (k, 'non-finite observation')
     obs_dev = replay.stage_obs(batch, obs_keys)
     self.carry, acts, outs = policy(self.carry, obs_dev, **self.kwargs)
     assert all(k not in acts for k in outs), (list(outs), list(acts))
     host_acts = replay.commit_batch(batch, acts, outs)
+    for k, v in host_acts.items():           # jax/agent.py:254-259 on the masked host copy
+      if v.dtype.kind in 'iu':
+        assert (v >= 0).all(), (k, 'negative discrete action')
+      elif v.dtype.kind == 'f':
+        assert np.isfinite(v).all(), (k, 'non-finite action')
     is_last = views['is_last'][:n].copy()
     self.acts = {**host_acts, 'reset': is_last}
     generic = [fn for fn in self.callbacks if fn is not replay]

@@ -14,12 +14,21 @@
 //
 // Everything here is byte/integer exact; the only arithmetic is the typed
 // multiply of Driver._mask and float(u8)/255-0.5 (IEEE fp32 divide, no FMA).
+//
+// Two engines for the big units:
+//   rows_tma_kernel (default): one elected lane per CTA drives a 4-stage shared-memory ring with
+//     TMA bulk copies -- cp.async.bulk global -> shared (mbarrier complete_tx), then shared ->
+//     global (bulk_group) -- two loads and up to two stores in flight per CTA, three CTAs per SM
+//     (192 KiB in flight per SM without a single register); the other seven warps convert the
+//     u8 -> f32 normalised copy out of the staged tile (stage_obs) and run the small units;
+//   rows_kernel: register-staged ld.global.nc / st.global (EMB_ROWS_TMA=0).
 
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -153,58 +162,12 @@ __device__ __forceinline__ uint32_t dtype_size(uint32_t dtype) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads)
-rows_kernel(const __grid_constant__ Table tab,
-            const int64_t* __restrict__ src_rows,
-            const int64_t* __restrict__ dst_rows,
-            int64_t nrows, int32_t window) {
-  const uint64_t big_units = (uint64_t)nrows * tab.big_units_per_row;
-  const uint64_t total = big_units + tab.small_units;
-  for (uint64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
-    if (unit < big_units) {
-      // ---------------- big path: one 16 KiB slice of one row of one key
-      const int64_t r = (int64_t)(unit / tab.big_units_per_row);
-      const uint32_t j = (uint32_t)(unit % tab.big_units_per_row);
-      uint32_t ki = 0;
-      while (ki + 1 < tab.nbig && tab.k[ki + 1].unit_begin <= j) ++ki;
-      const DevKey& key = tab.k[ki];
-      const int64_t sr = src_rows ? src_rows[r] : r;
-      const int64_t dr = dst_rows ? dst_rows[r] : r;
-      if (sr < 0 || dr < 0) continue;
-      const uint32_t off = (j - key.unit_begin) * kBigSlice;
-      const uint32_t nvec = (min(key.row_bytes - off, kBigSlice)) >> 4;
-      const uint4* s = reinterpret_cast<const uint4*>(
-          key.src + (uint64_t)sr * key.src_stride + off);
-      uint4* d = key.dst ? reinterpret_cast<uint4*>(
-          key.dst + (uint64_t)dr * key.dst_stride + off) : nullptr;
-      uint8_t* d2 = key.dst2 ? key.dst2 + (uint64_t)r * key.dst2_stride : nullptr;
-      const bool norm = key.op == EMB_OP_NORM_U8_F32;
-      // 4 independent 16-byte loads per thread before the stores (64 B/thread,
-      // 16 KiB per CTA iteration in flight).
-      uint4 v[4];
-      const uint32_t t = threadIdx.x;
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = t + u * kThreads;
-        if (i < nvec) v[u] = ld_stream(s + i);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t i = t + u * kThreads;
-        if (i < nvec) {
-          if (d) st_stream(d + i, v[u]);
-          if (d2) {
-            if (norm) {
-              store_norm16(reinterpret_cast<float*>(d2) + (off + i * 16), v[u]);
-            } else {
-              st_stream(reinterpret_cast<uint4*>(d2 + off) + i, v[u]);
-            }
-          }
-        }
-      }
-    } else {
-      // ---------------- small path: 1024 (row, vector) elements of one key
-      const uint32_t su = (uint32_t)(unit - big_units);
+// ---------------- small path: 1024 (row, vector) elements of one key, by `nthreads` threads
+__device__ __forceinline__ void small_unit(const Table& tab, uint32_t su, const int64_t* src_rows,
+                                           const int64_t* dst_rows, int64_t nrows, int32_t window,
+                                           uint32_t tid, uint32_t nthreads) {
+  {
+    {
       uint32_t ki = tab.nbig;
       const uint32_t kend = tab.nbig + tab.nsmall;
       while (ki + 1 < kend && tab.k[ki + 1].unit_begin <= su) ++ki;
@@ -212,8 +175,8 @@ rows_kernel(const __grid_constant__ Table tab,
       const uint64_t base = (uint64_t)(su - key.unit_begin) * kSmallElems;
       const uint64_t nelem = (uint64_t)nrows * key.vecs_per_row;
 #pragma unroll 1
-      for (uint32_t u = 0; u < kSmallElems / kThreads; ++u) {
-        const uint64_t e = base + threadIdx.x + u * kThreads;
+      for (uint32_t el = tid; el < kSmallElems; el += nthreads) {
+        const uint64_t e = base + el;
         if (e >= nelem) break;
         const int64_t r = (int64_t)(e / key.vecs_per_row);
         const uint32_t c = (uint32_t)(e % key.vecs_per_row) * key.vec;
@@ -271,6 +234,205 @@ rows_kernel(const __grid_constant__ Table tab,
         }
       }
     }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+rows_kernel(const __grid_constant__ Table tab,
+            const int64_t* __restrict__ src_rows,
+            const int64_t* __restrict__ dst_rows,
+            int64_t nrows, int32_t window) {
+  const uint64_t big_units = (uint64_t)nrows * tab.big_units_per_row;
+  const uint64_t total = big_units + tab.small_units;
+  for (uint64_t unit = blockIdx.x; unit < total; unit += gridDim.x) {
+    if (unit < big_units) {
+      // ---------------- big path: one 16 KiB slice of one row of one key
+      const int64_t r = (int64_t)(unit / tab.big_units_per_row);
+      const uint32_t j = (uint32_t)(unit % tab.big_units_per_row);
+      uint32_t ki = 0;
+      while (ki + 1 < tab.nbig && tab.k[ki + 1].unit_begin <= j) ++ki;
+      const DevKey& key = tab.k[ki];
+      const int64_t sr = src_rows ? src_rows[r] : r;
+      const int64_t dr = dst_rows ? dst_rows[r] : r;
+      if (sr < 0 || dr < 0) continue;
+      const uint32_t off = (j - key.unit_begin) * kBigSlice;
+      const uint32_t nvec = (min(key.row_bytes - off, kBigSlice)) >> 4;
+      const uint4* s = reinterpret_cast<const uint4*>(
+          key.src + (uint64_t)sr * key.src_stride + off);
+      uint4* d = key.dst ? reinterpret_cast<uint4*>(
+          key.dst + (uint64_t)dr * key.dst_stride + off) : nullptr;
+      uint8_t* d2 = key.dst2 ? key.dst2 + (uint64_t)r * key.dst2_stride : nullptr;
+      const bool norm = key.op == EMB_OP_NORM_U8_F32;
+      // 4 independent 16-byte loads per thread before the stores (64 B/thread,
+      // 16 KiB per CTA iteration in flight).
+      uint4 v[4];
+      const uint32_t t = threadIdx.x;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = t + u * kThreads;
+        if (i < nvec) v[u] = ld_stream(s + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = t + u * kThreads;
+        if (i < nvec) {
+          if (d) st_stream(d + i, v[u]);
+          if (d2) {
+            if (norm) {
+              store_norm16(reinterpret_cast<float*>(d2) + (off + i * 16), v[u]);
+            } else {
+              st_stream(reinterpret_cast<uint4*>(d2 + off) + i, v[u]);
+            }
+          }
+        }
+      }
+    } else {
+      small_unit(tab, (uint32_t)(unit - big_units), src_rows, dst_rows, nrows, window, threadIdx.x,
+                 kThreads);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ TMA engine
+constexpr int kStagesT = 4;                  // 16 KiB stages per CTA
+constexpr int kAhead = 2;                    // loads issued ahead of the store cursor
+constexpr int kWorkers = kThreads - 32;      // warps 1..7
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "RW_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra RW_DONE;\n"
+      "bra RW_LOOP;\n"
+      "RW_DONE:\n"
+      "}\n" :: "r"(smem_u32(b)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :: "l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+
+struct BigUnit {        // one 16 KiB slice of one row of one big key
+  const uint8_t* src;
+  uint8_t* dst;
+  uint8_t* dst2;
+  uint32_t bytes;
+  uint32_t off;
+  bool norm, live;
+};
+
+__device__ __forceinline__ BigUnit big_unit(const Table& tab, uint64_t unit, const int64_t* src_rows,
+                                            const int64_t* dst_rows) {
+  BigUnit u;
+  const int64_t r = (int64_t)(unit / tab.big_units_per_row);
+  const uint32_t j = (uint32_t)(unit % tab.big_units_per_row);
+  uint32_t ki = 0;
+  while (ki + 1 < tab.nbig && tab.k[ki + 1].unit_begin <= j) ++ki;
+  const DevKey& key = tab.k[ki];
+  const int64_t sr = src_rows ? src_rows[r] : r;
+  const int64_t dr = dst_rows ? dst_rows[r] : r;
+  u.live = sr >= 0 && dr >= 0;
+  u.off = (j - key.unit_begin) * kBigSlice;
+  u.bytes = min(key.row_bytes - u.off, kBigSlice);
+  u.norm = key.op == EMB_OP_NORM_U8_F32;
+  u.src = key.src + (uint64_t)(u.live ? sr : 0) * key.src_stride + u.off;
+  u.dst = key.dst ? key.dst + (uint64_t)(u.live ? dr : 0) * key.dst_stride + u.off : nullptr;
+  u.dst2 = key.dst2 ? key.dst2 + (uint64_t)r * key.dst2_stride : nullptr;
+  return u;
+}
+
+__global__ void __launch_bounds__(kThreads)
+rows_tma_kernel(const __grid_constant__ Table tab, const int64_t* __restrict__ src_rows,
+                const int64_t* __restrict__ dst_rows, int64_t nrows, int32_t window, int has_norm) {
+  extern __shared__ __align__(128) uint8_t ring[];          // kStagesT x 16 KiB, then the barriers
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + kStagesT * kBigSlice);
+  uint64_t* wdone = full + kStagesT;                         // workers finished converting a stage
+  const uint64_t big_units = (uint64_t)nrows * tab.big_units_per_row;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kStagesT; ++i) { mbar_init(&full[i], 1); mbar_init(&wdone[i], kWorkers / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // this CTA's big units: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const uint64_t mine = big_units > blockIdx.x ? (big_units - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    // ---------------------------------------------------------- the copy engine (one lane)
+    uint64_t loaded = 0;
+    for (uint64_t k = 0; k < mine; ++k) {
+      // keep kAhead loads in front of the store cursor; a stage is reused once the bulk store
+      // that read it has drained (at most kStagesT - kAhead - 1 younger stores pending) and,
+      // for normalised keys, once the workers are done with it
+      while (loaded < mine && loaded < k + kAhead) {
+        const int st = (int)(loaded % kStagesT);
+        if (loaded >= kStagesT) {
+          bulk_wait_read<kStagesT - kAhead - 1>();
+          if (has_norm) mbar_wait(&wdone[st], (uint32_t)((loaded / kStagesT - 1) & 1));
+        }
+        const BigUnit u = big_unit(tab, blockIdx.x + loaded * gridDim.x, src_rows, dst_rows);
+        if (u.live) {
+          mbar_expect_tx(&full[st], u.bytes);
+          bulk_g2s(ring + st * kBigSlice, u.src, u.bytes, &full[st]);
+        } else {
+          mbar_arrive(&full[st]);                            // evicted row: nothing to move
+        }
+        ++loaded;
+      }
+      const int st = (int)(k % kStagesT);
+      const BigUnit u = big_unit(tab, blockIdx.x + k * gridDim.x, src_rows, dst_rows);
+      mbar_wait(&full[st], (uint32_t)((k / kStagesT) & 1));
+      if (u.live) {
+        if (u.dst) bulk_s2g(u.dst, ring + st * kBigSlice, u.bytes);
+        if (u.dst2 && !u.norm) bulk_s2g(u.dst2 + u.off, ring + st * kBigSlice, u.bytes);
+      }
+      bulk_commit();
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every store has completed
+  } else if (threadIdx.x >= 32) {
+    const uint32_t tid = threadIdx.x - 32;
+    if (has_norm) {
+      // ------------------------------------------------ workers: u8 -> f32 out of the staged tile
+      for (uint64_t k = 0; k < mine; ++k) {
+        const int st = (int)(k % kStagesT);
+        const BigUnit u = big_unit(tab, blockIdx.x + k * gridDim.x, src_rows, dst_rows);
+        mbar_wait(&full[st], (uint32_t)((k / kStagesT) & 1));
+        if (u.live && u.norm && u.dst2) {
+          const uint4* tile = reinterpret_cast<const uint4*>(ring + st * kBigSlice);
+          float* out = reinterpret_cast<float*>(u.dst2) + u.off;
+          for (uint32_t i = tid; i < (u.bytes >> 4); i += kWorkers) store_norm16(out + i * 16, tile[i]);
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&wdone[st]);
+      }
+    }
+    // ---------------------------------------------------------------- small units
+    for (uint64_t su = blockIdx.x; su < tab.small_units; su += gridDim.x)
+      small_unit(tab, (uint32_t)su, src_rows, dst_rows, nrows, window, tid, kWorkers);
   }
 }
 
@@ -370,6 +532,34 @@ int launch(const emb_key_t* keys, int nkeys, const int64_t* src_rows,
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       return emb::fail_cuda(who);
     g_sm_count = sms;
+  }
+  static int use_tma = -1;
+  if (use_tma < 0) {
+    const char* e = getenv("EMB_ROWS_TMA");
+    use_tma = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_tma && nbig > 0) {
+    // TMA engine: three CTAs per SM (64 KiB ring each); every big slice is a 16-byte multiple
+    // (vec == 16 was required to classify the key as big)
+    int has_norm = 0;
+    for (uint32_t i = 0; i < nbig; ++i) has_norm |= big[i].op == EMB_OP_NORM_U8_F32;
+    const size_t smem = (size_t)kStagesT * kBigSlice + 2 * kStagesT * sizeof(uint64_t);
+    static bool attr = false;
+    if (!attr) {
+      if (cudaFuncSetAttribute((const void*)rows_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem) != cudaSuccess)
+        return emb::fail_cuda(who);
+      attr = true;
+    }
+    uint64_t grid = (uint64_t)g_sm_count * 3;
+    const uint64_t big_total = (uint64_t)nrows * big_units;
+    const uint64_t want = big_total > small_units ? big_total : small_units;
+    if (want < grid) grid = want;
+    rows_tma_kernel<<<(unsigned)grid, kThreads, smem, (cudaStream_t)stream>>>(
+        tab, src_rows, dst_rows, nrows, window, has_norm);
+    emb::count_launch();
+    if (cudaPeekAtLastError() != cudaSuccess) return emb::fail_cuda(who);
+    return 0;
   }
   // persistent grid: a multiple of the SM count (8 x 256 threads = full SM)
   uint64_t grid = (uint64_t)g_sm_count * 8;

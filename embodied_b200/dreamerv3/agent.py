@@ -122,6 +122,7 @@ class Agent(base.Agent):
   def policy(self, carry, obs, mode='train', noise=None):    # agent.py:115-135
     self._backend_flags()
     cfg, m = self.cfg, self.model
+    assert not any(k.startswith('log/') for k in obs), list(obs)          # jax/agent.py:223
     deter, stoch, prevact = carry
     image = obs['image']
     if not isinstance(image, torch.Tensor):
