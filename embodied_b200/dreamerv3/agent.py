@@ -29,6 +29,29 @@ from . import params as paramlib
 f32 = torch.float32
 
 
+def _clone(tree):
+  if isinstance(tree, dict):
+    return {k: _clone(v) for k, v in tree.items()}
+  if isinstance(tree, (tuple, list)):
+    return type(tree)(_clone(v) for v in tree)
+  return tree.clone()
+
+
+def _copy_into(dst, src):
+  """dst <- src leaf by leaf; a bare tensor stands for a single-key dict."""
+  if isinstance(dst, dict):
+    if not isinstance(src, dict):
+      assert len(dst) == 1, list(dst)
+      src = {next(iter(dst)): src}
+    for k in dst:
+      _copy_into(dst[k], src[k])
+  elif isinstance(dst, (tuple, list)):
+    for a, b in zip(dst, src):
+      _copy_into(a, b)
+  else:
+    dst.copy_(src)
+
+
 def _detach(tree):
   if isinstance(tree, dict):
     return {k: _detach(v) for k, v in tree.items()}
@@ -47,17 +70,15 @@ class Agent(base.Agent):
     self.obs_space = dict(obs_space)
     self.act_space = {k: v for k, v in act_space.items() if k != 'reset'}
     cfg = config if isinstance(config, configlib.Config) else configlib.make(**(config or {}))
-    imgkeys = [k for k, s in self.obs_space.items()
-               if s.dtype == np.uint8 and len(s.shape) == 3]
-    if imgkeys != ['image'] or list(self.act_space) != ['action'] or \
-        not self.act_space['action'].discrete:
-      raise NotImplementedError(
-          'this build covers the BASELINE configs: one uint8 `image` observation '
-          f'and one discrete `action` (got obs {list(self.obs_space)}, '
-          f'act {list(self.act_space)})')
+    from . import spaces as spacelib
     cfg = configlib.Config(cfg)
-    cfg.update(image=tuple(self.obs_space['image'].shape),
-               actions=int(np.asarray(self.act_space['action'].classes).flatten()[0]))
+    info = spacelib.analyze(self.obs_space, self.act_space)
+    if not info['actspec']:
+      raise ValueError('the action space has no key besides `reset`')
+    cfg.update(image=info['image'], imgkeys=info['imgkeys'], vecspec=info['vecspec'],
+               actspec=info['actspec'], actions=sum(spacelib.width(a) for a in info['actspec']))
+    self.obskeys = [k for k, _ in info['imgkeys']] + [v[0] for v in info['vecspec']]
+    self.actkeys = [a[0] for a in info['actspec']]
     self.cfg = cfg
     self.device = torch.device(device if device is not None else
                                f'cuda:{torch.cuda.current_device()}')
@@ -102,9 +123,13 @@ class Agent(base.Agent):
 
   def init_policy(self, batch_size):                         # agent.py:101-107
     cfg, dev = self.cfg, self.device
+    prevact = {
+        name: torch.zeros((batch_size, *shape), device=dev,
+                          dtype=torch.int32 if kind == 'disc' else f32)
+        for name, kind, shape, _ in cfg.actspec}
     return (torch.zeros((batch_size, cfg.deter), dtype=self.cd, device=dev),
             torch.zeros((batch_size, cfg.stoch, cfg.classes), dtype=self.cd, device=dev),
-            torch.zeros((batch_size,), dtype=torch.int32, device=dev))
+            prevact)
 
   init_train = init_policy
   init_report = init_policy
@@ -124,58 +149,68 @@ class Agent(base.Agent):
     cfg, m = self.cfg, self.model
     assert not any(k.startswith('log/') for k in obs), list(obs)          # jax/agent.py:223
     deter, stoch, prevact = carry
-    image = obs['image']
-    if not isinstance(image, torch.Tensor):
-      image = torch.as_tensor(np.asarray(image), device=self.device)
-    normalized = (getattr(obs, 'normalized', None) or {}).get('image')
-    reset = obs['is_first']
-    if not isinstance(reset, torch.Tensor):
-      reset = torch.as_tensor(np.asarray(reset), device=self.device)
+    if not isinstance(prevact, dict):                        # a bare tensor: the single action key
+      prevact = {self.actkeys[0]: prevact}
+    dev = lambda x: x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x), device=self.device)
+    inputs = {k: dev(obs[k]) for k in self.obskeys}
+    normalized = None
+    if len(cfg.imgkeys) == 1:
+      normalized = (getattr(obs, 'normalized', None) or {}).get(cfg.imgkeys[0][0])
+    reset = dev(obs['is_first'])
     n = len(reset)
     if noise is None:
-      noise = dict(
-          stoch=modellib.gumbel_like((n, cfg.stoch, cfg.classes), self.device, self.gen),
-          action=modellib.gumbel_like((n, cfg.actions), self.device, self.gen))
-    tokens = m.encoder(image, normalized)
+      noise = dict(stoch=modellib.gumbel_like((n, cfg.stoch, cfg.classes), self.device, self.gen),
+                   action=m.action_noise((n,), self.gen))
+    anoise = noise['action']
+    if not isinstance(anoise, dict):
+      anoise = {self.actkeys[0]: anoise}
+    tokens = m.encoder(inputs, normalized)
     (deter, stoch), feat = m.observe(
-        (deter, stoch), tokens[:, None], prevact[:, None], reset[:, None],
+        (deter, stoch), tokens[:, None], {k: v[:, None] for k, v in prevact.items()}, reset[:, None],
         noise['stoch'][:, None])
-    logits = m.head(m.feat2tensor(deter, stoch), 'pol', cfg.pol_layers, 'action/logits')
-    act = torch.argmax(logits + noise['action'], -1).to(torch.int32)
+    act = m.policy_sample(m.policy_outputs(m.feat2tensor(deter, stoch)), anoise)
     out = {'dyn/deter': deter.to(f32), 'dyn/stoch': stoch.to(f32)}   # _take_outs upcast, jax/agent.py:399-403
-    return (deter, stoch, act), {'action': act}, out
+    return (deter, stoch, act), dict(act), out
 
   # ---------------------------------------------------------------------- train
   def _apply_replay_context(self, carry, data):              # agent.py:312-340
     K = self.cfg.replay_context
     deter, stoch, prevact = carry
-    obs = {k: data[k] for k in ('image', 'reward', 'is_first', 'is_last', 'is_terminal')}
-    act = data['action']
+    if not isinstance(prevact, dict):
+      prevact = {self.actkeys[0]: prevact}
+    obs = {k: data[k] for k in (*self.obskeys, 'reward', 'is_first', 'is_last', 'is_terminal')}
+    act = {k: data[k] for k in self.actkeys}
     if not K:
-      pa = torch.cat([prevact[:, None], act[:, :-1]], 1)
+      pa = {k: torch.cat([prevact[k][:, None], act[k][:, :-1]], 1) for k in act}
       return (deter, stoch), obs, pa, data['stepid']
     first = data['consec'][:, 0] == 0
     rep_deter = data['dyn/deter'][:, K - 1].to(self.cd)
     rep_stoch = data['dyn/stoch'][:, K - 1].to(self.cd)
-    normal_pa = torch.cat([prevact[:, None], act[:, :-1]], 1)[:, K:]
-    rep_pa = act[:, K - 1: -1]
+    # prepend(prev, act)[:, K:] == act[:, K-1:-1] for K >= 1: both branches of agent.py:336-339 agree
+    pa = {k: act[k][:, K - 1: -1] for k in act}
     deter = torch.where(first[:, None], rep_deter, deter)
     stoch = torch.where(first[:, None, None], rep_stoch, stoch)
-    pa = torch.where(first[:, None], rep_pa, normal_pa)
     obs = {k: v[:, K:] for k, v in obs.items()}
     return (deter, stoch), obs, pa, data['stepid'][:, K:]
 
   def make_noise(self, B, T, out=None):
-    """Gumbel noise of one train step (an explicit input).  With
-    `out` the static buffers of the captured step are refilled in place."""
+    """Sampling noise of one train step (an explicit input): Gumbel tensors for the
+    categorical latents / actions, normal noise for continuous actions.  With `out` the static
+    buffers of the captured step are refilled in place."""
     cfg, dev, H = self.cfg, self.device, self.cfg.imag_length
     shapes = dict(observe=(B, T, cfg.stoch, cfg.classes),
-                  imag_stoch=(B * T, H, cfg.stoch, cfg.classes),
-                  imag_act=(B * T, H + 1, cfg.actions))
+                  imag_stoch=(B * T, H, cfg.stoch, cfg.classes))
     if out is None:
-      return {k: modellib.gumbel_like(s, dev, self.gen) for k, s in shapes.items()}
+      noise = {k: modellib.gumbel_like(s, dev, self.gen) for k, s in shapes.items()}
+      act = self.model.action_noise((B * T, H + 1), self.gen)
+      # one scalar discrete action: the bare tensor (the original layout of this dict)
+      noise['imag_act'] = act[self.actkeys[0]] if self.model.single_disc else act
+      return noise
     for k in shapes:
       modellib.gumbel_(out[k], self.gen)
+    for (name, kind, _, _) in cfg.actspec:
+      buf = out['imag_act'][name] if isinstance(out['imag_act'], dict) else out['imag_act']
+      modellib.gumbel_(buf, self.gen) if kind == 'disc' else buf.normal_(generator=self.gen)
     return out
 
   # The device work of one update, split where the data-parallel gradient
@@ -209,7 +244,7 @@ class Agent(base.Agent):
     feat = outs['feat']
     replay = {'stepid': stepid, 'dyn/deter': feat['deter'].detach().to(f32),
               'dyn/stoch': feat['stoch'].detach().to(f32)}
-    carry = (carry[0].detach(), carry[1].detach(), data['action'][:, -1].clone())
+    carry = (carry[0].detach(), carry[1].detach(), {k: data[k][:, -1].clone() for k in self.actkeys})
     return carry, replay, metrics
 
   def _allreduce(self):
@@ -256,7 +291,7 @@ class Agent(base.Agent):
     B, T = data['is_first'].shape[0], data['is_first'].shape[1] - self.cfg.replay_context
     st = types.SimpleNamespace()
     st.data = {k: v.clone() for k, v in data.items()}
-    st.carry = tuple(c.clone() for c in carry)
+    st.carry = _clone(tuple(carry))
     st.noise = self.make_noise(B, T)
     scan = self.model.scan
     if scan is not None:
@@ -304,15 +339,13 @@ class Agent(base.Agent):
     return st
 
   def _train_graphed(self, st, carry, data, noise=None):
-    for a, b in zip(st.carry, carry):      # carry first: it may alias last step's outputs
-      a.copy_(b)
+    _copy_into(st.carry, tuple(carry))     # carry first: it may alias last step's outputs
     for k, v in st.data.items():
       v.copy_(data[k])
     if noise is None:
       self.make_noise(*st.noise['observe'].shape[:2], out=st.noise)
     else:
-      for k, v in st.noise.items():
-        v.copy_(noise[k])
+      _copy_into(st.noise, noise)
     st.ga.replay()
     self._allreduce()
     extra = self.opt.begin_update()
@@ -342,7 +375,7 @@ class Agent(base.Agent):
     total, carry, outs, metrics = self.model.loss(carry, obs, prevact, noise, update=False)
     self.store.begin_step()
     metrics['loss'] = total
-    carry = (carry[0], carry[1], data['action'][:, -1])
+    carry = (carry[0], carry[1], {k: data[k][:, -1] for k in self.actkeys})
     return carry, metrics
 
   def stream(self, st):

@@ -18,12 +18,40 @@ Compute dtype is bfloat16 (the reference default, embodied/jax/nets.py:12) or
 float32 (parity); norms, softmaxes and losses are always float32
 (nets.py:372, outs.py:209,276).
 """
+import math
+
 import torch
 import torch.nn.functional as F
 
 from . import ops
+from . import spaces
 
 f32 = torch.float32
+
+
+def symlog(x):
+  return torch.sign(x) * torch.log1p(torch.abs(x))
+
+
+def dict_concat(specs, values, squish=None):
+  """nets.DictConcat (embodied/jax/nets.py:467-500) with fdims = 1: every key flattened behind its
+  batch axes -- integers one-hot, floats through `squish` -- and concatenated in the (sorted) order
+  of `specs`.  Unavailable entries (-inf floats, -1 integers: nets.py:80-94) contribute zeros."""
+  parts = []
+  for name, kind, shape, classes in specs:
+    x = values[name]
+    lead = x.shape[:x.dim() - len(shape)]
+    if kind == 'disc':
+      idx = x.long()
+      ok = idx >= 0
+      y = F.one_hot(torch.where(ok, idx, torch.zeros_like(idx)), classes).to(f32) * ok[..., None]
+    else:
+      x = x.to(f32)
+      ok = x != float('-inf')
+      x = torch.where(ok, x, torch.zeros_like(x))
+      y = (squish(x) if squish else x) * ok
+    parts.append(y.reshape(*lead, -1))
+  return torch.cat(parts, -1) if len(parts) > 1 else parts[0]
 
 
 def silu(x):
@@ -78,6 +106,11 @@ class Model:
     self.bins = torch.cat([half, -half[:-1].flip(0)], 0).to(self.device)   # heads.py:132-144
     self.ret_lo = torch.zeros((), dtype=f32, device=self.device)
     self.ret_hi = torch.zeros((), dtype=f32, device=self.device)
+    self.actspec = cfg.get('actspec') or [('action', 'disc', (), cfg.actions)]
+    self.vecspec = cfg.get('vecspec') or []
+    self.imgkeys = cfg.get('imgkeys') or ([('image', cfg.image[2])] if cfg.get('image') else [])
+    # one scalar discrete action: the one-hot matmul of dynin2 is a row lookup
+    self.single_disc = len(self.actspec) == 1 and self.actspec[0][1:3] == ('disc', ())
     self.fused_norm = bool(cfg.get('fused_norm', True)) and self.device.type == 'cuda'
     self.fused_spatial = bool(cfg.get('fused_spatial', True)) and self.device.type == 'cuda'
     self.tc_conv = bool(cfg.get('tc_conv', True)) and self.device.type == 'cuda'
@@ -159,31 +192,51 @@ class Model:
     return x
 
   # -------------------------------------------------------------------- encoder
-  def encoder(self, image, normalized=None):                 # rssm.py:226-246 (image keys)
-    """image: uint8 (..., H, W, C) or `normalized` float32 x/255-0.5 already
-    produced by emb_driver_stage_obs."""
+  def encoder(self, obs, normalized=None):                   # rssm.py:210-250
+    """obs: {key: tensor (..., *shape)} (a bare image tensor is accepted for the single-image
+    case); `normalized`: float32 x/255-0.5 of the (concatenated) image already produced by
+    emb_driver_stage_obs.  Tokens = [vector branch | image branch] (rssm.py:218-246)."""
     cfg = self.cfg
-    if normalized is None:
-      x = image.to(f32) / 255 - 0.5
-    else:
-      x = normalized
-    lead = x.shape[:-3]
-    x = x.reshape(-1, *x.shape[-3:]).to(self.cd)
-    for i in range(len(cfg.mults)):
-      if self.fused_spatial and ops.thin_conv_supported(x, x.shape[-1], cfg.depth * cfg.mults[i]):
-        x = self.conv_thin_in(x, f'enc/cnn{i}')
+    if isinstance(obs, torch.Tensor):
+      obs = {self.imgkeys[0][0]: obs}
+    outs, lead = [], None
+    if self.vecspec:                                          # DictConcat(symlog) -> MLP
+      x = dict_concat(self.vecspec, obs, symlog)
+      lead = x.shape[:-1]
+      x = x.reshape(-1, x.shape[-1]).to(self.cd)
+      for i in range(cfg.get('enc_layers', 3)):
+        x = self.norm(self.dense(x, f'enc/mlp{i}'), f'enc/mlp{i}norm')
+      outs.append(x)
+    if self.imgkeys:
+      if normalized is None:
+        imgs = [obs[k] for k, _ in self.imgkeys]
+        x = (imgs[0] if len(imgs) == 1 else torch.cat(imgs, -1)).to(f32) / 255 - 0.5
       else:
-        x = self.conv(x, f'enc/cnn{i}', bias=False)
-      x = self.pool(x)
-      x = self.norm(x, f'enc/cnn{i}norm', bias=self.store.w[f'enc/cnn{i}/bias'])
+        x = normalized
+      lead = x.shape[:-3]
+      x = x.reshape(-1, *x.shape[-3:]).to(self.cd)
+      for i in range(len(cfg.mults)):
+        if self.fused_spatial and ops.thin_conv_supported(x, x.shape[-1], cfg.depth * cfg.mults[i]):
+          x = self.conv_thin_in(x, f'enc/cnn{i}')
+        else:
+          x = self.conv(x, f'enc/cnn{i}', bias=False)
+        x = self.pool(x)
+        x = self.norm(x, f'enc/cnn{i}norm', bias=self.store.w[f'enc/cnn{i}/bias'])
+      outs.append(x.reshape(x.shape[0], -1))
+    x = outs[0] if len(outs) == 1 else torch.cat(outs, -1)
     return x.reshape(*lead, -1)
 
   # ----------------------------------------------------------------------- rssm
   def action_embed(self, action, reset):
-    """DictConcat one-hot (nets.py:467-500) with the reset mask of
-    rssm.py:76-79, then `action / max(1, |action|)` (rssm.py:137)."""
-    a = F.one_hot(action.long(), self.cfg.actions).to(self.cd)
-    return a * (~reset)[..., None].to(self.cd)
+    """DictConcat of the action dict (nets.py:467-500; a bare tensor = the single action key) with
+    the reset mask of rssm.py:76-79, then `action / max(1, |action|)` (rssm.py:137; a no-op for
+    one-hot columns)."""
+    if isinstance(action, torch.Tensor):
+      action = {self.actspec[0][0]: action}
+    a = dict_concat(self.actspec, action)
+    a = a * (~reset)[..., None]
+    a = a / torch.clamp(a.abs(), min=1.0)
+    return a.to(self.cd)
 
   def core(self, deter, stoch_flat, x2, out=None):           # rssm.py:135-159
     """x2 = silu(rms(dynin2(action))) is precomputed by the caller.  dynhid0's
@@ -240,7 +293,10 @@ class Model:
     return value
 
   def act_branch(self, action, reset):
-    if not torch.is_grad_enabled() and action.dim() == 1:
+    if isinstance(action, dict) and self.single_disc:
+      action = action[self.actspec[0][0]]
+    if (not torch.is_grad_enabled() and self.single_disc and isinstance(action, torch.Tensor)
+        and action.dim() == 1):
       # one-hot @ kernel is a row lookup; rows of reset steps see a zero action (bias only)
       w, b = self.W('dyn/dynin2/kernel'), self.W('dyn/dynin2/bias')
       y = w[action.long()] * (~reset)[:, None].to(w.dtype) + b
@@ -324,9 +380,23 @@ class Model:
     return dyn, rep, mets
 
   # -------------------------------------------------------------------- decoder
-  def decoder(self, deter, stoch):                           # rssm.py:288-359 (image key)
+  def decoder(self, deter, stoch):                           # rssm.py:288-359
+    """-> {'image': sigmoid reconstruction of the (channel-concatenated) image keys (fp32),
+    <vector key>: raw head output (fp32): `pred` in symlog space or categorical logits}."""
     cfg = self.cfg
     lead = deter.shape[:-1]
+    recons = {}
+    if self.vecspec:                                          # rssm.py:323-334
+      sflat = stoch.reshape(*lead, -1).to(self.cd)
+      x = torch.cat([sflat, deter.to(self.cd)], -1)           # [stoch | deter] (rssm.py:319-321)
+      x = self.mlp(x.reshape(-1, x.shape[-1]), 'dec', cfg.get('dec_layers', 3))
+      for spec in self.vecspec:
+        name = f'dec/vec/{spec[0]}/' + ('logits' if spec[1] == 'disc' else 'pred')
+        y = self.dense(x, name).to(f32)
+        shape = spec[2] + ((spec[3],) if spec[1] == 'disc' else ())
+        recons[spec[0]] = y.reshape(*lead, *shape)
+    if not self.imgkeys:
+      return recons
     depths = [cfg.depth * m for m in cfg.mults]
     minres = cfg.image[0] // 2 ** len(cfg.mults)
     g, c = cfg.bspace, depths[-1] // cfg.bspace
@@ -351,7 +421,29 @@ class Model:
     else:
       x = self.conv(self.upsample(x), 'dec/imgout')
     x = torch.sigmoid(x.to(f32))
-    return x.reshape(*lead, *x.shape[1:])
+    recons['image'] = x.reshape(*lead, *x.shape[1:])
+    return recons
+
+  def recon_losses(self, recons, obs):
+    """One (B, T) loss per decoded key (agent.py:176-180): images MSE against x / 255 summed over
+    H, W, C (rssm.py:354-357, split per image key); float vectors MSE in symlog space, integer
+    vectors categorical cross-entropy, both summed over the key's own axes (heads.py:87-88)."""
+    out = {}
+    if self.imgkeys:
+      c0 = 0
+      for key, ch in self.imgkeys:
+        target = obs[key].to(f32) / 255
+        out[key] = (recons['image'][..., c0: c0 + ch] - target).square().sum((-3, -2, -1))
+        c0 += ch
+    for name, kind, shape, classes in self.vecspec:
+      y, dims = recons[name], tuple(range(-len(shape), 0)) if shape else ()
+      if kind == 'disc':
+        logp = torch.log_softmax(y, -1).gather(-1, obs[name].long()[..., None]).squeeze(-1)
+        loss = -logp
+      else:
+        loss = (y - symlog(obs[name].to(f32))).square()
+      out[name] = loss.sum(dims) if dims else loss
+    return out
 
   def upsample(self, x):                                     # x.repeat(2,-2).repeat(2,-3), NHWC
     if self.fused_spatial and ops.spatial_supported(x):
@@ -370,6 +462,66 @@ class Model:
 
   def head(self, x, name, layers, out):                      # heads.py:34-41
     return self.dense(self.mlp(x, name, layers), f'{name}/head/{out}').to(f32)
+
+  # -- policy: one distribution per action key (agent.py:61-64, heads.py:103-155) ---------
+  def policy_outputs(self, x):
+    """{key: logits (..., *shape, classes)} for discrete keys, {key: (mean, std)} for continuous
+    ones: bounded_normal = Normal(tanh(mean), (maxstd - minstd) * sigmoid(std + 2) + minstd)."""
+    cfg = self.cfg
+    h = self.mlp(x, 'pol', cfg.pol_layers)
+    outs = {}
+    for name, kind, shape, classes in self.actspec:
+      if kind == 'disc':
+        y = self.dense(h, f'pol/head/{name}/logits').to(f32)
+        outs[name] = y.reshape(*y.shape[:-1], *shape, classes)
+      else:
+        mean = self.dense(h, f'pol/head/{name}/mean').to(f32)
+        std = self.dense(h, f'pol/head/{name}/stddev').to(f32)
+        lo, hi = cfg.get('minstd', 0.1), cfg.get('maxstd', 1.0)
+        std = (hi - lo) * torch.sigmoid(std + 2.0) + lo
+        outs[name] = (torch.tanh(mean).reshape(*mean.shape[:-1], *shape),
+                      std.reshape(*std.shape[:-1], *shape))
+    return outs
+
+  def policy_sample(self, outs, noise):
+    """Categorical: argmax(logits + Gumbel) (jax.random.categorical); Normal: mean + std * eps."""
+    acts = {}
+    for name, kind, shape, classes in self.actspec:
+      if kind == 'disc':
+        acts[name] = torch.argmax(outs[name] + noise[name], -1).to(torch.int32)
+      else:
+        mean, std = outs[name]
+        acts[name] = mean + std * noise[name]
+    return acts
+
+  def policy_logp_entropy(self, outs, acts):
+    """sum_k logp_k(act_k), sum_k entropy_k (agent.py:407-408), each summed over the key's own
+    axes (outs.Agg).  Normal: outs.py:160-167."""
+    logp, ent = 0.0, 0.0
+    for name, kind, shape, classes in self.actspec:
+      dims = tuple(range(-len(shape), 0)) if shape else ()
+      if kind == 'disc':
+        la = torch.log_softmax(outs[name], -1)
+        lp = la.gather(-1, acts[name].long()[..., None]).squeeze(-1)
+        en = -(torch.softmax(outs[name], -1) * la).sum(-1)
+      else:
+        mean, std = outs[name]
+        a = acts[name].to(f32)
+        lp = -0.5 * ((a - mean) / std).square() - torch.log(std) - 0.5 * math.log(2 * math.pi)
+        en = 0.5 * torch.log(2 * math.pi * std.square()) + 0.5
+      logp = logp + (lp.sum(dims) if dims else lp)
+      ent = ent + (en.sum(dims) if dims else en)
+    return logp, ent
+
+  def action_noise(self, lead, generator=None):
+    """{key: Gumbel noise (*lead, *shape, classes) | normal noise (*lead, *shape)}."""
+    out = {}
+    for name, kind, shape, classes in self.actspec:
+      if kind == 'disc':
+        out[name] = gumbel_like((*lead, *shape, classes), self.device, generator)
+      else:
+        out[name] = torch.randn((*lead, *shape), device=self.device, generator=generator)
+    return out
 
   def slow_value_logits(self, x):
     """The slow critic (utils.py:94-127): val's architecture, slow parameters."""
@@ -458,7 +610,7 @@ class Model:
   def imagine(self, deter, stoch, noise_stoch, noise_act):   # rssm.py:94-118, agent.py:188-200
     """From B*K start states roll H steps with the policy in the loop.  Returns
     the features (BK, H+1, D + S*C) -- deter | flat stoch, written in place step
-    by step -- and the actions (BK, H+1)."""
+    by step -- and the actions {key: (BK, H+1, *shape)}.  noise_act: {key: (BK, H+1, ...)}."""
     cfg = self.cfg
     H, D = cfg.imag_length, cfg.deter
     n = len(deter)
@@ -466,19 +618,19 @@ class Model:
     feat = torch.empty((n, H + 1, D + cfg.stoch * cfg.classes), dtype=self.cd, device=deter.device)
     feat[:, 0, :D] = deter
     feat[:, 0, D:] = stoch.reshape(n, -1)
-    acts = []
+    acts = {spec[0]: [] for spec in self.actspec}
     for h in range(H + 1):
       cur = feat[:, h]                  # (n, D + S*C) rows of the buffer: no per-step copies,
-      logits = self.head(cur, 'pol', cfg.pol_layers, 'action/logits')
-      a = torch.argmax(logits + noise_act[:, h], -1)
-      acts.append(a)
+      a = self.policy_sample(self.policy_outputs(cur), {k: v[:, h] for k, v in noise_act.items()})
+      for k, v in a.items():
+        acts[k].append(v)
       if h == H:
         break
       x2 = self.act_branch(a, never)
       nxt = feat[:, h + 1]              # the next state is written where it is kept
       self.core(cur[:, :D], cur[:, D:], x2, out=nxt[:, :D])
       self.sample_stoch(self.prior(nxt[:, :D]), noise_stoch[:, h], out=nxt[:, D:])
-    return feat, torch.stack(acts, 1)
+    return feat, {k: torch.stack(v, 1) for k, v in acts.items()}
 
   # ------------------------------------------------------------------------ loss
   def loss(self, carry, obs, prevact, noise, update=True):   # agent.py:156-245
@@ -486,7 +638,7 @@ class Model:
     reset = obs['is_first']
     B, T = reset.shape
     losses, metrics = {}, {}
-    tokens = self.encoder(obs['image'])
+    tokens = self.encoder(obs)
     carry, feat = self.observe(carry, tokens, prevact, reset, noise['observe'])
     dyn, rep, mets = self.kl_losses(feat['logit'], self.prior(feat['deter']))
     losses['dyn'], losses['rep'] = dyn, rep
@@ -500,14 +652,16 @@ class Model:
       con = con * (1 - 1 / cfg.horizon)
     clogit = self.head(inp, 'con', cfg.con_layers, 'logit').squeeze(-1)
     losses['con'] = -(con * F.logsigmoid(clogit) + (1 - con) * F.logsigmoid(-clogit))
-    target = obs['image'].to(f32) / 255
-    losses['image'] = (recon - target).square().sum((-3, -2, -1))
+    losses.update(self.recon_losses(recon, obs))
 
     K, H = T, cfg.imag_length
+    noise_act = noise['imag_act']
+    if not isinstance(noise_act, dict):
+      noise_act = {self.actspec[0][0]: noise_act}
     imgfeat, imgact = self.imagine(
         feat['deter'].detach().reshape(B * K, -1),
         feat['stoch'].detach().reshape(B * K, cfg.stoch, cfg.classes),
-        noise['imag_stoch'], noise['imag_act'])
+        noise['imag_stoch'], noise_act)
     imgdeter = imgfeat[..., :cfg.deter]
     imgstoch = imgfeat[..., cfg.deter:].reshape(B * K, H + 1, cfg.stoch, cfg.classes)
     los, ret, mets = self.imag_loss(imgact, imgfeat, update)
@@ -526,15 +680,20 @@ class Model:
     weight = (~obs['is_last']).to(f32)
     losses['repval'] = weight[:, :-1] * self.twohot_loss(vlogits, padded, slow, cfg.slowreg)[:, :-1]
 
-    assert set(losses) == set(cfg.scales), (sorted(losses), sorted(cfg.scales))
+    scales = dict(cfg.scales)
+    rec = scales.pop('image')                                # agent.py:75-78: `rec` for every decoded key
+    scales.update({k: rec for k, _ in self.imgkeys})
+    scales.update({spec[0]: rec for spec in self.vecspec})
+    assert set(losses) == set(scales), (sorted(losses), sorted(scales))
     if self.fused_norm and total_fusable(losses):
-      total, means = ops.loss_sum(losses, cfg.scales)        # one launch (agent.py:237-240)
+      total, means = ops.loss_sum(losses, scales)            # one launch (agent.py:237-240)
       metrics.update({f'loss/{k}': v for k, v in means.items()})
     else:
       metrics.update({f'loss/{k}': v.detach().mean() for k, v in losses.items()})
-      total = sum(v.mean() * cfg.scales[k] for k, v in losses.items())
+      total = sum(v.mean() * scales[k] for k, v in losses.items())
     outs = dict(tokens=tokens, feat=feat, losses=losses, recon=recon,
-                imgdeter=imgdeter, imgstoch=imgstoch, imgact=imgact, ret=ret)
+                imgdeter=imgdeter, imgstoch=imgstoch, ret=ret,
+                imgact=imgact[self.actspec[0][0]] if len(self.actspec) == 1 else imgact)
     return total, carry, outs, metrics
 
   def imag_loss(self, act, inp, update):                     # agent.py:382-446
@@ -543,7 +702,7 @@ class Model:
       rew = self.twohot_pred(self.head(inp, 'rew', cfg.rew_layers, 'logits'))
       con = torch.sigmoid(self.head(inp, 'con', cfg.con_layers, 'logit').squeeze(-1))
       slowval = self.twohot_pred(self.slow_value_logits(inp))
-    pol = self.head(inp, 'pol', cfg.pol_layers, 'action/logits')
+    pol = self.policy_outputs(inp)
     vlogits = self.head(inp, 'val', cfg.val_layers, 'logits')
     val = self.twohot_pred(vlogits.detach())
     disc = 1 if cfg.contdisc else 1 - 1 / cfg.horizon
@@ -551,9 +710,8 @@ class Model:
     ret = self.lambda_return(torch.zeros_like(con), 1 - con, rew, val, val, disc, cfg.lam)
     roffset, rscale = self.retnorm(ret, update)
     adv = (ret - val[:, :-1]) / rscale
-    logp_all = torch.log_softmax(pol, -1)
-    logpi = logp_all.gather(-1, act[..., None]).squeeze(-1)[:, :-1]
-    ent = -(torch.softmax(pol, -1) * logp_all).sum(-1)[:, :-1]
+    logpi, ent = self.policy_logp_entropy(pol, act)
+    logpi, ent = logpi[:, :-1], ent[:, :-1]
     losses = {}
     losses['policy'] = weight[:, :-1] * -(logpi * adv + cfg.actent * ent)
     padded = torch.cat([ret, 0 * ret[:, -1:]], 1)

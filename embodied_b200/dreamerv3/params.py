@@ -24,11 +24,19 @@ ALIGN = 16   # elements (64 B in fp32)
 
 def shapes(cfg):
   """name -> (shape, fan_in or None, outscale).  Order is the storage order."""
+  from . import spaces
   D, H, S, C, g = cfg.deter, cfg.hidden, cfg.stoch, cfg.classes, cfg.blocks
   U, A, k = cfg.units, cfg.actions, cfg.kernel
+  image = cfg.get('image')
+  vecspec, actspec = cfg.get('vecspec') or [], cfg.get('actspec')
+  if actspec is None:                       # the original single discrete `action` key
+    actspec = [('action', 'disc', (), A)]
   depths = [cfg.depth * m for m in cfg.mults]
-  minres = cfg.image[0] // 2 ** len(cfg.mults)
-  sp = minres * minres * depths[-1]
+  sp = 0
+  if image:
+    minres = image[0] // 2 ** len(cfg.mults)
+    sp = minres * minres * depths[-1]
+  tokens = (U if vecspec else 0) + sp
   out = {}
 
   def dense(name, i, o, outscale=1.0):
@@ -52,35 +60,54 @@ def shapes(cfg):
   dense('dyn/dynin2', A, H); norm('dyn/dynin2norm', H)
   block('dyn/dynhid0', D + g * 3 * H, D); norm('dyn/dynhid0norm', D)
   block('dyn/dyngru', D, 3 * D)
-  dense('dyn/obs0', D + sp, H); norm('dyn/obs0norm', H)
+  dense('dyn/obs0', D + tokens, H); norm('dyn/obs0norm', H)
   dense('dyn/obslogit', H, S * C)
   dense('dyn/prior0', D, H); norm('dyn/prior0norm', H)
   dense('dyn/prior1', H, H); norm('dyn/prior1norm', H)
   dense('dyn/priorlogit', H, S * C)
-  cin = cfg.image[2]
-  for i, d in enumerate(depths):
-    conv(f'enc/cnn{i}', cin, d); norm(f'enc/cnn{i}norm', d); cin = d
-  block('dec/sp0', D, sp)
-  dense('dec/sp1', S * C, 2 * U); norm('dec/sp1norm', 2 * U)
-  dense('dec/sp2', 2 * U, sp)
-  norm('dec/spnorm', depths[-1])
-  cin = depths[-1]
-  for i in reversed(range(len(depths) - 1)):
-    conv(f'dec/conv{i}', cin, depths[i]); norm(f'dec/conv{i}norm', depths[i])
-    cin = depths[i]
-  conv('dec/imgout', cin, cfg.image[2])
   feat = D + S * C
+  if vecspec:                               # rssm.py:218-224: DictConcat -> MLP
+    i = sum(spaces.width(v) for v in vecspec)
+    for l in range(cfg.get('enc_layers', 3)):
+      dense(f'enc/mlp{l}', i, U); norm(f'enc/mlp{l}norm', U); i = U
+  if image:
+    cin = image[2]
+    for i, d in enumerate(depths):
+      conv(f'enc/cnn{i}', cin, d); norm(f'enc/cnn{i}norm', d); cin = d
+  if vecspec:                               # rssm.py:326-334: MLP -> one head per key
+    i = feat
+    for l in range(cfg.get('dec_layers', 3)):
+      dense(f'dec/mlp/linear{l}', i, U); norm(f'dec/mlp/norm{l}', U); i = U
+    for v in vecspec:
+      dense(f'dec/vec/{v[0]}/' + ('logits' if v[1] == 'disc' else 'pred'), U, spaces.width(v))
+  if image:
+    block('dec/sp0', D, sp)
+    dense('dec/sp1', S * C, 2 * U); norm('dec/sp1norm', 2 * U)
+    dense('dec/sp2', 2 * U, sp)
+    norm('dec/spnorm', depths[-1])
+    cin = depths[-1]
+    for i in reversed(range(len(depths) - 1)):
+      conv(f'dec/conv{i}', cin, depths[i]); norm(f'dec/conv{i}norm', depths[i])
+      cin = depths[i]
+    conv('dec/imgout', cin, image[2])
 
-  def head(name, layers, outname, outdim, outscale):
+  def head(name, layers, outs):
     i = feat
     for l in range(layers):
       dense(f'{name}/mlp/linear{l}', i, U); norm(f'{name}/mlp/norm{l}', U); i = U
-    dense(f'{name}/head/{outname}', U, outdim, outscale)
+    for outname, outdim, outscale in outs:
+      dense(f'{name}/head/{outname}', U, outdim, outscale)
 
-  head('rew', cfg.rew_layers, 'logits', cfg.bins, 0.0)
-  head('con', cfg.con_layers, 'logit', 1, 1.0)
-  head('pol', cfg.pol_layers, 'action/logits', A, 0.01)
-  head('val', cfg.val_layers, 'logits', cfg.bins, 0.0)
+  head('rew', cfg.rew_layers, [('logits', cfg.bins, 0.0)])
+  head('con', cfg.con_layers, [('logit', 1, 1.0)])
+  pol = []
+  for a in actspec:                         # heads.py:103-112 categorical / :146-155 bounded_normal
+    if a[1] == 'disc':
+      pol.append((f'{a[0]}/logits', spaces.width(a), 0.01))
+    else:
+      pol += [(f'{a[0]}/mean', spaces.size(a), 0.01), (f'{a[0]}/stddev', spaces.size(a), 0.01)]
+  head('pol', cfg.pol_layers, pol)
+  head('val', cfg.val_layers, [('logits', cfg.bins, 0.0)])
   return out
 
 

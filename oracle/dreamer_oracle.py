@@ -122,6 +122,46 @@ def symexp(x):
   return torch.sign(x) * torch.expm1(torch.abs(x))
 
 
+def symlog(x):                                                  # nets.py:59-60
+  return torch.sign(x) * torch.log1p(torch.abs(x))
+
+
+def dict_concat(specs, values, squish=None):                    # nets.py:467-500 (fdims = 1)
+  """specs: sorted list of (key, kind 'disc'|'cont', shape, classes).  Integers -> one-hot,
+  floats -> squish; -1 / -inf entries are `unavailable` and masked to zero (nets.py:76-94)."""
+  ys = []
+  for key, kind, shape, classes in specs:
+    x = values[key]
+    lead = x.shape[:x.dim() - len(shape)]
+    if kind == 'disc':
+      x = x.long()
+      m = x != -1
+      y = F.one_hot(torch.where(m, x, torch.zeros_like(x)), classes).to(f32) * m[..., None]
+    else:
+      x = x.to(f32)
+      m = x != float('-inf')
+      x = torch.where(m, x, torch.zeros_like(x))
+      y = (squish(x) if squish else x) * m
+    ys.append(y.reshape(*lead, -1))
+  return torch.cat(ys, -1)
+
+
+def space_specs(cfg):
+  """(imgkeys [(key, channels)], vecspec, actspec) of a config; the defaults describe config 2:
+  one `image` key and one scalar discrete `action` with cfg.actions classes."""
+  img = cfg.get('imgkeys')
+  if img is None:
+    img = [('image', cfg.image[2])] if cfg.get('image') else []
+  vec = cfg.get('vecspec') or []
+  act = cfg.get('actspec') or [('action', 'disc', (), cfg.actions)]
+  return img, vec, act
+
+
+def spec_width(spec):
+  n = int(np.prod(spec[2], dtype=np.int64))
+  return n * (spec[3] if spec[1] == 'disc' else 1)
+
+
 def twohot_bins(n=255):                                         # heads.py:132-144
   assert n % 2 == 1
   half = symexp(torch.linspace(-20, 0, (n - 1) // 2 + 1, dtype=f32))
@@ -186,27 +226,44 @@ class Dreamer:
         step=0, nu={k: torch.zeros_like(v) for k, v in params.items()},
         mu={k: torch.zeros_like(v) for k, v in params.items()})
 
-  # -- encoder (rssm.py:210-250, image keys only: config 2 has no vector obs) --
-  def encoder(self, image_u8):
+  # -- encoder (rssm.py:210-250) ------------------------------------------------
+  def encoder(self, obs):
+    """obs: dict of the observation keys (a bare uint8 tensor = the single image key)."""
     p, cfg = self.p, self.cfg
-    x = image_u8.to(f32) / 255 - 0.5
-    lead = x.shape[:-3]
-    x = x.reshape(-1, *x.shape[-3:])
-    for i in range(len(cfg.mults)):
-      x = conv(p, f'enc/cnn{i}', x)
-      n, h, w, c = x.shape
-      x = x.reshape(n, h // 2, 2, w // 2, 2, c).amax((2, 4))
-      x = silu(rms(x, p[f'enc/cnn{i}norm/scale']))
-    return x.reshape(*lead, -1)
+    img, vec, _ = space_specs(cfg)
+    if torch.is_tensor(obs):
+      obs = {img[0][0]: obs}
+    outs = []
+    if vec:                                                     # :215-224 DictConcat(symlog) -> MLP
+      x = dict_concat(vec, obs, symlog)
+      lead = x.shape[:-1]
+      x = x.reshape(-1, x.shape[-1])
+      for i in range(cfg.get('enc_layers', 3)):
+        x = layer(p, f'enc/mlp{i}', x)
+      outs.append(x)
+    if img:                                                     # :226-246
+      x = torch.cat([obs[k] for k, _ in img], -1).to(f32) / 255 - 0.5
+      lead = x.shape[:-3]
+      x = x.reshape(-1, *x.shape[-3:])
+      for i in range(len(cfg.mults)):
+        x = conv(p, f'enc/cnn{i}', x)
+        n, h, w, c = x.shape
+        x = x.reshape(n, h // 2, 2, w // 2, 2, c).amax((2, 4))
+        x = silu(rms(x, p[f'enc/cnn{i}norm/scale']))
+      outs.append(x.reshape(x.shape[0], -1))
+    return torch.cat(outs, -1).reshape(*lead, -1)
 
   # -- rssm ------------------------------------------------------------------
   def action_embed(self, action, reset=None):
-    """DictConcat one-hot of the single discrete action (nets.py:467-500) with
-    the reset masking of rssm.py:76-79."""
-    a = action.long()
+    """rssm.py:76-79: mask the action dict where reset, DictConcat (nets.py:467-500), mask again.
+    A bare tensor is the single action key."""
+    _, _, act = space_specs(self.cfg)
+    if torch.is_tensor(action):
+      action = {act[0][0]: action}
     if reset is not None:
-      a = torch.where(reset, torch.zeros_like(a), a)
-    a = F.one_hot(a, self.cfg.actions).to(f32)
+      action = {k: torch.where(reset.reshape(reset.shape + (1,) * (v.dim() - reset.dim())),
+                               torch.zeros_like(v), v) for k, v in action.items()}
+    a = dict_concat(act, action)
     if reset is not None:
       a = a * (~reset)[..., None]
     return a
@@ -253,8 +310,8 @@ class Dreamer:
   def observe(self, carry, tokens, action, reset, gumbel):       # rssm.py:61-73
     feats = []
     for t in range(tokens.shape[1]):
-      carry, feat = self.observe_step(
-          carry, tokens[:, t], action[:, t], reset[:, t], gumbel[:, t])
+      act_t = {k: v[:, t] for k, v in action.items()} if isinstance(action, dict) else action[:, t]
+      carry, feat = self.observe_step(carry, tokens[:, t], act_t, reset[:, t], gumbel[:, t])
       feats.append(feat)
     feat = {k: torch.stack([f[k] for f in feats], 1) for k in feats[0]}
     return carry, feat
@@ -277,10 +334,22 @@ class Dreamer:
     stoch = onehot_sample(logit, self.cfg.unimix, gumbel)
     return dict(deter=deter, stoch=stoch)
 
-  # -- decoder (rssm.py:288-359, image key only) -------------------------------
+  # -- decoder (rssm.py:288-359) --------------------------------------------------
   def decoder(self, deter, stoch):
+    """-> {'image': sigmoid reconstruction of the concatenated image keys, <vector key>: head
+    output (`pred` in symlog space | categorical logits)}."""
     p, cfg = self.p, self.cfg
+    img, vec, _ = space_specs(cfg)
     lead = deter.shape[:-1]
+    recons = {}
+    if vec:                                                     # :323-334
+      x = torch.cat([stoch.reshape(*lead, -1), deter], -1)      # inp = [stoch, deter] (:319-321)
+      x = mlp(p, 'dec/mlp', x.reshape(-1, x.shape[-1]), cfg.get('dec_layers', 3))
+      for key, kind, shape, classes in vec:
+        y = linear(p, f'dec/vec/{key}/' + ('logits' if kind == 'disc' else 'pred'), x)
+        recons[key] = y.reshape(*lead, *shape, *((classes,) if kind == 'disc' else ()))
+    if not img:
+      return recons
     x0 = deter.reshape(-1, deter.shape[-1])
     x1 = stoch.reshape(x0.shape[0], -1)
     minres = cfg.image[0] // 2 ** len(cfg.mults)
@@ -298,7 +367,26 @@ class Dreamer:
       x = silu(rms(x, p[f'dec/conv{i}norm/scale']))
     x = x.repeat_interleave(2, 2).repeat_interleave(2, 1)
     x = torch.sigmoid(conv(p, 'dec/imgout', x))
-    return x.reshape(*lead, *x.shape[1:])
+    recons['image'] = x.reshape(*lead, *x.shape[1:])
+    return recons
+
+  def recon_losses(self, recons, obs):                          # agent.py:176-180
+    img, vec, _ = space_specs(self.cfg)
+    out, c0 = {}, 0
+    for key, ch in img:                                         # rssm.py:354-357: MSE, Agg(3, sum)
+      target = obs[key].to(f32) / 255
+      out[key] = ((recons['image'][..., c0: c0 + ch] - target) ** 2).sum((-3, -2, -1))
+      c0 += ch
+    for key, kind, shape, classes in vec:
+      y = recons[key]
+      if kind == 'disc':                                        # categorical: -logp (outs.py:23-24)
+        loss = -torch.log_softmax(y, -1).gather(-1, obs[key].long()[..., None]).squeeze(-1)
+      else:                                                     # symlog_mse (heads.py:126-129)
+        loss = (y - symlog(obs[key].to(f32))) ** 2
+      for _ in shape:                                           # Agg over the key's own axes (heads.py:87-88)
+        loss = loss.sum(-1)
+      out[key] = loss
+    return out
 
   # -- heads (heads.py:16-41) ----------------------------------------------------
   def feat2tensor(self, deter, stoch):                          # agent.py:51-53
@@ -315,8 +403,56 @@ class Dreamer:
   def con_logit(self, x):
     return self.head('con', x, self.cfg.con_layers, 'logit').squeeze(-1)
 
-  def pol_logits(self, x):
-    return self.head('pol', x, self.cfg.pol_layers, 'action/logits')
+  def pol_outputs(self, x):                                     # heads.py:103-112, 146-155
+    """{key: logits} (categorical) / {key: (mean, std)} (bounded_normal) per action key."""
+    cfg = self.cfg
+    _, _, act = space_specs(cfg)
+    h = mlp(self.p, 'pol/mlp', x, cfg.pol_layers)
+    outs = {}
+    for key, kind, shape, classes in act:
+      if kind == 'disc':
+        y = linear(self.p, f'pol/head/{key}/logits', h)
+        outs[key] = y.reshape(*y.shape[:-1], *shape, classes)
+      else:
+        mean = linear(self.p, f'pol/head/{key}/mean', h)
+        std = linear(self.p, f'pol/head/{key}/stddev', h)
+        lo, hi = cfg.get('minstd', 0.1), cfg.get('maxstd', 1.0)
+        std = (hi - lo) * torch.sigmoid(std + 2.0) + lo
+        outs[key] = (torch.tanh(mean).reshape(*mean.shape[:-1], *shape),
+                     std.reshape(*std.shape[:-1], *shape))
+    return outs
+
+  def pol_sample(self, outs, noise):
+    """noise: {key: Gumbel (categorical) | standard normal (Normal.sample, outs.py:156-158)};
+    a bare tensor is the single action key."""
+    _, _, act = space_specs(self.cfg)
+    if torch.is_tensor(noise):
+      noise = {act[0][0]: noise}
+    res = {}
+    for key, kind, shape, classes in act:
+      if kind == 'disc':
+        res[key] = torch.argmax(outs[key] + noise[key], -1).to(torch.int32)
+      else:
+        mean, std = outs[key]
+        res[key] = noise[key] * std + mean
+    return res
+
+  def pol_logp_entropy(self, outs, acts):                       # agent.py:407-408
+    _, _, act = space_specs(self.cfg)
+    logp, ent = 0.0, 0.0
+    for key, kind, shape, classes in act:
+      if kind == 'disc':
+        la = torch.log_softmax(outs[key], -1)
+        lp = la.gather(-1, acts[key].long()[..., None]).squeeze(-1)
+        en = -(torch.softmax(outs[key], -1) * la).sum(-1)
+      else:
+        mean, std = outs[key]
+        lp = torch.distributions.Normal(mean, std).log_prob(acts[key].to(f32))   # outs.py:160-163
+        en = 0.5 * torch.log(2 * math.pi * std ** 2) + 0.5                        # outs.py:165-166
+      for _ in shape:
+        lp, en = lp.sum(-1), en.sum(-1)
+      logp, ent = logp + lp, ent + en
+    return logp, ent
 
   def val_logits(self, x):
     return self.head('val', x, self.cfg.val_layers, 'logits')
@@ -325,17 +461,21 @@ class Dreamer:
     return self.head('slowval', x, self.cfg.val_layers, 'logits', self.slow)
 
   # -- policy (agent.py:115-135) ---------------------------------------------------
-  def policy(self, carry, image_u8, is_first, noise):
-    """carry: dict(deter, stoch, action); noise: dict(stoch=(N,S,C), action=(N,A))."""
+  def policy(self, carry, obs, is_first, noise):
+    """carry: dict(deter, stoch, action); obs: observation dict (or the bare image);
+    noise: dict(stoch=(N,S,C), action={key: ...} | tensor)."""
+    _, _, act = space_specs(self.cfg)
+    single = len(act) == 1
     with torch.no_grad():
-      tokens = self.encoder(image_u8)
+      tokens = self.encoder(obs)
       dyn, feat = self.observe_step(
           carry, tokens, carry['action'], is_first, noise['stoch'])
-      logits = self.pol_logits(self.feat2tensor(feat['deter'], feat['stoch']))
-      act = torch.argmax(logits + noise['action'], -1).to(torch.int32)
-    carry = dict(deter=dyn['deter'], stoch=dyn['stoch'], action=act)
+      outs = self.pol_outputs(self.feat2tensor(feat['deter'], feat['stoch']))
+      acts = self.pol_sample(outs, noise['action'])
+    prev = acts[act[0][0]] if single and torch.is_tensor(carry['action']) else acts
+    carry = dict(deter=dyn['deter'], stoch=dyn['stoch'], action=prev)
     out = {'dyn/deter': dyn['deter'], 'dyn/stoch': dyn['stoch']}
-    return carry, {'action': act}, out
+    return carry, acts, out
 
   # -- replay context (agent.py:312-340), K = replay_context -----------------------------
   def apply_replay_context(self, data, carry=None):
@@ -349,8 +489,10 @@ class Dreamer:
       first = data['consec'][:, 0] == 0
       rep = dict(deter=torch.where(first[:, None], rep['deter'], carry['deter']),
                  stoch=torch.where(first[:, None, None], rep['stoch'], carry['stoch']))
-    obs = {k: data[k][:, K:] for k in ('image', 'reward', 'is_first', 'is_last', 'is_terminal')}
-    prevact = data['action'][:, K - 1: -1]
+    img, vec, act = space_specs(self.cfg)
+    keys = [k for k, _ in img] + [v[0] for v in vec] + ['reward', 'is_first', 'is_last', 'is_terminal']
+    obs = {k: data[k][:, K:] for k in keys}
+    prevact = {a[0]: data[a[0]][:, K - 1: -1] for a in act}
     return rep, obs, prevact, data['stepid'][:, K:]
 
   # -- loss (agent.py:156-245) --------------------------------------------------------
@@ -360,7 +502,8 @@ class Dreamer:
     reset = obs['is_first']
     B, T = reset.shape
     losses, metrics = {}, {}
-    tokens = self.encoder(obs['image'])
+    img, vec, act = space_specs(cfg)
+    tokens = self.encoder(obs)
     carry, feat = self.observe(carry, tokens, prevact, reset, noise['observe'])
     los, mets = self.rssm_loss(feat)
     losses.update(los)
@@ -372,8 +515,7 @@ class Dreamer:
     if cfg.contdisc:
       con = con * (1 - 1 / cfg.horizon)
     losses['con'] = -binary_logp(self.con_logit(inp), con)
-    target = obs['image'].to(f32) / 255
-    losses['image'] = ((recon - target) ** 2).sum((-3, -2, -1))
+    losses.update(self.recon_losses(recon, obs))
 
     # imagination: forward only (imgfeat is stop-gradient'ed, ac_grads False)
     K, H = T, cfg.imag_length
@@ -381,17 +523,20 @@ class Dreamer:
       c = dict(deter=feat['deter'].reshape(B * K, -1),
                stoch=feat['stoch'].reshape(B * K, cfg.stoch, cfg.classes))
       deters, stochs, acts = [c['deter']], [c['stoch']], []
-      for h in range(H):
-        logits = self.pol_logits(self.feat2tensor(c['deter'], c['stoch']))
-        a = torch.argmax(logits + noise['imag_act'][:, h], -1)
-        c = self.imagine_step(c, F.one_hot(a, cfg.actions).to(f32), noise['imag_stoch'][:, h])
+      anoise = noise['imag_act']
+      if torch.is_tensor(anoise):
+        anoise = {act[0][0]: anoise}
+      for h in range(H + 1):
+        outs = self.pol_outputs(self.feat2tensor(c['deter'], c['stoch']))
+        a = self.pol_sample(outs, {k: v[:, h] for k, v in anoise.items()})
         acts.append(a)
+        if h == H:
+          break
+        c = self.imagine_step(c, self.action_embed(a), noise['imag_stoch'][:, h])
         deters.append(c['deter'])
         stochs.append(c['stoch'])
-      logits = self.pol_logits(self.feat2tensor(c['deter'], c['stoch']))
-      acts.append(torch.argmax(logits + noise['imag_act'][:, H], -1))
       imgdeter, imgstoch = torch.stack(deters, 1), torch.stack(stochs, 1)
-      imgact = torch.stack(acts, 1)
+      imgact = {k: torch.stack([a[k] for a in acts], 1) for k in acts[0]}
     inp = self.feat2tensor(imgdeter, imgstoch)
     los, ret, mets = self.imag_loss(imgact, inp, update)
     losses.update({k: v.mean(1).reshape(B, K) for k, v in los.items()})
@@ -411,19 +556,24 @@ class Dreamer:
         twohot_loss(vlogits, self.bins, padded) +
         cfg.slowreg * twohot_loss(vlogits, self.bins, slow))[:, :-1]
 
-    assert set(losses) == set(cfg.scales), (sorted(losses), sorted(cfg.scales))
+    scales = dict(cfg.scales)
+    rec = scales.pop('image')                                   # agent.py:75-78
+    scales.update({k: rec for k, _ in img})
+    scales.update({v[0]: rec for v in vec})
+    assert set(losses) == set(scales), (sorted(losses), sorted(scales))
     metrics.update({f'loss/{k}': v.mean() for k, v in losses.items()})
-    total = sum(v.mean() * cfg.scales[k] for k, v in losses.items())
+    total = sum(v.mean() * scales[k] for k, v in losses.items())
     entries = {'dyn/deter': feat['deter'], 'dyn/stoch': feat['stoch']}
     outs = dict(tokens=tokens, feat=feat, losses=losses, recon=recon,
-                imgdeter=imgdeter, imgstoch=imgstoch, imgact=imgact, ret=ret)
+                imgdeter=imgdeter, imgstoch=imgstoch, ret=ret,
+                imgact=imgact[act[0][0]].long() if len(act) == 1 else imgact)
     return total, carry, entries, outs, metrics
 
   def imag_loss(self, act, inp, update):                        # agent.py:382-446
     cfg = self.cfg
     rew = twohot_pred(self.rew_logits(inp), self.bins)
     con = torch.exp(binary_logp(self.con_logit(inp), torch.ones(())))
-    pol = self.pol_logits(inp)
+    pol = self.pol_outputs(inp)
     vlogits = self.val_logits(inp)
     val = twohot_pred(vlogits, self.bins)
     slowval = twohot_pred(self.slowval_logits(inp), self.bins)
@@ -435,9 +585,8 @@ class Dreamer:
     ret = lambda_return(last, term, rew, tarval, tarval, disc, cfg.lam)
     roffset, rscale = self.retnorm(ret, update)
     adv = (ret - tarval[:, :-1]) / rscale
-    logp_all = torch.log_softmax(pol, -1)
-    logpi = logp_all.gather(-1, act[..., None].long()).squeeze(-1)[:, :-1]
-    ent = -(torch.softmax(pol, -1) * logp_all).sum(-1)[:, :-1]
+    logpi, ent = self.pol_logp_entropy(pol, act)
+    logpi, ent = logpi[:, :-1], ent[:, :-1]
     losses = {}
     losses['policy'] = weight[:, :-1].detach() * -(
         logpi * adv.detach() + cfg.actent * ent)
@@ -515,10 +664,13 @@ def param_shapes(cfg):
   """Every optimised parameter and its shape, in the reference's naming; also the
   fan-in and outscale its initialiser uses (nets.py:144-197)."""
   D, H, S, C, g = cfg.deter, cfg.hidden, cfg.stoch, cfg.classes, cfg.blocks
-  U, A = cfg.units, cfg.actions
+  U = cfg.units
+  img, vec, act = space_specs(cfg)
+  A = sum(spec_width(a) for a in act)                           # DictConcat width of the action dict
   depths = [cfg.depth * m for m in cfg.mults]
-  minres = cfg.image[0] // 2 ** len(cfg.mults)
-  tokens = minres * minres * depths[-1]
+  minres = cfg.image[0] // 2 ** len(cfg.mults) if img else 0
+  sp = minres * minres * depths[-1]
+  tokens = (U if vec else 0) + sp
   out = {}
 
   def lin(name, i, o, outscale=1.0):
@@ -537,8 +689,12 @@ def param_shapes(cfg):
   def nrm(name, n):
     out[f'{name}/scale'] = ((n,), None, None)
 
-  cin = cfg.image[2]
-  for i, d in enumerate(depths):
+  if vec:                                                       # rssm.py:218-224
+    i = sum(spec_width(v) for v in vec)
+    for l in range(cfg.get('enc_layers', 3)):
+      lin(f'enc/mlp{l}', i, U); nrm(f'enc/mlp{l}norm', U); i = U
+  cin = cfg.image[2] if img else 0
+  for i, d in enumerate(depths if img else []):
     cnv(f'enc/cnn{i}', cin, d); nrm(f'enc/cnn{i}norm', d); cin = d
   lin('dyn/dynin0', D, H); nrm('dyn/dynin0norm', H)
   lin('dyn/dynin1', S * C, H); nrm('dyn/dynin1norm', H)
@@ -550,14 +706,21 @@ def param_shapes(cfg):
   lin('dyn/prior0', D, H); nrm('dyn/prior0norm', H)
   lin('dyn/prior1', H, H); nrm('dyn/prior1norm', H)
   lin('dyn/priorlogit', H, S * C)
-  blk('dec/sp0', D, minres * minres * depths[-1])
-  lin('dec/sp1', S * C, 2 * U); nrm('dec/sp1norm', 2 * U)
-  lin('dec/sp2', 2 * U, minres * minres * depths[-1])
-  nrm('dec/spnorm', depths[-1])
-  cin = depths[-1]
-  for i in reversed(range(len(depths) - 1)):
-    cnv(f'dec/conv{i}', cin, depths[i]); nrm(f'dec/conv{i}norm', depths[i]); cin = depths[i]
-  cnv('dec/imgout', cin, cfg.image[2])
+  if vec:                                                       # rssm.py:326-334
+    i = D + S * C
+    for l in range(cfg.get('dec_layers', 3)):
+      lin(f'dec/mlp/linear{l}', i, U); nrm(f'dec/mlp/norm{l}', U); i = U
+    for v in vec:
+      lin(f'dec/vec/{v[0]}/' + ('logits' if v[1] == 'disc' else 'pred'), U, spec_width(v))
+  if img:
+    blk('dec/sp0', D, sp)
+    lin('dec/sp1', S * C, 2 * U); nrm('dec/sp1norm', 2 * U)
+    lin('dec/sp2', 2 * U, sp)
+    nrm('dec/spnorm', depths[-1])
+    cin = depths[-1]
+    for i in reversed(range(len(depths) - 1)):
+      cnv(f'dec/conv{i}', cin, depths[i]); nrm(f'dec/conv{i}norm', depths[i]); cin = depths[i]
+    cnv('dec/imgout', cin, cfg.image[2])
   F_ = D + S * C
 
   def headmlp(name, layers):
@@ -567,7 +730,13 @@ def param_shapes(cfg):
 
   headmlp('rew', cfg.rew_layers); lin('rew/head/logits', U, cfg.bins, 0.0)
   headmlp('con', cfg.con_layers); lin('con/head/logit', U, 1, 1.0)
-  headmlp('pol', cfg.pol_layers); lin('pol/head/action/logits', U, A, 0.01)
+  headmlp('pol', cfg.pol_layers)
+  for a in act:                                                 # heads.py:103-112, 146-155
+    n = int(np.prod(a[2], dtype=np.int64))
+    if a[1] == 'disc':
+      lin(f'pol/head/{a[0]}/logits', U, n * a[3], 0.01)
+    else:
+      lin(f'pol/head/{a[0]}/mean', U, n, 0.01); lin(f'pol/head/{a[0]}/stddev', U, n, 0.01)
   headmlp('val', cfg.val_layers); lin('val/head/logits', U, cfg.bins, 0.0)
   return out
 
@@ -598,9 +767,17 @@ def make_noise(cfg, B, T, seed=0):
   def gumbel(*shape):
     u = torch.rand(shape, generator=gen, dtype=f32).clamp_(1e-20, 1 - 1e-7)
     return -torch.log(-torch.log(u))
-  S, C, A, H = cfg.stoch, cfg.classes, cfg.actions, cfg.imag_length
-  return dict(observe=gumbel(B, T, S, C), imag_stoch=gumbel(B * T, H, S, C),
-              imag_act=gumbel(B * T, H + 1, A))
+  S, C, H = cfg.stoch, cfg.classes, cfg.imag_length
+  out = dict(observe=gumbel(B, T, S, C), imag_stoch=gumbel(B * T, H, S, C))
+  _, _, act = space_specs(cfg)
+  if len(act) == 1 and act[0][1:3] == ('disc', ()):             # the original layout: one tensor
+    out['imag_act'] = gumbel(B * T, H + 1, act[0][3])
+  else:
+    out['imag_act'] = {
+        key: gumbel(B * T, H + 1, *shape, classes) if kind == 'disc'
+        else torch.randn((B * T, H + 1, *shape), generator=gen, dtype=f32)
+        for key, kind, shape, classes in act}
+  return out
 
 
 def tiny_config(**over):

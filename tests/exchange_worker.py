@@ -44,7 +44,7 @@ def main():
     noise = cases.to_device(do.make_noise(ocfg, B, T, seed=1000 * rank + it))
     for name, a in agents.items():
       carry = a.init_train(B)
-      _, _, mets = a.train(carry, data, {k: v.clone() for k, v in noise.items()})
+      _, _, mets = a.train(carry, data, cases.clone(noise))
       norms[name].append(float(mets['opt/grad_norm']))
   torch.cuda.synchronize()
   a, b = agents['bucketed'].store, agents['plain'].store

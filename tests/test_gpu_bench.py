@@ -43,7 +43,8 @@ def test_policy_runs_without_autograd():
          'is_first': torch.ones(n, dtype=torch.bool, device='cuda')}
   assert torch.is_grad_enabled()
   carry, act, out = agent.policy(carry, obs)
-  for t in list(carry) + list(act.values()) + list(out.values()):
+  leaves = [carry[0], carry[1], *carry[2].values(), *act.values(), *out.values()]
+  for t in leaves:
     assert not t.requires_grad and t.grad_fn is None
 
 

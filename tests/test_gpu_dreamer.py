@@ -246,7 +246,7 @@ def test_tc_convolutions_track_library_convolutions_at_size200m_widths():
   losses = []
   for a in agents:
     a.opt.launch = lambda: torch.zeros(())          # keep the raw gradients in the buffer
-    _, _, mets = a.train(a.init_train(B), data, {k: v.clone() for k, v in noise.items()})
+    _, _, mets = a.train(a.init_train(B), data, cases.clone(noise))
     losses.append(float(mets['loss']))
   assert abs(losses[0] - losses[1]) <= 2e-2 * abs(losses[1]), losses
   for k in agents[0].store.specs:
@@ -313,3 +313,65 @@ def test_product_matches_the_committed_oracle_golden():
     assert rel(carry[0], torch.from_numpy(want[f's{it}/deter_last'])) < RTOL
     for k in gg.PROBES:
       assert close(grads[k], want[f's{it}/gradnorm/{k}'], GTOL), (it, k)
+
+
+@pytest.mark.parametrize('case', sorted(cases.SPACE_CASES))
+def test_vector_observations_and_action_dicts_match_oracle_fp32(case):
+  """dreamerv3/rssm.py:215-224 (symlog + DictConcat + MLP encoder), :323-334 (vector decoder heads),
+  nets.py:467-500 (action DictConcat), heads.py:103-155 (categorical / bounded_normal policy heads):
+  two updates and a policy step on mixed image + vector observations with discrete and continuous
+  actions, vectors only (DMC-proprio shape), and two image keys with a vector-valued discrete action."""
+  ocfg, obs_space, act_space = cases.oracle_config_for(case)
+  vals = do.init_params(ocfg, 7, outscale_override=1.0)
+  oracle = do.Dreamer(ocfg, {k: v.clone() for k, v in vals.items()})
+  agent = dreamerv3.Agent(obs_space, act_space, cases.product_config(ocfg, 'float32'),
+                          values={k: v.numpy() for k, v in vals.items()})
+  assert sorted(agent.store.specs) == sorted(vals), set(agent.store.specs) ^ set(vals)
+  B, T = 3, 6
+  carry = agent.init_train(B)
+  for it in range(2):
+    data = cases.batch(ocfg, B, T, seed=40 + it)
+    noise = do.make_noise(ocfg, B, T, seed=it)
+    ocarry, oouts, omets, ograds, oo = oracle.train(data, noise)
+    carry, outs, mets = agent.train(carry, cases.to_device(data), cases.to_device(noise))
+    assert rel(mets['loss'], omets['loss']) < RTOL, (case, it)
+    for k, v in oo['losses'].items():
+      assert rel(agent.last_outs['losses'][k], v) < RTOL, (case, it, k)
+    feat = agent.last_outs['feat']
+    assert torch.equal(feat['stoch'].detach().argmax(-1).cpu(), oo['feat']['stoch'].argmax(-1))
+    assert rel(feat['deter'], oo['feat']['deter']) < RTOL
+    got = agent.last_outs['imgact']
+    want = oo['imgact']
+    if not isinstance(want, dict):
+      got, want = {'a': got}, {'a': want}
+    for k in want:
+      if want[k].dtype.is_floating_point:
+        assert rel(got[k], want[k]) < 1e-4, (case, k)       # sampled: mean + std * eps
+      else:
+        assert torch.equal(got[k].cpu().long(), want[k].long()), (case, k)
+    worst = max((rel2(agent.store.view('master', k), oracle.p[k]), k) for k in oracle.p)
+    assert worst[0] < GTOL, (case, it, worst)
+  # one policy step on the same spaces
+  n = 4
+  g = torch.Generator().manual_seed(3)
+  obs = {k: v[:n, 0] for k, v in cases.batch(ocfg, n, T, seed=77).items()
+         if k in agent.obskeys}
+  first = torch.tensor([True, False, False, True])
+  pnoise = dict(stoch=do.make_noise(ocfg, n, 1, seed=5)['observe'][:, 0],
+                action={k: v[:n, 0] for k, v in (
+                    do.make_noise(ocfg, n, 1, seed=6)['imag_act'] if isinstance(
+                        do.make_noise(ocfg, n, 1, seed=6)['imag_act'], dict) else
+                    {agent.actkeys[0]: do.make_noise(ocfg, n, 1, seed=6)['imag_act']}).items()})
+  zero_act = {name: torch.zeros((n, *shape), dtype=torch.int32 if kind == 'disc' else torch.float32)
+              for name, kind, shape, _ in ocfg.actspec}
+  ocarry = dict(deter=torch.zeros(n, ocfg.deter), stoch=torch.zeros(n, ocfg.stoch, ocfg.classes),
+                action=zero_act)
+  _, oact, oout = oracle.policy(ocarry, obs, first, pnoise)
+  _, act, out = agent.policy(agent.init_policy(n), {**cases.to_device(obs), 'is_first': first.cuda()},
+                             noise=cases.to_device(pnoise))
+  assert rel(out['dyn/deter'], oout['dyn/deter']) < RTOL
+  for k, v in oact.items():
+    if v.dtype.is_floating_point:
+      assert rel(act[k], v) < 1e-4, k
+    else:
+      assert torch.equal(act[k].cpu(), v), k
