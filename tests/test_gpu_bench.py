@@ -132,3 +132,21 @@ def test_partial_restore_by_regex():
     if k.endswith('/kernel'):               # biases / scales start identical (zeros / ones)
       same = torch.equal(b.store.view('master', k), a.store.view('master', k))
       assert same == k.startswith('enc/'), k
+
+
+def test_entry_point_trains_on_the_dummy_env_with_every_key_kind(tmp_path):
+  """BASELINE config-1 environment (embodied/envs/dummy.py: image, float vector / matrix, integer
+  token / matrix observations; one discrete and one continuous action) through the config-level
+  entry point with the dreamerv3 agent: Driver, Replay rows for all keys, general encoder /
+  decoder / policy heads, learner updates."""
+  from embodied_b200.dreamerv3 import main as mainlib
+  mainlib.main([
+      '--configs', 'size1m', '--task', 'dummy_disc', '--logdir', str(tmp_path),
+      '--batch_size', '4', '--batch_length', '8', '--report_length', '8', '--replay.size', '5000',
+      '--run.envs', '4', '--run.steps', '300', '--run.train_ratio', '16', '--run.log_every', '-1',
+      '--run.report_every', '1000', '--run.save_every', '1000'])
+  rows = [json.loads(l) for l in (tmp_path / 'metrics.jsonl').read_text().strip().splitlines()]
+  keys = {k for row in rows for k in row}
+  for name in ('image', 'vector', 'token', 'float2d', 'int2d', 'policy', 'value', 'dyn'):
+    assert f'train/loss/{name}' in keys, (name, sorted(keys))
+  assert all(np.isfinite(v) for row in rows for k, v in row.items() if k.startswith('train/loss'))
