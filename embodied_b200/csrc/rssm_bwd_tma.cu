@@ -643,7 +643,8 @@ int launch_bwd(const emb_rssm_bwd_args& a, void* stream, bool dry) {
     if (per[i] > rssm_tma::kMaxPer)
       return emb::fail(-1, "%s: %d tiles per CTA exceed %d (model too wide for %d CTAs)", who, per[i],
                        rssm_tma::kMaxPer, a.ncta);
-    if (per[i] > maxper) maxper = per[i];
+    // `out` holds a layer's tile plus the slabs its k-lanes reduce through (rssm_tma.cuh out_tiles)
+    if (rssm_tma::out_tiles(per[i]) > maxper) maxper = rssm_tma::out_tiles(per[i]);
   }
   int stage_bytes = rssm_tma::kStageBytesDefault, stage_cap = 0;
   if (const char* e = getenv("EMB_TMA_STAGE_KB")) stage_bytes = atoi(e) * 1024;

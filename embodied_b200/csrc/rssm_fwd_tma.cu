@@ -50,6 +50,7 @@ using namespace rssm_tma;
 
 struct Plan {                 // static work split of one CTA; identical on producer and consumers
   int per_hid, per_gru, per_ph1, per_log;          // n8 tiles per CTA block, padded (gru: 3 per unit)
+  int wk;
   int raw_ph1;
   int ks_hid, ks_gru, ks_ph1, ks_log;              // k16 steps
   bool on_hid, on_gru, on_log;
@@ -57,7 +58,30 @@ struct Plan {                 // static work split of one CTA; identical on prod
   const unsigned char *blk_hid, *blk_gru, *blk_ph1, *blk_log;
 };
 
-__device__ __forceinline__ Plan make_plan(const emb_rssm_fwd_args& a) {
+// CTA -> batch row it serves in the sampling phase (or -1): CTAs WITHOUT tiles in the
+// block-diagonal layers, so that sampling runs underneath the other CTAs' dynhid0; the last
+// 16 CTAs when there are too few of those.
+__device__ __forceinline__ bool rows_on_spare_ctas(const emb_rssm_fwd_args& a) {
+  const int ncta = gridDim.x, G = a.G, units = a.D / a.G / 8;
+  const int cpg = max(1, ncta / G), per = (units + cpg - 1) / cpg, used = (units + per - 1) / per;
+  return (cpg - used) * G + (ncta - G * cpg) >= kRows;
+}
+__device__ __forceinline__ int row_of_cta(const emb_rssm_fwd_args& a, int cta) {
+  const int ncta = gridDim.x, G = a.G, units = a.D / a.G / 8;
+  const int cpg = max(1, ncta / G), per = (units + cpg - 1) / cpg, used = (units + per - 1) / per;
+  const int spare = cpg - used, tail = ncta - G * cpg;
+  int row = ncta - 1 - cta;
+  if (rows_on_spare_ctas(a)) {
+    const int g = cta / cpg, j = cta - g * cpg;
+    if (g >= G) row = G * spare + (cta - G * cpg);
+    else row = j >= used ? g * spare + (j - used) : -1;
+  }
+  return row >= 0 && row < kRows ? row : -1;
+}
+
+// `wk` = this CTA's index among the CTAs that do not serve a row (they share the two dense
+// layers obs0 | dynin0 and obslogit; a row CTA passes gridDim.x and owns no tiles).
+__device__ __forceinline__ Plan make_plan(const emb_rssm_fwd_args& a, int wk) {
   Plan p;
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int D = a.D, H = a.H, Dg = a.D / a.G, SC = a.S * a.C, Kh = Dg + 2 * H;
@@ -69,13 +93,15 @@ __device__ __forceinline__ Plan make_plan(const emb_rssm_fwd_args& a) {
   p.per_ph1 = pad_tiles(p.raw_ph1, 1);
   const int tiles_log = SC / 8, raw_log = (tiles_log + ncta - 1) / ncta;
   p.per_log = pad_tiles(raw_log, 1);
-  p.u0_log = min(tiles_log, cta * raw_log); p.u1_log = min(tiles_log, p.u0_log + raw_log);
+  p.wk = wk;
+  p.u0_log = min(tiles_log, wk * raw_log); p.u1_log = min(tiles_log, p.u0_log + raw_log);
   p.on_log = p.u0_log < p.u1_log;
   p.ks_hid = Kh / 16; p.ks_gru = Dg / 16; p.ks_ph1 = D / 16; p.ks_log = H / 16;
   p.blk_hid = reinterpret_cast<const unsigned char*>(a.w_hid) + (size_t)cta * p.ks_hid * p.per_hid * 256;
   p.blk_gru = reinterpret_cast<const unsigned char*>(a.w_gru) + (size_t)cta * p.ks_gru * p.per_gru * 256;
-  p.blk_ph1 = reinterpret_cast<const unsigned char*>(a.w_ph1) + (size_t)cta * p.ks_ph1 * p.per_ph1 * 256;
-  p.blk_log = reinterpret_cast<const unsigned char*>(a.w_logit) + (size_t)cta * p.ks_log * p.per_log * 256;
+  const int wb = min(wk, ncta - 1);
+  p.blk_ph1 = reinterpret_cast<const unsigned char*>(a.w_ph1) + (size_t)wb * p.ks_ph1 * p.per_ph1 * 256;
+  p.blk_log = reinterpret_cast<const unsigned char*>(a.w_logit) + (size_t)wb * p.ks_log * p.per_log * 256;
   return p;
 }
 
@@ -93,7 +119,7 @@ __device__ __forceinline__ bool __syncthreads_or_consumers(bool pred, float* scr
 __device__ __forceinline__ void ph1_range(const emb_rssm_fwd_args& a, const Plan& p, bool last,
                                           int& u0, int& u1) {
   const int total = (last ? a.H : 2 * a.H) / 8;
-  u0 = min(total, (int)blockIdx.x * p.raw_ph1);
+  u0 = min(total, p.wk * p.raw_ph1);
   u1 = min(total, u0 + p.raw_ph1);
 }
 
@@ -186,7 +212,10 @@ __device__ __forceinline__ void convert_staged(__nv_bfloat16* afrag, const float
   }
 }
 
-__global__ void __launch_bounds__(kAllThreads, 1)
+// 8 consumer warps + the weight-producer warp + one operand-fetch warp
+constexpr int kFwdThreads = kAllThreads + 32;
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
 rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int T = a.T, D = a.D, H = a.H, S = a.S, C = a.C, G = a.G;
@@ -230,12 +259,22 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   }
   __syncthreads();
 
-  const Plan p = make_plan(a);
+  const int myrow = row_of_cta(a, cta);
+  const bool rowcta = myrow >= 0;
+  int wk = cta;                                    // (row CTAs keep their dense tiles in the fallback)
+  if (rows_on_spare_ctas(a)) {
+    wk = ncta;
+    if (!rowcta) {
+      wk = 0;
+      for (int c = 0; c < cta; ++c) wk += row_of_cta(a, c) < 0;
+    }
+  }
+  const Plan p = make_plan(a, wk);
   {
     const int g0 = p.on_gru ? p.u0_gru / (Dg / 8) : 0;
-    for (int i = tid; i < Dg; i += kAllThreads) c_shid[i] = a.s_hid[g0 * Dg + i];
-    for (int i = tid; i < H; i += kAllThreads) c_sobs[i] = a.s_obs[i];
-    for (int i = tid; i < 3 * Dg; i += kAllThreads) c_bgru[i] = a.b_gru[(size_t)g0 * 3 * Dg + i];
+    for (int i = tid; i < Dg; i += kFwdThreads) c_shid[i] = a.s_hid[g0 * Dg + i];
+    for (int i = tid; i < H; i += kFwdThreads) c_sobs[i] = a.s_obs[i];
+    for (int i = tid; i < 3 * Dg; i += kFwdThreads) c_bgru[i] = a.b_gru[(size_t)g0 * 3 * Dg + i];
   }
   __syncthreads();
   __nv_bfloat16* deterA = reinterpret_cast<__nv_bfloat16*>(a.deterA);
@@ -265,6 +304,23 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
     if (p.on_log) segs[n++] = Seg{p.blk_log, p.per_log, p.ks_log, 0};
     run_producer(ring, segs, n, T, skip_last, (a.tma_cfg >> 24) & 0x7f);
   }
+  // Tenth warp (one lane): fetches P4's x1 fragments the moment the 16 row CTAs
+  // have published them (release / acquire counter a.barrier[32], +16 per step) -- the
+  // sampling phase of step t-1 runs underneath the first two k ranges of step t's dynhid0.
+  if (tid == kAllThreads && p.on_hid) {
+    const unsigned* flag = a.barrier + 32;
+    const uint32_t xpart_ = (uint32_t)H * kRows * 2, part_ = (uint32_t)Dg * kRows * 2;
+    for (int t = 0; t < T; ++t) {
+      const unsigned want = (unsigned)kRows * (unsigned)(t + 1);
+      unsigned v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+      } while ((int)(v - want) < 0);
+      fence_proxy_async();
+      mbar_expect_tx(afull2, xpart_);
+      bulk_g2s(abase + part_ + xpart_, x1A, xpart_, afull2);
+    }
+  }
   if (tid >= kCThreads) return;
 
   // ========================================================== consumer warps
@@ -275,8 +331,6 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
   // fragments in the first 32 n bytes of the A region, the fp32 tile behind them
   const size_t aregion = emb_tma::a_region_bytes(a);
   const bool stage_hid = aregion >= (size_t)kRows * Dg * 6, stage_obs = aregion >= (size_t)kRows * H * 6;
-  const int myrow = ncta - 1 - cta;                  // rows 0..15 are served by the LAST 16 CTAs
-  const bool rowcta = myrow >= 0 && myrow < kRows;
   const int gh = p.on_hid ? p.u0_hid / (Dg / 8) : 0;
   const uint32_t part = (uint32_t)Dg * kRows * 2, xpart = (uint32_t)H * kRows * 2;
 
@@ -310,15 +364,28 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
     finish_row(load_row(a.y1 + (size_t)myrow * H), H, myrow, a.s1, a.eps, red, nullptr,
                a.rstd + kRows + myrow, x1A);
   }
+  // x1 fragments of the next step are final: publish (generic writes -> later TMA reads)
+  auto publish_x1 = [&]() {
+    fence_proxy_async();
+    cbar();
+    if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 1;" :: "l"(a.barrier + 32) : "memory");
+  };
+  if (rowcta) publish_x1();
   bar.sync();
   issue_a01(0);
 
   // phase marks of CTA 0 (set 0) and of the CTA serving row 0 (set 1): timing[2][T][16]
 #define MARK(i)                                                              \
-  if (a.timing && (cta == 0 || cta == ncta - 1) && tid == 0) {               \
+  if (a.timing && (cta == 0 || myrow == 0) && tid == 0) {               \
     unsigned long long now_;                                                 \
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                  \
     a.timing[((size_t)(cta ? T : 0) + t) * 16 + (i)] = now_;                 \
+  }
+#define MARKALL(i)                                                           \
+  if (a.timing && t == 20 && tid == 0) {                                     \
+    unsigned long long now_;                                                 \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now_));                  \
+    a.timing[(size_t)2 * T * 16 + cta * 4 + (i)] = now_;                     \
   }
   for (int t = 0; t < T; ++t) {
     MARK(0)
@@ -330,11 +397,7 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
 
     // ------------------------------------------------------------------ P4
     if (p.on_hid) {
-      if (tid == 0) {       // part 2 of A: x1, final since the barrier just passed
-        mbar_expect_tx(afull2, xpart);
-        bulk_g2s(abase + part + xpart, x1A, xpart, afull2);
-      }
-      mbar_wait(afull01, aphase);
+      mbar_wait(afull01, aphase);   // (part 2 of A, x1, is fetched by the operand-fetch warp)
       // reset rows: deter_{t-1} enters as zero (rssm.py:76-77); rare, so patched in place
       float kp = tid < kRows ? ldcg(keep + tid) : 1.f;
       if (__syncthreads_or_consumers(kp == 0.f, red)) {
@@ -348,10 +411,14 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
         cbar();
       }
       MARK(1)
+      MARKALL(0)
       EMB_CONSUME(false, ring, p.per_hid, ks01, afrag4, nullptr, out, true)
+      MARKALL(1)
       mbar_wait(afull2, aphase);
       aphase ^= 1u;
+      MARKALL(2)
       EMB_CONSUME(false, ring, p.per_hid, ks2, afrag4 + (size_t)ks01 * 32, nullptr, out, false)
+      MARKALL(3)
       const int ncols = p.per_hid * 8, nvalid = (p.u1_hid - p.u0_hid) * 8;
       const float* pre = a.hid_pre + (size_t)t * RD;
       // epilogue: + hoisted action branch and bias -> yhid ; row sums of squares -> sumsq[t]
@@ -409,9 +476,9 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
       }
       cbar();
       MARK(12)
+      const int ncols = p.per_gru * 8, nu = p.u1_gru - p.u0_gru;
       EMB_CONSUME(false, ring, p.per_gru, p.ks_gru, afrag4, nullptr, out, true)
       MARK(13)
-      const int ncols = p.per_gru * 8, nu = p.u1_gru - p.u0_gru;
       // epilogue: GRU gates (rssm.py:152-158); columns of a unit: [reset 8 | cand 8 | update 8].
       // Loads of all of a thread's elements first (L2 latency once), then the maths.
       constexpr int kE = 4;
@@ -462,10 +529,10 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
       ph1_range(a, p, last, u0, u1);
       if (u0 < u1) {
         const uint4* dA = reinterpret_cast<const uint4*>(deterA + (size_t)(t & 1) * RD);
-        EMB_CONSUME(true, ring, p.per_ph1, p.ks_ph1, dA, abase, out, true)
         const int ncols = p.per_ph1 * 8, nvalid = (u1 - u0) * 8;
         // thread i: row i / 16; yobs columns also feed the row's sum of squares (P2's norm)
         const int r = tid >> 4, c0 = tid & 15;
+        EMB_CONSUME(true, ring, p.per_ph1, p.ks_ph1, dA, abase, out, true)
         float sq = 0.f;
         for (int c = c0; c < nvalid; c += 16) {
           const int col = u0 * 8 + c;
@@ -539,8 +606,10 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
       const int r = myrow;
       const bool live = r < a.B;
       if (live) {
-        // LP lanes per latent (<= 4 classes per lane): a warp samples 32 / LP latents at once
-        const int LP = C > 64 ? 32 : (C > 32 ? 16 : 8);
+        // LP lanes per latent (<= kNC classes per lane): a warp samples 32 / LP latents at once
+        // (size200m: 8 lanes x 8 classes, the 32 latents of a row in ONE round of the 8 warps)
+        constexpr int kNC = 8;
+        const int LP = C > 128 ? 32 : (C > 64 ? 16 : (C > 32 ? 8 : (C > 16 ? 4 : (C > 8 ? 2 : 1))));
         const int sub = lane / LP, ll = lane % LP, nsub = 32 / LP;
         const float* gum = a.gumbel + (size_t)t * RSC + (size_t)r * SC;
         const float* lrow = logit + (size_t)r * SC;
@@ -559,34 +628,37 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
           lrow = sl;
           gum = sl + SC;
         }
+        MARKALL(0)
 #pragma unroll 1
         for (int sb = warp * nsub; sb < S; sb += kCWarps * nsub) {
           const int sv = sb + sub;
           const bool lat = sv < S;
-          float lv[4], gv[4];
+          float lv[kNC], gv[kNC];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < kNC; ++i) {
             const int c = ll + LP * i;
             const bool on = lat && c < C;
             lv[i] = on ? (staged ? lrow[sv * C + c] : ldcg(lrow + (size_t)sv * C + c)) : -INFINITY;
             gv[i] = on ? (staged ? gum[sv * C + c] : ldcg(gum + (size_t)sv * C + c)) : 0.f;
           }
-          float m = fmaxf(fmaxf(lv[0], lv[1]), fmaxf(lv[2], lv[3]));
-          for (int o = LP >> 1; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-          float e[4], z = 0.f;
+          float m = lv[0];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { e[i] = (lat && ll + LP * i < C) ? expf(lv[i] - m) : 0.f; z += e[i]; }
+          for (int i = 1; i < kNC; ++i) m = fmaxf(m, lv[i]);
+          for (int o = LP >> 1; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          float e[kNC], z = 0.f;
+#pragma unroll
+          for (int i = 0; i < kNC; ++i) { e[i] = (lat && ll + LP * i < C) ? __expf(lv[i] - m) : 0.f; z += e[i]; }
           for (int o = LP >> 1; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+          const float rz = 1.0f / z, um = 1.0f - a.unimix, uc = a.unimix / (float)C;
           float best = -INFINITY;
           int arg = 0x7fffffff;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < kNC; ++i) {
             const int c = ll + LP * i;
             if (lat && c < C) {
-              const float pr = e[i] / z;
+              const float pr = e[i] * rz;
               a.probs[(size_t)t * RSC + (size_t)r * SC + (size_t)sv * C + c] = pr;
-              const float pm = (1.0f - a.unimix) * pr + a.unimix / (float)C;
-              const float v = logf(pm) + gv[i];
+              const float v = __logf(um * pr + uc) + gv[i];
               if (v > best || (v == best && c < arg)) { best = v; arg = c; }
             }
           }
@@ -602,6 +674,7 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
         }
       }
       cbar();
+      MARKALL(1)
       if (!last) {
         // y1'[r] = b1 + keep' * sum_s dynin1[s*C + idx_s]
         const float kn = live ? ldcg(keep_next + r) : 0.f;
@@ -612,7 +685,7 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
           const int c = gI * kCThreads * 4 + tid * 4;
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
           if (c < H && kn != 0.f) {
-#pragma unroll 16
+#pragma unroll 32
             for (int sv = 0; sv < S; ++sv) {
               const uint2 q = __ldg(reinterpret_cast<const uint2*>(w1 + ((size_t)sv * C + sidx[sv]) * H + c));
               const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
@@ -628,13 +701,14 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
             y.v[gI] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
+        MARKALL(3)
         finish_row(y, H, r, a.s1, a.eps, red, a.y1 + (size_t)(t + 1) * RH + (size_t)r * H,
                    a.rstd + (size_t)(t + 1) * 3 * kRows + kRows + r, x1A);
+        publish_x1();
       }
     }
     MARK(10)
-    bar.sync();
-    MARK(11)
+    MARK(11)       // no grid barrier here: dynhid0's last k range waits for the x1 counter instead
   }
 #undef MARK
 }
@@ -682,6 +756,7 @@ int launch_fwd(const emb_rssm_fwd_args& a, void* stream, bool dry) {
     return emb::fail(-1, "%s: %d/%d/%d/%d tiles per CTA exceed %d (model too wide for %d CTAs)", who,
                      per_hid, per_gru, per_ph1, per_log, rssm_tma::kMaxPer, a.ncta);
   if (a.S > 128) return emb::fail(-1, "%s: stoch=%d > 128", who, a.S);
+  if (a.C > 256) return emb::fail(-1, "%s: classes=%d > 256", who, a.C);
   if (a.H > 4096 || a.H % 4) return emb::fail(-1, "%s: hidden=%d must be <= 4096 and a multiple of 4", who, a.H);
   if (!a.sumsq_obs) return emb::fail(-1, "%s: the bf16 engine needs sumsq_obs", who);
   // tuning knobs (diagnostics): ring stage size in KiB and a cap on the stage count
@@ -695,9 +770,10 @@ int launch_fwd(const emb_rssm_fwd_args& a, void* stream, bool dry) {
     return emb::fail(-1, "%s: D/16=%d must be a multiple of the %d k-lanes of the deter layer", who,
                      a.D / 16, rssm_tma::kCWarps / rssm_tma::tile_groups(per_ph1));
   emb_rssm_fwd_args copy = a;
-  int nstages = stage_cap, maxper = per_gru > per_hid ? per_gru : per_hid;
-  if (per_ph1 > maxper) maxper = per_ph1;
-  if (per_log > maxper) maxper = per_log;
+  // `out` holds a layer's tile plus the slabs its k-lanes reduce through (rssm_tma.cuh out_tiles)
+  int nstages = stage_cap, maxper = 0;
+  for (int per : {per_hid, per_gru, per_ph1, per_log})
+    if (rssm_tma::out_tiles(per) > maxper) maxper = rssm_tma::out_tiles(per);
   const size_t smem = fwd_smem_bytes(a, maxper, stage_bytes, &nstages);
   if (nstages < 2)
     return emb::fail(-1, "%s: A operand (%d columns) leaves no room for the weight ring", who, Dg + 2 * a.H);
@@ -714,7 +790,7 @@ int launch_fwd(const emb_rssm_fwd_args& a, void* stream, bool dry) {
   if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return emb::fail_cuda(who);
   void* params[] = {&copy};
-  if (cudaLaunchCooperativeKernel(fn, dim3(a.ncta), dim3(rssm_tma::kAllThreads), params, smem,
+  if (cudaLaunchCooperativeKernel(fn, dim3(a.ncta), dim3(kFwdThreads), params, smem,
                                   (cudaStream_t)stream) != cudaSuccess)
     return emb::fail_cuda(who);
   emb::count_launch();

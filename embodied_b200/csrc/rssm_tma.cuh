@@ -243,9 +243,19 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   its own 16-byte fragments kADepth stages ahead with cp.async into a private
 //   shared-memory ring (`apriv`, kAPrivBytes for the CTA) -- no registers held.
 // `first` false accumulates onto `out` (a layer consumed in two k ranges).
-// Ends with a consumer barrier.
+// The k-lanes' partial sums meet in shared-memory slabs BEHIND `out` (out must hold
+// 16 x per*8*KW floats: out_tiles() below), summed in a fixed order by lane 0's warps:
+// no atomics, bit-reproducible.  Ends with a consumer barrier.
+// The fragment loads of k16 step i+1 are issued before the mma of step i (the loads are
+// volatile asm, so program order is issue order), and layers with few tiles per warp keep
+// two accumulator sets: one warp's chunk is otherwise a serial LDS -> HMMA -> HMMA chain
+// (measured 0.33 us per 24 KiB chunk with the data already in the ring -- slower than HBM).
 // (Not inlined: one body per (TW, A_GLOBAL) for all call sites keeps the
 // per-step instruction footprint inside the instruction cache.)
+__host__ __device__ __forceinline__ int out_tiles(int per) {        // tiles of `out` a layer needs
+  return per * (kCWarps / tile_groups(per));
+}
+
 template <int TW, bool A_GLOBAL>
 __device__ __noinline__ uint32_t consume(Ring r, int per, int ksteps, const uint4* __restrict__ afrag,
                                          unsigned char* apriv, float* out, bool first) {
@@ -258,13 +268,12 @@ __device__ __noinline__ uint32_t consume(Ring r, int per, int ksteps, const uint
   const uint32_t wofs = ((uint32_t)(tgi * TW) * 32u + lane) * 8u + (uint32_t)kl * per * 256u;
   const uint4* ap = afrag + (size_t)kl * 32 + lane;                  // this warp's first fragment
   const size_t astride = (size_t)KW * 32;                            // uint4 between its k16 steps
-  float acc[TW][4];
+  constexpr int NA = 1;                                              // accumulator sets
+  float acc[NA][TW][4];
 #pragma unroll
-  for (int j = 0; j < TW; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-  if (KW > 1 && first) {
-    for (int i = threadIdx.x; i < kRows * ncols; i += kCThreads) out[i] = 0.f;
-    cbar();
-  }
+  for (int s = 0; s < NA; ++s)
+#pragma unroll
+    for (int j = 0; j < TW; ++j) acc[s][j][0] = acc[s][j][1] = acc[s][j][2] = acc[s][j][3] = 0.f;
   int stage = r.stage;
   uint32_t phase = r.phase;
   const int nstages = r.nstages;
@@ -305,7 +314,7 @@ __device__ __noinline__ uint32_t consume(Ring r, int per, int ksteps, const uint
 #pragma unroll
         for (int j = 0; j < TW; ++j) b[j] = lds_u2(bp + j * 256);
 #pragma unroll
-        for (int j = 0; j < TW; ++j) mma_bf16_nv(acc[j], av, b[j]);
+        for (int j = 0; j < TW; ++j) mma_bf16_nv(acc[0][j], av, b[j]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&r.empty[stage]);
@@ -327,22 +336,43 @@ __device__ __noinline__ uint32_t consume(Ring r, int per, int ksteps, const uint
 #pragma unroll
         for (int j = 0; j < TW; ++j) b[j] = lds_u2(bp + j * 256);
 #pragma unroll
-        for (int j = 0; j < TW; ++j) mma_bf16_nv(acc[j], av, b[j]);
+        for (int j = 0; j < TW; ++j) mma_bf16_nv(acc[0][j], av, b[j]);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&r.empty[stage]);
       if (++stage == nstages) { stage = 0; phase ^= 1u; }
     }
   }
-  const int g = lane >> 2, q = lane & 3;
+  if (NA == 2) {
 #pragma unroll
-  for (int j = 0; j < TW; ++j) {
-    float* o = out + (tgi * TW + j) * 8 + 2 * q;
-    if (KW > 1) {
-      atomicAdd(o + g * ncols, acc[j][0]); atomicAdd(o + g * ncols + 1, acc[j][1]);
-      atomicAdd(o + (g + 8) * ncols, acc[j][2]); atomicAdd(o + (g + 8) * ncols + 1, acc[j][3]);
-    } else {
-      float2 lo = make_float2(acc[j][0], acc[j][1]), hi = make_float2(acc[j][2], acc[j][3]);
+    for (int j = 0; j < TW; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[0][j][e] += acc[NA - 1][j][e];
+  }
+  const int g = lane >> 2, q = lane & 3;
+  if (KW > 1) {
+    // k-lanes 1.. leave their partial tiles in the slabs behind `out`; k-lane 0 sums them in order
+    if (kl > 0) {
+      float* slab = out + (size_t)kl * kRows * ncols;
+#pragma unroll
+      for (int j = 0; j < TW; ++j) {
+        float* o = slab + (tgi * TW + j) * 8 + 2 * q;
+        *reinterpret_cast<float2*>(o + g * ncols) = make_float2(acc[0][j][0], acc[0][j][1]);
+        *reinterpret_cast<float2*>(o + (g + 8) * ncols) = make_float2(acc[0][j][2], acc[0][j][3]);
+      }
+    }
+    cbar();
+  }
+  if (kl == 0) {
+#pragma unroll
+    for (int j = 0; j < TW; ++j) {
+      float* o = out + (tgi * TW + j) * 8 + 2 * q;
+      float2 lo = make_float2(acc[0][j][0], acc[0][j][1]), hi = make_float2(acc[0][j][2], acc[0][j][3]);
+      for (int k = 1; k < KW; ++k) {
+        const float2 plo = *reinterpret_cast<const float2*>(o + (size_t)k * kRows * ncols + g * ncols);
+        const float2 phi = *reinterpret_cast<const float2*>(o + (size_t)k * kRows * ncols + (g + 8) * ncols);
+        lo.x += plo.x; lo.y += plo.y; hi.x += phi.x; hi.y += phi.y;
+      }
       if (!first) {
         const float2 plo = *reinterpret_cast<const float2*>(o + g * ncols);
         const float2 phi = *reinterpret_cast<const float2*>(o + (g + 8) * ncols);

@@ -379,7 +379,7 @@ class Scan:
         sumsq=torch.zeros((T, ROWS), dtype=f32, device=dev),
         sumsq_obs=torch.zeros((T, ROWS), dtype=f32, device=dev),
         deterA=torch.zeros(2 * ROWS * D + 2 * ROWS * H, dtype=torch.bfloat16, device=dev),
-        barrier=torch.zeros(4, dtype=torch.int32, device=dev))
+        barrier=torch.zeros(64, dtype=torch.int32, device=dev))      # [0] grid barrier, [32] x1 counter
     sv['x2_f32'] = sv['x2']
     if self.engine == ENG_LEGACY:
       sv['x2'] = a_fragments(sv['x2'])
@@ -398,7 +398,7 @@ class Scan:
     args = FwdArgs(B=B, T=T, D=D, H=H, S=S, C=C, G=G, engine=self.engine, ncta=self.ncta,
                    unimix=cfg.unimix, eps=1e-4)
     if self.timing:
-      sv['timing'] = torch.zeros((2, T, 16), dtype=torch.int64, device=dev)
+      sv['timing'] = torch.zeros((2 * T * 16 + 4 * 160,), dtype=torch.int64, device=dev)
     for k, v in {**w, **vec, **sv}.items():
       if k in ('x2_f32', 'w_hid_x2'):
         continue

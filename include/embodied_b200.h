@@ -185,7 +185,7 @@ typedef struct emb_rssm_fwd_args {
   float* rstd;           /* [T+1][3][16] rsqrt(mean(y^2)+eps) of y0[t], y1[t], yobs[t] */
   /* scratch */
   void* deterA;          /* bf16 engines scratch: (2*16*D + 2*16*H) bf16, A-fragment order */
-  uint32_t* barrier;     /* one ZEROED u32 */
+  uint32_t* barrier;     /* 64 ZEROED u32: [0] grid barrier; bf16 engine: [32] counts published x1 operands */
   uint64_t* timing;      /* optional [T][16] globaltimer marks of CTA 0 (NULL = off) */
   /* engine 1 only: the action branch is hoisted out of the scan entirely.  w_hid then
    * holds rows [deter_g | x0 | x1] of dynhid0 ([G][D/G+2H][D/G]) and the caller passes
