@@ -628,7 +628,6 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
           lrow = sl;
           gum = sl + SC;
         }
-        MARKALL(0)
 #pragma unroll 1
         for (int sb = warp * nsub; sb < S; sb += kCWarps * nsub) {
           const int sv = sb + sub;
@@ -674,7 +673,6 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
         }
       }
       cbar();
-      MARKALL(1)
       if (!last) {
         // y1'[r] = b1 + keep' * sum_s dynin1[s*C + idx_s]
         const float kn = live ? ldcg(keep_next + r) : 0.f;
@@ -701,7 +699,6 @@ rssm_fwd_tma_kernel(const __grid_constant__ emb_rssm_fwd_args a) {
             y.v[gI] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
         }
-        MARKALL(3)
         finish_row(y, H, r, a.s1, a.eps, red, a.y1 + (size_t)(t + 1) * RH + (size_t)r * H,
                    a.rstd + (size_t)(t + 1) * 3 * kRows + kRows + r, x1A);
         publish_x1();

@@ -57,16 +57,13 @@ def main():
   raw = sv['timing'].cpu().numpy().astype(np.int64)
   tm = raw[:2 * T * 16].reshape(-1, T, 16)
   per = raw[2 * T * 16:].reshape(-1, 4)[:148]
-  if per.any() and T > 20:
-    base = tm[1, 20, 9]          # the P2 barrier of step 19 as seen by the last CTA ... approximate origin
-    rel = (per - per[:, 2].min()) / 1e3
-    print('per-CTA dynhid0 marks at t=20 (us after the earliest start): start / range01 done / x1 landed / range2 done')
-    for name, col in zip(('start', 'r01', 'arrive', 'r2'), rel.T):
-      col = col[col > -1e6]
-      print(f'  {name}: min {col.min():.2f} median {np.median(col):.2f} max {col.max():.2f} argmax {int(col.argmax())}')
-    print('  row CTAs (staged, sampled, arrive, gathered):', [[round(float(x), 2) for x in rel[c]] for c in range(132, 148)])
-    print('  CTA 0 range 2: x1 landed, chunk-ready stamps, done (us):', [round(float(x - per[0, 2]) / 1e3, 2) for x in list(raw[2 * T * 16 + 144 * 4:][:10]) + [per[0, 3]]])
-    print('  slowest ten (cta, r2 done):', sorted(((round(float(v), 2), i) for i, v in enumerate(rel[:, 2])), reverse=True)[:24])
+  hid = [c for c in range(len(per)) if per[c, 2] and per[c, 3] > per[c, 2] > per[c, 1] > per[c, 0]]
+  if hid and T > 20:
+    # per-CTA marks of dynhid0 at t = 20 (CTAs with block-diagonal tiles): k ranges 0/1 done, x1 landed,
+    # k range 2 done, in us after the CTA's own start of the phase
+    rel = (per[hid] - per[hid][:, :1]) / 1e3
+    for name, col in zip(('ranges 0/1 done', 'x1 landed', 'range 2 done'), rel.T[[1, 2, 3]]):
+      print(f'  dynhid0 per CTA, {name}: min {col.min():.2f} median {np.median(col):.2f} max {col.max():.2f} us')
   names = ['P4 prologue', 'P4 gemm', 'bar', 'P5', 'bar', 'P1', 'bar', 'P2', 'bar', 'P3', 'bar']
   for which, tmx in enumerate(tm):
     d = np.diff(tmx[:, :12], axis=1)[8:].mean(0) / 1e3
