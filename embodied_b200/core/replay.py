@@ -67,7 +67,7 @@ class Replay:
     self.capacity = capacity and int(capacity)
     self.chunksize = int(chunksize)
     self.name = name
-    self.sampler = selector or selectors.Uniform(seed)
+    self.sampler = selector if selector is not None else selectors.Uniform(seed)
 
     self.chunks = {}      # UUID -> Chunk
     self.refs = {}        # UUID -> int
@@ -339,8 +339,24 @@ class Replay:
     itemid = self.itemid
     self.itemid += 1
     self.items[itemid] = (uuid, index)
-    self.sampler[itemid] = None   # Uniform ignores stepids (selectors.py:45-48)
+    # Uniform / Recency ignore the step ids (selectors.py:45-48,93-96); priority-based selectors
+    # key their priorities by them (selectors.py:172-177): formed on the host, no device read
+    wants = getattr(self.sampler, 'wants_stepids', False)
+    self.sampler[itemid] = self._window_stepids(uuid, index) if wants else None
     self.fifo.append(itemid)
+
+  def _window_stepids(self, uuid, index):
+    """The `length` step ids of the window starting at (chunk, index), as the 20-byte strings
+    the table holds: 16 B chunk uuid | be32 index (replay.py:90-91), following succ links."""
+    out, left = [], self.length
+    while left > 0:
+      chunk = self.chunks[uuid]
+      prefix = bytes(uuid)
+      take = min(left, chunk.length - index)
+      out += [prefix + (index + i).to_bytes(4, 'big') for i in range(take)]
+      left -= take
+      uuid, index = chunk.succ, 0
+    return out
 
   def _remove(self):                                 # replay.py:181-191
     itemid = self.fifo.popleft()

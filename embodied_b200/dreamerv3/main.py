@@ -175,10 +175,15 @@ def make_replay(config, folder, mode='train', **kwargs):     # main.py:183-196
   capacity = config.replay.size if mode == 'train' else config.replay.size / 10
   length = consec * batlen + config.replay_context
   assert config.batch_size * length <= capacity, (config.batch_size, length, capacity)
-  if config.replay.fracs.uniform < 1 and mode == 'train':
-    raise NotImplementedError(
-        'replay.fracs.uniform < 1: the Prioritized / Recency / Mixture selectors '
-        '(embodied/core/selectors.py:60-229) are outside the hot-path scope (SURVEY.md 8f rank 4)')
+  if config.replay.fracs.uniform < 1 and mode == 'train':                 # main.py:196-206
+    assert config.jax.compute_dtype in ('bfloat16', 'float32'), config.jax.compute_dtype
+    from ..core import selectors
+    recency = 1.0 / np.arange(1, int(capacity) + 1) ** config.replay.recexp
+    kwargs['selector'] = selectors.Mixture(dict(
+        uniform=selectors.Uniform(),
+        priority=selectors.Prioritized(**config.replay.prio),
+        recency=selectors.Recency(recency),
+    ), dict(config.replay.fracs))
   directory = elements.Path(config.logdir) / folder
   if config.replicas > 1:
     directory /= f'{config.replica:05}'
@@ -217,17 +222,25 @@ def main(argv=None):
   config = load_config(argv)
   logdir = elements.Path(config.logdir)
   print('Logdir:', logdir)
-  if config.script != 'train':
+  if config.script not in ('train', 'train_eval'):
     raise NotImplementedError(
-        f"script {config.script!r}: only `train` (embodied/run/train.py) is on the hot path; "
-        "train_eval / eval_only / parallel* are SURVEY.md 8f rank 4 and section 8 'out of scope'")
+        f"script {config.script!r}: `train` (embodied/run/train.py) and `train_eval` "
+        "(embodied/run/train_eval.py) are built; eval_only / parallel* are SURVEY.md section 8 "
+        "'out of scope' (portal RPC)")
   logdir.mkdir()
   import yaml
   (logdir / 'config.yaml').write(yaml.safe_dump(_plain(config)))
-  from ..run import train
+  from .. import run
   bind = functools.partial
-  train(bind(make_agent, config), bind(make_replay, config, 'replay'), bind(make_env, config),
-        bind(make_stream, config), bind(make_logger, config), run_args(config))
+  if config.script == 'train':
+    run.train(bind(make_agent, config), bind(make_replay, config, 'replay'), bind(make_env, config),
+              bind(make_stream, config), bind(make_logger, config), run_args(config))
+  else:                                                                   # main.py:77-86
+    run.train_eval(
+        bind(make_agent, config), bind(make_replay, config, 'replay'),
+        bind(make_replay, config, 'eval_replay', 'eval'), bind(make_env, config),
+        bind(make_env, config), bind(make_stream, config), bind(make_logger, config),
+        run_args(config))
 
 
 def _plain(config):

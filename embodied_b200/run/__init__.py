@@ -1,1 +1,2 @@
 from .train import train
+from .train_eval import train_eval

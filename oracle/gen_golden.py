@@ -196,6 +196,44 @@ def gen_chunkdir(ns):
   ns.elements.UUID.reset(debug=False)
 
 
+def fixed_recency(ns):
+  """The reference's Recency with the unbound `segment` of selectors.py:109 replaced by the
+  intended `p` (as shipped the class raises UnboundLocalError on its first draw; asserted in
+  tests/test_selectors_host.py).  Everything else -- table, bookkeeping, rescaling -- is the
+  reference's own code."""
+  class Recency(ns.selectors.Recency):
+    def _sample(self, tree, rng, bfactor=16):
+      path = []
+      for level, prob in enumerate(tree):
+        p = prob
+        for segment in path:
+          p = p[segment]
+        path.append(rng.choice(len(p), p=p))
+      return sum(index * bfactor ** (len(tree) - level - 1) for level, index in enumerate(path))
+  return Recency
+
+
+def gen_selectors(ns):
+  """Draw sequences of the reference's SampleTree / Prioritized / Recency / Mixture on the seeded
+  operation streams of tests/selector_cases.py."""
+  import sys, types
+  sys.path.insert(0, str(OUT.parent))
+  import selector_cases as sc
+  out = {}
+  for name, spec in sc.TREE_CASES.items():
+    out[f'tree/{name}'] = sc.drive_tree(ns.selectors.SampleTree(spec['branching'], seed=spec['seed']), spec)
+  for name, spec in sc.PRIO_CASES.items():
+    out[f'prio/{name}'] = sc.drive_selector(ns.selectors.Prioritized(seed=spec['seed'], **spec['kwargs']), spec['seed'])
+  Recency = fixed_recency(ns)
+  out['recency/draws'] = sc.drive_selector(Recency(sc.recency_uprobs(), seed=9), 9)
+  for level, table in enumerate(ns.selectors.Recency(sc.recency_uprobs(300, 0.7)).tree):
+    out[f'recency/table{level}'] = table
+  mod = types.SimpleNamespace(Uniform=ns.selectors.Uniform, Prioritized=ns.selectors.Prioritized,
+                              Recency=Recency, Mixture=ns.selectors.Mixture)
+  out['mixture/draws'] = sc.drive_selector(sc.make_mixture(mod), 21)
+  np.savez_compressed(OUT / 'selectors.npz', **out)
+
+
 def main():
   OUT.mkdir(parents=True, exist_ok=True)
   ns = refload.load()
@@ -205,6 +243,7 @@ def main():
   gen_driver(ns)
   gen_consec(ns)
   gen_chunkdir(ns)
+  gen_selectors(ns)
   for p in sorted(OUT.glob('*.npz')):
     print(p.name, p.stat().st_size)
 
