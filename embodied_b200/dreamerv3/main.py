@@ -41,9 +41,11 @@ def builtin_configs():
       logger=dict(outputs=['jsonl'], filter='score|length|fps|ratio|train/loss/', timer=True),
       env=dict(dummy=dict(), synthetic=dict(size=[64, 64, 3], classes=5, length=500)),
       replay=dict(size=5e6, online=True, chunksize=1024,
-                  fracs=dict(uniform=1.0, priority=0.0, recency=0.0)),
+                  fracs=dict(uniform=1.0, priority=0.0, recency=0.0),
+                  prio=dict(exponent=0.8, maxfrac=0.5, initial=float('inf'), zero_on_sample=True),
+                  priosignal='model', recexp=1.0),
       run=dict(steps=1e10, train_ratio=32.0, log_every=120, report_every=300, save_every=900,
-               envs=16, report_batches=1, from_checkpoint='', debug=True,
+               envs=16, eval_envs=4, eval_eps=1, report_batches=1, from_checkpoint='', debug=True,
                usage=dict(psutil=True)),
       jax=dict(platform='cuda', compute_dtype='bfloat16'),
       agent=configlib.schema('size200m'))

@@ -93,8 +93,8 @@ def test_unsupported_options_are_refused_by_name():
   config = mainlib.load_config(['--agent.ac_grads', 'True', '--agent.retnorm.impl', 'meanstd'])
   with pytest.raises(NotImplementedError, match='ac_grads.*retnorm.impl|retnorm.impl.*ac_grads'):
     configlib.from_reference(config.agent)
-  with pytest.raises(NotImplementedError, match='selectors'):
-    mainlib.make_replay(mainlib.load_config(['--replay.fracs.uniform', '0.5']), 'replay')
+  with pytest.raises(NotImplementedError, match='eval_only'):
+    mainlib.main(['--script', 'eval_only', '--logdir', '/tmp/never_made'])
   with pytest.raises(NotImplementedError, match='atari'):
     mainlib.make_env(mainlib.load_config(['--task', 'atari_pong']), 0)
 
@@ -141,3 +141,22 @@ def test_factories_wire_replay_stream_and_wrappers(tmp_path):
   assert (stream.length, stream.consec, stream.prefix, stream.strict) == (10, 2, 1, True)
   agent = mainlib.make_agent(config.update(random_agent=True))
   assert set(agent.act_space) == {'act_disc', 'act_cont'} or 'reset' not in agent.act_space
+
+
+def test_replay_fracs_build_the_selector_mixture(tmp_path):
+  """replay.fracs.uniform < 1 -> Mixture(Uniform, Prioritized(**replay.prio), Recency(1 / age ** recexp))
+  (dreamerv3/main.py:196-206); fractions of 0 drop their selector (selectors.py:203-206)."""
+  from embodied_b200.core import selectors
+  import doubles
+  config = mainlib.load_config(['--replay.fracs.uniform', '0.5', '--replay.fracs.priority', '0.5',
+                                '--replay.size', '40000', '--logdir', str(tmp_path)])
+  replay = mainlib.make_replay(config, 'replay', store=doubles.HostStore(1024, staging_rows=16))
+  mix = replay.sampler
+  assert isinstance(mix, selectors.Mixture)
+  assert [type(s) for s in mix.selectors] == [selectors.Prioritized, selectors.Uniform]
+  prio = mix.selectors[0]
+  assert (prio.exponent, prio.maxfrac, prio.initial, prio.zero_on_sample) == (0.8, 0.5, float('inf'), True)
+  # evaluation replays always sample uniformly (main.py:196 `mode == 'train'`)
+  assert isinstance(mainlib.make_replay(config, 'eval_replay', 'eval',
+                                        store=doubles.HostStore(1024, staging_rows=16)).sampler,
+                    selectors.Uniform)
