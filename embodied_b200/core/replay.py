@@ -246,7 +246,8 @@ class Replay:
       if k != 'reset':
         specs[k] = (s.dtype, s.shape)
     for k, s in (ext_space or {}).items():
-      specs[k] = (s.dtype, s.shape)
+      if k not in ('consec', 'stepid'):        # formed by the replay itself (replay.py:90-91, streams.py:118)
+        specs[k] = (s.dtype, s.shape)
     with self._lock:
       self._configure({k: np.zeros(sh, dt) for k, (dt, sh) in specs.items()})
 

