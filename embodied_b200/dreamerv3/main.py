@@ -93,15 +93,33 @@ def _typed(old, tokens, key):
   return one(old, tokens[0])
 
 
-def load_config(argv=None, configs_file=None):
+def _yaml_load(text):
+  """safe_load with YAML 1.2 floats: the reference reads its configs with ruamel.yaml, for which
+  `1e5` / `3e-4` / `inf` are numbers; PyYAML's 1.1 resolver leaves them strings."""
+  import re
+  import yaml
+
+  class Loader(yaml.SafeLoader):
+    pass
+  Loader.add_implicit_resolver(
+      'tag:yaml.org,2002:float',
+      re.compile(r'^[-+]?(?:[0-9][0-9_]*\.?[0-9_]*|\.[0-9_]+)(?:[eE][-+]?[0-9]+)?$|^[-+]?\.?(?:inf|Inf|INF)$|^\.?(?:nan|NaN|NAN)$'),
+      list('-+0123456789.in'))
+  def as_float(loader, node):
+    text = loader.construct_scalar(node).replace('_', '').lower().replace('.inf', 'inf').replace('.nan', 'nan')
+    return float(text)
+  Loader.add_constructor('tag:yaml.org,2002:float', as_float)
+  return yaml.load(text, Loader=Loader)
+
+
+def load_config(argv=None, configs_file=None, builtin=None):
   """The run configuration as an elements.Config (main.py:22-31)."""
   flags = parse_flags(list(sys.argv[1:] if argv is None else argv))
   configs_file = (flags.pop('configs-file', None) or [configs_file])[0]
   if configs_file:
-    import yaml
-    blocks = yaml.safe_load(elements.Path(configs_file).read())
+    blocks = _yaml_load(elements.Path(configs_file).read())
   else:
-    blocks = builtin_configs()
+    blocks = (builtin or builtin_configs)()
   config = elements.Config(blocks['defaults'])
   for name in flags.pop('configs', []):
     if name == 'defaults':

@@ -13,6 +13,12 @@ def dummy_spaces():
   return env.obs_space, act
 
 
+def vector_spaces():
+  """The dummy env without its image: the encoder is DictEmbed + MLP only."""
+  obs, act = dummy_spaces()
+  return {k: v for k, v in obs.items() if k != 'image'}, act
+
+
 def small_spaces():
   """A 16x16 two-camera + vector case: the 3x3/stride-2 SAME pool on odd and even sizes."""
   from embodied_b200 import elements

@@ -160,3 +160,40 @@ def test_replay_fracs_build_the_selector_mixture(tmp_path):
   assert isinstance(mainlib.make_replay(config, 'eval_replay', 'eval',
                                         store=doubles.HostStore(1024, staging_rows=16)).sampler,
                     selectors.Uniform)
+
+
+# ------------------------------------------------------------------------------ ppo/main.py
+PPO_YAML = pathlib.Path('/root/reference/ppo/configs.yaml')
+
+
+def test_yaml_12_floats():
+  """`1e5`, `3e-4`, `inf` are numbers for the reference's ruamel.yaml reader (configs.yaml:41,109)."""
+  tree = mainlib._yaml_load('a: 1e5\nb: 3e-4\nc: inf\nd: 16\ne: 1.5\nf: name\ng: [1, 2e2]\nh: True\n')
+  assert tree == dict(a=1e5, b=3e-4, c=float('inf'), d=16, e=1.5, f='name', g=[1, 200.0], h=True)
+  assert isinstance(tree['d'], int) and isinstance(tree['a'], float)
+
+
+def test_ppo_builtin_tree_round_trips():
+  from embodied_b200.ppo import config as pcfg, main as pmain
+  config = pmain.load_config(['--logdir', '/tmp/x'])
+  assert pcfg.from_reference(config.agent) == pcfg.make()
+  assert (config.batch_size, config.batch_length, config.run.train_ratio, config.replay.size) == (16, 64, 3.0, 1e5)
+  debug = pmain.load_config(['--logdir', '/tmp/x', '--configs', 'debug'])
+  flat = pcfg.from_reference(debug.agent)
+  assert flat == pcfg.debug(), {k: (flat[k], pcfg.debug()[k]) for k in flat if flat[k] != pcfg.debug()[k]}
+  with pytest.raises(NotImplementedError, match='policy_dist_cont'):
+    pcfg.from_reference(config.update({'agent.policy_dist_cont': 'normal_logstd'}).agent)
+
+
+@pytest.mark.skipif(not PPO_YAML.exists(), reason='/root/reference not on this machine')
+def test_ppo_reference_configs_yaml_is_consumed_unchanged():
+  from embodied_b200.ppo import config as pcfg, main as pmain
+  ref = pmain.load_config(['--logdir', '/tmp/x'], configs_file=str(PPO_YAML))
+  own = pmain.load_config(['--logdir', '/tmp/x'])
+  assert pcfg.from_reference(ref.agent) == pcfg.from_reference(own.agent)
+  for key in ('batch_size', 'batch_length', 'replay_context', 'consec_train'):
+    assert ref[key] == own[key], key
+  assert ref.replay.size == own.replay.size == 1e5 and ref.run.train_ratio == own.run.train_ratio
+  dbg = pmain.load_config(['--logdir', '/tmp/x', '--configs', 'debug'], configs_file=str(PPO_YAML))
+  assert pcfg.from_reference(dbg.agent) == pcfg.debug()
+  assert (dbg.batch_size, dbg.batch_length, dbg.run.envs) == (8, 12, 4)
