@@ -197,7 +197,7 @@ class Driver:
       if not self._replay.store.configured:
         ext = getattr(getattr(policy, '__self__', policy), 'ext_space', None)
         self._replay.configure_spaces(
-            self._envs.obs_space, self.act_space, ext)
+            self._envs.obs_space, self.act_space, ext, workers=self.length)
       return self._step_fused(policy, per_env, step, episode)
     obs = self._envs.step(per_env)
     obs = {k: np.stack([x[k] for x in obs]) for k in obs[0].keys()}

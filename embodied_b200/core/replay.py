@@ -96,6 +96,9 @@ class Replay:
       from . import store as storelib
       store = storelib.DeviceStore(
           self.chunksize, device=device, staging_rows=staging_rows)
+    if int(store.chunksize) != self.chunksize:
+      raise ValueError(f'store.chunksize={store.chunksize} != chunksize={self.chunksize}: one slab '
+                       'of the store backs exactly one chunk')
     self.store = store
     self._workers_hint = int(workers)
     self._lock = threading.RLock()
@@ -204,6 +207,8 @@ class Replay:
     trans = {k: v for k, v in trans.items() if not k.startswith('log/')}
     n = len(next(iter(trans.values())))
     workers = range(n) if workers is None else workers
+    if not self.store.configured:
+      self._workers_hint = max(self._workers_hint, n)     # planned before the first reserve
     with self._lock:
       self._flush()
       if not self.store.configured:
@@ -235,9 +240,13 @@ class Replay:
         done += m
 
   # -- three-phase add used by the fused Driver step -------------------------
-  def configure_spaces(self, obs_space, act_space, ext_space=None):
+  def configure_spaces(self, obs_space, act_space, ext_space=None, workers=None):
     """Fix the row layout up front from spaces (obs minus log/, actions minus
-    reset, the agent's replay-context entries) instead of from a first row."""
+    reset, the agent's replay-context entries) instead of from a first row.
+    `workers`: how many streams will append (the Driver's env count): every one
+    holds a current chunk, so the slab pool is planned for them up front."""
+    if workers:
+      self._workers_hint = max(self._workers_hint, int(workers))
     specs = {}
     for k, s in obs_space.items():
       if not k.startswith('log/'):
