@@ -537,6 +537,223 @@ def run_sweep(args):
     dist.destroy_process_group()
 
 
+# ---------------------------------------------- configs 3 / 4: the Driver + Replay half
+ROWS_WORKLOADS = {
+    # name: (BASELINE config, envs in all, shards the config names, env factory, policy kind)
+    'atari_rows': ('config 3: Atari-shape image u8[84,84,1], 18 discrete actions, 1024 envs, replay sharded '
+                   'by worker (Driver + Replay half; the dreamerv3 update of this config runs at 96x96, SURVEY F7)',
+                   1024, 8),
+    'proprio_rows': ('config 4: DMC-proprio-shape dummy (orientations f32[14], height f32[], velocity f32[9], '
+                     'action f32[6]), 512 envs, Driver + Replay + a host old-API policy (the director agent\'s '
+                     'role; its networks are not built)', 512, 4),
+}
+
+
+def rows_cpu_line(workload, seconds=8.0):
+  """The reference's CPU path for a rows workload on this host: oracle Driver (serial, the
+  reference default) + OracleReplay.add per transition + sample(B) -> Consec view every
+  B*T/train_ratio env steps, same synthetic envs, a host random policy; timed over >= `seconds`
+  of steady state with time.perf_counter.  Single-threaded Python like the reference."""
+  import itertools
+  from oracle import host_oracle as ho
+  from embodied_b200.envs import synthetic
+  name, total_envs, shards = ROWS_WORKLOADS[workload]
+  atari = workload == 'atari_rows'
+  n = total_envs
+  if atari:
+    envs = [synthetic.SyntheticImage(i, size=(84, 84, 1), classes=18, length=500) for i in range(n)]
+  else:
+    envs = [synthetic.SyntheticProprio(i, length=500) for i in range(n)]
+  replay = ho.OracleReplay(L, int(2e5), 1024, True, 0, ids=itertools.count(1))
+  driver = ho.OracleDriver(envs, {k: v for k, v in envs[0].act_space.items() if k != 'reset'})
+  driver.callbacks.append(lambda row, w: replay.add(row, w))
+  rng = np.random.default_rng(0)
+  acts = (rng.integers(0, 18, (4, n)).astype(np.int32) if atari else
+          rng.uniform(-1, 1, (4, n, 6)).astype(np.float32))
+  state = {'t': 0}
+
+  def policy(carry, obs):
+    if atari:
+      ho.normalize_image(obs['image'])                       # the agent's input cast (rssm.py:230)
+    state['t'] += 1
+    return carry, {'action': acts[state['t'] % 4]}, {}
+  per_step = max(1, TRAIN_RATIO * n // (B * T))
+  while len(replay) < 4 * B * L:
+    driver.step(policy)
+  t0, steps = time.perf_counter(), 0
+  while time.perf_counter() - t0 < seconds:
+    driver.step(policy)
+    for _ in range(per_step):
+      ho.consec_view(replay.sample(B), T, 0, PREFIX)
+    steps += 1
+  dt = (time.perf_counter() - t0) / steps
+  return {'value': n / dt, 'unit': 'env steps/s', 'cores': 1, 'kind': 'port',
+          'sample': f'{steps} Driver steps over {n} envs + {per_step} x (Replay.sample({B}) + Consec view) each, '
+                    f'{seconds:.0f} s of steady state; oracle/host_oracle.py = numpy restatement of '
+                    'embodied/core/{driver,replay,chunk,selectors,streams}.py (pinned byte for byte against '
+                    'the reference files, tests/test_oracle_pinned.py)', 'seconds_per_step': dt}
+
+
+def run_rows_reference(args):
+  line = rows_cpu_line(args.workload, seconds=max(5.0, 2.0 * (args.steps + args.warmup)))
+  print(json.dumps({
+      'impl': 'reference', 'metric': 'env_steps_per_sec', 'value': line['value'], 'unit': 'env steps/s',
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+      'ms_per_step': line['seconds_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'strong',
+      'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+      'config': {'workload': ROWS_WORKLOADS[args.workload][0] + ' -- CPU restatement of the reference (oracle/)'},
+      'cpu_baseline': line,
+      'e2e': {'value': line['value'], 'unit': 'env steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}),
+      flush=True)
+
+
+def run_rows(args):
+  """BASELINE configs 3 and 4, the part of them this library computes: N envs stepped on the
+  host -> pinned staging -> ONE H2D -> emb_driver_stage_obs (append + normalise) -> a device
+  policy stand-in -> emb_driver_scatter_mask_actions, and one Replay.sample(B=16) + Consec per
+  `train_ratio` env steps (emb_replay_gather).  One step = one Driver step over this rank's envs.
+  `value`: the step with observations resident in HBM; `e2e`: through Driver(...) over host envs."""
+  import torch
+  import torch.distributed as dist
+  import embodied_b200 as embodied
+  from embodied_b200 import _lib, elements
+  from embodied_b200.envs import synthetic
+  rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  peak, peak_src = peaks()
+  name, total_envs, shards = ROWS_WORKLOADS[args.workload]
+  n = total_envs // world                                       # strong split: the config fixes the env count
+  atari = args.workload == 'atari_rows'
+  if atari:
+    mk = lambda i: synthetic.SyntheticImage(rank * n + i, size=(84, 84, 1), classes=18, length=500)
+  else:
+    mk = lambda i: synthetic.SyntheticProprio(rank * n + i, length=500)
+  env = mk(0)
+  obs_space, act_space = env.obs_space, env.act_space
+  g = torch.Generator(device='cuda').manual_seed(rank)
+
+  class Policy:                                                  # device policy stand-in, Agent protocol
+    device_obs = True
+    ext_space = {}
+    def __init__(self):
+      if atari:
+        self.acts = torch.randint(0, 18, (4, n), generator=g, device='cuda', dtype=torch.int32)
+      else:
+        self.acts = torch.rand((4, n, 6), generator=g, device='cuda') * 2 - 1
+      self.t = 0
+    def init_policy(self, k):
+      return ()
+    def policy(self, carry, obs, mode='train'):
+      self.t += 1
+      return carry, {'action': self.acts[self.t % 4]}, {}
+
+  agent = Policy()
+  replay = embodied.Replay(L, int(args.capacity), chunksize=1024, online=True, seed=0,
+                           staging_rows=n, workers=n)
+  stream = iter(embodied.streams.Consec(embodied.streams.Stateless(replay.sample, B, 'train'),
+                                        length=T, consec=1, prefix=PREFIX, strict=True, contiguous=True))
+  driver = embodied.Driver([(lambda i=i: mk(i)) for i in range(n)], parallel=False, fetch_outs=False)
+  driver.on_step(replay.add)
+  samples_per_step = max(1, TRAIN_RATIO * n // (B * T))
+  state = {'on': False, 'last': None}
+
+  def sample(trans=None, k=None):
+    if state['on']:
+      for _ in range(samples_per_step):
+        state['last'] = next(stream)
+  driver.on_batch(sample)
+  driver.reset(agent.init_policy)
+  while len(replay) < 4 * B * L:
+    driver(agent.policy, steps=n)
+  state['on'] = True
+  rowbytes = replay.store.bytes_per_row
+  res = {k: (torch.randint(0, 256, (n, *s.shape), generator=g, device='cuda', dtype=torch.uint8)
+             if s.dtype == np.uint8 else
+             torch.zeros((n, *s.shape), dtype=torch.bool, device='cuda') if s.dtype == bool else
+             torch.randn((n, *s.shape), generator=g, device='cuda'))
+         for k, s in obs_space.items()}
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+  def step_e2e():
+    driver(agent.policy, steps=n)
+    return state['last']['reward'][0, 0].cpu()
+
+  def step_resident():
+    _, acts, _ = agent.policy((), res)
+    replay.add_batch({**res, **acts})
+    sample()
+
+  def timed(fn):
+    for _ in range(max(args.warmup, 3)):
+      fn()
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+    total = 0.0
+    for _ in range(args.steps):
+      flush.zero_()
+      torch.cuda.synchronize()
+      t0 = time.perf_counter()
+      a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      a.record()
+      fn()
+      b.record()
+      torch.cuda.synchronize()
+      # the step is host-driven (env stepping, index bookkeeping): wall time of the synchronised
+      # step, never less than the device span
+      total += max(time.perf_counter() - t0, a.elapsed_time(b) * 1e-3)
+    t = torch.tensor([total], device='cuda', dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) / args.steps
+
+  launches0 = _lib.launch_count()
+  with ClockSampler(local) as clocks:
+    dt = timed(step_resident)
+    launches = _lib.launch_count() - launches0
+    dt_e2e = timed(step_e2e)
+  # the gather launch alone, CUDA events on its stream, L2 flushed
+  us = []
+  for _ in range(10):
+    flush.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    batch = next(stream)
+    b.record()
+    torch.cuda.synchronize()
+    us.append(a.elapsed_time(b) * 1e3)
+  gather_bytes = 2 * B * L * (rowbytes + 4)
+  med = sorted(us)[len(us) // 2]
+  h2d = sum(int(np.dtype(s.dtype).itemsize * np.prod(s.shape, dtype=np.int64)) for s in obs_space.values()) * n
+  line = {
+      'metric': 'env_steps_per_sec', 'value': world * n / dt, 'unit': 'env steps/s', 'n_gpus': world,
+      'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': dt * 1e3,
+      'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
+      'config': {'workload': name, 'envs_per_gpu': n, 'batch': [B, T], 'row_bytes': rowbytes,
+                 'samples_per_step': samples_per_step,
+                 'parallelism': f'{world} replay shards by worker, no collective',
+                 'cache': 'L2 flushed (256 MiB write) before every timed step'},
+      'e2e': {'value': world * n / dt_e2e, 'unit': 'env steps/s', 'ms_per_step': dt_e2e * 1e3,
+              'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4 + n * (4 if atari else 24)},
+      'gpu_launches': launches,
+      'roofline': {'kernel': f'rows_kernel (emb_replay_gather, B={B} L={L}, whole Replay.sample call)',
+                   'bound': 'hbm', 'achieved': gather_bytes / (med * 1e-6) / 1e9, 'peak': peak,
+                   'peak_source': peak_src, 'unit': 'GB/s', 'frac': gather_bytes / (med * 1e-6) / 1e9 / peak,
+                   'us_per_launch': med, 'algorithmic_bytes': gather_bytes, 'traffic': None},
+      'clocks': clocks.summary(),
+      'cpu_baseline': None}
+  if rank == 0:
+    if world == 1 and not args.no_cpu:
+      line['cpu_baseline'] = rows_cpu_line(args.workload)
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def workload_name(args):
   if args.agent == 'feed':
     return ('config 2 PLUMBING ONLY: Driver(256 envs, 64x64x3 u8) + Replay(L=65, 53 299 B rows '
@@ -718,15 +935,20 @@ def main():
   ap.add_argument('--no-cpu', action='store_true')
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                   help='weak: 256 envs and a (16, 64) batch PER GPU; strong: in all (SURVEY 8e)')
-  ap.add_argument('--workload', default='train', choices=['train', 'replay_sweep'],
-                  help='train = BASELINE config 2 (the headline); replay_sweep = config 5')
+  ap.add_argument('--workload', default='train', choices=['train', 'replay_sweep', 'atari_rows', 'proprio_rows'],
+                  help='train = BASELINE config 2 (the headline); replay_sweep = config 5; atari_rows / '
+                       'proprio_rows = the Driver + Replay half of configs 3 / 4')
   ap.add_argument('--sweep-points', default='', help='e.g. 16x64,128x256 (default: the full 5x5 grid)')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3 if args.impl != 'reference' else 1)
   if args.impl == 'reference':
-    run_reference(args)
+    if int(os.environ.get('RANK', 0)) != 0:
+      return                                   # rank 0 alone runs the CPU arm
+    run_rows_reference(args) if args.workload in ROWS_WORKLOADS else run_reference(args)
   elif args.workload == 'replay_sweep':
     run_sweep(args)
+  elif args.workload in ROWS_WORKLOADS:
+    run_rows(args)
   else:
     run_b200(args)
 
