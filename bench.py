@@ -46,8 +46,8 @@ CLASSES = 5
 ROW_BYTES = 12288 + 32768 + 8192 + 20 + 4 + 4 + 3      # image, deter, stoch, stepid, reward, action, 3 flags
 TRAINS_PER_STEP = TRAIN_RATIO * NENVS // (B * T)        # 8
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/)
-NCU_TRAFFIC = {'rssm_fwd': 8863621000 + 194722816,      # profiles/r01_rssm_fwd_tma_kernel.md
-               'rssm_bwd': 10104900000 + 137023232}     # profiles/r01_rssm_bwd_tma_kernel.md
+NCU_TRAFFIC = {'rssm_fwd': 8866091000 + 192772352,      # profiles/r02_rssm_tma_kernels_ncu.md
+               'rssm_bwd': 10102213000 + 138353664}
 
 
 def peaks():
