@@ -425,6 +425,57 @@ class Replay:
       except KeyError:
         continue
 
+  def _draw_many(self, batch, mode):
+    """`batch` windows and their (batch * length) table rows.  Same attempts in the same order
+    as `batch` calls of _draw (online queue first, then one selector draw per attempt, an
+    attempt whose chunk is gone is skipped: replay.py:151-169) -- but a selector that can draw
+    in bulk (`Uniform.draw`) is asked once per round, and windows that lie inside one chunk
+    (all but the few straddling a chunk end) become rows by one broadcast add."""
+    bulk = getattr(self.sampler, 'draw', None)
+    if bulk is None:
+      picks = [self._draw(mode) for _ in range(batch)]
+      return [p[0] for p in picks], np.concatenate([p[1] for p in picks])
+    assert mode in ('train', 'report', 'eval'), mode
+    L, cs, chunks, items = self.length, self.chunksize, self.chunks, self.items
+    wins, starts, avails, nexts, odd = [], [], [], [], []
+    if mode == 'train':
+      self.metrics['samples'] += batch
+    while len(wins) < batch:
+      need = batch - len(wins)
+      if self.online and self.queue and mode == 'train':
+        attempts = [self.queue.popleft() for _ in range(min(need, len(self.queue)))]
+        keyed = False
+      else:
+        attempts, keyed = bulk(need), True
+      for attempt in attempts:
+        try:
+          uuid, index = items[attempt] if keyed else attempt
+          chunk = chunks[uuid]
+          avail = chunk.length - index
+          if avail >= L:                                   # the window lies inside one chunk
+            nxt = 0
+          else:
+            succ = chunks[chunk.succ]
+            if succ.length >= L - avail:                   # ... or ends in its successor
+              nxt = succ.slab * cs
+            else:                                          # several hops (short chunks): the general walk
+              odd.append((len(wins), self._rows_of(uuid, index, L)))
+              avail, nxt = L, 0
+          starts.append(chunk.slab * cs + index)
+          avails.append(avail)
+          nexts.append(nxt)
+          wins.append((uuid, index))
+        except KeyError:
+          continue
+    t = np.arange(L, dtype=np.int64)
+    rows = np.asarray(starts, np.int64)[:, None] + t
+    if min(avails) < L:
+      avail = np.asarray(avails, np.int64)[:, None]
+      rows = np.where(t < avail, rows, np.asarray(nexts, np.int64)[:, None] + (t - avail))
+    for at, r in odd:
+      rows[at] = r
+    return wins, rows.reshape(-1)
+
   @elements.timer.section('replay_sample')
   def sample(self, batch, mode='train', consec=None):
     """Dense device batch {key: (B, L, ...)} incl. stepid u8[B, L, 20]
@@ -434,9 +485,7 @@ class Replay:
     limiters.wait(
         lambda: len(self.sampler), f'Replay buffer {self.name} is empty')
     with self._lock:
-      picks = [self._draw(mode) for _ in range(batch)]
-      wins = [p[0] for p in picks]
-      rows = np.concatenate([p[1] for p in picks])
+      wins, rows = self._draw_many(batch, mode)
       self._flush()
       data = self.store.gather(rows, batch, self.length, consec=consec)
       self._recent.append((data['stepid'], wins))

@@ -35,6 +35,14 @@ class Uniform:
     with self.lock:
       return self.keys[self.rng.integers(0, len(self.keys)).item()]
 
+  def draw(self, count):
+    """`count` consecutive draws in one call.  numpy fills an array of bounded integers from the
+    same 32-bit stream, value by value, as `count` scalar calls would (pinned by
+    tests/test_selectors_host.py), so the sequence under a seed is unchanged."""
+    with self.lock:
+      keys = self.keys
+      return [keys[i] for i in self.rng.integers(0, len(keys), size=count).tolist()]
+
   def __setitem__(self, key, stepids):
     with self.lock:
       self.indices[key] = len(self.keys)

@@ -98,6 +98,7 @@ class DeviceStore:
     self._stagings = []
     self._turn = 0
     self._idx_ring = []
+    self._gather_plans = {}      # (keys, annotate, consec?, nslabs) -> (emb_key_t array, key order)
 
   # ------------------------------------------------------------ configuration
   @property
@@ -190,7 +191,7 @@ class DeviceStore:
           f"'{spec.name}': shape {tuple(val.shape)} != {(n, *spec.shape)}")
     return val if val.is_contiguous() else val.contiguous()
 
-  def _rowids_to_device(self, rows_np):
+  def _rowids_to_device(self, rows_np, stream=None):
     """int64 row ids -> device, through a small ring of pinned buffers."""
     n = len(rows_np)
     slot = None
@@ -200,14 +201,15 @@ class DeviceStore:
         break
     if slot is None:
       cap = max(4096, 1 << int(np.ceil(np.log2(max(n, 1)))))
-      slot = [torch.empty(cap, dtype=torch.int64, pin_memory=True),
-              torch.empty(cap, dtype=torch.int64, device=self.device), None]
+      host = torch.empty(cap, dtype=torch.int64, pin_memory=True)
+      slot = [host, torch.empty(cap, dtype=torch.int64, device=self.device), None, host.numpy()]
       self._idx_ring.append(slot)
       if len(self._idx_ring) > 8:
         self._idx_ring.pop(0)
-    host, dev, _ = slot
-    host.numpy()[:n] = rows_np
-    stream = torch.cuda.current_stream(self.device)
+    host, dev, _, host_np = slot
+    host_np[:n] = rows_np
+    if stream is None:
+      stream = torch.cuda.current_stream(self.device)
     dev[:n].copy_(host[:n], non_blocking=True)
     ev = torch.cuda.Event()
     ev.record(stream)
@@ -306,42 +308,56 @@ class DeviceStore:
     rows = np.asarray(src_rows, np.int64).reshape(-1)
     assert len(rows) == batch * window, (len(rows), batch, window)
     stream = torch.cuda.current_stream(self.device)
-    rows_dev = self._rowids_to_device(rows)
+    rows_dev = self._rowids_to_device(rows, stream)
     names = list(self.specs) if keys is None else list(keys)
     out = {} if out is None else out
-    klist = []
-    first = self.specs.get('is_first')
+    # The key table of a (key set, annotate, consec) signature is built once; per call only the
+    # destination (and, after a table re-allocation, source) pointers are patched in place.
+    sig = (tuple(names), bool(annotate), consec is not None, self.nslabs)
+    plan = self._gather_plans.get(sig)
+    if plan is None:
+      klist, slots = [], []
+      first = self.specs.get('is_first')
+      for name in names:
+        spec = self.specs[name]
+        if spec.row_bytes == 0:
+          continue
+        op, aux, aux_stride = _lib.OP_COPY, None, 0
+        if annotate and name == 'is_first':
+          op = _lib.OP_FIRST
+        if annotate and name == 'is_last' and first is not None:
+          op, aux = _lib.OP_LAST, self.tables['is_first'].data_ptr()
+          aux_stride = first.row_bytes
+        slots.append(name)
+        klist.append(_lib.Key(
+            src=self.tables[name].data_ptr(), aux=aux, aux_stride=aux_stride,
+            src_stride=spec.row_bytes, dst_stride=spec.row_bytes,
+            row_bytes=spec.row_bytes, op=op))
+      if consec is not None:
+        slots.append('consec')
+        klist.append(_lib.Key(dst_stride=4, row_bytes=4, op=_lib.OP_FILL32))
+      if len(self._gather_plans) > 16:
+        self._gather_plans.clear()
+      plan = self._gather_plans[sig] = (_lib.keys_array(klist), slots)
+    karr, slots = plan
     for name in names:
-      spec = self.specs[name]
       if name not in out:
+        spec = self.specs[name]
         out[name] = torch.empty(
             (batch, window, *spec.shape), dtype=spec.tdtype, device=self.device)
-      if spec.row_bytes == 0:
-        continue
-      op, aux, aux_stride = _lib.OP_COPY, None, 0
-      if annotate and name == 'is_first':
-        op = _lib.OP_FIRST
-      if annotate and name == 'is_last' and first is not None:
-        op, aux = _lib.OP_LAST, self.tables['is_first'].data_ptr()
-        aux_stride = first.row_bytes
-      klist.append(_lib.Key(
-          src=self.tables[name].data_ptr(), dst=out[name].data_ptr(),
-          aux=aux, aux_stride=aux_stride,
-          src_stride=spec.row_bytes, dst_stride=spec.row_bytes,
-          row_bytes=spec.row_bytes, op=op))
     if consec is not None:
       out['consec'] = torch.empty(
           (batch, window), dtype=torch.int32, device=self.device)
-      klist.append(_lib.Key(
-          dst=out['consec'].data_ptr(), dst_stride=4, row_bytes=4,
-          op=_lib.OP_FILL32, fill=int(consec)))
+      karr[len(slots) - 1].fill = int(consec)
+    for i, name in enumerate(slots):
+      karr[i].dst = out[name].data_ptr()
     prof = PROFILE
     if prof is not None:
       t0 = torch.cuda.Event(enable_timing=True)
       t1 = torch.cuda.Event(enable_timing=True)
       t0.record(stream)
     _lib.check(self.lib.emb_replay_gather(
-        _lib.keys_array(klist), len(klist), rows_dev.data_ptr(),
+        karr, len(slots), rows_dev.data_ptr(),
         batch * window, window, stream.cuda_stream))
     if prof is not None:
       t1.record(stream)

@@ -151,3 +151,27 @@ def test_weights_shape_the_draw_frequencies():
   assert counts[4] == 0 and abs(counts[2] / 2000 - 0.75) < 0.04
   tree.update(1, float('inf'))                       # infinite weights win outright
   assert all(tree.sample() == 1 for _ in range(20))
+
+
+def test_uniform_bulk_draw_is_the_scalar_sequence():
+  """`Uniform.draw(n)` (one numpy call) must produce exactly the keys n scalar draws would, and
+  leave the generator where they would: Replay.sample's bulk path relies on it for the bit-exact
+  sampling contract (embodied/core/selectors.py:39-43)."""
+  import numpy as np
+  from embodied_b200.core import selectors
+  for n in (1, 2, 3, 10, 1000, 70001):
+    for seed in (0, 1, 7):
+      a, b = selectors.Uniform(seed), selectors.Uniform(seed)
+      for k in range(n):
+        a[k] = None
+        b[k] = None
+      scalar = [a() for _ in range(133)]
+      assert b.draw(100) + b.draw(1) + b.draw(32) == scalar
+      if n >= 2:                                 # the reference refuses to delete the last key (:51)
+        del a[n - 1], b[n - 1]
+      a[-5] = b[-5] = None
+      assert b.draw(17) == [a() for _ in range(17)]
+  for n in (2 ** 31 - 1, 2 ** 32 - 1, 2 ** 32, 2 ** 32 + 5, 2 ** 40):     # both Lemire widths
+    x, y = np.random.default_rng(3), np.random.default_rng(3)
+    assert [int(x.integers(0, n)) for _ in range(65)] == y.integers(0, n, size=65).tolist()
+    assert int(x.integers(0, n)) == int(y.integers(0, n))
