@@ -387,7 +387,7 @@ def run_b200(args):
                 'the backward pass; exposed = side-stream end minus backward end, CUDA events inside '
                 'the captured graph, rank 0'}
   env_steps = world * NENVS * args.steps
-  h2d = NENVS * (12288 + 4 + 3 + 20 + 8) + TRAINS_PER_STEP * (B * L * 8 + B * T * 8)
+  h2d = NENVS * (int(np.prod(IMAGE)) + 4 + 3 + 20 + 8) + TRAINS_PER_STEP * (B * L * 8 + B * T * 8)
   d2h = NENVS * 4 + 4
   line = {
       'metric': 'env_steps_per_sec', 'value': env_steps / t_dev, 'unit': 'env steps/s',
@@ -758,6 +758,10 @@ def workload_name(args):
   if args.agent == 'feed':
     return ('config 2 PLUMBING ONLY: Driver(256 envs, 64x64x3 u8) + Replay(L=65, 53 299 B rows '
             'incl. f32 latents) append/sample(B=16)/update; no model, latents from a device pool')
+  if IMAGE != (64, 64, 3):
+    return (f'config 3 (learner half): dreamerv3 {args.size} on a synthetic {"x".join(map(str, IMAGE))} image env '
+            f'({CLASSES} actions), 256 envs per GPU, replay (B=16,T=64,L=65), one Driver step + 8 x (sample -> '
+            'train -> update)')
   return (f'config 2: dreamerv3 {args.size} on synthetic 64x64x3 image env, 256 envs, '
           'replay (B=16,T=64,L=65), one Driver step + 8 x (sample -> train -> update)')
 
@@ -845,7 +849,7 @@ class OracleLearner:
     self.torch, self.do = torch, do
     self.threads = os.cpu_count() or 1
     torch.set_num_threads(self.threads)
-    self.cfg = do.default_config(**C.SIZES[size])
+    self.cfg = do.default_config(**dict(C.SIZES[size], image=tuple(IMAGE), actions=CLASSES))
     self.model = do.Dreamer(self.cfg, do.init_params(self.cfg, 0))
     self.noise = {}
 
@@ -938,9 +942,18 @@ def main():
   ap.add_argument('--workload', default='train', choices=['train', 'replay_sweep', 'atari_rows', 'proprio_rows'],
                   help='train = BASELINE config 2 (the headline); replay_sweep = config 5; atari_rows / '
                        'proprio_rows = the Driver + Replay half of configs 3 / 4')
+  ap.add_argument('--image', default='', help='HxWxC of the synthetic observation for the train workload '
+                  '(default 64x64x3 = config 2; 96x96x1 = the dreamerv3 update of config 3, SURVEY F7)')
+  ap.add_argument('--classes', type=int, default=0, help='discrete actions of the synthetic env (default 5; Atari: 18)')
   ap.add_argument('--sweep-points', default='', help='e.g. 16x64,128x256 (default: the full 5x5 grid)')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3 if args.impl != 'reference' else 1)
+  global IMAGE, CLASSES, ROW_BYTES
+  if args.image:
+    IMAGE = tuple(int(x) for x in args.image.lower().split('x'))
+    ROW_BYTES += int(np.prod(IMAGE)) - 12288
+  if args.classes:
+    CLASSES = args.classes
   if args.impl == 'reference':
     if int(os.environ.get('RANK', 0)) != 0:
       return                                   # rank 0 alone runs the CPU arm
