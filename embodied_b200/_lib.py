@@ -47,7 +47,7 @@ EXPORTS = (
     'emb_rmsnorm_act_bwd', 'emb_rssm_kl_fwd', 'emb_rssm_kl_bwd', 'emb_lambda_return', 'emb_onehot_sample', 'emb_opt_agc_rms_momentum', 'emb_opt_agc_rms_momentum_cast', 'emb_allreduce_bucket_update', 'emb_maxpool2_nhwc_fwd',
     'emb_maxpool2_nhwc_bwd', 'emb_upsample2_nhwc_fwd', 'emb_upsample2_nhwc_bwd',
     'emb_rmsnorm_grouped_fwd', 'emb_gru_gates_fwd', 'emb_pack_tiles', 'emb_conv_patches_nhwc', 'emb_conv_tapsum_nhwc', 'emb_probe_read', 'emb_twohot_loss_fwd', 'emb_twohot_loss_bwd', 'emb_twohot_pred', 'emb_loss_reduce', 'emb_conv5x5_nhwc_tc', 'emb_conv5x5_wgrad_tc', 'emb_conv_nhwc_tc', 'emb_conv_wgrad_tc', 'emb_event_create', 'emb_event_record', 'emb_event_elapsed_ms', 'emb_event_destroy',
-    'emb_gae_advantage', 'emb_opt_clip_adam',
+    'emb_gae_advantage', 'emb_opt_clip_adam', 'emb_gumbel_fill',
 )
 
 
@@ -89,6 +89,8 @@ def load():
     lib.emb_gae_advantage.restype = ctypes.c_int
     lib.emb_opt_clip_adam.argtypes = [vp, vp, vp, vp, vp, i64, vp, i32, vp, fl, i32, fl, fl, fl, fl, fl, vp]
     lib.emb_opt_clip_adam.restype = ctypes.c_int
+    lib.emb_gumbel_fill.argtypes = [vp, i64, ctypes.c_uint64, vp]
+    lib.emb_gumbel_fill.restype = ctypes.c_int
     _LIB = lib
     return lib
 

@@ -13,7 +13,7 @@ ROOT = pathlib.Path(__file__).resolve().parent
 CSRC = ROOT / 'csrc'
 OBJ = ROOT / 'build'
 LIB = ROOT / 'libembodied_b200.so'
-SOURCES = ['abi.cu', 'rows.cu', 'rssm_fwd.cu', 'rssm_fwd_tma.cu', 'rssm_bwd.cu', 'rssm_bwd_tma.cu', 'norm.cu', 'optim.cu', 'spatial.cu', 'kl.cu', 'probe.cu', 'thinconv.cu', 'gru.cu', 'pack.cu', 'conv_tc.cu', 'losses.cu', 'ppo.cu']
+SOURCES = ['abi.cu', 'rows.cu', 'rssm_fwd.cu', 'rssm_fwd_tma.cu', 'rssm_bwd.cu', 'rssm_bwd_tma.cu', 'norm.cu', 'optim.cu', 'spatial.cu', 'kl.cu', 'probe.cu', 'thinconv.cu', 'gru.cu', 'pack.cu', 'conv_tc.cu', 'losses.cu', 'ppo.cu', 'noise.cu']
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
     '-std=c++17', '-Xcompiler', '-fPIC',

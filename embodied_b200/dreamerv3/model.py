@@ -62,10 +62,22 @@ def symexp(x):
   return torch.sign(x) * torch.expm1(torch.abs(x))
 
 
+_GUMBEL_CALLS = [0]
+
+
 def gumbel_(u, generator=None):
-  """Fill `u` (fp32) with Gumbel(0, 1) noise in place: -log(E), E ~ Exp(1) (= -log(U));
-  three passes over the buffer.  E is clamped to what -log(clamp(U, 1e-20, 1 - 1e-7))
-  can be, so the noise stays inside [-3.9, 16.2] like the two-log formulation."""
+  """Fill `u` (fp32) with Gumbel(0, 1) noise in place: -log(E), E ~ Exp(1) (= -log(U)), E
+  clamped to what -log(clamp(U, 1e-20, 1 - 1e-7)) can be, so the noise stays inside
+  [-3.9, 16.2] like the two-log formulation.  On the device: one write-only pass of
+  emb_gumbel_fill (Philox keyed by the generator's seed and a per-process call counter)."""
+  if u.is_cuda and u.dtype == f32 and u.is_contiguous() and u.data_ptr() % 16 == 0:
+    from .. import _lib
+    _GUMBEL_CALLS[0] += 1
+    base = generator.initial_seed() if generator is not None else torch.initial_seed()
+    seed = (base * 0x9E3779B97F4A7C15 + _GUMBEL_CALLS[0] * 0xD1B54A32D192ED03) & ((1 << 64) - 1)
+    _lib.check(_lib.load().emb_gumbel_fill(
+        u.data_ptr(), u.numel(), seed, torch.cuda.current_stream(u.device).cuda_stream))
+    return u
   u.exponential_(1.0, generator=generator)
   u.clamp_(1e-7, 46.0)
   return u.log_().neg_()

@@ -288,6 +288,13 @@ int emb_onehot_sample(const void* logit, int32_t dtype, int64_t logit_stride, co
 int emb_lambda_return(const float* last, const float* term, const float* rew, const float* boot,
                       float* ret, int64_t rows, int32_t length, float disc, float lam, void* stream);
 
+/* Gumbel(0, 1) noise for the categorical draws of one update (outs.OneHot / Categorical
+ * sample = arg-max of log-probabilities + Gumbel noise; embodied/jax/outs.py:252-270 draws it
+ * with jax.random.categorical): out fp32 [n], 16-byte aligned, one write-only pass.
+ * Philox4x32-10 keyed by `seed` (callers pass a fresh seed per call); g = -log(E),
+ * E = -log(U) clamped to [1e-7, 46]. */
+int emb_gumbel_fill(float* out, int64_t n, uint64_t seed, void* stream);
+
 /* The advantage recurrence of ppo_loss (ppo/agent.py:204-212), one launch, one thread per row:
  *   live = (1 - term)(1 - 1/hor), cont = (1 - last)(1 - term) lam,
  *   adv[t] = rew[t+1] + live[t+1] val[t+1] - val[t] + live[t+1] cont[t+1] adv[t+1],  tar = adv + val.
