@@ -538,16 +538,24 @@ class Model:
   def slow_value_logits(self, x):
     """The slow critic (utils.py:94-127): val's architecture, slow parameters."""
     slow = self.store.slow
+    cache = self.store._cast           # cleared at every step boundary (ParamStore.begin_step)
+
+    def low(name):                     # the compute-dtype copy, made once per update (two call sites)
+      hit = cache.get(('slow', name))
+      if hit is None:
+        hit = cache[('slow', name)] = slow[name].to(self.cd)
+      return hit
     with torch.no_grad():
       for i in range(self.cfg.val_layers):
-        w = slow[f'slowval/mlp/linear{i}/kernel'].to(self.cd)
-        b = slow[f'slowval/mlp/linear{i}/bias'].to(self.cd)
+        w, b = low(f'slowval/mlp/linear{i}/kernel'), low(f'slowval/mlp/linear{i}/bias')
         x = torch.addmm(b, x.reshape(-1, x.shape[-1]), w).reshape(*x.shape[:-1], -1)
-        xf = x.to(f32)
-        x = silu((xf * (torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-4) *
-                        slow[f'slowval/mlp/norm{i}/scale'])).to(self.cd))
-      w = slow['slowval/head/logits/kernel'].to(self.cd)
-      b = slow['slowval/head/logits/bias'].to(self.cd)
+        scale = slow[f'slowval/mlp/norm{i}/scale']
+        if self.fused_norm and ops.rmsnorm_supported(x, False):
+          x = ops.rmsnorm_act(x, scale, True)                # one kernel instead of eight
+        else:
+          xf = x.to(f32)
+          x = silu((xf * (torch.rsqrt(xf.square().mean(-1, keepdim=True) + 1e-4) * scale)).to(self.cd))
+      w, b = low('slowval/head/logits/kernel'), low('slowval/head/logits/bias')
       return torch.addmm(b, x.reshape(-1, x.shape[-1]), w).reshape(
           *x.shape[:-1], -1).to(f32)
 

@@ -133,6 +133,10 @@ def pack_matrix(w, engine, ncta, unit=1, groups=1):
 
 # ---------------------------------------------------------------- fused packing
 FUSED_PACK = True      # False: the op-by-op torch formulation below (tests compare the two)
+# bf16 engines, inside a backward pass: the three large weight-gradient GEMMs of the scan
+# (dynhid0, dyngru, obs0[:D]) accumulate in fp32 STRAIGHT INTO the flat gradient buffer
+# (baddbmm with beta = 1 on the tensor's view) instead of bf16 result -> cast -> AccumulateGrad add.
+DIRECT_WGRAD = True
 # The bf16 engines pack straight from the flat fp32 parameter buffer with one
 # kernel per matrix (emb_pack_tiles, csrc/pack.cu).  A logical (K, N) matrix is
 # described per n8 column tile by (element offset of (k=0, n=8t), k stride,
@@ -269,13 +273,14 @@ def pack(store, cfg, engine, ncta):
     keep_rows = Dg + 2 * cfg.hidden
     extra['w_hid_x2'] = hid[:, keep_rows:].permute(1, 0, 2).reshape(-1, D).to(torch.bfloat16)
     hid = hid[:, :keep_rows]
-  hid = hid.permute(1, 0, 2).reshape(hid.shape[1], D)
-  gru = m('dyn/dyngru/kernel')                              # (G, Dg, 3*Dg), columns (gate, j)
-  gru = gru.reshape(G, Dg, 3, Dg // 8, 8).permute(1, 0, 3, 2, 4).reshape(Dg, 3 * D)
   cd = f32 if engine == ENG_F32 else torch.bfloat16
   if engine != ENG_F32 and FUSED_PACK:
     return dict(**extra, **_pack_fused(store, cfg, engine, ncta),
                 w_in1=m('dyn/dynin1/kernel').to(cd).contiguous())
+  # the torch formulation of the same layouts (fp32 parity engine, FUSED_PACK off)
+  hid = hid.permute(1, 0, 2).reshape(hid.shape[1], D)
+  gru = m('dyn/dyngru/kernel')                              # (G, Dg, 3*Dg), columns (gate, j)
+  gru = gru.reshape(G, Dg, 3, Dg // 8, 8).permute(1, 0, 3, 2, 4).reshape(Dg, 3 * D)
   return dict(
       **extra,
       w_ph1=pack_matrix(torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1), engine, ncta),
@@ -448,10 +453,6 @@ def pack_bwd(store, cfg, engine, ncta):
   Dg = D // G
   lay = engine       # fp32 [tile][K][8] | bf16 padded blocks (TMA ring) | bf16 plain blocks
   m = lambda n: store.view('master', n)
-  wobs = m('dyn/obs0/kernel')
-  ph1 = torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1)              # (D, 2H)
-  gru = m('dyn/dyngru/kernel')                                        # (G, Dg, 3Dg) -> (3Dg, G*Dg)
-  gru_t = gru.permute(2, 0, 1).reshape(3 * Dg, D)
   hid = m('dyn/dynhid0/kernel')                                       # (G, Kh, Dg) -> (Dg, G*Kh)
   extra = {}
   if engine != ENG_F32:
@@ -460,6 +461,11 @@ def pack_bwd(store, cfg, engine, ncta):
     hid = hid[:, :keep_rows]
   if engine != ENG_F32 and FUSED_PACK:
     return dict(**extra, **_pack_bwd_fused(store, cfg, engine, ncta))
+  # the torch formulation of the same layouts (fp32 parity engine, FUSED_PACK off)
+  wobs = m('dyn/obs0/kernel')
+  ph1 = torch.cat([wobs[:D], m('dyn/dynin0/kernel')], 1)              # (D, 2H)
+  gru = m('dyn/dyngru/kernel')                                        # (G, Dg, 3Dg) -> (3Dg, G*Dg)
+  gru_t = gru.permute(2, 0, 1).reshape(3 * Dg, D)
   hid_t = hid.permute(2, 0, 1).reshape(Dg, G * hid.shape[1])
   return dict(
       **extra,
@@ -502,9 +508,11 @@ def _norm_bwd(gx, y, s, eps=1e-4):
 
 
 @torch.no_grad()
-def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
+def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch, direct=None):
   """Runs emb_rssm_observe_bwd and forms every parameter / input gradient.
-  G_*: batch-major upstream gradients (B, T, ..).  Returns (input grads, param grads)."""
+  G_*: batch-major upstream gradients (B, T, ..).  Returns (input grads, param grads).
+  `direct(name)`: the fp32 view of `name` in the flat gradient buffer, for the weight gradients
+  that are added there in place (their entry in the returned dict is None)."""
   cfg, dev, lib = scan.cfg, G_deter.device, scan.lib
   _bind_bwd(lib)
   T = sv['keep'].shape[0] - 1
@@ -600,17 +608,27 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch):
   inp = torch.cat([dprev.reshape(T, ROWS, G, Dg),
                    x012[:, :, None, :].expand(-1, -1, G, -1)], -1)    # (T, 16, G, Kh)
   gyh = g_yhid.reshape(R, G, Dg)
-  pg['dyn/dynhid0/kernel'] = torch.einsum(
-      'rgk,rgj->gkj', inp.reshape(R, G, Kh).to(cd), gyh.to(cd)).to(f32)
+
+  def block_wgrad(name, a, b):                     # (R, G, K), (R, G, N) -> (G, K, N)
+    if direct is None or cd == f32:
+      return torch.einsum('rgk,rgn->gkn', a.to(cd), b.to(cd)).to(f32)
+    gv = direct(name)
+    torch.baddbmm(gv, a.to(cd).permute(1, 2, 0), b.to(cd).permute(1, 0, 2), out_dtype=f32, out=gv)
+    return None
+  pg['dyn/dynhid0/kernel'] = block_wgrad('dyn/dynhid0/kernel', inp.reshape(R, G, Kh), gyh)
   pg['dyn/dynhid0/bias'] = g_yhid.reshape(R, D).sum(0)
   pg['dyn/dynhid0norm/scale'] = g_shid
   gg = buf['g_gates'].reshape(R, G, 3 * Dg)
-  pg['dyn/dyngru/kernel'] = torch.einsum(
-      'rgk,rgn->gkn', h.reshape(R, G, Dg).to(cd), gg.to(cd)).to(f32)
+  pg['dyn/dyngru/kernel'] = block_wgrad('dyn/dyngru/kernel', h.reshape(R, G, Dg), gg)
   pg['dyn/dyngru/bias'] = gg.reshape(R, 3 * D).sum(0)
-  wobs = torch.zeros_like(m('dyn/obs0/kernel'))
-  wobs[:D] = mm(deter.reshape(R, D), g_yobs.reshape(R, H))
-  pg['dyn/obs0/kernel'] = wobs
+  if direct is None or cd == f32:
+    wobs = torch.zeros_like(m('dyn/obs0/kernel'))
+    wobs[:D] = mm(deter.reshape(R, D), g_yobs.reshape(R, H))
+    pg['dyn/obs0/kernel'] = wobs
+  else:                                            # rows [D:] (the token half) get theirs through autograd
+    gv = direct('dyn/obs0/kernel')[:D]
+    torch.addmm(gv, deter.reshape(R, D).to(cd).t(), g_yobs.reshape(R, H).to(cd), out_dtype=f32, out=gv)
+    pg['dyn/obs0/kernel'] = None
   pg['dyn/obs0norm/scale'] = g_sobs
   pg['dyn/obslogit/kernel'] = mm(xo.reshape(R, H), buf['g_logit'].reshape(R, SC))
   pg['dyn/obslogit/bias'] = buf['g_logit'].reshape(R, SC).sum(0)
@@ -652,8 +670,16 @@ class ObserveFn(torch.autograd.Function):
     cfg = scan.cfg
     z = lambda g, *s: torch.zeros((B, T, *s), dtype=f32, device=sv['deter'].device) \
         if g is None else g.to(f32)
+    store = scan.store
+    direct = None
+    if DIRECT_WGRAD and scan.engine != ENG_F32 and all(ctx.needs_input_grad[8:]):
+      direct = lambda name: store.view('grad', name)
     ig, pg, _ = scan_backward(
         scan, sv, B, z(G_deter, cfg.deter), z(G_logit, cfg.stoch, cfg.classes),
-        z(G_stoch, cfg.stoch, cfg.classes))
+        z(G_stoch, cfg.stoch, cfg.classes), direct)
+    if store.on_grad is not None:                  # the bucketed exchange counts arrivals per tensor
+      for n in PARAMS:
+        if pg[n] is None:
+          store.on_grad(n)
     return (None, None, ig['y0'], ig['y1'], ig['x2'], ig['pre_tok'], None, None,
             *[pg[n] for n in PARAMS])
