@@ -212,6 +212,13 @@ class Loop:
     self.learn()
 
 
+def _fallbacks(args):
+  if args.agent == 'feed':
+    return {}
+  from embodied_b200.dreamerv3 import ops
+  return dict(ops.FALLBACKS)
+
+
 def conv_lines(torch, cfg, flush):
   """The tcgen05 convolution kernels (csrc/conv_tc.cu) at this model's layer shapes, B*T = 1024
   images: each launch timed alone with CUDA events after the timed region (the captured train
@@ -409,6 +416,9 @@ def run_b200(args):
               'ms_per_step': t_e2e / args.steps * 1e3,
               'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
       'gpu_launches': launches,
+      # call sites of the learner that ran a library formulation because an own kernel does not
+      # take their shape (embodied_b200/dreamerv3/model.py Model._use); {} = none
+      'eager_fallbacks': _fallbacks(args),
       'roofline': roofline, 'kernels': kernels, 'exchange': exchange,
       'clocks': clk,
   }

@@ -132,6 +132,17 @@ class Model:
       engine = scanlib.ENG_BF16 if self.cd == torch.bfloat16 else scanlib.ENG_F32
       self.scan = scanlib.Scan(cfg, store, engine)
 
+  def _use(self, enabled, kernel, supported):
+    """Gate of every own-kernel call site: True -> launch the kernel.  A call site whose kernel
+    is enabled but does not take this shape / dtype runs the library formulation instead (still
+    on the device) and is COUNTED in ops.FALLBACKS -- bench.py prints the table and config 2 is
+    asserted to have none (tests/test_gpu_bench.py); `strict_kernels` turns it into an error."""
+    if enabled and supported:
+      return True
+    if enabled:
+      ops.note_fallback(kernel, bool(self.cfg.get('strict_kernels', False)))
+    return False
+
   # ---------------------------------------------------------------- primitives
   def W(self, name):
     return self.store.get(name)
@@ -153,7 +164,7 @@ class Model:
     instead of in a separate pass over the conv output."""
     scale = self.store.w[f'{name}/scale']
     need_grad = torch.is_grad_enabled() and (x.requires_grad or scale.requires_grad)
-    if self.fused_norm and ops.rmsnorm_supported(x, need_grad, bias is not None):
+    if self._use(self.fused_norm, 'rmsnorm_act', ops.rmsnorm_supported(x, need_grad, bias is not None)):
       return ops.rmsnorm_act(x, scale, act, bias=bias)       # one kernel each way
     if bias is not None:
       x = x + bias.to(x.dtype)
@@ -166,8 +177,7 @@ class Model:
     """bias=False: the caller adds the bias inside the following fused norm
     (after the 2x2 max-pool, with which a per-channel constant commutes)."""
     w = self.W(f'{name}/kernel')
-    if (self.tc_conv and not bias and
-        ops.conv_tc_supported(x, w.shape[2], w.shape[3], w.shape[0])):
+    if not bias and self._use(self.tc_conv, 'conv_tc', ops.conv_tc_supported(x, w.shape[2], w.shape[3], w.shape[0])):
       return ops.ConvTC.apply(x, w)                          # tcgen05 implicit GEMM (csrc/conv_tc.cu)
     w = w.permute(3, 2, 0, 1)                                # HWIO -> OIHW
     b = self.W(f'{name}/bias') if bias else None
@@ -228,7 +238,8 @@ class Model:
       lead = x.shape[:-3]
       x = x.reshape(-1, *x.shape[-3:]).to(self.cd)
       for i in range(len(cfg.mults)):
-        if self.fused_spatial and ops.thin_conv_supported(x, x.shape[-1], cfg.depth * cfg.mults[i]):
+        if x.shape[-1] <= 4 and self._use(self.fused_spatial, 'conv_patches',
+                                          ops.thin_conv_supported(x, x.shape[-1], cfg.depth * cfg.mults[i])):
           x = self.conv_thin_in(x, f'enc/cnn{i}')
         else:
           x = self.conv(x, f'enc/cnn{i}', bias=False)
@@ -328,7 +339,10 @@ class Model:
     tok = torch.addmm(bobs, tokens.reshape(B * T, -1), wobs[D:]).reshape(B, T, -1)
     deter, stoch = carry
     deter, stoch = deter.to(self.cd), stoch.to(self.cd)
-    if self.scan is not None and self.scan.supported and B <= 16:
+    # T == 1 is the policy's single step over all envs (hundreds of rows: GEMM-shaped work, not the
+    # 16-row weight-streaming scan); only a TRAINING scan that misses the kernel counts as a fallback
+    fits = self.scan is not None and self.scan.supported and B <= 16
+    if self._use(self.scan is not None and (T > 1 or fits), 'rssm_observe', fits):
       return self.observe_fused(deter, stoch, x2, tok, reset, gumbel)
     deters, stochs, logits = [], [], []
     for t in range(T):
@@ -372,7 +386,7 @@ class Model:
     """dyn = max(KL(sg(post) || prior), free), rep = max(KL(post || sg(prior)), free),
     both on unimixed distributions, summed over the S latents."""
     cfg = self.cfg
-    if self.fused_norm and post_logit.dim() == 4 and ops.kl_supported(post_logit, prior_logit):
+    if self._use(self.fused_norm, 'rssm_kl', post_logit.dim() == 4 and ops.kl_supported(post_logit, prior_logit)):
       dyn, rep, ent_post, ent_prior = ops.rssm_kl(
           post_logit, prior_logit, cfg.unimix, cfg.free_nats)
       return dyn, rep, dict(dyn_ent=ent_prior.mean(), rep_ent=ent_post.mean())
@@ -422,13 +436,13 @@ class Model:
     x = self.norm(x0 + x1, 'dec/spnorm')
     for i in reversed(range(len(depths) - 1)):
       w = self.W(f'dec/conv{i}/kernel')
-      if self.tc_conv and w.shape[0] == 5 and ops.subpixel_supported(x, w.shape[2], w.shape[3]):
+      if self._use(self.tc_conv, 'upconv_subpixel', w.shape[0] == 5 and ops.subpixel_supported(x, w.shape[2], w.shape[3])):
         # up-sample + 5x5 conv on the LOW-resolution grid: 36 instead of 100 taps per input pixel
         y = ops.upconv_subpixel(x, w)
       else:
         y = self.conv(self.upsample(x), f'dec/conv{i}', bias=False)
       x = self.norm(y, f'dec/conv{i}norm', bias=self.store.w[f'dec/conv{i}/bias'])
-    if self.fused_spatial and ops.thin_conv_supported(x, x.shape[-1], cfg.image[2]):
+    if self._use(self.fused_spatial, 'conv_tapsum', ops.thin_conv_supported(x, x.shape[-1], cfg.image[2])):
       x = self.conv_thin_out(x, 'dec/imgout', up=2)          # up-sampling folded in
     else:
       x = self.conv(self.upsample(x), 'dec/imgout')
@@ -458,13 +472,13 @@ class Model:
     return out
 
   def upsample(self, x):                                     # x.repeat(2,-2).repeat(2,-3), NHWC
-    if self.fused_spatial and ops.spatial_supported(x):
+    if self._use(self.fused_spatial, 'upsample2', ops.spatial_supported(x)):
       return ops.Upsample2.apply(x)
     y = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode='nearest')
     return y.permute(0, 2, 3, 1)
 
   def pool(self, x):                                         # rssm.py:239-240, NHWC
-    if self.fused_spatial and ops.spatial_supported(x):
+    if self._use(self.fused_spatial, 'maxpool2', ops.spatial_supported(x)):
       return ops.MaxPool2.apply(x)
     return F.max_pool2d(x.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
 
@@ -560,7 +574,7 @@ class Model:
           *x.shape[:-1], -1).to(f32)
 
   def twohot_pred(self, logits):                             # outs.py:285-302 (symmetric sum)
-    if self.fused_norm and not logits.requires_grad and ops.twohot_supported(logits):
+    if not logits.requires_grad and self._use(self.fused_norm, 'twohot_pred', ops.twohot_supported(logits)):
       return ops.twohot_pred(logits, self.bins)              # one launch
     probs = torch.softmax(logits, -1)
     bins = self.bins
@@ -571,7 +585,7 @@ class Model:
 
   def twohot_loss(self, logits, target, target2=None, w2=0.0):   # outs.py:311-330
     """CE against twohot(target) (+ w2 * CE against twohot(target2): the critic's two terms)."""
-    if self.fused_norm and ops.twohot_supported(logits):
+    if self._use(self.fused_norm, 'twohot_loss', ops.twohot_supported(logits)):
       return ops.twohot_loss(logits, self.bins, target, target2, w2)     # one launch each way
     if target2 is not None:
       return self.twohot_loss(logits, target) + w2 * self.twohot_loss(logits, target2)
@@ -705,7 +719,7 @@ class Model:
     scales.update({k: rec for k, _ in self.imgkeys})
     scales.update({spec[0]: rec for spec in self.vecspec})
     assert set(losses) == set(scales), (sorted(losses), sorted(scales))
-    if self.fused_norm and total_fusable(losses):
+    if self._use(self.fused_norm, 'loss_reduce', total_fusable(losses)):
       total, means = ops.loss_sum(losses, scales)            # one launch (agent.py:237-240)
       metrics.update({f'loss/{k}': v for k, v in means.items()})
     else:

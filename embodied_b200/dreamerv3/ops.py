@@ -47,6 +47,17 @@ def _lib_bound():
   return lib
 
 
+# kernel name -> how many call sites ran the library formulation instead because the kernel does
+# not take their shape / dtype (Model._use).  Empty on the benchmarked configuration.
+FALLBACKS = {}
+
+
+def note_fallback(kernel, strict=False):
+  if strict:
+    raise RuntimeError(f'strict_kernels: no {kernel} kernel for this shape / dtype')
+  FALLBACKS[kernel] = FALLBACKS.get(kernel, 0) + 1
+
+
 def _dtype_code(t):
   return {torch.float32: 0, torch.bfloat16: 1}[t.dtype]
 

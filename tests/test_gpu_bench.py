@@ -87,6 +87,28 @@ def test_bench_prints_contract_line():
   assert 'capture of the train step failed' not in err, err[-2000:]
 
 
+def test_config2_runs_on_own_kernels_only():
+  """The benchmarked configuration (size200m, bf16, B=16, T=64): no call site of the learner falls
+  back to a library formulation because a kernel does not take its shape (Model._use accounting),
+  and `strict_kernels` turns such a miss into an error instead of a silent degradation."""
+  line, err = _run_bench(['--steps', '1', '--warmup', '3', '--no-cpu'])
+  assert line['eager_fallbacks'] == {}, line['eager_fallbacks']
+  assert 'capture of the train step failed' not in err, err[-2000:]
+  from embodied_b200 import dreamerv3, elements
+  from embodied_b200.dreamerv3 import ops
+  S = elements.Space
+  obs = {'image': S(np.uint8, (96, 96, 1)), 'reward': S(np.float32), 'is_first': S(bool),
+         'is_last': S(bool), 'is_terminal': S(bool)}
+  act = {'reset': S(bool), 'action': S(np.int32, (), 0, 18)}
+  agent = dreamerv3.Agent(obs, act, dreamerv3.config.make('size12m', compute_dtype='bfloat16', graph='off',
+                                                          strict_kernels=True))
+  o = {'image': torch.zeros((4, 96, 96, 1), dtype=torch.uint8, device='cuda'),
+       'is_first': torch.ones(4, dtype=torch.bool, device='cuda')}
+  with pytest.raises(RuntimeError, match='strict_kernels'):      # 96-wide maps miss the conv kernels' tiles
+    agent.policy(agent.init_policy(4), o)
+  assert isinstance(ops.FALLBACKS, dict)
+
+
 def test_bench_survives_refused_capture():
   """EMB_GRAPH=off stands in for a refused capture: no graph stopwatches exist,
   the bench must still print value / e2e / roofline from the eager events."""
