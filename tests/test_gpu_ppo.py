@@ -207,3 +207,32 @@ def test_config_level_entry_point(tmp_path):
   keys = {k for row in rows for k in row}
   assert 'train/loss/policy_loss' in keys or any('policy_loss' in k for k in keys), sorted(keys)
   assert (tmp_path / 'checkpoint.pkl').exists()
+
+
+def _run_ppo_workers(nproc, mode, port):
+  import json, os, subprocess, sys
+  root = pathlib.Path(__file__).resolve().parent.parent
+  cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={nproc}',
+         '--master-addr', '127.0.0.1', '--master-port', str(port), 'tests/ppo_worker.py', mode]
+  proc = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600,
+                        env=dict(os.environ, MASTER_ADDR='127.0.0.1'))
+  assert proc.returncode == 0, proc.stderr[-3000:]
+  rows = [json.loads(l) for l in proc.stdout.splitlines() if l.startswith('{')]
+  assert len(rows) == nproc, proc.stdout[-2000:]
+  return rows
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs')
+def test_two_ranks_average_gradients_and_normalisers():
+  """Data-parallel ppo: gradient mean over ranks before the optimiser chain, batch
+  moments of the meanstd normalisers averaged like the reference's pmean.  Ranks stay
+  bit-identical; with the SAME batch on both ranks the result is the single-process oracle's."""
+  own = _run_ppo_workers(2, 'own', 29621)
+  for row in own:
+    assert row['max_diff_across_ranks'] == 0.0 and row['norm_diff_across_ranks'] == 0.0, row
+  assert own[0]['losses'] != own[1]['losses']                      # different batches went in
+  same = _run_ppo_workers(2, 'same', 29623)
+  for row in same:
+    assert row['max_diff_across_ranks'] == 0.0, row
+  assert same[0]['rel_diff_vs_oracle'] < 1e-5, same[0]
+  assert abs(same[0]['checksum'] - own[0]['checksum']) > 0
