@@ -339,10 +339,11 @@ class Model:
     tok = torch.addmm(bobs, tokens.reshape(B * T, -1), wobs[D:]).reshape(B, T, -1)
     deter, stoch = carry
     deter, stoch = deter.to(self.cd), stoch.to(self.cd)
-    # T == 1 is the policy's single step over all envs (hundreds of rows: GEMM-shaped work, not the
-    # 16-row weight-streaming scan); only a TRAINING scan that misses the kernel counts as a fallback
-    fits = self.scan is not None and self.scan.supported and B <= 16
-    if self._use(self.scan is not None and (T > 1 or fits), 'rssm_observe', fits):
+    # T == 1 with many rows is the policy's single step over all envs: GEMM-shaped work, not the
+    # 16-row weight-streaming scan.  A training scan always takes the kernel, 16 rows per launch.
+    single = T == 1 and B > 16
+    if not single and self._use(self.scan is not None, 'rssm_observe',
+                                self.scan is not None and self.scan.supported):
       return self.observe_fused(deter, stoch, x2, tok, reset, gumbel)
     deters, stochs, logits = [], [], []
     for t in range(T):
@@ -369,9 +370,15 @@ class Model:
     y0 = k0 * (deter0 @ self.W('dyn/dynin0/kernel')) + self.W('dyn/dynin0/bias')
     y1 = k0 * (stoch0.reshape(B, -1) @ self.W('dyn/dynin1/kernel')) + self.W('dyn/dynin1/bias')
     weights = [self.store.w[n] for n in scanlib.PARAMS]
-    deter, logit, stoch, _ = scanlib.ObserveFn.apply(
-        self.scan, deter0.detach(), y0.to(f32), y1.to(f32), x2.to(f32), tok.to(f32), keep,
-        gumbel, *weights)
+    y0, y1, x2, tok = y0.to(f32), y1.to(f32), x2.to(f32), tok.to(f32)
+    deter0 = deter0.detach()
+    parts = []
+    for lo in range(0, B, scanlib.ROWS):                    # the kernels walk 16 batch rows per launch:
+      rows = slice(lo, lo + scanlib.ROWS)                   # larger batches stream the weights once per 16 rows
+      parts.append(scanlib.ObserveFn.apply(
+          self.scan, deter0[rows], y0[rows], y1[rows], x2[rows], tok[rows], keep[rows],
+          gumbel[rows], *weights)[:3])
+    deter, logit, stoch = parts[0] if len(parts) == 1 else [torch.cat(p, 0) for p in zip(*parts)]
     feat = dict(deter=deter, stoch=stoch, logit=logit)
     return (deter[:, -1], stoch[:, -1]), feat
 

@@ -378,3 +378,33 @@ def test_vector_observations_and_action_dicts_match_oracle_fp32(case):
       assert rel(act[k], v) < 1e-4, k
     else:
       assert torch.equal(act[k].cpu(), v), k
+
+
+@pytest.mark.parametrize('dtype', ['float32', 'bfloat16'])
+def test_batches_wider_than_sixteen_rows_run_the_scan_kernels_in_row_groups(dtype):
+  """B > 16 (the larger batches of BASELINE config 5 / other batch sizes): the scan kernels walk
+  16 rows per launch, so a (40, T) batch is three launches each way -- not the per-step library
+  loop -- with the weight gradients of the three groups accumulated.  fp32: equals the oracle."""
+  from embodied_b200 import _lib
+  from embodied_b200.dreamerv3 import ops
+  ocfg, oracle, agent = make_pair(dtype=dtype)
+  B, T = 40, 5
+  data, noise = cases.batch(ocfg, B, T, seed=31), do.make_noise(ocfg, B, T, seed=32)
+  ops.FALLBACKS.clear()
+  before = _lib.launch_count()
+  carry, outs, mets = agent.train(agent.init_train(B), cases.to_device(data), cases.to_device(noise))
+  assert 'rssm_observe' not in ops.FALLBACKS, ops.FALLBACKS
+  assert _lib.launch_count() - before > 6
+  ocarry, oouts, omets, ograds, oo = oracle.train(data, noise)
+  feat = agent.last_outs['feat']
+  if dtype == 'float32':
+    assert rel(mets['loss'], omets['loss']) < RTOL
+    assert torch.equal(feat['stoch'].detach().argmax(-1).cpu(), oo['feat']['stoch'].argmax(-1))
+    for k in ('deter', 'logit'):
+      assert rel(feat[k], oo['feat'][k]) < RTOL, k
+    assert rel(carry[0], ocarry['deter']) < RTOL
+    worst = max((rel2(agent.store.view('grad', k), ograds[k]), k) for k in ograds if k.startswith('dyn/'))
+    assert worst[0] < 1e-4, worst
+  else:
+    assert rel(mets['loss'], omets['loss']) < 5e-2
+    assert rel(feat['deter'][:, 0], oo['feat']['deter'][:, 0]) < 3e-2
