@@ -12,9 +12,10 @@ are appended by ``emb_driver_scatter_mask_actions``; train batches are the dense
 the optimiser chain of ``Agent._make_opt`` is ``emb_opt_clip_adam`` over one pointer and the
 data-parallel gradient mean (embodied/jax/opt.py:52-54) is one NCCL call.  The advantage
 recurrence of ``ppo_loss`` is ``emb_gae_advantage``.  The networks themselves (3x3 convolutions,
-M = B*T GEMMs, the GRU) run as fp32 library GEMMs / convolutions under autograd: ppo is the
-plumbing configuration (BASELINE config 1), computed in fp32 where the reference defaults to
-bfloat16.  There is no CPU path.
+M = B*T GEMMs, the GRU) run as library GEMMs / convolutions under autograd, in ``compute_dtype``
+(bfloat16 like the reference's default: bf16 operands, fp32 master weights, norms, heads and
+losses; or float32 = the parity mode the tests compare with the oracle), and the whole update is
+replayed as one CUDA graph after two eager warm-up steps.  There is no CPU path.
 """
 import math
 import re
@@ -31,6 +32,25 @@ from . import config as configlib
 
 f32 = torch.float32
 EXCLUDE = ('is_first', 'is_last', 'is_terminal', 'reward')       # ppo/agent.py:136
+
+
+def _clone(tree):
+  if isinstance(tree, dict):
+    return {k: _clone(v) for k, v in tree.items()}
+  if isinstance(tree, (tuple, list)):
+    return type(tree)(_clone(v) for v in tree)
+  return tree.clone()
+
+
+def _copy_into(dst, src):
+  if isinstance(dst, dict):
+    for k in dst:
+      _copy_into(dst[k], src[k])
+  elif isinstance(dst, (tuple, list)):
+    for a, b in zip(dst, src):
+      _copy_into(a, b)
+  else:
+    dst.copy_(src)
 
 
 def _kind(space):
@@ -202,6 +222,7 @@ class Model:
   def __init__(self, cfg, obs_space, act_space, store):
     self.cfg, self.store = cfg, store
     self.act_space = act_space
+    self.cd = store.compute_dtype          # GEMMs / convolutions / GRU in it; norms, heads, losses in fp32
     enc = {k: v for k, v in obs_space.items() if k not in EXCLUDE and not k.startswith('log/')}
     assert all(len(s.shape) <= 3 for s in enc.values()), enc          # ppo/nets.py:23
     self.vec = {k: v for k, v in enc.items() if len(v.shape) <= 2}
@@ -213,17 +234,19 @@ class Model:
 
   # -- layers
   def linear(self, name, x):
-    return torch.addmm(self.w(f'{name}/bias'), x.reshape(-1, x.shape[-1]),
+    return torch.addmm(self.w(f'{name}/bias'), x.reshape(-1, x.shape[-1]).to(self.cd),
                        self.w(f'{name}/kernel')).reshape(*x.shape[:-1], -1)
 
   def norm(self, name, x, impl):                                      # nets.py:374-399
     if impl == 'none':
       return x
     assert impl == 'layer', impl
-    mean = x.mean(-1, keepdim=True)
-    var = torch.clamp((x * x).mean(-1, keepdim=True) - mean * mean, min=0)
-    return (x - mean) * (torch.rsqrt(var + self.cfg.norm_eps) * self.w(f'{name}/scale')) \
-        + self.w(f'{name}/shift')
+    xf = x.to(f32)                                                    # Norm computes in f32 (nets.py:376)
+    mean = xf.mean(-1, keepdim=True)
+    var = torch.clamp((xf * xf).mean(-1, keepdim=True) - mean * mean, min=0)
+    sw = self.store.w                                                 # fp32 scale / shift
+    y = (xf - mean) * (torch.rsqrt(var + self.cfg.norm_eps) * sw[f'{name}/scale']) + sw[f'{name}/shift']
+    return y.to(x.dtype)
 
   def act(self, name, x):
     return {'relu': torch.relu, 'silu': F.silu, 'none': lambda y: y}[name](x)
@@ -246,9 +269,9 @@ class Model:
       if ok is not None:
         x = torch.where(ok.reshape(*bshape, *([1] * (x.ndim - lead))), x, torch.zeros_like(x))
       if disc:
-        x = F.one_hot(x.long(), classes).to(f32)
+        x = F.one_hot(x.long(), classes).to(self.cd)
       else:
-        x = squish(x.to(f32))
+        x = squish(x.to(f32)).to(self.cd)
       x = self.linear(f'{name}/{key}', x.reshape(*bshape, -1))
       if ok is not None:
         x = torch.where(ok[..., None], x, torch.zeros_like(x))
@@ -269,7 +292,7 @@ class Model:
     if self.img:
       x = torch.cat([obs[k] for k in sorted(self.img)], -1)
       assert x.dtype == torch.uint8, x.dtype
-      x = x.reshape(-1, *x.shape[-3:]).permute(0, 3, 1, 2).to(f32) * 255 - 0.5   # sic, ppo/nets.py:46
+      x = x.reshape(-1, *x.shape[-3:]).permute(0, 3, 1, 2).to(self.cd) * 255 - 0.5   # sic, ppo/nets.py:46
       for s in range(len(cfg.mults)):
         x = self.conv(f'enc/s{s}in', x)
         # reduce_window(max, 3x3, stride 2, 'same', init -inf): pad like XLA's SAME (low = total // 2)
@@ -299,7 +322,7 @@ class Model:
 
   def gru_step(self, carry, inp, reset):                              # nets.py:657-669
     U = self.cfg.rnn_units
-    carry = carry * (~reset)[:, None].to(f32)
+    carry = carry * (~reset)[:, None].to(carry.dtype)
     x = self.norm('rnn/norm', torch.cat([carry, inp], -1), self.cfg.rnn_norm)
     x = self.linear('rnn/linear', x)
     res, cand, update = x[:, :U], x[:, U:2 * U], x[:, 2 * U:]
@@ -319,11 +342,11 @@ class Model:
     outs = {}
     for key, (disc, shape, classes) in self.actkind.items():
       if disc:
-        y = self.linear(f'policy/head/{key}/logits', h)
+        y = self.linear(f'policy/head/{key}/logits', h).to(f32)       # outs.* work in f32
         outs[key] = y.reshape(*y.shape[:-1], *shape, classes)
       else:
-        mean = self.linear(f'policy/head/{key}/mean', h)
-        std = self.linear(f'policy/head/{key}/stddev', h)
+        mean = self.linear(f'policy/head/{key}/mean', h).to(f32)
+        std = self.linear(f'policy/head/{key}/stddev', h).to(f32)
         std = (cfg.maxstd - cfg.minstd) * torch.sigmoid(std + 2.0) + cfg.minstd
         outs[key] = (torch.tanh(mean).reshape(*mean.shape[:-1], *shape),
                      std.reshape(*std.shape[:-1], *shape))
@@ -359,7 +382,7 @@ class Model:
 
   def value(self, feat):
     h = self.head_mlp('value', feat, self.cfg.val_layers)
-    return self.linear('value/head/pred', h).squeeze(-1)
+    return self.linear('value/head/pred', h).squeeze(-1).to(f32)
 
   def __call__(self, memory, obs, prevact, value=True, single=False):  # ppo/agent.py:162-183
     cfg = self.cfg
@@ -402,14 +425,13 @@ class Agent(base.Agent):
     cfg = config if isinstance(config, configlib.Config) else configlib.make(**(config or {}))
     self.cfg = cfg = configlib.Config(cfg)
     cfg.setdefault('norm_eps', 1e-4)
-    if cfg.compute_dtype != 'float32':
-      raise NotImplementedError('embodied_b200.ppo computes in float32 (compute_dtype=float32)')
+    self.cd = {'float32': f32, 'bfloat16': torch.bfloat16}[cfg.compute_dtype]
     self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
     self.world, self.rank = 1, 0
     if torch.distributed.is_available() and torch.distributed.is_initialized():
       self.world, self.rank = torch.distributed.get_world_size(), torch.distributed.get_rank()
     specs = param_specs(cfg, self.obs_space, self.act_space)
-    self.store = paramlib.ParamStore(cfg, self.device, f32, cfg.seed, values, specs=specs)
+    self.store = paramlib.ParamStore(cfg, self.device, self.cd, cfg.seed, values, specs=specs)
     self.model = Model(cfg, self.obs_space, self.act_space, self.store)
     self.opt = ClipAdam(cfg, self.store)
     self.advnorm = Normalize(cfg.norm_rate, cfg.norm_limit, self.device, self.world)
@@ -418,6 +440,10 @@ class Agent(base.Agent):
     self.gen.manual_seed(cfg.seed * 1000003 + self.rank)
     self.updates = 0
     self.obskeys = list(self.model.vec) + list(self.model.img)
+    # the update as ONE CUDA graph per batch signature (after GRAPH_WARMUP eager steps): the
+    # T-step GRU loop and its backward are ~2500 launches that cost one cudaGraphLaunch
+    self._graph_mode = cfg.get('graph', 'auto')
+    self._graphs, self._graph_seen, self._graph_ok = {}, {}, True
 
   # ------------------------------------------------------------------- plugin properties
   @property
@@ -436,7 +462,7 @@ class Agent(base.Agent):
 
   def _initial(self, batch_size):
     if self.cfg.recurrent:
-      return torch.zeros((batch_size, self.cfg.rnn_units), dtype=f32, device=self.device)
+      return torch.zeros((batch_size, self.cfg.rnn_units), dtype=self.cd, device=self.device)
     return ()
 
   def init_policy(self, batch_size):                                  # ppo/agent.py:53-58
@@ -451,8 +477,9 @@ class Agent(base.Agent):
     return ()
 
   def _flags(self):
-    torch.backends.cuda.matmul.allow_tf32 = False
-    torch.backends.cudnn.allow_tf32 = False
+    if self.cd == f32:                       # parity mode: strict IEEE GEMMs / convolutions
+      torch.backends.cuda.matmul.allow_tf32 = False
+      torch.backends.cudnn.allow_tf32 = False
 
   def _dev(self, x):
     return x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x), device=self.device)
@@ -485,7 +512,7 @@ class Agent(base.Agent):
     logps, _ = self.model.logp_entropy(pol, act)
     out = {f'logp/{k}': v for k, v in logps.items()}
     if self.cfg.recurrent:
-      out['memory'] = memory
+      out['memory'] = memory.to(f32)                                  # replay rows are f32 (ext_space)
     return (memory, act), dict(act), out
 
   # ----------------------------------------------------------------------------- train
@@ -551,13 +578,15 @@ class Agent(base.Agent):
       prevact = {k: data[k][:, K - 1: -1] for k in self.act_space}
       data = {k: v[:, K:] for k, v in data.items()}
       if cfg.recurrent:
-        memory = data.pop('memory').to(f32)[:, K - 1]                 # sic: row K-1 of the sliced rows
+        memory = data.pop('memory').to(self.cd)[:, K - 1]             # sic: row K-1 of the sliced rows
     else:
       prevact = {k: torch.cat([prevact[k][:, None], data[k][:, :-1]], 1) for k in self.act_space}
     return memory, prevact, data
 
-  def train(self, carry, data):                                       # ppo/agent.py:81-97
-    self._flags()
+  GRAPH_WARMUP = 2
+
+  def _device_step(self, carry, data):
+    """The device work of one update (ppo/agent.py:81-97): pure stream work, no host reads."""
     memory, prevact, data = self._context(carry, data)
     self.store.begin_step()
     self.store.grad.zero_()
@@ -568,12 +597,70 @@ class Agent(base.Agent):
     metrics = {k: v.detach() for k, v in metrics.items()}
     metrics['loss'] = total.detach()
     metrics['opt/grad_norm'] = self.opt.launch()
-    self.updates += 1
-    metrics['opt/updates'] = self.updates
+    if self.cd != f32:
+      self.store.refresh_low()                                        # the bf16 copy the next forward reads
     self.last_losses = {k: v.detach() for k, v in losses.items()}
     prevact = {k: data[k][:, -1].clone() for k in self.act_space}
     memory = memory.detach() if self.cfg.recurrent else memory
-    return (memory, prevact), {}, metrics
+    return (memory, prevact), metrics
+
+  def train(self, carry, data):                                       # ppo/agent.py:81-97
+    self._flags()
+    if self._graph_mode not in (False, 'off') and self._graph_ok and self.world == 1:
+      key = tuple((k, tuple(v.shape), v.dtype) for k, v in sorted(data.items()))
+      st = self._graphs.get(key)
+      if st is None:
+        seen = self._graph_seen.get(key, 0)
+        self._graph_seen[key] = seen + 1
+        if seen >= self.GRAPH_WARMUP:
+          st = self._capture(key, carry, data)
+      if st is not None:
+        return self._train_graphed(st, carry, data)
+    carry, metrics = self._device_step(carry, data)
+    self.updates += 1
+    metrics['opt/updates'] = self.updates
+    return carry, {}, metrics
+
+  def _capture(self, key, carry, data):
+    import types
+    import warnings
+    st = types.SimpleNamespace()
+    st.data = {k: v.clone() for k, v in data.items()}
+    st.carry = _clone(carry)
+    st.graph = torch.cuda.CUDAGraph()
+    launched = _lib.launch_count()
+    try:
+      torch.cuda.synchronize()
+      with torch.cuda.graph(st.graph):
+        st.carry_out, metrics = self._device_step(st.carry, st.data)
+        st.names = list(metrics)
+        st.mvec = torch.stack([metrics[k].to(f32).reshape(()) for k in st.names])
+      torch.cuda.synchronize()
+    except Exception as e:      # noqa: BLE001 -- capture refused: stay on eager launches (still the CUDA path)
+      warnings.warn(f'ppo.Agent: CUDA graph capture of the update failed ({e!r}); continuing with eager launches')
+      self._graph_ok = False
+      try:
+        torch.cuda.synchronize()
+      except Exception:         # noqa: BLE001
+        pass
+      return None
+    # a capture records, it does not execute: the caller replays it now
+    st.launches = _lib.launch_count() - launched
+    _lib.launch_count_add((1 << 64) - st.launches)
+    self._graphs[key] = st
+    return st
+
+  def _train_graphed(self, st, carry, data):
+    _copy_into(st.carry, carry)
+    for k, v in st.data.items():
+      v.copy_(data[k])
+    st.graph.replay()
+    _lib.launch_count_add(st.launches)
+    self.updates += 1
+    mv = st.mvec.clone()
+    metrics = {k: mv[i] for i, k in enumerate(st.names)}
+    metrics['opt/updates'] = self.updates
+    return st.carry_out, {}, metrics
 
   def report(self, carry, data):                                      # ppo/agent.py:99-100
     return carry, {}

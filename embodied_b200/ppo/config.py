@@ -25,7 +25,7 @@ def make(**over):
       scales=dict(policy=1.0, value=0.5), norm_rate=0.01, norm_limit=1e-8,
       # agent.opt
       lr=3e-4, eps=1e-7, clip=10.0, wd=0.0, warmup=1000, wdregex=r'/kernel$',
-      replay_context=1, seed=0, compute_dtype='float32')
+      replay_context=1, seed=0, compute_dtype='float32', graph='auto')
   cfg.update(over)
   return cfg
 

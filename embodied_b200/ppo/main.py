@@ -73,9 +73,9 @@ def make_agent(config):                                      # ppo/main.py:127-1
   if config.random_agent:
     return RandomAgent(obs_space, act_space)
   from .agent import Agent
-  # this build computes ppo in float32 whatever jax.compute_dtype says (>= the reference's bf16)
   return Agent(obs_space, act_space, configlib.from_reference(
-      config.agent, seed=config.seed, replay_context=config.replay_context))
+      config.agent, seed=config.seed, replay_context=config.replay_context,
+      compute_dtype=config.jax.compute_dtype))
 
 
 def main(argv=None):

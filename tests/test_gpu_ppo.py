@@ -236,3 +236,65 @@ def test_two_ranks_average_gradients_and_normalisers():
     assert row['max_diff_across_ranks'] == 0.0, row
   assert same[0]['rel_diff_vs_oracle'] < 1e-5, same[0]
   assert abs(same[0]['checksum'] - own[0]['checksum']) > 0
+
+
+def test_captured_update_matches_eager_launches():
+  """The update replayed from its CUDA graph (after two eager warm-up steps) against the same
+  updates launched eagerly: same parameters, metrics and carry."""
+  from embodied_b200 import ppo
+  obs, act = cases.dummy_spaces()
+  ocfg = po.tiny_config(warmup=2)
+  _, vals = cases.oracle_for(ocfg, obs, act)
+  mk = lambda graph: ppo.Agent(obs, act, cases.product_config(ocfg, graph=graph),
+                               values={k: v.numpy() for k, v in vals.items()})
+  a, b = mk('auto'), mk('off')
+  B, T = 3, 8
+  ca, cb = a.init_train(B), b.init_train(B)
+  for step in range(6):
+    data = cases.to_device(cases.batch(ocfg, obs, act, B, T, seed=40 + step))
+    ca, _, ma = a.train(ca, data)
+    cb, _, mb = b.train(cb, data)
+    assert set(ma) == set(mb)
+    for k in mb:         # two runs of the library's convolution gradients differ in their last bits
+      _close(ma[k], mb[k], f'{step}/{k}', rtol=1e-4, atol=1e-6)
+    _close(ca[0], cb[0], f'{step}/memory', rtol=1e-4, atol=1e-6)
+  assert len(a._graphs) == 1 and a._graph_ok and not b._graphs
+  assert a.updates == b.updates == 6
+  for k in a.store.specs:
+    _close(a.store.view('master', k), b.store.view('master', k), k, rtol=1e-4, atol=1e-6)
+  # the policy reads the parameters the replayed graph wrote
+  g = torch.Generator().manual_seed(1)
+  o = cases.to_device(cases.obs_batch(obs, (2,), g))
+  noise = cases.to_device(po.make_noise(act, (2,), 3))
+  _, acta, _ = a.policy(a.init_policy(2), o, noise=noise)
+  _, actb, _ = b.policy(b.init_policy(2), o, noise=noise)
+  _close(acta['act_cont'], actb['act_cont'], 'act_cont')
+
+
+def test_bf16_update_tracks_the_fp32_oracle():
+  """compute_dtype=bfloat16 (the reference's default): bf16 GEMMs / convolutions / GRU with fp32
+  master weights, norms, heads and losses.  Tracks the fp32 oracle loosely; every tensor that
+  gets a gradient in fp32 gets one in bf16, and the bf16 copy follows the optimiser."""
+  from embodied_b200 import ppo
+  obs, act = cases.vector_spaces()                  # no x255 image scale: see test_layer_norm_on_feature_maps
+  ocfg = po.tiny_config(warmup=0, lr=1e-3)
+  oracle, vals = cases.oracle_for(ocfg, obs, act)
+  agent = ppo.Agent(obs, act, cases.product_config(ocfg, compute_dtype='bfloat16'),
+                    values={k: v.numpy() for k, v in vals.items()})
+  B, T = 3, 8
+  zeros = {k: torch.zeros(B, *v.shape, dtype=torch.int32 if v.discrete else torch.float32) for k, v in act.items()}
+  oc, pc = (oracle.initial(B), zeros), agent.init_train(B)
+  assert pc[0].dtype == torch.bfloat16
+  for step in range(4):
+    data = cases.batch(ocfg, obs, act, B, T, seed=50 + step)
+    oc, _, omets, ograds, _ = oracle.train(oc, data)
+    pc, _, pmets = agent.train(pc, cases.to_device(data))
+    assert abs(float(pmets['loss']) - float(omets['loss'])) <= 5e-2 * abs(float(omets['loss'])) + 5e-3, step
+    if step == 0:
+      for k, v in ograds.items():
+        got = agent.store.view('grad', k)
+        assert (float(got.abs().max()) > 0) == (float(v.abs().max()) > 0), k
+  low = agent.store.low_buffer().float()
+  assert float((low - agent.store.master).abs().max()) <= 8e-3 * float(agent.store.master.abs().max())
+  out = agent.policy(agent.init_policy(2), cases.to_device(cases.obs_batch(obs, (2,), torch.Generator().manual_seed(0))))
+  assert out[2]['memory'].dtype == torch.float32 and torch.isfinite(out[2]['memory']).all()
