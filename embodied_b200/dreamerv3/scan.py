@@ -605,8 +605,6 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch, direct=None):
   pg['dyn/dynin1/bias'] = g_y1[1:].reshape(-1, H).sum(0)
   pg['dyn/dynin1norm/scale'] = g_s1
   x012 = torch.cat([x0, x1, x2f], -1)                                 # (T, 16, 3H)
-  inp = torch.cat([dprev.reshape(T, ROWS, G, Dg),
-                   x012[:, :, None, :].expand(-1, -1, G, -1)], -1)    # (T, 16, G, Kh)
   gyh = g_yhid.reshape(R, G, Dg)
 
   def block_wgrad(name, a, b):                     # (R, G, K), (R, G, N) -> (G, K, N)
@@ -615,7 +613,21 @@ def scan_backward(scan, sv, B, G_deter, G_logit, G_stoch, direct=None):
     gv = direct(name)
     torch.baddbmm(gv, a.to(cd).permute(1, 2, 0), b.to(cd).permute(1, 0, 2), out_dtype=f32, out=gv)
     return None
-  pg['dyn/dynhid0/kernel'] = block_wgrad('dyn/dynhid0/kernel', inp.reshape(R, G, Kh), gyh)
+  if direct is None or cd == f32:
+    inp = torch.cat([dprev.reshape(T, ROWS, G, Dg),
+                     x012[:, :, None, :].expand(-1, -1, G, -1)], -1)  # (T, 16, G, Kh)
+    pg['dyn/dynhid0/kernel'] = block_wgrad('dyn/dynhid0/kernel', inp.reshape(R, G, Kh), gyh)
+  else:
+    # rows [deter_g | x0 x1 x2] of every group are contiguous 2-D blocks of the gradient view: the
+    # x012 operand is shared by the groups, so it is never replicated G times (33 M elements)
+    gv = direct('dyn/dynhid0/kernel')                                 # (G, Kh, Dg)
+    dp = dprev.reshape(R, G, Dg).to(cd)
+    xt = x012.reshape(R, 3 * H).to(cd).t()
+    gy = gyh.to(cd)
+    for g in range(G):
+      torch.addmm(gv[g, :Dg], dp[:, g].t(), gy[:, g], out_dtype=f32, out=gv[g, :Dg])
+      torch.addmm(gv[g, Dg:], xt, gy[:, g], out_dtype=f32, out=gv[g, Dg:])
+    pg['dyn/dynhid0/kernel'] = None
   pg['dyn/dynhid0/bias'] = g_yhid.reshape(R, D).sum(0)
   pg['dyn/dynhid0norm/scale'] = g_shid
   gg = buf['g_gates'].reshape(R, G, 3 * Dg)
