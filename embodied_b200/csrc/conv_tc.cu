@@ -4,8 +4,9 @@
 //
 //   out[p][co] = sum_{tap=(ky,kx)} sum_ci  in[p + (ky-2, kx-2)][ci] * w[tap][co][ci]
 //
-// One persistent CTA per SM walks 128-pixel output tiles (whole image rows, so the
-// 128 pixels are contiguous in NHWC memory).  Per (tap, 64-channel block):
+// One persistent CTA per SM walks output tiles of whole image rows (contiguous in NHWC memory):
+// 128 pixels where the width divides 128, otherwise the largest whole-row / whole-image tile below
+// 128 (96-wide maps: 96 pixels) with the remaining MMA rows unused.  Per (tap, 64-channel block):
 //   A = the 128 x 64 window of the input shifted by the tap, fetched by ONE 4-D TMA
 //       tile copy (cp.async.bulk.tensor, 128-byte swizzle); the SAME padding is the
 //       TMA's out-of-bounds zero fill -- no halo handling in the kernel;
@@ -36,7 +37,10 @@ constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 
 struct ConvShape {
-  int tiles;           // 128-pixel output tiles
+  int tiles;           // output tiles of `tpix` pixels
+  int tpix;            // pixels per tile: whole rows (or whole images), at most 128; the MMA always runs
+                       // M = 128 rows -- rows >= tpix of the shared tile hold stale data and land in
+                       // accumulator lanes nobody reads (96-wide maps: one row = 96 pixels per tile)
   int hw;              // H * W
   int w;               // W
   int kblocks;         // Cin / 64
@@ -190,7 +194,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
   const int iters = s.groups * s.taps * s.kblocks;
   // stage = [msub x 16 KiB of A | weight tile]: 48 KiB either way (cout <= 128 with two sub-tiles)
   constexpr uint32_t a_bytes = (uint32_t)MSUB * kABytes;
-  const uint32_t stage_tx = a_bytes + (uint32_t)s.cout * 128u;
+  const uint32_t stage_tx = (uint32_t)MSUB * (uint32_t)s.tpix * 128u + (uint32_t)s.cout * 128u;
   const int half = s.ksize >> 1;
 
   if (warp == 0) {
@@ -202,7 +206,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
         int n0[MSUB], h0[MSUB];
 #pragma unroll
         for (int sub = 0; sub < MSUB; ++sub) {
-          const int pix0 = (tile * MSUB + sub) * 128;
+          const int pix0 = (tile * MSUB + sub) * s.tpix;
           n0[sub] = pix0 / s.hw;
           h0[sub] = (pix0 - n0[sub] * s.hw) / s.w;
         }
@@ -270,7 +274,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
 #pragma unroll
       for (int sub = 0; sub < MSUB; ++sub) {
         const int m = q * 32 + lane;
-        size_t opix = (size_t)(tile * MSUB + sub) * 128 + m;
+        if (q * 32 >= s.tpix) continue;      // a whole warp past a partially filled tile (warp-uniform)
+        const bool valid = m < s.tpix;       // the TMEM loads below are warp-collective: only stores are guarded
+        size_t opix = (size_t)(tile * MSUB + sub) * s.tpix + (valid ? m : 0);
         if (s.out_up == 2) {                 // pixel (n, y, x) -> (n, 2y + py, 2x + px) of the doubled grid
           const int pn = (int)(opix / s.hw), pr = (int)(opix - (size_t)pn * s.hw);
           const int py = pr / s.w, px = pr - py * s.w;
@@ -287,10 +293,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_constant
             for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(bias + c0 + j));
           }
           uint4* dst = reinterpret_cast<uint4*>(orow + c0);
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16(v[8 * j], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                  pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+          }
         }
       }
       tc_fence_before();
@@ -325,7 +333,10 @@ constexpr int kWRingSlabs = 24;                  // 192 KiB ring: 24 / SLABS sta
 //  bound by bytes in flight per SM, not by HBM latency of a leader.)
 
 struct WgradShape {
-  int chunks;          // 64-pixel chunks in all
+  int chunks;          // pixel chunks in all
+  int cpix;            // pixels per chunk = bw * ht * nt <= 64 (64 where the width divides 64); the K loop
+                       // always covers 64 rows: rows >= cpix of a slab are never written and stay zero
+  int bw;              // box width: the image width, or a divisor of it when w > 64 (chunks then walk x too)
   int splits;          // CTAs per tap
   int hw, w;           // H*W, W
   int m, n;            // channels on the M / N side (m in {128, 256})
@@ -378,6 +389,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_con
                  :: "r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (s.cpix < 64) {                       // partially filled chunks: the rows TMA never writes must be zero
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < kWRingSlabs * kWSlab / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -389,21 +405,23 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_con
   const int c_begin = (int)((long long)s.chunks * split / s.splits);
   const int c_end = (int)((long long)s.chunks * (split + 1) / s.splits);
   const int mslabs = s.m / 64, nslabs = s.n / 64, mtiles = s.m / 128;
-  const uint32_t stage_tx = (uint32_t)(mslabs + nslabs) * kWSlab;
+  const uint32_t stage_tx = (uint32_t)(mslabs + nslabs) * (uint32_t)s.cpix * 128u;
 
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       // (no divisions inside the loop: the producer's issue latency is on the critical path)
-      int n0 = c_begin * 64 / s.hw, h0 = (c_begin * 64 - n0 * s.hw) / s.w;
-      const int dmh = s.m_shifted ? ky - half : 0, mw = s.m_shifted ? kx - half : 0;
-      const int dnh = s.m_shifted ? 0 : ky - half, nw = s.m_shifted ? 0 : kx - half;
+      const long long p0 = (long long)c_begin * s.cpix;
+      int n0 = (int)(p0 / s.hw), h0 = (int)((p0 - (long long)n0 * s.hw) / s.w);
+      int x0 = s.bw < s.w ? (int)(p0 - (long long)n0 * s.hw - (long long)h0 * s.w) : 0;
+      const int dmh = s.m_shifted ? ky - half : 0, dmw = s.m_shifted ? kx - half : 0;
+      const int dnh = s.m_shifted ? 0 : ky - half, dnw = s.m_shifted ? 0 : kx - half;
       // the unshifted side is gy: possibly one phase of a tensor on the doubled grid
       const int mpy = s.m_shifted ? 0 : s.gy_py, mch = s.m_shifted ? 0 : s.gy_ch;
       const int npy = s.m_shifted ? s.gy_py : 0, nch = s.m_shifted ? s.gy_ch : 0;
       for (int c = c_begin; c < c_end; ++c) {
-        const int mh = h0 + dmh, nh = h0 + dnh;
+        const int mh = h0 + dmh, nh = h0 + dnh, mw = x0 + dmw, nw = x0 + dnw;
         mbar_wait(&empty[stage], phase ^ 1u);
         mbar_expect_tx(&full[stage], stage_tx);
         unsigned char* base = smem + stage * kWStageBytes;
@@ -412,8 +430,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_con
         for (int j = 0; j < nslabs; ++j)
           tma_load_5d(base + (mslabs + j) * kWSlab, &map_n, nch + j * 64, nw, npy, nh, n0, &full[stage]);
         if (++stage == kWStages) { stage = 0; phase ^= 1u; }
-        h0 += s.ht;
-        if (h0 >= s.h) { h0 = 0; n0 += s.nt; }
+        x0 += s.bw;
+        if (x0 >= s.w) {
+          x0 = 0;
+          h0 += s.ht;
+          if (h0 >= s.h) { h0 = 0; n0 += s.nt; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -517,15 +539,18 @@ static int sm_count(const char* who) {
   return 0;
 }
 
-// `px` consecutive pixels = whole rows of one image or whole images: box (w, rows, images)
-static int pixel_box(int64_t n, int h, int w, int px, int* ht, int* nt, const char* who) {
-  if (w > px || px % w) return emb::fail(-1, "%s: width %d must divide %d", who, w, px);
-  if (h * w >= px) {
-    *ht = px / w; *nt = 1;
-    if (h % *ht) return emb::fail(-1, "%s: height %d must be a multiple of %d rows per tile", who, h, *ht);
+// The largest tile of at most `px` consecutive pixels made of whole rows of one image (rows
+// dividing the height) or of whole images (a count dividing n): box (w, rows, images).
+static int tile_box(int64_t n, int h, int w, int px, int* ht, int* nt, const char* who) {
+  if (w > px || w < 1 || h < 1) return emb::fail(-1, "%s: width %d must be in [1, %d]", who, w, px);
+  if (h * w > px) {
+    int r = px / w;
+    while (h % r) --r;
+    *ht = r; *nt = 1;
   } else {
-    *ht = h; *nt = px / (h * w);
-    if (px % (h * w) || n % *nt) return emb::fail(-1, "%s: %dx%d images must pack into %d-pixel tiles", who, h, w, px);
+    int k = px / (h * w);
+    while (n % k) --k;
+    *ht = h; *nt = k;
   }
   return 0;
 }
@@ -545,8 +570,9 @@ extern "C" int emb_conv_nhwc_tc(const emb_conv_tc_args* a, void* stream) {
       a->out_phase > 3)
     return emb::fail(-1, "%s: in_up / out_up must be 1 or 2, out_phase in [0, 4)", who);
   int ht, nt;
-  if (int e = pixel_box(n, h, w, 128, &ht, &nt, who)) return e;
-  if ((n * h * w) % 128) return emb::fail(-1, "%s: n*h*w must be a multiple of 128", who);
+  if (int e = tile_box(n, h, w, 128, &ht, &nt, who)) return e;
+  const int tpix = ht * w * nt;
+  const int64_t ntiles = n * h * w / tpix;
   if (((uintptr_t)a->in | (uintptr_t)a->w_packed | (uintptr_t)a->out) & 15)
     return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
   if (int e = sm_count(who)) return e;
@@ -565,8 +591,9 @@ extern "C" int emb_conv_nhwc_tc(const emb_conv_tc_args* a, void* stream) {
     if (r != CUDA_SUCCESS) return emb::fail(-3, "%s: cuTensorMapEncodeTiled(weights) failed with %d", who, (int)r);
   }
   ConvShape s;
-  s.msub = (cout <= 128 && (n * h * w) % 256 == 0) ? 2 : 1;
-  s.tiles = (int)(n * h * w / (128 * s.msub));
+  s.msub = (cout <= 128 && ntiles % 2 == 0) ? 2 : 1;
+  s.tiles = (int)(ntiles / s.msub);
+  s.tpix = tpix;
   s.hw = h * w;
   s.w = w;
   s.kblocks = cin / 64;
@@ -625,17 +652,28 @@ extern "C" int emb_conv_wgrad_tc(const emb_conv_wgrad_tc_args* a, void* stream) 
   if (nn % 64 || nn < 64 || nn > 256) return emb::fail(-1, "%s: the N side has %d channels, need a multiple of 64 <= 256", who, nn);
   if ((a->gy_up != 1 && a->gy_up != 2) || a->gy_phase < 0 || a->gy_phase > 3)
     return emb::fail(-1, "%s: gy_up must be 1 or 2, gy_phase in [0, 4)", who);
-  int ht, nt;
-  if (int e = pixel_box(n, h, w, 64, &ht, &nt, who)) return e;
+  // chunk = box (bw, ht, nt) of at most 64 pixels: whole rows / whole images where a row fits,
+  // else the widest piece of a row that divides the width
+  int ht, nt, bw = w;
+  if (w > 64) {
+    bw = 64;
+    while (w % bw) --bw;
+    ht = 1; nt = 1;
+  } else if (int e = tile_box(n, h, w, 64, &ht, &nt, who)) {
+    return e;
+  }
+  const int cpix = bw * ht * nt;
   if (((uintptr_t)a->x | (uintptr_t)a->gy | (uintptr_t)a->dw) & 15)
     return emb::fail(-1, "%s: pointers must be 16-byte aligned", who);
   if (int e = sm_count(who)) return e;
   CUtensorMap map_x, map_gy;
-  if (int e = encode_act(&map_x, a->x, n, h, w, cin, 1, w, ht, nt, who)) return e;
-  if (int e = encode_act(&map_gy, a->gy, n, h, w, cout, a->gy_up, w, ht, nt, who)) return e;
+  if (int e = encode_act(&map_x, a->x, n, h, w, cin, 1, bw, ht, nt, who)) return e;
+  if (int e = encode_act(&map_gy, a->gy, n, h, w, cout, a->gy_up, bw, ht, nt, who)) return e;
   CUtensorMap* maps[2] = {a->m_is_in ? &map_x : &map_gy, a->m_is_in ? &map_gy : &map_x};
   WgradShape s;
-  s.chunks = (int)(n * h * w / 64);
+  s.chunks = (int)(n * h * w / cpix);
+  s.cpix = cpix;
+  s.bw = bw;
   const int taps = ksize * ksize;
   s.splits = g_sms / taps > 0 ? g_sms / taps : 1;
   if (s.splits > s.chunks) s.splits = s.chunks;

@@ -409,15 +409,12 @@ def onehot_sample(logit, gumbel, unimix, out_dtype, out=None):
 
 # ------------------------------------------- tcgen05 implicit-GEMM convolutions
 def conv_tc_supported(x, cin, cout, k=5):
-  """emb_conv5x5_nhwc_tc: bf16 NHWC, 64-channel K blocks, whole-row 128-pixel tiles."""
+  """emb_conv5x5_nhwc_tc: bf16 NHWC, 64-channel K blocks, whole-row tiles of at most 128 pixels."""
   if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4 or k not in (1, 3, 5):
     return False
   n, h, w, c = x.shape
-  if c != cin or cin % 64 or cout % 32 or not 32 <= cout <= 256 or w > 128 or 128 % w:
-    return False
-  if h * w >= 128:
-    return h % (128 // w) == 0
-  return 128 % (h * w) == 0 and n % (128 // (h * w)) == 0
+  # any width up to 128: tiles are whole rows / whole images of at most 128 pixels (csrc/conv_tc.cu tile_box)
+  return not (c != cin or cin % 64 or cout % 32 or not 32 <= cout <= 256 or w > 128)
 
 
 def pack_conv_weight(w, data_grad=False):
@@ -483,11 +480,7 @@ def conv_wgrad_tc_supported(x, gy, k):
   if not ((cin in (128, 256) and cout % 64 == 0 and 64 <= cout <= 256) or
           (cout in (128, 256) and cin % 64 == 0 and 64 <= cin <= 256)):
     return False
-  if w > 64 or 64 % w:
-    return False
-  if h * w >= 64:
-    return h % (64 // w) == 0
-  return 64 % (h * w) == 0 and n % (64 // (h * w)) == 0
+  return w <= 256            # any image size: chunks of whole rows / images (or row pieces) of <= 64 pixels
 
 
 def conv_wgrad(x, gy, k):
@@ -569,9 +562,7 @@ def subpixel_supported(x, cin, cout):
   n, h, w, _ = x.shape
   if not ((cin in (128, 256) and 64 <= cout <= 256) or (cout in (128, 256) and cin % 64 == 0 and 64 <= cin <= 256)):
     return False
-  if w > 64 or 64 % w:
-    return False
-  return h % (64 // w) == 0 if h * w >= 64 else (64 % (h * w) == 0 and n % (64 // (h * w)) == 0)
+  return w <= 128            # any map size: partially filled tiles / chunks (csrc/conv_tc.cu)
 
 
 class SubpixelConv(torch.autograd.Function):

@@ -29,6 +29,10 @@ SHAPES = [  # n, h, w, cin, cout, k  -- the dreamerv3 size200m layers (rssm.py:2
     (2, 16, 16, 256, 192, 5), (2, 32, 32, 192, 128, 5),
     (2, 8, 8, 64, 32, 5), (3, 32, 32, 64, 64, 3), (8, 4, 4, 64, 96, 5), (8, 4, 8, 128, 64, 1),
     (150, 16, 16, 64, 64, 5),       # more tiles than SMs: every CTA loops, both accumulator buffers reused
+    # widths that do not divide 128 (the reference's Atari config is 96x96, dreamerv3/configs.yaml:30):
+    # partially filled tiles of whole rows / whole images -- 96, 96, 96, 72, 72 (3 x 5: 15 pixels x 8 images = 120) pixels
+    (3, 96, 96, 64, 128, 5), (2, 48, 48, 128, 192, 5), (4, 24, 24, 192, 256, 5), (6, 12, 12, 256, 256, 5),
+    (10, 6, 6, 256, 64, 3), (16, 3, 5, 64, 32, 5), (5, 7, 9, 64, 64, 3), (1, 2, 100, 64, 96, 5),
 ]
 
 
@@ -72,6 +76,24 @@ def test_bias_and_data_gradient_packing():
   assert float((gx.float() - xf.grad).abs().max()) <= 2.0 ** -7 * float(xf.grad.abs().max())
 
 
+@pytest.mark.parametrize('n,h,w,cin,cout,k', [(2, 48, 48, 128, 192, 5), (3, 12, 12, 256, 128, 3), (4, 6, 6, 64, 64, 5)])
+def test_autograd_function_on_partial_tiles(n, h, w, cin, cout, k):
+  """ConvTC on a width that does not divide 128: forward and input gradient from the tcgen05 kernel
+  (partially filled tiles), weight gradient from whichever path takes the shape."""
+  g = torch.Generator(device='cuda').manual_seed(7)
+  x = torch.randn((n, h, w, cin), generator=g, device='cuda').to(torch.bfloat16).requires_grad_(True)
+  wt = (torch.randn((k, k, cin, cout), generator=g, device='cuda') / (k * cin ** 0.5)).requires_grad_(True)
+  gy = torch.randn((n, h, w, cout), generator=g, device='cuda').to(torch.bfloat16)
+  y = ops.ConvTC.apply(x, wt.to(torch.bfloat16))
+  (y.float() * gy.float()).sum().backward()
+  xf = x.detach().float().requires_grad_(True)
+  wf = wt.detach().to(torch.bfloat16).float().requires_grad_(True)
+  (reference(xf, wf) * gy.float()).sum().backward()
+  assert float((y.float() - reference(xf, wf)).abs().max()) <= 2.0 ** -7 * float(reference(xf, wf).abs().max())
+  assert float((x.grad.float() - xf.grad).abs().max()) <= 2.0 ** -6 * float(xf.grad.abs().max())
+  assert float((wt.grad - wf.grad).abs().max()) <= 2.0 ** -6 * float(wf.grad.abs().max())
+
+
 def test_rejects_unsupported_shapes():
   x = torch.zeros((2, 8, 8, 48), dtype=torch.bfloat16, device='cuda')
   assert not ops.conv_tc_supported(x, 48, 64)
@@ -106,6 +128,10 @@ def test_autograd_function_matches_library_convolution():
 WSHAPES = [  # n, h, w, cin, cout, k
     (8, 32, 32, 128, 192, 5), (8, 16, 16, 192, 256, 5), (8, 8, 8, 256, 256, 5),
     (8, 16, 16, 256, 192, 5), (8, 32, 32, 192, 128, 5), (4, 16, 16, 128, 64, 3), (300, 8, 8, 128, 128, 5),
+    # image sizes whose rows do not pack into 64-pixel chunks (96 x 96 and its down-sampled maps, odd sizes):
+    # partially filled chunks on a zero-initialised ring, row pieces where a row is wider than 64 pixels
+    (3, 96, 96, 128, 64, 5), (2, 48, 48, 128, 192, 5), (4, 24, 24, 192, 256, 5), (6, 12, 12, 256, 256, 5),
+    (10, 6, 6, 256, 128, 3), (9, 3, 5, 128, 64, 5), (5, 7, 9, 64, 128, 3), (2, 4, 100, 128, 128, 5),
 ]
 
 
@@ -131,7 +157,8 @@ def test_weight_gradient_matches_fp32(n, h, w, cin, cout, k):
   assert err <= 1e-4 * float(wt.grad.abs().max()), err
 
 
-@pytest.mark.parametrize('n,h,w,cin,cout', [(8, 4, 4, 256, 256), (4, 8, 8, 256, 192), (4, 16, 16, 192, 128)])
+@pytest.mark.parametrize('n,h,w,cin,cout', [(8, 4, 4, 256, 256), (4, 8, 8, 256, 192), (4, 16, 16, 192, 128),
+                                            (3, 6, 6, 256, 256), (2, 12, 12, 256, 192), (2, 24, 24, 192, 128), (3, 5, 7, 128, 64)])
 def test_subpixel_upconv_matches_upsample_then_conv(n, h, w, cin, cout):
   """ops.upconv_subpixel (four 3x3 phase convolutions on the low-resolution grid) against
   nearest x2 up-sampling + 5x5 SAME convolution in fp32 on the same bf16 operands: output, input
