@@ -42,6 +42,7 @@ EXPORTS = (
     'emb_device_sm_count', 'emb_rows_copy', 'emb_replay_gather',
     'emb_replay_append_rows', 'emb_replay_scatter_update',
     'emb_driver_stage_obs', 'emb_driver_scatter_mask_actions',
+    'emb_replay_export_chunk', 'emb_replay_import_chunk',
     # learner (bound where they are used: dreamerv3/scan.py, ops.py, optim.py)
     'emb_rssm_observe_fwd', 'emb_rssm_observe_bwd', 'emb_rssm_tma_fits', 'emb_rssm_legacy_fits', 'emb_rmsnorm_act_fwd',
     'emb_rmsnorm_act_bwd', 'emb_rssm_kl_fwd', 'emb_rssm_kl_bwd', 'emb_lambda_return', 'emb_onehot_sample', 'emb_opt_agc_rms_momentum', 'emb_opt_agc_rms_momentum_cast', 'emb_allreduce_bucket_update', 'emb_maxpool2_nhwc_fwd',
@@ -76,7 +77,9 @@ def load():
     for name in ('emb_replay_append_rows', 'emb_replay_scatter_update',
                  'emb_driver_stage_obs', 'emb_driver_scatter_mask_actions'):
       getattr(lib, name).argtypes = [kp, ctypes.c_int, vp, i64, vp]
-    for name in EXPORTS[5:11]:
+    for name in ('emb_replay_export_chunk', 'emb_replay_import_chunk'):
+      getattr(lib, name).argtypes = [kp, ctypes.c_int, i64, i64, vp]
+    for name in EXPORTS[5:13]:
       getattr(lib, name).restype = ctypes.c_int
     lib.emb_event_create.argtypes = [ctypes.POINTER(vp)]
     lib.emb_event_record.argtypes = [vp, vp]

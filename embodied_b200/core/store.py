@@ -393,23 +393,50 @@ class DeviceStore:
 
   # --------------------------------------------------------------- chunk I/O
   def export_slab(self, slab, length):
-    """Rows [0, length) of a slab as host numpy arrays (chunk save)."""
+    """Rows [0, length) of a slab as host numpy arrays (chunk save): emb_replay_export_chunk,
+    one strided device-to-pinned-host copy per key, one stream synchronise."""
     lo = slab * self.chunksize
+    stream = torch.cuda.current_stream(self.device)
+    hosts, keys = {}, []
+    for spec in self.specs.values():
+      if spec.row_bytes == 0 or length == 0:
+        continue
+      hosts[spec.name] = torch.empty((length, spec.row_bytes), dtype=torch.uint8, pin_memory=True)
+      keys.append(_lib.Key(src=self.tables[spec.name].data_ptr(), dst=hosts[spec.name].data_ptr(),
+                           src_stride=self.tables[spec.name].stride(0), dst_stride=spec.row_bytes,
+                           row_bytes=spec.row_bytes))
+    if keys:
+      _lib.check(self.lib.emb_replay_export_chunk(
+          _lib.keys_array(keys), len(keys), lo, length, stream.cuda_stream))
+      stream.synchronize()
     out = {}
     for spec in self.specs.values():
-      raw = self.tables[spec.name][lo: lo + length].cpu().numpy()
-      out[spec.name] = raw.reshape(-1).view(spec.dtype).reshape(
-          (length, *spec.shape)) if spec.row_bytes else np.empty(
-              (length, *spec.shape), spec.dtype)
+      if spec.name in hosts:
+        out[spec.name] = hosts[spec.name].numpy().reshape(-1).view(spec.dtype).reshape(
+            (length, *spec.shape)).copy()
+      else:
+        out[spec.name] = np.empty((length, *spec.shape), spec.dtype)
     return out
 
   def import_slab(self, slab, data):
-    """Host arrays {key: (length, *shape)} -> rows [0, length) of a slab."""
+    """Host arrays {key: (length, *shape)} -> rows [0, length) of a slab (chunk load):
+    emb_replay_import_chunk, one strided copy per key."""
     lo = slab * self.chunksize
+    stream = torch.cuda.current_stream(self.device)
+    keys, keep, n = [], [], 0
     for spec in self.specs.values():
       arr = np.ascontiguousarray(data[spec.name], spec.dtype)
       n = len(arr)
+      if n > self.chunksize:
+        raise ValueError(f'{n} rows do not fit a slab of {self.chunksize}')
       if spec.row_bytes == 0 or n == 0:
         continue
       raw = torch.from_numpy(arr.reshape(n, -1).view(np.uint8))
-      self.tables[spec.name][lo: lo + n].copy_(raw)
+      keep.append(raw)
+      keys.append(_lib.Key(src=raw.data_ptr(), dst=self.tables[spec.name].data_ptr(),
+                           src_stride=spec.row_bytes, dst_stride=self.tables[spec.name].stride(0),
+                           row_bytes=spec.row_bytes))
+    if keys:
+      _lib.check(self.lib.emb_replay_import_chunk(
+          _lib.keys_array(keys), len(keys), lo, n, stream.cuda_stream))
+      stream.synchronize()          # pageable sources: the arrays may go away after this call

@@ -625,3 +625,36 @@ int emb_driver_scatter_mask_actions(const emb_key_t* keys, int nkeys,
 }
 
 }  // extern "C"
+
+// Chunk.save / load: a slab's rows are consecutive rows of every table (embodied/core/chunk.py:64-99)
+static int chunk_copy(const emb_key_t* keys, int nkeys, int64_t row0, int64_t nrows, void* stream,
+                      bool to_table, const char* who) {
+  if (nkeys < 0 || nkeys > EMB_MAX_KEYS)
+    return emb::fail(-1, "%s: nkeys=%d outside [0,%d]", who, nkeys, EMB_MAX_KEYS);
+  if (row0 < 0 || nrows < 0) return emb::fail(-1, "%s: row0=%lld nrows=%lld", who, (long long)row0, (long long)nrows);
+  if (nrows == 0 || nkeys == 0) return 0;
+  if (!keys) return emb::fail(-1, "%s: keys is NULL", who);
+  for (int i = 0; i < nkeys; ++i) {
+    const emb_key_t& k = keys[i];
+    if (k.row_bytes == 0) continue;
+    if (!k.src || !k.dst) return emb::fail(-2, "%s: key %d needs src and dst", who, i);
+    const size_t sp = k.src_stride ? k.src_stride : k.row_bytes, dp = k.dst_stride ? k.dst_stride : k.row_bytes;
+    if (sp < k.row_bytes || dp < k.row_bytes) return emb::fail(-2, "%s: key %d has a pitch below its row size", who, i);
+    const unsigned char* src = (const unsigned char*)k.src + (to_table ? 0 : (size_t)row0 * sp);
+    unsigned char* dst = (unsigned char*)k.dst + (to_table ? (size_t)row0 * dp : 0);
+    if (cudaMemcpy2DAsync(dst, dp, src, sp, k.row_bytes, (size_t)nrows, cudaMemcpyDefault,
+                          (cudaStream_t)stream) != cudaSuccess)
+      return emb::fail_cuda(who);
+  }
+  return 0;
+}
+
+extern "C" int emb_replay_export_chunk(const emb_key_t* keys, int nkeys, int64_t row0, int64_t nrows,
+                                       void* stream) {
+  return chunk_copy(keys, nkeys, row0, nrows, stream, false, "emb_replay_export_chunk");
+}
+
+extern "C" int emb_replay_import_chunk(const emb_key_t* keys, int nkeys, int64_t row0, int64_t nrows,
+                                       void* stream) {
+  return chunk_copy(keys, nkeys, row0, nrows, stream, true, "emb_replay_import_chunk");
+}

@@ -136,6 +136,19 @@ int emb_driver_scatter_mask_actions(const emb_key_t* keys, int nkeys,
                                     const int64_t* dst_rows, int64_t nrows,
                                     void* stream);
 
+/* Chunk.save / Chunk.load (embodied/core/chunk.py:64-99, driven by Replay.save / load,
+ * replay.py:295-388): rows [row0, row0 + nrows) of every key's table <-> dense caller buffers
+ * [nrows][row_bytes], one strided copy per key on `stream` (a slab's rows are consecutive table
+ * rows, so no row list and no kernel are needed).
+ *   export: keys[i].src = table base (src_stride = its row pitch), keys[i].dst = the buffer;
+ *   import: keys[i].src = the buffer, keys[i].dst = table base (dst_stride = its row pitch).
+ * The buffer may be device memory or (pinned) host memory; only row_bytes, src, dst and the two
+ * strides of a key are read (a stride of 0 means row_bytes). */
+int emb_replay_export_chunk(const emb_key_t* keys, int nkeys, int64_t row0, int64_t nrows,
+                            void* stream);
+int emb_replay_import_chunk(const emb_key_t* keys, int nkeys, int64_t row0, int64_t nrows,
+                            void* stream);
+
 
 /* ------------------------------------------------------------------ learner:
  * the fused RSSM scan (dreamerv3/rssm.py:61-92 `_observe`, :135-159 `_core`).

@@ -50,6 +50,11 @@ def test_argument_validation_needs_no_device(lib):
   assert lib.emb_replay_gather(keys, 1, 8, 5, 2, None) == -1   # 5 % 2
   assert lib.emb_rows_copy(keys, 99, None, None, 1, 0, None) == -1
   assert lib.emb_rows_copy(keys, 1, None, None, 0, 0, None) == 0   # empty: no-op
+  # chunk export / import: argument checks before any copy is issued
+  assert lib.emb_replay_export_chunk(keys, 1, -1, 4, None) == -1
+  assert lib.emb_replay_export_chunk(keys, 1, 0, 4, None) == -2      # key without src / dst
+  assert b'src and dst' in lib.emb_last_error()
+  assert lib.emb_replay_import_chunk(keys, 1, 0, 0, None) == 0       # empty: no-op
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
