@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/embodied_b200.h"
 #include "common.cuh"
@@ -505,6 +506,139 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_con
   }
 }
 
+// ---- weight gradient, two taps per CTA (M side of 128 channels) ----------------------
+// With M = 128 a tap's D tile is 128 x N: every operand byte fetched from L2 feeds only 128 or N
+// multiply-adds, and the 32 x 32 layers (1 M pixels) run into the L2 -> shared-memory rate.  A CTA
+// that owns TWO taps keeps two accumulators (2 x 256 TMEM columns) and fetches the UNSHIFTED
+// operand (gy) once for both: 7-8 slabs per chunk instead of 10 for the same multiply-adds.
+// Stage = [shared slabs | tap 0 slabs | tap 1 slabs]; the last group of an odd tap count has one tap.
+template <int SLABS>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_pair_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_n,
+                       float* __restrict__ dw, const WgradShape s) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int kWStages = kWRingSlabs / SLABS;
+  constexpr int kWStageBytes = SLABS * kWSlab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWRingSlabs * kWSlab);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWStages;
+  uint64_t* done = bars + 2 * kWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_m) : "memory");
+    asm volatile("prefetch.tensormap [%0];" :: "l"(&map_n) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                 :: "r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (s.cpix < 64) {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    for (int i = threadIdx.x; i < kWRingSlabs * kWSlab / 16; i += kThreads) z[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = s.ksize * s.ksize, half = s.ksize >> 1;
+  const int ngroups = (taps + 1) >> 1;
+  const int group = blockIdx.x % ngroups, split = blockIdx.x / ngroups;
+  const int tap0 = group * 2, ng = taps - tap0 >= 2 ? 2 : 1;
+  const int c_begin = (int)((long long)s.chunks * split / s.splits);
+  const int c_end = (int)((long long)s.chunks * (split + 1) / s.splits);
+  const int mslabs = s.m / 64, nslabs = s.n / 64;            // m == 128: mslabs == 2
+  // the shifted tensor (the convolution input) is fetched per tap, the other one (gy) once
+  const int shared_slabs = s.m_shifted ? nslabs : mslabs, tap_slabs = s.m_shifted ? mslabs : nslabs;
+  const uint32_t stage_tx = (uint32_t)(shared_slabs + ng * tap_slabs) * (uint32_t)s.cpix * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const long long p0 = (long long)c_begin * s.cpix;
+      int n0 = (int)(p0 / s.hw), h0 = (int)((p0 - (long long)n0 * s.hw) / s.w);
+      const CUtensorMap* map_sh = s.m_shifted ? &map_n : &map_m;      // unshifted: gy
+      const CUtensorMap* map_tp = s.m_shifted ? &map_m : &map_n;      // shifted: x
+      int dh[2], dx[2];
+      for (int g = 0; g < 2; ++g) {
+        const int tap = tap0 + (g < ng ? g : 0);
+        const int ky = tap / s.ksize;
+        dh[g] = ky - half;
+        dx[g] = tap - ky * s.ksize - half;
+      }
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_expect_tx(&full[stage], stage_tx);
+        unsigned char* base = smem + stage * kWStageBytes;
+        for (int j = 0; j < shared_slabs; ++j)
+          tma_load_5d(base + j * kWSlab, map_sh, s.gy_ch + j * 64, 0, s.gy_py, h0, n0, &full[stage]);
+        for (int g = 0; g < ng; ++g)
+          for (int j = 0; j < tap_slabs; ++j)
+            tma_load_5d(base + (shared_slabs + g * tap_slabs + j) * kWSlab, map_tp, j * 64, dx[g], 0, h0 + dh[g], n0,
+                        &full[stage]);
+        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+        h0 += s.ht;
+        if (h0 >= s.h) { h0 = 0; n0 += s.nt; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, s.n) | (1u << 15) | (1u << 16);   // both MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int c = c_begin; c < c_end; ++c) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem + stage * kWStageBytes);
+        for (int g = 0; g < ng; ++g) {
+          const uint32_t tp = base + (uint32_t)(shared_slabs + g * tap_slabs) * kWSlab;
+          const uint32_t a0 = s.m_shifted ? tp : base, b0 = s.m_shifted ? base : tp;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + (uint32_t)g * 256u, umma_desc_mn_sw128(a0 + k * 2048, kWSlab),
+                      umma_desc_mn_sw128(b0 + k * 2048, kWSlab), idesc, (c > c_begin || k) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == kWStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(done);
+    }
+  } else if (c_begin < c_end) {
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    for (int g = 0; g < ng; ++g) {
+      float* drow = dw + ((size_t)(tap0 + g) * s.m + m) * s.n;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
+      for (int c0 = 0; c0 < s.n; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red_add_v4(drow + c0 + 4 * j, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                 :: "r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
 // ---- host side ----------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
@@ -708,6 +842,34 @@ extern "C" int emb_conv_wgrad_tc(const emb_conv_wgrad_tc_args* a, void* stream) 
   s.gy_ch = a->gy_up == 2 ? (a->gy_phase & 1) * cout : 0;
   const size_t smem = (size_t)kWRingSlabs * kWSlab + 1024 + 256;
   const void* fn = nullptr;
+  // two taps per CTA where the M side has 128 channels and a stage of both taps stays within 8
+  // slabs (three ring stages); whole-row chunks only; EMB_WGRAD_PAIR=0 keeps one tap per CTA
+  static int pair_on = -1;
+  if (pair_on < 0) {
+    const char* e = getenv("EMB_WGRAD_PAIR");
+    pair_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  const int pair_slabs = s.m_shifted ? nn / 64 + 2 * (m / 64) : m / 64 + 2 * (nn / 64);
+  if (pair_on && m == 128 && taps > 1 && bw == w && pair_slabs <= 8) {
+    const int ngroups = (taps + 1) / 2;
+    s.splits = g_sms / ngroups > 0 ? g_sms / ngroups : 1;
+    if (s.splits > s.chunks) s.splits = s.chunks;
+    switch (pair_slabs) {
+      case 5: fn = (const void*)conv_wgrad_pair_kernel<5>; break;
+      case 6: fn = (const void*)conv_wgrad_pair_kernel<6>; break;
+      case 7: fn = (const void*)conv_wgrad_pair_kernel<7>; break;
+      default: fn = (const void*)conv_wgrad_pair_kernel<8>; break;
+    }
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return emb::fail_cuda(who);
+    float* dwp = a->dw;
+    void* pargs[] = {maps[0], maps[1], &dwp, &s};
+    if (cudaLaunchKernel(fn, dim3(ngroups * s.splits), dim3(kThreads), pargs, smem, (cudaStream_t)stream) !=
+        cudaSuccess)
+      return emb::fail_cuda(who);
+    emb::count_launch();
+    return 0;
+  }
   switch ((m + nn) / 64) {
     case 3: fn = (const void*)conv_wgrad_tc_kernel<3>; break;
     case 4: fn = (const void*)conv_wgrad_tc_kernel<4>; break;
