@@ -801,7 +801,10 @@ extern "C" int emb_conv_wgrad_tc(const emb_conv_wgrad_tc_args* a, void* stream) 
   if (ksize != 5 && ksize != 3 && ksize != 1) return emb::fail(-1, "%s: kernel size %d not in {1, 3, 5}", who, ksize);
   const int m = a->m_is_in ? cin : cout, nn = a->m_is_in ? cout : cin;
   if (m != 128 && m != 256) return emb::fail(-1, "%s: the M side has %d channels, need 128 or 256", who, m);
-  if (nn % 64 || nn < 64 || nn > 256) return emb::fail(-1, "%s: the N side has %d channels, need a multiple of 64 <= 256", who, nn);
+  // the N side may have any multiple of 8 channels (16-byte rows for TMA): its last 64-channel slab is
+  // then partly out of bounds, which TMA fills with zeros, and dw has n_pad = 64 * ceil(n / 64) columns
+  if (nn % 8 || nn < 8 || nn > 256) return emb::fail(-1, "%s: the N side has %d channels, need a multiple of 8 <= 256", who, nn);
+  const int n_pad = (nn + 63) / 64 * 64;
   if ((a->gy_up != 1 && a->gy_up != 2) || a->gy_phase < 0 || a->gy_phase > 3)
     return emb::fail(-1, "%s: gy_up must be 1 or 2, gy_phase in [0, 4)", who);
   // chunk = box (bw, ht, nt) of at most 64 pixels: whole rows / whole images where a row fits,
@@ -832,7 +835,7 @@ extern "C" int emb_conv_wgrad_tc(const emb_conv_wgrad_tc_args* a, void* stream) 
   s.hw = h * w;
   s.w = w;
   s.m = m;
-  s.n = nn;
+  s.n = n_pad;
   s.ksize = ksize;
   s.m_shifted = a->m_is_in ? 1 : 0;
   s.h = h;
@@ -849,7 +852,7 @@ extern "C" int emb_conv_wgrad_tc(const emb_conv_wgrad_tc_args* a, void* stream) 
     const char* e = getenv("EMB_WGRAD_PAIR");
     pair_on = (e && e[0] == '0') ? 0 : 1;
   }
-  const int pair_slabs = s.m_shifted ? nn / 64 + 2 * (m / 64) : m / 64 + 2 * (nn / 64);
+  const int pair_slabs = s.m_shifted ? n_pad / 64 + 2 * (m / 64) : m / 64 + 2 * (n_pad / 64);
   if (pair_on && m == 128 && taps > 1 && bw == w && pair_slabs <= 8) {
     const int ngroups = (taps + 1) / 2;
     s.splits = g_sms / ngroups > 0 ? g_sms / ngroups : 1;
@@ -870,7 +873,7 @@ extern "C" int emb_conv_wgrad_tc(const emb_conv_wgrad_tc_args* a, void* stream) 
     emb::count_launch();
     return 0;
   }
-  switch ((m + nn) / 64) {
+  switch ((m + n_pad) / 64) {
     case 3: fn = (const void*)conv_wgrad_tc_kernel<3>; break;
     case 4: fn = (const void*)conv_wgrad_tc_kernel<4>; break;
     case 5: fn = (const void*)conv_wgrad_tc_kernel<5>; break;

@@ -193,7 +193,10 @@ class Model:
     n, h, ww, _ = x.shape
     kp = ops.patch_columns(k, cin)
     w2 = F.pad(w.reshape(k * k * cin, cout), (0, 0, 0, kp - k * k * cin))
-    return (ops.ConvPatches.apply(x, k) @ w2).reshape(n, h, ww, cout)
+    patches = ops.ConvPatches.apply(x, k)
+    if self._use(self.tc_conv, 'thin_matmul', ops.thin_matmul_supported(patches, w2)):
+      return ops.ThinMatmul.apply(patches, w2).reshape(n, h, ww, cout)
+    return (patches @ w2).reshape(n, h, ww, cout)
 
   def conv_thin_out(self, x, name, up=1):
     """SAME conv with <= 4 output channels (the decoder's image head), optionally
@@ -204,7 +207,11 @@ class Model:
     n, h, ww, _ = x.shape
     kp = ops.patch_columns(k, cout)
     w2 = F.pad(w.permute(2, 0, 1, 3).reshape(cin, k * k * cout), (0, kp - k * k * cout))
-    z = x.reshape(n * h * ww, cin) @ w2
+    x2 = x.reshape(n * h * ww, cin)
+    if self._use(self.tc_conv, 'thin_matmul', ops.thin_matmul_supported(x2, w2)):
+      z = ops.ThinMatmul.apply(x2, w2)
+    else:
+      z = x2 @ w2
     return ops.ConvTapSum.apply(z, self.store.w[f'{name}/bias'], (n, h * up, ww * up, cout), k, up)
 
   def mlp(self, x, name, layers, params=None):               # nets.py:580-587

@@ -1,6 +1,7 @@
 """torch.autograd wrappers of the element-wise / reduction kernels in
 libembodied_b200.so (include/embodied_b200.h)."""
 import ctypes
+import os
 
 import torch
 
@@ -282,6 +283,52 @@ class ConvPatches(torch.autograd.Function):
   @staticmethod
   def backward(ctx, g):
     return None, None
+
+
+def thin_matmul_supported(a, w):
+  """a (P, K) @ w (K, N) bf16 with one side of 128 / 256 columns and the other a multiple of 8:
+  the weight gradient is emb_conv_wgrad_tc with ksize = 1 over P / 64 chunks of 64 rows."""
+  if not (a.is_cuda and a.dtype == w.dtype == torch.bfloat16 and a.dim() == 2 and a.is_contiguous()):
+    return False
+  if os.environ.get('EMB_THIN_MATMUL', '1') == '0':          # A/B switch (profiles/)
+    return False
+  P, K = a.shape
+  N = w.shape[1]
+  return P % 64 == 0 and ((K in (128, 256) and N % 8 == 0 and N <= 256) or
+                          (N in (128, 256) and K % 8 == 0 and K <= 256))
+
+
+class ThinMatmul(torch.autograd.Function):
+  """y = a @ w for the two thin convolutions (a = rows of image patches, or w = the tap matrix of
+  the image head): millions of pixel rows times a small matrix.  The forward product is a library
+  GEMM; the WEIGHT gradient a^T @ gy -- a reduction over all pixels into an (80 x 128)-sized
+  result, HBM-bound -- streams both operands once through the tcgen05 weight-gradient kernel
+  (ksize = 1) instead of a split-K library GEMM."""
+
+  @staticmethod
+  def forward(ctx, a, w):
+    ctx.save_for_backward(a, w)
+    return a @ w
+
+  @staticmethod
+  def backward(ctx, gy):
+    a, w = ctx.saved_tensors
+    ga = gw = None
+    if ctx.needs_input_grad[0]:
+      ga = gy @ w.t()
+    if ctx.needs_input_grad[1]:
+      P, K = a.shape
+      N = w.shape[1]
+      gy = gy.contiguous()
+      m_is_in = K in (128, 256)
+      m, n = (K, N) if m_is_in else (N, K)
+      n_pad = (n + 63) // 64 * 64
+      dw = torch.zeros((1, m, n_pad), dtype=f32, device=a.device)
+      _conv_general(x=a.data_ptr(), gy=gy.data_ptr(), dw=dw.data_ptr(), n=P // 64, h=1, w=64, cin=K,
+                    cout=N, ksize=1, m_is_in=int(m_is_in), gy_up=1, gy_phase=0)
+      gw = dw[0, :, :n] if m_is_in else dw[0, :, :n].t()
+      gw = gw.to(w.dtype)
+    return ga, gw
 
 
 class ConvTapSum(torch.autograd.Function):

@@ -515,8 +515,10 @@ int emb_conv_nhwc_tc(const emb_conv_tc_args* args, void* stream);
  * gradient).  The reduction axis is the pixel axis, so both NHWC tensors feed the tcgen05 MMAs
  * as MN-major operands straight from their TMA tiles.  m_is_in = 1: m = cin, n = cout (dw is the
  * HWIO gradient); 0: m = cout, n = cin (dw = its transpose per tap).  The M side must have 128 or
- * 256 channels, the N side a multiple of 64 <= 256; 64 % w == 0 and images tile into 64-pixel runs
- * of whole rows. */
+ * 256 channels; the N side any multiple of 8 <= 256 -- dw then has n_pad = 64 * ceil(n / 64) columns
+ * (columns >= n stay zero: the out-of-bounds channels of its last slab are TMA zero fill).  Any image
+ * size: the pixels are walked in chunks of whole rows / images (or pieces of a row) of <= 64 pixels.
+ * ksize = 1 is the weight gradient of a plain matrix product over pixel rows. */
 int emb_conv5x5_wgrad_tc(const void* x, const void* gy, float* dw, int64_t n, int32_t h, int32_t w,
                          int32_t cin, int32_t cout, int32_t ksize, int32_t m_is_in, void* stream);
 

@@ -181,3 +181,24 @@ def test_subpixel_upconv_matches_upsample_then_conv(n, h, w, cin, cout):
   assert rel2(y, yr) < 6e-3, rel2(y, yr)
   assert rel2(x.grad, xr.grad) < 6e-3, rel2(x.grad, xr.grad)
   assert rel2(wt.grad, wr.grad) < 6e-3, rel2(wt.grad, wr.grad)
+
+
+@pytest.mark.parametrize('P,K,N', [(64 * 200, 80, 128), (64 * 150, 128, 80), (64 * 3, 256, 8), (64 * 40, 24, 256)])
+def test_thin_matmul_weight_gradient(P, K, N):
+  """ops.ThinMatmul: y = a @ w with millions of pixel rows and a small matrix; the weight gradient
+  a^T @ gy comes from the tcgen05 weight-gradient kernel with ksize = 1 (the N side padded to 64
+  channels by TMA zero fill)."""
+  g = torch.Generator(device='cuda').manual_seed(P + K + N)
+  a = torch.randn((P, K), generator=g, device='cuda').to(torch.bfloat16).requires_grad_(K in (128, 256))
+  w = (torch.randn((K, N), generator=g, device='cuda') / K ** 0.5).to(torch.bfloat16).requires_grad_(True)
+  gy = torch.randn((P, N), generator=g, device='cuda').to(torch.bfloat16)
+  assert ops.thin_matmul_supported(a, w)
+  y = ops.ThinMatmul.apply(a, w)
+  (y.float() * gy.float()).sum().backward()
+  want_w = a.detach().double().t() @ gy.double()
+  err = float((w.grad.double() - want_w).abs().max())
+  assert err <= 2.0 ** -7 * float(want_w.abs().max()), err          # the result is rounded to bf16 once
+  assert float((y.float() - a.detach().float() @ w.detach().float()).abs().max()) <= 2.0 ** -6 * float(y.float().abs().max())
+  if a.requires_grad:
+    want_a = gy.float() @ w.detach().float().t()
+    assert float((a.grad.float() - want_a).abs().max()) <= 2.0 ** -6 * float(want_a.abs().max())
