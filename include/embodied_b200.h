@@ -481,10 +481,11 @@ int emb_loss_reduce(const float* const* terms, const int64_t* counts, const floa
  * with zeros outside the image.  w_packed: [k*k][cout][cin] bf16 (the HWIO kernel with its last
  * two axes swapped); packing the spatially flipped kernel with channels exchanged
  * ([24-tap][cin][cout]) makes the same launch the convolution's DATA GRADIENT.
- * Constraints: k in {1, 3, 5}; cin % 64 == 0; cout % 32 == 0, 32 <= cout <= 256; 128 % w == 0 and
- * the images tile into 128-pixel runs of whole rows (h*w >= 128: h % (128/w) == 0; smaller
- * images: 128 % (h*w) == 0 and n % (128/(h*w)) == 0); 16-byte aligned pointers.  bias (fp32
- * [cout]) may be NULL. */
+ * Constraints: k in {1, 3, 5}; cin % 64 == 0; cout % 32 == 0, 32 <= cout <= 256; w <= 128;
+ * 16-byte aligned pointers.  Any image size: an output tile is the largest run of whole rows (a
+ * row count dividing h) or whole images (a count dividing n) of at most 128 pixels -- 128 where w
+ * divides 128 and the rows pack, e.g. 96 pixels for 96-, 48- and 24-wide maps.  bias (fp32 [cout])
+ * may be NULL. */
 int emb_conv5x5_nhwc_tc(const void* in, const void* w_packed, const float* bias, void* out,
                         int64_t n, int32_t h, int32_t w, int32_t cin, int32_t cout, int32_t ksize,
                         void* stream);
